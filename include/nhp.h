@@ -1,0 +1,161 @@
+/*
+ * nhp.h -- C ABI of libnhp, the B200 (sm_100a) implementation of the event-history hot path
+ * of NetworkHawkesProcesses.jl.  This is the drop-in boundary: the Julia package keeps its
+ * API and forwards the methods cited below to these entry points with `ccall`
+ * (INTEGRATION.md shows the stubs).  Plain pointers and sizes only; no torch / CUDA types.
+ *
+ * Conventions (identical to the Julia arrays so no reshaping happens at the boundary):
+ *   - Float64 everywhere; matrices column-major, X[parent + K*child] (0-based offsets);
+ *   - nodes are 1-based Int64; parent indices are 1-based Int64 with 0 = baseline;
+ *   - every pointer argument is a HOST pointer unless its name ends in `_dev`; the library
+ *     copies in/out and never keeps a host pointer past the call;
+ *   - every function returns NHP_OK (0) or a negative nhp_status; nhp_last_error() gives the
+ *     message.  There is NO CPU fallback: without a usable sm_100 GPU nhp_create fails.
+ *   - calls on one context are synchronous (stream-synchronised before return) and must not
+ *     be issued concurrently from several threads; use one context per host thread.
+ *
+ * Reference citations are file:line under /root/reference/src/.
+ */
+#ifndef NHP_H
+#define NHP_H
+#include <stdint.h>
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef enum {
+    NHP_OK = 0,
+    NHP_ERR_INVALID = -1,     /* bad argument (the reference would throw error()/DomainError) */
+    NHP_ERR_CUDA = -2,        /* CUDA runtime failure */
+    NHP_ERR_NO_DEVICE = -3,   /* no sm_100 device: the library has no CPU path */
+    NHP_ERR_STATE = -4,       /* call sequence error (e.g. parameters not set) */
+    NHP_ERR_NUMERIC = -5,     /* NaN / negative intensities where the reference's Categorical/Poisson would throw */
+    NHP_ERR_UNSUPPORTED = -6
+} nhp_status;
+
+#define NHP_EXPONENTIAL 0 /* ExponentialImpulseResponse  impulses.jl:30-37  */
+#define NHP_LOGITNORMAL 1 /* LogitNormalImpulseResponse  impulses.jl:138-148 */
+
+typedef struct nhp_ctx nhp_ctx;       /* one device + one stream + parameter/statistic buffers */
+typedef struct nhp_events nhp_events; /* device-resident continuous data (times, nodes, duration) */
+typedef struct nhp_disc nhp_disc;     /* device-resident discrete data (N x T counts) + convolution */
+
+/* ---- context ------------------------------------------------------------------------- */
+int nhp_create(int device, nhp_ctx **out);
+int nhp_destroy(nhp_ctx *ctx);
+const char *nhp_last_error(const nhp_ctx *ctx); /* ctx may be NULL: last error of a failed nhp_create */
+int nhp_version(void);
+/* kernels launched by this context since creation (bench.py's gpu_launches claim) */
+int64_t nhp_launch_count(const nhp_ctx *ctx);
+/* device-time (CUDA events on the context stream) of the kernels of the most recent call, ms */
+double nhp_last_kernel_ms(const nhp_ctx *ctx);
+
+/* ---- continuous data: data = (events, nodes, duration) of continuous.jl:14 ------------- */
+/* Upload once; mle!/mcmc! call the likelihood thousands of times on the same data
+ * (continuous.jl:146-149, inference.jl:55-62).
+ * Time sharding (multi-GPU): a shard passes its own events preceded by `n_halo` read-only
+ * predecessor events (those within dtmax of its first event); `index_base` is the global
+ * 0-based index of the first passed event, so parent indices stay global.  `flags` bit 0:
+ * this shard adds the baseline integral term to the log-likelihood (set on exactly one
+ * shard; pass 1 when not sharding). */
+int nhp_events_upload(nhp_ctx *ctx, const double *times, const int64_t *nodes, int64_t n, double duration, int64_t K,
+                      int64_t n_halo, int64_t index_base, int flags, nhp_events **out);
+int nhp_events_free(nhp_ctx *ctx, nhp_events *ev);
+int64_t nhp_events_count(const nhp_events *ev);
+
+/* ---- continuous parameters --------------------------------------------------------------
+ * lambda0[K]  HomogeneousProcess.lambda (baselines.jl:27-39);  W[K*K] weights.W (weights.jl:47-55);
+ * A[K*K] adjacency_matrix or NULL for ContinuousStandardHawkesProcess (continuous.jl:108-112, 315-321);
+ * p1 = theta (Exponential) | mu (LogitNormal); p2 = tau (LogitNormal) | NULL; dtmax may be +Inf
+ * for Exponential (impulses.jl:37).  Length checks mirror impulses.jl:44-45,155-156, weights.jl:10-11. */
+int nhp_cont_params_set(nhp_ctx *ctx, int kind, int64_t K, const double *lambda0, const double *W, const double *A,
+                        const double *p1, const double *p2, double dtmax);
+
+/* Look-back horizon the sweeps use for the current parameters: dtmax for LogitNormal; for
+ * Exponential min(dtmax, H) where H is the cut-off beyond which the omitted tail of any event's
+ * history is < 1e-14 of the smallest baseline rate (every omitted term <= max(W theta)
+ * exp(-min(theta) H), fewer than n_total of them).  A time shard's halo must cover it. */
+int nhp_cont_horizon(nhp_ctx *ctx, int64_t n_total, int recursive, double *horizon);
+
+/* loglikelihood(process, data; recursive)  continuous.jl:210-239 / 360-389.  recursive != 0 with
+ * an Exponential impulse selects the full-history semantics of recursive_loglikelihood
+ * (continuous.jl:241-276 / 407-442, incl. quirks Q3/Q6/Q7 of SURVEY.md section 9).  For a shard
+ * the result is the shard's additive share (sum over ranks = ll). */
+int nhp_cont_loglik(nhp_ctx *ctx, nhp_events *ev, int recursive, double *ll);
+/* total_intensity at every (non-halo) event  continuous.jl:286-300 / 391-405; out[n - n_halo] */
+int nhp_cont_event_intensity(nhp_ctx *ctx, nhp_events *ev, double *out);
+/* intensity(process, data, times::Vector{Float64})  continuous.jl:76-96; out[nq*K], out[q + nq*k] */
+int nhp_cont_intensity(nhp_ctx *ctx, nhp_events *ev, const double *times, int64_t nq, double *out);
+
+/* resample_parents(process, data)  parents.jl:1-46, fused with the counters and impulse
+ * statistics of parents.jl:61-79, baselines.jl:87-96, impulses.jl:84-96,230-240 so parents need
+ * not leave the GPU.  Uniforms: u != NULL -> u[i] is the uniform of (non-halo) event i (parity
+ * tests); u == NULL -> Philox4x32-10 keyed by (seed; global event index, counter).
+ * parents / parentnodes may be NULL (kept on device for nhp_cont_suffstats). */
+int nhp_cont_resample_parents(nhp_ctx *ctx, nhp_events *ev, uint64_t seed, uint64_t counter, const double *u,
+                              int64_t *parents, int64_t *parentnodes);
+/* Import a parent assignment (1-based global indices, 0 = baseline) and rebuild the fused
+ * statistics from it: the "statistics given identical parent assignments" entry. */
+int nhp_cont_parents_set(nhp_ctx *ctx, nhp_events *ev, const int64_t *parents);
+/* Sufficient statistics of the current parent assignment; any output may be NULL.
+ *   M0[K]   baseline counts                node_counts(nodes,parentnodes,K)  baselines.jl:87-96
+ *   Mn[K]   events per node                node_counts(nodes,K)              parents.jl:61-68
+ *   Mnm[K*K] parent->child counts          parent_counts                     parents.jl:70-79
+ *   S1[K*K] Exponential: sum of durations (duration_mean*Mnm, impulses.jl:84-96);
+ *           LogitNormal: log_duration_sum  impulses.jl:230-240
+ *   S2[K*K] LogitNormal: log_duration_variation around S1/Mnm  impulses.jl:242-252 (two-pass); Exponential: zeros.
+ * Unsharded use only (sharded ranks go through the *_dev accessors below and allreduce). */
+int nhp_cont_suffstats(nhp_ctx *ctx, nhp_events *ev, double *M0, double *Mn, double *Mnm, double *S1, double *S2);
+
+/* resample_adjacency_matrix!(process, data)  continuous.jl:444-519: Gibbs over A[:,c], columns
+ * independent, p sequential.  rho[K*K] = link_probability(network) (networks.jl:65-68);
+ * u[K*K] uniforms (u[p + K*c]; Bernoulli draw is u <= p1) or NULL for Philox (seed, counter).
+ * A_inout is read (current state), updated, and also becomes the context's A. */
+int nhp_cont_resample_adjacency(nhp_ctx *ctx, nhp_events *ev, const double *rho, uint64_t seed, uint64_t counter,
+                                const double *u, double *A_inout);
+
+/* ---- multi-GPU plumbing (one process per GPU; the host allreduces with NCCL) -------------
+ * Device pointer + length (in doubles) of the contiguous reduction buffer
+ *   [ ll_logsum, ll_rowsum, M0[K], Mn[K], Mnm[K*K], S1[K*K] ]   (phase 0)
+ *   [ S2[K*K] ]                                                 (phase 1)
+ * Protocol: resample_parents -> allreduce(phase 0) -> nhp_cont_suffstats_second_pass ->
+ * allreduce(phase 1) -> nhp_cont_suffstats_read. */
+int nhp_cont_stats_dev(nhp_ctx *ctx, int phase, void **ptr_dev, int64_t *count);
+int nhp_cont_suffstats_second_pass(nhp_ctx *ctx, nhp_events *ev);
+int nhp_cont_suffstats_read(nhp_ctx *ctx, double *M0, double *Mn, double *Mnm, double *S1, double *S2);
+/* log-likelihood share left on the device in the phase-0 buffer slots 0..1 (no host sync) */
+int nhp_cont_loglik_dev(nhp_ctx *ctx, nhp_events *ev, int recursive);
+
+/* ---- discrete path -------------------------------------------------------------------- */
+/* data::Matrix{Int64} N x T, data[n + N*t]  (discrete.jl:18).  Sharding: `t_halo` leading bins are
+ * read-only history for the convolution. */
+int nhp_disc_upload(nhp_ctx *ctx, const int64_t *data, int64_t N, int64_t T, int64_t t_halo, nhp_disc **out);
+int nhp_disc_free(nhp_ctx *ctx, nhp_disc *dd);
+/* basis(impulse)  impulses.jl:321-335 -> phi[l + L*b] */
+int nhp_disc_basis(int64_t L, int64_t B, double dt, double *phi);
+/* convolve(process, data)  discrete.jl:146-151; result stays on the device; conv_out (T*N*B,
+ * conv[t + T*(n + N*b)]) may be NULL */
+int nhp_disc_convolve(nhp_ctx *ctx, nhp_disc *dd, const double *phi, int64_t L, int64_t B, double *conv_out);
+/* lambda0[N], W[N*N], A[N*N]|NULL, theta[N*N*B] (theta[p + N*(c + N*b)]), dt   discrete.jl:161-170, 395-402 */
+int nhp_disc_params_set(nhp_ctx *ctx, int64_t N, int64_t B, const double *lambda0, const double *W, const double *A,
+                        const double *theta, double dt);
+/* intensity(process, convolved)  discrete.jl:115-129 -> lam[t + T*c] */
+int nhp_disc_intensity(nhp_ctx *ctx, nhp_disc *dd, double *lam);
+/* loglikelihood(process, data, convolved)  discrete.jl:91-102 */
+int nhp_disc_loglik(nhp_ctx *ctx, nhp_disc *dd, double *ll);
+/* resample_parents(process, data, convolved) reduced over t  parents.jl:82-134:
+ * counts[c + N*k], k = 0 baseline, k = 1 + p*B + b.  u (one uniform per event, consumed in
+ * (t outer, c inner, draw) order) or NULL for Philox. */
+int nhp_disc_gibbs_counts(nhp_ctx *ctx, nhp_disc *dd, uint64_t seed, uint64_t counter, const double *u, int64_t nu, double *counts);
+/* update_parents + the three VB reductions  parents.jl:136-177, baselines.jl:444-452,
+ * weights.jl:70-91, impulses.jl:355-371.  e0[N], E[N*N*B] are the exp-expectations. */
+int nhp_disc_vb_stats(nhp_ctx *ctx, nhp_disc *dd, const double *e0, const double *E, double *alpha_sum, double *kappa_sum,
+                      double *nu_sum, double *gamma_sum);
+/* resample_adjacency_matrix!(process, data, convolved)  discrete.jl:426-480 */
+int nhp_disc_resample_adjacency(nhp_ctx *ctx, nhp_disc *dd, const double *rho, uint64_t seed, uint64_t counter, const double *u,
+                                double *A_inout);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

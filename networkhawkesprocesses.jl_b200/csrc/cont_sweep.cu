@@ -1,0 +1,584 @@
+// cont_sweep.cu -- dense predecessor-window sweeps over the time-sorted event stream:
+//   * log-likelihood / per-event total intensity   (continuous.jl:210-239, 286-300, 360-405)
+//   * Gibbs parent resampling fused with the counters and impulse statistics
+//     (parents.jl:1-46, 61-79; baselines.jl:87-96; impulses.jl:84-96, 230-252)
+// One CTA owns a tile of consecutive child events; the union of their dtmax windows is staged
+// into shared memory with one cp.async.bulk (TMA) transaction; a group of G lanes walks one
+// event's window most-recent-first, exactly the order of the reference loops.
+#include "cont_sweep.cuh"
+#include <algorithm>
+#include <cstdlib>
+
+enum { MODE_LOGLIK = 0, MODE_INTENSITY = 1 };
+
+// ---------------------------------------------------------------------------------------
+// window-start prepass: lo(i0) = first j with t[j] > t[i0] - horizon, for i0 = first + 64 b
+// ---------------------------------------------------------------------------------------
+__global__ void k_tile_lo(const double *__restrict__ t, int64_t first, int64_t n, double horizon, int *__restrict__ tile_lo, int64_t nb,
+                          unsigned long long *__restrict__ winstat) {
+    int64_t b = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (b >= nb) return;
+    int64_t i0 = first + b * NHP_TQ;
+    double thr = t[i0] - horizon;
+    int64_t good = i0, bad = -1, step = 64;
+    while (true) {  // gallop backwards: windows are short compared with the stream
+        int64_t cand = i0 - step;
+        if (cand <= 0) {
+            if (t[0] > thr) good = 0; else bad = 0;
+            break;
+        }
+        if (t[cand] > thr) { good = cand; step <<= 1; }
+        else { bad = cand; break; }
+    }
+    while (good - bad > 1) {
+        int64_t mid = (good + bad) >> 1;
+        if (t[mid] > thr) good = mid; else bad = mid;
+    }
+    if (good > i0) good = i0;
+    tile_lo[b] = (int)good;
+    unsigned long long w = (unsigned long long)(i0 - good);
+    atomicMax(&winstat[0], w);
+    atomicAdd(&winstat[1], w);
+}
+
+int nhp_cont_prepare_windows(nhp_ctx *ctx, nhp_events *ev, double horizon) {
+    if (ev->cache_horizon == horizon && ev->d_tile_lo) return NHP_OK;
+    int64_t own = ev->n - ev->n_halo;
+    int64_t nb = (own + NHP_TQ - 1) / NHP_TQ;
+    if (!ev->d_tile_lo) {
+        NHP_CUDA(ctx, cudaMalloc(&ev->d_tile_lo, (size_t)std::max<int64_t>(nb, 1) * sizeof(int)));
+        ev->n_bound = nb;
+    }
+    ev->max_win = 0; ev->mean_win = 0.0;
+    if (nb > 0) {
+        NHP_CUDA(ctx, cudaMemsetAsync(ctx->d_winstat, 0, 2 * sizeof(int64_t), ctx->stream));
+        k_tile_lo<<<(unsigned)((nb + 127) / 128), 128, 0, ctx->stream>>>(ev->d_t, ev->n_halo, ev->n, horizon, ev->d_tile_lo, nb,
+                                                                          (unsigned long long *)ctx->d_winstat);
+        NHP_LAUNCHED(ctx);
+        int64_t ws[2];
+        NHP_CUDA(ctx, cudaMemcpyAsync(ws, ctx->d_winstat, sizeof(ws), cudaMemcpyDeviceToHost, ctx->stream));
+        NHP_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+        ev->max_win = ws[0];
+        ev->mean_win = (double)ws[1] / (double)nb;
+    }
+    ev->cache_horizon = horizon;
+    return NHP_OK;
+}
+
+// ---------------------------------------------------------------------------------------
+// log-likelihood / intensity sweep
+// ---------------------------------------------------------------------------------------
+template <int KIND, int G, int MODE, bool ST>
+__device__ __forceinline__ void sweep_body(const SweepArgs &a, const Tile &tl, double &sum_log, double &sum_row) {
+    typedef typename EntryOf<KIND>::type E;
+    constexpr int NG = NHP_BLOCK / G;
+    const int gid = threadIdx.x / G, gl = threadIdx.x % G;
+    const unsigned gmask = group_mask<G>();
+    const int64_t jlo = max(tl.lo, a.jmin);
+    for (int64_t i = tl.i0 + gid; i < tl.i1; i += NG) {
+        const double ti = tile_T<ST>(a, tl, i);
+        const int ci = tile_C<ST>(a, tl, i);
+        const double thr = ti - a.horizon;
+        const E *col = reinterpret_cast<const E *>(a.table) + (size_t)ci * a.K;
+        double acc = 0.0;
+        for (int64_t j = i - 1 - gl; j >= jlo; j -= G) {
+            double tj = tile_T<ST>(a, tl, j);
+            if (!(tj > thr)) break;  // events[parentindex] > time - dtmax   (continuous.jl:291)
+            int cj = tile_C<ST>(a, tl, j);
+            acc += pair_value(load_entry(col + cj), ti - tj, a.D);
+        }
+        acc = group_sum<G>(acc, gmask);
+        if (gl == 0) {
+            double lam = __ldg(a.lambda0 + ci) + acc;
+            if (MODE == MODE_INTENSITY) a.lam_out[i - a.first] = lam;
+            else { sum_log += log(lam); sum_row += __ldg(a.rowsum + ci); }
+        }
+    }
+}
+
+template <int KIND, int G, int MODE>
+__global__ void __launch_bounds__(NHP_BLOCK) k_sweep(const SweepArgs a) {
+    extern __shared__ __align__(128) unsigned char smem[];
+    __shared__ double red[16];
+    Tile tl = stage_tile(a, smem);
+    double sum_log = 0.0, sum_row = 0.0;
+    if (tl.staged) sweep_body<KIND, G, MODE, true>(a, tl, sum_log, sum_row);
+    else sweep_body<KIND, G, MODE, false>(a, tl, sum_log, sum_row);
+    if (MODE == MODE_LOGLIK) {
+        block_sum2(sum_log, sum_row, red);
+        if (threadIdx.x == 0) { a.partials[2 * (size_t)blockIdx.x] = sum_log; a.partials[2 * (size_t)blockIdx.x + 1] = sum_row; }
+    }
+}
+
+// fixed-order second-stage reduction of the per-CTA partials -> out[0], out[1]
+__global__ void k_reduce_partials(const double *__restrict__ partials, int64_t nblocks, double *__restrict__ out) {
+    __shared__ double sx[1024], sy[1024];
+    double x = 0.0, y = 0.0;
+    for (int64_t b = threadIdx.x; b < nblocks; b += blockDim.x) { x += partials[2 * b]; y += partials[2 * b + 1]; }
+    sx[threadIdx.x] = x; sy[threadIdx.x] = y;
+    __syncthreads();
+    for (int s = blockDim.x / 2; s > 0; s >>= 1) {
+        if ((int)threadIdx.x < s) { sx[threadIdx.x] += sx[threadIdx.x + s]; sy[threadIdx.x] += sy[threadIdx.x + s]; }
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) { out[0] = sx[0]; out[1] = sy[0]; }
+}
+
+// ---------------------------------------------------------------------------------------
+// Gibbs parent sweep (parents.jl:25-46): weights most-recent-first then the baseline,
+// one uniform per event, inverse-cdf walk in that order; fused statistics.
+// ---------------------------------------------------------------------------------------
+template <int KIND, int G, int R, bool ST>
+__device__ __forceinline__ void parents_body(const SweepArgs &a, const Tile &tl) {
+    typedef typename EntryOf<KIND>::type E;
+    constexpr int NG = NHP_BLOCK / G;
+    const int gid = threadIdx.x / G, gl = threadIdx.x % G;
+    const unsigned gmask = group_mask<G>();
+    const int gshift = (threadIdx.x & 31) / G * G;
+    const int64_t jlo = max(tl.lo, a.jmin);
+    const StatsLayout sl{a.K};
+    for (int64_t i = tl.i0 + gid; i < tl.i1; i += NG) {
+        const double ti = tile_T<ST>(a, tl, i);
+        const int ci = tile_C<ST>(a, tl, i);
+        const double thr = ti - a.horizon;
+        const E *col = reinterpret_cast<const E *>(a.table) + (size_t)ci * a.K;
+        // pass 1: weights; the first R rows (G entries each) stay in registers
+        double vc[R];
+        double acc = 0.0;
+        int64_t j = i - 1 - gl;
+#pragma unroll
+        for (int r = 0; r < R; r++) {
+            double v = 0.0;
+            if (j >= jlo) {
+                double tj = tile_T<ST>(a, tl, j);
+                if (tj > thr) v = pair_value(load_entry(col + tile_C<ST>(a, tl, j)), ti - tj, a.D);
+            }
+            vc[r] = v;
+            acc += v;
+            j -= G;
+        }
+        for (; j >= jlo; j -= G) {
+            double tj = tile_T<ST>(a, tl, j);
+            if (!(tj > thr)) break;
+            acc += pair_value(load_entry(col + tile_C<ST>(a, tl, j)), ti - tj, a.D);
+        }
+        const double lam0 = __ldg(a.lambda0 + ci);
+        const double S = group_sum<G>(acc, gmask) + lam0;  // sum([weights...; baseline])
+        const int64_t gi = a.index_base + i;
+        const double u = a.u ? __ldg(a.u + (i - a.first)) : philox_uniform(a.seed, (uint64_t)gi, a.counter);
+        const double target = u * S;
+        // pass 2: first k with cumulative weight > u * S   (cp <= draw keeps walking)
+        int chosen = 0;  // i - j of the chosen parent, 0 = baseline
+        double carry = 0.0;
+        bool done = (gi == 0);  // index == 1 && return 0, 0   (parents.jl:26-28)
+#pragma unroll
+        for (int r = 0; r < R; r++) {
+            if (!done) {
+                double x = group_incl_scan<G>(vc[r], gmask, gl);
+                unsigned b = (__ballot_sync(gmask, carry + x > target) >> gshift) & (G == 32 ? 0xffffffffu : ((1u << G) - 1u));
+                if (b) { chosen = r * G + (__ffs(b) - 1) + 1; done = true; }
+                carry += __shfl_sync(gmask, x, G - 1, G);
+            }
+        }
+        if (!done) {
+            for (int64_t jr = i - 1 - (int64_t)R * G; jr >= jlo; jr -= G) {  // jr: the row's most recent entry
+                if (!(tile_T<ST>(a, tl, jr) > thr)) break;
+                int64_t jj = jr - gl;
+                double v = 0.0;
+                if (jj >= jlo) {
+                    double tj = tile_T<ST>(a, tl, jj);
+                    if (tj > thr) v = pair_value(load_entry(col + tile_C<ST>(a, tl, jj)), ti - tj, a.D);
+                }
+                double x = group_incl_scan<G>(v, gmask, gl);
+                unsigned b = (__ballot_sync(gmask, carry + x > target) >> gshift) & (G == 32 ? 0xffffffffu : ((1u << G) - 1u));
+                if (b) { chosen = (int)(i - jr) + (__ffs(b) - 1); break; }
+                carry += __shfl_sync(gmask, x, G - 1, G);
+            }
+        }
+        if (gl == 0) {
+            if (!(S > 0.0) || S > 1.7976931348623157e308) atomicOr(a.flag, 8);  // Categorical would reject the vector
+            a.poff[i] = chosen;
+            if (chosen == 0) red_add_f64(a.stats + sl.off_M0() + ci, 1.0);
+            else {
+                int64_t jp = i - chosen;
+                int cj = tile_C<ST>(a, tl, jp);
+                double dt = ti - tile_T<ST>(a, tl, jp);
+                int64_t k = cj + (int64_t)a.K * ci;
+                red_add_f64(a.stats + sl.off_Mnm() + k, 1.0);
+                red_add_f64(a.stats + sl.off_S1() + k, KIND == NHP_LOGITNORMAL ? log_duration_dev(dt, a.D) : dt);
+            }
+        }
+    }
+}
+
+template <int KIND, int G, int R>
+__global__ void __launch_bounds__(NHP_BLOCK) k_parents(const SweepArgs a) {
+    extern __shared__ __align__(128) unsigned char smem[];
+    Tile tl = stage_tile(a, smem);
+    if (tl.staged) parents_body<KIND, G, R, true>(a, tl);
+    else parents_body<KIND, G, R, false>(a, tl);
+}
+
+// ---------------------------------------------------------------------------------------
+// statistics helpers
+// ---------------------------------------------------------------------------------------
+__global__ void k_xbar(const double *__restrict__ Mnm, const double *__restrict__ S1, double *__restrict__ xbar, int64_t KK) {
+    int64_t k = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (k < KK) xbar[k] = S1[k] / Mnm[k];  // NaN where no pair was observed (impulses.jl:222-223)
+}
+
+// log_duration_variation (impulses.jl:242-252): second pass around the per-pair mean
+__global__ void k_second_pass(const double *__restrict__ t, const int *__restrict__ c, const int *__restrict__ poff, int64_t first, int64_t n,
+                              int K, double D, const double *__restrict__ xbar, double *__restrict__ S2) {
+    int64_t i = first + (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    int off = poff[i];
+    if (off <= 0) return;
+    int64_t j = i - off;
+    int64_t k = c[j] + (int64_t)K * c[i];
+    double d = log_duration_dev(t[i] - t[j], D) - xbar[k];
+    red_add_f64(S2 + k, d * d);
+}
+
+// counters + first-pass statistics from a stored parent assignment
+template <int KIND>
+__global__ void k_stats_from_parents(const double *__restrict__ t, const int *__restrict__ c, const int *__restrict__ poff, int64_t first,
+                                     int64_t n, int K, double D, double *__restrict__ stats) {
+    int64_t i = first + (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    StatsLayout sl{K};
+    int off = poff[i];
+    if (off == 0) red_add_f64(stats + sl.off_M0() + c[i], 1.0);
+    else if (off > 0) {
+        int64_t j = i - off;
+        int64_t k = c[j] + (int64_t)K * c[i];
+        double dt = t[i] - t[j];
+        red_add_f64(stats + sl.off_Mnm() + k, 1.0);
+        red_add_f64(stats + sl.off_S1() + k, KIND == NHP_LOGITNORMAL ? log_duration_dev(dt, D) : dt);
+    }
+}
+
+__global__ void k_export_parents(const int *__restrict__ c, const int *__restrict__ poff, int64_t first, int64_t n, int64_t index_base,
+                                 int64_t *__restrict__ parents, int64_t *__restrict__ parentnodes) {
+    int64_t i = first + (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    int off = poff[i];
+    int64_t j = i - off;
+    if (parents) parents[i - first] = off > 0 ? index_base + j + 1 : 0;
+    if (parentnodes) parentnodes[i - first] = off > 0 ? (int64_t)c[j] + 1 : 0;
+}
+
+__global__ void k_import_parents(const int64_t *__restrict__ parents, int64_t first, int64_t n, int64_t index_base, int *__restrict__ poff,
+                                 int *__restrict__ flag) {
+    int64_t i = first + (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    int64_t p = parents[i - first];
+    if (p == 0) { poff[i] = 0; return; }
+    int64_t j = p - 1 - index_base;  // local index of the parent
+    if (j < 0 || j >= i) { atomicOr(flag, 16); poff[i] = 0; return; }
+    poff[i] = (int)(i - j);
+}
+
+// ---------------------------------------------------------------------------------------
+// host-side dispatch
+// ---------------------------------------------------------------------------------------
+static int pick_group(const nhp_events *ev) {
+    const char *env = getenv("NHP_G");
+    if (env) {
+        int g = atoi(env);
+        if (g == 1 || g == 2 || g == 4 || g == 8 || g == 16 || g == 32) return g;
+    }
+    double w = ev->mean_win;
+    int64_t own = ev->n - ev->n_halo;
+    if (own < 200000) return w < 8 ? 8 : 32;  // small streams: spread each event over more lanes to fill the chip
+    if (w < 3) return 1;
+    if (w < 6) return 2;
+    if (w < 12) return 4;
+    if (w < 160) return 8;
+    if (w < 640) return 16;
+    return 32;
+}
+
+struct LaunchPlan { int G, te, cap; size_t smem; int64_t tiles; };
+
+static LaunchPlan make_plan(nhp_ctx *ctx, const nhp_events *ev) {
+    LaunchPlan p;
+    p.G = pick_group(ev);
+    int64_t own = ev->n - ev->n_halo;
+    p.te = 256;
+    if (p.G == 32 && own < 200000) p.te = 64;
+    const char *env = getenv("NHP_TE");
+    if (env) { int v = atoi(env); if (v >= 64 && v % 64 == 0 && v <= 4096) p.te = v; }
+    p.tiles = (own + p.te - 1) / p.te;
+    int64_t need = ((ev->max_win + p.te + 8) + 3) & ~(int64_t)3;
+    int64_t limit = ((int64_t)ctx->smem_optin - 1024 - 16) / 12;
+    limit &= ~(int64_t)3;
+    int64_t soft = 8192;  // keep several CTAs per SM resident; larger ranges fall back to L1/L2 reads
+    p.cap = (int)std::min(need, std::min(limit, soft));
+    p.smem = 16 + (size_t)p.cap * 12;
+    return p;
+}
+
+template <typename KernelT> static int launch_sweep(nhp_ctx *ctx, KernelT kernel, const LaunchPlan &p, const SweepArgs &a) {
+    if (p.smem > 48 * 1024) NHP_CUDA(ctx, cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p.smem));
+    kernel<<<(unsigned)p.tiles, NHP_BLOCK, p.smem, ctx->stream>>>(a);
+    NHP_LAUNCHED(ctx);
+    NHP_CUDA(ctx, cudaGetLastError());
+    return NHP_OK;
+}
+
+template <int KIND, int MODE> static int dispatch_sweep(nhp_ctx *ctx, const LaunchPlan &p, const SweepArgs &a) {
+    switch (p.G) {
+        case 1: return launch_sweep(ctx, k_sweep<KIND, 1, MODE>, p, a);
+        case 2: return launch_sweep(ctx, k_sweep<KIND, 2, MODE>, p, a);
+        case 4: return launch_sweep(ctx, k_sweep<KIND, 4, MODE>, p, a);
+        case 8: return launch_sweep(ctx, k_sweep<KIND, 8, MODE>, p, a);
+        case 16: return launch_sweep(ctx, k_sweep<KIND, 16, MODE>, p, a);
+        default: return launch_sweep(ctx, k_sweep<KIND, 32, MODE>, p, a);
+    }
+}
+
+template <int KIND> static int dispatch_parents(nhp_ctx *ctx, const LaunchPlan &p, const SweepArgs &a) {
+    switch (p.G) {
+        case 1: return launch_sweep(ctx, k_parents<KIND, 1, 8>, p, a);
+        case 2: return launch_sweep(ctx, k_parents<KIND, 2, 8>, p, a);
+        case 4: return launch_sweep(ctx, k_parents<KIND, 4, 8>, p, a);
+        case 8: return launch_sweep(ctx, k_parents<KIND, 8, 8>, p, a);
+        case 16: return launch_sweep(ctx, k_parents<KIND, 16, 4>, p, a);
+        default: return launch_sweep(ctx, k_parents<KIND, 32, 2>, p, a);
+    }
+}
+
+// Look-back horizon.  LogitNormal: dtmax.  Exponential: dtmax, shortened to the cut-off beyond
+// which the omitted tail is < 1e-14 of the smallest baseline rate: every omitted term is at most
+// wt_max exp(-theta_min H) and an event has fewer than n_total predecessors.
+double nhp_cont_horizon_value(const nhp_ctx *ctx, int64_t n_total, int recursive) {
+    double h = ctx->dtmax;
+    if (ctx->kind != NHP_EXPONENTIAL) return h;
+    if (recursive) h = INFINITY;  // recursive_loglikelihood ignores dtmax (quirk Q7)
+    if (ctx->wt_max <= 0.0) return std::min(h, 0.0 + 1e-300);  // no active pair: any horizon gives zero impulse mass
+    if (ctx->theta_min > 0.0 && std::isfinite(ctx->theta_min) && ctx->lambda0_min > 0.0 && n_total > 0) {
+        double cut = log((double)n_total * ctx->wt_max / (1e-14 * ctx->lambda0_min)) / ctx->theta_min;
+        if (cut > 0.0 && cut < h) h = cut;
+    }
+    return h;
+}
+
+extern "C" int nhp_cont_horizon(nhp_ctx *ctx, int64_t n_total, int recursive, double *horizon) {
+    NHP_CHECK(ctx, ctx != nullptr, NHP_ERR_INVALID, "ctx is NULL");
+    NHP_CHECK(ctx, ctx->cont_set, NHP_ERR_STATE, "continuous parameters not set");
+    NHP_CHECK(ctx, horizon != nullptr, NHP_ERR_INVALID, "nhp_cont_horizon: horizon is NULL");
+    *horizon = nhp_cont_horizon_value(ctx, n_total, recursive && ctx->kind == NHP_EXPONENTIAL);
+    return NHP_OK;
+}
+
+static int fill_args(nhp_ctx *ctx, nhp_events *ev, int recursive, SweepArgs &a, LaunchPlan &p) {
+    NHP_CHECK(ctx, ctx->cont_set, NHP_ERR_STATE, "continuous parameters not set (call nhp_cont_params_set)");
+    NHP_CHECK(ctx, ev != nullptr, NHP_ERR_INVALID, "events handle is NULL");
+    NHP_CHECK(ctx, ev->K == ctx->K, NHP_ERR_INVALID, "events were uploaded with K=%lld but parameters have K=%lld", (long long)ev->K, (long long)ctx->K);
+    bool rec = recursive && ctx->kind == NHP_EXPONENTIAL;
+    double horizon = nhp_cont_horizon_value(ctx, ev->index_base + ev->n, rec);
+    NHP_TRY(nhp_cont_prepare_windows(ctx, ev, horizon));
+    p = make_plan(ctx, ev);
+    a.t = ev->d_t; a.c = ev->d_c; a.n = ev->n; a.first = ev->n_halo; a.index_base = ev->index_base;
+    a.jmin = rec ? ev->n_t0 : 0;
+    a.tile_lo = ev->d_tile_lo; a.te = p.te; a.cap = p.cap; a.K = (int)ctx->K;
+    a.table = ctx->d_table; a.lambda0 = ctx->d_lambda0;
+    a.rowsum = (rec && ctx->has_A) ? ctx->d_rowsum_w : ctx->d_rowsum;  // quirk Q3
+    a.D = ctx->dtmax; a.horizon = horizon;
+    a.partials = nullptr; a.lam_out = nullptr; a.poff = ev->d_poff; a.u = nullptr; a.seed = 0; a.counter = 0;
+    a.stats = ctx->d_stats0; a.flag = ctx->d_flag;
+    return NHP_OK;
+}
+
+// leaves (log-sum, row-sum) in stats0[0..1]; no host synchronisation
+int nhp_cont_run_loglik(nhp_ctx *ctx, nhp_events *ev, int recursive) {
+    SweepArgs a; LaunchPlan p;
+    NHP_TRY(fill_args(ctx, ev, recursive, a, p));
+    if (p.tiles == 0) { NHP_CUDA(ctx, cudaMemsetAsync(ctx->d_stats0, 0, 2 * sizeof(double), ctx->stream)); return NHP_OK; }
+    NHP_TRY(nhp_partials(ctx, 2 * p.tiles, &a.partials));
+    if (ctx->kind == NHP_LOGITNORMAL) NHP_TRY((dispatch_sweep<NHP_LOGITNORMAL, MODE_LOGLIK>(ctx, p, a)));
+    else NHP_TRY((dispatch_sweep<NHP_EXPONENTIAL, MODE_LOGLIK>(ctx, p, a)));
+    k_reduce_partials<<<1, 1024, 0, ctx->stream>>>(a.partials, p.tiles, ctx->d_stats0);
+    NHP_LAUNCHED(ctx);
+    NHP_CUDA(ctx, cudaGetLastError());
+    return NHP_OK;
+}
+
+extern "C" int nhp_cont_loglik_dev(nhp_ctx *ctx, nhp_events *ev, int recursive) {
+    NHP_CHECK(ctx, ctx != nullptr, NHP_ERR_INVALID, "ctx is NULL");
+    NHP_CUDA(ctx, cudaSetDevice(ctx->device));
+    return nhp_cont_run_loglik(ctx, ev, recursive);
+}
+
+extern "C" int nhp_cont_loglik(nhp_ctx *ctx, nhp_events *ev, int recursive, double *ll) {
+    NHP_CHECK(ctx, ctx != nullptr, NHP_ERR_INVALID, "ctx is NULL");
+    NHP_CHECK(ctx, ll != nullptr, NHP_ERR_INVALID, "nhp_cont_loglik: ll is NULL");
+    NHP_CUDA(ctx, cudaSetDevice(ctx->device));
+    NHP_TRY(nhp_timer_begin(ctx));
+    NHP_TRY(nhp_cont_run_loglik(ctx, ev, recursive));
+    double h[2];
+    NHP_CUDA(ctx, cudaMemcpyAsync(h, ctx->d_stats0, sizeof(h), cudaMemcpyDeviceToHost, ctx->stream));
+    NHP_TRY(nhp_timer_end(ctx));
+    double base = (ev->flags & 1) ? ctx->lambda0_sum * ev->duration : 0.0;  // sum(integrated_intensity(baseline, duration))
+    // ll = -sum_k lambda0_k T - sum_i rowsum(c_i) + sum_i log lambda_i   (continuous.jl:217-238)
+    *ll = (0.0 - base) - h[1] + h[0];
+    return NHP_OK;
+}
+
+extern "C" int nhp_cont_event_intensity(nhp_ctx *ctx, nhp_events *ev, double *out) {
+    NHP_CHECK(ctx, ctx != nullptr, NHP_ERR_INVALID, "ctx is NULL");
+    NHP_CHECK(ctx, out != nullptr, NHP_ERR_INVALID, "nhp_cont_event_intensity: out is NULL");
+    NHP_CUDA(ctx, cudaSetDevice(ctx->device));
+    SweepArgs a; LaunchPlan p;
+    NHP_TRY(fill_args(ctx, ev, 0, a, p));
+    int64_t own = ev->n - ev->n_halo;
+    if (own == 0) return NHP_OK;
+    void *scratch;
+    NHP_TRY(nhp_scratch(ctx, (size_t)own * sizeof(double), &scratch));
+    a.lam_out = (double *)scratch;
+    NHP_TRY(nhp_timer_begin(ctx));
+    if (ctx->kind == NHP_LOGITNORMAL) NHP_TRY((dispatch_sweep<NHP_LOGITNORMAL, MODE_INTENSITY>(ctx, p, a)));
+    else NHP_TRY((dispatch_sweep<NHP_EXPONENTIAL, MODE_INTENSITY>(ctx, p, a)));
+    NHP_TRY(nhp_timer_end(ctx));
+    NHP_CUDA(ctx, cudaMemcpyAsync(out, scratch, (size_t)own * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+    NHP_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    return NHP_OK;
+}
+
+// ---- parents + statistics -----------------------------------------------------------------
+static int zero_stats(nhp_ctx *ctx, nhp_events *ev) {
+    StatsLayout sl{ctx->K};
+    NHP_CUDA(ctx, cudaMemsetAsync(ctx->d_stats0 + sl.off_M0(), 0, (size_t)(sl.total() - sl.off_M0()) * sizeof(double), ctx->stream));
+    NHP_CUDA(ctx, cudaMemcpyAsync(ctx->d_stats0 + sl.off_Mn(), ev->d_Mn, (size_t)ctx->K * sizeof(double), cudaMemcpyDeviceToDevice, ctx->stream));
+    NHP_CUDA(ctx, cudaMemsetAsync(ctx->d_stats1, 0, (size_t)(ctx->K * ctx->K) * sizeof(double), ctx->stream));
+    NHP_CUDA(ctx, cudaMemsetAsync(ctx->d_flag, 0, sizeof(int), ctx->stream));
+    return NHP_OK;
+}
+
+static int export_parents(nhp_ctx *ctx, nhp_events *ev, int64_t *parents, int64_t *parentnodes) {
+    int64_t own = ev->n - ev->n_halo;
+    if (own == 0 || (!parents && !parentnodes)) return NHP_OK;
+    void *scratch;
+    NHP_TRY(nhp_scratch(ctx, (size_t)own * 2 * sizeof(int64_t), &scratch));
+    int64_t *dp = (int64_t *)scratch, *dn = dp + own;
+    k_export_parents<<<(unsigned)((own + 255) / 256), 256, 0, ctx->stream>>>(ev->d_c, ev->d_poff, ev->n_halo, ev->n, ev->index_base, dp, dn);
+    NHP_LAUNCHED(ctx);
+    if (parents) NHP_CUDA(ctx, cudaMemcpyAsync(parents, dp, (size_t)own * sizeof(int64_t), cudaMemcpyDeviceToHost, ctx->stream));
+    if (parentnodes) NHP_CUDA(ctx, cudaMemcpyAsync(parentnodes, dn, (size_t)own * sizeof(int64_t), cudaMemcpyDeviceToHost, ctx->stream));
+    NHP_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    return NHP_OK;
+}
+
+extern "C" int nhp_cont_resample_parents(nhp_ctx *ctx, nhp_events *ev, uint64_t seed, uint64_t counter, const double *u, int64_t *parents,
+                                         int64_t *parentnodes) {
+    NHP_CHECK(ctx, ctx != nullptr, NHP_ERR_INVALID, "ctx is NULL");
+    NHP_CUDA(ctx, cudaSetDevice(ctx->device));
+    SweepArgs a; LaunchPlan p;
+    NHP_TRY(fill_args(ctx, ev, 0, a, p));
+    int64_t own = ev->n - ev->n_halo;
+    ctx->parents_valid = false;
+    NHP_TRY(zero_stats(ctx, ev));
+    double *du = nullptr;
+    if (u && own > 0) {
+        // uniforms live behind the export scratch area
+        void *scratch;
+        NHP_TRY(nhp_scratch(ctx, (size_t)own * 3 * sizeof(int64_t), &scratch));
+        du = (double *)scratch + 2 * own;
+        NHP_CUDA(ctx, cudaMemcpyAsync(du, u, (size_t)own * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
+    }
+    a.u = du; a.seed = seed; a.counter = counter;
+    NHP_TRY(nhp_timer_begin(ctx));
+    if (p.tiles > 0) {
+        if (ctx->kind == NHP_LOGITNORMAL) NHP_TRY(dispatch_parents<NHP_LOGITNORMAL>(ctx, p, a));
+        else NHP_TRY(dispatch_parents<NHP_EXPONENTIAL>(ctx, p, a));
+    }
+    int flag = 0;
+    NHP_CUDA(ctx, cudaMemcpyAsync(&flag, ctx->d_flag, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+    NHP_TRY(nhp_timer_end(ctx));
+    NHP_CHECK(ctx, !(flag & 8), NHP_ERR_NUMERIC, "resample_parents: non-positive or non-finite total intensity (Categorical would throw, parents.jl:42)");
+    ctx->parents_valid = true;
+    return export_parents(ctx, ev, parents, parentnodes);
+}
+
+extern "C" int nhp_cont_parents_set(nhp_ctx *ctx, nhp_events *ev, const int64_t *parents) {
+    NHP_CHECK(ctx, ctx != nullptr, NHP_ERR_INVALID, "ctx is NULL");
+    NHP_CHECK(ctx, ctx->cont_set, NHP_ERR_STATE, "continuous parameters not set");
+    NHP_CHECK(ctx, ev && parents, NHP_ERR_INVALID, "nhp_cont_parents_set: NULL argument");
+    NHP_CHECK(ctx, ev->K == ctx->K, NHP_ERR_INVALID, "events/parameter K mismatch");
+    NHP_CUDA(ctx, cudaSetDevice(ctx->device));
+    int64_t own = ev->n - ev->n_halo;
+    ctx->parents_valid = false;
+    NHP_TRY(zero_stats(ctx, ev));
+    if (own > 0) {
+        void *scratch;
+        NHP_TRY(nhp_scratch(ctx, (size_t)own * sizeof(int64_t), &scratch));
+        NHP_CUDA(ctx, cudaMemcpyAsync(scratch, parents, (size_t)own * sizeof(int64_t), cudaMemcpyHostToDevice, ctx->stream));
+        unsigned blocks = (unsigned)((own + 255) / 256);
+        k_import_parents<<<blocks, 256, 0, ctx->stream>>>((const int64_t *)scratch, ev->n_halo, ev->n, ev->index_base, ev->d_poff, ctx->d_flag);
+        NHP_LAUNCHED(ctx);
+        if (ctx->kind == NHP_LOGITNORMAL)
+            k_stats_from_parents<NHP_LOGITNORMAL><<<blocks, 256, 0, ctx->stream>>>(ev->d_t, ev->d_c, ev->d_poff, ev->n_halo, ev->n, (int)ctx->K, ctx->dtmax, ctx->d_stats0);
+        else
+            k_stats_from_parents<NHP_EXPONENTIAL><<<blocks, 256, 0, ctx->stream>>>(ev->d_t, ev->d_c, ev->d_poff, ev->n_halo, ev->n, (int)ctx->K, ctx->dtmax, ctx->d_stats0);
+        NHP_LAUNCHED(ctx);
+    }
+    int flag = 0;
+    NHP_CUDA(ctx, cudaMemcpyAsync(&flag, ctx->d_flag, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+    NHP_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    NHP_CHECK(ctx, !(flag & 16), NHP_ERR_INVALID, "nhp_cont_parents_set: a parent index is not an earlier event of this handle");
+    ctx->parents_valid = true;
+    return NHP_OK;
+}
+
+extern "C" int nhp_cont_suffstats_second_pass(nhp_ctx *ctx, nhp_events *ev) {
+    NHP_CHECK(ctx, ctx != nullptr, NHP_ERR_INVALID, "ctx is NULL");
+    NHP_CHECK(ctx, ctx->parents_valid, NHP_ERR_STATE, "no parent assignment (call nhp_cont_resample_parents or nhp_cont_parents_set)");
+    NHP_CUDA(ctx, cudaSetDevice(ctx->device));
+    int64_t KK = ctx->K * ctx->K;
+    NHP_CUDA(ctx, cudaMemsetAsync(ctx->d_stats1, 0, (size_t)KK * sizeof(double), ctx->stream));
+    if (ctx->kind != NHP_LOGITNORMAL) return NHP_OK;
+    StatsLayout sl{ctx->K};
+    k_xbar<<<(unsigned)((KK + 255) / 256), 256, 0, ctx->stream>>>(ctx->d_stats0 + sl.off_Mnm(), ctx->d_stats0 + sl.off_S1(), ctx->d_xbar, KK);
+    NHP_LAUNCHED(ctx);
+    int64_t own = ev->n - ev->n_halo;
+    if (own > 0) {
+        k_second_pass<<<(unsigned)((own + 255) / 256), 256, 0, ctx->stream>>>(ev->d_t, ev->d_c, ev->d_poff, ev->n_halo, ev->n, (int)ctx->K, ctx->dtmax, ctx->d_xbar, ctx->d_stats1);
+        NHP_LAUNCHED(ctx);
+    }
+    NHP_CUDA(ctx, cudaGetLastError());
+    return NHP_OK;
+}
+
+extern "C" int nhp_cont_suffstats_read(nhp_ctx *ctx, double *M0, double *Mn, double *Mnm, double *S1, double *S2) {
+    NHP_CHECK(ctx, ctx != nullptr, NHP_ERR_INVALID, "ctx is NULL");
+    NHP_CHECK(ctx, ctx->cont_set, NHP_ERR_STATE, "continuous parameters not set");
+    NHP_CUDA(ctx, cudaSetDevice(ctx->device));
+    StatsLayout sl{ctx->K};
+    int64_t K = ctx->K, KK = K * K;
+    cudaStream_t s = ctx->stream;
+    if (M0) NHP_CUDA(ctx, cudaMemcpyAsync(M0, ctx->d_stats0 + sl.off_M0(), (size_t)K * sizeof(double), cudaMemcpyDeviceToHost, s));
+    if (Mn) NHP_CUDA(ctx, cudaMemcpyAsync(Mn, ctx->d_stats0 + sl.off_Mn(), (size_t)K * sizeof(double), cudaMemcpyDeviceToHost, s));
+    if (Mnm) NHP_CUDA(ctx, cudaMemcpyAsync(Mnm, ctx->d_stats0 + sl.off_Mnm(), (size_t)KK * sizeof(double), cudaMemcpyDeviceToHost, s));
+    if (S1) NHP_CUDA(ctx, cudaMemcpyAsync(S1, ctx->d_stats0 + sl.off_S1(), (size_t)KK * sizeof(double), cudaMemcpyDeviceToHost, s));
+    if (S2) NHP_CUDA(ctx, cudaMemcpyAsync(S2, ctx->d_stats1, (size_t)KK * sizeof(double), cudaMemcpyDeviceToHost, s));
+    NHP_CUDA(ctx, cudaStreamSynchronize(s));
+    return NHP_OK;
+}
+
+extern "C" int nhp_cont_suffstats(nhp_ctx *ctx, nhp_events *ev, double *M0, double *Mn, double *Mnm, double *S1, double *S2) {
+    NHP_CHECK(ctx, ctx != nullptr, NHP_ERR_INVALID, "ctx is NULL");
+    if (S2) NHP_TRY(nhp_cont_suffstats_second_pass(ctx, ev));
+    else NHP_CHECK(ctx, ctx->parents_valid, NHP_ERR_STATE, "no parent assignment");
+    return nhp_cont_suffstats_read(ctx, M0, Mn, Mnm, S1, S2);
+}
+
+extern "C" int nhp_cont_stats_dev(nhp_ctx *ctx, int phase, void **ptr_dev, int64_t *count) {
+    NHP_CHECK(ctx, ctx != nullptr, NHP_ERR_INVALID, "ctx is NULL");
+    NHP_CHECK(ctx, ctx->cont_set, NHP_ERR_STATE, "continuous parameters not set");
+    NHP_CHECK(ctx, ptr_dev && count, NHP_ERR_INVALID, "nhp_cont_stats_dev: NULL output");
+    StatsLayout sl{ctx->K};
+    if (phase == 0) { *ptr_dev = ctx->d_stats0; *count = sl.total(); }
+    else { *ptr_dev = ctx->d_stats1; *count = ctx->K * ctx->K; }
+    return NHP_OK;
+}

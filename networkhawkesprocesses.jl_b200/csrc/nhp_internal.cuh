@@ -1,0 +1,201 @@
+// nhp_internal.cuh -- shared declarations of libnhp (sm_100a only).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <math.h>
+#include <string>
+#include <vector>
+#include "../../include/nhp.h"
+
+#define NHP_VERSION 100
+
+// ---------------------------------------------------------------------------------------
+// error plumbing
+// ---------------------------------------------------------------------------------------
+int nhp_fail(nhp_ctx *ctx, int code, const char *fmt, ...);
+
+#define NHP_CUDA(ctx, call)                                                                               \
+    do {                                                                                                  \
+        cudaError_t e__ = (call);                                                                         \
+        if (e__ != cudaSuccess) return nhp_fail((ctx), NHP_ERR_CUDA, "%s failed: %s (%s:%d)", #call,       \
+                                                cudaGetErrorString(e__), __FILE__, __LINE__);             \
+    } while (0)
+
+#define NHP_CHECK(ctx, cond, code, ...)                                  \
+    do {                                                                 \
+        if (!(cond)) return nhp_fail((ctx), (code), __VA_ARGS__);        \
+    } while (0)
+
+#define NHP_TRY(expr)                 \
+    do {                              \
+        int rc__ = (expr);            \
+        if (rc__ != NHP_OK) return rc__; \
+    } while (0)
+
+// ---------------------------------------------------------------------------------------
+// per-(parent, child) parameter table entries.  Layout in HBM: child-major,
+// table[child * K + parent], so a child's parents are contiguous (one 32 B / 16 B sector per pair).
+// ---------------------------------------------------------------------------------------
+struct __align__(32) EntryLN {  // LogitNormal: value = cf * exp(-h (z - mu)^2) / (dt (D - dt)),  z = log(dt/(D-dt))
+    double cf;                  // [A] * W * sqrt(tau) * invsqrt2pi * D^2
+    double mu;
+    double h;                   // tau / 2
+    double pad;
+};
+struct __align__(16) EntryEX {  // Exponential: value = wt * exp(-theta dt)
+    double wt;                  // [A] * W * theta
+    double theta;
+};
+template <int KIND> struct EntryOf;
+template <> struct EntryOf<NHP_EXPONENTIAL> { typedef EntryEX type; };
+template <> struct EntryOf<NHP_LOGITNORMAL> { typedef EntryLN type; };
+
+// stats buffer layout (phase 0): [ll_logsum, ll_rowsum, M0[K], Mn[K], Mnm[K*K], S1[K*K]]
+struct StatsLayout {
+    int64_t K;
+    __host__ __device__ int64_t off_ll() const { return 0; }
+    __host__ __device__ int64_t off_M0() const { return 2; }
+    __host__ __device__ int64_t off_Mn() const { return 2 + K; }
+    __host__ __device__ int64_t off_Mnm() const { return 2 + 2 * K; }
+    __host__ __device__ int64_t off_S1() const { return 2 + 2 * K + K * K; }
+    __host__ __device__ int64_t total() const { return 2 + 2 * K + 2 * K * K; }
+};
+
+struct nhp_events {
+    int64_t n = 0;          // events passed (halo + own)
+    int64_t n_halo = 0;     // leading read-only predecessors
+    int64_t index_base = 0; // global 0-based index of event 0
+    int flags = 1;
+    double duration = 0.0;
+    int64_t K = 0;
+    double *d_t = nullptr;      // [n + pad]
+    int *d_c = nullptr;         // [n + pad] 0-based nodes
+    int *d_poff = nullptr;      // [n] parent offset i - j (>0) | 0 baseline | -1 unset
+    double *d_Mn = nullptr;     // [K] own-event counts per node
+    int64_t n_t0 = 0;           // number of leading events with t == 0.0 exactly (quirk Q6)
+    // tile window-start cache (depends on the look-back horizon)
+    double cache_horizon = -1.0;
+    int *d_tile_lo = nullptr;   // [ceil((n - n_halo)/64)]
+    int64_t n_bound = 0;
+    int64_t max_win = 0;        // max over boundaries of (i0 - lo)
+    double mean_win = 0.0;
+};
+
+struct nhp_disc {
+    int64_t N = 0, T = 0, t_halo = 0;
+    int *d_data = nullptr;      // [T][N] counts as int32, time-major (t outer, n inner) == Julia data[n + N*t]
+    double *d_conv = nullptr;   // [B][N][T]  conv[t + T*(n + N*b)]
+    int64_t L = 0, B = 0;
+    int64_t total_events = 0;
+    int64_t *d_scan = nullptr;  // exclusive scan of data in memory order (uniform index of each bin's first draw)
+};
+
+struct nhp_ctx {
+    int device = 0;
+    cudaStream_t stream = nullptr;
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+    std::string err;
+    int64_t launches = 0;
+    double last_ms = 0.0;
+    int sm_count = 148;
+    int smem_optin = 0;
+
+    // ---- continuous parameters
+    bool cont_set = false;
+    int kind = 0;
+    int64_t K = 0;
+    double dtmax = 0.0;
+    bool has_A = false;
+    double density = 1.0;       // fraction of non-zero effective weights
+    double theta_min = 0.0, wt_max = 0.0, lambda0_min = 0.0; // Exponential cut-off horizon inputs
+    double lambda0_sum = 0.0;
+    double *d_lambda0 = nullptr;  // [K]
+    double *d_W = nullptr, *d_A = nullptr, *d_p1 = nullptr, *d_p2 = nullptr; // raw [K*K] parent-major as passed
+    void *d_table = nullptr;      // EntryLN/EntryEX [K*K] child-major
+    double *d_rowsum = nullptr;   // [K] sum_c [A]W[p,c]
+    double *d_rowsum_w = nullptr; // [K] sum_c W[p,c] (recursive Network quirk Q3)
+    uint32_t *d_abits = nullptr;  // adjacency/non-zero bitmask, child-major rows of abits_words words
+    int64_t abits_words = 0;
+    int64_t cap_K = 0;            // allocated for this K
+
+    // ---- statistics
+    double *d_stats0 = nullptr;   // StatsLayout
+    double *d_stats1 = nullptr;   // [K*K] S2
+    double *d_xbar = nullptr;     // [K*K] S1/Mnm scratch
+    int *d_flag = nullptr;        // device error flag
+    bool parents_valid = false;
+
+    // ---- scratch
+    double *d_partials = nullptr;
+    int64_t partials_cap = 0;
+    void *d_scratch = nullptr;
+    size_t scratch_cap = 0;
+    int64_t *d_winstat = nullptr; // [2]: max window, sum window
+
+    // ---- discrete parameters
+    bool disc_set = false;
+    int64_t dN = 0, dB = 0;
+    double ddt = 1.0;
+    bool d_has_A = false;
+    double *dd_lambda0 = nullptr, *dd_W = nullptr, *dd_A = nullptr, *dd_theta = nullptr;
+    double *dd_bump = nullptr;    // [N*B][N] row k=(p*B+b), col c: [A]W theta dt
+};
+
+// launch bookkeeping
+#define NHP_LAUNCHED(ctx) ((ctx)->launches++)
+
+int nhp_scratch(nhp_ctx *ctx, size_t bytes, void **out);
+int nhp_partials(nhp_ctx *ctx, int64_t count, double **out);
+int nhp_timer_begin(nhp_ctx *ctx);
+int nhp_timer_end(nhp_ctx *ctx);  // synchronises the stream and stores last_ms
+
+// ---------------------------------------------------------------------------------------
+// device helpers
+// ---------------------------------------------------------------------------------------
+#define NHP_INVSQRT2PI 0.3989422804014327
+
+// Philox4x32-10 (Salmon et al. 2011): counter (c0..c3), key (k0,k1)
+__host__ __device__ inline void philox4x32_10(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3, uint32_t k0, uint32_t k1, uint32_t out[4]) {
+    const uint32_t M0 = 0xD2511F53u, M1 = 0xCD9E8D57u, W0 = 0x9E3779B9u, W1 = 0xBB67AE85u;
+#pragma unroll
+    for (int r = 0; r < 10; r++) {
+        uint64_t p0 = (uint64_t)M0 * c0, p1 = (uint64_t)M1 * c2;
+        uint32_t hi0 = (uint32_t)(p0 >> 32), lo0 = (uint32_t)p0, hi1 = (uint32_t)(p1 >> 32), lo1 = (uint32_t)p1;
+        uint32_t n0 = hi1 ^ c1 ^ k0, n1 = lo1, n2 = hi0 ^ c3 ^ k1, n3 = lo0;
+        c0 = n0; c1 = n1; c2 = n2; c3 = n3;
+        k0 += W0; k1 += W1;
+    }
+    out[0] = c0; out[1] = c1; out[2] = c2; out[3] = c3;
+}
+// uniform double in [0,1) with 53 random bits, keyed by (seed; index, counter)
+__host__ __device__ inline double philox_uniform(uint64_t seed, uint64_t index, uint64_t counter) {
+    uint32_t r[4];
+    philox4x32_10((uint32_t)index, (uint32_t)(index >> 32), (uint32_t)counter, (uint32_t)(counter >> 32), (uint32_t)seed, (uint32_t)(seed >> 32), r);
+    uint64_t x = (((uint64_t)r[0] << 32) | (uint64_t)r[1]) >> 11;
+    return (double)x * 1.1102230246251565e-16; // 2^-53
+}
+
+#ifdef __CUDACC__
+__device__ __forceinline__ double pair_value(const EntryLN &e, double dt, double D) {
+    // Distributions.pdf(LogitNormal(mu, tau^-1/2), dt/D): zero outside 0 < x < 1 (impulses.jl:174-178)
+    if (!(dt > 0.0 && dt < D)) return 0.0;
+    double inv = 1.0 / (dt * (D - dt));
+    double z = log(dt * dt * inv);
+    double dz = z - e.mu;
+    return e.cf * exp(-e.h * dz * dz) * inv;
+}
+__device__ __forceinline__ double pair_value(const EntryEX &e, double dt, double) {
+    // Distributions.pdf(Exponential(1/theta), dt): theta exp(-theta dt), zero for dt < 0 (impulses.jl:106-108)
+    if (dt < 0.0) return 0.0;
+    return e.wt * exp(-e.theta * dt);
+}
+// log_duration(parent, child, dtmax)  impulses.jl:228
+__device__ __forceinline__ double log_duration_dev(double dt, double D) { return log(dt / (D - dt)); }
+
+__device__ __forceinline__ void red_add_f64(double *addr, double v) { atomicAdd(addr, v); }
+#endif
+
+// internal entry points shared between translation units
+int nhp_cont_prepare_windows(nhp_ctx *ctx, nhp_events *ev, double horizon);
+int nhp_cont_run_loglik(nhp_ctx *ctx, nhp_events *ev, int recursive);
+double nhp_cont_horizon_value(const nhp_ctx *ctx, int64_t n_total, int recursive);

@@ -1,0 +1,9 @@
+"""nhp_b200 -- host-side mirror of NetworkHawkesProcesses.jl's event-history API over libnhp
+(hand-written sm_100a CUDA behind the C ABI of include/nhp.h).  No CPU fallback."""
+from ._lib import NHPError, LIB_PATH, load  # noqa: F401
+from .core import Context, ContinuousData, default_context  # noqa: F401
+from .continuous import (  # noqa: F401
+    HomogeneousProcess, ExponentialImpulseResponse, LogitNormalImpulseResponse, DenseWeightModel, SparseWeightModel,
+    DenseNetworkModel, BernoulliNetworkModel, ContinuousStandardHawkesProcess, ContinuousNetworkHawkesProcess,
+    loglikelihood, event_intensity, intensity, resample_parents, sufficient_statistics, resample_adjacency_matrix_,
+    resample_, mcmc_, mle_, rand, MarkovChainMonteCarlo, MaximumLikelihood)

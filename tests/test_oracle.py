@@ -1,0 +1,124 @@
+"""CPU tests: the oracle against the formula-derived KAT vectors (tests/golden/kat.json, made by
+tests/golden/make_kat.py with SciPy) and against the fixtures of the reference's own tests
+(/root/reference/test/baselines.jl:10-23, 77-78)."""
+import numpy as np
+import pytest
+
+import oracle_ffi as orc
+
+RTOL = 1e-13
+
+
+def test_kat_a_exponential(kat):
+    k = kat["A"]
+    m = orc.Cont(0, k["lambda0"], np.array(k["W"]), np.array(k["theta"]))
+    lam = m.event_intensity(k["events"], k["nodes"])
+    np.testing.assert_allclose(lam, k["intensities"], rtol=RTOL)
+    assert m.loglik(k["events"], k["nodes"], k["duration"], recursive=False) == pytest.approx(k["ll"], rel=RTOL)
+    # recursive and windowed forms agree (continuous.jl:241-276 vs 210-239)
+    assert m.loglik(k["events"], k["nodes"], k["duration"], recursive=True) == pytest.approx(k["ll"], rel=RTOL)
+
+
+def test_kat_b_logitnormal(kat):
+    k = kat["B"]
+    W = np.array(k["W"])
+    mu, tau = np.full((2, 2), k["mu"]), np.full((2, 2), k["tau"])
+    m = orc.Cont(1, k["lambda0"], W, mu, tau, dtmax=k["dtmax"])
+    np.testing.assert_allclose(m.event_intensity(k["events"], k["nodes"]), k["intensities"], rtol=RTOL)
+    assert m.loglik(k["events"], k["nodes"], k["duration"]) == pytest.approx(k["ll"], rel=RTOL)
+    mn = orc.Cont(1, k["lambda0"], W, mu, tau, A=np.array(k["A"]), dtmax=k["dtmax"])
+    np.testing.assert_allclose(mn.event_intensity(k["events"], k["nodes"]), k["intensities_network"], rtol=RTOL)
+    assert mn.loglik(k["events"], k["nodes"], k["duration"]) == pytest.approx(k["ll_network"], rel=RTOL)
+
+
+def test_kat_c_parent_draws(kat):
+    kb, kc = kat["B"], kat["C"]
+    m = orc.Cont(1, kb["lambda0"], np.array(kb["W"]), np.full((2, 2), 1.0), np.full((2, 2), 1.0), dtmax=1.0)
+    for d in kc["draws"]:
+        u = np.full(6, 0.999999)
+        u[3] = d["u"]
+        par, pn = m.resample_parents(kb["events"], kb["nodes"], u)
+        assert par[3] == d["parent"]
+        assert pn[3] == (kb["nodes"][d["parent"] - 1] if d["parent"] > 0 else 0)
+        assert par[0] == 0 and pn[0] == 0  # index == 1 -> (0, 0)  parents.jl:26-28
+
+
+def test_kat_d_sufficient_statistics(kat):
+    kb, kd = kat["B"], kat["D"]
+    nodes = np.array(kb["nodes"])
+    par = np.array(kd["parents"])
+    pn = np.where(par > 0, nodes[np.maximum(par, 1) - 1], 0)
+    st = orc.suffstats(1, kb["events"], nodes, par, pn, 2, 1.0)
+    np.testing.assert_array_equal(st["M0"], kd["M0"])
+    np.testing.assert_array_equal(st["Mn"], kd["Mn"])
+    np.testing.assert_array_equal(st["Mnm"], kd["Mnm"])
+    np.testing.assert_allclose(st["S1"], kd["Xsum"], rtol=RTOL)
+    np.testing.assert_allclose(st["S2"], kd["V"], rtol=1e-12, atol=1e-300)
+    ste = orc.suffstats(0, kb["events"], nodes, par, pn, 2, np.inf)
+    np.testing.assert_allclose(ste["duration_mean"], kd["duration_mean"], rtol=RTOL)
+
+
+def test_kat_e_discrete(kat):
+    k = kat["E"]
+    phi = orc.disc_basis(k["L"], k["B"], k["dt"])
+    np.testing.assert_allclose(phi, k["phi"], rtol=RTOL)
+    data = np.array(k["data"], dtype=np.int64)
+    conv = orc.disc_convolve(data, phi)
+    np.testing.assert_allclose(conv, k["conv"], rtol=RTOL, atol=1e-300)
+    m = orc.Disc(k["lambda0"], np.array(k["W"]), np.full((2, 2, 3), 1.0 / 3.0), dt=k["dt"])
+    np.testing.assert_allclose(m.intensity(conv), k["lam"], rtol=RTOL)
+    assert m.loglik(data, conv) == pytest.approx(k["ll"], rel=1e-12)
+
+
+def test_reference_fixture_node_counts(kat):
+    # test/baselines.jl:10-23
+    import ctypes
+    for case in kat["ref_tests"]["node_counts"]:
+        nodes = np.array(case["nodes"], dtype=np.int64)
+        pn = np.array(case["parentnodes"], dtype=np.int64)
+        out = np.empty(case["K"])
+        orc.lib().orc_baseline_counts(orc._p(nodes), orc._p(pn), ctypes.c_int64(nodes.size), ctypes.c_int64(case["K"]), orc._p(out))
+        np.testing.assert_array_equal(out, case["expect"])
+
+
+def test_reference_fixture_discrete_counts(kat):
+    # test/baselines.jl:77-78: sufficient_statistics(process, data) == ([3, 2], 10); nu_sum carries the same row sums
+    c = kat["ref_tests"]["disc_suffstats"]
+    data = np.array(c["data"], dtype=np.int64)
+    conv = orc.disc_convolve(data, orc.disc_basis(4, 3))
+    st = orc.disc_vb_stats(data, conv, np.ones(2), np.ones((2, 2, 3)))
+    np.testing.assert_array_equal(st["nu_sum"][:, 0], c["expect_Mn"])
+    assert data.shape[1] == c["expect_T"]
+
+
+def test_recursive_equals_windowed_full_history():
+    import synth
+    t, nodes, T = synth.poisson_stream(400, 3, 5.0, 1)
+    lam0, W, theta, _ = synth.exp_params(3, 2, wmax=0.3)
+    m = orc.Cont(0, lam0, W, theta)
+    assert m.loglik(t, nodes, T, recursive=True) == pytest.approx(m.loglik(t, nodes, T, recursive=False), rel=1e-12)
+
+
+def test_threads_match_serial():
+    import synth
+    t, nodes, T = synth.poisson_stream(3000, 5, 50.0, 3)
+    lam0, W, mu, tau, A = synth.ln_params(5, 4, wmax=0.2, density=0.5)
+    m = orc.Cont(1, lam0, W, mu, tau, A=A, dtmax=1.0)
+    u = np.random.default_rng(0).random(t.size)
+    orc.set_threads(1)
+    ll1 = m.loglik(t, nodes, T)
+    p1 = m.resample_parents(t, nodes, u)
+    orc.set_threads(4)
+    ll4 = m.loglik(t, nodes, T)
+    p4 = m.resample_parents(t, nodes, u)
+    orc.set_threads(1)
+    assert ll4 == pytest.approx(ll1, rel=1e-12)
+    np.testing.assert_array_equal(p1[0], p4[0])
+
+
+def test_philox_reference_vector():
+    # Random123 known-answer test for philox4x32-10: counter = key = 0 -> 6627e8d5 e169c58d bc57ac4c 9b00dbd8
+    import synth
+    u = synth.philox_uniform(0, np.array([0], dtype=np.uint64), 0)
+    x = ((0x6627E8D5 << 32) | 0xE169C58D) >> 11
+    assert u[0] == x * 2.0 ** -53

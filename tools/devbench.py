@@ -1,0 +1,58 @@
+"""Developer micro-benchmark (not the driver's bench.py): times the continuous sweeps on synthetic streams."""
+import os
+import sys
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, os.path.join(ROOT, "networkhawkesprocesses.jl_b200"))
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+import nhp_b200 as nhp  # noqa: E402
+import synth  # noqa: E402
+
+
+def run(name, K, n, rate, density, kind="ln", reps=5, G=None):
+    if G is not None:
+        os.environ["NHP_G"] = str(G)
+    else:
+        os.environ.pop("NHP_G", None)
+    t, nodes, T = synth.poisson_stream(n, K, rate, 1)
+    if kind == "ln":
+        lam0, W, mu, tau, A = synth.ln_params(K, 2, density=density)
+        imp = nhp.LogitNormalImpulseResponse(mu, tau, 1.0)
+    else:
+        lam0, W, theta, A = synth.exp_params(K, 2, density=density)
+        imp = nhp.ExponentialImpulseResponse(theta, dtmax=1.0)
+    base, wts = nhp.HomogeneousProcess(lam0), nhp.DenseWeightModel(W)
+    proc = nhp.ContinuousStandardHawkesProcess(base, imp, wts) if A is None else nhp.ContinuousNetworkHawkesProcess(base, imp, wts, A, nhp.BernoulliNetworkModel(density, K))
+    ctx = proc._ctx()
+    d = proc.upload((t, nodes, T))
+    out = {}
+    for op in ("loglik", "parents"):
+        ms = []
+        for r in range(reps + 2):
+            if op == "loglik":
+                nhp.loglikelihood(proc, d)
+            else:
+                nhp.resample_parents(proc, d, seed=1, counter=r, export=False)
+            ms.append(ctx.last_kernel_ms)
+        out[op] = float(np.median(ms[2:]))
+    w = rate * 1.0
+    print(f"{name:34s} K={K:5d} n={n:.1e} w~{w:5.0f} dens={density} G={G}  loglik {out['loglik']:8.3f} ms = {n / out['loglik'] / 1e3:9.1f} Mev/s "
+          f"({n * w / out['loglik'] / 1e6:7.1f} Gpair/s) | parents {out['parents']:8.3f} ms = {n / out['parents'] / 1e3:9.1f} Mev/s", flush=True)
+    d.free()
+
+
+if __name__ == "__main__":
+    which = sys.argv[1] if len(sys.argv) > 1 else "all"
+    if which in ("all", "g"):
+        for G in (1, 2, 4, 8, 16, 32):
+            run("cfg2 LN std K=50", 50, 1_000_000, 100.0, None, G=G)
+        for G in (1, 4, 8, 16, 32):
+            run("cfg4-like LN std K=1000", 1000, 4_000_000, 64.0, None, G=G)
+    if which in ("all", "main"):
+        run("cfg2 LN std K=50", 50, 1_000_000, 100.0, None)
+        run("cfg4-like LN std K=1000 dense", 1000, 10_000_000, 64.0, None)
+        run("cfg4-like LN net K=1000 rho=.05", 1000, 10_000_000, 64.0, 0.05)
+        run("exp std K=50 dtmax=1", 50, 1_000_000, 100.0, None, kind="exp")
