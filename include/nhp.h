@@ -50,6 +50,17 @@ int64_t nhp_launch_count(const nhp_ctx *ctx);
 /* device-time (CUDA events on the context stream) of the kernels of the most recent call, ms */
 double nhp_last_kernel_ms(const nhp_ctx *ctx);
 
+/* Run every later call of this context on the caller's CUDA stream (a cudaStream_t passed as
+ * void*; NULL restores the context's own stream), e.g. torch.cuda.current_stream().cuda_stream so
+ * that the caller's CUDA events and NCCL collectives order with the library's kernels. */
+int nhp_set_stream(nhp_ctx *ctx, void *cuda_stream);
+/* Roofline denominators measured on this device: which = 0 FP64 FMA peak [TFLOP/s],
+ * 1 LogitNormal / 2 Exponential register-resident impulse evaluations [pairs/s]. */
+int nhp_bench_fp64(nhp_ctx *ctx, int which, double *result);
+/* Test hook for the table-driven FP64 log (which = 0) / exp (which = 1) the impulse evaluation uses:
+ * out[i] = f(x[i]), host pointers. */
+int nhp_test_fastmath(nhp_ctx *ctx, int which, const double *x, int64_t n, double *out);
+
 /* ---- continuous data: data = (events, nodes, duration) of continuous.jl:14 ------------- */
 /* Upload once; mle!/mcmc! call the likelihood thousands of times on the same data
  * (continuous.jl:146-149, inference.jl:55-62).

@@ -1,0 +1,318 @@
+// cont_adjacency.cu -- resample_adjacency_matrix!(process, data)  (continuous.jl:444-519).
+//
+// The reference evaluates, for every (p, c), two full passes over all N events (2 K^2 N work).  The
+// conditional it samples from only depends on the child events on c whose window holds an event of
+// node p:  with G_i[p] = W[p,c] sum_{j in win(i), c_j = p} h_pc(t_i - t_j)  and
+// lambda_i = lambda0_c + sum_p A[p,c] G_i[p],
+//     ll1 - ll0 = -W[p,c] n_p + sum_{i on c, G_i[p] > 0} [ log(lambda_i^{-p} + G_i[p]) - log(lambda_i^{-p}) ]
+//                 + log rho - log(1 - rho),          A[p,c] ~ Bernoulli(exp(ll1 - logsumexp(ll0, ll1))),
+// p = 1..K sequentially inside a column, columns independent (the reference's Threads.@threads axis).
+// One CTA owns a column: (A) it walks the windows of the column's child events once and buckets the
+// (event, G) entries by parent node in a per-CTA scratch area (counting sort, shared-memory
+// histogram), (B) then runs the K sequential Bernoulli steps, each a block-wide reduction over one
+// bucket.  Same conditional distribution, O(N w) work per sweep instead of O(K^2 N).
+#include "cont_sweep.cuh"
+#include <cub/cub.cuh>
+
+struct AdjArgs {
+    const double *t; const int *c; int64_t n;
+    const int *order;        // child events sorted by (node, time): event indices
+    const int *node_ptr;     // [K+1] offsets into order
+    const double *Mn;        // [K] events per node
+    int K; const void *table_w;  // table without the adjacency factor
+    const double *lambda0; const double *W; double *A;  // A: [K*K] parent-major as passed, updated in place
+    const double *rho; const double *u; uint64_t seed, counter;
+    double D, horizon, duration;
+    int64_t cap;             // scratch entries per CTA
+    int *ent_i; double *ent_v; double *lam; double *gacc;  // per-CTA scratch regions
+    int64_t max_col;         // max child events per column
+    int *flag;
+};
+
+__device__ __forceinline__ int lo_of_event(const double *t, int64_t i, double horizon) {
+    // first j with t[j] > t[i] - horizon (galloping backwards, as k_tile_lo)
+    double thr = t[i] - horizon;
+    int64_t good = i, bad = -1, step = 32;
+    while (true) {
+        int64_t cand = i - step;
+        if (cand <= 0) { if (t[0] > thr) good = 0; else bad = 0; break; }
+        if (t[cand] > thr) { good = cand; step <<= 1; } else { bad = cand; break; }
+    }
+    while (good - bad > 1) { int64_t mid = (good + bad) >> 1; if (t[mid] > thr) good = mid; else bad = mid; }
+    return (int)good;
+}
+
+template <int KIND> __global__ void __launch_bounds__(256) k_adjacency(const AdjArgs a) {
+    typedef typename EntryOf<KIND>::type E;
+    extern __shared__ int s_dyn[];  // [K+1] bucket offsets, [K] cursors
+    __shared__ FastTables s_ft;
+    __shared__ double s_red[8];
+    __shared__ double s_anew;
+    int *s_off = s_dyn, *s_cur = s_dyn + a.K + 1;
+    fast_tables_load(&s_ft);
+    int *ent_i = a.ent_i + (size_t)blockIdx.x * a.cap;
+    double *ent_v = a.ent_v + (size_t)blockIdx.x * a.cap;
+    double *lam = a.lam + (size_t)blockIdx.x * a.max_col;
+    double *gacc = a.gacc + (size_t)blockIdx.x * a.max_col;
+    for (int c = blockIdx.x; c < a.K; c += gridDim.x) {
+        const int e0 = a.node_ptr[c], e1 = a.node_ptr[c + 1];
+        const E *col = reinterpret_cast<const E *>(a.table_w) + (size_t)c * a.K;
+        const double lam0 = a.lambda0[c];
+        // ---- A1: bucket sizes
+        for (int k = threadIdx.x; k <= a.K; k += blockDim.x) s_off[k] = 0;
+        __syncthreads();
+        for (int e = e0 + threadIdx.x; e < e1; e += blockDim.x) {
+            int i = a.order[e];
+            double ti = a.t[i], thr = ti - a.horizon;
+            for (int j = i - 1; j >= 0; j--) {
+                if (!(a.t[j] > thr)) break;
+                atomicAdd(&s_off[a.c[j] + 1], 1);
+            }
+        }
+        __syncthreads();
+        if (threadIdx.x == 0) {  // exclusive scan (K is small next to the event work)
+            int run = 0;
+            for (int k = 0; k < a.K; k++) { int v = s_off[k + 1]; s_off[k] = run; s_cur[k] = run; run += v; }
+            s_off[a.K] = run;
+            if (run > a.cap) atomicOr(a.flag, 32);
+        }
+        __syncthreads();
+        if (s_off[a.K] > a.cap) continue;  // cannot happen: cap is sized from the exact per-column totals
+        // ---- A2: emit (event, G) entries and the current intensities
+        for (int e = e0 + threadIdx.x; e < e1; e += blockDim.x) {
+            int i = a.order[e];
+            double ti = a.t[i], thr = ti - a.horizon, s = lam0;
+            for (int j = i - 1; j >= 0; j--) {
+                double tj = a.t[j];
+                if (!(tj > thr)) break;
+                int p = a.c[j];
+                double v = pair_value(load_entry(col + p), ti - tj, a.D, &s_ft);
+                int pos = atomicAdd(&s_cur[p], 1);
+                ent_i[pos] = e - e0;
+                ent_v[pos] = v;
+                s += a.A[p + (int64_t)a.K * c] * v;
+            }
+            lam[e - e0] = s;
+            gacc[e - e0] = 0.0;
+        }
+        __syncthreads();
+        // ---- B: K sequential Bernoulli steps
+        for (int p = 0; p < a.K; p++) {
+            const int b0 = s_off[p], b1 = s_off[p + 1];
+            const int64_t kk = p + (int64_t)a.K * c;
+            const double a_old = a.A[kk];
+            double part = 0.0;
+            if (b1 > b0) {
+                for (int e = b0 + threadIdx.x; e < b1; e += blockDim.x) {
+                    double v = ent_v[e];
+                    if (v > 0.0) {
+                        double old = atomicAdd(&gacc[ent_i[e]], v);
+                        if (old == 0.0) ent_i[e] |= 0x40000000;  // owner of this event's aggregate
+                    }
+                }
+                __syncthreads();
+                for (int e = b0 + threadIdx.x; e < b1; e += blockDim.x) {
+                    int ii = ent_i[e];
+                    if (ii & 0x40000000) {
+                        ii &= 0x3fffffff;
+                        double g = gacc[ii], l = lam[ii];
+                        double base = a_old != 0.0 ? l - g : l;
+                        part += log((base + g) / base);
+                    }
+                }
+                part = warp_sum(part);
+                if ((threadIdx.x & 31) == 0) s_red[threadIdx.x >> 5] = part;
+                __syncthreads();
+            }
+            if (threadIdx.x == 0) {
+                double sum = 0.0;
+                if (b1 > b0) for (int w = 0; w < 8; w++) sum += s_red[w];
+                double rho = a.rho[kk];
+                // ll1 - ll0 (continuous.jl:477-483): integrated-intensity difference, log-intensity difference, prior
+                double delta = -a.W[kk] * a.Mn[p] + sum + (log(rho) - log(1.0 - rho));
+                double p1 = delta >= 0.0 ? 1.0 / (1.0 + exp(-delta)) : exp(delta) / (1.0 + exp(delta));
+                if (delta != delta) { atomicOr(a.flag, 64); p1 = 0.0; }
+                double uu = a.u ? a.u[kk] : philox_uniform(a.seed, (uint64_t)kk, a.counter);
+                double an = uu <= p1 ? 1.0 : 0.0;  // rand(Bernoulli(p)) = rand() <= p
+                a.A[kk] = an;
+                s_anew = an;
+            }
+            __syncthreads();
+            if (b1 > b0) {
+                const double an = s_anew;
+                for (int e = b0 + threadIdx.x; e < b1; e += blockDim.x) {
+                    int ii = ent_i[e];
+                    if (ii & 0x40000000) {
+                        ii &= 0x3fffffff;
+                        double g = gacc[ii], l = lam[ii];
+                        double base = a_old != 0.0 ? l - g : l;
+                        lam[ii] = an != 0.0 ? base + g : base;
+                        gacc[ii] = 0.0;
+                    }
+                }
+                __syncthreads();
+            }
+        }
+        __syncthreads();
+    }
+}
+
+// per-column entry totals: colcount[c_i] += window length of event i
+__global__ void k_adj_count(const double *__restrict__ t, const int *__restrict__ c, int64_t n, double horizon, unsigned long long *__restrict__ colcount) {
+    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    int lo = lo_of_event(t, i, horizon);
+    if (i > lo) atomicAdd(&colcount[c[i]], (unsigned long long)(i - lo));
+}
+
+__global__ void k_iota(int *v, int64_t n) {
+    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) v[i] = (int)i;
+}
+__global__ void k_node_ptr(const double *__restrict__ Mn, int K, int *__restrict__ ptr) {
+    if (threadIdx.x == 0 && blockIdx.x == 0) {
+        int run = 0;
+        for (int k = 0; k < K; k++) { ptr[k] = run; run += (int)Mn[k]; }
+        ptr[K] = run;
+    }
+}
+
+// table without the adjacency factor (the sampler needs W h for both values of A[p,c])
+__global__ void k_table_noA_ln(int K, const double *__restrict__ W, const double *__restrict__ mu, const double *__restrict__ tau, double D, EntryLN *__restrict__ table) {
+    int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (e >= (int64_t)K * K) return;
+    int cc = (int)(e / K), p = (int)(e % K);
+    int64_t src = p + (int64_t)K * cc;
+    double tt = tau[src];
+    EntryLN en;
+    en.cf = W[src] * sqrt(tt) * NHP_INVSQRT2PI * (D * D); en.mu = mu[src]; en.h = 0.5 * tt; en.pad = 0.0;
+    table[e] = en;
+}
+__global__ void k_table_noA_ex(int K, const double *__restrict__ W, const double *__restrict__ theta, EntryEX *__restrict__ table) {
+    int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (e >= (int64_t)K * K) return;
+    int cc = (int)(e / K), p = (int)(e % K);
+    int64_t src = p + (int64_t)K * cc;
+    EntryEX en;
+    en.theta = theta[src]; en.wt = W[src] * en.theta;
+    table[e] = en;
+}
+
+extern "C" int nhp_cont_resample_adjacency(nhp_ctx *ctx, nhp_events *ev, const double *rho, uint64_t seed, uint64_t counter, const double *u,
+                                           double *A_inout) {
+    NHP_CHECK(ctx, ctx != nullptr, NHP_ERR_INVALID, "ctx is NULL");
+    NHP_CHECK(ctx, ctx->cont_set, NHP_ERR_STATE, "continuous parameters not set (call nhp_cont_params_set)");
+    NHP_CHECK(ctx, ev != nullptr && ev->K == ctx->K, NHP_ERR_INVALID, "nhp_cont_resample_adjacency: bad events handle");
+    NHP_CHECK(ctx, rho && A_inout, NHP_ERR_INVALID, "nhp_cont_resample_adjacency: NULL rho/A");
+    NHP_CHECK(ctx, ev->n_halo == 0 && ev->index_base == 0, NHP_ERR_UNSUPPORTED,
+              "nhp_cont_resample_adjacency works on unsharded data (multi-GPU partitions the columns, not the time axis)");
+    NHP_CUDA(ctx, cudaSetDevice(ctx->device));
+    NHP_CUDA(ctx, fast_tables_upload(ctx->stream));
+    const int64_t K = ctx->K, KK = K * K, n = ev->n;
+    cudaStream_t s = ctx->stream;
+    double horizon = nhp_cont_horizon_value(ctx, n, 0);
+    // ---- device buffers (freed at the end; the sampler is called once per Gibbs sweep)
+    double *d_rho = nullptr, *d_u = nullptr, *d_A = nullptr;
+    void *d_tw = nullptr, *d_sort = nullptr;
+    int *d_keys = nullptr, *d_vals = nullptr, *d_order = nullptr, *d_ptr = nullptr, *d_ckeys = nullptr;
+    unsigned long long *d_cc = nullptr;
+    int *d_ent_i = nullptr; double *d_ent_v = nullptr, *d_lam = nullptr, *d_gacc = nullptr;
+    auto fin = [&](int rc) {
+        cudaStreamSynchronize(s);
+        cudaFree(d_rho); cudaFree(d_u); cudaFree(d_A); cudaFree(d_tw); cudaFree(d_sort); cudaFree(d_keys); cudaFree(d_vals); cudaFree(d_order);
+        cudaFree(d_ptr); cudaFree(d_ckeys); cudaFree(d_cc); cudaFree(d_ent_i); cudaFree(d_ent_v); cudaFree(d_lam); cudaFree(d_gacc);
+        return rc;
+    };
+#define ADJ_CUDA(call) do { cudaError_t e__ = (call); if (e__ != cudaSuccess) return fin(nhp_fail(ctx, NHP_ERR_CUDA, "%s failed: %s", #call, cudaGetErrorString(e__))); } while (0)
+    ADJ_CUDA(cudaMalloc(&d_rho, KK * sizeof(double)));
+    ADJ_CUDA(cudaMalloc(&d_A, KK * sizeof(double)));
+    ADJ_CUDA(cudaMalloc(&d_tw, KK * sizeof(EntryLN)));
+    ADJ_CUDA(cudaMalloc(&d_ptr, (K + 1) * sizeof(int)));
+    ADJ_CUDA(cudaMalloc(&d_cc, K * sizeof(unsigned long long)));
+    ADJ_CUDA(cudaMemcpyAsync(d_rho, rho, KK * sizeof(double), cudaMemcpyHostToDevice, s));
+    ADJ_CUDA(cudaMemcpyAsync(d_A, A_inout, KK * sizeof(double), cudaMemcpyHostToDevice, s));
+    if (u) { ADJ_CUDA(cudaMalloc(&d_u, KK * sizeof(double))); ADJ_CUDA(cudaMemcpyAsync(d_u, u, KK * sizeof(double), cudaMemcpyHostToDevice, s)); }
+    unsigned kb = (unsigned)((KK + 255) / 256);
+    if (ctx->kind == NHP_LOGITNORMAL) k_table_noA_ln<<<kb, 256, 0, s>>>((int)K, ctx->d_W, ctx->d_p1, ctx->d_p2, ctx->dtmax, (EntryLN *)d_tw);
+    else k_table_noA_ex<<<kb, 256, 0, s>>>((int)K, ctx->d_W, ctx->d_p1, (EntryEX *)d_tw);
+    NHP_LAUNCHED(ctx);
+    ADJ_CUDA(cudaMemsetAsync(ctx->d_flag, 0, sizeof(int), s));
+    int64_t max_entries = 0, max_col = 0;
+    if (n > 0) {
+        // ---- child events grouped by node, time order kept (stable radix sort of (node, index))
+        ADJ_CUDA(cudaMalloc(&d_vals, n * sizeof(int)));
+        ADJ_CUDA(cudaMalloc(&d_order, n * sizeof(int)));
+        ADJ_CUDA(cudaMalloc(&d_ckeys, n * sizeof(int)));
+        k_iota<<<(unsigned)((n + 255) / 256), 256, 0, s>>>(d_vals, n);
+        NHP_LAUNCHED(ctx);
+        size_t tmp_bytes = 0;
+        int bits = 1;
+        while ((1 << bits) < K) bits++;
+        cub::DeviceRadixSort::SortPairs(nullptr, tmp_bytes, ev->d_c, d_ckeys, d_vals, d_order, (int)n, 0, bits, s);
+        ADJ_CUDA(cudaMalloc(&d_sort, tmp_bytes));
+        ADJ_CUDA(cub::DeviceRadixSort::SortPairs(d_sort, tmp_bytes, ev->d_c, d_ckeys, d_vals, d_order, (int)n, 0, bits, s));
+        NHP_LAUNCHED(ctx);
+        ADJ_CUDA(cudaMemsetAsync(d_cc, 0, K * sizeof(unsigned long long), s));
+        k_adj_count<<<(unsigned)((n + 255) / 256), 256, 0, s>>>(ev->d_t, ev->d_c, n, horizon, d_cc);
+        NHP_LAUNCHED(ctx);
+        std::vector<unsigned long long> cc(K);
+        std::vector<double> mn(K);
+        ADJ_CUDA(cudaMemcpyAsync(cc.data(), d_cc, K * sizeof(unsigned long long), cudaMemcpyDeviceToHost, s));
+        ADJ_CUDA(cudaMemcpyAsync(mn.data(), ev->d_Mn, K * sizeof(double), cudaMemcpyDeviceToHost, s));
+        ADJ_CUDA(cudaStreamSynchronize(s));
+        for (int64_t k = 0; k < K; k++) { max_entries = std::max<int64_t>(max_entries, (int64_t)cc[k]); max_col = std::max<int64_t>(max_col, (int64_t)mn[k]); }
+        if (max_entries >= (int64_t)0x3fffffff) return fin(nhp_fail(ctx, NHP_ERR_UNSUPPORTED, "adjacency sampler: a column has %lld window entries (limit 2^30)", (long long)max_entries));
+    }
+    k_node_ptr<<<1, 32, 0, s>>>(ev->d_Mn, (int)K, d_ptr);
+    NHP_LAUNCHED(ctx);
+    int grid = (int)std::min<int64_t>(K, (int64_t)ctx->sm_count * 2);
+    // bound the scratch area: entries cost 12 B per CTA slot
+    size_t free_b = 0, total_b = 0;
+    cudaMemGetInfo(&free_b, &total_b);
+    int64_t cap = std::max<int64_t>(max_entries, 1), mc = std::max<int64_t>(max_col, 1);
+    while (grid > 1 && (size_t)grid * ((size_t)cap * 12 + (size_t)mc * 16) > free_b / 2) grid = (grid + 1) / 2;
+    if ((size_t)grid * ((size_t)cap * 12 + (size_t)mc * 16) > free_b / 2)
+        return fin(nhp_fail(ctx, NHP_ERR_UNSUPPORTED, "adjacency sampler: one column needs %lld window entries, more than the free device memory holds", (long long)cap));
+    ADJ_CUDA(cudaMalloc(&d_ent_i, (size_t)grid * cap * sizeof(int)));
+    ADJ_CUDA(cudaMalloc(&d_ent_v, (size_t)grid * cap * sizeof(double)));
+    ADJ_CUDA(cudaMalloc(&d_lam, (size_t)grid * mc * sizeof(double)));
+    ADJ_CUDA(cudaMalloc(&d_gacc, (size_t)grid * mc * sizeof(double)));
+    AdjArgs a;
+    a.t = ev->d_t; a.c = ev->d_c; a.n = n; a.order = d_order; a.node_ptr = d_ptr; a.Mn = ev->d_Mn; a.K = (int)K; a.table_w = d_tw;
+    a.lambda0 = ctx->d_lambda0; a.W = ctx->d_W; a.A = d_A; a.rho = d_rho; a.u = d_u; a.seed = seed; a.counter = counter;
+    a.D = ctx->dtmax; a.horizon = horizon; a.duration = ev->duration; a.cap = cap; a.ent_i = d_ent_i; a.ent_v = d_ent_v; a.lam = d_lam; a.gacc = d_gacc;
+    a.max_col = mc; a.flag = ctx->d_flag;
+    size_t smem = (size_t)(2 * K + 2) * sizeof(int);
+    int rc = nhp_timer_begin(ctx);
+    if (rc != NHP_OK) return fin(rc);
+    if (ctx->kind == NHP_LOGITNORMAL) {
+        if (smem > 48 * 1024) ADJ_CUDA(cudaFuncSetAttribute(k_adjacency<NHP_LOGITNORMAL>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        k_adjacency<NHP_LOGITNORMAL><<<grid, 256, smem, s>>>(a);
+    } else {
+        if (smem > 48 * 1024) ADJ_CUDA(cudaFuncSetAttribute(k_adjacency<NHP_EXPONENTIAL>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        k_adjacency<NHP_EXPONENTIAL><<<grid, 256, smem, s>>>(a);
+    }
+    NHP_LAUNCHED(ctx);
+    ADJ_CUDA(cudaGetLastError());
+    int flag = 0;
+    ADJ_CUDA(cudaMemcpyAsync(&flag, ctx->d_flag, sizeof(int), cudaMemcpyDeviceToHost, s));
+    rc = nhp_timer_end(ctx);
+    if (rc != NHP_OK) return fin(rc);
+    if (flag & 32) return fin(nhp_fail(ctx, NHP_ERR_CUDA, "adjacency sampler: scratch overflow (internal error)"));
+    if (flag & 64) return fin(nhp_fail(ctx, NHP_ERR_NUMERIC, "adjacency sampler: NaN log-likelihood difference"));
+    ADJ_CUDA(cudaMemcpyAsync(A_inout, d_A, KK * sizeof(double), cudaMemcpyDeviceToHost, s));
+    ADJ_CUDA(cudaStreamSynchronize(s));
+#undef ADJ_CUDA
+    fin(NHP_OK);
+    // the new adjacency becomes the context's A: rebuild the masked tables
+    std::vector<double> l0(K);
+    NHP_CUDA(ctx, cudaMemcpy(l0.data(), ctx->d_lambda0, K * sizeof(double), cudaMemcpyDeviceToHost));
+    if (ctx->has_A) {
+        std::vector<double> W(KK), p1(KK), p2(KK);
+        NHP_CUDA(ctx, cudaMemcpy(W.data(), ctx->d_W, KK * sizeof(double), cudaMemcpyDeviceToHost));
+        NHP_CUDA(ctx, cudaMemcpy(p1.data(), ctx->d_p1, KK * sizeof(double), cudaMemcpyDeviceToHost));
+        if (ctx->kind == NHP_LOGITNORMAL) NHP_CUDA(ctx, cudaMemcpy(p2.data(), ctx->d_p2, KK * sizeof(double), cudaMemcpyDeviceToHost));
+        return nhp_cont_params_set(ctx, ctx->kind, K, l0.data(), W.data(), A_inout, p1.data(), ctx->kind == NHP_LOGITNORMAL ? p2.data() : nullptr, ctx->dtmax);
+    }
+    return NHP_OK;
+}

@@ -69,7 +69,7 @@ int nhp_cont_prepare_windows(nhp_ctx *ctx, nhp_events *ev, double horizon) {
 // log-likelihood / intensity sweep
 // ---------------------------------------------------------------------------------------
 template <int KIND, int G, int MODE, bool ST>
-__device__ __forceinline__ void sweep_body(const SweepArgs &a, const Tile &tl, double &sum_log, double &sum_row) {
+__device__ __forceinline__ void sweep_body(const SweepArgs &a, const Tile &tl, const FastTables *ft, double &sum_log, double &sum_row) {
     typedef typename EntryOf<KIND>::type E;
     constexpr int NG = NHP_BLOCK / G;
     const int gid = threadIdx.x / G, gl = threadIdx.x % G;
@@ -85,7 +85,7 @@ __device__ __forceinline__ void sweep_body(const SweepArgs &a, const Tile &tl, d
             double tj = tile_T<ST>(a, tl, j);
             if (!(tj > thr)) break;  // events[parentindex] > time - dtmax   (continuous.jl:291)
             int cj = tile_C<ST>(a, tl, j);
-            acc += pair_value(load_entry(col + cj), ti - tj, a.D);
+            acc += pair_value(load_entry(col + cj), ti - tj, a.D, ft);
         }
         acc = group_sum<G>(acc, gmask);
         if (gl == 0) {
@@ -100,10 +100,13 @@ template <int KIND, int G, int MODE>
 __global__ void __launch_bounds__(NHP_BLOCK) k_sweep(const SweepArgs a) {
     extern __shared__ __align__(128) unsigned char smem[];
     __shared__ double red[16];
+    __shared__ FastTables s_ft;
+    fast_tables_load(&s_ft);
+    __syncthreads();
     Tile tl = stage_tile(a, smem);
     double sum_log = 0.0, sum_row = 0.0;
-    if (tl.staged) sweep_body<KIND, G, MODE, true>(a, tl, sum_log, sum_row);
-    else sweep_body<KIND, G, MODE, false>(a, tl, sum_log, sum_row);
+    if (tl.staged) sweep_body<KIND, G, MODE, true>(a, tl, &s_ft, sum_log, sum_row);
+    else sweep_body<KIND, G, MODE, false>(a, tl, &s_ft, sum_log, sum_row);
     if (MODE == MODE_LOGLIK) {
         block_sum2(sum_log, sum_row, red);
         if (threadIdx.x == 0) { a.partials[2 * (size_t)blockIdx.x] = sum_log; a.partials[2 * (size_t)blockIdx.x + 1] = sum_row; }
@@ -129,7 +132,7 @@ __global__ void k_reduce_partials(const double *__restrict__ partials, int64_t n
 // one uniform per event, inverse-cdf walk in that order; fused statistics.
 // ---------------------------------------------------------------------------------------
 template <int KIND, int G, int R, bool ST>
-__device__ __forceinline__ void parents_body(const SweepArgs &a, const Tile &tl) {
+__device__ __forceinline__ void parents_body(const SweepArgs &a, const Tile &tl, const FastTables *ft) {
     typedef typename EntryOf<KIND>::type E;
     constexpr int NG = NHP_BLOCK / G;
     const int gid = threadIdx.x / G, gl = threadIdx.x % G;
@@ -151,7 +154,7 @@ __device__ __forceinline__ void parents_body(const SweepArgs &a, const Tile &tl)
             double v = 0.0;
             if (j >= jlo) {
                 double tj = tile_T<ST>(a, tl, j);
-                if (tj > thr) v = pair_value(load_entry(col + tile_C<ST>(a, tl, j)), ti - tj, a.D);
+                if (tj > thr) v = pair_value(load_entry(col + tile_C<ST>(a, tl, j)), ti - tj, a.D, ft);
             }
             vc[r] = v;
             acc += v;
@@ -160,7 +163,7 @@ __device__ __forceinline__ void parents_body(const SweepArgs &a, const Tile &tl)
         for (; j >= jlo; j -= G) {
             double tj = tile_T<ST>(a, tl, j);
             if (!(tj > thr)) break;
-            acc += pair_value(load_entry(col + tile_C<ST>(a, tl, j)), ti - tj, a.D);
+            acc += pair_value(load_entry(col + tile_C<ST>(a, tl, j)), ti - tj, a.D, ft);
         }
         const double lam0 = __ldg(a.lambda0 + ci);
         const double S = group_sum<G>(acc, gmask) + lam0;  // sum([weights...; baseline])
@@ -187,7 +190,7 @@ __device__ __forceinline__ void parents_body(const SweepArgs &a, const Tile &tl)
                 double v = 0.0;
                 if (jj >= jlo) {
                     double tj = tile_T<ST>(a, tl, jj);
-                    if (tj > thr) v = pair_value(load_entry(col + tile_C<ST>(a, tl, jj)), ti - tj, a.D);
+                    if (tj > thr) v = pair_value(load_entry(col + tile_C<ST>(a, tl, jj)), ti - tj, a.D, ft);
                 }
                 double x = group_incl_scan<G>(v, gmask, gl);
                 unsigned b = (__ballot_sync(gmask, carry + x > target) >> gshift) & (G == 32 ? 0xffffffffu : ((1u << G) - 1u));
@@ -214,9 +217,12 @@ __device__ __forceinline__ void parents_body(const SweepArgs &a, const Tile &tl)
 template <int KIND, int G, int R>
 __global__ void __launch_bounds__(NHP_BLOCK) k_parents(const SweepArgs a) {
     extern __shared__ __align__(128) unsigned char smem[];
+    __shared__ FastTables s_ft;
+    fast_tables_load(&s_ft);
+    __syncthreads();
     Tile tl = stage_tile(a, smem);
-    if (tl.staged) parents_body<KIND, G, R, true>(a, tl);
-    else parents_body<KIND, G, R, false>(a, tl);
+    if (tl.staged) parents_body<KIND, G, R, true>(a, tl, &s_ft);
+    else parents_body<KIND, G, R, false>(a, tl, &s_ft);
 }
 
 // ---------------------------------------------------------------------------------------
@@ -379,6 +385,7 @@ static int fill_args(nhp_ctx *ctx, nhp_events *ev, int recursive, SweepArgs &a, 
     bool rec = recursive && ctx->kind == NHP_EXPONENTIAL;
     double horizon = nhp_cont_horizon_value(ctx, ev->index_base + ev->n, rec);
     NHP_TRY(nhp_cont_prepare_windows(ctx, ev, horizon));
+    NHP_CUDA(ctx, fast_tables_upload(ctx->stream));
     p = make_plan(ctx, ev);
     a.t = ev->d_t; a.c = ev->d_c; a.n = ev->n; a.first = ev->n_halo; a.index_base = ev->index_base;
     a.jmin = rec ? ev->n_t0 : 0;

@@ -47,6 +47,7 @@ extern "C" int nhp_create(int device, nhp_ctx **out) {
         delete ctx;
         return rc;
     }
+    ctx->own_stream = ctx->stream;
     cudaMemsetAsync(ctx->d_flag, 0, sizeof(int), ctx->stream);
     *out = ctx;
     return NHP_OK;
@@ -69,8 +70,16 @@ extern "C" int nhp_destroy(nhp_ctx *ctx) {
     cudaFree(ctx->d_partials); cudaFree(ctx->d_scratch); cudaFree(ctx->d_flag); cudaFree(ctx->d_winstat);
     cudaFree(ctx->dd_lambda0); cudaFree(ctx->dd_W); cudaFree(ctx->dd_A); cudaFree(ctx->dd_theta); cudaFree(ctx->dd_bump);
     cudaEventDestroy(ctx->ev0); cudaEventDestroy(ctx->ev1);
-    cudaStreamDestroy(ctx->stream);
+    cudaStreamDestroy(ctx->own_stream);
     delete ctx;
+    return NHP_OK;
+}
+
+extern "C" int nhp_set_stream(nhp_ctx *ctx, void *cuda_stream) {
+    NHP_CHECK(ctx, ctx != nullptr, NHP_ERR_INVALID, "ctx is NULL");
+    NHP_CUDA(ctx, cudaSetDevice(ctx->device));
+    NHP_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    ctx->stream = cuda_stream ? (cudaStream_t)cuda_stream : ctx->own_stream;
     return NHP_OK;
 }
 

@@ -6,6 +6,7 @@
 #include <string>
 #include <vector>
 #include "../../include/nhp.h"
+#include "fastmath.cuh"
 
 #define NHP_VERSION 100
 
@@ -93,6 +94,7 @@ struct nhp_disc {
 struct nhp_ctx {
     int device = 0;
     cudaStream_t stream = nullptr;
+    cudaStream_t own_stream = nullptr;
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
     std::string err;
     int64_t launches = 0;
@@ -176,18 +178,19 @@ __host__ __device__ inline double philox_uniform(uint64_t seed, uint64_t index, 
 }
 
 #ifdef __CUDACC__
-__device__ __forceinline__ double pair_value(const EntryLN &e, double dt, double D) {
+__device__ __forceinline__ double pair_value(const EntryLN &e, double dt, double D, const FastTables *ft) {
     // Distributions.pdf(LogitNormal(mu, tau^-1/2), dt/D): zero outside 0 < x < 1 (impulses.jl:174-178)
+    //   = cf exp(-h (z - mu)^2 - log dt - log(D - dt)),  z = log dt - log(D - dt),  cf carries D^2
     if (!(dt > 0.0 && dt < D)) return 0.0;
-    double inv = 1.0 / (dt * (D - dt));
-    double z = log(dt * dt * inv);
-    double dz = z - e.mu;
-    return e.cf * exp(-e.h * dz * dz) * inv;
+    double la = fast_log(dt, ft), lb = fast_log(D - dt, ft);
+    double dz = (la - lb) - e.mu;
+    double hd = e.h * dz;
+    return e.cf * fast_exp(fma(-hd, dz, -(la + lb)), ft);
 }
-__device__ __forceinline__ double pair_value(const EntryEX &e, double dt, double) {
+__device__ __forceinline__ double pair_value(const EntryEX &e, double dt, double, const FastTables *ft) {
     // Distributions.pdf(Exponential(1/theta), dt): theta exp(-theta dt), zero for dt < 0 (impulses.jl:106-108)
     if (dt < 0.0) return 0.0;
-    return e.wt * exp(-e.theta * dt);
+    return e.wt * fast_exp(-e.theta * dt, ft);
 }
 // log_duration(parent, child, dtmax)  impulses.jl:228
 __device__ __forceinline__ double log_duration_dev(double dt, double D) { return log(dt / (D - dt)); }

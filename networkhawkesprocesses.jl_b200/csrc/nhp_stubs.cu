@@ -5,8 +5,6 @@
 #define NHP_STUB(name, ...)                                                                          \
     extern "C" int name(__VA_ARGS__) { return nhp_fail(ctx, NHP_ERR_UNSUPPORTED, #name ": not implemented in this build"); }
 
-NHP_STUB(nhp_cont_intensity, nhp_ctx *ctx, nhp_events *, const double *, int64_t, double *)
-NHP_STUB(nhp_cont_resample_adjacency, nhp_ctx *ctx, nhp_events *, const double *, uint64_t, uint64_t, const double *, double *)
 NHP_STUB(nhp_disc_upload, nhp_ctx *ctx, const int64_t *, int64_t, int64_t, int64_t, nhp_disc **)
 NHP_STUB(nhp_disc_free, nhp_ctx *ctx, nhp_disc *)
 NHP_STUB(nhp_disc_convolve, nhp_ctx *ctx, nhp_disc *, const double *, int64_t, int64_t, double *)

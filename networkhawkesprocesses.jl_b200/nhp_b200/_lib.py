@@ -23,6 +23,9 @@ PROTOTYPES = {
     "nhp_version": (c_int, []),
     "nhp_launch_count": (c_int64, [c_void_p]),
     "nhp_last_kernel_ms": (c_double, [c_void_p]),
+    "nhp_set_stream": (c_int, [c_void_p, c_void_p]),
+    "nhp_bench_fp64": (c_int, [c_void_p, c_int, c_double_p]),
+    "nhp_test_fastmath": (c_int, [c_void_p, c_int, c_void_p, c_int64, c_void_p]),
     "nhp_events_upload": (c_int, [c_void_p, c_void_p, c_void_p, c_int64, c_double, c_int64, c_int64, c_int64, c_int, POINTER(c_void_p)]),
     "nhp_events_free": (c_int, [c_void_p, c_void_p]),
     "nhp_events_count": (c_int64, [c_void_p]),

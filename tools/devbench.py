@@ -46,6 +46,10 @@ def run(name, K, n, rate, density, kind="ln", reps=5, G=None):
 
 if __name__ == "__main__":
     which = sys.argv[1] if len(sys.argv) > 1 else "all"
+    if which == "one":  # one K n rate density [kind] [reps]
+        K, n, rate = int(sys.argv[2]), int(float(sys.argv[3])), float(sys.argv[4])
+        dens = None if sys.argv[5] == "none" else float(sys.argv[5])
+        run("one", K, n, rate, dens, kind=sys.argv[6] if len(sys.argv) > 6 else "ln", reps=int(sys.argv[7]) if len(sys.argv) > 7 else 2)
     if which in ("all", "g"):
         for G in (1, 2, 4, 8, 16, 32):
             run("cfg2 LN std K=50", 50, 1_000_000, 100.0, None, G=G)
