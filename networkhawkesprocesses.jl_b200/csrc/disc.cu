@@ -1,0 +1,797 @@
+// disc.cu -- discrete-time path (discrete.jl, parents.jl:82-177, impulses.jl:310-371, weights.jl:70-91,
+// baselines.jl:402-456).
+//
+// Device layout: counts d_data[t*N + n] (int32; same order as Julia's data[n + N*t]); the
+// convolution is kept as convT[t*(N*B) + p*B + b] (the (p,b) axis contiguous) so that the
+// contraction  lambda = conv * bump  is a row-major GEMM and the Gibbs / VB / adjacency consumers
+// read one contiguous row per non-zero bin.  The reference's dense T x N x (1+N*B) `parents` / `u`
+// arrays (1.9 TB at config 3) are never materialised: every downstream statistic is weighted by
+// data[c,t], so only the ~4 % non-zero bins are visited (CSR by child node, built at upload).
+#include "nhp_internal.cuh"
+#include <cub/cub.cuh>
+#include <algorithm>
+
+struct DiscExtra {  // hangs off nhp_disc (kept here so the public struct stays small)
+    int64_t nnz = 0;
+    int *nz_t = nullptr;        // [nnz] time bin, grouped by child, time order inside a child
+    int *nz_s = nullptr;        // [nnz] count
+    int64_t *nz_off = nullptr;  // [nnz] index of the bin's first uniform ((t outer, c inner, draw) order)
+    int *child_ptr = nullptr;   // [N+1]
+    double *rowsum = nullptr;   // [N] sum_t data[p,t] over own bins
+    double *phi = nullptr;      // [L*B]
+    double *csum = nullptr;     // [N*B] sum over own bins of convT[:, k]
+};
+static DiscExtra *extra_of(nhp_disc *dd) { return reinterpret_cast<DiscExtra *>(dd->d_scan); }
+
+#define DCUDA(ctx, call) NHP_CUDA(ctx, call)
+
+__device__ __forceinline__ double warp_sum_d(double v) {
+#pragma unroll
+    for (int d = 16; d >= 1; d >>= 1) v += __shfl_xor_sync(0xffffffffu, v, d);
+    return v;
+}
+
+// ---------------------------------------------------------------------------------------
+// upload
+// ---------------------------------------------------------------------------------------
+__global__ void k_disc_ingest(const int64_t *__restrict__ src, int *__restrict__ dst, int64_t total, int *flag) {
+    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= total) return;
+    int64_t v = src[i];
+    if (v < 0 || v > 2147483647) atomicOr(flag, 1);
+    dst[i] = (int)v;
+}
+__global__ void k_disc_flags(const int *__restrict__ data, int64_t total, int64_t first, unsigned char *__restrict__ flags, int64_t *__restrict__ cnt64) {
+    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= total) return;
+    int v = i >= first ? data[i] : 0;
+    flags[i] = v > 0;
+    cnt64[i] = v;
+}
+__global__ void k_disc_gather(const int64_t *__restrict__ idx, const int64_t *__restrict__ scan, const int *__restrict__ data, int64_t nnz, int N,
+                              int *__restrict__ key_c, int *__restrict__ pos) {
+    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= nnz) return;
+    key_c[i] = (int)(idx[i] % N);
+    pos[i] = (int)i;
+}
+__global__ void k_disc_fill(const int *__restrict__ pos_sorted, const int *__restrict__ key_sorted, const int64_t *__restrict__ idx, const int64_t *__restrict__ scan,
+                            const int *__restrict__ data, int64_t nnz, int N, int *__restrict__ nz_t, int *__restrict__ nz_s, int64_t *__restrict__ nz_off,
+                            int *__restrict__ child_cnt) {
+    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= nnz) return;
+    int64_t lin = idx[pos_sorted[i]];
+    nz_t[i] = (int)(lin / N);
+    nz_s[i] = data[lin];
+    nz_off[i] = scan[lin];
+    atomicAdd(&child_cnt[key_sorted[i] + 1], 1);
+}
+__global__ void k_disc_rowsum(const int *__restrict__ data, int N, int64_t T, int64_t t0, double *__restrict__ rowsum) {
+    // one block per slab of time bins; threads over nodes
+    for (int n = threadIdx.x; n < N; n += blockDim.x) {
+        long long s = 0;
+        for (int64_t t = t0 + blockIdx.x; t < T; t += gridDim.x) s += data[t * N + n];
+        if (s) atomicAdd(&rowsum[n], (double)s);
+    }
+}
+__global__ void k_prefix_small(int *v, int n) {
+    if (threadIdx.x == 0 && blockIdx.x == 0) {
+        int run = 0;
+        for (int i = 0; i <= n; i++) { run += v[i]; v[i] = run; }
+    }
+}
+
+extern "C" int nhp_disc_free(nhp_ctx *ctx, nhp_disc *dd) {
+    if (!dd) return NHP_OK;
+    if (ctx) { cudaSetDevice(ctx->device); cudaStreamSynchronize(ctx->stream); }
+    DiscExtra *ex = extra_of(dd);
+    if (ex) {
+        cudaFree(ex->nz_t); cudaFree(ex->nz_s); cudaFree(ex->nz_off); cudaFree(ex->child_ptr); cudaFree(ex->rowsum); cudaFree(ex->phi); cudaFree(ex->csum);
+        delete ex;
+    }
+    cudaFree(dd->d_data); cudaFree(dd->d_conv);
+    delete dd;
+    return NHP_OK;
+}
+
+extern "C" int nhp_disc_upload(nhp_ctx *ctx, const int64_t *data, int64_t N, int64_t T, int64_t t_halo, nhp_disc **out) {
+    NHP_CHECK(ctx, ctx != nullptr, NHP_ERR_INVALID, "ctx is NULL");
+    NHP_CHECK(ctx, out != nullptr && data != nullptr, NHP_ERR_INVALID, "nhp_disc_upload: NULL argument");
+    *out = nullptr;
+    NHP_CHECK(ctx, N >= 1 && N <= 32768 && T >= 1 && t_halo >= 0 && t_halo < T, NHP_ERR_INVALID, "nhp_disc_upload: bad dimensions N=%lld T=%lld t_halo=%lld", (long long)N, (long long)T, (long long)t_halo);
+    NHP_CHECK(ctx, N * T < (int64_t)2147483000, NHP_ERR_INVALID, "nhp_disc_upload: N*T must stay below 2^31 per handle (shard the time axis)");
+    DCUDA(ctx, cudaSetDevice(ctx->device));
+    cudaStream_t s = ctx->stream;
+    const int64_t total = N * T, first = t_halo * N;
+    nhp_disc *dd = new nhp_disc();
+    DiscExtra *ex = new DiscExtra();
+    dd->N = N; dd->T = T; dd->t_halo = t_halo; dd->d_scan = reinterpret_cast<int64_t *>(ex);
+    unsigned char *d_flags = nullptr; int64_t *d_cnt = nullptr, *d_scan = nullptr, *d_idx = nullptr, *d_nnz = nullptr; void *d_tmp = nullptr;
+    int *d_key = nullptr, *d_pos = nullptr, *d_key2 = nullptr, *d_pos2 = nullptr;
+    auto fin = [&](int rc) {
+        cudaStreamSynchronize(s);
+        cudaFree(d_flags); cudaFree(d_cnt); cudaFree(d_scan); cudaFree(d_idx); cudaFree(d_nnz); cudaFree(d_tmp); cudaFree(d_key); cudaFree(d_pos); cudaFree(d_key2); cudaFree(d_pos2);
+        if (rc != NHP_OK) nhp_disc_free(ctx, dd);
+        return rc;
+    };
+#define UP_CUDA(call) do { cudaError_t e__ = (call); if (e__ != cudaSuccess) return fin(nhp_fail(ctx, NHP_ERR_CUDA, "%s failed: %s", #call, cudaGetErrorString(e__))); } while (0)
+    void *scratch;
+    { int rc = nhp_scratch(ctx, (size_t)total * sizeof(int64_t), &scratch); if (rc != NHP_OK) return fin(rc); }
+    UP_CUDA(cudaMalloc(&dd->d_data, (size_t)total * sizeof(int)));
+    UP_CUDA(cudaMemcpyAsync(scratch, data, (size_t)total * sizeof(int64_t), cudaMemcpyHostToDevice, s));
+    UP_CUDA(cudaMemsetAsync(ctx->d_flag, 0, sizeof(int), s));
+    unsigned blocks = (unsigned)((total + 255) / 256);
+    k_disc_ingest<<<blocks, 256, 0, s>>>((const int64_t *)scratch, dd->d_data, total, ctx->d_flag);
+    NHP_LAUNCHED(ctx);
+    // non-zero bins (own bins only) in memory order + the running draw index
+    UP_CUDA(cudaMalloc(&d_flags, (size_t)total));
+    UP_CUDA(cudaMalloc(&d_cnt, (size_t)total * sizeof(int64_t)));
+    UP_CUDA(cudaMalloc(&d_scan, (size_t)total * sizeof(int64_t)));
+    UP_CUDA(cudaMalloc(&d_idx, (size_t)total * sizeof(int64_t)));
+    UP_CUDA(cudaMalloc(&d_nnz, 2 * sizeof(int64_t)));
+    k_disc_flags<<<blocks, 256, 0, s>>>(dd->d_data, total, first, d_flags, d_cnt);
+    NHP_LAUNCHED(ctx);
+    size_t tb1 = 0, tb2 = 0;
+    cub::DeviceScan::ExclusiveSum(nullptr, tb1, d_cnt, d_scan, (int)total, s);
+    cub::CountingInputIterator<int64_t> iota(0);
+    cub::DeviceSelect::Flagged(nullptr, tb2, iota, d_flags, d_idx, d_nnz, (int)total, s);
+    size_t tb = std::max(tb1, tb2);
+    UP_CUDA(cudaMalloc(&d_tmp, tb));
+    UP_CUDA(cub::DeviceScan::ExclusiveSum(d_tmp, tb, d_cnt, d_scan, (int)total, s));
+    UP_CUDA(cub::DeviceSelect::Flagged(d_tmp, tb, iota, d_flags, d_idx, d_nnz, (int)total, s));
+    NHP_LAUNCHED(ctx); NHP_LAUNCHED(ctx);
+    int64_t h_nnz = 0, h_last[2] = {0, 0};
+    int flag = 0;
+    UP_CUDA(cudaMemcpyAsync(&h_nnz, d_nnz, sizeof(int64_t), cudaMemcpyDeviceToHost, s));
+    UP_CUDA(cudaMemcpyAsync(&h_last[0], d_scan + total - 1, sizeof(int64_t), cudaMemcpyDeviceToHost, s));
+    UP_CUDA(cudaMemcpyAsync(&h_last[1], d_cnt + total - 1, sizeof(int64_t), cudaMemcpyDeviceToHost, s));
+    UP_CUDA(cudaMemcpyAsync(&flag, ctx->d_flag, sizeof(int), cudaMemcpyDeviceToHost, s));
+    UP_CUDA(cudaStreamSynchronize(s));
+    if (flag & 1) return fin(nhp_fail(ctx, NHP_ERR_INVALID, "nhp_disc_upload: counts must be in [0, 2^31)"));
+    if (h_nnz >= (int64_t)2147483000) return fin(nhp_fail(ctx, NHP_ERR_INVALID, "nhp_disc_upload: too many non-zero bins"));
+    ex->nnz = h_nnz;
+    dd->total_events = h_last[0] + h_last[1];
+    UP_CUDA(cudaMalloc(&ex->child_ptr, (size_t)(N + 1) * sizeof(int)));
+    UP_CUDA(cudaMemsetAsync(ex->child_ptr, 0, (size_t)(N + 1) * sizeof(int), s));
+    UP_CUDA(cudaMalloc(&ex->rowsum, (size_t)N * sizeof(double)));
+    UP_CUDA(cudaMemsetAsync(ex->rowsum, 0, (size_t)N * sizeof(double), s));
+    k_disc_rowsum<<<(unsigned)std::min<int64_t>(T - t_halo, 1024), 128, 0, s>>>(dd->d_data, (int)N, T, t_halo, ex->rowsum);
+    NHP_LAUNCHED(ctx);
+    if (h_nnz > 0) {
+        UP_CUDA(cudaMalloc(&d_key, (size_t)h_nnz * sizeof(int))); UP_CUDA(cudaMalloc(&d_pos, (size_t)h_nnz * sizeof(int)));
+        UP_CUDA(cudaMalloc(&d_key2, (size_t)h_nnz * sizeof(int))); UP_CUDA(cudaMalloc(&d_pos2, (size_t)h_nnz * sizeof(int)));
+        UP_CUDA(cudaMalloc(&ex->nz_t, (size_t)h_nnz * sizeof(int))); UP_CUDA(cudaMalloc(&ex->nz_s, (size_t)h_nnz * sizeof(int)));
+        UP_CUDA(cudaMalloc(&ex->nz_off, (size_t)h_nnz * sizeof(int64_t)));
+        unsigned nb = (unsigned)((h_nnz + 255) / 256);
+        k_disc_gather<<<nb, 256, 0, s>>>(d_idx, d_scan, dd->d_data, h_nnz, (int)N, d_key, d_pos);
+        NHP_LAUNCHED(ctx);
+        int bits = 1;
+        while ((1 << bits) < N) bits++;
+        size_t tb3 = 0;
+        cub::DeviceRadixSort::SortPairs(nullptr, tb3, d_key, d_key2, d_pos, d_pos2, (int)h_nnz, 0, bits, s);
+        if (tb3 > tb) { cudaFree(d_tmp); d_tmp = nullptr; UP_CUDA(cudaMalloc(&d_tmp, tb3)); tb = tb3; }
+        UP_CUDA(cub::DeviceRadixSort::SortPairs(d_tmp, tb3, d_key, d_key2, d_pos, d_pos2, (int)h_nnz, 0, bits, s));  // stable: time order kept per child
+        NHP_LAUNCHED(ctx);
+        k_disc_fill<<<nb, 256, 0, s>>>(d_pos2, d_key2, d_idx, d_scan, dd->d_data, h_nnz, (int)N, ex->nz_t, ex->nz_s, ex->nz_off, ex->child_ptr);
+        NHP_LAUNCHED(ctx);
+    }
+    k_prefix_small<<<1, 32, 0, s>>>(ex->child_ptr, (int)N);
+    NHP_LAUNCHED(ctx);
+    UP_CUDA(cudaGetLastError());
+#undef UP_CUDA
+    int rc = fin(NHP_OK);
+    if (rc == NHP_OK) *out = dd;
+    return rc;
+}
+
+// ---------------------------------------------------------------------------------------
+// basis (host; impulses.jl:321-335) and convolution (discrete.jl:146-151)
+// ---------------------------------------------------------------------------------------
+extern "C" int nhp_disc_basis(int64_t L, int64_t B, double dt, double *phi) {
+    if (L < 1 || B < 1 || !phi || !(dt > 0.0)) return NHP_ERR_INVALID;
+    double sigma = (double)L / (double)(B - 1);
+    for (int64_t b = 0; b < B; b++) {
+        // means: LinRange(1, L, B+2)[2:end-1] when B < L, else LinRange(1, L, B)
+        int64_t len = B < L ? B + 2 : B, j = B < L ? b + 1 : b;
+        double tt = len == 1 ? 0.0 : (double)j / (double)(len - 1);
+        double mu = len == 1 ? 1.0 : (1.0 - tt) * 1.0 + tt * (double)L;
+        double s = 0.0;
+        for (int64_t l = 0; l < L; l++) {
+            double d = (double)(l + 1) - mu;
+            double v = exp(-1.0 / 2.0 * (1.0 / sigma) / 2.0 * (d * d));  // exp(-1/2 * sigma^-1 / 2 * (lag - mu)^2)
+            phi[l + L * b] = v;
+            s += v;
+        }
+        for (int64_t l = 0; l < L; l++) phi[l + L * b] = phi[l + L * b] / (s * dt);
+    }
+    return NHP_OK;
+}
+
+// convT[t][p*B + b] = max(0, sum_{l=1..L, t-l>=0} phi[l-1 + L*b] * data[t-l][p]); lags ascending as in the FIR restatement
+__global__ void __launch_bounds__(256) k_convolve(const int *__restrict__ data, int N, int64_t T, const double *__restrict__ phi, int L, int B,
+                                                  double *__restrict__ convT) {
+    extern __shared__ double s_phi[];
+    for (int i = threadIdx.x; i < L * B; i += blockDim.x) s_phi[i] = phi[i];
+    __syncthreads();
+    const int NB = N * B;
+    for (int64_t t = blockIdx.x; t < T; t += gridDim.x) {
+        for (int k = threadIdx.x; k < NB; k += blockDim.x) {
+            int p = k / B, b = k - p * B;
+            double s = 0.0;
+            for (int l = 1; l <= L; l++) {
+                if (t - l < 0) break;
+                int v = __ldg(data + (t - l) * N + p);
+                if (v) s += s_phi[(l - 1) + L * b] * (double)v;
+            }
+            convT[t * NB + k] = s > 0.0 ? s : 0.0;
+        }
+    }
+}
+// Julia layout export: out[t + T*(n + N*b)] = convT[t][n*B + b]   (tiled transpose)
+__global__ void k_conv_export(const double *__restrict__ convT, int N, int B, int64_t T, double *__restrict__ out) {
+    __shared__ double tile[32][33];
+    const int NB = N * B;
+    int64_t t0 = (int64_t)blockIdx.x * 32;
+    int k0 = blockIdx.y * 32;
+    for (int r = threadIdx.y; r < 32; r += blockDim.y) {
+        int64_t t = t0 + r; int k = k0 + threadIdx.x;
+        tile[r][threadIdx.x] = (t < T && k < NB) ? convT[t * NB + k] : 0.0;
+    }
+    __syncthreads();
+    for (int r = threadIdx.y; r < 32; r += blockDim.y) {
+        int k = k0 + r; int64_t t = t0 + threadIdx.x;
+        if (t < T && k < NB) { int p = k / B, b = k - p * B; out[t + T * (p + (int64_t)N * b)] = tile[threadIdx.x][r]; }
+    }
+}
+// csum[k] = sum over own bins of convT[t][k]
+__global__ void k_conv_colsum(const double *__restrict__ convT, int NB, int64_t T, int64_t t0, double *__restrict__ csum) {
+    for (int k = threadIdx.x; k < NB; k += blockDim.x) {
+        double s = 0.0;
+        for (int64_t t = t0 + blockIdx.x; t < T; t += gridDim.x) s += convT[t * NB + k];
+        atomicAdd(&csum[k], s);
+    }
+}
+
+extern "C" int nhp_disc_convolve(nhp_ctx *ctx, nhp_disc *dd, const double *phi, int64_t L, int64_t B, double *conv_out) {
+    NHP_CHECK(ctx, ctx != nullptr, NHP_ERR_INVALID, "ctx is NULL");
+    NHP_CHECK(ctx, dd && phi && L >= 1 && B >= 1 && L * B <= 4096, NHP_ERR_INVALID, "nhp_disc_convolve: bad argument");
+    DCUDA(ctx, cudaSetDevice(ctx->device));
+    cudaStream_t s = ctx->stream;
+    DiscExtra *ex = extra_of(dd);
+    const int64_t NB = dd->N * B;
+    if (dd->B != B || !dd->d_conv) {
+        DCUDA(ctx, cudaStreamSynchronize(s));
+        cudaFree(dd->d_conv); dd->d_conv = nullptr;
+        cudaFree(ex->csum); ex->csum = nullptr;
+        DCUDA(ctx, cudaMalloc(&dd->d_conv, (size_t)dd->T * NB * sizeof(double)));
+        DCUDA(ctx, cudaMalloc(&ex->csum, (size_t)NB * sizeof(double)));
+    }
+    cudaFree(ex->phi); ex->phi = nullptr;
+    DCUDA(ctx, cudaMalloc(&ex->phi, (size_t)(L * B) * sizeof(double)));
+    DCUDA(ctx, cudaMemcpyAsync(ex->phi, phi, (size_t)(L * B) * sizeof(double), cudaMemcpyHostToDevice, s));
+    dd->L = L; dd->B = B;
+    NHP_TRY(nhp_timer_begin(ctx));
+    int grid = (int)std::min<int64_t>(dd->T, (int64_t)ctx->sm_count * 16);
+    k_convolve<<<grid, 256, (size_t)(L * B) * sizeof(double), s>>>(dd->d_data, (int)dd->N, dd->T, ex->phi, (int)L, (int)B, dd->d_conv);
+    NHP_LAUNCHED(ctx);
+    DCUDA(ctx, cudaMemsetAsync(ex->csum, 0, (size_t)NB * sizeof(double), s));
+    k_conv_colsum<<<(unsigned)std::min<int64_t>(dd->T - dd->t_halo, 2048), 256, 0, s>>>(dd->d_conv, (int)NB, dd->T, dd->t_halo, ex->csum);
+    NHP_LAUNCHED(ctx);
+    DCUDA(ctx, cudaGetLastError());
+    NHP_TRY(nhp_timer_end(ctx));
+    if (conv_out) {
+        void *scratch;
+        NHP_TRY(nhp_scratch(ctx, (size_t)dd->T * NB * sizeof(double), &scratch));
+        dim3 g((unsigned)((dd->T + 31) / 32), (unsigned)((NB + 31) / 32)), b(32, 8);
+        k_conv_export<<<g, b, 0, s>>>(dd->d_conv, (int)dd->N, (int)B, dd->T, (double *)scratch);
+        NHP_LAUNCHED(ctx);
+        DCUDA(ctx, cudaMemcpyAsync(conv_out, scratch, (size_t)dd->T * NB * sizeof(double), cudaMemcpyDeviceToHost, s));
+        DCUDA(ctx, cudaStreamSynchronize(s));
+    }
+    return NHP_OK;
+}
+
+// ---------------------------------------------------------------------------------------
+// parameters: bump[p,c,b] = [A] W theta dt  (discrete.jl:381-385, 511-516)
+// ---------------------------------------------------------------------------------------
+__global__ void k_bump(int N, int B, const double *__restrict__ W, const double *__restrict__ A, const double *__restrict__ theta, double dt,
+                       double *__restrict__ bumpM /* [k][c] */, double *__restrict__ bumpT /* [c][k] */) {
+    int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    int64_t NB = (int64_t)N * B;
+    if (e >= NB * N) return;
+    int c = (int)(e / NB), k = (int)(e % NB);
+    int p = k / B, b = k - p * B;
+    int64_t pc = p + (int64_t)N * c;
+    double w = W[pc], th = theta[pc + (int64_t)N * N * b];
+    double v = A ? A[pc] * w * th * dt : w * th * dt;
+    bumpT[e] = v;
+    bumpM[(int64_t)k * N + c] = v;
+}
+
+extern "C" int nhp_disc_params_set(nhp_ctx *ctx, int64_t N, int64_t B, const double *lambda0, const double *W, const double *A, const double *theta, double dt) {
+    NHP_CHECK(ctx, ctx != nullptr, NHP_ERR_INVALID, "ctx is NULL");
+    NHP_CHECK(ctx, N >= 1 && B >= 1 && lambda0 && W && theta && dt > 0.0, NHP_ERR_INVALID, "nhp_disc_params_set: bad argument");
+    for (int64_t n = 0; n < N; n++) NHP_CHECK(ctx, lambda0[n] >= 0.0, NHP_ERR_INVALID, "DiscreteHomogeneousProcess: intensity parameter must be non-negative (baselines.jl:367)");
+    DCUDA(ctx, cudaSetDevice(ctx->device));
+    cudaStream_t s = ctx->stream;
+    const int64_t NN = N * N, NB = N * B;
+    if (ctx->dN != N || ctx->dB != B) {
+        DCUDA(ctx, cudaStreamSynchronize(s));
+        cudaFree(ctx->dd_lambda0); cudaFree(ctx->dd_W); cudaFree(ctx->dd_A); cudaFree(ctx->dd_theta); cudaFree(ctx->dd_bump);
+        ctx->dd_lambda0 = ctx->dd_W = ctx->dd_A = ctx->dd_theta = ctx->dd_bump = nullptr;
+        DCUDA(ctx, cudaMalloc(&ctx->dd_lambda0, (size_t)N * sizeof(double)));
+        DCUDA(ctx, cudaMalloc(&ctx->dd_W, (size_t)NN * sizeof(double)));
+        DCUDA(ctx, cudaMalloc(&ctx->dd_A, (size_t)NN * sizeof(double)));
+        DCUDA(ctx, cudaMalloc(&ctx->dd_theta, (size_t)(NN * B) * sizeof(double)));
+        DCUDA(ctx, cudaMalloc(&ctx->dd_bump, (size_t)(2 * NB * N) * sizeof(double)));
+        ctx->dN = N; ctx->dB = B;
+    }
+    ctx->disc_set = false;
+    ctx->ddt = dt; ctx->d_has_A = A != nullptr;
+    DCUDA(ctx, cudaMemcpyAsync(ctx->dd_lambda0, lambda0, (size_t)N * sizeof(double), cudaMemcpyHostToDevice, s));
+    DCUDA(ctx, cudaMemcpyAsync(ctx->dd_W, W, (size_t)NN * sizeof(double), cudaMemcpyHostToDevice, s));
+    if (A) DCUDA(ctx, cudaMemcpyAsync(ctx->dd_A, A, (size_t)NN * sizeof(double), cudaMemcpyHostToDevice, s));
+    DCUDA(ctx, cudaMemcpyAsync(ctx->dd_theta, theta, (size_t)(NN * B) * sizeof(double), cudaMemcpyHostToDevice, s));
+    k_bump<<<(unsigned)((NB * N + 255) / 256), 256, 0, s>>>((int)N, (int)B, ctx->dd_W, A ? ctx->dd_A : nullptr, ctx->dd_theta, dt, ctx->dd_bump, ctx->dd_bump + NB * N);
+    NHP_LAUNCHED(ctx);
+    DCUDA(ctx, cudaGetLastError());
+    DCUDA(ctx, cudaStreamSynchronize(s));
+    ctx->disc_set = true;
+    return NHP_OK;
+}
+
+static int disc_ready(nhp_ctx *ctx, nhp_disc *dd, const char *who) {
+    NHP_CHECK(ctx, ctx != nullptr, NHP_ERR_INVALID, "ctx is NULL");
+    NHP_CHECK(ctx, dd != nullptr, NHP_ERR_INVALID, "%s: data handle is NULL", who);
+    NHP_CHECK(ctx, ctx->disc_set, NHP_ERR_STATE, "%s: discrete parameters not set (call nhp_disc_params_set)", who);
+    NHP_CHECK(ctx, dd->d_conv != nullptr, NHP_ERR_STATE, "%s: call nhp_disc_convolve first", who);
+    NHP_CHECK(ctx, dd->N == ctx->dN && dd->B == ctx->dB, NHP_ERR_INVALID, "%s: data (N=%lld,B=%lld) and parameters (N=%lld,B=%lld) disagree", who,
+              (long long)dd->N, (long long)dd->B, (long long)ctx->dN, (long long)ctx->dB);
+    DCUDA(ctx, cudaSetDevice(ctx->device));
+    return NHP_OK;
+}
+
+// ---------------------------------------------------------------------------------------
+// intensity / log-likelihood: lambda[t,c] = lambda0_c dt + sum_k convT[t,k] bumpM[k,c]   (discrete.jl:115-129)
+// FP64 register-tiled GEMM, 128 x 64 output tile per CTA, 8 x 4 per thread, fused Poisson epilogue.
+// ---------------------------------------------------------------------------------------
+constexpr int GBM = 128, GBN = 64, GBK = 16;
+
+template <bool LOGLIK>
+__global__ void __launch_bounds__(256) k_disc_gemm(const double *__restrict__ convT, const double *__restrict__ bumpM, const double *__restrict__ lambda0,
+                                                   double dt, int N, int NB, int64_t T, int64_t t_first, const int *__restrict__ data,
+                                                   double *__restrict__ lam_out, double *__restrict__ partials) {
+    __shared__ double As[GBK][GBM + 4];
+    __shared__ double Bs[GBK][GBN];
+    __shared__ double red[8];
+    const int tx = threadIdx.x % 16, ty = threadIdx.x / 16;  // tx -> 4 columns, ty -> 8 rows
+    const int64_t t0 = t_first + (int64_t)blockIdx.x * GBM;
+    const int c0 = blockIdx.y * GBN;
+    double acc[8][4];
+#pragma unroll
+    for (int i = 0; i < 8; i++)
+#pragma unroll
+        for (int j = 0; j < 4; j++) acc[i][j] = 0.0;
+    for (int k0 = 0; k0 < NB; k0 += GBK) {
+        // A tile: 128 rows x 16 k (row-major source, k contiguous)
+        for (int e = threadIdx.x; e < GBM * GBK; e += 256) {
+            int r = e / GBK, kk = e % GBK;
+            int64_t t = t0 + r;
+            As[kk][r] = (t < T && k0 + kk < NB) ? __ldg(convT + t * NB + k0 + kk) : 0.0;
+        }
+        for (int e = threadIdx.x; e < GBK * GBN; e += 256) {
+            int kk = e / GBN, cc = e % GBN;
+            Bs[kk][cc] = (k0 + kk < NB && c0 + cc < N) ? __ldg(bumpM + (int64_t)(k0 + kk) * N + c0 + cc) : 0.0;
+        }
+        __syncthreads();
+#pragma unroll
+        for (int kk = 0; kk < GBK; kk++) {
+            double a[8], b[4];
+#pragma unroll
+            for (int i = 0; i < 8; i++) a[i] = As[kk][ty + 16 * i];
+#pragma unroll
+            for (int j = 0; j < 4; j++) b[j] = Bs[kk][tx + 16 * j];
+#pragma unroll
+            for (int i = 0; i < 8; i++)
+#pragma unroll
+                for (int j = 0; j < 4; j++) acc[i][j] = fma(a[i], b[j], acc[i][j]);
+        }
+        __syncthreads();
+    }
+    double part = 0.0;
+#pragma unroll
+    for (int i = 0; i < 8; i++) {
+        int64_t t = t0 + ty + 16 * i;
+#pragma unroll
+        for (int j = 0; j < 4; j++) {
+            int c = c0 + tx + 16 * j;
+            if (t < T && c < N) {
+                double lam = lambda0[c] * dt + acc[i][j];
+                if (LOGLIK) {
+                    int sct = data[t * N + c];
+                    // log pdf(Poisson(lam), s) = xlogy(s, lam) - lam - loggamma(s + 1)   (discrete.jl:98)
+                    part += (sct ? (double)sct * log(lam) : 0.0) - lam - lgamma((double)sct + 1.0);
+                } else lam_out[t + T * (int64_t)c] = lam;
+            }
+        }
+    }
+    if (LOGLIK) {
+        part = warp_sum_d(part);
+        if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = part;
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            double s = 0.0;
+            for (int w = 0; w < 8; w++) s += red[w];
+            partials[(size_t)blockIdx.y * gridDim.x + blockIdx.x] = s;
+        }
+    }
+}
+
+__global__ void k_sum_partials(const double *__restrict__ partials, int64_t n, double *__restrict__ out) {
+    __shared__ double sx[1024];
+    double x = 0.0;
+    for (int64_t i = threadIdx.x; i < n; i += blockDim.x) x += partials[i];
+    sx[threadIdx.x] = x;
+    __syncthreads();
+    for (int s = blockDim.x / 2; s > 0; s >>= 1) { if ((int)threadIdx.x < s) sx[threadIdx.x] += sx[threadIdx.x + s]; __syncthreads(); }
+    if (threadIdx.x == 0) out[0] = sx[0];
+}
+
+extern "C" int nhp_disc_intensity(nhp_ctx *ctx, nhp_disc *dd, double *lam) {
+    NHP_TRY(disc_ready(ctx, dd, "nhp_disc_intensity"));
+    NHP_CHECK(ctx, lam != nullptr, NHP_ERR_INVALID, "nhp_disc_intensity: lam is NULL");
+    const int64_t N = dd->N, NB = N * dd->B, T = dd->T;
+    void *scratch;
+    NHP_TRY(nhp_scratch(ctx, (size_t)T * N * sizeof(double), &scratch));
+    dim3 grid((unsigned)((T + GBM - 1) / GBM), (unsigned)((N + GBN - 1) / GBN));
+    NHP_TRY(nhp_timer_begin(ctx));
+    k_disc_gemm<false><<<grid, 256, 0, ctx->stream>>>(dd->d_conv, ctx->dd_bump, ctx->dd_lambda0, ctx->ddt, (int)N, (int)NB, T, 0, dd->d_data, (double *)scratch, nullptr);
+    NHP_LAUNCHED(ctx);
+    DCUDA(ctx, cudaGetLastError());
+    NHP_TRY(nhp_timer_end(ctx));
+    DCUDA(ctx, cudaMemcpyAsync(lam, scratch, (size_t)T * N * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+    DCUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    return NHP_OK;
+}
+
+extern "C" int nhp_disc_loglik(nhp_ctx *ctx, nhp_disc *dd, double *ll) {
+    NHP_TRY(disc_ready(ctx, dd, "nhp_disc_loglik"));
+    NHP_CHECK(ctx, ll != nullptr, NHP_ERR_INVALID, "nhp_disc_loglik: ll is NULL");
+    const int64_t N = dd->N, NB = N * dd->B, T = dd->T, own = T - dd->t_halo;
+    dim3 grid((unsigned)((own + GBM - 1) / GBM), (unsigned)((N + GBN - 1) / GBN));
+    double *partials;
+    NHP_TRY(nhp_partials(ctx, (int64_t)grid.x * grid.y + 1, &partials));
+    NHP_TRY(nhp_timer_begin(ctx));
+    k_disc_gemm<true><<<grid, 256, 0, ctx->stream>>>(dd->d_conv, ctx->dd_bump, ctx->dd_lambda0, ctx->ddt, (int)N, (int)NB, T, dd->t_halo, dd->d_data, nullptr, partials + 1);
+    NHP_LAUNCHED(ctx);
+    k_sum_partials<<<1, 1024, 0, ctx->stream>>>(partials + 1, (int64_t)grid.x * grid.y, partials);
+    NHP_LAUNCHED(ctx);
+    DCUDA(ctx, cudaGetLastError());
+    DCUDA(ctx, cudaMemcpyAsync(ll, partials, sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+    NHP_TRY(nhp_timer_end(ctx));
+    return NHP_OK;
+}
+
+// ---------------------------------------------------------------------------------------
+// Gibbs parent counts (parents.jl:82-134) and VB statistics (parents.jl:136-177 + the three update!
+// reductions): one CTA per (child node, slab of its non-zero bins); threads own the k = (p,b) axis.
+// ---------------------------------------------------------------------------------------
+constexpr int KPT = 8;  // k entries per thread: N*B <= 256 * KPT * passes (looped)
+
+__device__ __forceinline__ double block_sum_256(double v, double *red) {
+    v = warp_sum_d(v);
+    __syncthreads();
+    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = v;
+    __syncthreads();
+    double s = 0.0;
+#pragma unroll
+    for (int w = 0; w < 8; w++) s += red[w];
+    return s;
+}
+
+// counts[c + N*k'] with k' = 0 baseline, 1 + k.  mu_k = convT[t,k] * bumpT[c][k], baseline mu_0 = lambda0_c dt first in the cdf order.
+__global__ void __launch_bounds__(256) k_disc_gibbs(const double *__restrict__ convT, const double *__restrict__ bumpT, const double *__restrict__ lambda0, double dt,
+                                                    int N, int NB, const int *__restrict__ nz_t, const int *__restrict__ nz_s, const int64_t *__restrict__ nz_off,
+                                                    const int *__restrict__ child_ptr, int slabs, const double *__restrict__ u, uint64_t seed, uint64_t counter,
+                                                    double *__restrict__ counts, int *__restrict__ flag) {
+    extern __shared__ double s_cum[];  // [NB + 1] inclusive cumulative weights, index 0 = baseline
+    __shared__ double red[8];
+    __shared__ int s_pick;
+    const int c = blockIdx.x / slabs, slab = blockIdx.x % slabs;
+    const int e0 = child_ptr[c], e1 = child_ptr[c + 1];
+    const int per = (e1 - e0 + slabs - 1) / slabs;
+    const int b0 = e0 + slab * per, b1 = min(e1, b0 + per);
+    const double *bt = bumpT + (int64_t)c * NB;
+    const double mu0 = lambda0[c] * dt;
+    for (int e = b0; e < b1; e++) {
+        const int t = nz_t[e], s = nz_s[e];
+        const double *row = convT + (int64_t)t * NB;
+        // block-wide inclusive scan of [mu0, mu_1..mu_NB] in index order
+        double carry = mu0;
+        if (threadIdx.x == 0) s_cum[0] = mu0;
+        for (int k0 = 0; k0 < NB; k0 += 256) {
+            int k = k0 + threadIdx.x;
+            double v = k < NB ? __ldg(row + k) * __ldg(bt + k) : 0.0;
+            // warp scan
+            double x = v;
+#pragma unroll
+            for (int d = 1; d < 32; d <<= 1) { double y = __shfl_up_sync(0xffffffffu, x, d); if ((threadIdx.x & 31) >= d) x += y; }
+            __syncthreads();
+            if ((threadIdx.x & 31) == 31) red[threadIdx.x >> 5] = x;
+            __syncthreads();
+            double base = carry;
+            for (int w = 0; w < (int)(threadIdx.x >> 5); w++) base += red[w];
+            if (k < NB) s_cum[k + 1] = base + x;
+            double tot = 0.0;
+            for (int w = 0; w < 8; w++) tot += red[w];
+            carry += tot;
+        }
+        __syncthreads();
+        const double S = s_cum[NB];
+        if (threadIdx.x == 0 && !(S > 0.0 && S < 1.7e308)) atomicOr(flag, 8);
+        for (int d = 0; d < s; d++) {
+            const int64_t ui = nz_off[e] + d;
+            const double uu = u ? u[ui] : philox_uniform(seed, (uint64_t)ui, counter);
+            const double target = uu * S;
+            // first index with cum > target (cp <= u keeps walking); last index if none
+            if (threadIdx.x == 0) s_pick = NB;
+            __syncthreads();
+            for (int k = threadIdx.x; k <= NB; k += 256) {
+                double ck = s_cum[k], prev = k > 0 ? s_cum[k - 1] : -1.0;
+                if (ck > target && !(prev > target)) atomicMin(&s_pick, k);
+            }
+            __syncthreads();
+            if (threadIdx.x == 0) atomicAdd(&counts[c + (int64_t)N * s_pick], 1.0);
+            __syncthreads();
+        }
+    }
+}
+
+// VB: Z = e0_c + sum_k convT[t,k] ET[c][k];  alpha_sum[c] += s e0_c / Z;  gamma[c][k] += s convT[t,k] ET[c][k] / Z
+__global__ void __launch_bounds__(256) k_disc_vb(const double *__restrict__ convT, const double *__restrict__ ET, const double *__restrict__ e0, int N, int NB,
+                                                 const int *__restrict__ nz_t, const int *__restrict__ nz_s, const int *__restrict__ child_ptr, int slabs,
+                                                 double *__restrict__ alpha_sum, double *__restrict__ gammaT /* [c][k] */) {
+    __shared__ double red[8];
+    const int c = blockIdx.x / slabs, slab = blockIdx.x % slabs;
+    const int e0i = child_ptr[c], e1 = child_ptr[c + 1];
+    const int per = (e1 - e0i + slabs - 1) / slabs;
+    const int b0 = e0i + slab * per, b1 = min(e1, b0 + per);
+    const double *et = ET + (int64_t)c * NB;
+    const double base = e0[c];
+    double asum = 0.0;
+    for (int k0 = 0; k0 < NB; k0 += 256 * KPT) {
+        double acc[KPT];
+#pragma unroll
+        for (int m = 0; m < KPT; m++) acc[m] = 0.0;
+        for (int e = b0; e < b1; e++) {
+            const double *row = convT + (int64_t)nz_t[e] * NB;
+            // full Z needs every k: recompute the dot product over all k each pass (passes > 1 only when N*B > 2048)
+            double part = 0.0;
+            for (int k = threadIdx.x; k < NB; k += 256) part += __ldg(row + k) * __ldg(et + k);
+            double Z = base + block_sum_256(part, red);
+            double r = (double)nz_s[e] / Z;
+            if (k0 == 0) asum += r * base;
+#pragma unroll
+            for (int m = 0; m < KPT; m++) {
+                int k = k0 + m * 256 + threadIdx.x;
+                if (k < NB) acc[m] += r * __ldg(row + k) * __ldg(et + k);
+            }
+        }
+#pragma unroll
+        for (int m = 0; m < KPT; m++) {
+            int k = k0 + m * 256 + threadIdx.x;
+            if (k < NB && acc[m] != 0.0) atomicAdd(&gammaT[(int64_t)c * NB + k], acc[m]);
+        }
+    }
+    if (threadIdx.x == 0 && asum != 0.0) atomicAdd(&alpha_sum[c], asum);
+}
+
+static int pick_slabs(nhp_ctx *ctx, int64_t N, int64_t nnz) {
+    int64_t want = (int64_t)ctx->sm_count * 8;
+    int64_t slabs = std::max<int64_t>(1, want / std::max<int64_t>(N, 1));
+    slabs = std::min<int64_t>(slabs, std::max<int64_t>(1, nnz / std::max<int64_t>(N, 1) / 4));
+    return (int)std::max<int64_t>(1, slabs);
+}
+
+extern "C" int nhp_disc_gibbs_counts(nhp_ctx *ctx, nhp_disc *dd, uint64_t seed, uint64_t counter, const double *u, int64_t nu, double *counts) {
+    NHP_TRY(disc_ready(ctx, dd, "nhp_disc_gibbs_counts"));
+    NHP_CHECK(ctx, counts != nullptr, NHP_ERR_INVALID, "nhp_disc_gibbs_counts: counts is NULL");
+    NHP_CHECK(ctx, !u || nu >= dd->total_events, NHP_ERR_INVALID, "nhp_disc_gibbs_counts: need %lld uniforms, got %lld", (long long)dd->total_events, (long long)nu);
+    DiscExtra *ex = extra_of(dd);
+    const int64_t N = dd->N, NB = N * dd->B, NK = 1 + NB;
+    cudaStream_t s = ctx->stream;
+    void *scratch;
+    size_t bytes_c = (size_t)(N * NK) * sizeof(double), bytes_u = u ? (size_t)dd->total_events * sizeof(double) : 0;
+    NHP_TRY(nhp_scratch(ctx, bytes_c + bytes_u + 16, &scratch));
+    double *d_counts = (double *)scratch, *d_u = u ? d_counts + N * NK : nullptr;
+    DCUDA(ctx, cudaMemsetAsync(d_counts, 0, bytes_c, s));
+    DCUDA(ctx, cudaMemsetAsync(ctx->d_flag, 0, sizeof(int), s));
+    if (u && dd->total_events > 0) DCUDA(ctx, cudaMemcpyAsync(d_u, u, bytes_u, cudaMemcpyHostToDevice, s));
+    NHP_TRY(nhp_timer_begin(ctx));
+    if (ex->nnz > 0) {
+        int slabs = pick_slabs(ctx, N, ex->nnz);
+        size_t smem = (size_t)(NB + 1) * sizeof(double);
+        if (smem > 48 * 1024) DCUDA(ctx, cudaFuncSetAttribute(k_disc_gibbs, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        k_disc_gibbs<<<(unsigned)(N * slabs), 256, smem, s>>>(dd->d_conv, ctx->dd_bump + NB * N, ctx->dd_lambda0, ctx->ddt, (int)N, (int)NB, ex->nz_t, ex->nz_s, ex->nz_off,
+                                                               ex->child_ptr, slabs, d_u, seed, counter, d_counts, ctx->d_flag);
+        NHP_LAUNCHED(ctx);
+        DCUDA(ctx, cudaGetLastError());
+    }
+    int flag = 0;
+    DCUDA(ctx, cudaMemcpyAsync(&flag, ctx->d_flag, sizeof(int), cudaMemcpyDeviceToHost, s));
+    NHP_TRY(nhp_timer_end(ctx));
+    NHP_CHECK(ctx, !(flag & 8), NHP_ERR_NUMERIC, "resample_parents (discrete): invalid Multinomial probability vector (parents.jl:116)");
+    DCUDA(ctx, cudaMemcpyAsync(counts, d_counts, bytes_c, cudaMemcpyDeviceToHost, s));
+    DCUDA(ctx, cudaStreamSynchronize(s));
+    return NHP_OK;
+}
+
+// ET[c][k] = E[p + N*(c + N*b)]
+__global__ void k_transpose_E(const double *__restrict__ E, int N, int B, double *__restrict__ ET) {
+    int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    int64_t NB = (int64_t)N * B;
+    if (e >= NB * N) return;
+    int c = (int)(e / NB), k = (int)(e % NB), p = k / B, b = k - p * B;
+    ET[e] = E[p + (int64_t)N * (c + (int64_t)N * b)];
+}
+// kappa_sum[p,c] = sum_b gamma[p,c,b]; gamma_sum[p + N*(c + N*b)] = gammaT[c][p*B+b]; nu_sum[p,c] = rowsum[p]
+__global__ void k_vb_finish(const double *__restrict__ gammaT, const double *__restrict__ rowsum, int N, int B, double *__restrict__ kappa, double *__restrict__ nu,
+                            double *__restrict__ gamma) {
+    int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (e >= (int64_t)N * N) return;
+    int c = (int)(e / N), p = (int)(e % N);
+    double ks = 0.0;
+    for (int b = 0; b < B; b++) {
+        double g = gammaT[(int64_t)c * N * B + p * B + b];
+        ks += g;
+        gamma[p + (int64_t)N * (c + (int64_t)N * b)] = g;
+    }
+    kappa[p + (int64_t)N * c] = ks;
+    nu[p + (int64_t)N * c] = rowsum[p];
+}
+
+extern "C" int nhp_disc_vb_stats(nhp_ctx *ctx, nhp_disc *dd, const double *e0, const double *E, double *alpha_sum, double *kappa_sum, double *nu_sum,
+                                 double *gamma_sum) {
+    NHP_CHECK(ctx, ctx != nullptr, NHP_ERR_INVALID, "ctx is NULL");
+    NHP_CHECK(ctx, dd && dd->d_conv, NHP_ERR_STATE, "nhp_disc_vb_stats: call nhp_disc_convolve first");
+    NHP_CHECK(ctx, e0 && E && alpha_sum && kappa_sum && nu_sum && gamma_sum, NHP_ERR_INVALID, "nhp_disc_vb_stats: NULL argument");
+    DCUDA(ctx, cudaSetDevice(ctx->device));
+    DiscExtra *ex = extra_of(dd);
+    const int64_t N = dd->N, B = dd->B, NB = N * B;
+    cudaStream_t s = ctx->stream;
+    void *scratch;
+    // layout: e0[N] | E[N*N*B] | ET[N*NB] | gammaT[N*NB] | alpha[N] | kappa[N*N] | nu[N*N] | gamma[N*N*B]
+    size_t tot = (size_t)(N + NB * N * 4 + N + 2 * N * N) * sizeof(double);
+    NHP_TRY(nhp_scratch(ctx, tot, &scratch));
+    double *d_e0 = (double *)scratch, *d_E = d_e0 + N, *d_ET = d_E + NB * N, *d_gT = d_ET + NB * N, *d_alpha = d_gT + NB * N, *d_kappa = d_alpha + N,
+           *d_nu = d_kappa + N * N, *d_gamma = d_nu + N * N;
+    DCUDA(ctx, cudaMemcpyAsync(d_e0, e0, (size_t)N * sizeof(double), cudaMemcpyHostToDevice, s));
+    DCUDA(ctx, cudaMemcpyAsync(d_E, E, (size_t)(NB * N) * sizeof(double), cudaMemcpyHostToDevice, s));
+    DCUDA(ctx, cudaMemsetAsync(d_gT, 0, (size_t)(NB * N + N) * sizeof(double), s));
+    unsigned eb = (unsigned)((NB * N + 255) / 256);
+    k_transpose_E<<<eb, 256, 0, s>>>(d_E, (int)N, (int)B, d_ET);
+    NHP_LAUNCHED(ctx);
+    NHP_TRY(nhp_timer_begin(ctx));
+    if (ex->nnz > 0) {
+        int slabs = pick_slabs(ctx, N, ex->nnz);
+        k_disc_vb<<<(unsigned)(N * slabs), 256, 0, s>>>(dd->d_conv, d_ET, d_e0, (int)N, (int)NB, ex->nz_t, ex->nz_s, ex->child_ptr, slabs, d_alpha, d_gT);
+        NHP_LAUNCHED(ctx);
+    }
+    k_vb_finish<<<(unsigned)((N * N + 255) / 256), 256, 0, s>>>(d_gT, ex->rowsum, (int)N, (int)B, d_kappa, d_nu, d_gamma);
+    NHP_LAUNCHED(ctx);
+    DCUDA(ctx, cudaGetLastError());
+    NHP_TRY(nhp_timer_end(ctx));
+    DCUDA(ctx, cudaMemcpyAsync(alpha_sum, d_alpha, (size_t)N * sizeof(double), cudaMemcpyDeviceToHost, s));
+    DCUDA(ctx, cudaMemcpyAsync(kappa_sum, d_kappa, (size_t)(N * N) * sizeof(double), cudaMemcpyDeviceToHost, s));
+    DCUDA(ctx, cudaMemcpyAsync(nu_sum, d_nu, (size_t)(N * N) * sizeof(double), cudaMemcpyDeviceToHost, s));
+    DCUDA(ctx, cudaMemcpyAsync(gamma_sum, d_gamma, (size_t)(NB * N) * sizeof(double), cudaMemcpyDeviceToHost, s));
+    DCUDA(ctx, cudaStreamSynchronize(s));
+    return NHP_OK;
+}
+
+// ---------------------------------------------------------------------------------------
+// discrete adjacency Gibbs (discrete.jl:426-480): per column c, p sequential.
+//   ll1 - ll0 = sum_{t: s>0} s [log(lam^{-p} + G_p) - log(lam^{-p})] - sum_t G_p[t] + log rho - log(1-rho),
+//   G_p[t] = sum_b convT[t,(p,b)] W[p,c] theta[p,c,b] dt.   One CTA per column; the rank-1 update of the
+//   column's intensities touches only its non-zero bins; sum_t G_p[t] comes from the conv column sums.
+// ---------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) k_disc_adjacency(const double *__restrict__ convT, const double *__restrict__ csum, const double *__restrict__ lambda0,
+                                                        const double *__restrict__ W, const double *__restrict__ theta, double dt, double *__restrict__ A,
+                                                        const double *__restrict__ rho, const double *__restrict__ u, uint64_t seed, uint64_t counter, int N, int B,
+                                                        const int *__restrict__ nz_t, const int *__restrict__ nz_s, const int *__restrict__ child_ptr,
+                                                        double *__restrict__ lam_scratch, int *__restrict__ flag) {
+    __shared__ double red[8];
+    __shared__ double s_anew;
+    const int c = blockIdx.x;
+    const int NB = N * B;
+    const int e0 = child_ptr[c], e1 = child_ptr[c + 1];
+    double *lam = lam_scratch + e0;
+    // current intensities at the column's non-zero bins
+    for (int e = e0 + threadIdx.x; e < e1; e += 256) {
+        const double *row = convT + (int64_t)nz_t[e] * NB;
+        double v = lambda0[c] * dt;
+        for (int p = 0; p < N; p++) {
+            double a = A[p + (int64_t)N * c], w = W[p + (int64_t)N * c];
+            if (a != 0.0)
+                for (int b = 0; b < B; b++) v += row[p * B + b] * a * w * theta[p + (int64_t)N * (c + (int64_t)N * b)] * dt;
+        }
+        lam[e - e0] = v;
+    }
+    __syncthreads();
+    for (int p = 0; p < N; p++) {
+        const int64_t kk = p + (int64_t)N * c;
+        const double a_old = A[kk], w = W[kk];
+        double gsum = 0.0;  // sum over all own bins of G_p
+        for (int b = 0; b < B; b++) gsum += csum[p * B + b] * w * theta[kk + (int64_t)N * N * b] * dt;
+        double part = 0.0;
+        for (int e = e0 + threadIdx.x; e < e1; e += 256) {
+            const double *row = convT + (int64_t)nz_t[e] * NB + p * B;
+            double g = 0.0;
+            for (int b = 0; b < B; b++) g += row[b] * w * theta[kk + (int64_t)N * N * b] * dt;
+            if (g != 0.0) {
+                double l = lam[e - e0];
+                double base = a_old != 0.0 ? l - g : l;
+                part += (double)nz_s[e] * log((base + g) / base);
+            }
+        }
+        double sum = block_sum_256(part, red);
+        if (threadIdx.x == 0) {
+            double r = rho[kk];
+            double delta = sum - gsum + (log(r) - log(1.0 - r));
+            double p1 = delta >= 0.0 ? 1.0 / (1.0 + exp(-delta)) : exp(delta) / (1.0 + exp(delta));
+            if (delta != delta) { atomicOr(flag, 64); p1 = 0.0; }
+            double uu = u ? u[kk] : philox_uniform(seed, (uint64_t)kk, counter);
+            double an = uu <= p1 ? 1.0 : 0.0;
+            A[kk] = an;
+            s_anew = an;
+        }
+        __syncthreads();
+        const double an = s_anew;
+        if (an != a_old) {
+            for (int e = e0 + threadIdx.x; e < e1; e += 256) {
+                const double *row = convT + (int64_t)nz_t[e] * NB + p * B;
+                double g = 0.0;
+                for (int b = 0; b < B; b++) g += row[b] * w * theta[kk + (int64_t)N * N * b] * dt;
+                lam[e - e0] += an != 0.0 ? g : -g;
+            }
+        }
+        __syncthreads();
+    }
+}
+
+extern "C" int nhp_disc_resample_adjacency(nhp_ctx *ctx, nhp_disc *dd, const double *rho, uint64_t seed, uint64_t counter, const double *u, double *A_inout) {
+    NHP_TRY(disc_ready(ctx, dd, "nhp_disc_resample_adjacency"));
+    NHP_CHECK(ctx, rho && A_inout, NHP_ERR_INVALID, "nhp_disc_resample_adjacency: NULL rho/A");
+    NHP_CHECK(ctx, dd->t_halo == 0, NHP_ERR_UNSUPPORTED, "nhp_disc_resample_adjacency works on unsharded data");
+    DiscExtra *ex = extra_of(dd);
+    const int64_t N = dd->N, B = dd->B, NN = N * N;
+    cudaStream_t s = ctx->stream;
+    void *scratch;
+    size_t tot = (size_t)(3 * NN + std::max<int64_t>(ex->nnz, 1)) * sizeof(double);
+    NHP_TRY(nhp_scratch(ctx, tot, &scratch));
+    double *d_A = (double *)scratch, *d_rho = d_A + NN, *d_u = d_rho + NN, *d_lam = d_u + NN;
+    DCUDA(ctx, cudaMemcpyAsync(d_A, A_inout, (size_t)NN * sizeof(double), cudaMemcpyHostToDevice, s));
+    DCUDA(ctx, cudaMemcpyAsync(d_rho, rho, (size_t)NN * sizeof(double), cudaMemcpyHostToDevice, s));
+    if (u) DCUDA(ctx, cudaMemcpyAsync(d_u, u, (size_t)NN * sizeof(double), cudaMemcpyHostToDevice, s));
+    DCUDA(ctx, cudaMemsetAsync(ctx->d_flag, 0, sizeof(int), s));
+    NHP_TRY(nhp_timer_begin(ctx));
+    k_disc_adjacency<<<(unsigned)N, 256, 0, s>>>(dd->d_conv, ex->csum, ctx->dd_lambda0, ctx->dd_W, ctx->dd_theta, ctx->ddt, d_A, d_rho, u ? d_u : nullptr, seed, counter,
+                                                 (int)N, (int)B, ex->nz_t, ex->nz_s, ex->child_ptr, d_lam, ctx->d_flag);
+    NHP_LAUNCHED(ctx);
+    DCUDA(ctx, cudaGetLastError());
+    int flag = 0;
+    DCUDA(ctx, cudaMemcpyAsync(&flag, ctx->d_flag, sizeof(int), cudaMemcpyDeviceToHost, s));
+    NHP_TRY(nhp_timer_end(ctx));
+    NHP_CHECK(ctx, !(flag & 64), NHP_ERR_NUMERIC, "discrete adjacency sampler: NaN log-likelihood difference");
+    DCUDA(ctx, cudaMemcpyAsync(A_inout, d_A, (size_t)NN * sizeof(double), cudaMemcpyDeviceToHost, s));
+    DCUDA(ctx, cudaStreamSynchronize(s));
+    // the new adjacency becomes the context's A
+    if (ctx->d_has_A) {
+        DCUDA(ctx, cudaMemcpyAsync(ctx->dd_A, A_inout, (size_t)NN * sizeof(double), cudaMemcpyHostToDevice, s));
+        int64_t NB = N * B;
+        k_bump<<<(unsigned)((NB * N + 255) / 256), 256, 0, s>>>((int)N, (int)B, ctx->dd_W, ctx->dd_A, ctx->dd_theta, ctx->ddt, ctx->dd_bump, ctx->dd_bump + NB * N);
+        NHP_LAUNCHED(ctx);
+        DCUDA(ctx, cudaStreamSynchronize(s));
+    }
+    return NHP_OK;
+}

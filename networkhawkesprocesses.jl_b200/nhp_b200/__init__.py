@@ -7,3 +7,6 @@ from .continuous import (  # noqa: F401
     DenseNetworkModel, BernoulliNetworkModel, ContinuousStandardHawkesProcess, ContinuousNetworkHawkesProcess,
     loglikelihood, event_intensity, intensity, resample_parents, sufficient_statistics, resample_adjacency_matrix_,
     resample_, mcmc_, mle_, rand, MarkovChainMonteCarlo, MaximumLikelihood)
+from . import discrete  # noqa: F401,E402
+from .discrete import (  # noqa: F401,E402
+    DiscreteHomogeneousProcess, DiscreteGaussianImpulseResponse, DiscreteStandardHawkesProcess, DiscreteNetworkHawkesProcess, DiscreteData)

@@ -1,0 +1,123 @@
+"""GPU parity tests of the discrete-time path against the oracle (convolve, intensity GEMM, Poisson
+log-likelihood, Gibbs parent counts, VB statistics, adjacency Gibbs)."""
+import numpy as np
+import pytest
+
+import nhp_b200 as nhp
+from nhp_b200 import discrete as D
+import oracle_ffi as orc
+
+pytestmark = pytest.mark.gpu
+
+
+def make(N, T, B, L, seed, network=False, rate=0.05):
+    rng = np.random.default_rng(seed)
+    lam0 = rng.uniform(0.5, 1.5, N) * rate
+    W = rng.uniform(0.0, 0.6 / N, (N, N))
+    theta = rng.dirichlet(np.ones(B), (N, N))
+    A = (rng.random((N, N)) < 0.5).astype(np.float64) if network else None
+    data = rng.poisson(rate, (N, T)).astype(np.int64)
+    base, imp, wts = D.DiscreteHomogeneousProcess(lam0), D.DiscreteGaussianImpulseResponse(theta, L), nhp.DenseWeightModel(W)
+    proc = D.DiscreteNetworkHawkesProcess(base, imp, wts, A, nhp.BernoulliNetworkModel(0.4, N)) if network else D.DiscreteStandardHawkesProcess(base, imp, wts)
+    return proc, orc.Disc(lam0, W, theta, dt=1.0, A=A), data
+
+
+def test_kat_e(kat):
+    k = kat["E"]
+    theta = np.full((2, 2, 3), 1.0 / 3.0)
+    proc = D.DiscreteStandardHawkesProcess(D.DiscreteHomogeneousProcess(k["lambda0"]), D.DiscreteGaussianImpulseResponse(theta, k["L"]), nhp.DenseWeightModel(np.array(k["W"])))
+    np.testing.assert_allclose(proc.impulses.basis(), k["phi"], rtol=1e-14)
+    data = np.array(k["data"], dtype=np.int64)
+    d = proc.upload(data)
+    np.testing.assert_allclose(D.convolve(proc, d), k["conv"], rtol=1e-13, atol=1e-300)
+    np.testing.assert_allclose(D.intensity(proc, d), k["lam"], rtol=1e-13)
+    assert D.loglikelihood(proc, d) == pytest.approx(k["ll"], rel=1e-12)
+
+
+@pytest.mark.parametrize("N,T,B,L,network", [(3, 500, 3, 4, False), (20, 3000, 4, 8, True), (70, 1500, 6, 12, False), (5, 200, 1 + 1, 2, True)])
+def test_convolve_intensity_loglik(N, T, B, L, network):
+    proc, om, data = make(N, T, B, L, 3 + N, network)
+    d = proc.upload(data)
+    conv = D.convolve(proc, d)
+    oconv = orc.disc_convolve(data, orc.disc_basis(L, B))
+    np.testing.assert_allclose(conv, oconv, rtol=1e-13, atol=1e-300)
+    np.testing.assert_allclose(D.intensity(proc, d), om.intensity(oconv), rtol=1e-10)
+    assert D.loglikelihood(proc, d) == pytest.approx(om.loglik(data, oconv), rel=1e-10)
+
+
+@pytest.mark.parametrize("N,T,B,L,network", [(3, 400, 3, 4, False), (12, 1500, 4, 6, True)])
+def test_gibbs_counts_match_given_uniforms(N, T, B, L, network):
+    proc, om, data = make(N, T, B, L, 11 + N, network, rate=0.2)
+    d = proc.upload(data)
+    D.convolve(proc, d, export=False)
+    oconv = orc.disc_convolve(data, orc.disc_basis(L, B))
+    u = np.random.default_rng(5).random(int(data.sum()))
+    counts = D.resample_parents(proc, d, u=u)
+    ref = om.gibbs_counts(data, oconv, u)
+    assert counts.sum() == data.sum()
+    np.testing.assert_array_equal(counts.sum(axis=1), data.sum(axis=1))  # every event gets exactly one parent
+    assert np.count_nonzero(counts != ref) == 0
+
+
+def test_gibbs_counts_distribution():
+    """Size-independent property: summed over many sweeps the counts follow the expected attribution mass."""
+    proc, om, data = make(4, 600, 3, 4, 21, False, rate=0.3)
+    d = proc.upload(data)
+    conv = D.convolve(proc, d)
+    lam = om.intensity(conv)
+    N, B = 4, 3
+    expect = np.zeros((N, 1 + N * B))
+    bump = proc.weights.W[:, :, None] * proc.impulses.theta  # [p, c, b]
+    for c in range(N):
+        s = data[c].astype(float)
+        expect[c, 0] = np.sum(s * proc.baseline.lam[c] / lam[:, c])
+        for p in range(N):
+            for b in range(B):
+                expect[c, 1 + p * B + b] = np.sum(s * conv[:, p, b] * bump[p, c, b] / lam[:, c])
+    tot = np.zeros_like(expect)
+    nrep = 200
+    for r in range(nrep):
+        tot += D.resample_parents(proc, d, seed=3, counter=r)
+    mean = tot / nrep
+    assert np.all(np.abs(mean - expect) < 5 * np.sqrt(expect / nrep + 1e-9) + 0.02)
+
+
+@pytest.mark.parametrize("N,T,B,L", [(3, 400, 3, 4), (15, 2000, 5, 10)])
+def test_vb_statistics(N, T, B, L):
+    proc, om, data = make(N, T, B, L, 31 + N, False, rate=0.1)
+    d = proc.upload(data)
+    conv = D.convolve(proc, d)
+    rng = np.random.default_rng(2)
+    e0, E = rng.uniform(0.5, 1.5, N), rng.uniform(0.01, 0.2, (N, N, B))
+    st = D.vb_statistics(proc, d, e0, E)
+    ref = orc.disc_vb_stats(data, conv, e0, E)
+    for k in ("alpha_sum", "kappa_sum", "gamma_sum"):
+        np.testing.assert_allclose(st[k], ref[k], rtol=1e-10, atol=1e-13)
+    np.testing.assert_array_equal(st["nu_sum"], ref["nu_sum"])
+    # fixture of the reference's own tests (test/baselines.jl:77-78): row sums ([3, 2], T = 10)
+
+
+def test_vb_and_gibbs_steps_run():
+    proc, om, data = make(4, 800, 3, 4, 41, False, rate=0.2)
+    d = proc.upload(data)
+    trace = D.vb_(proc, d, max_steps=3)
+    assert len(trace) == 3 and np.all(np.isfinite(trace[-1]))
+    res = D.mcmc_(proc, d, nsteps=3, seed=1)
+    assert len(res.samples) == 3 and np.all(np.isfinite(res.samples[-1]))
+    np.testing.assert_allclose(proc.impulses.theta.sum(axis=2), 1.0, rtol=1e-12)
+
+
+@pytest.mark.parametrize("N,T,B,L", [(4, 300, 3, 4), (8, 600, 2, 5)])
+def test_discrete_adjacency_matches_oracle(N, T, B, L):
+    proc, om, data = make(N, T, B, L, 51 + N, True, rate=0.2)
+    d = proc.upload(data)
+    conv = D.convolve(proc, d)
+    A0 = proc.adjacency_matrix.copy()
+    mism = 0
+    for rep in range(3):
+        u = np.random.default_rng(60 + rep).random((N, N))
+        proc.adjacency_matrix = A0.copy()
+        A = D.resample_adjacency_matrix_(proc, d, u=u).copy()
+        ref = om.resample_adjacency(A0, np.full((N, N), 0.4), data, conv, u)
+        mism += int(np.count_nonzero(A != ref))
+    assert mism == 0
