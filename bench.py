@@ -155,7 +155,9 @@ def run_ours(args, rank, world, local_rank):
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
     ctx = nhp.Context(local_rank)
-    stream = torch.cuda.current_stream()
+    # one explicit (non-default) stream shared by libnhp's kernels, the NCCL collectives and the timing events
+    stream = torch.cuda.Stream(device=dev)
+    torch.cuda.set_stream(stream)
     ctx.check(ctx.lib.nhp_set_stream(ctx.h, ctypes.c_void_p(stream.cuda_stream)))
     lib = ctx.lib
     K, n = args.nodes, int(args.events)
@@ -283,19 +285,29 @@ def run_ours(args, rank, world, local_rank):
     sync_all()
     tb = torch.cuda.Event(enable_timing=True); te = torch.cuda.Event(enable_timing=True)
     tb.record(stream)
+    e2e_parts = {"params_set": 0.0, "upload": 0.0, "loglik": 0.0, "gibbs": 0.0, "readback+free": 0.0}
     for k in range(e2e_steps):
+        w0 = time.perf_counter()
         set_params()
+        w1 = time.perf_counter()
         ev = upload()
+        w2 = time.perf_counter()
         ll = ctypes.c_double()
         ctx.check(lib.nhp_cont_loglik(ctx.h, ev, 0, ctypes.byref(ll)))
+        w3 = time.perf_counter()
         ctx.check(lib.nhp_cont_resample_parents(ctx.h, ev, 20261018, 100 + k, None, None, None))
         if world > 1:
             dist.all_reduce(st0)
         ctx.check(lib.nhp_cont_suffstats_second_pass(ctx.h, ev))
         if world > 1:
             dist.all_reduce(st1)
+        stream.synchronize()
+        w4 = time.perf_counter()
         ctx.check(lib.nhp_cont_suffstats_read(ctx.h, _ptr(M0), _ptr(Mn), _ptr(Mnm), _ptr(S1), _ptr(S2)))
         lib.nhp_events_free(ctx.h, ev)
+        w5 = time.perf_counter()
+        for key, dtv in zip(e2e_parts, (w1 - w0, w2 - w1, w3 - w2, w4 - w3, w5 - w4)):
+            e2e_parts[key] += 1e3 * dtv / e2e_steps
     te.record(stream)
     sync_all()
     e2e_ms = torch.tensor([tb.elapsed_time(te)], dtype=torch.float64, device=dev)
@@ -336,7 +348,8 @@ def run_ours(args, rank, world, local_rank):
             "ms_per_step": total_ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
             "data": "synthetic", "config": workload_config(args, world), "clocks": sampler.summary(),
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "steps": e2e_steps,
-                    "what": "nhp_cont_params_set + nhp_events_upload (pinned host buffers) + nhp_cont_loglik + nhp_cont_resample_parents + statistics read back"},
+                    "what": "nhp_cont_params_set + nhp_events_upload (pinned host buffers) + nhp_cont_loglik + nhp_cont_resample_parents + statistics read back",
+                    "host_ms_per_step": e2e_parts},
             "gpu_launches": int(launches), "roofline": roofline,
             "detail": {"loglik_events_per_s": world * n / (med["loglik"] * 1e-3), "gibbs_sweep_events_per_s": world * n / ((med["parents"] + med["second_pass"]) * 1e-3)}}
 

@@ -46,6 +46,32 @@ def run(name, K, n, rate, density, kind="ln", reps=5, G=None):
 
 if __name__ == "__main__":
     which = sys.argv[1] if len(sys.argv) > 1 else "all"
+    if which == "upload":
+        import ctypes
+        from nhp_b200.core import _ptr
+        n, K = int(float(sys.argv[2])), 1000
+        t, nodes, T = synth.poisson_stream(n, K, 64.0, 1)
+        ctx = nhp.default_context()
+        import torch
+        pt = torch.empty(n, dtype=torch.float64, pin_memory=True); pt.numpy()[:] = t
+        pc = torch.empty(n, dtype=torch.int64, pin_memory=True); pc.numpy()[:] = nodes
+        for name, a, b in (("pageable", _ptr(t), _ptr(nodes)), ("pinned", ctypes.c_void_p(pt.data_ptr()), ctypes.c_void_p(pc.data_ptr()))):
+            for rep in range(3):
+                h = ctypes.c_void_p()
+                t0 = time.perf_counter()
+                ctx.check(ctx.lib.nhp_events_upload(ctx.h, a, b, n, T, K, 0, 0, 1, ctypes.byref(h)))
+                t1 = time.perf_counter()
+                ctx.lib.nhp_events_free(ctx.h, h)
+                t2 = time.perf_counter()
+                print(f"upload {name} n={n:.1e}: upload {1e3*(t1-t0):.1f} ms ({n*16/(t1-t0)/1e9:.1f} GB/s), free {1e3*(t2-t1):.1f} ms", flush=True)
+        lam0, W, mu, tau, A = synth.ln_params(K, 2, density=0.05)
+        from nhp_b200.core import _fmat
+        pl0, pW, pA, pmu, ptau = (np.ascontiguousarray(lam0), _fmat(W), _fmat(A), _fmat(mu), _fmat(tau))
+        for rep in range(3):
+            t0 = time.perf_counter()
+            ctx.check(ctx.lib.nhp_cont_params_set(ctx.h, 1, K, _ptr(pl0), _ptr(pW), _ptr(pA), _ptr(pmu), _ptr(ptau), 1.0))
+            print(f"params_set K={K}: {1e3*(time.perf_counter()-t0):.1f} ms", flush=True)
+        sys.exit(0)
     if which == "one":  # one K n rate density [kind] [reps]
         K, n, rate = int(sys.argv[2]), int(float(sys.argv[3])), float(sys.argv[4])
         dens = None if sys.argv[5] == "none" else float(sys.argv[5])
