@@ -1,0 +1,343 @@
+// cont_sparse.cu -- window sweeps for sparse effective weights (ContinuousNetworkHawkesProcess with a
+// Bernoulli adjacency, continuous.jl:315-321, 521-525): a pair contributes a*w*pdf, which is exactly 0
+// wherever A[p,c]*W[p,c] == 0, so only the active pairs need the FP64 impulse evaluation.
+//
+// Per CTA (tile of TE consecutive child events, window staged by TMA exactly as the dense sweep):
+//   1. filter  -- four threads per child event, each walking a contiguous quarter of the window
+//                 most-recent-first and testing one adjacency bit per predecessor.  The bit-rows of the
+//                 tile's children are staged in shared memory by coalesced warp loads (row of event e
+//                 at [e*wp .. ), wp odd); the hits are flagged in a 64-bit register mask.
+//   2. compact -- block exclusive scan of the hit counts -> contiguous, ordered segment per event.
+//   3. evaluate-- all threads stride over the dense hit list: table gather (L2) + FP64 impulse.
+//   4. combine -- one thread per event folds its segment in window order: log-likelihood term, or the
+//                 inverse-cdf parent draw of parents.jl:25-46 (zero-weight entries can never be drawn and
+//                 do not move the cumulative sum, so skipping them is exact) + fused statistics.
+// Events whose window share exceeds the 64-bit mask, tiles with more hits than the list holds, and tiles
+// whose window does not fit the staging buffer take the direct path (same arithmetic, in place).
+#include "cont_sweep.cuh"
+
+enum { SP_LOGLIK = 0, SP_INTENSITY = 1, SP_PARENTS = 2 };
+
+struct SparseArgs {
+    SweepArgs s;
+    const uint32_t *abits;  // [K * words] child-major bit rows (bit p of row c <=> A*W*... != 0)
+    int words;
+    int cape;               // capacity of the per-tile hit list
+    int m0_smem;            // baseline-count histogram lives in shared memory (K small enough)
+};
+
+template <int KIND, bool ST>
+__device__ __forceinline__ double direct_sum(const SweepArgs &a, const Tile &tl, const FastTables *ft, int64_t i, double ti, int ci, int64_t jlo) {
+    typedef typename EntryOf<KIND>::type E;
+    const E *col = reinterpret_cast<const E *>(a.table) + (size_t)ci * a.K;
+    const double thr = ti - a.horizon;
+    double acc = 0.0;
+    for (int64_t j = i - 1; j >= jlo; j--) {
+        double tj = tile_T<ST>(a, tl, j);
+        if (!(tj > thr)) break;
+        acc += pair_value(load_entry(col + tile_C<ST>(a, tl, j)), ti - tj, a.D, ft);
+    }
+    return acc;
+}
+
+// inverse-cdf walk over the full window (direct path): returns i - j of the chosen parent, 0 = baseline
+template <int KIND, bool ST>
+__device__ __forceinline__ int direct_pick(const SweepArgs &a, const Tile &tl, const FastTables *ft, int64_t i, double ti, int ci, int64_t jlo, double target) {
+    typedef typename EntryOf<KIND>::type E;
+    const E *col = reinterpret_cast<const E *>(a.table) + (size_t)ci * a.K;
+    const double thr = ti - a.horizon;
+    double cum = 0.0;
+    for (int64_t j = i - 1; j >= jlo; j--) {
+        double tj = tile_T<ST>(a, tl, j);
+        if (!(tj > thr)) break;
+        cum += pair_value(load_entry(col + tile_C<ST>(a, tl, j)), ti - tj, a.D, ft);
+        if (cum > target) return (int)(i - j);
+    }
+    return 0;
+}
+
+template <int KIND, bool ST>
+__device__ __forceinline__ void finish_parent(const SweepArgs &a, const Tile &tl, int64_t i, double ti, int ci, double S, int chosen, int *m0_hist) {
+    const StatsLayout sl{a.K};
+    if (!(S > 0.0) || S > 1.7976931348623157e308) atomicOr(a.flag, 8);
+    a.poff[i] = chosen;
+    if (chosen == 0) {
+        if (m0_hist) atomicAdd(m0_hist + ci, 1);  // most events are baseline events: keep that counter in shared memory
+        else red_add_f64(a.stats + sl.off_M0() + ci, 1.0);
+    }
+    else {
+        int64_t jp = i - chosen;
+        int cj = tile_C<ST>(a, tl, jp);
+        double dt = ti - tile_T<ST>(a, tl, jp);
+        int64_t k = cj + (int64_t)a.K * ci;
+        red_add_f64(a.stats + sl.off_Mnm() + k, 1.0);
+        red_add_f64(a.stats + sl.off_S1() + k, KIND == NHP_LOGITNORMAL ? log_duration_dev(dt, a.D) : dt);
+    }
+}
+
+constexpr int SG = 4;                   // threads per child event in the filter
+constexpr int STE = NHP_BLOCK / SG;     // child events per tile
+constexpr int SQMAX = 64;               // window entries one filter thread can flag (64-bit hit mask)
+
+// Persistent CTAs: each loops over tiles of STE child events so the per-CTA set-up (log/exp tables,
+// barrier init) is paid once.
+template <int KIND, int MODE>
+__global__ void __launch_bounds__(NHP_BLOCK, 5) k_sweep_sparse(const SparseArgs sa, const int64_t ntiles) {
+    typedef typename EntryOf<KIND>::type E;
+    const SweepArgs &a = sa.s;
+    extern __shared__ __align__(128) unsigned char smem[];
+    __shared__ double red[16];
+    __shared__ FastTables s_ft;
+    __shared__ int s_wsum[NHP_BLOCK / 32];
+    __shared__ int s_eoff[STE], s_ecnt[STE];  // per event: segment offset, hit count (-1 = direct path)
+    fast_tables_load(&s_ft);
+    const FastTables *ft = &s_ft;
+    uint64_t *bar = reinterpret_cast<uint64_t *>(smem);
+    double *st = reinterpret_cast<double *>(smem + 16);
+    int *sc = reinterpret_cast<int *>(smem + 16 + (size_t)a.cap * 8);
+    if (threadIdx.x == 0) { mbar_init(bar, 1); fence_mbar_init(); }
+    unsigned char *p = smem + 16 + (size_t)a.cap * 12;
+    p = (unsigned char *)(((uintptr_t)p + 15) & ~(uintptr_t)15);
+    const int wp = sa.words | 1;                                     // odd row pitch spreads the banks
+    uint32_t *rows = reinterpret_cast<uint32_t *>(p);                // [STE][wp]
+    uint32_t *list = rows + (size_t)wp * STE;                        // [sa.cape] (event << 16) | (i - j)
+    double *val = reinterpret_cast<double *>((((uintptr_t)(list + sa.cape)) + 7) & ~(uintptr_t)7);  // [sa.cape]
+    int *m0_hist = (MODE == SP_PARENTS && sa.m0_smem) ? reinterpret_cast<int *>(val + sa.cape) : nullptr;     // [K]
+    if (m0_hist) for (int k = threadIdx.x; k < a.K; k += NHP_BLOCK) m0_hist[k] = 0;
+    const int e = threadIdx.x / SG, g = threadIdx.x % SG;
+    const unsigned gmask = group_mask<SG>();
+    double sum_log = 0.0, sum_row = 0.0;
+    uint32_t parity = 0;
+    __syncthreads();
+
+    for (int64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+        Tile tl;
+        tl.i0 = a.first + tile * STE;
+        tl.i1 = min(a.n, tl.i0 + (int64_t)STE);
+        tl.lo = a.tile_lo[tile];
+        tl.base = tl.lo & ~(int64_t)3;
+        tl.st = st; tl.sc = sc;
+        const int64_t cnt_stage = (tl.i1 - tl.base + 3) & ~(int64_t)3;
+        tl.staged = cnt_stage <= a.cap;
+        const int64_t jlo = max(tl.lo, a.jmin);
+        if (tl.staged) {
+            if (threadIdx.x == 0) {
+                mbar_expect_tx(bar, (uint32_t)(cnt_stage * 12));
+                bulk_g2s(st, a.t + tl.base, (uint32_t)(cnt_stage * 8), bar);
+                bulk_g2s(sc, a.c + tl.base, (uint32_t)(cnt_stage * 4), bar);
+            }
+            mbar_wait(bar, parity);
+            parity ^= 1u;
+        }
+        const int64_t i = tl.i0 + e;
+        const bool live = i < tl.i1;
+        const int ib = (int)(i - tl.base);
+        if (!tl.staged) {  // window larger than the staging buffer: direct path from global memory
+            if (live && g == 0) {
+                const double ti = __ldg(a.t + i);
+                const int ci = __ldg(a.c + i);
+                const double S = direct_sum<KIND, false>(a, tl, ft, i, ti, ci, jlo) + __ldg(a.lambda0 + ci);
+                if (MODE == SP_LOGLIK) { sum_log += log(S); sum_row += __ldg(a.rowsum + ci); }
+                else if (MODE == SP_INTENSITY) a.lam_out[i - a.first] = S;
+                else {
+                    const int64_t gi = a.index_base + i;
+                    const double u = a.u ? __ldg(a.u + (i - a.first)) : philox_uniform(a.seed, (uint64_t)gi, a.counter);
+                    int chosen = gi == 0 ? 0 : direct_pick<KIND, false>(a, tl, ft, i, ti, ci, jlo, u * S);
+                    finish_parent<KIND, false>(a, tl, i, ti, ci, S, chosen, m0_hist);
+                }
+            }
+            __syncthreads();
+            continue;
+        }
+        // ---- 1. filter -------------------------------------------------------------------------------------
+        const int ci = live ? sc[ib] : 0;
+        // adjacency bit-rows of the warp's 8 children: one coalesced load + one conflict-free store per row
+        {
+            const int lane = threadIdx.x & 31;
+            uint32_t *dst = rows + (size_t)((threadIdx.x >> 5) * (32 / SG)) * wp + lane;
+#pragma unroll
+            for (int r = 0; r < 32 / SG; r++) {
+                const int cr = __shfl_sync(0xffffffffu, ci, r * SG);
+                const uint32_t *row = sa.abits + (size_t)cr * sa.words + lane;
+                if (lane < sa.words) dst[r * wp] = __ldg(row);
+                for (int w = 32; w + lane < sa.words; w += 32) dst[r * wp + w] = __ldg(row + w);
+            }
+        }
+        __syncwarp();
+        unsigned long long hits = 0ull;
+        int k0 = 0;
+        bool over = false;
+        if (live) {
+            // window start: first j in [jlo, i) with t_j > t_i - horizon (binary search on the staged times)
+            const double thr = st[ib] - a.horizon;
+            int lo = (int)(jlo - tl.base), hi = ib;
+            while (lo < hi) { int mid = (lo + hi) >> 1; if (st[mid] > thr) hi = mid; else lo = mid + 1; }
+            const int wlen = ib - lo;
+            // this thread's contiguous share of the window, most recent first: positions k0+1 .. k1
+            const int q = (wlen + SG - 1) / SG;
+            k0 = g * q;
+            const int k1 = min(wlen, k0 + q);
+            over = q > SQMAX || wlen > 65535;
+            if (!over) {
+                const uint32_t *myrow = rows + (size_t)e * wp;
+                const int *src = sc + ib - k0 - 1;  // position k0+1+m is src[-m]
+                const int cntk = k1 - k0;
+                int m = 0;
+                for (; m + 4 <= cntk; m += 4) {  // four independent probes per trip
+                    int p0 = src[-m], p1 = src[-m - 1], p2 = src[-m - 2], p3 = src[-m - 3];
+                    uint32_t w0 = myrow[p0 >> 5], w1 = myrow[p1 >> 5], w2 = myrow[p2 >> 5], w3 = myrow[p3 >> 5];
+                    unsigned long long b4 = (unsigned long long)(((w0 >> (p0 & 31)) & 1u) | (((w1 >> (p1 & 31)) & 1u) << 1) |
+                                                                 (((w2 >> (p2 & 31)) & 1u) << 2) | (((w3 >> (p3 & 31)) & 1u) << 3));
+                    hits |= b4 << m;
+                }
+                for (; m < cntk; m++) {
+                    int p0 = src[-m];
+                    hits |= (unsigned long long)((myrow[p0 >> 5] >> (p0 & 31)) & 1u) << m;
+                }
+            }
+        }
+        const bool overflow = (__ballot_sync(0xffffffffu, over) & gmask) != 0u;
+        const int cnt = overflow ? 0 : __popcll(hits);
+        // ---- 2. compact: exclusive scan of cnt over the block (thread order == (event, window order)) -------
+        int x = cnt;
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) { int y = __shfl_up_sync(0xffffffffu, x, d); if ((threadIdx.x & 31) >= d) x += y; }
+        if ((threadIdx.x & 31) == 31) s_wsum[threadIdx.x >> 5] = x;
+        __syncthreads();
+        int off = x - cnt, total = 0;
+#pragma unroll
+        for (int w = 0; w < NHP_BLOCK / 32; w++) { int v = s_wsum[w]; if (w < (int)(threadIdx.x >> 5)) off += v; total += v; }
+        const bool fits = total <= sa.cape;  // block-uniform; otherwise every event of the tile takes the direct path
+        if (fits) {
+            unsigned long long h = hits;
+            int o = off;
+            while (h) {
+                int b = __ffsll((long long)h) - 1;
+                h &= h - 1;
+                list[o++] = ((uint32_t)e << 16) | (uint32_t)(k0 + 1 + b);
+            }
+        }
+        {
+            int ecnt = cnt;
+#pragma unroll
+            for (int d = SG / 2; d >= 1; d >>= 1) ecnt += __shfl_xor_sync(gmask, ecnt, d, SG);
+            if (g == 0) { s_eoff[e] = off; s_ecnt[e] = (overflow || !fits) ? -1 : ecnt; }
+        }
+        __syncthreads();
+        // ---- 3. evaluate the active pairs ------------------------------------------------------------------
+        if (fits) {
+            for (int qd = threadIdx.x; qd < total; qd += NHP_BLOCK) {
+                uint32_t en = list[qd];
+                int ibe = (int)(tl.i0 - tl.base) + (int)(en >> 16), k = (int)(en & 0xffff);
+                const E *col = reinterpret_cast<const E *>(a.table) + (size_t)sc[ibe] * a.K;
+                val[qd] = pair_value(load_entry(col + sc[ibe - k]), st[ibe] - st[ibe - k], a.D, ft);
+            }
+        }
+        __syncthreads();
+        // ---- 4. combine: thread ev < STE owns event ev (two warps instead of eight quarter-filled ones) ------
+        if (threadIdx.x < STE && tl.i0 + threadIdx.x < tl.i1) {
+            const int64_t ie = tl.i0 + threadIdx.x;
+            const int ibe = (int)(ie - tl.base);
+            const double ti = st[ibe];
+            const int ce = sc[ibe];
+            const int ecnt = s_ecnt[threadIdx.x], eoff = s_eoff[threadIdx.x];
+            double S = 0.0;
+            if (ecnt < 0) S = direct_sum<KIND, true>(a, tl, ft, ie, ti, ce, jlo);
+            else for (int k = 0; k < ecnt; k++) S += val[eoff + k];
+            S += __ldg(a.lambda0 + ce);
+            if (MODE == SP_LOGLIK) { sum_log += log(S); sum_row += __ldg(a.rowsum + ce); }
+            else if (MODE == SP_INTENSITY) a.lam_out[ie - a.first] = S;
+            else {
+                const int64_t gi = a.index_base + ie;
+                const double u = a.u ? __ldg(a.u + (ie - a.first)) : philox_uniform(a.seed, (uint64_t)gi, a.counter);
+                const double target = u * S;
+                int chosen = 0;
+                if (gi != 0) {
+                    if (ecnt < 0) chosen = direct_pick<KIND, true>(a, tl, ft, ie, ti, ce, jlo, target);
+                    else {
+                        double cum = 0.0;
+                        for (int k = 0; k < ecnt; k++) {
+                            cum += val[eoff + k];
+                            if (cum > target) { chosen = (int)(list[eoff + k] & 0xffff); break; }
+                        }
+                    }
+                }
+                finish_parent<KIND, true>(a, tl, ie, ti, ce, S, chosen, m0_hist);
+            }
+        }
+        __syncthreads();  // staging buffers, rows, list and val are reused by the next tile
+    }
+    if (MODE == SP_LOGLIK) {
+        block_sum2(sum_log, sum_row, red);
+        if (threadIdx.x == 0) { a.partials[2 * (size_t)blockIdx.x] = sum_log; a.partials[2 * (size_t)blockIdx.x + 1] = sum_row; }
+    }
+    if (m0_hist) {
+        const StatsLayout sl{a.K};
+        for (int k = threadIdx.x; k < a.K; k += NHP_BLOCK)
+            if (m0_hist[k]) red_add_f64(a.stats + sl.off_M0() + k, (double)m0_hist[k]);
+    }
+}
+
+// ---------------------------------------------------------------------------------------
+// host side: decide whether the sparse path applies and launch it
+// ---------------------------------------------------------------------------------------
+size_t nhp_sparse_smem(int cap, int words, int lcap, int m0_entries) {
+    size_t b = 16 + (size_t)cap * 12 + 16;
+    b += (size_t)(words | 1) * STE * 4;
+    b += (size_t)lcap * 4 + 8;
+    b += (size_t)lcap * 8;
+    b += (size_t)m0_entries * 4;
+    return b;
+}
+
+template <typename KernelT> static int launch_sparse(nhp_ctx *ctx, KernelT kernel, int *grid_out, size_t smem, const SparseArgs &sa, int64_t ntiles) {
+    if (smem > 48 * 1024) NHP_CUDA(ctx, cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    NHP_CUDA(ctx, cudaFuncSetAttribute(kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
+    int per_sm = 1;
+    NHP_CUDA(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, NHP_BLOCK, smem));
+    int grid = (int)std::min<int64_t>(ntiles, (int64_t)ctx->sm_count * std::max(per_sm, 1));  // persistent: exactly one resident wave
+    *grid_out = grid;
+    kernel<<<grid, NHP_BLOCK, smem, ctx->stream>>>(sa, ntiles);
+    NHP_LAUNCHED(ctx);
+    NHP_CUDA(ctx, cudaGetLastError());
+    return NHP_OK;
+}
+
+// mode: 0 loglik, 1 intensity, 2 parents.  Returns NHP_OK after launching (grid size in *grid_out: the number of
+// log-likelihood partials), 1 if the sparse path does not apply, < 0 on error.
+int nhp_cont_try_sparse(nhp_ctx *ctx, const nhp_events *ev, SweepArgs &a, int mode, int *grid_out) {
+    const char *env = getenv("NHP_SPARSE");
+    if (env && atoi(env) == 0) return 1;
+    bool force = env && atoi(env) == 1;
+    if (!force && !(ctx->density <= 0.25)) return 1;
+    int words = (int)ctx->abits_words;
+    // capacity of the per-tile hit list: 3x the expected number of active pairs of a tile, at least 512
+    double expect = ev->mean_win * ctx->density * STE;
+    int lcap = 512;
+    while (lcap < 16384 && lcap < 3.0 * expect + 256.0) lcap <<= 1;
+    int64_t own = ev->n - ev->n_halo;
+    int64_t need = ((ev->max_win + STE + 8) + 3) & ~(int64_t)3;
+    int cap = (int)std::min<int64_t>(need, 8192);
+    int m0_entries = (mode == 2 && ctx->K <= 4096) ? (int)ctx->K : 0;
+    size_t smem = nhp_sparse_smem(cap, words, lcap, m0_entries);
+    if (smem > 100 * 1024) {
+        cap = (int)std::min<int64_t>(need, 1024);
+        smem = nhp_sparse_smem(cap, words, lcap, m0_entries);
+        if (smem > (size_t)ctx->smem_optin - 4096) return 1;
+    }
+    int64_t ntiles = (own + STE - 1) / STE;
+    if (ntiles == 0) return 1;
+    NHP_CUDA(ctx, fast_tables_upload(ctx->stream));  // this translation unit's copy of the log/exp tables
+    SparseArgs sa;
+    a.te = STE; a.cap = cap;
+    sa.s = a; sa.abits = ctx->d_abits; sa.words = words; sa.cape = lcap; sa.m0_smem = m0_entries > 0;
+    int *grid = grid_out;
+    if (ctx->kind == NHP_LOGITNORMAL) {
+        if (mode == 0) return launch_sparse(ctx, k_sweep_sparse<NHP_LOGITNORMAL, SP_LOGLIK>, grid, smem, sa, ntiles);
+        if (mode == 1) return launch_sparse(ctx, k_sweep_sparse<NHP_LOGITNORMAL, SP_INTENSITY>, grid, smem, sa, ntiles);
+        return launch_sparse(ctx, k_sweep_sparse<NHP_LOGITNORMAL, SP_PARENTS>, grid, smem, sa, ntiles);
+    }
+    if (mode == 0) return launch_sparse(ctx, k_sweep_sparse<NHP_EXPONENTIAL, SP_LOGLIK>, grid, smem, sa, ntiles);
+    if (mode == 1) return launch_sparse(ctx, k_sweep_sparse<NHP_EXPONENTIAL, SP_INTENSITY>, grid, smem, sa, ntiles);
+    return launch_sparse(ctx, k_sweep_sparse<NHP_EXPONENTIAL, SP_PARENTS>, grid, smem, sa, ntiles);
+}

@@ -66,7 +66,7 @@ int nhp_cont_prepare_windows(nhp_ctx *ctx, nhp_events *ev, double horizon) {
 }
 
 // ---------------------------------------------------------------------------------------
-// log-likelihood / intensity sweep
+// log-likelihood / intensity sweep (persistent CTAs looping over tiles of a.te child events)
 // ---------------------------------------------------------------------------------------
 template <int KIND, int G, int MODE, bool ST>
 __device__ __forceinline__ void sweep_body(const SweepArgs &a, const Tile &tl, const FastTables *ft, double &sum_log, double &sum_row) {
@@ -74,39 +74,45 @@ __device__ __forceinline__ void sweep_body(const SweepArgs &a, const Tile &tl, c
     constexpr int NG = NHP_BLOCK / G;
     const int gid = threadIdx.x / G, gl = threadIdx.x % G;
     const unsigned gmask = group_mask<G>();
-    const int64_t jlo = max(tl.lo, a.jmin);
-    for (int64_t i = tl.i0 + gid; i < tl.i1; i += NG) {
-        const double ti = tile_T<ST>(a, tl, i);
-        const int ci = tile_C<ST>(a, tl, i);
+    const WinView<ST> W(a, tl);
+    const int jl_lo = (int)(max(tl.lo, a.jmin) - tl.base);
+    const int ib0 = (int)(tl.i0 - tl.base), nev = (int)(tl.i1 - tl.i0);
+    for (int ev = gid; ev < nev; ev += NG) {
+        const int ib = ib0 + ev;
+        const double ti = W.T(ib);
+        const int ci = W.C(ib);
         const double thr = ti - a.horizon;
         const E *col = reinterpret_cast<const E *>(a.table) + (size_t)ci * a.K;
         double acc = 0.0;
-        for (int64_t j = i - 1 - gl; j >= jlo; j -= G) {
-            double tj = tile_T<ST>(a, tl, j);
+        for (int jl = ib - 1 - gl; jl >= jl_lo; jl -= G) {
+            const double tj = W.T(jl);
             if (!(tj > thr)) break;  // events[parentindex] > time - dtmax   (continuous.jl:291)
-            int cj = tile_C<ST>(a, tl, j);
-            acc += pair_value(load_entry(col + cj), ti - tj, a.D, ft);
+            acc += pair_value(load_entry(col + W.C(jl)), ti - tj, a.D, ft);
         }
         acc = group_sum<G>(acc, gmask);
         if (gl == 0) {
-            double lam = __ldg(a.lambda0 + ci) + acc;
-            if (MODE == MODE_INTENSITY) a.lam_out[i - a.first] = lam;
+            const double lam = __ldg(a.lambda0 + ci) + acc;
+            if (MODE == MODE_INTENSITY) a.lam_out[tl.i0 + ev - a.first] = lam;
             else { sum_log += log(lam); sum_row += __ldg(a.rowsum + ci); }
         }
     }
 }
 
 template <int KIND, int G, int MODE>
-__global__ void __launch_bounds__(NHP_BLOCK) k_sweep(const SweepArgs a) {
+__global__ void __launch_bounds__(NHP_BLOCK) k_sweep(const SweepArgs a, const int64_t ntiles) {
     extern __shared__ __align__(128) unsigned char smem[];
     __shared__ double red[16];
     __shared__ FastTables s_ft;
     fast_tables_load(&s_ft);
+    Stager sg = stager_init(a, smem);
     __syncthreads();
-    Tile tl = stage_tile(a, smem);
     double sum_log = 0.0, sum_row = 0.0;
-    if (tl.staged) sweep_body<KIND, G, MODE, true>(a, tl, &s_ft, sum_log, sum_row);
-    else sweep_body<KIND, G, MODE, false>(a, tl, &s_ft, sum_log, sum_row);
+    for (int64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+        Tile tl = stage_tile_at(a, sg, tile);
+        if (tl.staged) sweep_body<KIND, G, MODE, true>(a, tl, &s_ft, sum_log, sum_row);
+        else sweep_body<KIND, G, MODE, false>(a, tl, &s_ft, sum_log, sum_row);
+        __syncthreads();  // the staging buffers are refilled by the next tile
+    }
     if (MODE == MODE_LOGLIK) {
         block_sum2(sum_log, sum_row, red);
         if (threadIdx.x == 0) { a.partials[2 * (size_t)blockIdx.x] = sum_log; a.partials[2 * (size_t)blockIdx.x + 1] = sum_row; }
@@ -132,38 +138,43 @@ __global__ void k_reduce_partials(const double *__restrict__ partials, int64_t n
 // one uniform per event, inverse-cdf walk in that order; fused statistics.
 // ---------------------------------------------------------------------------------------
 template <int KIND, int G, int R, bool ST>
-__device__ __forceinline__ void parents_body(const SweepArgs &a, const Tile &tl, const FastTables *ft) {
+__device__ __forceinline__ void parents_body(const SweepArgs &a, const Tile &tl, const FastTables *ft, int *m0_hist) {
     typedef typename EntryOf<KIND>::type E;
     constexpr int NG = NHP_BLOCK / G;
     const int gid = threadIdx.x / G, gl = threadIdx.x % G;
     const unsigned gmask = group_mask<G>();
     const int gshift = (threadIdx.x & 31) / G * G;
-    const int64_t jlo = max(tl.lo, a.jmin);
+    const unsigned gbits = G == 32 ? 0xffffffffu : ((1u << G) - 1u);
+    const WinView<ST> W(a, tl);
+    const int jl_lo = (int)(max(tl.lo, a.jmin) - tl.base);
+    const int ib0 = (int)(tl.i0 - tl.base), nev = (int)(tl.i1 - tl.i0);
     const StatsLayout sl{a.K};
-    for (int64_t i = tl.i0 + gid; i < tl.i1; i += NG) {
-        const double ti = tile_T<ST>(a, tl, i);
-        const int ci = tile_C<ST>(a, tl, i);
+    for (int ev = gid; ev < nev; ev += NG) {
+        const int ib = ib0 + ev;
+        const int64_t i = tl.i0 + ev;
+        const double ti = W.T(ib);
+        const int ci = W.C(ib);
         const double thr = ti - a.horizon;
         const E *col = reinterpret_cast<const E *>(a.table) + (size_t)ci * a.K;
         // pass 1: weights; the first R rows (G entries each) stay in registers
         double vc[R];
         double acc = 0.0;
-        int64_t j = i - 1 - gl;
+        int jl = ib - 1 - gl;
 #pragma unroll
         for (int r = 0; r < R; r++) {
             double v = 0.0;
-            if (j >= jlo) {
-                double tj = tile_T<ST>(a, tl, j);
-                if (tj > thr) v = pair_value(load_entry(col + tile_C<ST>(a, tl, j)), ti - tj, a.D, ft);
+            if (jl >= jl_lo) {
+                const double tj = W.T(jl);
+                if (tj > thr) v = pair_value(load_entry(col + W.C(jl)), ti - tj, a.D, ft);
             }
             vc[r] = v;
             acc += v;
-            j -= G;
+            jl -= G;
         }
-        for (; j >= jlo; j -= G) {
-            double tj = tile_T<ST>(a, tl, j);
+        for (; jl >= jl_lo; jl -= G) {
+            const double tj = W.T(jl);
             if (!(tj > thr)) break;
-            acc += pair_value(load_entry(col + tile_C<ST>(a, tl, j)), ti - tj, a.D, ft);
+            acc += pair_value(load_entry(col + W.C(jl)), ti - tj, a.D, ft);
         }
         const double lam0 = __ldg(a.lambda0 + ci);
         const double S = group_sum<G>(acc, gmask) + lam0;  // sum([weights...; baseline])
@@ -177,36 +188,38 @@ __device__ __forceinline__ void parents_body(const SweepArgs &a, const Tile &tl,
 #pragma unroll
         for (int r = 0; r < R; r++) {
             if (!done) {
-                double x = group_incl_scan<G>(vc[r], gmask, gl);
-                unsigned b = (__ballot_sync(gmask, carry + x > target) >> gshift) & (G == 32 ? 0xffffffffu : ((1u << G) - 1u));
+                const double x = group_incl_scan<G>(vc[r], gmask, gl);
+                const unsigned b = (__ballot_sync(gmask, carry + x > target) >> gshift) & gbits;
                 if (b) { chosen = r * G + (__ffs(b) - 1) + 1; done = true; }
                 carry += __shfl_sync(gmask, x, G - 1, G);
             }
         }
         if (!done) {
-            for (int64_t jr = i - 1 - (int64_t)R * G; jr >= jlo; jr -= G) {  // jr: the row's most recent entry
-                if (!(tile_T<ST>(a, tl, jr) > thr)) break;
-                int64_t jj = jr - gl;
+            for (int jr = ib - 1 - R * G; jr >= jl_lo; jr -= G) {  // jr: the row's most recent entry
+                if (!(W.T(jr) > thr)) break;
+                const int jj = jr - gl;
                 double v = 0.0;
-                if (jj >= jlo) {
-                    double tj = tile_T<ST>(a, tl, jj);
-                    if (tj > thr) v = pair_value(load_entry(col + tile_C<ST>(a, tl, jj)), ti - tj, a.D, ft);
+                if (jj >= jl_lo) {
+                    const double tj = W.T(jj);
+                    if (tj > thr) v = pair_value(load_entry(col + W.C(jj)), ti - tj, a.D, ft);
                 }
-                double x = group_incl_scan<G>(v, gmask, gl);
-                unsigned b = (__ballot_sync(gmask, carry + x > target) >> gshift) & (G == 32 ? 0xffffffffu : ((1u << G) - 1u));
-                if (b) { chosen = (int)(i - jr) + (__ffs(b) - 1); break; }
+                const double x = group_incl_scan<G>(v, gmask, gl);
+                const unsigned b = (__ballot_sync(gmask, carry + x > target) >> gshift) & gbits;
+                if (b) { chosen = (ib - jr) + (__ffs(b) - 1); break; }
                 carry += __shfl_sync(gmask, x, G - 1, G);
             }
         }
         if (gl == 0) {
             if (!(S > 0.0) || S > 1.7976931348623157e308) atomicOr(a.flag, 8);  // Categorical would reject the vector
             a.poff[i] = chosen;
-            if (chosen == 0) red_add_f64(a.stats + sl.off_M0() + ci, 1.0);
-            else {
-                int64_t jp = i - chosen;
-                int cj = tile_C<ST>(a, tl, jp);
-                double dt = ti - tile_T<ST>(a, tl, jp);
-                int64_t k = cj + (int64_t)a.K * ci;
+            if (chosen == 0) {
+                if (m0_hist) atomicAdd(m0_hist + ci, 1);
+                else red_add_f64(a.stats + sl.off_M0() + ci, 1.0);
+            } else {
+                const int jp = ib - chosen;
+                const int cj = W.C(jp);
+                const double dt = ti - W.T(jp);
+                const int64_t k = cj + (int64_t)a.K * ci;
                 red_add_f64(a.stats + sl.off_Mnm() + k, 1.0);
                 red_add_f64(a.stats + sl.off_S1() + k, KIND == NHP_LOGITNORMAL ? log_duration_dev(dt, a.D) : dt);
             }
@@ -215,14 +228,26 @@ __device__ __forceinline__ void parents_body(const SweepArgs &a, const Tile &tl,
 }
 
 template <int KIND, int G, int R>
-__global__ void __launch_bounds__(NHP_BLOCK) k_parents(const SweepArgs a) {
+__global__ void __launch_bounds__(NHP_BLOCK) k_parents(const SweepArgs a, const int64_t ntiles, const int m0_smem) {
     extern __shared__ __align__(128) unsigned char smem[];
     __shared__ FastTables s_ft;
     fast_tables_load(&s_ft);
+    Stager sg = stager_init(a, smem);
+    // baseline-attribution histogram in shared memory behind the staging area (most events are baseline events)
+    int *m0_hist = m0_smem ? reinterpret_cast<int *>(smem + ((16 + (size_t)a.cap * 12 + 15) & ~(size_t)15)) : nullptr;
+    if (m0_hist) for (int k = threadIdx.x; k < a.K; k += NHP_BLOCK) m0_hist[k] = 0;
     __syncthreads();
-    Tile tl = stage_tile(a, smem);
-    if (tl.staged) parents_body<KIND, G, R, true>(a, tl, &s_ft);
-    else parents_body<KIND, G, R, false>(a, tl, &s_ft);
+    for (int64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+        Tile tl = stage_tile_at(a, sg, tile);
+        if (tl.staged) parents_body<KIND, G, R, true>(a, tl, &s_ft, m0_hist);
+        else parents_body<KIND, G, R, false>(a, tl, &s_ft, m0_hist);
+        __syncthreads();
+    }
+    if (m0_hist) {
+        const StatsLayout sl{a.K};
+        for (int k = threadIdx.x; k < a.K; k += NHP_BLOCK)
+            if (m0_hist[k]) red_add_f64(a.stats + sl.off_M0() + k, (double)m0_hist[k]);
+    }
 }
 
 // ---------------------------------------------------------------------------------------
@@ -305,7 +330,7 @@ static int pick_group(const nhp_events *ev) {
     return 32;
 }
 
-struct LaunchPlan { int G, te, cap; size_t smem; int64_t tiles; };
+struct LaunchPlan { int G, te, cap, grid; size_t smem; int64_t tiles; };
 
 static LaunchPlan make_plan(nhp_ctx *ctx, const nhp_events *ev) {
     LaunchPlan p;
@@ -325,33 +350,41 @@ static LaunchPlan make_plan(nhp_ctx *ctx, const nhp_events *ev) {
     return p;
 }
 
-template <typename KernelT> static int launch_sweep(nhp_ctx *ctx, KernelT kernel, const LaunchPlan &p, const SweepArgs &a) {
-    if (p.smem > 48 * 1024) NHP_CUDA(ctx, cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p.smem));
-    kernel<<<(unsigned)p.tiles, NHP_BLOCK, p.smem, ctx->stream>>>(a);
+// persistent launch: one resident wave of CTAs looping over the tiles
+template <typename KernelT, typename... Extra>
+static int launch_persistent(nhp_ctx *ctx, KernelT kernel, LaunchPlan &p, size_t smem, const SweepArgs &a, Extra... extra) {
+    if (smem > 48 * 1024) NHP_CUDA(ctx, cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    NHP_CUDA(ctx, cudaFuncSetAttribute(kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
+    int per_sm = 1;
+    NHP_CUDA(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, NHP_BLOCK, smem));
+    p.grid = (int)std::min<int64_t>(p.tiles, (int64_t)ctx->sm_count * std::max(per_sm, 1));
+    kernel<<<p.grid, NHP_BLOCK, smem, ctx->stream>>>(a, p.tiles, extra...);
     NHP_LAUNCHED(ctx);
     NHP_CUDA(ctx, cudaGetLastError());
     return NHP_OK;
 }
 
-template <int KIND, int MODE> static int dispatch_sweep(nhp_ctx *ctx, const LaunchPlan &p, const SweepArgs &a) {
+template <int KIND, int MODE> static int dispatch_sweep(nhp_ctx *ctx, LaunchPlan &p, const SweepArgs &a) {
     switch (p.G) {
-        case 1: return launch_sweep(ctx, k_sweep<KIND, 1, MODE>, p, a);
-        case 2: return launch_sweep(ctx, k_sweep<KIND, 2, MODE>, p, a);
-        case 4: return launch_sweep(ctx, k_sweep<KIND, 4, MODE>, p, a);
-        case 8: return launch_sweep(ctx, k_sweep<KIND, 8, MODE>, p, a);
-        case 16: return launch_sweep(ctx, k_sweep<KIND, 16, MODE>, p, a);
-        default: return launch_sweep(ctx, k_sweep<KIND, 32, MODE>, p, a);
+        case 1: return launch_persistent(ctx, k_sweep<KIND, 1, MODE>, p, p.smem, a);
+        case 2: return launch_persistent(ctx, k_sweep<KIND, 2, MODE>, p, p.smem, a);
+        case 4: return launch_persistent(ctx, k_sweep<KIND, 4, MODE>, p, p.smem, a);
+        case 8: return launch_persistent(ctx, k_sweep<KIND, 8, MODE>, p, p.smem, a);
+        case 16: return launch_persistent(ctx, k_sweep<KIND, 16, MODE>, p, p.smem, a);
+        default: return launch_persistent(ctx, k_sweep<KIND, 32, MODE>, p, p.smem, a);
     }
 }
 
-template <int KIND> static int dispatch_parents(nhp_ctx *ctx, const LaunchPlan &p, const SweepArgs &a) {
+template <int KIND> static int dispatch_parents(nhp_ctx *ctx, LaunchPlan &p, const SweepArgs &a) {
+    const int m0 = a.K <= 8192 ? 1 : 0;
+    const size_t smem = m0 ? ((p.smem + 15) & ~(size_t)15) + (size_t)a.K * sizeof(int) : p.smem;
     switch (p.G) {
-        case 1: return launch_sweep(ctx, k_parents<KIND, 1, 8>, p, a);
-        case 2: return launch_sweep(ctx, k_parents<KIND, 2, 8>, p, a);
-        case 4: return launch_sweep(ctx, k_parents<KIND, 4, 8>, p, a);
-        case 8: return launch_sweep(ctx, k_parents<KIND, 8, 8>, p, a);
-        case 16: return launch_sweep(ctx, k_parents<KIND, 16, 4>, p, a);
-        default: return launch_sweep(ctx, k_parents<KIND, 32, 2>, p, a);
+        case 1: return launch_persistent(ctx, k_parents<KIND, 1, 8>, p, smem, a, m0);
+        case 2: return launch_persistent(ctx, k_parents<KIND, 2, 8>, p, smem, a, m0);
+        case 4: return launch_persistent(ctx, k_parents<KIND, 4, 8>, p, smem, a, m0);
+        case 8: return launch_persistent(ctx, k_parents<KIND, 8, 8>, p, smem, a, m0);
+        case 16: return launch_persistent(ctx, k_parents<KIND, 16, 4>, p, smem, a, m0);
+        default: return launch_persistent(ctx, k_parents<KIND, 32, 2>, p, smem, a, m0);
     }
 }
 
@@ -398,15 +431,21 @@ static int fill_args(nhp_ctx *ctx, nhp_events *ev, int recursive, SweepArgs &a, 
     return NHP_OK;
 }
 
+int nhp_cont_try_sparse(nhp_ctx *ctx, const nhp_events *ev, SweepArgs &a, int mode, int *grid_out);  // cont_sparse.cu
+
 // leaves (log-sum, row-sum) in stats0[0..1]; no host synchronisation
 int nhp_cont_run_loglik(nhp_ctx *ctx, nhp_events *ev, int recursive) {
     SweepArgs a; LaunchPlan p;
     NHP_TRY(fill_args(ctx, ev, recursive, a, p));
     if (p.tiles == 0) { NHP_CUDA(ctx, cudaMemsetAsync(ctx->d_stats0, 0, 2 * sizeof(double), ctx->stream)); return NHP_OK; }
-    NHP_TRY(nhp_partials(ctx, 2 * p.tiles, &a.partials));
-    if (ctx->kind == NHP_LOGITNORMAL) NHP_TRY((dispatch_sweep<NHP_LOGITNORMAL, MODE_LOGLIK>(ctx, p, a)));
+    NHP_TRY(nhp_partials(ctx, 2 * (int64_t)ctx->sm_count * 32, &a.partials));  // one partial per persistent CTA
+    int sgrid = 0;
+    int sp = nhp_cont_try_sparse(ctx, ev, a, 0, &sgrid);
+    if (sp < 0) return sp;
+    if (sp == NHP_OK) p.grid = sgrid;
+    else if (ctx->kind == NHP_LOGITNORMAL) NHP_TRY((dispatch_sweep<NHP_LOGITNORMAL, MODE_LOGLIK>(ctx, p, a)));
     else NHP_TRY((dispatch_sweep<NHP_EXPONENTIAL, MODE_LOGLIK>(ctx, p, a)));
-    k_reduce_partials<<<1, 1024, 0, ctx->stream>>>(a.partials, p.tiles, ctx->d_stats0);
+    k_reduce_partials<<<1, 1024, 0, ctx->stream>>>(a.partials, p.grid, ctx->d_stats0);
     NHP_LAUNCHED(ctx);
     NHP_CUDA(ctx, cudaGetLastError());
     return NHP_OK;
@@ -445,7 +484,11 @@ extern "C" int nhp_cont_event_intensity(nhp_ctx *ctx, nhp_events *ev, double *ou
     NHP_TRY(nhp_scratch(ctx, (size_t)own * sizeof(double), &scratch));
     a.lam_out = (double *)scratch;
     NHP_TRY(nhp_timer_begin(ctx));
-    if (ctx->kind == NHP_LOGITNORMAL) NHP_TRY((dispatch_sweep<NHP_LOGITNORMAL, MODE_INTENSITY>(ctx, p, a)));
+    int sgrid = 0;
+    int sp = nhp_cont_try_sparse(ctx, ev, a, 1, &sgrid);
+    if (sp < 0) return sp;
+    if (sp == NHP_OK) {}
+    else if (ctx->kind == NHP_LOGITNORMAL) NHP_TRY((dispatch_sweep<NHP_LOGITNORMAL, MODE_INTENSITY>(ctx, p, a)));
     else NHP_TRY((dispatch_sweep<NHP_EXPONENTIAL, MODE_INTENSITY>(ctx, p, a)));
     NHP_TRY(nhp_timer_end(ctx));
     NHP_CUDA(ctx, cudaMemcpyAsync(out, scratch, (size_t)own * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
@@ -497,7 +540,11 @@ extern "C" int nhp_cont_resample_parents(nhp_ctx *ctx, nhp_events *ev, uint64_t 
     a.u = du; a.seed = seed; a.counter = counter;
     NHP_TRY(nhp_timer_begin(ctx));
     if (p.tiles > 0) {
-        if (ctx->kind == NHP_LOGITNORMAL) NHP_TRY(dispatch_parents<NHP_LOGITNORMAL>(ctx, p, a));
+        int sgrid = 0;
+        int sp = nhp_cont_try_sparse(ctx, ev, a, 2, &sgrid);
+        if (sp < 0) return sp;
+        if (sp == NHP_OK) {}
+        else if (ctx->kind == NHP_LOGITNORMAL) NHP_TRY(dispatch_parents<NHP_LOGITNORMAL>(ctx, p, a));
         else NHP_TRY(dispatch_parents<NHP_EXPONENTIAL>(ctx, p, a));
     }
     int flag = 0;

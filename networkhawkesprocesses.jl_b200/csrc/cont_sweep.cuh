@@ -110,6 +110,70 @@ template <bool ST> __device__ __forceinline__ int tile_C(const SweepArgs &a, con
 }
 
 // ---------------------------------------------------------------------------------------
+// window view with 32-bit local offsets: entry (tl.base + jl) of the stream.  Staged tiles read shared
+// memory through explicit 32-bit shared addresses (plain LDS, no generic-address arithmetic); the
+// fallback reads global memory through the read-only path.
+// ---------------------------------------------------------------------------------------
+__device__ __forceinline__ double lds_f64(uint32_t addr) {
+    double v;
+    asm volatile("ld.shared.f64 %0, [%1];" : "=d"(v) : "r"(addr));
+    return v;
+}
+__device__ __forceinline__ int lds_s32(uint32_t addr) {
+    int v;
+    asm volatile("ld.shared.s32 %0, [%1];" : "=r"(v) : "r"(addr));
+    return v;
+}
+template <bool ST> struct WinView {
+    uint32_t st_addr, sc_addr;
+    const double *gt;
+    const int *gc;
+    __device__ __forceinline__ WinView(const SweepArgs &a, const Tile &tl)
+        : st_addr(smem_u32(tl.st)), sc_addr(smem_u32(tl.sc)), gt(a.t + tl.base), gc(a.c + tl.base) {}
+    __device__ __forceinline__ double T(int jl) const { return ST ? lds_f64(st_addr + 8u * (uint32_t)jl) : __ldg(gt + jl); }
+    __device__ __forceinline__ int C(int jl) const { return ST ? lds_s32(sc_addr + 4u * (uint32_t)jl) : __ldg(gc + jl); }
+};
+
+// persistent-CTA staging: one mbarrier reused across tiles (phase parity tracked by the caller)
+struct Stager {
+    uint64_t *bar;
+    double *st;
+    int *sc;
+    uint32_t parity;
+};
+__device__ __forceinline__ Stager stager_init(const SweepArgs &a, unsigned char *smem) {
+    Stager sg;
+    sg.bar = reinterpret_cast<uint64_t *>(smem);
+    sg.st = reinterpret_cast<double *>(smem + 16);
+    sg.sc = reinterpret_cast<int *>(smem + 16 + (size_t)a.cap * 8);
+    sg.parity = 0;
+    if (threadIdx.x == 0) { mbar_init(sg.bar, 1); fence_mbar_init(); }
+    return sg;  // caller: __syncthreads() before the first stage_tile_at
+}
+// all threads call; the previous tile's readers must have passed a __syncthreads() before
+__device__ __forceinline__ Tile stage_tile_at(const SweepArgs &a, Stager &sg, int64_t tile) {
+    Tile tl;
+    tl.i0 = a.first + tile * a.te;
+    tl.i1 = min(a.n, tl.i0 + (int64_t)a.te);
+    tl.lo = a.tile_lo[tile * (a.te / NHP_TQ)];
+    tl.base = tl.lo & ~(int64_t)3;
+    const int64_t cnt = (tl.i1 - tl.base + 3) & ~(int64_t)3;
+    tl.staged = cnt <= a.cap;
+    tl.st = sg.st;
+    tl.sc = sg.sc;
+    if (tl.staged) {
+        if (threadIdx.x == 0) {
+            mbar_expect_tx(sg.bar, (uint32_t)(cnt * 12));
+            bulk_g2s(sg.st, a.t + tl.base, (uint32_t)(cnt * 8), sg.bar);
+            bulk_g2s(sg.sc, a.c + tl.base, (uint32_t)(cnt * 4), sg.bar);
+        }
+        mbar_wait(sg.bar, sg.parity);
+        sg.parity ^= 1u;
+    }
+    return tl;
+}
+
+// ---------------------------------------------------------------------------------------
 // table loads through the read-only path (L1-resident for small K, L2 for K ~ 1000)
 // ---------------------------------------------------------------------------------------
 __device__ __forceinline__ EntryLN load_entry(const EntryLN *p) {

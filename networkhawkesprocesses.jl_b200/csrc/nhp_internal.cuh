@@ -178,19 +178,32 @@ __host__ __device__ inline double philox_uniform(uint64_t seed, uint64_t index, 
 }
 
 #ifdef __CUDACC__
+// out-of-line rare paths: subnormal arguments / overflowing exponent (libdevice arithmetic)
+static __device__ __noinline__ double slow_pair_ln(double cf, double mu, double h, double dt, double D) {
+    if (!(dt > 0.0 && dt < D)) return 0.0;
+    double la = log(dt), lb = log(D - dt), dz = (la - lb) - mu;
+    return cf * exp(-h * dz * dz - (la + lb));
+}
 __device__ __forceinline__ double pair_value(const EntryLN &e, double dt, double D, const FastTables *ft) {
     // Distributions.pdf(LogitNormal(mu, tau^-1/2), dt/D): zero outside 0 < x < 1 (impulses.jl:174-178)
     //   = cf exp(-h (z - mu)^2 - log dt - log(D - dt)),  z = log dt - log(D - dt),  cf carries D^2
-    if (!(dt > 0.0 && dt < D)) return 0.0;
-    double la = fast_log(dt, ft), lb = fast_log(D - dt, ft);
-    double dz = (la - lb) - e.mu;
-    double hd = e.h * dz;
-    return e.cf * fast_exp(fma(-hd, dz, -(la + lb)), ft);
+    const double b = D - dt;
+    // dt and D - dt both positive normal  =>  0 < dt < D and both logs are on the table-driven path
+    if (is_pos_normal(dt) && is_pos_normal(b)) {
+        const double la = fast_log_n(dt, ft), lb = fast_log_n(b, ft);
+        const double dz = (la - lb) - e.mu;
+        const double arg = fma(-(e.h * dz), dz, -(la + lb));
+        if (__double2hiint(arg) >= 0x40862800) return e.cf * slow_exp(arg);  // arg >= 709 (or NaN): only for sub-1e-300 gaps
+        return e.cf * fast_exp_c(arg, ft);
+    }
+    return slow_pair_ln(e.cf, e.mu, e.h, dt, D);
 }
 __device__ __forceinline__ double pair_value(const EntryEX &e, double dt, double, const FastTables *ft) {
     // Distributions.pdf(Exponential(1/theta), dt): theta exp(-theta dt), zero for dt < 0 (impulses.jl:106-108)
-    if (dt < 0.0) return 0.0;
-    return e.wt * fast_exp(-e.theta * dt, ft);
+    const double x = -e.theta * dt;
+    if (__double2hiint(dt) < 0) return dt < 0.0 ? 0.0 : e.wt;  // dt < 0 (or -0.0)
+    if (__double2hiint(x) >= 0x40862800) return e.wt * slow_exp(x);
+    return e.wt * fast_exp_c(x, ft);
 }
 // log_duration(parent, child, dtmax)  impulses.jl:228
 __device__ __forceinline__ double log_duration_dev(double dt, double D) { return log(dt / (D - dt)); }
