@@ -46,6 +46,7 @@ def parse():
     ap.add_argument("--nodes", type=int, default=1000)
     ap.add_argument("--cpu-sample", type=float, default=2e6, help="events of the CPU-baseline sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--adjacency", action="store_true", help="also time one adjacency Gibbs sweep (reported in detail, not in value)")
     return ap.parse_args()
 
 
@@ -137,7 +138,7 @@ def run_reference(args, rank, world):
             "config": workload_config(args, world),
             "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
             "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}, "gpu_launches": 0}
-    print(json.dumps(line), flush=True)
+    emit(line)
 
 
 # ------------------------------------------------------------------------------------------
@@ -325,23 +326,37 @@ def run_ours(args, rank, world, local_rank):
     # ---- roofline of the dominant kernel (per-launch device time measured with CUDA events on the launching stream)
     med = {k: float(np.median(v)) for k, v in op_ms.items() if v}
     dom = max(("loglik", "parents"), key=lambda k: med[k])
-    pairs = n * RATE * DTMAX
+    secs = med[dom] * 1e-3
+    density = float(np.count_nonzero(A * W)) / A.size
+    probes = n * RATE * DTMAX                       # adjacency-bit probes (every window pair)
+    pairs = probes * density                        # pairs with a non-zero effective weight: the FP64 impulse evaluations
     flops = pairs * FLOPS_PER_LN_PAIR + n * FLOPS_PER_EVENT
-    tf = flops / (med[dom] * 1e-3) / 1e12
     peaks_file = os.path.join(ROOT, "MEASURED_PEAKS.json")
     hbm_peak, hbm_src = 6650.0, "B200_PROFILING.md fallback (of fallback)"
     if os.path.exists(peaks_file):
         with open(peaks_file) as f:
             hbm_peak, hbm_src = float(json.load(f)["hbm_gbs"]), "MEASURED_PEAKS.json hbm_gbs (of measured)"
     bytes_alg = n * (BYTES_LOGLIK if dom == "loglik" else BYTES_PARENTS)
-    gbs = bytes_alg / (med[dom] * 1e-3) / 1e9
-    roofline = {"kernel": "k_sweep (loglik)" if dom == "loglik" else "k_parents (Gibbs parent sweep + fused statistics)", "bound": "fp64",
-                "achieved": tf, "peak": peaks["fp64_fma_tflops"], "unit": "TFLOP/s", "frac": tf / peaks["fp64_fma_tflops"], "traffic": None,
-                "peak_source": "FP64 FMA peak measured in this run by nhp_bench_fp64 (MEASURED_PEAKS.json carries no FP64 figure)",
-                "algorithmic_flops_per_launch": flops, "pairs_per_s": pairs / (med[dom] * 1e-3),
-                "pairs_per_s_register_ceiling": peaks["ln_pairs_per_s"], "frac_of_register_ceiling": pairs / (med[dom] * 1e-3) / peaks["ln_pairs_per_s"],
-                "hbm_view": {"bound": "hbm", "achieved": gbs, "peak": hbm_peak, "unit": "GB/s", "frac": gbs / hbm_peak,
-                             "algorithmic_bytes_per_launch": bytes_alg, "peak_source": hbm_src},
+    gbs = bytes_alg / secs / 1e9
+    sm_hz = (sampler.summary().get("sm_mhz") or 1965.0) * 1e6
+    lsu_peak = 148 * 32 * sm_hz / 2.0               # 2 shared-memory loads (node id, adjacency word) per probe, 32 lanes/clk/SM
+    tf = flops / secs / 1e12
+    traffic = None
+    prof = os.path.join(ROOT, "profiles", "r01_ncu_dominant_kernel.json")
+    if os.path.exists(prof):
+        with open(prof) as f:
+            traffic = json.load(f).get("dram_bytes_per_launch_at_1e8_events")
+    roofline = {"kernel": "k_sweep_sparse<LOGITNORMAL, %s>" % ("LOGLIK" if dom == "loglik" else "PARENTS"),
+                "bound": "hbm", "achieved": gbs, "peak": hbm_peak, "unit": "GB/s", "frac": gbs / hbm_peak, "traffic": traffic,
+                "peak_source": hbm_src, "algorithmic_bytes_per_launch": bytes_alg,
+                "binding_resource": "instruction issue + shared-memory (LSU) pipe, not HBM: 12 B of event data carry ~64 adjacency probes and ~3 FP64 "
+                                    "impulse evaluations per event (ncu: profiles/r01_*.md); the HBM fraction is therefore small by construction",
+                "lsu_view": {"bound": "shared-memory pipe", "achieved": probes / secs, "peak": lsu_peak, "unit": "probes/s", "frac": probes / secs / lsu_peak,
+                             "algorithmic_probes_per_launch": probes},
+                "fp64_view": {"bound": "fp64", "achieved": tf, "peak": peaks["fp64_fma_tflops"], "unit": "TFLOP/s", "frac": tf / peaks["fp64_fma_tflops"],
+                              "algorithmic_flops_per_launch": flops, "active_pairs_per_launch": pairs,
+                              "peak_source": "FP64 FMA peak measured in this run by nhp_bench_fp64 (MEASURED_PEAKS.json carries no FP64 figure)",
+                              "ln_pairs_per_s_register_ceiling": peaks["ln_pairs_per_s"]},
                 "kernel_ms": med}
 
     line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
@@ -353,18 +368,41 @@ def run_ours(args, rank, world, local_rank):
             "gpu_launches": int(launches), "roofline": roofline,
             "detail": {"loglik_events_per_s": world * n / (med["loglik"] * 1e-3), "gibbs_sweep_events_per_s": world * n / ((med["parents"] + med["second_pass"]) * 1e-3)}}
 
+    if world == 1 and args.adjacency:
+        # continuous.jl:444-519 on the same resident data (not part of the timed step; reported for completeness)
+        ev2 = upload()
+        rho = np.full(K2, RHO)
+        Acur = pA.copy()
+        ms = []
+        for r in range(2):
+            ctx.check(lib.nhp_cont_resample_adjacency(ctx.h, ev2, _ptr(rho), 20261018, 900 + r, None, _ptr(Acur)))
+            ms.append(ctx.last_kernel_ms)
+        lib.nhp_events_free(ctx.h, ev2)
+        line["detail"]["adjacency_sweep_ms"] = float(min(ms))
+        line["detail"]["full_gibbs_sweep_incl_adjacency_events_per_s"] = n / ((med["parents"] + med["second_pass"] + min(ms)) * 1e-3)
+
     if world == 1 and not args.no_cpu_baseline:
         n_sample = int(min(args.cpu_sample, n))
         times, cores = cpu_step_time(args, n_sample, 2)
         cpu_v = n_sample / min(times)
         line["cpu_baseline"] = {"value": cpu_v, "unit": UNIT, "cores": cores, "kind": "port",
                                 "sample": "first %d events of the workload (oracle loglik + resample_parents + statistics, OpenMP %d threads), best of 2" % (n_sample, cores)}
-    print(json.dumps(line), flush=True)
+    emit(line)
     if world > 1:
         dist.destroy_process_group()
 
 
+_REAL_STDOUT = None
+
+
+def emit(line):
+    os.write(_REAL_STDOUT, (json.dumps(line) + "\n").encode())
+
+
 def main():
+    global _REAL_STDOUT
+    _REAL_STDOUT = os.dup(1)
+    os.dup2(2, 1)  # NCCL / torch banners must not pollute the single JSON line
     args = parse()
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))

@@ -61,12 +61,14 @@ template <int KIND> __global__ void __launch_bounds__(256) k_adjacency(const Adj
         // ---- A1: bucket sizes
         for (int k = threadIdx.x; k <= a.K; k += blockDim.x) s_off[k] = 0;
         __syncthreads();
-        for (int e = e0 + threadIdx.x; e < e1; e += blockDim.x) {
+        // one warp per child event, lanes striding its window (coalesced reads of the time-sorted stream)
+        const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5, nw = blockDim.x >> 5;
+        for (int e = e0 + wid; e < e1; e += nw) {
             int i = a.order[e];
-            double ti = a.t[i], thr = ti - a.horizon;
-            for (int j = i - 1; j >= 0; j--) {
-                if (!(a.t[j] > thr)) break;
-                atomicAdd(&s_off[a.c[j] + 1], 1);
+            double thr = a.t[i] - a.horizon;
+            for (int j = i - 1 - lane; j >= 0; j -= 32) {
+                if (!(__ldg(a.t + j) > thr)) break;
+                atomicAdd(&s_off[__ldg(a.c + j) + 1], 1);
             }
         }
         __syncthreads();
@@ -79,21 +81,21 @@ template <int KIND> __global__ void __launch_bounds__(256) k_adjacency(const Adj
         __syncthreads();
         if (s_off[a.K] > a.cap) continue;  // cannot happen: cap is sized from the exact per-column totals
         // ---- A2: emit (event, G) entries and the current intensities
-        for (int e = e0 + threadIdx.x; e < e1; e += blockDim.x) {
+        for (int e = e0 + wid; e < e1; e += nw) {
             int i = a.order[e];
-            double ti = a.t[i], thr = ti - a.horizon, s = lam0;
-            for (int j = i - 1; j >= 0; j--) {
-                double tj = a.t[j];
+            double ti = a.t[i], thr = ti - a.horizon, s = 0.0;
+            for (int j = i - 1 - lane; j >= 0; j -= 32) {
+                double tj = __ldg(a.t + j);
                 if (!(tj > thr)) break;
-                int p = a.c[j];
+                int p = __ldg(a.c + j);
                 double v = pair_value(load_entry(col + p), ti - tj, a.D, &s_ft);
                 int pos = atomicAdd(&s_cur[p], 1);
                 ent_i[pos] = e - e0;
                 ent_v[pos] = v;
                 s += a.A[p + (int64_t)a.K * c] * v;
             }
-            lam[e - e0] = s;
-            gacc[e - e0] = 0.0;
+            s = warp_sum(s);
+            if (lane == 0) { lam[e - e0] = lam0 + s; gacc[e - e0] = 0.0; }
         }
         __syncthreads();
         // ---- B: K sequential Bernoulli steps

@@ -177,11 +177,9 @@ __device__ __forceinline__ Tile stage_tile_at(const SweepArgs &a, Stager &sg, in
 // table loads through the read-only path (L1-resident for small K, L2 for K ~ 1000)
 // ---------------------------------------------------------------------------------------
 __device__ __forceinline__ EntryLN load_entry(const EntryLN *p) {
-    const double2 *q = reinterpret_cast<const double2 *>(p);
-    double2 a = __ldg(q);
-    double b = __ldg(reinterpret_cast<const double *>(p) + 2);
+    // one 256-bit read-only load per 32 B entry (sm_100: LDG.E.256): a divergent gather costs one request per lane
     EntryLN e;
-    e.cf = a.x; e.mu = a.y; e.h = b; e.pad = 0.0;
+    asm("ld.global.nc.v4.f64 {%0,%1,%2,%3}, [%4];" : "=d"(e.cf), "=d"(e.mu), "=d"(e.h), "=d"(e.pad) : "l"(p));
     return e;
 }
 __device__ __forceinline__ EntryEX load_entry(const EntryEX *p) {

@@ -5,7 +5,8 @@
 // so an implementation with ~1e-15 absolute error in log and ~2e-16 relative error in exp is exact
 // for the purpose while costing 11 + 10 DP instructions (tables in shared memory, integer work on the
 // ALU pipe, polynomial coefficients as constant-bank operands).
-//   log(x)  = e ln2 + (-log c_i) + log1p(m c_i - 1),   c_i ~ 1/m on the i-th of 128 mantissa intervals
+//   log(x)  = e ln2 + (-log c_i) + log1p(m c_i - 1),   c_i ~ 1/m on the i-th of 32 mantissa intervals
+//             (32 x 16 B = four 128 B rows: a warp's lookup costs at most 4 shared-memory wavefronts)
 //   exp(x)  = 2^(k/64) (1 + expm1(r)),                  k = round(64 x / ln2), r = x - k ln2/64
 // Tables are correctly rounded (tools/gen_fastmath_tables.py).
 #pragma once
@@ -13,25 +14,25 @@
 #include "fastmath_tables.h"
 
 struct FastTables {
-    double2 logtab[128];  // {c, -log c}
+    double2 logtab[32];   // {c, -log c}
     double exptab[64];    // 2^(j/64)
 };
 
 // polynomial coefficients and split constants live in the constant bank so a DFMA can take them as
 // an operand (no per-use 64-bit immediate moves)
 struct FastConsts {
-    double l6, l5, l4, l3, l2;           // log1p: -1/6, 1/5, -1/4, 1/3, -1/2
+    double l8, l7, l6, l5, l4, l3, l2;   // log1p: -1/8, 1/7, -1/6, 1/5, -1/4, 1/3, -1/2
     double ln2_hi, ln2_lo, emagic;       // e ln2 split; 2^52 + 2^31
     double e5, e4, e3, e2;               // expm1: 1/120, 1/24, 1/6, 1/2
     double inv, kmagic, l64_hi, l64_lo;  // 64/ln2; 1.5 * 2^52; -ln2/64 split
 };
-static __constant__ FastConsts c_fm = {-1.0 / 6.0,      0.2,        -0.25,          1.0 / 3.0,      -0.5,
+static __constant__ FastConsts c_fm = {-0.125, 1.0 / 7.0, -1.0 / 6.0,      0.2,        -0.25,          1.0 / 3.0,      -0.5,
                                        NHP_LN2_HI,      NHP_LN2_LO, 4503601774854144.0,
                                        1.0 / 120.0,     1.0 / 24.0, 1.0 / 6.0,      0.5,
                                        NHP_64_OVER_LN2, 6755399441055744.0, -NHP_LN2_64_HI, -NHP_LN2_64_LO};
 
-// one copy per translation unit (2.5 KB), read once per CTA through L2
-static __device__ unsigned long long g_nhp_logtab[256];
+// one copy per translation unit (1 KB), read once per CTA through L2
+static __device__ unsigned long long g_nhp_logtab[64];
 static __device__ unsigned long long g_nhp_exptab[64];
 // host: copy the generated tables into this translation unit's device arrays (idempotent)
 static inline cudaError_t fast_tables_upload(cudaStream_t s) {
@@ -40,10 +41,10 @@ static inline cudaError_t fast_tables_upload(cudaStream_t s) {
     return cudaMemcpyToSymbolAsync(g_nhp_exptab, NHP_EXPTAB_BITS, sizeof(NHP_EXPTAB_BITS), 0, cudaMemcpyHostToDevice, s);
 }
 
-// cooperative load of the tables into shared memory (2.5 KB); caller synchronises afterwards
+// cooperative load of the tables into shared memory (1 KB); caller synchronises afterwards
 __device__ __forceinline__ void fast_tables_load(FastTables *ft) {
     unsigned long long *dst = reinterpret_cast<unsigned long long *>(ft);
-    for (int i = threadIdx.x; i < 256 + 64; i += blockDim.x) dst[i] = i < 256 ? g_nhp_logtab[i] : g_nhp_exptab[i - 256];
+    for (int i = threadIdx.x; i < 64 + 64; i += blockDim.x) dst[i] = i < 64 ? g_nhp_logtab[i] : g_nhp_exptab[i - 64];
 }
 
 // rare-path fallbacks kept out of line so the hot loops stay small
@@ -58,9 +59,11 @@ __device__ __forceinline__ double fast_log_n(double x, const FastTables *ft) {
     const int hi = __double2hiint(x), lo = __double2loint(x);
     const int e = (hi >> 20) - 1023;
     const double m = __hiloint2double((hi & 0x000fffff) | 0x3ff00000, lo);
-    const double2 t = ft->logtab[(hi >> 13) & 127];
-    const double r = fma(m, t.x, -1.0);
-    double q = fma(r, c_fm.l6, c_fm.l5);
+    const double2 t = ft->logtab[(hi >> 15) & 31];
+    const double r = fma(m, t.x, -1.0);  // |r| <= 1/64: degree-8 log1p, truncation r^9/9 < 6e-18
+    double q = fma(r, c_fm.l8, c_fm.l7);
+    q = fma(r, q, c_fm.l6);
+    q = fma(r, q, c_fm.l5);
     q = fma(r, q, c_fm.l4);
     q = fma(r, q, c_fm.l3);
     q = fma(r, q, c_fm.l2);

@@ -72,6 +72,19 @@ if __name__ == "__main__":
             ctx.check(ctx.lib.nhp_cont_params_set(ctx.h, 1, K, _ptr(pl0), _ptr(pW), _ptr(pA), _ptr(pmu), _ptr(ptau), 1.0))
             print(f"params_set K={K}: {1e3*(time.perf_counter()-t0):.1f} ms", flush=True)
         sys.exit(0)
+    if which == "adj":  # adj K n rate density
+        K, n, rate, dens = int(sys.argv[2]), int(float(sys.argv[3])), float(sys.argv[4]), float(sys.argv[5])
+        t, nodes, T = synth.poisson_stream(n, K, rate, 1)
+        lam0, W, mu, tau, A = synth.ln_params(K, 2, wmax=0.5 / (K * dens), density=dens)
+        proc = nhp.ContinuousNetworkHawkesProcess(nhp.HomogeneousProcess(lam0), nhp.LogitNormalImpulseResponse(mu, tau, 1.0), nhp.DenseWeightModel(W), A,
+                                                  nhp.BernoulliNetworkModel(dens, K))
+        d = proc.upload((t, nodes, T))
+        ctx = proc._ctx()
+        for rep in range(3):
+            t0 = time.perf_counter()
+            nhp.resample_adjacency_matrix_(proc, d, seed=1, counter=rep)
+            print(f"adjacency K={K} n={n:.1e}: kernel {ctx.last_kernel_ms:.2f} ms, call {1e3*(time.perf_counter()-t0):.1f} ms, links {int(proc.adjacency_matrix.sum())}", flush=True)
+        sys.exit(0)
     if which == "one":  # one K n rate density [kind] [reps]
         K, n, rate = int(sys.argv[2]), int(float(sys.argv[3])), float(sys.argv[4])
         dens = None if sys.argv[5] == "none" else float(sys.argv[5])
