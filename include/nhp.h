@@ -55,7 +55,8 @@ double nhp_last_kernel_ms(const nhp_ctx *ctx);
  * that the caller's CUDA events and NCCL collectives order with the library's kernels. */
 int nhp_set_stream(nhp_ctx *ctx, void *cuda_stream);
 /* Roofline denominators measured on this device: which = 0 FP64 FMA peak [TFLOP/s],
- * 1 LogitNormal / 2 Exponential register-resident impulse evaluations [pairs/s]. */
+ * 1 LogitNormal / 2 Exponential register-resident impulse evaluations [pairs/s], 3 FP64 tensor-core
+ * (mma.sync m8n8k4.f64) peak [TFLOP/s]. */
 int nhp_bench_fp64(nhp_ctx *ctx, int which, double *result);
 /* Test hook for the table-driven FP64 log (which = 0) / exp (which = 1) the impulse evaluation uses:
  * out[i] = f(x[i]), host pointers. */

@@ -14,6 +14,20 @@ __global__ void __launch_bounds__(256) k_dfma_peak(double *out, int iters, doubl
     if (s == 12345.678) out[0] = s;
 }
 
+// FP64 tensor-core rate: mma.sync.aligned.m8n8k4.f64 (DMMA), 4 independent accumulator tiles per warp
+__global__ void __launch_bounds__(256) k_dmma_peak(double *out, int iters) {
+    double a = 1.0 + threadIdx.x * 1e-3, b = 0.5 - threadIdx.x * 1e-3;
+    double c0 = 0, c1 = 0, d0 = 0, d1 = 0, e0 = 0, e1 = 0, f0 = 0, f1 = 0;
+    for (int i = 0; i < iters; i++) {
+        asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};" : "+d"(c0), "+d"(c1) : "d"(a), "d"(b));
+        asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};" : "+d"(d0), "+d"(d1) : "d"(a), "d"(b));
+        asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};" : "+d"(e0), "+d"(e1) : "d"(a), "d"(b));
+        asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};" : "+d"(f0), "+d"(f1) : "d"(a), "d"(b));
+    }
+    double s = c0 + c1 + d0 + d1 + e0 + e1 + f0 + f1;
+    if (s == 12345.678) out[0] = s;
+}
+
 // the device impulse function on register inputs (dt marches through the support)
 template <typename E> __global__ void __launch_bounds__(256) k_pair_peak(double *out, int iters, E e, double D) {
     __shared__ FastTables s_ft;
@@ -30,10 +44,10 @@ template <typename E> __global__ void __launch_bounds__(256) k_pair_peak(double 
     if (acc == 12345.678) out[0] = acc;
 }
 
-// which: 0 = DFMA TFLOP/s (2 flops per FMA), 1 = LogitNormal pairs/s, 2 = Exponential pairs/s
+// which: 0 = DFMA TFLOP/s (2 flops per FMA), 1 = LogitNormal pairs/s, 2 = Exponential pairs/s, 3 = DMMA m8n8k4 TFLOP/s
 extern "C" int nhp_bench_fp64(nhp_ctx *ctx, int which, double *result) {
     NHP_CHECK(ctx, ctx != nullptr, NHP_ERR_INVALID, "ctx is NULL");
-    NHP_CHECK(ctx, result != nullptr && which >= 0 && which <= 2, NHP_ERR_INVALID, "nhp_bench_fp64: bad argument");
+    NHP_CHECK(ctx, result != nullptr && which >= 0 && which <= 3, NHP_ERR_INVALID, "nhp_bench_fp64: bad argument");
     NHP_CUDA(ctx, cudaSetDevice(ctx->device));
     void *scratch;
     NHP_TRY(nhp_scratch(ctx, 64, &scratch));
@@ -43,6 +57,7 @@ extern "C" int nhp_bench_fp64(nhp_ctx *ctx, int which, double *result) {
     for (int rep = 0; rep < 4; rep++) {
         NHP_TRY(nhp_timer_begin(ctx));
         if (which == 0) k_dfma_peak<<<blocks, 256, 0, ctx->stream>>>((double *)scratch, iters, 0.999999, 1e-9);
+        else if (which == 3) k_dmma_peak<<<blocks, 256, 0, ctx->stream>>>((double *)scratch, iters);
         else if (which == 1) { EntryLN e{0.3, 0.1, 0.6, 0.0}; k_pair_peak<EntryLN><<<blocks, 256, 0, ctx->stream>>>((double *)scratch, iters, e, 1.0); }
         else { EntryEX e{0.3, 1.1}; k_pair_peak<EntryEX><<<blocks, 256, 0, ctx->stream>>>((double *)scratch, iters, e, 1.0); }
         NHP_LAUNCHED(ctx);
@@ -50,7 +65,8 @@ extern "C" int nhp_bench_fp64(nhp_ctx *ctx, int which, double *result) {
         if (rep > 0 && ctx->last_ms < best) best = ctx->last_ms;
     }
     double work = (double)blocks * 256.0 * iters * (which == 0 ? 16.0 : 2.0);
-    *result = work / (best * 1e-3) / (which == 0 ? 1e12 : 1.0);
+    if (which == 3) work = (double)blocks * 8.0 * iters * 4.0 * 512.0;  // 8 warps x 4 DMMA x (8*8*4*2 flops)
+    *result = work / (best * 1e-3) / ((which == 0 || which == 3) ? 1e12 : 1.0);
     return NHP_OK;
 }
 

@@ -85,6 +85,39 @@ if __name__ == "__main__":
             nhp.resample_adjacency_matrix_(proc, d, seed=1, counter=rep)
             print(f"adjacency K={K} n={n:.1e}: kernel {ctx.last_kernel_ms:.2f} ms, call {1e3*(time.perf_counter()-t0):.1f} ms, links {int(proc.adjacency_matrix.sum())}", flush=True)
         sys.exit(0)
+    if which == "disc":  # disc N T B L rate
+        from nhp_b200 import discrete as D
+        N, T, B, L, rate = int(sys.argv[2]), int(float(sys.argv[3])), int(sys.argv[4]), int(sys.argv[5]), float(sys.argv[6])
+        rng = np.random.default_rng(3)
+        lam0 = np.full(N, 0.02)
+        A = (rng.random((N, N)) < 0.1).astype(np.float64)
+        W = rng.uniform(0.0, 0.5, (N, N)) * A
+        W *= 0.5 / max(1e-9, np.max(np.abs(np.linalg.eigvals(W))))
+        theta = rng.dirichlet(np.ones(B), (N, N))
+        data = rng.poisson(rate, (N, T)).astype(np.int64)
+        proc = D.DiscreteNetworkHawkesProcess(D.DiscreteHomogeneousProcess(lam0), D.DiscreteGaussianImpulseResponse(theta, L), nhp.DenseWeightModel(W), A,
+                                              nhp.BernoulliNetworkModel(0.1, N))
+        ctx = proc._ctx()
+        t0 = time.perf_counter(); d = proc.upload(data); print(f"upload {1e3*(time.perf_counter()-t0):.0f} ms, events {int(data.sum())}, nonzero bins {int((data>0).sum())}", flush=True)
+        for rep in range(2):
+            D.convolve(proc, d, export=False); print(f"convolve kernel {ctx.last_kernel_ms:.2f} ms ({(4*N*T + 8*T*N*B)/ctx.last_kernel_ms/1e6:.0f} GB/s)", flush=True)
+        for rep in range(3):
+            ll = D.loglikelihood(proc, d); ms = ctx.last_kernel_ms
+            print(f"loglik (GEMM+Poisson) {ms:.2f} ms = {2*T*N*N*B/ms/1e9:.2f} TFLOP/s, {T/ms/1e3:.1f} Mbins/s  ll={ll:.6e}", flush=True)
+        for rep in range(2):
+            C = D.resample_parents(proc, d, seed=1, counter=rep); print(f"gibbs counts {ctx.last_kernel_ms:.2f} ms  (sum {C.sum():.0f})", flush=True)
+        e0 = np.ones(N); E = rng.uniform(0.01, 0.2, (N, N, B))
+        for rep in range(2):
+            st = D.vb_statistics(proc, d, e0, E); print(f"vb stats {ctx.last_kernel_ms:.2f} ms", flush=True)
+        for rep in range(2):
+            D.resample_adjacency_matrix_(proc, d, seed=2, counter=rep); print(f"disc adjacency {ctx.last_kernel_ms:.2f} ms links {int(proc.adjacency_matrix.sum())}", flush=True)
+        sys.exit(0)
+    if which == "peaks":
+        import ctypes
+        ctx = nhp.default_context()
+        for w, name in ((0, "DFMA TFLOP/s"), (3, "DMMA m8n8k4 TFLOP/s"), (1, "LN pairs/s"), (2, "EXP pairs/s")):
+            r = ctypes.c_double(); ctx.check(ctx.lib.nhp_bench_fp64(ctx.h, w, ctypes.byref(r))); print(name, r.value, flush=True)
+        sys.exit(0)
     if which == "one":  # one K n rate density [kind] [reps]
         K, n, rate = int(sys.argv[2]), int(float(sys.argv[3])), float(sys.argv[4])
         dens = None if sys.argv[5] == "none" else float(sys.argv[5])
