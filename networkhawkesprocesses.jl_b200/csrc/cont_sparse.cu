@@ -24,6 +24,7 @@ struct SparseArgs {
     int words;
     int cape;               // capacity of the per-tile hit list
     int m0_smem;            // baseline-count histogram lives in shared memory (K small enough)
+    const unsigned short *wlen;  // [n - first] cached window length per own event (65535 = saturated)
 };
 
 template <int KIND, bool ST>
@@ -82,7 +83,7 @@ constexpr int SQMAX = 64;               // window entries one filter thread can 
 // Persistent CTAs: each loops over tiles of STE child events so the per-CTA set-up (log/exp tables,
 // barrier init) is paid once.
 template <int KIND, int MODE>
-__global__ void __launch_bounds__(NHP_BLOCK, 5) k_sweep_sparse(const SparseArgs sa, const int64_t ntiles) {
+__global__ void __launch_bounds__(NHP_BLOCK, 6) k_sweep_sparse(const SparseArgs sa, const int64_t ntiles) {
     typedef typename EntryOf<KIND>::type E;
     const SweepArgs &a = sa.s;
     extern __shared__ __align__(128) unsigned char smem[];
@@ -168,16 +169,14 @@ __global__ void __launch_bounds__(NHP_BLOCK, 5) k_sweep_sparse(const SparseArgs 
         int k0 = 0;
         bool over = false;
         if (live) {
-            // window start: first j in [jlo, i) with t_j > t_i - horizon (binary search on the staged times)
-            const double thr = st[ib] - a.horizon;
-            int lo = (int)(jlo - tl.base), hi = ib;
-            while (lo < hi) { int mid = (lo + hi) >> 1; if (st[mid] > thr) hi = mid; else lo = mid + 1; }
-            const int wlen = ib - lo;
+            // window length from the per-event cache (k_win_len), clipped to the first admissible parent
+            const int wraw = __ldg(sa.wlen + (i - a.first));
+            const int wlen = min(wraw, ib - (int)(jlo - tl.base));
             // this thread's contiguous share of the window, most recent first: positions k0+1 .. k1
             const int q = (wlen + SG - 1) / SG;
             k0 = g * q;
             const int k1 = min(wlen, k0 + q);
-            over = q > SQMAX || wlen > 65535;
+            over = q > SQMAX || wraw >= 65535;
             if (!over) {
                 const uint32_t *myrow = rows + (size_t)e * wp;
                 const int *src = sc + ib - k0 - 1;  // position k0+1+m is src[-m]
@@ -190,9 +189,15 @@ __global__ void __launch_bounds__(NHP_BLOCK, 5) k_sweep_sparse(const SparseArgs 
                                                                  (((w2 >> (p2 & 31)) & 1u) << 2) | (((w3 >> (p3 & 31)) & 1u) << 3));
                     hits |= b4 << m;
                 }
-                for (; m < cntk; m++) {
-                    int p0 = src[-m];
-                    hits |= (unsigned long long)((myrow[p0 >> 5] >> (p0 & 31)) & 1u) << m;
+                if (m < cntk) {  // up to three left-over probes, branch-free
+                    unsigned long long b3 = 0ull;
+#pragma unroll
+                    for (int r = 0; r < 3; r++) {
+                        const bool ok = m + r < cntk;
+                        int p0 = ok ? src[-m - r] : 0;
+                        b3 |= (unsigned long long)(ok ? ((myrow[p0 >> 5] >> (p0 & 31)) & 1u) : 0u) << r;
+                    }
+                    hits |= b3 << m;
                 }
             }
         }
@@ -330,7 +335,7 @@ int nhp_cont_try_sparse(nhp_ctx *ctx, const nhp_events *ev, SweepArgs &a, int mo
     NHP_CUDA(ctx, fast_tables_upload(ctx->stream));  // this translation unit's copy of the log/exp tables
     SparseArgs sa;
     a.te = STE; a.cap = cap;
-    sa.s = a; sa.abits = ctx->d_abits; sa.words = words; sa.cape = lcap; sa.m0_smem = m0_entries > 0;
+    sa.s = a; sa.abits = ctx->d_abits; sa.words = words; sa.cape = lcap; sa.m0_smem = m0_entries > 0; sa.wlen = ev->d_wlen;
     int *grid = grid_out;
     if (ctx->kind == NHP_LOGITNORMAL) {
         if (mode == 0) return launch_sparse(ctx, k_sweep_sparse<NHP_LOGITNORMAL, SP_LOGLIK>, grid, smem, sa, ntiles);

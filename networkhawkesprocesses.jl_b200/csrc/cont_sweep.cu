@@ -41,12 +41,32 @@ __global__ void k_tile_lo(const double *__restrict__ t, int64_t first, int64_t n
     atomicAdd(&winstat[1], w);
 }
 
+// window length of every own event: i - (first j with t[j] > t[i] - horizon), saturated at 65535.  The windows of
+// consecutive events overlap almost completely, so a short backward gallop from the event finds the start.
+__global__ void k_win_len(const double *__restrict__ t, int64_t first, int64_t n, double horizon, unsigned short *__restrict__ wlen) {
+    int64_t i = first + (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const double thr = t[i] - horizon;
+    int64_t good = i, bad = -1, step = 16;
+    while (true) {
+        int64_t cand = i - step;
+        if (cand <= 0) { if (t[0] > thr) good = 0; else bad = 0; break; }
+        if (t[cand] > thr) { good = cand; step <<= 1; if (step > 131072) { bad = -2; break; } }
+        else { bad = cand; break; }
+    }
+    if (bad == -2) { wlen[i - first] = 65535; return; }
+    while (good - bad > 1) { int64_t mid = (good + bad) >> 1; if (t[mid] > thr) good = mid; else bad = mid; }
+    int64_t w = i - good;
+    wlen[i - first] = (unsigned short)(w > 65535 ? 65535 : w);
+}
+
 int nhp_cont_prepare_windows(nhp_ctx *ctx, nhp_events *ev, double horizon) {
     if (ev->cache_horizon == horizon && ev->d_tile_lo) return NHP_OK;
     int64_t own = ev->n - ev->n_halo;
     int64_t nb = (own + NHP_TQ - 1) / NHP_TQ;
     if (!ev->d_tile_lo) {
         NHP_CUDA(ctx, cudaMalloc(&ev->d_tile_lo, (size_t)std::max<int64_t>(nb, 1) * sizeof(int)));
+        NHP_CUDA(ctx, cudaMalloc(&ev->d_wlen, (size_t)std::max<int64_t>(own, 1) * sizeof(unsigned short)));
         ev->n_bound = nb;
     }
     ev->max_win = 0; ev->mean_win = 0.0;
@@ -54,6 +74,8 @@ int nhp_cont_prepare_windows(nhp_ctx *ctx, nhp_events *ev, double horizon) {
         NHP_CUDA(ctx, cudaMemsetAsync(ctx->d_winstat, 0, 2 * sizeof(int64_t), ctx->stream));
         k_tile_lo<<<(unsigned)((nb + 127) / 128), 128, 0, ctx->stream>>>(ev->d_t, ev->n_halo, ev->n, horizon, ev->d_tile_lo, nb,
                                                                           (unsigned long long *)ctx->d_winstat);
+        NHP_LAUNCHED(ctx);
+        k_win_len<<<(unsigned)((own + 255) / 256), 256, 0, ctx->stream>>>(ev->d_t, ev->n_halo, ev->n, horizon, ev->d_wlen);
         NHP_LAUNCHED(ctx);
         int64_t ws[2];
         NHP_CUDA(ctx, cudaMemcpyAsync(ws, ctx->d_winstat, sizeof(ws), cudaMemcpyDeviceToHost, ctx->stream));
@@ -138,7 +160,7 @@ __global__ void k_reduce_partials(const double *__restrict__ partials, int64_t n
 // one uniform per event, inverse-cdf walk in that order; fused statistics.
 // ---------------------------------------------------------------------------------------
 template <int KIND, int G, int R, bool ST>
-__device__ __forceinline__ void parents_body(const SweepArgs &a, const Tile &tl, const FastTables *ft, int *m0_hist) {
+__device__ __forceinline__ void parents_body(const SweepArgs &a, const Tile &tl, const FastTables *ft, int *m0_hist, double *s_v) {
     typedef typename EntryOf<KIND>::type E;
     constexpr int NG = NHP_BLOCK / G;
     const int gid = threadIdx.x / G, gl = threadIdx.x % G;
@@ -149,6 +171,7 @@ __device__ __forceinline__ void parents_body(const SweepArgs &a, const Tile &tl,
     const int jl_lo = (int)(max(tl.lo, a.jmin) - tl.base);
     const int ib0 = (int)(tl.i0 - tl.base), nev = (int)(tl.i1 - tl.i0);
     const StatsLayout sl{a.K};
+    double *my_v = s_v + threadIdx.x;  // this lane's cached weights: row r at my_v[r * NHP_BLOCK] (conflict-free)
     for (int ev = gid; ev < nev; ev += NG) {
         const int ib = ib0 + ev;
         const int64_t i = tl.i0 + ev;
@@ -156,58 +179,39 @@ __device__ __forceinline__ void parents_body(const SweepArgs &a, const Tile &tl,
         const int ci = W.C(ib);
         const double thr = ti - a.horizon;
         const E *col = reinterpret_cast<const E *>(a.table) + (size_t)ci * a.K;
-        // pass 1: weights; the first R rows (G entries each) stay in registers
-        double vc[R];
+        // pass 1: window weights, most recent first; the first R rows (G entries each) are kept in shared memory
         double acc = 0.0;
-        int jl = ib - 1 - gl;
-#pragma unroll
-        for (int r = 0; r < R; r++) {
-            double v = 0.0;
-            if (jl >= jl_lo) {
-                const double tj = W.T(jl);
-                if (tj > thr) v = pair_value(load_entry(col + W.C(jl)), ti - tj, a.D, ft);
-            }
-            vc[r] = v;
-            acc += v;
-            jl -= G;
-        }
-        for (; jl >= jl_lo; jl -= G) {
+        int nr = 0;  // rows in which this lane has an in-window entry
+        for (int jl = ib - 1 - gl; jl >= jl_lo; jl -= G, nr++) {
             const double tj = W.T(jl);
-            if (!(tj > thr)) break;
-            acc += pair_value(load_entry(col + W.C(jl)), ti - tj, a.D, ft);
+            if (!(tj > thr)) break;  // events[parentindex] > time - dtmax   (parents.jl:32)
+            const double v = pair_value(load_entry(col + W.C(jl)), ti - tj, a.D, ft);
+            acc += v;
+            if (nr < R) my_v[nr * NHP_BLOCK] = v;
         }
         const double lam0 = __ldg(a.lambda0 + ci);
         const double S = group_sum<G>(acc, gmask) + lam0;  // sum([weights...; baseline])
         const int64_t gi = a.index_base + i;
         const double u = a.u ? __ldg(a.u + (i - a.first)) : philox_uniform(a.seed, (uint64_t)gi, a.counter);
         const double target = u * S;
-        // pass 2: first k with cumulative weight > u * S   (cp <= draw keeps walking)
+        // pass 2: first k with cumulative weight > u * S   (cp <= draw keeps walking); lane 0 owns the most
+        // recent entry of every row, so its row count bounds the walk
+        const int nrows = (gi == 0) ? 0 : __shfl_sync(gmask, nr, 0, G);  // index == 1 && return 0, 0   (parents.jl:26-28)
         int chosen = 0;  // i - j of the chosen parent, 0 = baseline
         double carry = 0.0;
-        bool done = (gi == 0);  // index == 1 && return 0, 0   (parents.jl:26-28)
-#pragma unroll
-        for (int r = 0; r < R; r++) {
-            if (!done) {
-                const double x = group_incl_scan<G>(vc[r], gmask, gl);
-                const unsigned b = (__ballot_sync(gmask, carry + x > target) >> gshift) & gbits;
-                if (b) { chosen = r * G + (__ffs(b) - 1) + 1; done = true; }
-                carry += __shfl_sync(gmask, x, G - 1, G);
-            }
-        }
-        if (!done) {
-            for (int jr = ib - 1 - R * G; jr >= jl_lo; jr -= G) {  // jr: the row's most recent entry
-                if (!(W.T(jr) > thr)) break;
-                const int jj = jr - gl;
-                double v = 0.0;
-                if (jj >= jl_lo) {
-                    const double tj = W.T(jj);
-                    if (tj > thr) v = pair_value(load_entry(col + W.C(jj)), ti - tj, a.D, ft);
+        for (int r = 0; r < nrows; r++) {
+            double v = 0.0;
+            if (r < nr) {
+                if (r < R) v = my_v[r * NHP_BLOCK];
+                else {
+                    const int jj = ib - 1 - gl - r * G;
+                    v = pair_value(load_entry(col + W.C(jj)), ti - W.T(jj), a.D, ft);
                 }
-                const double x = group_incl_scan<G>(v, gmask, gl);
-                const unsigned b = (__ballot_sync(gmask, carry + x > target) >> gshift) & gbits;
-                if (b) { chosen = (ib - jr) + (__ffs(b) - 1); break; }
-                carry += __shfl_sync(gmask, x, G - 1, G);
             }
+            const double x = group_incl_scan<G>(v, gmask, gl);
+            const unsigned b = (__ballot_sync(gmask, carry + x > target) >> gshift) & gbits;
+            if (b) { chosen = r * G + (__ffs(b) - 1) + 1; break; }
+            carry += __shfl_sync(gmask, x, G - 1, G);
         }
         if (gl == 0) {
             if (!(S > 0.0) || S > 1.7976931348623157e308) atomicOr(a.flag, 8);  // Categorical would reject the vector
@@ -231,6 +235,7 @@ template <int KIND, int G, int R>
 __global__ void __launch_bounds__(NHP_BLOCK) k_parents(const SweepArgs a, const int64_t ntiles, const int m0_smem) {
     extern __shared__ __align__(128) unsigned char smem[];
     __shared__ FastTables s_ft;
+    __shared__ double s_v[R * NHP_BLOCK];  // cached window weights of pass 1
     fast_tables_load(&s_ft);
     Stager sg = stager_init(a, smem);
     // baseline-attribution histogram in shared memory behind the staging area (most events are baseline events)
@@ -239,8 +244,8 @@ __global__ void __launch_bounds__(NHP_BLOCK) k_parents(const SweepArgs a, const 
     __syncthreads();
     for (int64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
         Tile tl = stage_tile_at(a, sg, tile);
-        if (tl.staged) parents_body<KIND, G, R, true>(a, tl, &s_ft, m0_hist);
-        else parents_body<KIND, G, R, false>(a, tl, &s_ft, m0_hist);
+        if (tl.staged) parents_body<KIND, G, R, true>(a, tl, &s_ft, m0_hist, s_v);
+        else parents_body<KIND, G, R, false>(a, tl, &s_ft, m0_hist, s_v);
         __syncthreads();
     }
     if (m0_hist) {
@@ -379,12 +384,12 @@ template <int KIND> static int dispatch_parents(nhp_ctx *ctx, LaunchPlan &p, con
     const int m0 = a.K <= 8192 ? 1 : 0;
     const size_t smem = m0 ? ((p.smem + 15) & ~(size_t)15) + (size_t)a.K * sizeof(int) : p.smem;
     switch (p.G) {
-        case 1: return launch_persistent(ctx, k_parents<KIND, 1, 8>, p, smem, a, m0);
-        case 2: return launch_persistent(ctx, k_parents<KIND, 2, 8>, p, smem, a, m0);
-        case 4: return launch_persistent(ctx, k_parents<KIND, 4, 8>, p, smem, a, m0);
-        case 8: return launch_persistent(ctx, k_parents<KIND, 8, 8>, p, smem, a, m0);
-        case 16: return launch_persistent(ctx, k_parents<KIND, 16, 4>, p, smem, a, m0);
-        default: return launch_persistent(ctx, k_parents<KIND, 32, 2>, p, smem, a, m0);
+        case 1: return launch_persistent(ctx, k_parents<KIND, 1, 16>, p, smem, a, m0);
+        case 2: return launch_persistent(ctx, k_parents<KIND, 2, 16>, p, smem, a, m0);
+        case 4: return launch_persistent(ctx, k_parents<KIND, 4, 16>, p, smem, a, m0);
+        case 8: return launch_persistent(ctx, k_parents<KIND, 8, 16>, p, smem, a, m0);
+        case 16: return launch_persistent(ctx, k_parents<KIND, 16, 8>, p, smem, a, m0);
+        default: return launch_persistent(ctx, k_parents<KIND, 32, 8>, p, smem, a, m0);
     }
 }
 

@@ -214,7 +214,7 @@ extern "C" int nhp_events_upload(nhp_ctx *ctx, const double *times, const int64_
 extern "C" int nhp_events_free(nhp_ctx *ctx, nhp_events *ev) {
     if (!ev) return NHP_OK;
     if (ctx) { cudaSetDevice(ctx->device); cudaStreamSynchronize(ctx->stream); }
-    cudaFree(ev->d_t); cudaFree(ev->d_c); cudaFree(ev->d_poff); cudaFree(ev->d_Mn); cudaFree(ev->d_tile_lo);
+    cudaFree(ev->d_t); cudaFree(ev->d_c); cudaFree(ev->d_poff); cudaFree(ev->d_Mn); cudaFree(ev->d_tile_lo); cudaFree(ev->d_wlen);
     delete ev;
     return NHP_OK;
 }

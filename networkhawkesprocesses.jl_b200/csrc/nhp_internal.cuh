@@ -78,6 +78,7 @@ struct nhp_events {
     double cache_horizon = -1.0;
     int *d_tile_lo = nullptr;   // [ceil((n - n_halo)/64)]
     int64_t n_bound = 0;
+    unsigned short *d_wlen = nullptr;  // [n - n_halo] window length of every own event (saturated at 65535), same cache
     int64_t max_win = 0;        // max over boundaries of (i0 - lo)
     double mean_win = 0.0;
 };
