@@ -65,8 +65,8 @@ int nhp_cont_prepare_windows(nhp_ctx *ctx, nhp_events *ev, double horizon) {
     int64_t own = ev->n - ev->n_halo;
     int64_t nb = (own + NHP_TQ - 1) / NHP_TQ;
     if (!ev->d_tile_lo) {
-        NHP_CUDA(ctx, cudaMalloc(&ev->d_tile_lo, (size_t)std::max<int64_t>(nb, 1) * sizeof(int)));
-        NHP_CUDA(ctx, cudaMalloc(&ev->d_wlen, (size_t)std::max<int64_t>(own, 1) * sizeof(unsigned short)));
+        NHP_CUDA(ctx, cudaMallocAsync(&ev->d_tile_lo, (size_t)std::max<int64_t>(nb, 1) * sizeof(int), ctx->stream));
+        NHP_CUDA(ctx, cudaMallocAsync(&ev->d_wlen, (size_t)std::max<int64_t>(own, 1) * sizeof(unsigned short), ctx->stream));
         ev->n_bound = nb;
     }
     ev->max_win = 0; ev->mean_win = 0.0;

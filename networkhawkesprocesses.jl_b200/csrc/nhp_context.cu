@@ -48,6 +48,14 @@ extern "C" int nhp_create(int device, nhp_ctx **out) {
         return rc;
     }
     ctx->own_stream = ctx->stream;
+    {   // keep freed event buffers in the device's stream-ordered pool: mle!/mcmc! drivers (and the e2e bench) upload
+        // data sets of the same size over and over, and cudaFree of multi-GB buffers costs tens of milliseconds
+        cudaMemPool_t pool;
+        if (cudaDeviceGetDefaultMemPool(&pool, device) == cudaSuccess) {
+            unsigned long long keep = ~0ull;
+            cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep);
+        }
+    }
     cudaMemsetAsync(ctx->d_flag, 0, sizeof(int), ctx->stream);
     *out = ctx;
     return NHP_OK;
@@ -171,8 +179,9 @@ extern "C" int nhp_events_upload(nhp_ctx *ctx, const double *times, const int64_
     const int64_t pad = 64;
     int rc = NHP_OK;
     auto cleanup = [&](int code) { nhp_events_free(ctx, ev); return code; };
-    if (cudaMalloc(&ev->d_t, (size_t)(n + pad) * sizeof(double)) != cudaSuccess || cudaMalloc(&ev->d_c, (size_t)(n + pad) * sizeof(int)) != cudaSuccess ||
-        cudaMalloc(&ev->d_poff, (size_t)(n + pad) * sizeof(int)) != cudaSuccess || cudaMalloc(&ev->d_Mn, (size_t)K * sizeof(double)) != cudaSuccess)
+    cudaStream_t as = ctx->stream;
+    if (cudaMallocAsync(&ev->d_t, (size_t)(n + pad) * sizeof(double), as) != cudaSuccess || cudaMallocAsync(&ev->d_c, (size_t)(n + pad) * sizeof(int), as) != cudaSuccess ||
+        cudaMallocAsync(&ev->d_poff, (size_t)(n + pad) * sizeof(int), as) != cudaSuccess || cudaMallocAsync(&ev->d_Mn, (size_t)K * sizeof(double), as) != cudaSuccess)
         return cleanup(nhp_fail(ctx, NHP_ERR_CUDA, "nhp_events_upload: cudaMalloc failed: %s", cudaGetErrorString(cudaGetLastError())));
     cudaMemsetAsync(ev->d_t + n, 0, pad * sizeof(double), ctx->stream);
     cudaMemsetAsync(ev->d_c + n, 0, pad * sizeof(int), ctx->stream);
@@ -213,8 +222,18 @@ extern "C" int nhp_events_upload(nhp_ctx *ctx, const double *times, const int64_
 
 extern "C" int nhp_events_free(nhp_ctx *ctx, nhp_events *ev) {
     if (!ev) return NHP_OK;
-    if (ctx) { cudaSetDevice(ctx->device); cudaStreamSynchronize(ctx->stream); }
-    cudaFree(ev->d_t); cudaFree(ev->d_c); cudaFree(ev->d_poff); cudaFree(ev->d_Mn); cudaFree(ev->d_tile_lo); cudaFree(ev->d_wlen);
+    if (ctx) {
+        cudaSetDevice(ctx->device);
+        cudaStream_t as = ctx->stream;  // stream-ordered: no device synchronisation, the blocks go back to the pool
+        if (ev->d_t) cudaFreeAsync(ev->d_t, as);
+        if (ev->d_c) cudaFreeAsync(ev->d_c, as);
+        if (ev->d_poff) cudaFreeAsync(ev->d_poff, as);
+        if (ev->d_Mn) cudaFreeAsync(ev->d_Mn, as);
+        if (ev->d_tile_lo) cudaFreeAsync(ev->d_tile_lo, as);
+        if (ev->d_wlen) cudaFreeAsync(ev->d_wlen, as);
+    } else {
+        cudaFree(ev->d_t); cudaFree(ev->d_c); cudaFree(ev->d_poff); cudaFree(ev->d_Mn); cudaFree(ev->d_tile_lo); cudaFree(ev->d_wlen);
+    }
     delete ev;
     return NHP_OK;
 }
