@@ -358,7 +358,7 @@ static LaunchPlan make_plan(nhp_ctx *ctx, const nhp_events *ev) {
 // persistent launch: one resident wave of CTAs looping over the tiles
 template <typename KernelT, typename... Extra>
 static int launch_persistent(nhp_ctx *ctx, KernelT kernel, LaunchPlan &p, size_t smem, const SweepArgs &a, Extra... extra) {
-    if (smem > 48 * 1024) NHP_CUDA(ctx, cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    if (smem > 32 * 1024) NHP_CUDA(ctx, cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));  // static + dynamic may exceed the 48 KB default
     NHP_CUDA(ctx, cudaFuncSetAttribute(kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
     int per_sm = 1;
     NHP_CUDA(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, NHP_BLOCK, smem));
@@ -437,6 +437,14 @@ static int fill_args(nhp_ctx *ctx, nhp_events *ev, int recursive, SweepArgs &a, 
 }
 
 int nhp_cont_try_sparse(nhp_ctx *ctx, const nhp_events *ev, SweepArgs &a, int mode, int *grid_out);  // cont_sparse.cu
+int nhp_cont_try_child(nhp_ctx *ctx, nhp_events *ev, SweepArgs &a, int mode, int *grid_out);          // cont_child.cu
+
+// sparse-adjacency sweep if it applies, else the child-major sweep for large tables; 1 = neither (time-tiled dense sweep)
+static int try_special(nhp_ctx *ctx, nhp_events *ev, SweepArgs &a, int mode, int *grid_out) {
+    int sp = nhp_cont_try_sparse(ctx, ev, a, mode, grid_out);
+    if (sp != 1) return sp;
+    return nhp_cont_try_child(ctx, ev, a, mode, grid_out);
+}
 
 // leaves (log-sum, row-sum) in stats0[0..1]; no host synchronisation
 int nhp_cont_run_loglik(nhp_ctx *ctx, nhp_events *ev, int recursive) {
@@ -445,7 +453,7 @@ int nhp_cont_run_loglik(nhp_ctx *ctx, nhp_events *ev, int recursive) {
     if (p.tiles == 0) { NHP_CUDA(ctx, cudaMemsetAsync(ctx->d_stats0, 0, 2 * sizeof(double), ctx->stream)); return NHP_OK; }
     NHP_TRY(nhp_partials(ctx, 2 * (int64_t)ctx->sm_count * 32, &a.partials));  // one partial per persistent CTA
     int sgrid = 0;
-    int sp = nhp_cont_try_sparse(ctx, ev, a, 0, &sgrid);
+    int sp = try_special(ctx, ev, a, 0, &sgrid);
     if (sp < 0) return sp;
     if (sp == NHP_OK) p.grid = sgrid;
     else if (ctx->kind == NHP_LOGITNORMAL) NHP_TRY((dispatch_sweep<NHP_LOGITNORMAL, MODE_LOGLIK>(ctx, p, a)));
@@ -490,7 +498,7 @@ extern "C" int nhp_cont_event_intensity(nhp_ctx *ctx, nhp_events *ev, double *ou
     a.lam_out = (double *)scratch;
     NHP_TRY(nhp_timer_begin(ctx));
     int sgrid = 0;
-    int sp = nhp_cont_try_sparse(ctx, ev, a, 1, &sgrid);
+    int sp = try_special(ctx, ev, a, 1, &sgrid);
     if (sp < 0) return sp;
     if (sp == NHP_OK) {}
     else if (ctx->kind == NHP_LOGITNORMAL) NHP_TRY((dispatch_sweep<NHP_LOGITNORMAL, MODE_INTENSITY>(ctx, p, a)));
@@ -546,7 +554,7 @@ extern "C" int nhp_cont_resample_parents(nhp_ctx *ctx, nhp_events *ev, uint64_t 
     NHP_TRY(nhp_timer_begin(ctx));
     if (p.tiles > 0) {
         int sgrid = 0;
-        int sp = nhp_cont_try_sparse(ctx, ev, a, 2, &sgrid);
+        int sp = try_special(ctx, ev, a, 2, &sgrid);
         if (sp < 0) return sp;
         if (sp == NHP_OK) {}
         else if (ctx->kind == NHP_LOGITNORMAL) NHP_TRY(dispatch_parents<NHP_LOGITNORMAL>(ctx, p, a));

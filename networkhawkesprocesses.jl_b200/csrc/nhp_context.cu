@@ -234,6 +234,7 @@ extern "C" int nhp_events_free(nhp_ctx *ctx, nhp_events *ev) {
     } else {
         cudaFree(ev->d_t); cudaFree(ev->d_c); cudaFree(ev->d_poff); cudaFree(ev->d_Mn); cudaFree(ev->d_tile_lo); cudaFree(ev->d_wlen);
     }
+    cudaFree(ev->d_order); cudaFree(ev->d_node_ptr); cudaFree(ev->d_item_node); cudaFree(ev->d_item_e0);
     delete ev;
     return NHP_OK;
 }

@@ -79,6 +79,9 @@ struct nhp_events {
     int *d_tile_lo = nullptr;   // [ceil((n - n_halo)/64)]
     int64_t n_bound = 0;
     unsigned short *d_wlen = nullptr;  // [n - n_halo] window length of every own event (saturated at 65535), same cache
+    // by-node order of the own events + work items of the child-major sweep (cont_child.cu), built on first use
+    int *d_order = nullptr, *d_node_ptr = nullptr, *d_item_node = nullptr, *d_item_e0 = nullptr;
+    int64_t n_items = 0;
     int64_t max_win = 0;        // max over boundaries of (i0 - lo)
     double mean_win = 0.0;
 };

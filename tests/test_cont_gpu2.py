@@ -83,3 +83,16 @@ def test_full_gibbs_sweep_runs_and_moves_parameters():
     res = nhp.mcmc_(proc, (t, nodes, T), nsteps=5, seed=3)
     assert len(res.samples) == 5 and all(np.all(np.isfinite(s)) for s in res.samples)
     assert not np.allclose(res.samples[0], res.samples[-1])
+
+
+def test_config5_shape_large_K_exponential_recursive():
+    """config 5 shape (K = 5000 Exponential standard process, full-history semantics) at an oracle-sized N:
+    the cut-off-horizon sweep against the reference's O(N K) recursion."""
+    K, n = 5000, 20000
+    t, nodes, T = synth.poisson_stream(n, K, 3.2, 17)
+    proc, om = make_exp(K, 18, wmax=0.5 / K)
+    d = proc.upload((t, nodes, T))
+    assert nhp.loglikelihood(proc, d, recursive=True) == pytest.approx(om.loglik(t, nodes, T, recursive=True), rel=1e-10)
+    u = np.random.default_rng(2).random(n)
+    par, pn = nhp.resample_parents(proc, d, u=u)
+    assert par.shape == (n,) and np.all(par < np.arange(1, n + 1))

@@ -112,6 +112,17 @@ if __name__ == "__main__":
         for rep in range(2):
             D.resample_adjacency_matrix_(proc, d, seed=2, counter=rep); print(f"disc adjacency {ctx.last_kernel_ms:.2f} ms links {int(proc.adjacency_matrix.sum())}", flush=True)
         sys.exit(0)
+    if which == "cfg5":  # cfg5 n
+        n, K = int(float(sys.argv[2])), 5000
+        t, nodes, T = synth.poisson_stream(n, K, 3.2, 1)
+        lam0, W, theta, _ = synth.exp_params(K, 2)
+        proc = nhp.ContinuousStandardHawkesProcess(nhp.HomogeneousProcess(lam0), nhp.ExponentialImpulseResponse(theta), nhp.DenseWeightModel(W))
+        ctx = proc._ctx()
+        d = proc.upload((t, nodes, T))
+        for rep in range(3):
+            t0 = time.perf_counter(); ll = nhp.loglikelihood(proc, d, recursive=True)
+            print(f"cfg5-like exp K=5000 n={n:.1e}: loglik kernel {ctx.last_kernel_ms:.2f} ms = {n/ctx.last_kernel_ms/1e3:.1f} Mev/s, call {1e3*(time.perf_counter()-t0):.0f} ms, ll={ll:.6e}", flush=True)
+        sys.exit(0)
     if which == "peaks":
         import ctypes
         ctx = nhp.default_context()
