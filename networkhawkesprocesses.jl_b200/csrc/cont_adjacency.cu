@@ -105,21 +105,22 @@ template <int KIND> __global__ void __launch_bounds__(256) k_adjacency(const Adj
             const double a_old = a.A[kk];
             double part = 0.0;
             if (b1 > b0) {
+                // aggregate G_i[p] over the (rare) events that hold node p more than once in their window:
+                // fire-and-forget reductions, no ownership protocol
                 for (int e = b0 + threadIdx.x; e < b1; e += blockDim.x) {
-                    double v = ent_v[e];
-                    if (v > 0.0) {
-                        double old = atomicAdd(&gacc[ent_i[e]], v);
-                        if (old == 0.0) ent_i[e] |= 0x40000000;  // owner of this event's aggregate
-                    }
+                    const double v = ent_v[e];
+                    if (v > 0.0) red_add_f64(&gacc[ent_i[e]], v);
                 }
                 __syncthreads();
+                // every entry carries its share v/g of the event's term log((base + g)/base)
                 for (int e = b0 + threadIdx.x; e < b1; e += blockDim.x) {
-                    int ii = ent_i[e];
-                    if (ii & 0x40000000) {
-                        ii &= 0x3fffffff;
-                        double g = gacc[ii], l = lam[ii];
-                        double base = a_old != 0.0 ? l - g : l;
-                        part += log((base + g) / base);
+                    const double v = ent_v[e];
+                    if (v > 0.0) {
+                        const int ii = ent_i[e];
+                        const double g = gacc[ii], l = lam[ii];
+                        const double base = a_old != 0.0 ? l - g : l;
+                        const double term = log((base + g) / base);
+                        part += (v == g) ? term : term * (v / g);
                     }
                 }
                 part = warp_sum(part);
@@ -142,13 +143,12 @@ template <int KIND> __global__ void __launch_bounds__(256) k_adjacency(const Adj
             __syncthreads();
             if (b1 > b0) {
                 const double an = s_anew;
+                const double sgn = an - a_old;  // +1 link switched on, -1 switched off, 0 unchanged
                 for (int e = b0 + threadIdx.x; e < b1; e += blockDim.x) {
-                    int ii = ent_i[e];
-                    if (ii & 0x40000000) {
-                        ii &= 0x3fffffff;
-                        double g = gacc[ii], l = lam[ii];
-                        double base = a_old != 0.0 ? l - g : l;
-                        lam[ii] = an != 0.0 ? base + g : base;
+                    const double v = ent_v[e];
+                    if (v > 0.0) {
+                        const int ii = ent_i[e];
+                        if (sgn != 0.0) red_add_f64(&lam[ii], sgn * v);
                         gacc[ii] = 0.0;
                     }
                 }
@@ -267,7 +267,7 @@ extern "C" int nhp_cont_resample_adjacency(nhp_ctx *ctx, nhp_events *ev, const d
     }
     k_node_ptr<<<1, 32, 0, s>>>(ev->d_Mn, (int)K, d_ptr);
     NHP_LAUNCHED(ctx);
-    int grid = (int)std::min<int64_t>(K, (int64_t)ctx->sm_count * 2);
+    int grid = (int)std::min<int64_t>(K, (int64_t)ctx->sm_count * 8);  // latency-bound phases: as many columns in flight as the scratch area allows
     // bound the scratch area: entries cost 12 B per CTA slot
     size_t free_b = 0, total_b = 0;
     cudaMemGetInfo(&free_b, &total_b);
