@@ -726,6 +726,104 @@ __global__ void __launch_bounds__(256) k_disc_vb(const double *__restrict__ conv
     if (threadIdx.x == 0 && asum != 0.0) atomicAdd(&alpha_sum[c], asum);
 }
 
+// ---------------------------------------------------------------------------------------
+// warp-per-bin variants (no block barriers in the bin loop): used whenever the per-warp buffers fit shared memory
+// ---------------------------------------------------------------------------------------
+// Gibbs: the warp stores the NB weights of a bin in its shared-memory buffer, every lane sums a contiguous chunk,
+// a warp scan of the chunk sums gives the cdf at chunk granularity, and the lane owning the target walks its chunk.
+__global__ void __launch_bounds__(256) k_disc_gibbs_warp(const double *__restrict__ convT, const double *__restrict__ bumpT, const double *__restrict__ lambda0, double dt,
+                                                         int N, int NB, const int *__restrict__ nz_t, const int *__restrict__ nz_s, const int64_t *__restrict__ nz_off,
+                                                         const int *__restrict__ child_ptr, int slabs, const double *__restrict__ u, uint64_t seed, uint64_t counter,
+                                                         double *__restrict__ counts, int *__restrict__ flag) {
+    extern __shared__ double s_buf[];  // [8 warps][NBP]
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int L = ((NB + 31) / 32) | 1;  // odd chunk length: conflict-free strided reads
+    const int NBP = 32 * L;
+    double *w = s_buf + (size_t)warp * NBP;
+    const int c = blockIdx.x / slabs, slab = blockIdx.x % slabs;
+    const int e0 = child_ptr[c], e1 = child_ptr[c + 1];
+    const int per = (e1 - e0 + slabs - 1) / slabs;
+    const int b0 = e0 + slab * per, b1 = min(e1, b0 + per);
+    const double *bt = bumpT + (int64_t)c * NB;
+    const double mu0 = lambda0[c] * dt;
+    for (int e = b0 + warp; e < b1; e += 8) {
+        const int t = nz_t[e], s = nz_s[e];
+        const double *row = convT + (int64_t)t * NB;
+        for (int k = lane; k < NBP; k += 32) w[k] = k < NB ? __ldg(row + k) * __ldg(bt + k) : 0.0;
+        __syncwarp();
+        double cs = 0.0;
+        const double *mine = w + lane * L;
+        for (int m = 0; m < L; m++) cs += mine[m];
+        double incl = cs;
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) { double y = __shfl_up_sync(0xffffffffu, incl, d); if (lane >= d) incl += y; }
+        incl += mu0;  // cumulative weight up to the end of this lane's chunk, baseline first
+        const double S = __shfl_sync(0xffffffffu, incl, 31);
+        if (lane == 0 && !(S > 0.0 && S < 1.7e308)) atomicOr(flag, 8);
+        for (int d = 0; d < s; d++) {
+            const int64_t ui = nz_off[e] + d;
+            const double uu = u ? u[ui] : philox_uniform(seed, (uint64_t)ui, counter);
+            const double target = uu * S;
+            int pick;
+            if (mu0 > target) pick = 0;  // first index with cumulative weight > target (cp <= u keeps walking)
+            else {
+                const unsigned b = __ballot_sync(0xffffffffu, incl > target);
+                if (b == 0u) pick = NB;  // rounding: target >= S -> last index, as the reference's `i < n` guard
+                else {
+                    const int owner = __ffs(b) - 1;
+                    int found = NB;
+                    if (lane == owner) {
+                        double cum = incl - cs;
+                        for (int m = 0; m < L; m++) {
+                            cum += mine[m];
+                            if (cum > target) { found = 1 + lane * L + m; break; }
+                        }
+                        if (found > NB) found = NB;
+                    }
+                    pick = __shfl_sync(0xffffffffu, found, owner);
+                }
+            }
+            if (lane == 0) atomicAdd(&counts[c + (int64_t)N * pick], 1.0);
+        }
+        __syncwarp();
+    }
+}
+
+// VB: Z and the gamma accumulators per warp; the child's exp-expectation row is shared by the CTA.
+__global__ void __launch_bounds__(256) k_disc_vb_warp(const double *__restrict__ convT, const double *__restrict__ ET, const double *__restrict__ e0, int N, int NB,
+                                                      const int *__restrict__ nz_t, const int *__restrict__ nz_s, const int *__restrict__ child_ptr, int slabs,
+                                                      double *__restrict__ alpha_sum, double *__restrict__ gammaT) {
+    extern __shared__ double s_buf[];  // [NB] ET row | [8][NB] per-warp accumulators
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    double *et = s_buf, *acc = s_buf + NB + (size_t)warp * NB;
+    const int c = blockIdx.x / slabs, slab = blockIdx.x % slabs;
+    const int ei0 = child_ptr[c], e1 = child_ptr[c + 1];
+    const int per = (e1 - ei0 + slabs - 1) / slabs;
+    const int b0 = ei0 + slab * per, b1 = min(e1, b0 + per);
+    for (int k = threadIdx.x; k < NB; k += 256) et[k] = ET[(int64_t)c * NB + k];
+    for (int k = lane; k < NB; k += 32) acc[k] = 0.0;
+    __syncthreads();
+    const double base = e0[c];
+    double asum = 0.0;
+    for (int e = b0 + warp; e < b1; e += 8) {
+        const double *row = convT + (int64_t)nz_t[e] * NB;
+        double part = 0.0;
+        for (int k = lane; k < NB; k += 32) part += __ldg(row + k) * et[k];
+        const double Z = base + warp_sum_d(part);
+        const double r = (double)nz_s[e] / Z;
+        asum += r * base;
+        for (int k = lane; k < NB; k += 32) acc[k] += r * __ldg(row + k) * et[k];
+    }
+    __syncthreads();
+    for (int k = threadIdx.x; k < NB; k += 256) {
+        double g = 0.0;
+#pragma unroll
+        for (int wv = 0; wv < 8; wv++) g += s_buf[NB + (size_t)wv * NB + k];
+        if (g != 0.0) atomicAdd(&gammaT[(int64_t)c * NB + k], g);
+    }
+    if (lane == 0 && asum != 0.0) atomicAdd(&alpha_sum[c], asum);
+}
+
 static int pick_slabs(nhp_ctx *ctx, int64_t N, int64_t nnz) {
     int64_t want = (int64_t)ctx->sm_count * 8;
     int64_t slabs = std::max<int64_t>(1, want / std::max<int64_t>(N, 1));
@@ -750,10 +848,18 @@ extern "C" int nhp_disc_gibbs_counts(nhp_ctx *ctx, nhp_disc *dd, uint64_t seed, 
     NHP_TRY(nhp_timer_begin(ctx));
     if (ex->nnz > 0) {
         int slabs = pick_slabs(ctx, N, ex->nnz);
+        const size_t wsmem = (size_t)8 * 32 * (((NB + 31) / 32) | 1) * sizeof(double);
+        const char *envw = getenv("NHP_DISC_WARP");
+        if (wsmem <= (size_t)ctx->smem_optin - 4096 && !(envw && atoi(envw) == 0)) {
+            DCUDA(ctx, cudaFuncSetAttribute(k_disc_gibbs_warp, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)wsmem));
+            k_disc_gibbs_warp<<<(unsigned)(N * slabs), 256, wsmem, s>>>(dd->d_conv, ctx->dd_bump + NB * N, ctx->dd_lambda0, ctx->ddt, (int)N, (int)NB, ex->nz_t, ex->nz_s,
+                                                                         ex->nz_off, ex->child_ptr, slabs, d_u, seed, counter, d_counts, ctx->d_flag);
+        } else {
         size_t smem = (size_t)(NB + 1) * sizeof(double);
         if (smem > 48 * 1024) DCUDA(ctx, cudaFuncSetAttribute(k_disc_gibbs, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         k_disc_gibbs<<<(unsigned)(N * slabs), 256, smem, s>>>(dd->d_conv, ctx->dd_bump + NB * N, ctx->dd_lambda0, ctx->ddt, (int)N, (int)NB, ex->nz_t, ex->nz_s, ex->nz_off,
                                                                ex->child_ptr, slabs, d_u, seed, counter, d_counts, ctx->d_flag);
+        }
         NHP_LAUNCHED(ctx);
         DCUDA(ctx, cudaGetLastError());
     }
@@ -814,6 +920,12 @@ extern "C" int nhp_disc_vb_stats(nhp_ctx *ctx, nhp_disc *dd, const double *e0, c
     NHP_TRY(nhp_timer_begin(ctx));
     if (ex->nnz > 0) {
         int slabs = pick_slabs(ctx, N, ex->nnz);
+        const size_t wsmem = (size_t)9 * NB * sizeof(double);
+        const char *envw = getenv("NHP_DISC_WARP");
+        if (wsmem <= (size_t)ctx->smem_optin - 4096 && !(envw && atoi(envw) == 0)) {
+            DCUDA(ctx, cudaFuncSetAttribute(k_disc_vb_warp, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)wsmem));
+            k_disc_vb_warp<<<(unsigned)(N * slabs), 256, wsmem, s>>>(dd->d_conv, d_ET, d_e0, (int)N, (int)NB, ex->nz_t, ex->nz_s, ex->child_ptr, slabs, d_alpha, d_gT);
+        } else
         k_disc_vb<<<(unsigned)(N * slabs), 256, 0, s>>>(dd->d_conv, d_ET, d_e0, (int)N, (int)NB, ex->nz_t, ex->nz_s, ex->child_ptr, slabs, d_alpha, d_gT);
         NHP_LAUNCHED(ctx);
     }

@@ -45,8 +45,10 @@ def test_convolve_intensity_loglik(N, T, B, L, network):
     assert D.loglikelihood(proc, d) == pytest.approx(om.loglik(data, oconv), rel=1e-10)
 
 
-@pytest.mark.parametrize("N,T,B,L,network", [(3, 400, 3, 4, False), (12, 1500, 4, 6, True)])
-def test_gibbs_counts_match_given_uniforms(N, T, B, L, network):
+@pytest.mark.parametrize("warp", ["1", "0"])
+@pytest.mark.parametrize("N,T,B,L,network", [(3, 400, 3, 4, False), (12, 1500, 4, 6, True), (70, 800, 6, 12, False)])
+def test_gibbs_counts_match_given_uniforms(N, T, B, L, network, warp, monkeypatch):
+    monkeypatch.setenv("NHP_DISC_WARP", warp)
     proc, om, data = make(N, T, B, L, 11 + N, network, rate=0.2)
     d = proc.upload(data)
     D.convolve(proc, d, export=False)
@@ -82,8 +84,10 @@ def test_gibbs_counts_distribution():
     assert np.all(np.abs(mean - expect) < 5 * np.sqrt(expect / nrep + 1e-9) + 0.02)
 
 
-@pytest.mark.parametrize("N,T,B,L", [(3, 400, 3, 4), (15, 2000, 5, 10)])
-def test_vb_statistics(N, T, B, L):
+@pytest.mark.parametrize("warp", ["1", "0"])
+@pytest.mark.parametrize("N,T,B,L", [(3, 400, 3, 4), (15, 2000, 5, 10), (70, 800, 6, 12)])
+def test_vb_statistics(N, T, B, L, warp, monkeypatch):
+    monkeypatch.setenv("NHP_DISC_WARP", warp)
     proc, om, data = make(N, T, B, L, 31 + N, False, rate=0.1)
     d = proc.upload(data)
     conv = D.convolve(proc, d)
