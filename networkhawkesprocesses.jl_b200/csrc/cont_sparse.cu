@@ -121,22 +121,36 @@ __global__ void __launch_bounds__(NHP_BLOCK, 6) k_sweep_sparse(const SparseArgs 
         const int64_t cnt_stage = (tl.i1 - tl.base + 3) & ~(int64_t)3;
         tl.staged = cnt_stage <= a.cap;
         const int64_t jlo = max(tl.lo, a.jmin);
+        const int64_t i = tl.i0 + e;
+        const bool live = i < tl.i1;
+        const int ib = (int)(i - tl.base);
+        // the child's node id and its cached window length come straight from global memory so that the adjacency
+        // bit-row gather (below) overlaps the TMA transfer instead of waiting for it
+        const int ci = live ? __ldg(a.c + i) : 0;
+        const int wraw = live ? (int)__ldg(sa.wlen + (i - a.first)) : 0;
         if (tl.staged) {
             if (threadIdx.x == 0) {
                 mbar_expect_tx(bar, (uint32_t)(cnt_stage * 12));
                 bulk_g2s(st, a.t + tl.base, (uint32_t)(cnt_stage * 8), bar);
                 bulk_g2s(sc, a.c + tl.base, (uint32_t)(cnt_stage * 4), bar);
             }
+            // adjacency bit-rows of the warp's 8 children: one coalesced load + one conflict-free store per row
+            const int lane = threadIdx.x & 31;
+            uint32_t *dst = rows + (size_t)((threadIdx.x >> 5) * (32 / SG)) * wp + lane;
+#pragma unroll
+            for (int r = 0; r < 32 / SG; r++) {
+                const int cr = __shfl_sync(0xffffffffu, ci, r * SG);
+                const uint32_t *row = sa.abits + (size_t)cr * sa.words + lane;
+                if (lane < sa.words) dst[r * wp] = __ldg(row);
+                for (int w = 32; w + lane < sa.words; w += 32) dst[r * wp + w] = __ldg(row + w);
+            }
+            __syncwarp();
             mbar_wait(bar, parity);
             parity ^= 1u;
         }
-        const int64_t i = tl.i0 + e;
-        const bool live = i < tl.i1;
-        const int ib = (int)(i - tl.base);
         if (!tl.staged) {  // window larger than the staging buffer: direct path from global memory
             if (live && g == 0) {
                 const double ti = __ldg(a.t + i);
-                const int ci = __ldg(a.c + i);
                 const double S = direct_sum<KIND, false>(a, tl, ft, i, ti, ci, jlo) + __ldg(a.lambda0 + ci);
                 if (MODE == SP_LOGLIK) { sum_log += log(S); sum_row += __ldg(a.rowsum + ci); }
                 else if (MODE == SP_INTENSITY) a.lam_out[i - a.first] = S;
@@ -151,26 +165,11 @@ __global__ void __launch_bounds__(NHP_BLOCK, 6) k_sweep_sparse(const SparseArgs 
             continue;
         }
         // ---- 1. filter -------------------------------------------------------------------------------------
-        const int ci = live ? sc[ib] : 0;
-        // adjacency bit-rows of the warp's 8 children: one coalesced load + one conflict-free store per row
-        {
-            const int lane = threadIdx.x & 31;
-            uint32_t *dst = rows + (size_t)((threadIdx.x >> 5) * (32 / SG)) * wp + lane;
-#pragma unroll
-            for (int r = 0; r < 32 / SG; r++) {
-                const int cr = __shfl_sync(0xffffffffu, ci, r * SG);
-                const uint32_t *row = sa.abits + (size_t)cr * sa.words + lane;
-                if (lane < sa.words) dst[r * wp] = __ldg(row);
-                for (int w = 32; w + lane < sa.words; w += 32) dst[r * wp + w] = __ldg(row + w);
-            }
-        }
-        __syncwarp();
         unsigned long long hits = 0ull;
         int k0 = 0;
         bool over = false;
         if (live) {
             // window length from the per-event cache (k_win_len), clipped to the first admissible parent
-            const int wraw = __ldg(sa.wlen + (i - a.first));
             const int wlen = min(wraw, ib - (int)(jlo - tl.base));
             // this thread's contiguous share of the window, most recent first: positions k0+1 .. k1
             const int q = (wlen + SG - 1) / SG;
