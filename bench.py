@@ -33,13 +33,13 @@ METRIC = "loglik+gibbs_sweep_events_per_s"
 UNIT = "events/s"
 RATE, DTMAX, RHO = 64.0, 1.0, 0.05
 FLOPS_PER_LN_PAIR, FLOPS_PER_EVENT = 96.0, 40.0  # SURVEY.md section 8d (nominal FP64 flops, libdevice-class accuracy)
-BYTES_LOGLIK, BYTES_PARENTS = 12.0, 16.0        # per event: 8 B time + 4 B node (+ 4 B parent offset written)
+BYTES_LOGLIK, BYTES_PARENTS = 14.0, 18.0        # per event: 8 B time + 4 B node + 2 B cached window length (+ 4 B parent offset written)
 
 
 def parse():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--events", type=float, default=1e8, help="events per GPU")
@@ -341,16 +341,25 @@ def run_ours(args, rank, world, local_rank):
     sm_hz = (sampler.summary().get("sm_mhz") or 1965.0) * 1e6
     lsu_peak = 148 * 32 * sm_hz / 2.0               # 2 shared-memory loads (node id, adjacency word) per probe, 32 lanes/clk/SM
     tf = flops / secs / 1e12
-    traffic = None
+    traffic, issue_view = None, None
     prof = os.path.join(ROOT, "profiles", "r01_ncu_dominant_kernel.json")
     if os.path.exists(prof):
         with open(prof) as f:
-            traffic = json.load(f).get("dram_bytes_per_launch_at_1e8_events")
+            pj = json.load(f)
+        if n == pj.get("events"):
+            traffic = pj.get("dram_bytes_per_launch_at_1e8_events")
+        ipe = pj.get("warp_instructions_per_event")
+        if ipe:
+            issue_peak = 148 * 4 * sm_hz  # one warp instruction per SM sub-partition per cycle
+            issue_view = {"bound": "instruction issue", "achieved": ipe * n / secs, "peak": issue_peak, "unit": "warp-instructions/s",
+                          "frac": ipe * n / secs / issue_peak, "warp_instructions_per_event": ipe,
+                          "source": "instruction count per event from the committed ncu capture (profiles/r01_ncu_dominant_kernel.json), rate measured live"}
     roofline = {"kernel": "k_sweep_sparse<LOGITNORMAL, %s>" % ("LOGLIK" if dom == "loglik" else "PARENTS"),
                 "bound": "hbm", "achieved": gbs, "peak": hbm_peak, "unit": "GB/s", "frac": gbs / hbm_peak, "traffic": traffic,
                 "peak_source": hbm_src, "algorithmic_bytes_per_launch": bytes_alg,
                 "binding_resource": "instruction issue + shared-memory (LSU) pipe, not HBM: 12 B of event data carry ~64 adjacency probes and ~3 FP64 "
                                     "impulse evaluations per event (ncu: profiles/r01_*.md); the HBM fraction is therefore small by construction",
+                "issue_view": issue_view,
                 "lsu_view": {"bound": "shared-memory pipe", "achieved": probes / secs, "peak": lsu_peak, "unit": "probes/s", "frac": probes / secs / lsu_peak,
                              "algorithmic_probes_per_launch": probes},
                 "fp64_view": {"bound": "fp64", "achieved": tf, "peak": peaks["fp64_fma_tflops"], "unit": "TFLOP/s", "frac": tf / peaks["fp64_fma_tflops"],
