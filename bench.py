@@ -45,6 +45,8 @@ def parse():
     ap.add_argument("--events", type=float, default=1e8, help="events per GPU")
     ap.add_argument("--nodes", type=int, default=1000)
     ap.add_argument("--cpu-sample", type=float, default=2e6, help="events of the CPU-baseline sample")
+    ap.add_argument("--scaling", default="weak", choices=["weak", "strong"],
+                    help="weak: --events per GPU (default, the driver's contract); strong: --events in total, split over the GPUs")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--adjacency", action="store_true", help="also time one adjacency Gibbs sweep (reported in detail, not in value)")
     return ap.parse_args()
@@ -53,7 +55,8 @@ def parse():
 def workload_config(args, world):
     return {"workload": "cfg4: continuous LogitNormal network Hawkes, Bernoulli(rho=0.05) adjacency, K=%d, %.0e events per GPU, "
                         "rate 64/s, dtmax=1 (mean window 64), step = loglikelihood + Gibbs sweep (parents + fused statistics)" % (args.nodes, args.events),
-            "K": args.nodes, "events_per_gpu": int(args.events), "global_events": int(args.events) * world, "mean_window": RATE * DTMAX,
+            "K": args.nodes, "events_per_gpu": int(args.events) // (world if args.scaling == "strong" else 1),
+            "global_events": int(args.events) * (1 if args.scaling == "strong" else world), "mean_window": RATE * DTMAX,
             "rho": RHO, "sharding": "contiguous time shards + dtmax halo" if world > 1 else "single shard",
             "l2_policy": "inputs (1.2 GB of events per GPU) are larger than the 126 MB L2; no explicit flush"}
 
@@ -177,7 +180,7 @@ def run_ours(args, rank, world, local_rank):
     torch.cuda.set_stream(stream)
     ctx.check(ctx.lib.nhp_set_stream(ctx.h, ctypes.c_void_p(stream.cuda_stream)))
     lib = ctx.lib
-    K, n = args.nodes, int(args.events)
+    K, n = args.nodes, int(args.events) // (world if args.scaling == "strong" else 1)
 
     # ---- synthetic shard (pinned host buffers so the e2e leg copies at PCIe speed)
     lam0, W, mu, tau, A = make_params(K)
@@ -385,7 +388,7 @@ def run_ours(args, rank, world, local_rank):
                 "kernel_ms": med}
 
     line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
-            "ms_per_step": total_ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
+            "ms_per_step": total_ms / args.steps, "higher_is_better": True, "scaling": args.scaling, "vs_baseline": None, "dtype": "f64",
             "data": "synthetic", "config": workload_config(args, world), "clocks": sampler.summary(),
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "steps": e2e_steps,
                     "what": "nhp_cont_params_set + nhp_events_upload (pinned host buffers) + nhp_cont_loglik + nhp_cont_resample_parents + statistics read back",
