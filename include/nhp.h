@@ -125,6 +125,12 @@ int nhp_cont_suffstats(nhp_ctx *ctx, nhp_events *ev, double *M0, double *Mn, dou
  * A_inout is read (current state), updated, and also becomes the context's A. */
 int nhp_cont_resample_adjacency(nhp_ctx *ctx, nhp_events *ev, const double *rho, uint64_t seed, uint64_t counter,
                                 const double *u, double *A_inout);
+/* Multi-GPU form: columns are conditionally independent (the reference's Threads.@threads axis,
+ * continuous.jl:462-464), so rank r of R resamples only the columns c with c % col_stride == col_begin
+ * (events replicated on every rank) and leaves the others untouched; the host then exchanges the
+ * owned columns (allgather / masked allreduce).  col_begin = 0, col_stride = 1 is the full sweep. */
+int nhp_cont_resample_adjacency_cols(nhp_ctx *ctx, nhp_events *ev, const double *rho, uint64_t seed, uint64_t counter,
+                                     const double *u, double *A_inout, int64_t col_begin, int64_t col_stride);
 
 /* ---- multi-GPU plumbing (one process per GPU; the host allreduces with NCCL) -------------
  * Device pointer + length (in doubles) of the contiguous reduction buffer

@@ -27,6 +27,7 @@ struct AdjArgs {
     int *ent_i; double *ent_v; double *lam; double *gacc;  // per-CTA scratch regions
     int64_t max_col;         // max child events per column
     int *flag;
+    int col_begin, col_stride;  // this call owns the columns c with c % col_stride == col_begin
 };
 
 __device__ __forceinline__ int lo_of_event(const double *t, int64_t i, double horizon) {
@@ -54,7 +55,7 @@ template <int KIND> __global__ void __launch_bounds__(256) k_adjacency(const Adj
     double *ent_v = a.ent_v + (size_t)blockIdx.x * a.cap;
     double *lam = a.lam + (size_t)blockIdx.x * a.max_col;
     double *gacc = a.gacc + (size_t)blockIdx.x * a.max_col;
-    for (int c = blockIdx.x; c < a.K; c += gridDim.x) {
+    for (int c = a.col_begin + blockIdx.x * a.col_stride; c < a.K; c += gridDim.x * a.col_stride) {
         const int e0 = a.node_ptr[c], e1 = a.node_ptr[c + 1];
         const E *col = reinterpret_cast<const E *>(a.table_w) + (size_t)c * a.K;
         const double lam0 = a.lambda0[c];
@@ -202,7 +203,13 @@ __global__ void k_table_noA_ex(int K, const double *__restrict__ W, const double
 
 extern "C" int nhp_cont_resample_adjacency(nhp_ctx *ctx, nhp_events *ev, const double *rho, uint64_t seed, uint64_t counter, const double *u,
                                            double *A_inout) {
+    return nhp_cont_resample_adjacency_cols(ctx, ev, rho, seed, counter, u, A_inout, 0, 1);
+}
+
+extern "C" int nhp_cont_resample_adjacency_cols(nhp_ctx *ctx, nhp_events *ev, const double *rho, uint64_t seed, uint64_t counter, const double *u,
+                                                double *A_inout, int64_t col_begin, int64_t col_stride) {
     NHP_CHECK(ctx, ctx != nullptr, NHP_ERR_INVALID, "ctx is NULL");
+    NHP_CHECK(ctx, col_stride >= 1 && col_begin >= 0 && col_begin < col_stride, NHP_ERR_INVALID, "nhp_cont_resample_adjacency_cols: need 0 <= col_begin < col_stride");
     NHP_CHECK(ctx, ctx->cont_set, NHP_ERR_STATE, "continuous parameters not set (call nhp_cont_params_set)");
     NHP_CHECK(ctx, ev != nullptr && ev->K == ctx->K, NHP_ERR_INVALID, "nhp_cont_resample_adjacency: bad events handle");
     NHP_CHECK(ctx, rho && A_inout, NHP_ERR_INVALID, "nhp_cont_resample_adjacency: NULL rho/A");
@@ -283,7 +290,7 @@ extern "C" int nhp_cont_resample_adjacency(nhp_ctx *ctx, nhp_events *ev, const d
     a.t = ev->d_t; a.c = ev->d_c; a.n = n; a.order = d_order; a.node_ptr = d_ptr; a.Mn = ev->d_Mn; a.K = (int)K; a.table_w = d_tw;
     a.lambda0 = ctx->d_lambda0; a.W = ctx->d_W; a.A = d_A; a.rho = d_rho; a.u = d_u; a.seed = seed; a.counter = counter;
     a.D = ctx->dtmax; a.horizon = horizon; a.duration = ev->duration; a.cap = cap; a.ent_i = d_ent_i; a.ent_v = d_ent_v; a.lam = d_lam; a.gacc = d_gacc;
-    a.max_col = mc; a.flag = ctx->d_flag;
+    a.max_col = mc; a.flag = ctx->d_flag; a.col_begin = (int)col_begin; a.col_stride = (int)col_stride;
     size_t smem = (size_t)(2 * K + 2) * sizeof(int);
     int rc = nhp_timer_begin(ctx);
     if (rc != NHP_OK) return fin(rc);

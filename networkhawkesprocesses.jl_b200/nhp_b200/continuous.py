@@ -398,8 +398,9 @@ def _read_stats(ctx, d, K):
     return dict(M0=M0, Mn=Mn, Mnm=f(Mnm), S1=f(S1), S2=f(S2))
 
 
-def resample_adjacency_matrix_(process, data, seed=0, counter=0, u=None):
-    """continuous.jl:444-487; mutates process.adjacency_matrix."""
+def resample_adjacency_matrix_(process, data, seed=0, counter=0, u=None, col_begin=0, col_stride=1):
+    """continuous.jl:444-487; mutates process.adjacency_matrix.  col_begin/col_stride: resample only the columns
+    c with c % col_stride == col_begin (multi-GPU column partition; the caller exchanges the owned columns)."""
     ctx = process._ctx()
     d, tmp = process._data(data)
     try:
@@ -408,7 +409,7 @@ def resample_adjacency_matrix_(process, data, seed=0, counter=0, u=None):
         rho = _fmat(process.network.link_probability())
         A = _fmat(process.adjacency_matrix).copy()
         uu = None if u is None else _fmat(u)
-        ctx.check(ctx.lib.nhp_cont_resample_adjacency(ctx.h, d.h, _ptr(rho), int(seed), int(counter), _ptr(uu), _ptr(A)))
+        ctx.check(ctx.lib.nhp_cont_resample_adjacency_cols(ctx.h, d.h, _ptr(rho), int(seed), int(counter), _ptr(uu), _ptr(A), int(col_begin), int(col_stride)))
         process.adjacency_matrix = A.reshape(K, K).T.copy()
         return process.adjacency_matrix
     finally:

@@ -96,3 +96,25 @@ def test_config5_shape_large_K_exponential_recursive():
     u = np.random.default_rng(2).random(n)
     par, pn = nhp.resample_parents(proc, d, u=u)
     assert par.shape == (n,) and np.all(par < np.arange(1, n + 1))
+
+
+def test_adjacency_column_partition_reproduces_full_sweep():
+    """Multi-GPU form: ranks own interleaved columns; merging the owned columns equals the full sweep."""
+    K, n = 7, 1200
+    t, nodes, T = synth.poisson_stream(n, K, 30.0, 33)
+    proc, om = make_ln(K, 34, density=0.5, wmax=1.0 / K)
+    proc.network = nhp.BernoulliNetworkModel(0.3, K)
+    A0 = proc.adjacency_matrix.copy()
+    u = np.random.default_rng(8).random((K, K))
+    d = proc.upload((t, nodes, T))
+    full = nhp.resample_adjacency_matrix_(proc, d, u=u).copy()
+    merged = A0.copy()
+    R = 3
+    for r in range(R):
+        proc.adjacency_matrix = A0.copy()
+        part = nhp.resample_adjacency_matrix_(proc, d, u=u, col_begin=r, col_stride=R)
+        other = [c for c in range(K) if c % R != r]
+        np.testing.assert_array_equal(part[:, other], A0[:, other])  # columns of other ranks untouched
+        merged[:, r::R] = part[:, r::R]
+    np.testing.assert_array_equal(merged, full)
+    np.testing.assert_array_equal(full, om.resample_adjacency(A0, np.full((K, K), 0.3), t, nodes, T, u))

@@ -125,3 +125,34 @@ def test_discrete_adjacency_matches_oracle(N, T, B, L):
         ref = om.resample_adjacency(A0, np.full((N, N), 0.4), data, conv, u)
         mism += int(np.count_nonzero(A != ref))
     assert mism == 0
+
+
+def test_time_shards_with_lag_halo_reproduce_unsharded():
+    """Discrete multi-GPU form: contiguous time shards, each preceded by an L-bin halo of counts; the
+    log-likelihood shares, Gibbs counts and VB statistics add up to the unsharded results."""
+    N, T, B, L = 6, 1200, 3, 5
+    proc, om, data = make(N, T, B, L, 77, False, rate=0.15)
+    ctx = proc._ctx()
+    d = proc.upload(data)
+    D.convolve(proc, d, export=False)
+    ll_ref = D.loglikelihood(proc, d)
+    rng = np.random.default_rng(4)
+    e0, E = rng.uniform(0.5, 1.5, N), rng.uniform(0.01, 0.2, (N, N, B))
+    vb_ref = D.vb_statistics(proc, d, e0, E)
+    cnt_ref = D.resample_parents(proc, d, seed=5, counter=1).sum()
+    ll, kappa, alpha, total = 0.0, 0.0, 0.0, 0.0
+    bounds = [0, 400, 401, 900, T]
+    for r in range(4):
+        a, b = bounds[r], bounds[r + 1]
+        lo = max(0, a - L)
+        sh = D.DiscreteData(ctx, data[:, lo:b], t_halo=a - lo)
+        D.convolve(proc, sh, export=False)
+        ll += D.loglikelihood(proc, sh)
+        st = D.vb_statistics(proc, sh, e0, E)
+        kappa = kappa + st["kappa_sum"]
+        alpha = alpha + st["alpha_sum"]
+        total += D.resample_parents(proc, sh, seed=5, counter=1).sum()
+    assert ll == pytest.approx(ll_ref, rel=1e-12)
+    np.testing.assert_allclose(kappa, vb_ref["kappa_sum"], rtol=1e-11, atol=1e-13)
+    np.testing.assert_allclose(alpha, vb_ref["alpha_sum"], rtol=1e-11)
+    assert total == cnt_ref == data.sum()
