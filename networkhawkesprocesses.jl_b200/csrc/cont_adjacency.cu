@@ -247,20 +247,9 @@ extern "C" int nhp_cont_resample_adjacency_cols(nhp_ctx *ctx, nhp_events *ev, co
     NHP_LAUNCHED(ctx);
     ADJ_CUDA(cudaMemsetAsync(ctx->d_flag, 0, sizeof(int), s));
     int64_t max_entries = 0, max_col = 0;
+    // ---- child events grouped by node, time order kept: the cached by-node index of the events handle
+    { int rc = nhp_events_build_node_index(ctx, ev); if (rc != NHP_OK) return fin(rc); }
     if (n > 0) {
-        // ---- child events grouped by node, time order kept (stable radix sort of (node, index))
-        ADJ_CUDA(cudaMalloc(&d_vals, n * sizeof(int)));
-        ADJ_CUDA(cudaMalloc(&d_order, n * sizeof(int)));
-        ADJ_CUDA(cudaMalloc(&d_ckeys, n * sizeof(int)));
-        k_iota<<<(unsigned)((n + 255) / 256), 256, 0, s>>>(d_vals, n);
-        NHP_LAUNCHED(ctx);
-        size_t tmp_bytes = 0;
-        int bits = 1;
-        while ((1 << bits) < K) bits++;
-        cub::DeviceRadixSort::SortPairs(nullptr, tmp_bytes, ev->d_c, d_ckeys, d_vals, d_order, (int)n, 0, bits, s);
-        ADJ_CUDA(cudaMalloc(&d_sort, tmp_bytes));
-        ADJ_CUDA(cub::DeviceRadixSort::SortPairs(d_sort, tmp_bytes, ev->d_c, d_ckeys, d_vals, d_order, (int)n, 0, bits, s));
-        NHP_LAUNCHED(ctx);
         ADJ_CUDA(cudaMemsetAsync(d_cc, 0, K * sizeof(unsigned long long), s));
         k_adj_count<<<(unsigned)((n + 255) / 256), 256, 0, s>>>(ev->d_t, ev->d_c, n, horizon, d_cc);
         NHP_LAUNCHED(ctx);
@@ -272,8 +261,6 @@ extern "C" int nhp_cont_resample_adjacency_cols(nhp_ctx *ctx, nhp_events *ev, co
         for (int64_t k = 0; k < K; k++) { max_entries = std::max<int64_t>(max_entries, (int64_t)cc[k]); max_col = std::max<int64_t>(max_col, (int64_t)mn[k]); }
         if (max_entries >= (int64_t)0x3fffffff) return fin(nhp_fail(ctx, NHP_ERR_UNSUPPORTED, "adjacency sampler: a column has %lld window entries (limit 2^30)", (long long)max_entries));
     }
-    k_node_ptr<<<1, 32, 0, s>>>(ev->d_Mn, (int)K, d_ptr);
-    NHP_LAUNCHED(ctx);
     int grid = (int)std::min<int64_t>(K, (int64_t)ctx->sm_count * 8);  // latency-bound phases: as many columns in flight as the scratch area allows
     // bound the scratch area: entries cost 12 B per CTA slot
     size_t free_b = 0, total_b = 0;
@@ -287,7 +274,7 @@ extern "C" int nhp_cont_resample_adjacency_cols(nhp_ctx *ctx, nhp_events *ev, co
     ADJ_CUDA(cudaMalloc(&d_lam, (size_t)grid * mc * sizeof(double)));
     ADJ_CUDA(cudaMalloc(&d_gacc, (size_t)grid * mc * sizeof(double)));
     AdjArgs a;
-    a.t = ev->d_t; a.c = ev->d_c; a.n = n; a.order = d_order; a.node_ptr = d_ptr; a.Mn = ev->d_Mn; a.K = (int)K; a.table_w = d_tw;
+    a.t = ev->d_t; a.c = ev->d_c; a.n = n; a.order = ev->d_order; a.node_ptr = ev->d_node_ptr; a.Mn = ev->d_Mn; a.K = (int)K; a.table_w = d_tw;
     a.lambda0 = ctx->d_lambda0; a.W = ctx->d_W; a.A = d_A; a.rho = d_rho; a.u = d_u; a.seed = seed; a.counter = counter;
     a.D = ctx->dtmax; a.horizon = horizon; a.duration = ev->duration; a.cap = cap; a.ent_i = d_ent_i; a.ent_v = d_ent_v; a.lam = d_lam; a.gacc = d_gacc;
     a.max_col = mc; a.flag = ctx->d_flag; a.col_begin = (int)col_begin; a.col_stride = (int)col_stride;

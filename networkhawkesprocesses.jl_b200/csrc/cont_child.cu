@@ -120,7 +120,7 @@ template <int KIND> __global__ void __launch_bounds__(NHP_BLOCK) k_child_sweep(c
 }
 
 // by-node order of the own events + work items; cached in the events handle (data dependent only)
-static int build_child_index(nhp_ctx *ctx, nhp_events *ev) {
+int nhp_events_build_node_index(nhp_ctx *ctx, nhp_events *ev) {
     if (ev->d_order) return NHP_OK;
     const int64_t own = ev->n - ev->n_halo, K = ev->K;
     cudaStream_t s = ctx->stream;
@@ -129,15 +129,17 @@ static int build_child_index(nhp_ctx *ctx, nhp_events *ev) {
     NHP_CUDA(ctx, cudaMalloc(&ev->d_order, (size_t)std::max<int64_t>(own, 1) * sizeof(int)));
     NHP_CUDA(ctx, cudaMalloc(&d_vals, (size_t)std::max<int64_t>(own, 1) * sizeof(int)));
     NHP_CUDA(ctx, cudaMalloc(&d_keys, (size_t)std::max<int64_t>(own, 1) * sizeof(int)));
-    k_child_iota<<<(unsigned)((own + 255) / 256), 256, 0, s>>>(d_vals, own, (int)ev->n_halo);
-    NHP_LAUNCHED(ctx);
-    int bits = 1;
-    while ((1 << bits) < K) bits++;
-    size_t tb = 0;
-    cub::DeviceRadixSort::SortPairs(nullptr, tb, ev->d_c + ev->n_halo, d_keys, d_vals, ev->d_order, (int)own, 0, bits, s);
-    NHP_CUDA(ctx, cudaMalloc(&d_tmp, tb));
-    NHP_CUDA(ctx, cub::DeviceRadixSort::SortPairs(d_tmp, tb, ev->d_c + ev->n_halo, d_keys, d_vals, ev->d_order, (int)own, 0, bits, s));  // stable
-    NHP_LAUNCHED(ctx);
+    if (own > 0) {
+        k_child_iota<<<(unsigned)((own + 255) / 256), 256, 0, s>>>(d_vals, own, (int)ev->n_halo);
+        NHP_LAUNCHED(ctx);
+        int bits = 1;
+        while ((1 << bits) < K) bits++;
+        size_t tb = 0;
+        cub::DeviceRadixSort::SortPairs(nullptr, tb, ev->d_c + ev->n_halo, d_keys, d_vals, ev->d_order, (int)own, 0, bits, s);
+        NHP_CUDA(ctx, cudaMalloc(&d_tmp, tb));
+        NHP_CUDA(ctx, cub::DeviceRadixSort::SortPairs(d_tmp, tb, ev->d_c + ev->n_halo, d_keys, d_vals, ev->d_order, (int)own, 0, bits, s));  // stable
+        NHP_LAUNCHED(ctx);
+    }
     std::vector<double> mn(K);
     NHP_CUDA(ctx, cudaMemcpyAsync(mn.data(), ev->d_Mn, (size_t)K * sizeof(double), cudaMemcpyDeviceToHost, s));
     NHP_CUDA(ctx, cudaStreamSynchronize(s));
@@ -176,7 +178,7 @@ int nhp_cont_try_child(nhp_ctx *ctx, nhp_events *ev, SweepArgs &a, int mode, int
     const bool big_table = (double)K * K * esz > 96e6;  // beyond L2 (126 MB): measured crossover (K = 1000 LN, 32 MB: time-tiled 5.1 ms vs child-major 7.7 ms per 1e7 events; K = 5000 Exp, 400 MB: 140 ms vs 61 ms per 2e7)
     const bool amortised = (double)own / K * std::max(ev->mean_win, 1.0) > 8.0 * K;
     if (!force && !(big_table && amortised)) return 1;
-    NHP_TRY(build_child_index(ctx, ev));
+    NHP_TRY(nhp_events_build_node_index(ctx, ev));
     if (ev->n_items == 0) return 1;
     NHP_CUDA(ctx, fast_tables_upload(ctx->stream));
     ChildArgs ca;
