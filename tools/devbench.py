@@ -123,6 +123,28 @@ if __name__ == "__main__":
             t0 = time.perf_counter(); ll = nhp.loglikelihood(proc, d, recursive=True)
             print(f"cfg5-like exp K=5000 n={n:.1e}: loglik kernel {ctx.last_kernel_ms:.2f} ms = {n/ctx.last_kernel_ms/1e3:.1f} Mev/s, call {1e3*(time.perf_counter()-t0):.0f} ms, ll={ll:.6e}", flush=True)
         sys.exit(0)
+    if which == "cfg1":  # README example: K=2 exponential, T=1000: per-call latency of loglikelihood (params pushed each call, as mle! does)
+        sys.path.insert(0, os.path.join(ROOT, "oracle"))
+        import oracle_ffi as orc
+        K = 2
+        proc = nhp.ContinuousStandardHawkesProcess(nhp.HomogeneousProcess(np.ones(K)), nhp.ExponentialImpulseResponse(np.ones((K, K))), nhp.DenseWeightModel(0.1 * np.ones((K, K))))
+        t, nodes, T = nhp.rand(proc, 1000.0, np.random.default_rng(0))
+        d = proc.upload((t, nodes, T))
+        for rec in (True, False):
+            for _ in range(20):
+                nhp.loglikelihood(proc, d, recursive=rec)
+            t0 = time.perf_counter()
+            for _ in range(500):
+                ll = nhp.loglikelihood(proc, d, recursive=rec)
+            dt = (time.perf_counter() - t0) / 500
+            print(f"cfg1 K=2 n={len(t)} recursive={rec}: {1e6*dt:.0f} us per loglikelihood call (kernel {1e3*proc._ctx().last_kernel_ms:.0f} us), ll={ll:.6f}", flush=True)
+        om = orc.Cont(0, np.ones(K), 0.1 * np.ones((K, K)), np.ones((K, K)))
+        for rec in (True, False):
+            t0 = time.perf_counter()
+            for _ in range(50):
+                llo = om.loglik(t, nodes, T, recursive=rec)
+            print(f"oracle (1 thread) recursive={rec}: {1e6*(time.perf_counter()-t0)/50:.0f} us per call, ll={llo:.6f}", flush=True)
+        sys.exit(0)
     if which == "peaks":
         import ctypes
         ctx = nhp.default_context()
