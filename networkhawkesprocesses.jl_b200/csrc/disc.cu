@@ -227,6 +227,38 @@ __global__ void __launch_bounds__(256) k_convolve(const int *__restrict__ data, 
         }
     }
 }
+// Same arithmetic (lags ascending), one thread per (t, p) producing all B basis outputs from L coalesced count loads;
+// the (t, p)-major thread order makes a warp's stores one contiguous 32*B*8-byte span of convT.
+template <int BMAX>
+__global__ void __launch_bounds__(256) k_convolve_tp(const int *__restrict__ data, int N, int64_t T, const double *__restrict__ phi, int L, int B,
+                                                     double *__restrict__ convT) {
+    extern __shared__ double s_phi[];
+    for (int i = threadIdx.x; i < L * B; i += blockDim.x) s_phi[i] = phi[i];
+    __syncthreads();
+    const int64_t total = T * N;
+    for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (int64_t)gridDim.x * blockDim.x) {
+        const int64_t t = e / N;
+        const int p = (int)(e - t * N);
+        double acc[BMAX];
+#pragma unroll
+        for (int b = 0; b < BMAX; b++) acc[b] = 0.0;
+        for (int l = 1; l <= L; l++) {
+            if (t - l < 0) break;
+            const int v = __ldg(data + (t - l) * N + p);
+            if (v) {
+                const double dv = (double)v;
+#pragma unroll
+                for (int b = 0; b < BMAX; b++)
+                    if (b < B) acc[b] += s_phi[(l - 1) + L * b] * dv;
+            }
+        }
+        double *dst = convT + e * B;
+#pragma unroll
+        for (int b = 0; b < BMAX; b++)
+            if (b < B) dst[b] = acc[b] > 0.0 ? acc[b] : 0.0;
+    }
+}
+
 // Julia layout export: out[t + T*(n + N*b)] = convT[t][n*B + b]   (tiled transpose)
 __global__ void k_conv_export(const double *__restrict__ convT, int N, int B, int64_t T, double *__restrict__ out) {
     __shared__ double tile[32][33];
@@ -272,6 +304,10 @@ extern "C" int nhp_disc_convolve(nhp_ctx *ctx, nhp_disc *dd, const double *phi, 
     dd->L = L; dd->B = B;
     NHP_TRY(nhp_timer_begin(ctx));
     int grid = (int)std::min<int64_t>(dd->T, (int64_t)ctx->sm_count * 16);
+    if (B <= 8) {
+        int g2 = (int)std::min<int64_t>((dd->T * dd->N + 255) / 256, (int64_t)ctx->sm_count * 32);
+        k_convolve_tp<8><<<g2, 256, (size_t)(L * B) * sizeof(double), s>>>(dd->d_data, (int)dd->N, dd->T, ex->phi, (int)L, (int)B, dd->d_conv);
+    } else
     k_convolve<<<grid, 256, (size_t)(L * B) * sizeof(double), s>>>(dd->d_data, (int)dd->N, dd->T, ex->phi, (int)L, (int)B, dd->d_conv);
     NHP_LAUNCHED(ctx);
     DCUDA(ctx, cudaMemsetAsync(ex->csum, 0, (size_t)NB * sizeof(double), s));
