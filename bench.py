@@ -396,6 +396,25 @@ def run_ours(args, rank, world, local_rank):
             "gpu_launches": int(launches), "roofline": roofline,
             "detail": {"loglik_events_per_s": world * n / (med["loglik"] * 1e-3), "gibbs_sweep_events_per_s": world * n / ((med["parents"] + med["second_pass"]) * 1e-3)}}
 
+    # one-pass variant: the parent sweep also yields the log-likelihood (nhp_cont_sweep_loglik); reported, not the headline
+    if world == 1:
+        ev3 = upload()
+        ctx.check(lib.nhp_set_option(ctx.h, 1, 1))  # NHP_OPT_SWEEP_LOGLIK
+        fused = []
+        for r in range(5):
+            f0 = torch.cuda.Event(enable_timing=True); f1 = torch.cuda.Event(enable_timing=True)
+            f0.record(stream)
+            ctx.check(lib.nhp_cont_resample_parents(ctx.h, ev3, 20261018, 500 + r, None, None, None))
+            ctx.check(lib.nhp_cont_suffstats_second_pass(ctx.h, ev3))
+            llf = ctypes.c_double()
+            ctx.check(lib.nhp_cont_sweep_loglik(ctx.h, ev3, ctypes.byref(llf)))
+            f1.record(stream); f1.synchronize()
+            fused.append(f0.elapsed_time(f1))
+        lib.nhp_events_free(ctx.h, ev3)
+        ctx.check(lib.nhp_set_option(ctx.h, 1, 0))
+        line["detail"]["fused_loglik_and_gibbs_sweep_ms"] = float(np.median(fused[1:]))
+        line["detail"]["fused_loglik_and_gibbs_sweep_events_per_s"] = n / (float(np.median(fused[1:])) * 1e-3)
+
     if world == 1 and args.adjacency:
         # continuous.jl:444-519 on the same resident data (not part of the timed step; reported for completeness)
         ev2 = upload()

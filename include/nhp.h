@@ -50,6 +50,9 @@ int64_t nhp_launch_count(const nhp_ctx *ctx);
 /* device-time (CUDA events on the context stream) of the kernels of the most recent call, ms */
 double nhp_last_kernel_ms(const nhp_ctx *ctx);
 
+/* Context options. */
+#define NHP_OPT_SWEEP_LOGLIK 1 /* value != 0: nhp_cont_resample_parents also accumulates the log-likelihood terms */
+int nhp_set_option(nhp_ctx *ctx, int option, int64_t value);
 /* Run every later call of this context on the caller's CUDA stream (a cudaStream_t passed as
  * void*; NULL restores the context's own stream), e.g. torch.cuda.current_stream().cuda_stream so
  * that the caller's CUDA events and NCCL collectives order with the library's kernels. */
@@ -106,6 +109,11 @@ int nhp_cont_intensity(nhp_ctx *ctx, nhp_events *ev, const double *times, int64_
  * parents / parentnodes may be NULL (kept on device for nhp_cont_suffstats). */
 int nhp_cont_resample_parents(nhp_ctx *ctx, nhp_events *ev, uint64_t seed, uint64_t counter, const double *u,
                               int64_t *parents, int64_t *parentnodes);
+/* The parent sweep evaluates every event's total intensity anyway; with NHP_OPT_SWEEP_LOGLIK enabled it also
+ * accumulates the log-likelihood terms of the parameters it ran with (one extra log per event), and this call
+ * returns that log-likelihood (same value as nhp_cont_loglik with recursive = 0) without a second pass over the events.  For a shard: the shard's additive share; the terms
+ * also sit in slots 0..1 of the phase-0 statistics buffer, so the multi-GPU all-reduce carries them. */
+int nhp_cont_sweep_loglik(nhp_ctx *ctx, nhp_events *ev, double *ll);
 /* Import a parent assignment (1-based global indices, 0 = baseline) and rebuild the fused
  * statistics from it: the "statistics given identical parent assignments" entry. */
 int nhp_cont_parents_set(nhp_ctx *ctx, nhp_events *ev, const int64_t *parents);

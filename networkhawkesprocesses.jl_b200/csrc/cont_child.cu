@@ -98,6 +98,7 @@ template <int KIND> __global__ void __launch_bounds__(NHP_BLOCK) k_child_sweep(c
                 }
                 if (lane == 0) {
                     if (!(S > 0.0) || S > 1.7976931348623157e308) atomicOr(a.flag, 8);
+                    if (a.want_ll) { sum_log += log(S); sum_row += __ldg(a.rowsum + c); }
                     a.poff[i] = chosen;
                     if (chosen == 0) m0++;
                     else {
@@ -113,7 +114,7 @@ template <int KIND> __global__ void __launch_bounds__(NHP_BLOCK) k_child_sweep(c
         }
         if (ca.mode == 2 && lane == 0 && m0) red_add_f64(a.stats + sl.off_M0() + c, (double)m0);
     }
-    if (ca.mode == 0) {
+    if (ca.mode == 0 || ca.mode == 2) {
         block_sum2(sum_log, sum_row, red);
         if (threadIdx.x == 0) { a.partials[2 * (size_t)blockIdx.x] = sum_log; a.partials[2 * (size_t)blockIdx.x + 1] = sum_row; }
     }

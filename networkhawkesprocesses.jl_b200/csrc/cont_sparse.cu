@@ -83,7 +83,7 @@ constexpr int SQMAX = 64;               // window entries one filter thread can 
 // Persistent CTAs: each loops over tiles of STE child events so the per-CTA set-up (log/exp tables,
 // barrier init) is paid once.
 template <int KIND, int MODE>
-__global__ void __launch_bounds__(NHP_BLOCK, 6) k_sweep_sparse(const SparseArgs sa, const int64_t ntiles) {
+__global__ void __launch_bounds__(NHP_BLOCK, 5) k_sweep_sparse(const SparseArgs sa, const int64_t ntiles) {
     typedef typename EntryOf<KIND>::type E;
     const SweepArgs &a = sa.s;
     extern __shared__ __align__(128) unsigned char smem[];
@@ -159,6 +159,7 @@ __global__ void __launch_bounds__(NHP_BLOCK, 6) k_sweep_sparse(const SparseArgs 
                     const double u = a.u ? __ldg(a.u + (i - a.first)) : philox_uniform(a.seed, (uint64_t)gi, a.counter);
                     int chosen = gi == 0 ? 0 : direct_pick<KIND, false>(a, tl, ft, i, ti, ci, jlo, u * S);
                     finish_parent<KIND, false>(a, tl, i, ti, ci, S, chosen, m0_hist);
+                    if (a.want_ll) { sum_log += log(S); sum_row += __ldg(a.rowsum + ci); }
                 }
             }
             __syncthreads();
@@ -267,11 +268,12 @@ __global__ void __launch_bounds__(NHP_BLOCK, 6) k_sweep_sparse(const SparseArgs 
                     }
                 }
                 finish_parent<KIND, true>(a, tl, ie, ti, ce, S, chosen, m0_hist);
+                if (a.want_ll) { sum_log += log(S); sum_row += __ldg(a.rowsum + ce); }  // log-likelihood terms for free
             }
         }
         __syncthreads();  // staging buffers, rows, list and val are reused by the next tile
     }
-    if (MODE == SP_LOGLIK) {
+    if (MODE == SP_LOGLIK || MODE == SP_PARENTS) {
         block_sum2(sum_log, sum_row, red);
         if (threadIdx.x == 0) { a.partials[2 * (size_t)blockIdx.x] = sum_log; a.partials[2 * (size_t)blockIdx.x + 1] = sum_row; }
     }

@@ -160,7 +160,7 @@ __global__ void k_reduce_partials(const double *__restrict__ partials, int64_t n
 // one uniform per event, inverse-cdf walk in that order; fused statistics.
 // ---------------------------------------------------------------------------------------
 template <int KIND, int G, int R, bool ST>
-__device__ __forceinline__ void parents_body(const SweepArgs &a, const Tile &tl, const FastTables *ft, int *m0_hist, double *s_v) {
+__device__ __forceinline__ void parents_body(const SweepArgs &a, const Tile &tl, const FastTables *ft, int *m0_hist, double *s_v, double &sum_log, double &sum_row) {
     typedef typename EntryOf<KIND>::type E;
     constexpr int NG = NHP_BLOCK / G;
     const int gid = threadIdx.x / G, gl = threadIdx.x % G;
@@ -215,6 +215,8 @@ __device__ __forceinline__ void parents_body(const SweepArgs &a, const Tile &tl,
         }
         if (gl == 0) {
             if (!(S > 0.0) || S > 1.7976931348623157e308) atomicOr(a.flag, 8);  // Categorical would reject the vector
+            // S is the event's total intensity: the log-likelihood terms come for free with the sweep
+            if (a.want_ll) { sum_log += log(S); sum_row += __ldg(a.rowsum + ci); }
             a.poff[i] = chosen;
             if (chosen == 0) {
                 if (m0_hist) atomicAdd(m0_hist + ci, 1);
@@ -236,6 +238,8 @@ __global__ void __launch_bounds__(NHP_BLOCK) k_parents(const SweepArgs a, const 
     extern __shared__ __align__(128) unsigned char smem[];
     __shared__ FastTables s_ft;
     __shared__ double s_v[R * NHP_BLOCK];  // cached window weights of pass 1
+    __shared__ double red[16];
+    double sum_log = 0.0, sum_row = 0.0;
     fast_tables_load(&s_ft);
     Stager sg = stager_init(a, smem);
     // baseline-attribution histogram in shared memory behind the staging area (most events are baseline events)
@@ -244,10 +248,12 @@ __global__ void __launch_bounds__(NHP_BLOCK) k_parents(const SweepArgs a, const 
     __syncthreads();
     for (int64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
         Tile tl = stage_tile_at(a, sg, tile);
-        if (tl.staged) parents_body<KIND, G, R, true>(a, tl, &s_ft, m0_hist, s_v);
-        else parents_body<KIND, G, R, false>(a, tl, &s_ft, m0_hist, s_v);
+        if (tl.staged) parents_body<KIND, G, R, true>(a, tl, &s_ft, m0_hist, s_v, sum_log, sum_row);
+        else parents_body<KIND, G, R, false>(a, tl, &s_ft, m0_hist, s_v, sum_log, sum_row);
         __syncthreads();
     }
+    block_sum2(sum_log, sum_row, red);
+    if (threadIdx.x == 0) { a.partials[2 * (size_t)blockIdx.x] = sum_log; a.partials[2 * (size_t)blockIdx.x + 1] = sum_row; }
     if (m0_hist) {
         const StatsLayout sl{a.K};
         for (int k = threadIdx.x; k < a.K; k += NHP_BLOCK)
@@ -432,7 +438,7 @@ static int fill_args(nhp_ctx *ctx, nhp_events *ev, int recursive, SweepArgs &a, 
     a.rowsum = (rec && ctx->has_A) ? ctx->d_rowsum_w : ctx->d_rowsum;  // quirk Q3
     a.D = ctx->dtmax; a.horizon = horizon;
     a.partials = nullptr; a.lam_out = nullptr; a.poff = ev->d_poff; a.u = nullptr; a.seed = 0; a.counter = 0;
-    a.stats = ctx->d_stats0; a.flag = ctx->d_flag;
+    a.stats = ctx->d_stats0; a.flag = ctx->d_flag; a.want_ll = ctx->opt_sweep_ll ? 1 : 0;
     return NHP_OK;
 }
 
@@ -541,6 +547,7 @@ extern "C" int nhp_cont_resample_parents(nhp_ctx *ctx, nhp_events *ev, uint64_t 
     NHP_TRY(fill_args(ctx, ev, 0, a, p));
     int64_t own = ev->n - ev->n_halo;
     ctx->parents_valid = false;
+    ctx->sweep_ll_valid = false;
     NHP_TRY(zero_stats(ctx, ev));
     double *du = nullptr;
     if (u && own > 0) {
@@ -551,21 +558,41 @@ extern "C" int nhp_cont_resample_parents(nhp_ctx *ctx, nhp_events *ev, uint64_t 
         NHP_CUDA(ctx, cudaMemcpyAsync(du, u, (size_t)own * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
     }
     a.u = du; a.seed = seed; a.counter = counter;
+    NHP_TRY(nhp_partials(ctx, 2 * (int64_t)ctx->sm_count * 32, &a.partials));  // one partial per persistent CTA
     NHP_TRY(nhp_timer_begin(ctx));
     if (p.tiles > 0) {
         int sgrid = 0;
         int sp = try_special(ctx, ev, a, 2, &sgrid);
         if (sp < 0) return sp;
-        if (sp == NHP_OK) {}
+        if (sp == NHP_OK) p.grid = sgrid;
         else if (ctx->kind == NHP_LOGITNORMAL) NHP_TRY(dispatch_parents<NHP_LOGITNORMAL>(ctx, p, a));
         else NHP_TRY(dispatch_parents<NHP_EXPONENTIAL>(ctx, p, a));
-    }
+        // the sweep also produced the log-likelihood terms (sum log lambda_i, sum rowsum): stats0[0..1]
+        k_reduce_partials<<<1, 1024, 0, ctx->stream>>>(a.partials, p.grid, ctx->d_stats0);
+        NHP_LAUNCHED(ctx);
+    } else NHP_CUDA(ctx, cudaMemsetAsync(ctx->d_stats0, 0, 2 * sizeof(double), ctx->stream));
     int flag = 0;
     NHP_CUDA(ctx, cudaMemcpyAsync(&flag, ctx->d_flag, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
     NHP_TRY(nhp_timer_end(ctx));
     NHP_CHECK(ctx, !(flag & 8), NHP_ERR_NUMERIC, "resample_parents: non-positive or non-finite total intensity (Categorical would throw, parents.jl:42)");
     ctx->parents_valid = true;
+    ctx->sweep_ll_valid = ctx->opt_sweep_ll;
     return export_parents(ctx, ev, parents, parentnodes);
+}
+
+// log-likelihood of the parameters used by the most recent parent sweep, from the terms that sweep accumulated
+extern "C" int nhp_cont_sweep_loglik(nhp_ctx *ctx, nhp_events *ev, double *ll) {
+    NHP_CHECK(ctx, ctx != nullptr, NHP_ERR_INVALID, "ctx is NULL");
+    NHP_CHECK(ctx, ev && ll, NHP_ERR_INVALID, "nhp_cont_sweep_loglik: NULL argument");
+    NHP_CHECK(ctx, ctx->parents_valid && ctx->sweep_ll_valid, NHP_ERR_STATE,
+              "nhp_cont_sweep_loglik: enable NHP_OPT_SWEEP_LOGLIK (nhp_set_option) and run nhp_cont_resample_parents with the current parameters first");
+    NHP_CUDA(ctx, cudaSetDevice(ctx->device));
+    double h[2];
+    NHP_CUDA(ctx, cudaMemcpyAsync(h, ctx->d_stats0, sizeof(h), cudaMemcpyDeviceToHost, ctx->stream));
+    NHP_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    double base = (ev->flags & 1) ? ctx->lambda0_sum * ev->duration : 0.0;
+    *ll = (0.0 - base) - h[1] + h[0];
+    return NHP_OK;
 }
 
 extern "C" int nhp_cont_parents_set(nhp_ctx *ctx, nhp_events *ev, const int64_t *parents) {
@@ -576,6 +603,7 @@ extern "C" int nhp_cont_parents_set(nhp_ctx *ctx, nhp_events *ev, const int64_t 
     NHP_CUDA(ctx, cudaSetDevice(ctx->device));
     int64_t own = ev->n - ev->n_halo;
     ctx->parents_valid = false;
+    ctx->sweep_ll_valid = false;
     NHP_TRY(zero_stats(ctx, ev));
     if (own > 0) {
         void *scratch;

@@ -30,6 +30,7 @@ struct SweepArgs {
     uint64_t seed, counter;
     double *stats;          // StatsLayout buffer
     int *flag;              // device error flag
+    int want_ll;            // parent sweep also accumulates the log-likelihood terms (NHP_OPT_SWEEP_LOGLIK)
 };
 
 // ---------------------------------------------------------------------------------------

@@ -91,6 +91,14 @@ extern "C" int nhp_set_stream(nhp_ctx *ctx, void *cuda_stream) {
     return NHP_OK;
 }
 
+extern "C" int nhp_set_option(nhp_ctx *ctx, int option, int64_t value) {
+    NHP_CHECK(ctx, ctx != nullptr, NHP_ERR_INVALID, "ctx is NULL");
+    switch (option) {
+        case NHP_OPT_SWEEP_LOGLIK: ctx->opt_sweep_ll = value != 0; ctx->sweep_ll_valid = false; return NHP_OK;
+        default: return nhp_fail(ctx, NHP_ERR_INVALID, "nhp_set_option: unknown option %d", option);
+    }
+}
+
 int nhp_scratch(nhp_ctx *ctx, size_t bytes, void **out) {
     if (bytes > ctx->scratch_cap) {
         NHP_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
@@ -340,6 +348,7 @@ extern "C" int nhp_cont_params_set(nhp_ctx *ctx, int kind, int64_t K, const doub
         ctx->cap_K = K;
     }
     ctx->cont_set = false;
+    ctx->sweep_ll_valid = false;
     ctx->kind = kind; ctx->K = K; ctx->dtmax = dtmax; ctx->has_A = (A != nullptr);
     ctx->density = (double)nnz / (double)KK;
     ctx->theta_min = thmin; ctx->wt_max = wtmax; ctx->lambda0_min = l0min; ctx->lambda0_sum = l0sum;

@@ -130,6 +130,8 @@ struct nhp_ctx {
     double *d_xbar = nullptr;     // [K*K] S1/Mnm scratch
     int *d_flag = nullptr;        // device error flag
     bool parents_valid = false;
+    bool opt_sweep_ll = false;     // NHP_OPT_SWEEP_LOGLIK
+    bool sweep_ll_valid = false;   // stats0[0..1] hold the log-likelihood terms of the last parent sweep
 
     // ---- scratch
     double *d_partials = nullptr;

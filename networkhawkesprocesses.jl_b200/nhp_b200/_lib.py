@@ -11,6 +11,7 @@ LIB_PATH = os.path.join(os.path.dirname(_HERE), "lib", "libnhp.so")
 NHP_OK = 0
 NHP_ERR_INVALID, NHP_ERR_CUDA, NHP_ERR_NO_DEVICE, NHP_ERR_STATE, NHP_ERR_NUMERIC, NHP_ERR_UNSUPPORTED = -1, -2, -3, -4, -5, -6
 NHP_EXPONENTIAL, NHP_LOGITNORMAL = 0, 1
+NHP_OPT_SWEEP_LOGLIK = 1
 
 c_double_p = POINTER(c_double)
 c_int64_p = POINTER(c_int64)
@@ -23,6 +24,7 @@ PROTOTYPES = {
     "nhp_version": (c_int, []),
     "nhp_launch_count": (c_int64, [c_void_p]),
     "nhp_last_kernel_ms": (c_double, [c_void_p]),
+    "nhp_set_option": (c_int, [c_void_p, c_int, c_int64]),
     "nhp_set_stream": (c_int, [c_void_p, c_void_p]),
     "nhp_bench_fp64": (c_int, [c_void_p, c_int, c_double_p]),
     "nhp_test_fastmath": (c_int, [c_void_p, c_int, c_void_p, c_int64, c_void_p]),
@@ -35,6 +37,7 @@ PROTOTYPES = {
     "nhp_cont_event_intensity": (c_int, [c_void_p, c_void_p, c_void_p]),
     "nhp_cont_intensity": (c_int, [c_void_p, c_void_p, c_void_p, c_int64, c_void_p]),
     "nhp_cont_resample_parents": (c_int, [c_void_p, c_void_p, c_uint64, c_uint64, c_void_p, c_void_p, c_void_p]),
+    "nhp_cont_sweep_loglik": (c_int, [c_void_p, c_void_p, c_double_p]),
     "nhp_cont_parents_set": (c_int, [c_void_p, c_void_p, c_void_p]),
     "nhp_cont_suffstats": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]),
     "nhp_cont_resample_adjacency": (c_int, [c_void_p, c_void_p, c_void_p, c_uint64, c_uint64, c_void_p, c_void_p]),

@@ -351,9 +351,11 @@ def intensity(process, data, times):
             d.free()
 
 
-def resample_parents(process, data, seed=0, counter=0, u=None, export=True):
-    """parents.jl:1-23 -> (parents, parentnodes), 1-based, 0 = baseline."""
+def resample_parents(process, data, seed=0, counter=0, u=None, export=True, with_loglik=False):
+    """parents.jl:1-23 -> (parents, parentnodes), 1-based, 0 = baseline.  with_loglik: the sweep also accumulates the
+    log-likelihood terms (read them with sweep_loglikelihood)."""
     ctx = process._ctx()
+    ctx.check(ctx.lib.nhp_set_option(ctx.h, 1, int(bool(with_loglik))))
     d, tmp = process._data(data)
     try:
         process._push(ctx)
@@ -371,6 +373,15 @@ def _resample_parents(ctx, d, seed, counter, u, export):
         raise ValueError("u must hold one uniform per event")
     ctx.check(ctx.lib.nhp_cont_resample_parents(ctx.h, d.h, int(seed), int(counter), _ptr(uu), _ptr(par), _ptr(pn)))
     return par, pn
+
+
+def sweep_loglikelihood(process, data):
+    """Log-likelihood of the parameters the most recent `resample_parents` sweep on `data` ran with; the sweep
+    accumulates the terms while it evaluates the intensities, so no second pass over the events is needed."""
+    ctx = process._ctx()
+    ll = ctypes.c_double()
+    ctx.check(ctx.lib.nhp_cont_sweep_loglik(ctx.h, data.h, ctypes.byref(ll)))
+    return ll.value
 
 
 def sufficient_statistics(process, data, parents=None):

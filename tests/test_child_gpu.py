@@ -34,7 +34,8 @@ def test_child_major_sweep_matches_oracle(kind, K, n, rate, density, dtmax, monk
         monkeypatch.setenv("NHP_CHILD", mode)
         assert nhp.loglikelihood(proc, d, recursive=False) == pytest.approx(ref_ll, rel=1e-10)
         np.testing.assert_allclose(nhp.event_intensity(proc, d), ref_lam, rtol=1e-10)
-        par, pn = nhp.resample_parents(proc, d, u=u)
+        par, pn = nhp.resample_parents(proc, d, u=u, with_loglik=True)
+        assert nhp.sweep_loglikelihood(proc, d) == pytest.approx(ref_ll, rel=1e-10)  # fused with the sweep
         assert np.count_nonzero(par != ref_par) == 0
         st = nhp.sufficient_statistics(proc, d)
         for key in ("M0", "Mn", "Mnm"):

@@ -160,11 +160,12 @@ def test_parents_bit_exact_given_uniforms(kind, K, n, rate, density, G, monkeypa
         proc, om = make_exp(K, 60 + K, density=density, wmax=0.5 / K, dtmax=1.5)
     u = np.random.default_rng(7).random(n)
     d = proc.upload((t, nodes, T))
-    par, pn = nhp.resample_parents(proc, d, u=u)
+    par, pn = nhp.resample_parents(proc, d, u=u, with_loglik=True)
     opar, opn = om.resample_parents(t, nodes, u)
     assert np.count_nonzero(par != opar) == 0
     np.testing.assert_array_equal(pn, opn)
     # statistics of that assignment: counts bit-exact, float sums to 1e-12
+    assert nhp.sweep_loglikelihood(proc, d) == pytest.approx(om.loglik(t, nodes, T, recursive=False), rel=1e-10)  # fused with the sweep
     st = nhp.sufficient_statistics(proc, d)
     ost = orc.suffstats(1 if kind == "ln" else 0, t, nodes, opar, opn, K, proc.impulses.dtmax)
     for key in ("M0", "Mn", "Mnm"):

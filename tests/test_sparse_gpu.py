@@ -35,7 +35,8 @@ def test_sparse_path_matches_oracle_and_dense(kind, K, n, rate, density, dtmax, 
         monkeypatch.setenv("NHP_SPARSE", mode)
         assert nhp.loglikelihood(proc, d, recursive=False) == pytest.approx(ref_ll, rel=1e-10)
         np.testing.assert_allclose(nhp.event_intensity(proc, d), ref_lam, rtol=1e-10)
-        par, pn = nhp.resample_parents(proc, d, u=u)
+        par, pn = nhp.resample_parents(proc, d, u=u, with_loglik=True)
+        assert nhp.sweep_loglikelihood(proc, d) == pytest.approx(ref_ll, rel=1e-10)  # fused with the sweep
         assert np.count_nonzero(par != ref_par) == 0
         np.testing.assert_array_equal(pn, ref_pn)
         st = nhp.sufficient_statistics(proc, d)
