@@ -12,6 +12,11 @@ sys.path.insert(0, ROOT)
 
 def pytest_configure(config):
     config.addinivalue_line("markers", "gpu: needs a B200 (run with -m gpu on the GPU box)")
+    # the shared library is a build artefact (git-ignored): build it in-tree if this checkout has not been built yet
+    lib = os.path.join(ROOT, "networkhawkesprocesses.jl_b200", "lib", "libnhp.so")
+    if not os.path.exists(lib):
+        import subprocess
+        subprocess.check_call(["make", "-C", os.path.join(ROOT, "networkhawkesprocesses.jl_b200", "csrc"), "-j8", "-s"])
 
 
 @pytest.fixture(scope="session")

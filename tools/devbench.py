@@ -145,6 +145,17 @@ if __name__ == "__main__":
                 llo = om.loglik(t, nodes, T, recursive=rec)
             print(f"oracle (1 thread) recursive={rec}: {1e6*(time.perf_counter()-t0)/50:.0f} us per call, ll={llo:.6f}", flush=True)
         sys.exit(0)
+    if which == "query":  # query K n rate nq
+        K, n, rate, nq = int(sys.argv[2]), int(float(sys.argv[3])), float(sys.argv[4]), int(sys.argv[5])
+        t, nodes, T = synth.poisson_stream(n, K, rate, 1)
+        lam0, W, mu, tau, A = synth.ln_params(K, 2)
+        proc = nhp.ContinuousStandardHawkesProcess(nhp.HomogeneousProcess(lam0), nhp.LogitNormalImpulseResponse(mu, tau, 1.0), nhp.DenseWeightModel(W))
+        d = proc.upload((t, nodes, T))
+        tq = np.linspace(0.0, T, nq)
+        for rep in range(3):
+            t0 = time.perf_counter(); lam = nhp.intensity(proc, d, tq)
+            print(f"intensity(process, data, times) K={K} nq={nq} w~{rate:.0f}: kernel {proc._ctx().last_kernel_ms:.2f} ms, call {1e3*(time.perf_counter()-t0):.1f} ms, {nq*rate*K/proc._ctx().last_kernel_ms/1e6:.1f} Gpair/s", flush=True)
+        sys.exit(0)
     if which == "peaks":
         import ctypes
         ctx = nhp.default_context()
