@@ -58,12 +58,12 @@ __device__ __forceinline__ int direct_pick(const SweepArgs &a, const Tile &tl, c
 }
 
 template <int KIND, bool ST>
-__device__ __forceinline__ void finish_parent(const SweepArgs &a, const Tile &tl, int64_t i, double ti, int ci, double S, int chosen, int *m0_hist) {
+__device__ __forceinline__ void finish_parent(const SweepArgs &a, const Tile &tl, int64_t i, double ti, int ci, double S, int chosen, int *m0_hist, bool use_hist) {
     const StatsLayout sl{a.K};
     if (!(S > 0.0) || S > 1.7976931348623157e308) atomicOr(a.flag, 8);
     a.poff[i] = chosen;
     if (chosen == 0) {
-        if (m0_hist) atomicAdd(m0_hist + ci, 1);  // most events are baseline events: keep that counter in shared memory
+        if (use_hist) atomicAdd(m0_hist + ci, 1);  // most events are baseline events: keep that counter in shared memory
         else red_add_f64(a.stats + sl.off_M0() + ci, 1.0);
     }
     else {
@@ -97,14 +97,17 @@ __global__ void __launch_bounds__(NHP_BLOCK, 5) k_sweep_sparse(const SparseArgs 
     double *st = reinterpret_cast<double *>(smem + 16);
     int *sc = reinterpret_cast<int *>(smem + 16 + (size_t)a.cap * 8);
     if (threadIdx.x == 0) { mbar_init(bar, 1); fence_mbar_init(); }
-    unsigned char *p = smem + 16 + (size_t)a.cap * 12;
-    p = (unsigned char *)(((uintptr_t)p + 15) & ~(uintptr_t)15);
-    const int wp = sa.words | 1;                                     // odd row pitch spreads the banks
-    uint32_t *rows = reinterpret_cast<uint32_t *>(p);                // [STE][wp]
-    uint32_t *list = rows + (size_t)wp * STE;                        // [sa.cape] (event << 16) | (i - j)
-    double *val = reinterpret_cast<double *>((((uintptr_t)(list + sa.cape)) + 7) & ~(uintptr_t)7);  // [sa.cape]
-    int *m0_hist = (MODE == SP_PARENTS && sa.m0_smem) ? reinterpret_cast<int *>(val + sa.cape) : nullptr;     // [K]
-    if (m0_hist) for (int k = threadIdx.x; k < a.K; k += NHP_BLOCK) m0_hist[k] = 0;
+    // offsets are rounded as integers (not through a pointer cast) so every access below stays a 32-bit LDS/STS
+    const int wp = sa.words | 1;                                              // odd row pitch spreads the banks
+    const uint32_t off_rows = (16u + (uint32_t)a.cap * 12u + 15u) & ~15u;
+    const uint32_t off_list = off_rows + (uint32_t)wp * STE * 4u;
+    const uint32_t off_val = (off_list + (uint32_t)sa.cape * 4u + 7u) & ~7u;
+    uint32_t *rows = reinterpret_cast<uint32_t *>(smem + off_rows);           // [STE][wp]
+    uint32_t *list = reinterpret_cast<uint32_t *>(smem + off_list);           // [sa.cape] (event << 16) | (i - j)
+    double *val = reinterpret_cast<double *>(smem + off_val);                 // [sa.cape]
+    int *m0_hist = reinterpret_cast<int *>(smem + off_val + (uint32_t)sa.cape * 8u);  // [K], parents mode with m0_smem only
+    const bool use_hist = MODE == SP_PARENTS && sa.m0_smem;
+    if (use_hist) for (int k = threadIdx.x; k < a.K; k += NHP_BLOCK) m0_hist[k] = 0;
     const int e = threadIdx.x / SG, g = threadIdx.x % SG;
     const unsigned gmask = group_mask<SG>();
     double sum_log = 0.0, sum_row = 0.0;
@@ -158,7 +161,7 @@ __global__ void __launch_bounds__(NHP_BLOCK, 5) k_sweep_sparse(const SparseArgs 
                     const int64_t gi = a.index_base + i;
                     const double u = a.u ? __ldg(a.u + (i - a.first)) : philox_uniform(a.seed, (uint64_t)gi, a.counter);
                     int chosen = gi == 0 ? 0 : direct_pick<KIND, false>(a, tl, ft, i, ti, ci, jlo, u * S);
-                    finish_parent<KIND, false>(a, tl, i, ti, ci, S, chosen, m0_hist);
+                    finish_parent<KIND, false>(a, tl, i, ti, ci, S, chosen, m0_hist, use_hist);
                     if (a.want_ll) { sum_log += log(S); sum_row += __ldg(a.rowsum + ci); }
                 }
             }
@@ -267,7 +270,7 @@ __global__ void __launch_bounds__(NHP_BLOCK, 5) k_sweep_sparse(const SparseArgs 
                         }
                     }
                 }
-                finish_parent<KIND, true>(a, tl, ie, ti, ce, S, chosen, m0_hist);
+                finish_parent<KIND, true>(a, tl, ie, ti, ce, S, chosen, m0_hist, use_hist);
                 if (a.want_ll) { sum_log += log(S); sum_row += __ldg(a.rowsum + ce); }  // log-likelihood terms for free
             }
         }
@@ -277,7 +280,7 @@ __global__ void __launch_bounds__(NHP_BLOCK, 5) k_sweep_sparse(const SparseArgs 
         block_sum2(sum_log, sum_row, red);
         if (threadIdx.x == 0) { a.partials[2 * (size_t)blockIdx.x] = sum_log; a.partials[2 * (size_t)blockIdx.x + 1] = sum_row; }
     }
-    if (m0_hist) {
+    if (use_hist) {
         const StatsLayout sl{a.K};
         for (int k = threadIdx.x; k < a.K; k += NHP_BLOCK)
             if (m0_hist[k]) red_add_f64(a.stats + sl.off_M0() + k, (double)m0_hist[k]);
