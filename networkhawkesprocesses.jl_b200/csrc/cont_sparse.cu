@@ -6,7 +6,7 @@
 //   1. filter  -- four threads per child event, each walking a contiguous quarter of the window
 //                 most-recent-first and testing one adjacency bit per predecessor.  The bit-rows of the
 //                 tile's children are staged in shared memory by coalesced warp loads (row of event e
-//                 at [e*wp .. ), wp odd); the hits are flagged in a 64-bit register mask.
+//                 at [e*words .. ), rows are 16-byte multiples); the hits are flagged in a 64-bit register mask.
 //   2. compact -- block exclusive scan of the hit counts -> contiguous, ordered segment per event.
 //   3. evaluate-- all threads stride over the dense hit list: table gather (L2) + FP64 impulse.
 //   4. combine -- one thread per event folds its segment in window order: log-likelihood term, or the
@@ -98,7 +98,7 @@ __global__ void __launch_bounds__(NHP_BLOCK, 5) k_sweep_sparse(const SparseArgs 
     int *sc = reinterpret_cast<int *>(smem + 16 + (size_t)a.cap * 8);
     if (threadIdx.x == 0) { mbar_init(bar, 1); fence_mbar_init(); }
     // offsets are rounded as integers (not through a pointer cast) so every access below stays a 32-bit LDS/STS
-    const int wp = sa.words | 1;                                              // odd row pitch spreads the banks
+    const int wp = sa.words;                                                  // row pitch (multiple of 4 words; probes are random, so no padding)
     const uint32_t off_rows = (16u + (uint32_t)a.cap * 12u + 15u) & ~15u;
     const uint32_t off_list = off_rows + (uint32_t)wp * STE * 4u;
     const uint32_t off_val = (off_list + (uint32_t)sa.cape * 4u + 7u) & ~7u;
@@ -114,11 +114,13 @@ __global__ void __launch_bounds__(NHP_BLOCK, 5) k_sweep_sparse(const SparseArgs 
     uint32_t parity = 0;
     __syncthreads();
 
+    int64_t lo_next = blockIdx.x < ntiles ? a.tile_lo[blockIdx.x] : 0;
     for (int64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
         Tile tl;
         tl.i0 = a.first + tile * STE;
         tl.i1 = min(a.n, tl.i0 + (int64_t)STE);
-        tl.lo = a.tile_lo[tile];
+        tl.lo = lo_next;
+        if (tile + gridDim.x < ntiles) lo_next = a.tile_lo[tile + gridDim.x];  // prefetched a whole tile ahead
         tl.base = tl.lo & ~(int64_t)3;
         tl.st = st; tl.sc = sc;
         const int64_t cnt_stage = (tl.i1 - tl.base + 3) & ~(int64_t)3;
@@ -137,15 +139,11 @@ __global__ void __launch_bounds__(NHP_BLOCK, 5) k_sweep_sparse(const SparseArgs 
                 bulk_g2s(st, a.t + tl.base, (uint32_t)(cnt_stage * 8), bar);
                 bulk_g2s(sc, a.c + tl.base, (uint32_t)(cnt_stage * 4), bar);
             }
-            // adjacency bit-rows of the warp's 8 children: one coalesced load + one conflict-free store per row
-            const int lane = threadIdx.x & 31;
-            uint32_t *dst = rows + (size_t)((threadIdx.x >> 5) * (32 / SG)) * wp + lane;
-#pragma unroll
-            for (int r = 0; r < 32 / SG; r++) {
-                const int cr = __shfl_sync(0xffffffffu, ci, r * SG);
-                const uint32_t *row = sa.abits + (size_t)cr * sa.words + lane;
-                if (lane < sa.words) dst[r * wp] = __ldg(row);
-                for (int w = 32; w + lane < sa.words; w += 32) dst[r * wp + w] = __ldg(row + w);
+            // adjacency bit-row of the thread's own child: its SG threads copy the row in 128-bit pieces
+            {
+                const uint4 *row4 = reinterpret_cast<const uint4 *>(sa.abits + (size_t)ci * sa.words);
+                uint4 *dst4 = reinterpret_cast<uint4 *>(rows + e * wp);
+                for (int w = g; w < (sa.words >> 2); w += SG) dst4[w] = __ldg(row4 + w);
             }
             __syncwarp();
             mbar_wait(bar, parity);
@@ -292,7 +290,7 @@ __global__ void __launch_bounds__(NHP_BLOCK, 5) k_sweep_sparse(const SparseArgs 
 // ---------------------------------------------------------------------------------------
 size_t nhp_sparse_smem(int cap, int words, int lcap, int m0_entries) {
     size_t b = 16 + (size_t)cap * 12 + 16;
-    b += (size_t)(words | 1) * STE * 4;
+    b += (size_t)words * STE * 4;
     b += (size_t)lcap * 4 + 8;
     b += (size_t)lcap * 8;
     b += (size_t)m0_entries * 4;
