@@ -76,14 +76,15 @@ __device__ __forceinline__ void finish_parent(const SweepArgs &a, const Tile &tl
     }
 }
 
-constexpr int SG = 4;                   // threads per child event in the filter
-constexpr int STE = NHP_BLOCK / SG;     // child events per tile
 constexpr int SQMAX = 64;               // window entries one filter thread can flag (64-bit hit mask)
 
 // Persistent CTAs: each loops over tiles of STE child events so the per-CTA set-up (log/exp tables,
 // barrier init) is paid once.
-template <int KIND, int MODE>
+// SG = threads per child event in the filter (2 for short windows: twice the events per tile, half the per-tile
+// overhead per event; 4 otherwise); STE = NHP_BLOCK / SG child events per tile.
+template <int KIND, int MODE, int SG>
 __global__ void __launch_bounds__(NHP_BLOCK, 5) k_sweep_sparse(const SparseArgs sa, const int64_t ntiles) {
+    constexpr int STE = NHP_BLOCK / SG;
     typedef typename EntryOf<KIND>::type E;
     const SweepArgs &a = sa.s;
     extern __shared__ __align__(128) unsigned char smem[];
@@ -114,13 +115,14 @@ __global__ void __launch_bounds__(NHP_BLOCK, 5) k_sweep_sparse(const SparseArgs 
     uint32_t parity = 0;
     __syncthreads();
 
-    int64_t lo_next = blockIdx.x < ntiles ? a.tile_lo[blockIdx.x] : 0;
+    constexpr int TQ = STE / NHP_TQ;  // tile_lo is kept per NHP_TQ events
+    int64_t lo_next = blockIdx.x < ntiles ? a.tile_lo[(int64_t)blockIdx.x * TQ] : 0;
     for (int64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
         Tile tl;
         tl.i0 = a.first + tile * STE;
         tl.i1 = min(a.n, tl.i0 + (int64_t)STE);
         tl.lo = lo_next;
-        if (tile + gridDim.x < ntiles) lo_next = a.tile_lo[tile + gridDim.x];  // prefetched a whole tile ahead
+        if (tile + gridDim.x < ntiles) lo_next = a.tile_lo[(tile + gridDim.x) * TQ];  // prefetched a whole tile ahead
         tl.base = tl.lo & ~(int64_t)3;
         tl.st = st; tl.sc = sc;
         const int64_t cnt_stage = (tl.i1 - tl.base + 3) & ~(int64_t)3;
@@ -288,9 +290,9 @@ __global__ void __launch_bounds__(NHP_BLOCK, 5) k_sweep_sparse(const SparseArgs 
 // ---------------------------------------------------------------------------------------
 // host side: decide whether the sparse path applies and launch it
 // ---------------------------------------------------------------------------------------
-size_t nhp_sparse_smem(int cap, int words, int lcap, int m0_entries) {
+size_t nhp_sparse_smem(int cap, int words, int lcap, int m0_entries, int ste) {
     size_t b = 16 + (size_t)cap * 12 + 16;
-    b += (size_t)words * STE * 4;
+    b += (size_t)words * ste * 4;
     b += (size_t)lcap * 4 + 8;
     b += (size_t)lcap * 8;
     b += (size_t)m0_entries * 4;
@@ -318,33 +320,43 @@ int nhp_cont_try_sparse(nhp_ctx *ctx, const nhp_events *ev, SweepArgs &a, int mo
     bool force = env && atoi(env) == 1;
     if (!force && !(ctx->density <= 0.25)) return 1;
     int words = (int)ctx->abits_words;
-    // capacity of the per-tile hit list: 3x the expected number of active pairs of a tile, at least 512
-    double expect = ev->mean_win * ctx->density * STE;
-    int lcap = 512;
-    while (lcap < 16384 && lcap < 3.0 * expect + 256.0) lcap <<= 1;
+    // two filter threads per event when the windows are short enough for their 64-bit hit masks (128 events per tile)
+    const char *sge = getenv("NHP_SPARSE_SG");
+    int sg = (ev->mean_win * 1.5 + 16.0 <= 2.0 * SQMAX) ? 2 : 4;
+    if (sge && (atoi(sge) == 2 || atoi(sge) == 4)) sg = atoi(sge);
+    const int ste = NHP_BLOCK / sg;
+    // capacity of the per-tile hit list: 2x the expected number of active pairs of a tile + 256, in steps of 256
+    double expect = ev->mean_win * ctx->density * ste;
+    int lcap = (int)std::min(16384.0, 256.0 * std::ceil((2.0 * expect + 256.0) / 256.0));
+    if (lcap < 512) lcap = 512;
     int64_t own = ev->n - ev->n_halo;
-    int64_t need = ((ev->max_win + STE + 8) + 3) & ~(int64_t)3;
+    int64_t need = ((ev->max_win + ste + 8) + 3) & ~(int64_t)3;
     int cap = (int)std::min<int64_t>(need, 8192);
     int m0_entries = (mode == 2 && ctx->K <= 4096) ? (int)ctx->K : 0;
-    size_t smem = nhp_sparse_smem(cap, words, lcap, m0_entries);
+    size_t smem = nhp_sparse_smem(cap, words, lcap, m0_entries, ste);
     if (smem > 100 * 1024) {
         cap = (int)std::min<int64_t>(need, 1024);
-        smem = nhp_sparse_smem(cap, words, lcap, m0_entries);
+        smem = nhp_sparse_smem(cap, words, lcap, m0_entries, ste);
         if (smem > (size_t)ctx->smem_optin - 4096) return 1;
     }
-    int64_t ntiles = (own + STE - 1) / STE;
+    int64_t ntiles = (own + ste - 1) / ste;
     if (ntiles == 0) return 1;
     NHP_CUDA(ctx, fast_tables_upload(ctx->stream));  // this translation unit's copy of the log/exp tables
     SparseArgs sa;
-    a.te = STE; a.cap = cap;
+    a.te = ste; a.cap = cap;
     sa.s = a; sa.abits = ctx->d_abits; sa.words = words; sa.cape = lcap; sa.m0_smem = m0_entries > 0; sa.wlen = ev->d_wlen;
     int *grid = grid_out;
+#define NHP_SPARSE_LAUNCH(KIND, SGV)                                                                                      \
+    do {                                                                                                                  \
+        if (mode == 0) return launch_sparse(ctx, k_sweep_sparse<KIND, SP_LOGLIK, SGV>, grid, smem, sa, ntiles);           \
+        if (mode == 1) return launch_sparse(ctx, k_sweep_sparse<KIND, SP_INTENSITY, SGV>, grid, smem, sa, ntiles);        \
+        return launch_sparse(ctx, k_sweep_sparse<KIND, SP_PARENTS, SGV>, grid, smem, sa, ntiles);                         \
+    } while (0)
     if (ctx->kind == NHP_LOGITNORMAL) {
-        if (mode == 0) return launch_sparse(ctx, k_sweep_sparse<NHP_LOGITNORMAL, SP_LOGLIK>, grid, smem, sa, ntiles);
-        if (mode == 1) return launch_sparse(ctx, k_sweep_sparse<NHP_LOGITNORMAL, SP_INTENSITY>, grid, smem, sa, ntiles);
-        return launch_sparse(ctx, k_sweep_sparse<NHP_LOGITNORMAL, SP_PARENTS>, grid, smem, sa, ntiles);
+        if (sg == 2) NHP_SPARSE_LAUNCH(NHP_LOGITNORMAL, 2);
+        NHP_SPARSE_LAUNCH(NHP_LOGITNORMAL, 4);
     }
-    if (mode == 0) return launch_sparse(ctx, k_sweep_sparse<NHP_EXPONENTIAL, SP_LOGLIK>, grid, smem, sa, ntiles);
-    if (mode == 1) return launch_sparse(ctx, k_sweep_sparse<NHP_EXPONENTIAL, SP_INTENSITY>, grid, smem, sa, ntiles);
-    return launch_sparse(ctx, k_sweep_sparse<NHP_EXPONENTIAL, SP_PARENTS>, grid, smem, sa, ntiles);
+    if (sg == 2) NHP_SPARSE_LAUNCH(NHP_EXPONENTIAL, 2);
+    NHP_SPARSE_LAUNCH(NHP_EXPONENTIAL, 4);
+#undef NHP_SPARSE_LAUNCH
 }
