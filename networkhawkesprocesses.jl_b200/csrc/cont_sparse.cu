@@ -80,8 +80,14 @@ constexpr int SQMAX = 64;               // window entries one filter thread can 
 
 // Persistent CTAs: each loops over tiles of STE child events so the per-CTA set-up (log/exp tables,
 // barrier init) is paid once.
-// SG = threads per child event in the filter (2 for short windows: twice the events per tile, half the per-tile
+// SG = filter threads per child event (2 for short windows: twice the events per tile, half the per-tile
 // overhead per event; 4 otherwise); STE = NHP_BLOCK / SG child events per tile.
+// Thread tid works on event e = tid % STE, share g = tid / STE: a warp holds 32 CONSECUTIVE events with the same
+// share index, so (i) its staged node-id loads touch 32 consecutive words and (ii) each lane can keep its
+// child's adjacency bit row in its own shared-memory bank ("vertical" rows: word w of lane l's row at
+// [w * 32 + l]) -- the random word probes of the filter are bank-conflict free.  The profile that led here
+// (profiles/r01_ncu_sweep_kernels.md) showed the horizontal layout at 84% of the LSU wavefront peak, 58% of the
+// wavefronts being bank conflicts.
 template <int KIND, int MODE, int SG>
 __global__ void __launch_bounds__(NHP_BLOCK, 5) k_sweep_sparse(const SparseArgs sa, const int64_t ntiles) {
     constexpr int STE = NHP_BLOCK / SG;
@@ -91,26 +97,28 @@ __global__ void __launch_bounds__(NHP_BLOCK, 5) k_sweep_sparse(const SparseArgs 
     __shared__ double red[16];
     __shared__ FastTables s_ft;
     __shared__ int s_wsum[NHP_BLOCK / 32];
-    __shared__ int s_eoff[STE], s_ecnt[STE];  // per event: segment offset, hit count (-1 = direct path)
+    __shared__ int s_off[NHP_BLOCK], s_cnt[NHP_BLOCK];  // per filter thread: list offset, hit count (-1 = direct path)
     fast_tables_load(&s_ft);
     const FastTables *ft = &s_ft;
     uint64_t *bar = reinterpret_cast<uint64_t *>(smem);
     double *st = reinterpret_cast<double *>(smem + 16);
     int *sc = reinterpret_cast<int *>(smem + 16 + (size_t)a.cap * 8);
-    if (threadIdx.x == 0) { mbar_init(bar, 1); fence_mbar_init(); }
+    // one arrival for the TMA transaction + one per warp for its share of the bit-row gather
+    if (threadIdx.x == 0) { mbar_init(bar, 1 + NHP_BLOCK / 32); fence_mbar_init(); }
     // offsets are rounded as integers (not through a pointer cast) so every access below stays a 32-bit LDS/STS
-    const int wp = sa.words;                                                  // row pitch (multiple of 4 words; probes are random, so no padding)
-    const uint32_t off_rows = (16u + (uint32_t)a.cap * 12u + 15u) & ~15u;
+    const int wp = sa.words;  // words per bit row (multiple of 4)
+    const uint32_t off_rows = (16u + (uint32_t)a.cap * 12u + 127u) & ~127u;
     const uint32_t off_list = off_rows + (uint32_t)wp * STE * 4u;
     const uint32_t off_val = (off_list + (uint32_t)sa.cape * 4u + 7u) & ~7u;
-    uint32_t *rows = reinterpret_cast<uint32_t *>(smem + off_rows);           // [STE][wp]
+    uint32_t *rows = reinterpret_cast<uint32_t *>(smem + off_rows);           // [STE / 32][wp][32 lanes]
     uint32_t *list = reinterpret_cast<uint32_t *>(smem + off_list);           // [sa.cape] (event << 16) | (i - j)
     double *val = reinterpret_cast<double *>(smem + off_val);                 // [sa.cape]
     int *m0_hist = reinterpret_cast<int *>(smem + off_val + (uint32_t)sa.cape * 8u);  // [K], parents mode with m0_smem only
     const bool use_hist = MODE == SP_PARENTS && sa.m0_smem;
     if (use_hist) for (int k = threadIdx.x; k < a.K; k += NHP_BLOCK) m0_hist[k] = 0;
-    const int e = threadIdx.x / SG, g = threadIdx.x % SG;
-    const unsigned gmask = group_mask<SG>();
+    const int e = threadIdx.x % STE, g = threadIdx.x / STE;
+    const int lane = threadIdx.x & 31;
+    uint32_t *myrow = rows + (size_t)(e >> 5) * wp * 32 + lane;  // word w of this event's bit row: myrow[w * 32]
     double sum_log = 0.0, sum_row = 0.0;
     uint32_t parity = 0;
     __syncthreads();
@@ -135,22 +143,6 @@ __global__ void __launch_bounds__(NHP_BLOCK, 5) k_sweep_sparse(const SparseArgs 
         // bit-row gather (below) overlaps the TMA transfer instead of waiting for it
         const int ci = live ? __ldg(a.c + i) : 0;
         const int wraw = live ? (int)__ldg(sa.wlen + (i - a.first)) : 0;
-        if (tl.staged) {
-            if (threadIdx.x == 0) {
-                mbar_expect_tx(bar, (uint32_t)(cnt_stage * 12));
-                bulk_g2s(st, a.t + tl.base, (uint32_t)(cnt_stage * 8), bar);
-                bulk_g2s(sc, a.c + tl.base, (uint32_t)(cnt_stage * 4), bar);
-            }
-            // adjacency bit-row of the thread's own child: its SG threads copy the row in 128-bit pieces
-            {
-                const uint4 *row4 = reinterpret_cast<const uint4 *>(sa.abits + (size_t)ci * sa.words);
-                uint4 *dst4 = reinterpret_cast<uint4 *>(rows + e * wp);
-                for (int w = g; w < (sa.words >> 2); w += SG) dst4[w] = __ldg(row4 + w);
-            }
-            __syncwarp();
-            mbar_wait(bar, parity);
-            parity ^= 1u;
-        }
         if (!tl.staged) {  // window larger than the staging buffer: direct path from global memory
             if (live && g == 0) {
                 const double ti = __ldg(a.t + i);
@@ -165,9 +157,27 @@ __global__ void __launch_bounds__(NHP_BLOCK, 5) k_sweep_sparse(const SparseArgs 
                     if (a.want_ll) { sum_log += log(S); sum_row += __ldg(a.rowsum + ci); }
                 }
             }
-            __syncthreads();
-            continue;
+            continue;  // nothing in shared memory was touched
         }
+        if (threadIdx.x == 0) {
+            mbar_expect_tx(bar, (uint32_t)(cnt_stage * 12));
+            bulk_g2s(st, a.t + tl.base, (uint32_t)(cnt_stage * 8), bar);
+            bulk_g2s(sc, a.c + tl.base, (uint32_t)(cnt_stage * 4), bar);
+        }
+        // adjacency bit row of the lane's child into the lane's bank; the SG warps that share these 32 events split
+        // the row's 16-byte pieces between them
+        {
+            const uint4 *row4 = reinterpret_cast<const uint4 *>(sa.abits + (size_t)ci * sa.words);
+            for (int j = g; j < (wp >> 2); j += SG) {
+                const uint4 v = __ldg(row4 + j);
+                uint32_t *d = myrow + j * 128;
+                d[0] = v.x; d[32] = v.y; d[64] = v.z; d[96] = v.w;
+            }
+        }
+        __syncwarp();
+        if (lane == 0) mbar_arrive(bar);
+        mbar_wait(bar, parity);
+        parity ^= 1u;
         // ---- 1. filter -------------------------------------------------------------------------------------
         unsigned long long hits = 0ull;
         int k0 = 0;
@@ -179,15 +189,14 @@ __global__ void __launch_bounds__(NHP_BLOCK, 5) k_sweep_sparse(const SparseArgs 
             const int q = (wlen + SG - 1) / SG;
             k0 = g * q;
             const int k1 = min(wlen, k0 + q);
-            over = q > SQMAX || wraw >= 65535;
+            over = q > SQMAX || wraw >= 65535;  // the same for every share of the event
             if (!over) {
-                const uint32_t *myrow = rows + (size_t)e * wp;
                 const int *src = sc + ib - k0 - 1;  // position k0+1+m is src[-m]
                 const int cntk = k1 - k0;
                 int m = 0;
                 for (; m + 4 <= cntk; m += 4) {  // four independent probes per trip
                     int p0 = src[-m], p1 = src[-m - 1], p2 = src[-m - 2], p3 = src[-m - 3];
-                    uint32_t w0 = myrow[p0 >> 5], w1 = myrow[p1 >> 5], w2 = myrow[p2 >> 5], w3 = myrow[p3 >> 5];
+                    uint32_t w0 = myrow[p0 & ~31], w1 = myrow[p1 & ~31], w2 = myrow[p2 & ~31], w3 = myrow[p3 & ~31];
                     unsigned long long b4 = (unsigned long long)(((w0 >> (p0 & 31)) & 1u) | (((w1 >> (p1 & 31)) & 1u) << 1) |
                                                                  (((w2 >> (p2 & 31)) & 1u) << 2) | (((w3 >> (p3 & 31)) & 1u) << 3));
                     hits |= b4 << m;
@@ -198,19 +207,19 @@ __global__ void __launch_bounds__(NHP_BLOCK, 5) k_sweep_sparse(const SparseArgs 
                     for (int r = 0; r < 3; r++) {
                         const bool ok = m + r < cntk;
                         int p0 = ok ? src[-m - r] : 0;
-                        b3 |= (unsigned long long)(ok ? ((myrow[p0 >> 5] >> (p0 & 31)) & 1u) : 0u) << r;
+                        b3 |= (unsigned long long)(ok ? ((myrow[p0 & ~31] >> (p0 & 31)) & 1u) : 0u) << r;
                     }
                     hits |= b3 << m;
                 }
             }
         }
-        const bool overflow = (__ballot_sync(0xffffffffu, over) & gmask) != 0u;
-        const int cnt = overflow ? 0 : __popcll(hits);
-        // ---- 2. compact: exclusive scan of cnt over the block (thread order == (event, window order)) -------
+        const int cnt = __popcll(hits);
+        // ---- 2. compact: exclusive scan of cnt over the block; an event's hits form SG segments (one per share),
+        //         each contiguous and in window order ----------------------------------------------------------
         int x = cnt;
 #pragma unroll
-        for (int d = 1; d < 32; d <<= 1) { int y = __shfl_up_sync(0xffffffffu, x, d); if ((threadIdx.x & 31) >= d) x += y; }
-        if ((threadIdx.x & 31) == 31) s_wsum[threadIdx.x >> 5] = x;
+        for (int d = 1; d < 32; d <<= 1) { int y = __shfl_up_sync(0xffffffffu, x, d); if (lane >= d) x += y; }
+        if (lane == 31) s_wsum[threadIdx.x >> 5] = x;
         __syncthreads();
         int off = x - cnt, total = 0;
 #pragma unroll
@@ -225,12 +234,8 @@ __global__ void __launch_bounds__(NHP_BLOCK, 5) k_sweep_sparse(const SparseArgs 
                 list[o++] = ((uint32_t)e << 16) | (uint32_t)(k0 + 1 + b);
             }
         }
-        {
-            int ecnt = cnt;
-#pragma unroll
-            for (int d = SG / 2; d >= 1; d >>= 1) ecnt += __shfl_xor_sync(gmask, ecnt, d, SG);
-            if (g == 0) { s_eoff[e] = off; s_ecnt[e] = (overflow || !fits) ? -1 : ecnt; }
-        }
+        s_off[threadIdx.x] = off;
+        s_cnt[threadIdx.x] = (over || !fits) ? -1 : cnt;
         __syncthreads();
         // ---- 3. evaluate the active pairs ------------------------------------------------------------------
         if (fits) {
@@ -242,36 +247,43 @@ __global__ void __launch_bounds__(NHP_BLOCK, 5) k_sweep_sparse(const SparseArgs 
             }
         }
         __syncthreads();
-        // ---- 4. combine: thread ev < STE owns event ev (two warps instead of eight quarter-filled ones) ------
-        if (threadIdx.x < STE && tl.i0 + threadIdx.x < tl.i1) {
-            const int64_t ie = tl.i0 + threadIdx.x;
-            const int ibe = (int)(ie - tl.base);
-            const double ti = st[ibe];
-            const int ce = sc[ibe];
-            const int ecnt = s_ecnt[threadIdx.x], eoff = s_eoff[threadIdx.x];
+        // ---- 4. combine: the share-0 thread of each event (STE / 32 full warps) ---------------------------------
+        if (g == 0 && live) {
+            const double ti = st[ib];
+            const bool direct = s_cnt[e] < 0;  // over / !fits are event- and tile-wide: share 0 tells
             double S = 0.0;
-            if (ecnt < 0) S = direct_sum<KIND, true>(a, tl, ft, ie, ti, ce, jlo);
-            else for (int k = 0; k < ecnt; k++) S += val[eoff + k];
-            S += __ldg(a.lambda0 + ce);
-            if (MODE == SP_LOGLIK) { sum_log += log(S); sum_row += __ldg(a.rowsum + ce); }
-            else if (MODE == SP_INTENSITY) a.lam_out[ie - a.first] = S;
+            if (direct) S = direct_sum<KIND, true>(a, tl, ft, i, ti, ci, jlo);
             else {
-                const int64_t gi = a.index_base + ie;
-                const double u = a.u ? __ldg(a.u + (ie - a.first)) : philox_uniform(a.seed, (uint64_t)gi, a.counter);
+#pragma unroll
+                for (int h = 0; h < SG; h++) {
+                    const int o = s_off[h * STE + e], c = s_cnt[h * STE + e];
+                    for (int k = 0; k < c; k++) S += val[o + k];
+                }
+            }
+            S += __ldg(a.lambda0 + ci);
+            if (MODE == SP_LOGLIK) { sum_log += log(S); sum_row += __ldg(a.rowsum + ci); }
+            else if (MODE == SP_INTENSITY) a.lam_out[i - a.first] = S;
+            else {
+                const int64_t gi = a.index_base + i;
+                const double u = a.u ? __ldg(a.u + (i - a.first)) : philox_uniform(a.seed, (uint64_t)gi, a.counter);
                 const double target = u * S;
                 int chosen = 0;
                 if (gi != 0) {
-                    if (ecnt < 0) chosen = direct_pick<KIND, true>(a, tl, ft, ie, ti, ce, jlo, target);
+                    if (direct) chosen = direct_pick<KIND, true>(a, tl, ft, i, ti, ci, jlo, target);
                     else {
                         double cum = 0.0;
-                        for (int k = 0; k < ecnt; k++) {
-                            cum += val[eoff + k];
-                            if (cum > target) { chosen = (int)(list[eoff + k] & 0xffff); break; }
+#pragma unroll
+                        for (int h = 0; h < SG; h++) {
+                            const int o = s_off[h * STE + e], c = s_cnt[h * STE + e];
+                            for (int k = 0; k < c && chosen == 0; k++) {
+                                cum += val[o + k];
+                                if (cum > target) chosen = (int)(list[o + k] & 0xffff);
+                            }
                         }
                     }
                 }
-                finish_parent<KIND, true>(a, tl, ie, ti, ce, S, chosen, m0_hist, use_hist);
-                if (a.want_ll) { sum_log += log(S); sum_row += __ldg(a.rowsum + ce); }  // log-likelihood terms for free
+                finish_parent<KIND, true>(a, tl, i, ti, ci, S, chosen, m0_hist, use_hist);
+                if (a.want_ll) { sum_log += log(S); sum_row += __ldg(a.rowsum + ci); }  // log-likelihood terms for free
             }
         }
         __syncthreads();  // staging buffers, rows, list and val are reused by the next tile
@@ -291,7 +303,7 @@ __global__ void __launch_bounds__(NHP_BLOCK, 5) k_sweep_sparse(const SparseArgs 
 // host side: decide whether the sparse path applies and launch it
 // ---------------------------------------------------------------------------------------
 size_t nhp_sparse_smem(int cap, int words, int lcap, int m0_entries, int ste) {
-    size_t b = 16 + (size_t)cap * 12 + 16;
+    size_t b = 16 + (size_t)cap * 12 + 128;
     b += (size_t)words * ste * 4;
     b += (size_t)lcap * 4 + 8;
     b += (size_t)lcap * 8;

@@ -6,7 +6,7 @@ import os
 from ctypes import POINTER, c_char_p, c_double, c_int, c_int64, c_uint64, c_void_p
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(os.path.dirname(_HERE), "lib", "libnhp.so")
+LIB_PATH = os.environ.get("NHP_LIB_PATH") or os.path.join(os.path.dirname(_HERE), "lib", "libnhp.so")  # override: A/B builds
 
 NHP_OK = 0
 NHP_ERR_INVALID, NHP_ERR_CUDA, NHP_ERR_NO_DEVICE, NHP_ERR_STATE, NHP_ERR_NUMERIC, NHP_ERR_UNSUPPORTED = -1, -2, -3, -4, -5, -6
