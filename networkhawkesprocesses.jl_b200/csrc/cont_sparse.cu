@@ -102,12 +102,13 @@ __global__ void __launch_bounds__(NHP_BLOCK, 5) k_sweep_sparse(const SparseArgs 
     const FastTables *ft = &s_ft;
     uint64_t *bar = reinterpret_cast<uint64_t *>(smem);
     double *st = reinterpret_cast<double *>(smem + 16);
-    int *sc = reinterpret_cast<int *>(smem + 16 + (size_t)a.cap * 8);
+    int *sc = reinterpret_cast<int *>(smem + 16 + (size_t)a.cap * 8 + 32);  // 8 zero ints in front: the filter may walk that far past a window
+    if (threadIdx.x < 8) sc[-1 - (int)threadIdx.x] = 0;
     // one arrival for the TMA transaction + one per warp for its share of the bit-row gather
     if (threadIdx.x == 0) { mbar_init(bar, 1 + NHP_BLOCK / 32); fence_mbar_init(); }
     // offsets are rounded as integers (not through a pointer cast) so every access below stays a 32-bit LDS/STS
     const int wp = sa.words;  // words per bit row (multiple of 4)
-    const uint32_t off_rows = (16u + (uint32_t)a.cap * 12u + 127u) & ~127u;
+    const uint32_t off_rows = (16u + (uint32_t)a.cap * 12u + 32u + 127u) & ~127u;
     const uint32_t off_list = off_rows + (uint32_t)wp * STE * 4u;
     const uint32_t off_val = (off_list + (uint32_t)sa.cape * 4u + 7u) & ~7u;
     uint32_t *rows = reinterpret_cast<uint32_t *>(smem + off_rows);           // [STE / 32][wp][32 lanes]
@@ -190,27 +191,23 @@ __global__ void __launch_bounds__(NHP_BLOCK, 5) k_sweep_sparse(const SparseArgs 
             k0 = g * q;
             const int k1 = min(wlen, k0 + q);
             over = q > SQMAX || wraw >= 65535;  // the same for every share of the event
-            if (!over) {
+            if (!over && k1 > k0) {
+                // Eight probes per trip and no remainder loop: a share is walked past its end in whole trips (the extra
+                // entries are older staged events, or the zero pad in front of sc) and the excess bits are masked off.
                 const int *src = sc + ib - k0 - 1;  // position k0+1+m is src[-m]
                 const int cntk = k1 - k0;
-                int m = 0;
-                for (; m + 4 <= cntk; m += 4) {  // four independent probes per trip
-                    int p0 = src[-m], p1 = src[-m - 1], p2 = src[-m - 2], p3 = src[-m - 3];
-                    uint32_t w0 = myrow[p0 & ~31], w1 = myrow[p1 & ~31], w2 = myrow[p2 & ~31], w3 = myrow[p3 & ~31];
-                    unsigned long long b4 = (unsigned long long)(((w0 >> (p0 & 31)) & 1u) | (((w1 >> (p1 & 31)) & 1u) << 1) |
-                                                                 (((w2 >> (p2 & 31)) & 1u) << 2) | (((w3 >> (p3 & 31)) & 1u) << 3));
-                    hits |= b4 << m;
+#pragma unroll 1
+                for (int m = 0; m < cntk; m += 8) {
+                    const int p0 = src[-m], p1 = src[-m - 1], p2 = src[-m - 2], p3 = src[-m - 3];
+                    const int p4 = src[-m - 4], p5 = src[-m - 5], p6 = src[-m - 6], p7 = src[-m - 7];
+                    const uint32_t w0 = myrow[p0 & ~31], w1 = myrow[p1 & ~31], w2 = myrow[p2 & ~31], w3 = myrow[p3 & ~31];
+                    const uint32_t w4 = myrow[p4 & ~31], w5 = myrow[p5 & ~31], w6 = myrow[p6 & ~31], w7 = myrow[p7 & ~31];
+                    const uint32_t b8 = ((w0 >> (p0 & 31)) & 1u) | (((w1 >> (p1 & 31)) & 1u) << 1) | (((w2 >> (p2 & 31)) & 1u) << 2) |
+                                        (((w3 >> (p3 & 31)) & 1u) << 3) | (((w4 >> (p4 & 31)) & 1u) << 4) | (((w5 >> (p5 & 31)) & 1u) << 5) |
+                                        (((w6 >> (p6 & 31)) & 1u) << 6) | (((w7 >> (p7 & 31)) & 1u) << 7);
+                    hits |= (unsigned long long)b8 << m;
                 }
-                if (m < cntk) {  // up to three left-over probes, branch-free
-                    unsigned long long b3 = 0ull;
-#pragma unroll
-                    for (int r = 0; r < 3; r++) {
-                        const bool ok = m + r < cntk;
-                        int p0 = ok ? src[-m - r] : 0;
-                        b3 |= (unsigned long long)(ok ? ((myrow[p0 & ~31] >> (p0 & 31)) & 1u) : 0u) << r;
-                    }
-                    hits |= b3 << m;
-                }
+                hits &= ~0ull >> (64 - cntk);  // 1 <= cntk <= SQMAX = 64
             }
         }
         const int cnt = __popcll(hits);
@@ -303,7 +300,7 @@ __global__ void __launch_bounds__(NHP_BLOCK, 5) k_sweep_sparse(const SparseArgs 
 // host side: decide whether the sparse path applies and launch it
 // ---------------------------------------------------------------------------------------
 size_t nhp_sparse_smem(int cap, int words, int lcap, int m0_entries, int ste) {
-    size_t b = 16 + (size_t)cap * 12 + 128;
+    size_t b = 16 + (size_t)cap * 12 + 32 + 128;
     b += (size_t)words * ste * 4;
     b += (size_t)lcap * 4 + 8;
     b += (size_t)lcap * 8;
