@@ -168,11 +168,13 @@ __global__ void __launch_bounds__(NHP_BLOCK, 5) k_sweep_sparse(const SparseArgs 
         // adjacency bit row of the lane's child into the lane's bank; the SG warps that share these 32 events split
         // the row's 16-byte pieces between them
         {
-            const uint4 *row4 = reinterpret_cast<const uint4 *>(sa.abits + (size_t)ci * sa.words);
-            for (int j = g; j < (wp >> 2); j += SG) {
-                const uint4 v = __ldg(row4 + j);
-                uint32_t *d = myrow + j * 128;
-                d[0] = v.x; d[32] = v.y; d[64] = v.z; d[96] = v.w;
+            const uint32_t *row = sa.abits + (size_t)ci * sa.words;  // rows are 32-byte multiples
+            for (int j = g; j < (wp >> 3); j += SG) {              // 256-bit pieces: a quarter of the L1 tag look-ups of 64-bit ones
+                uint32_t v[8];
+                ldg256_u32(row + 8 * j, v);
+                uint32_t *d = myrow + j * 256;
+#pragma unroll
+                for (int r = 0; r < 8; r++) d[32 * r] = v[r];
             }
         }
         __syncwarp();

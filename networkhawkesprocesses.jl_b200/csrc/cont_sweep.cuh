@@ -186,6 +186,13 @@ __device__ __forceinline__ EntryLN load_entry(const EntryLN *p) {
     asm("ld.global.nc.v4.f64 {%0,%1,%2,%3}, [%4];" : "=d"(e.cf), "=d"(e.mu), "=d"(e.h), "=d"(e.pad) : "l"(p));
     return e;
 }
+// 32 bytes (8 words) through the read-only path in one request; p must be 32-byte aligned
+__device__ __forceinline__ void ldg256_u32(const uint32_t *p, uint32_t (&w)[8]) {
+    unsigned long long a, b, c, d;
+    asm("ld.global.nc.v4.u64 {%0,%1,%2,%3}, [%4];" : "=l"(a), "=l"(b), "=l"(c), "=l"(d) : "l"(p));
+    w[0] = (uint32_t)a; w[1] = (uint32_t)(a >> 32); w[2] = (uint32_t)b; w[3] = (uint32_t)(b >> 32);
+    w[4] = (uint32_t)c; w[5] = (uint32_t)(c >> 32); w[6] = (uint32_t)d; w[7] = (uint32_t)(d >> 32);
+}
 __device__ __forceinline__ EntryEX load_entry(const EntryEX *p) {
     double2 a = __ldg(reinterpret_cast<const double2 *>(p));
     EntryEX e;

@@ -329,7 +329,7 @@ extern "C" int nhp_cont_params_set(nhp_ctx *ctx, int kind, int64_t K, const doub
         NHP_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
         free_cont(ctx);
         StatsLayout sl{K};
-        int64_t words = (((K + 31) / 32) + 3) & ~(int64_t)3;  // bit rows padded to 16 bytes (128-bit gathers)
+        int64_t words = (((K + 31) / 32) + 7) & ~(int64_t)7;  // bit rows padded to 32 bytes (256-bit gathers)
         NHP_CUDA(ctx, cudaMalloc(&ctx->d_lambda0, (size_t)K * sizeof(double)));
         NHP_CUDA(ctx, cudaMalloc(&ctx->d_W, (size_t)KK * sizeof(double)));
         NHP_CUDA(ctx, cudaMalloc(&ctx->d_A, (size_t)KK * sizeof(double)));
