@@ -148,14 +148,14 @@ __global__ void __launch_bounds__(NHP_BLOCK, 5) k_sweep_sparse(const SparseArgs 
             if (live && g == 0) {
                 const double ti = __ldg(a.t + i);
                 const double S = direct_sum<KIND, false>(a, tl, ft, i, ti, ci, jlo) + __ldg(a.lambda0 + ci);
-                if (MODE == SP_LOGLIK) { sum_log += log(S); sum_row += __ldg(a.rowsum + ci); }
+                if (MODE == SP_LOGLIK) sum_log += log(S);
                 else if (MODE == SP_INTENSITY) a.lam_out[i - a.first] = S;
                 else {
                     const int64_t gi = a.index_base + i;
                     const double u = a.u ? __ldg(a.u + (i - a.first)) : philox_uniform(a.seed, (uint64_t)gi, a.counter);
                     int chosen = gi == 0 ? 0 : direct_pick<KIND, false>(a, tl, ft, i, ti, ci, jlo, u * S);
                     finish_parent<KIND, false>(a, tl, i, ti, ci, S, chosen, m0_hist, use_hist);
-                    if (a.want_ll) { sum_log += log(S); sum_row += __ldg(a.rowsum + ci); }
+                    if (a.want_ll) sum_log += log(S);
                 }
             }
             continue;  // nothing in shared memory was touched
@@ -260,7 +260,7 @@ __global__ void __launch_bounds__(NHP_BLOCK, 5) k_sweep_sparse(const SparseArgs 
                 }
             }
             S += __ldg(a.lambda0 + ci);
-            if (MODE == SP_LOGLIK) { sum_log += log(S); sum_row += __ldg(a.rowsum + ci); }
+            if (MODE == SP_LOGLIK) sum_log += log(S);
             else if (MODE == SP_INTENSITY) a.lam_out[i - a.first] = S;
             else {
                 const int64_t gi = a.index_base + i;
@@ -282,7 +282,7 @@ __global__ void __launch_bounds__(NHP_BLOCK, 5) k_sweep_sparse(const SparseArgs 
                     }
                 }
                 finish_parent<KIND, true>(a, tl, i, ti, ci, S, chosen, m0_hist, use_hist);
-                if (a.want_ll) { sum_log += log(S); sum_row += __ldg(a.rowsum + ci); }  // log-likelihood terms for free
+                if (a.want_ll) sum_log += log(S);  // log-likelihood terms for free
             }
         }
         __syncthreads();  // staging buffers, rows, list and val are reused by the next tile

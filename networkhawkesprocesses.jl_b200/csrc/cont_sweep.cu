@@ -141,11 +141,17 @@ __global__ void __launch_bounds__(NHP_BLOCK) k_sweep(const SweepArgs a, const in
     }
 }
 
-// fixed-order second-stage reduction of the per-CTA partials -> out[0], out[1]
-__global__ void k_reduce_partials(const double *__restrict__ partials, int64_t nblocks, double *__restrict__ out) {
+// fixed-order second-stage reduction of the per-CTA partials -> out[0], out[1].  When Mn is given the sweep did not
+// accumulate the compensator term per event and out[1] = sum_c Mn[c] * rowsum[c] (= sum_i rowsum[c_i] over the own events).
+__global__ void k_reduce_partials(const double *__restrict__ partials, int64_t nblocks, double *__restrict__ out,
+                                  const double *__restrict__ Mn, const double *__restrict__ rowsum, int K) {
     __shared__ double sx[1024], sy[1024];
     double x = 0.0, y = 0.0;
     for (int64_t b = threadIdx.x; b < nblocks; b += blockDim.x) { x += partials[2 * b]; y += partials[2 * b + 1]; }
+    if (Mn) {
+        y = 0.0;
+        for (int c = threadIdx.x; c < K; c += blockDim.x) y += Mn[c] * rowsum[c];
+    }
     sx[threadIdx.x] = x; sy[threadIdx.x] = y;
     __syncthreads();
     for (int s = blockDim.x / 2; s > 0; s >>= 1) {
@@ -464,7 +470,7 @@ int nhp_cont_run_loglik(nhp_ctx *ctx, nhp_events *ev, int recursive) {
     if (sp == NHP_OK) p.grid = sgrid;
     else if (ctx->kind == NHP_LOGITNORMAL) NHP_TRY((dispatch_sweep<NHP_LOGITNORMAL, MODE_LOGLIK>(ctx, p, a)));
     else NHP_TRY((dispatch_sweep<NHP_EXPONENTIAL, MODE_LOGLIK>(ctx, p, a)));
-    k_reduce_partials<<<1, 1024, 0, ctx->stream>>>(a.partials, p.grid, ctx->d_stats0);
+    k_reduce_partials<<<1, 1024, 0, ctx->stream>>>(a.partials, p.grid, ctx->d_stats0, ev->d_Mn, a.rowsum, (int)ctx->K);
     NHP_LAUNCHED(ctx);
     NHP_CUDA(ctx, cudaGetLastError());
     return NHP_OK;
@@ -568,7 +574,7 @@ extern "C" int nhp_cont_resample_parents(nhp_ctx *ctx, nhp_events *ev, uint64_t 
         else if (ctx->kind == NHP_LOGITNORMAL) NHP_TRY(dispatch_parents<NHP_LOGITNORMAL>(ctx, p, a));
         else NHP_TRY(dispatch_parents<NHP_EXPONENTIAL>(ctx, p, a));
         // the sweep also produced the log-likelihood terms (sum log lambda_i, sum rowsum): stats0[0..1]
-        k_reduce_partials<<<1, 1024, 0, ctx->stream>>>(a.partials, p.grid, ctx->d_stats0);
+        k_reduce_partials<<<1, 1024, 0, ctx->stream>>>(a.partials, p.grid, ctx->d_stats0, ev->d_Mn, a.rowsum, (int)ctx->K);
         NHP_LAUNCHED(ctx);
     } else NHP_CUDA(ctx, cudaMemsetAsync(ctx->d_stats0, 0, 2 * sizeof(double), ctx->stream));
     int flag = 0;
