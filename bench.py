@@ -358,7 +358,6 @@ def run_ours(args, rank, world, local_rank):
     bytes_alg = n * (BYTES_LOGLIK if dom == "loglik" else BYTES_PARENTS)
     gbs = bytes_alg / secs / 1e9
     sm_hz = (sampler.summary().get("sm_mhz") or 1965.0) * 1e6
-    lsu_peak = 148 * 32 * sm_hz / 2.0               # 2 shared-memory loads (node id, adjacency word) per probe, 32 lanes/clk/SM
     tf = flops / secs / 1e12
     traffic, issue_view = None, None
     prof = os.path.join(ROOT, "profiles", "r01_ncu_dominant_kernel.json")
@@ -373,14 +372,21 @@ def run_ours(args, rank, world, local_rank):
             issue_view = {"bound": "instruction issue", "achieved": ipe * n / secs, "peak": issue_peak, "unit": "warp-instructions/s",
                           "frac": ipe * n / secs / issue_peak, "warp_instructions_per_event": ipe,
                           "source": "instruction count per event from the committed ncu capture (profiles/r01_ncu_dominant_kernel.json), rate measured live"}
+    # L1/shared-memory data pipe: utilisation seen by ncu for the same launch, rescaled by the live duration (same work)
+    lsu_view = {"bound": "L1/shared-memory data pipe (LSU wavefronts)", "unit": "fraction of wavefront peak", "peak": 1.0, "achieved": None, "frac": None,
+                "algorithmic_probes_per_launch": probes, "probes_per_s": probes / secs}
+    if os.path.exists(prof) and pj.get("l1_lsu_wavefront_pct_of_peak") and n == pj.get("events"):
+        lsu_frac = pj["l1_lsu_wavefront_pct_of_peak"] / 100.0 * (pj["duration_ms_under_ncu"] * 1e-3) / secs
+        lsu_view.update({"achieved": lsu_frac, "frac": lsu_frac,
+                         "source": "l1tex__data_pipe_lsu_wavefronts %% of peak from profiles/r01_ncu_dominant_kernel.json x (ncu duration / live duration)"})
     roofline = {"kernel": "k_sweep_sparse<LOGITNORMAL, %s>" % ("LOGLIK" if dom == "loglik" else "PARENTS"),
                 "bound": "hbm", "achieved": gbs, "peak": hbm_peak, "unit": "GB/s", "frac": gbs / hbm_peak, "traffic": traffic,
                 "peak_source": hbm_src, "algorithmic_bytes_per_launch": bytes_alg,
-                "binding_resource": "instruction issue + shared-memory (LSU) pipe, not HBM: 12 B of event data carry ~64 adjacency probes and ~3 FP64 "
-                                    "impulse evaluations per event (ncu: profiles/r01_*.md); the HBM fraction is therefore small by construction",
+                "binding_resource": "L1/shared-memory data pipe (~70 % of its wavefront peak) and instruction issue (~55 % of the slots), not HBM: 12 B of "
+                                    "event data carry ~64 adjacency probes and ~3 FP64 impulse evaluations per event (ncu: profiles/r01_*.md); the HBM "
+                                    "fraction is therefore small by construction",
                 "issue_view": issue_view,
-                "lsu_view": {"bound": "shared-memory pipe", "achieved": probes / secs, "peak": lsu_peak, "unit": "probes/s", "frac": probes / secs / lsu_peak,
-                             "algorithmic_probes_per_launch": probes},
+                "lsu_view": lsu_view,
                 "fp64_view": {"bound": "fp64", "achieved": tf, "peak": peaks["fp64_fma_tflops"], "unit": "TFLOP/s", "frac": tf / peaks["fp64_fma_tflops"],
                               "algorithmic_flops_per_launch": flops, "active_pairs_per_launch": pairs,
                               "peak_source": "FP64 FMA peak measured in this run by nhp_bench_fp64 (MEASURED_PEAKS.json carries no FP64 figure)",
