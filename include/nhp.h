@@ -97,6 +97,18 @@ int nhp_cont_horizon(nhp_ctx *ctx, int64_t n_total, int recursive, double *horiz
  * (continuous.jl:241-276 / 407-442, incl. quirks Q3/Q6/Q7 of SURVEY.md section 9).  For a shard
  * the result is the shard's additive share (sum over ranks = ll). */
 int nhp_cont_loglik(nhp_ctx *ctx, nhp_events *ev, int recursive, double *ll);
+/* Extension for mle! (continuous.jl:144-198; the reference gives Optim a gradient-free objective, i.e.
+ * ~2P log-likelihood evaluations per finite-difference gradient): the log-likelihood of nhp_cont_loglik
+ * together with its analytic gradient, from two sweeps over the events.  Layouts as the parameters:
+ * dlambda0[K]; dW, dp1, dp2 [K*K] parent-major (X[parent + K*child]); Exponential: dp1 = d/d theta, dp2
+ * untouched; LogitNormal: dp1 = d/d mu, dp2 = d/d tau.  Entries with A[p,c] = 0 get the derivative of the
+ * compensator only.  Any output pointer may be NULL.  For a shard every output is the shard's additive share.
+ * _dev leaves the result on the device in the statistics buffers (dlambda0 -> M0 slot, dW -> Mnm, dp1 -> S1 of
+ * phase 0; dp2 -> phase 1 of nhp_cont_stats_dev) so the multi-GPU reduction is the two all-reduces of the Gibbs
+ * statistics; _read copies it out.  Invalidates the parent-sweep statistics. */
+int nhp_cont_loglik_grad(nhp_ctx *ctx, nhp_events *ev, int recursive, double *ll, double *dlambda0, double *dW, double *dp1, double *dp2);
+int nhp_cont_loglik_grad_dev(nhp_ctx *ctx, nhp_events *ev, int recursive);
+int nhp_cont_loglik_grad_read(nhp_ctx *ctx, nhp_events *ev, double *ll, double *dlambda0, double *dW, double *dp1, double *dp2);
 /* total_intensity at every (non-halo) event  continuous.jl:286-300 / 391-405; out[n - n_halo] */
 int nhp_cont_event_intensity(nhp_ctx *ctx, nhp_events *ev, double *out);
 /* intensity(process, data, times::Vector{Float64})  continuous.jl:76-96; out[nq*K], out[q + nq*k] */

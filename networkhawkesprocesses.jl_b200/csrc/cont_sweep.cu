@@ -497,25 +497,46 @@ extern "C" int nhp_cont_loglik(nhp_ctx *ctx, nhp_events *ev, int recursive, doub
     return NHP_OK;
 }
 
-extern "C" int nhp_cont_event_intensity(nhp_ctx *ctx, nhp_events *ev, double *out) {
-    NHP_CHECK(ctx, ctx != nullptr, NHP_ERR_INVALID, "ctx is NULL");
-    NHP_CHECK(ctx, out != nullptr, NHP_ERR_INVALID, "nhp_cont_event_intensity: out is NULL");
-    NHP_CUDA(ctx, cudaSetDevice(ctx->device));
+// total intensity at every own event into a device buffer (no host synchronisation); shared with the gradient sweep
+int nhp_cont_run_event_intensity(nhp_ctx *ctx, nhp_events *ev, int recursive, double *d_out) {
     SweepArgs a; LaunchPlan p;
-    NHP_TRY(fill_args(ctx, ev, 0, a, p));
-    int64_t own = ev->n - ev->n_halo;
-    if (own == 0) return NHP_OK;
-    void *scratch;
-    NHP_TRY(nhp_scratch(ctx, (size_t)own * sizeof(double), &scratch));
-    a.lam_out = (double *)scratch;
-    NHP_TRY(nhp_timer_begin(ctx));
+    NHP_TRY(fill_args(ctx, ev, recursive, a, p));
+    if (ev->n - ev->n_halo == 0) return NHP_OK;
+    a.lam_out = d_out;
     int sgrid = 0;
     int sp = try_special(ctx, ev, a, 1, &sgrid);
     if (sp < 0) return sp;
     if (sp == NHP_OK) {}
     else if (ctx->kind == NHP_LOGITNORMAL) NHP_TRY((dispatch_sweep<NHP_LOGITNORMAL, MODE_INTENSITY>(ctx, p, a)));
     else NHP_TRY((dispatch_sweep<NHP_EXPONENTIAL, MODE_INTENSITY>(ctx, p, a)));
+    return NHP_OK;
+}
+
+int nhp_cont_fill_args(nhp_ctx *ctx, nhp_events *ev, int recursive, SweepArgs &a) {
+    LaunchPlan p;
+    return fill_args(ctx, ev, recursive, a, p);
+}
+
+// (sum log lambda, compensator) -> stats0[0..1] from the per-CTA partials of any sweep
+int nhp_cont_reduce_partials(nhp_ctx *ctx, nhp_events *ev, const double *partials, int grid, const double *rowsum) {
+    k_reduce_partials<<<1, 1024, 0, ctx->stream>>>(partials, grid, ctx->d_stats0, ev->d_Mn, rowsum, (int)ctx->K);
+    NHP_LAUNCHED(ctx);
+    NHP_CUDA(ctx, cudaGetLastError());
+    return NHP_OK;
+}
+
+extern "C" int nhp_cont_event_intensity(nhp_ctx *ctx, nhp_events *ev, double *out) {
+    NHP_CHECK(ctx, ctx != nullptr, NHP_ERR_INVALID, "ctx is NULL");
+    NHP_CHECK(ctx, out != nullptr, NHP_ERR_INVALID, "nhp_cont_event_intensity: out is NULL");
+    NHP_CUDA(ctx, cudaSetDevice(ctx->device));
+    NHP_CHECK(ctx, ev != nullptr, NHP_ERR_INVALID, "events handle is NULL");
+    int64_t own = ev->n - ev->n_halo;
+    void *scratch = nullptr;
+    if (own > 0) NHP_TRY(nhp_scratch(ctx, (size_t)own * sizeof(double), &scratch));
+    NHP_TRY(nhp_timer_begin(ctx));
+    NHP_TRY(nhp_cont_run_event_intensity(ctx, ev, 0, (double *)scratch));
     NHP_TRY(nhp_timer_end(ctx));
+    if (own == 0) return NHP_OK;
     NHP_CUDA(ctx, cudaMemcpyAsync(out, scratch, (size_t)own * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
     NHP_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
     return NHP_OK;
@@ -524,6 +545,7 @@ extern "C" int nhp_cont_event_intensity(nhp_ctx *ctx, nhp_events *ev, double *ou
 // ---- parents + statistics -----------------------------------------------------------------
 static int zero_stats(nhp_ctx *ctx, nhp_events *ev) {
     StatsLayout sl{ctx->K};
+    ctx->grad_valid = false;  // the gradient planes share these buffers
     NHP_CUDA(ctx, cudaMemsetAsync(ctx->d_stats0 + sl.off_M0(), 0, (size_t)(sl.total() - sl.off_M0()) * sizeof(double), ctx->stream));
     NHP_CUDA(ctx, cudaMemcpyAsync(ctx->d_stats0 + sl.off_Mn(), ev->d_Mn, (size_t)ctx->K * sizeof(double), cudaMemcpyDeviceToDevice, ctx->stream));
     NHP_CUDA(ctx, cudaMemsetAsync(ctx->d_stats1, 0, (size_t)(ctx->K * ctx->K) * sizeof(double), ctx->stream));

@@ -112,6 +112,7 @@ struct nhp_ctx {
     int64_t K = 0;
     double dtmax = 0.0;
     bool has_A = false;
+    bool grad_valid = false;    // the statistics buffers hold a gradient (nhp_cont_loglik_grad_dev)
     double density = 1.0;       // fraction of non-zero effective weights
     double theta_min = 0.0, wt_max = 0.0, lambda0_min = 0.0; // Exponential cut-off horizon inputs
     double lambda0_sum = 0.0;

@@ -5,7 +5,7 @@ from .core import Context, ContinuousData, default_context  # noqa: F401
 from .continuous import (  # noqa: F401
     HomogeneousProcess, ExponentialImpulseResponse, LogitNormalImpulseResponse, DenseWeightModel, SparseWeightModel,
     DenseNetworkModel, BernoulliNetworkModel, ContinuousStandardHawkesProcess, ContinuousNetworkHawkesProcess,
-    loglikelihood, event_intensity, intensity, resample_parents, sweep_loglikelihood, sufficient_statistics, resample_adjacency_matrix_,
+    loglikelihood, loglikelihood_gradient, gradient_vector, event_intensity, intensity, resample_parents, sweep_loglikelihood, sufficient_statistics, resample_adjacency_matrix_,
     resample_, mcmc_, mle_, rand, MarkovChainMonteCarlo, MaximumLikelihood)
 from . import discrete  # noqa: F401,E402
 from .discrete import (  # noqa: F401,E402

@@ -34,6 +34,9 @@ PROTOTYPES = {
     "nhp_cont_params_set": (c_int, [c_void_p, c_int, c_int64, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_double]),
     "nhp_cont_horizon": (c_int, [c_void_p, c_int64, c_int, c_double_p]),
     "nhp_cont_loglik": (c_int, [c_void_p, c_void_p, c_int, c_double_p]),
+    "nhp_cont_loglik_grad": (c_int, [c_void_p, c_void_p, c_int, c_double_p, c_void_p, c_void_p, c_void_p, c_void_p]),
+    "nhp_cont_loglik_grad_dev": (c_int, [c_void_p, c_void_p, c_int]),
+    "nhp_cont_loglik_grad_read": (c_int, [c_void_p, c_void_p, c_double_p, c_void_p, c_void_p, c_void_p, c_void_p]),
     "nhp_cont_event_intensity": (c_int, [c_void_p, c_void_p, c_void_p]),
     "nhp_cont_intensity": (c_int, [c_void_p, c_void_p, c_void_p, c_int64, c_void_p]),
     "nhp_cont_resample_parents": (c_int, [c_void_p, c_void_p, c_uint64, c_uint64, c_void_p, c_void_p, c_void_p]),

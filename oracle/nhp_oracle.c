@@ -163,6 +163,61 @@ int orc_cont_loglik(const orc_cont_model *m, const double *events, const int64_t
     return 0;
 }
 
+/* EXTENSION (no counterpart in the reference, which hands Optim a gradient-free objective, continuous.jl:144-198):
+ * analytic gradient of orc_cont_loglik.  Plain O(n * window) double loop in the reference's window order; for the
+ * recursive Exponential path the history is every earlier event with time > 0.0 (quirks Q6/Q7) and the compensator
+ * ignores A (Q3).  Pinned by central finite differences of orc_cont_loglik in tests/test_oracle.py. */
+int orc_cont_loglik_grad(const orc_cont_model *m, const double *events, const int64_t *nodes, int64_t n, double duration, int recursive, double *llout,
+                         double *dl0, double *dW, double *dp1, double *dp2) {
+    int64_t K = m->K;
+    int rec = (m->kind == ORC_EXPONENTIAL && recursive);
+    int rc = orc_cont_loglik(m, events, nodes, n, duration, recursive, llout);
+    if (rc) return rc;
+    for (int64_t k = 0; k < K; k++) dl0[k] = -duration;
+    for (int64_t k = 0; k < K * K; k++) { dW[k] = 0.0; dp1[k] = 0.0; if (dp2) dp2[k] = 0.0; }
+    for (int64_t i = 0; i < n; i++) { /* compensator: -sum_i rowsum(c_i) */
+        int64_t p = nodes[i] - 1;
+        for (int64_t c = 0; c < K; c++) dW[p + K * c] -= (m->A && !rec) ? m->A[p + K * c] : 1.0;
+    }
+    for (int64_t i = 0; i < n; i++) {
+        int64_t c = nodes[i] - 1;
+        double ti = events[i];
+        /* pass 1: lambda_i */
+        double lam = m->lambda0[c];
+        int64_t jstop = i; /* exclusive lower end of the window, found in pass 1 */
+        for (int64_t j = i - 1; j >= 0; j--) {
+            if (rec) { if (!(events[j] > 0.0)) { jstop = j + 1; break; } }
+            else if (!(events[j] > ti - m->dtmax)) { jstop = j + 1; break; }
+            lam += orc_impulse_response(m, nodes[j], c + 1, ti - events[j]);
+            jstop = j;
+        }
+        double inv = 1.0 / lam;
+        dl0[c] += inv;
+        /* pass 2: per-pair terms */
+        for (int64_t j = i - 1; j >= jstop; j--) {
+            int64_t p = nodes[j] - 1, k = p + K * c;
+            double dt = ti - events[j];
+            double a = m->A ? m->A[k] : 1.0, w = m->W[k];
+            if (m->kind == ORC_EXPONENTIAL) {
+                double th = m->p1[k];
+                double ex = dt < 0.0 ? 0.0 : exp(-th * dt);
+                dW[k] += a * th * ex * inv;
+                dp1[k] += a * w * ex * (1.0 - th * dt) * inv;
+            } else {
+                double x = dt / m->dtmax;
+                if (!(0.0 < x && x < 1.0)) continue;
+                double mu = m->p1[k], tau = m->p2[k];
+                double pdf = orc_logitnormal_pdf(mu, tau, x);
+                double z = log(x / (1.0 - x));
+                dW[k] += a * pdf * inv;
+                dp1[k] += a * w * pdf * tau * (z - mu) * inv;
+                if (dp2) dp2[k] += a * w * pdf * (0.5 / tau - 0.5 * (z - mu) * (z - mu)) * inv;
+            }
+        }
+    }
+    return 0;
+}
+
 /* continuous.jl:76-96: strict window  time - dtmax < events < time, all K children. */
 int orc_cont_intensity(const orc_cont_model *m, const double *events, const int64_t *nodes, int64_t n, const double *times, int64_t nq, double *out) {
     int64_t K = m->K;

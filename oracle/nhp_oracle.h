@@ -51,6 +51,9 @@ double orc_impulse_response(const orc_cont_model *m, int64_t parentnode, int64_t
 double orc_total_intensity(const orc_cont_model *m, const double *events, const int64_t *nodes, int64_t index1, double time, int64_t node); /* continuous.jl:286-300, 391-405 */
 int orc_cont_event_intensity(const orc_cont_model *m, const double *events, const int64_t *nodes, int64_t n, double *out);
 int orc_cont_loglik(const orc_cont_model *m, const double *events, const int64_t *nodes, int64_t n, double duration, int recursive, double *ll); /* continuous.jl:210-239, 360-389 */
+/* extension: analytic gradient of orc_cont_loglik (pinned by finite differences of it) */
+int orc_cont_loglik_grad(const orc_cont_model *m, const double *events, const int64_t *nodes, int64_t n, double duration, int recursive, double *ll,
+                         double *dl0, double *dW, double *dp1, double *dp2);
 int orc_cont_recursive_loglik(const orc_cont_model *m, const double *events, const int64_t *nodes, int64_t n, double duration, double *ll); /* continuous.jl:241-276, 407-442 */
 int orc_cont_intensity(const orc_cont_model *m, const double *events, const int64_t *nodes, int64_t n, const double *times, int64_t nq, double *out /* [nq*K] col-major */); /* continuous.jl:76-96 */
 

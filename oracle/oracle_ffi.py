@@ -73,6 +73,18 @@ class Cont:
         assert rc == 0
         return ll.value
 
+    def loglik_grad(self, events, nodes, duration, recursive=True):
+        """(ll, dlambda0[K], dW[K,K], dp1[K,K], dp2[K,K]) -- extension, see orc_cont_loglik_grad"""
+        ev, nd = self._ev(events, nodes)
+        K = self.K
+        ll = c_double()
+        dl0, dW, d1, d2 = np.zeros(K), np.zeros(K * K), np.zeros(K * K), np.zeros(K * K)
+        rc = lib().orc_cont_loglik_grad(ctypes.byref(self.m), _p(ev), _p(nd), c_int64(ev.size), c_double(duration), int(recursive), ctypes.byref(ll),
+                                        _p(dl0), _p(dW), _p(d1), _p(d2))
+        assert rc == 0
+        f = lambda v: v.reshape(K, K).T.copy()  # [parent, child]
+        return ll.value, dl0, f(dW), f(d1), f(d2)
+
     def event_intensity(self, events, nodes):
         ev, nd = self._ev(events, nodes)
         out = np.empty(ev.size)

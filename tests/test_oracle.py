@@ -122,3 +122,40 @@ def test_philox_reference_vector():
     u = synth.philox_uniform(0, np.array([0], dtype=np.uint64), 0)
     x = ((0x6627E8D5 << 32) | 0xE169C58D) >> 11
     assert u[0] == x * 2.0 ** -53
+
+
+# ---------------------------------------------------------------------------- extension: analytic gradient
+def _fd_grad(make, x0, f, h=1e-6):
+    g = np.zeros_like(x0)
+    for k in range(x0.size):
+        xp, xm = x0.copy(), x0.copy()
+        xp[k] += h
+        xm[k] -= h
+        g[k] = (f(make(xp)) - f(make(xm))) / (2 * h)
+    return g
+
+
+@pytest.mark.parametrize("kind,network,recursive", [(0, False, True), (0, False, False), (0, True, True), (0, True, False), (1, False, False), (1, True, False)])
+def test_gradient_oracle_matches_finite_differences(kind, network, recursive):
+    """The gradient has no reference counterpart: the oracle's analytic gradient is pinned by central differences
+    of the oracle's own log-likelihood (incl. the compensator quirks Q3 of the recursive network path)."""
+    rng = np.random.default_rng(5 + kind + 2 * network)
+    K, n, T = 3, 70, 20.0
+    dtmax = 1.5 if kind == 1 else (np.inf if recursive else 2.0)
+    ev = np.sort(rng.uniform(0.01, T, n))
+    nd = rng.integers(1, K + 1, n)
+    A = (rng.random((K, K)) < 0.6).astype(np.float64) if network else None
+    lam0, W = rng.uniform(0.5, 1.5, K), rng.uniform(0.05, 0.4, (K, K))
+    p1 = rng.uniform(0.5, 2.0, (K, K)) if kind == 0 else rng.uniform(-1, 1, (K, K))
+    p2 = None if kind == 0 else rng.uniform(0.5, 2.0, (K, K))
+    x0 = np.concatenate([lam0, W.ravel(), p1.ravel()] + ([] if p2 is None else [p2.ravel()]))
+
+    def make(x):
+        q2 = None if p2 is None else x[K + 2 * K * K:].reshape(K, K)
+        return orc.Cont(kind, x[:K], x[K:K + K * K].reshape(K, K), x[K + K * K:K + 2 * K * K].reshape(K, K), q2, A=A, dtmax=dtmax)
+
+    ll, g0, gW, g1, g2 = make(x0).loglik_grad(ev, nd, T, recursive=recursive)
+    assert ll == make(x0).loglik(ev, nd, T, recursive=recursive)
+    ana = np.concatenate([g0, gW.ravel(), g1.ravel()] + ([] if p2 is None else [g2.ravel()]))
+    num = _fd_grad(make, x0, lambda m: m.loglik(ev, nd, T, recursive=recursive))
+    np.testing.assert_allclose(ana, num, rtol=2e-6, atol=2e-6)
