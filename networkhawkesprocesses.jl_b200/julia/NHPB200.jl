@@ -81,6 +81,20 @@ function loglikelihood(process::ContinuousHawkesProcess, data; recursive=true)
     return ll[]
 end
 
+# ---- extension: objective + analytic gradient for mle! (Optim.only_fg!); layout of params(process), continuous.jl:116-119
+function loglikelihood_gradient(process::ContinuousStandardHawkesProcess, data; recursive=true)
+    ev = device_events(process, data)
+    push_params!(process)
+    K = ndims(process)
+    ll = Ref{Float64}(0.0)
+    dλ = Vector{Float64}(undef, K); dW = Matrix{Float64}(undef, K, K); d1 = Matrix{Float64}(undef, K, K); d2 = Matrix{Float64}(undef, K, K)
+    check(ccall((:nhp_cont_loglik_grad, LIB[]), Cint,
+        (Ptr{Cvoid}, Ptr{Cvoid}, Cint, Ref{Float64}, Ptr{Float64}, Ptr{Float64}, Ptr{Float64}, Ptr{Float64}),
+        CTX[], ev.h, recursive ? 1 : 0, ll, dλ, dW, d1, d2))
+    impulse_grad = process.impulses isa ExponentialImpulseResponse ? vec(d1) : [vec(d1); vec(d2)]
+    return ll[], [dλ; impulse_grad; vec(dW)]
+end
+
 # ---- continuous.jl:76 / :84 -----------------------------------------------------------------------------
 function intensity(process::ContinuousHawkesProcess, data, times::Vector{Float64})
     ev = device_events(process, data)

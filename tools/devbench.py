@@ -123,6 +123,29 @@ if __name__ == "__main__":
             t0 = time.perf_counter(); ll = nhp.loglikelihood(proc, d, recursive=True)
             print(f"cfg5-like exp K=5000 n={n:.1e}: loglik kernel {ctx.last_kernel_ms:.2f} ms = {n/ctx.last_kernel_ms/1e3:.1f} Mev/s, call {1e3*(time.perf_counter()-t0):.0f} ms, ll={ll:.6e}", flush=True)
         sys.exit(0)
+    if which == "grad":  # grad kind K n rate [density]
+        kind, K, n, rate = sys.argv[2], int(sys.argv[3]), int(float(sys.argv[4])), float(sys.argv[5])
+        dens = float(sys.argv[6]) if len(sys.argv) > 6 and sys.argv[6] != "none" else None
+        t, nodes, T = synth.poisson_stream(n, K, rate, 1)
+        if kind == "exp":
+            lam0, W, theta, A = synth.exp_params(K, 2, density=dens)
+            imp = nhp.ExponentialImpulseResponse(theta)
+        else:
+            lam0, W, mu, tau, A = synth.ln_params(K, 2, density=dens)
+            imp = nhp.LogitNormalImpulseResponse(mu, tau, 1.0)
+        if A is None:
+            proc = nhp.ContinuousStandardHawkesProcess(nhp.HomogeneousProcess(lam0), imp, nhp.DenseWeightModel(W))
+        else:
+            proc = nhp.ContinuousNetworkHawkesProcess(nhp.HomogeneousProcess(lam0), imp, nhp.DenseWeightModel(W), A, nhp.BernoulliNetworkModel(dens, K))
+        ctx = proc._ctx()
+        d = proc.upload((t, nodes, T))
+        proc._push(ctx)
+        import ctypes
+        for rep in range(3):
+            ll = nhp.loglikelihood(proc, d); k_ll = ctx.last_kernel_ms
+            ctx.check(ctx.lib.nhp_cont_loglik_grad_dev(ctx.h, d.h, 1)); ctx.lib.nhp_cont_loglik_grad_read(ctx.h, d.h, None, None, None, None, None); k_g = ctx.last_kernel_ms
+            print(f"grad {kind} K={K} n={n:.1e} dens={dens}: loglik {k_ll:.2f} ms, loglik+gradient {k_g:.2f} ms = {n/k_g/1e3:.1f} Mev/s (x{k_g/k_ll:.1f} of a loglik; finite differences: x{2*(K+(2 if kind=='exp' else 3)*K*K)} )", flush=True)
+        sys.exit(0)
     if which == "cfg1":  # README example: K=2 exponential, T=1000: per-call latency of loglikelihood (params pushed each call, as mle! does)
         sys.path.insert(0, os.path.join(ROOT, "oracle"))
         import oracle_ffi as orc
