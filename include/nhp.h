@@ -152,6 +152,19 @@ int nhp_cont_resample_adjacency(nhp_ctx *ctx, nhp_events *ev, const double *rho,
 int nhp_cont_resample_adjacency_cols(nhp_ctx *ctx, nhp_events *ev, const double *rho, uint64_t seed, uint64_t counter,
                                      const double *u, double *A_inout, int64_t col_begin, int64_t col_stride);
 
+/* Device-side conjugate draws of one Gibbs sweep (the `resample!` of baseline, weights and impulses:
+ * baselines.jl:72-77, weights.jl:59-64, impulses.jl:68-73 / 204-214) from the statistics of the last parent sweep,
+ * in place: the context's parameters are replaced and every derived table is rebuilt, so a chain can run without the
+ * K^2 statistics or parameters crossing PCIe.  hyper: [alpha0, beta0 (baseline), kappa, nu (weights), then
+ * Exponential: alpha, beta | LogitNormal: mumu, kappamu, alpha0, beta0]; `duration` is T of the whole data set.
+ * flags bit 0: run the LogitNormal second pass (S2) first (single GPU); without it the caller has completed the
+ * statistics (multi-GPU: all-reduce phase 0, nhp_cont_suffstats_second_pass, all-reduce phase 1) and every rank,
+ * holding the same statistics, draws the same parameters (Philox keyed by seed, element, counter).
+ * Parity with the reference is distributional. */
+int nhp_cont_resample_params(nhp_ctx *ctx, nhp_events *ev, uint64_t seed, uint64_t counter, double duration, const double *hyper, int n_hyper, int flags);
+/* Current parameters in the layouts of nhp_cont_params_set; any pointer may be NULL. */
+int nhp_cont_params_get(nhp_ctx *ctx, double *lambda0, double *W, double *A, double *p1, double *p2);
+
 /* ---- multi-GPU plumbing (one process per GPU; the host allreduces with NCCL) -------------
  * Device pointer + length (in doubles) of the contiguous reduction buffer
  *   [ ll_logsum, ll_rowsum, M0[K], Mn[K], Mnm[K*K], S1[K*K] ]   (phase 0)

@@ -12,6 +12,7 @@
 // histogram), (B) then runs the K sequential Bernoulli steps, each a block-wide reduction over one
 // bucket.  Same conditional distribution, O(N w) work per sweep instead of O(K^2 N).
 #include "cont_sweep.cuh"
+int nhp_cont_params_refresh(nhp_ctx *ctx);  // cont_conjugate.cu
 #include <cub/cub.cuh>
 
 struct AdjArgs {
@@ -297,18 +298,16 @@ extern "C" int nhp_cont_resample_adjacency_cols(nhp_ctx *ctx, nhp_events *ev, co
     if (flag & 32) return fin(nhp_fail(ctx, NHP_ERR_CUDA, "adjacency sampler: scratch overflow (internal error)"));
     if (flag & 64) return fin(nhp_fail(ctx, NHP_ERR_NUMERIC, "adjacency sampler: NaN log-likelihood difference"));
     ADJ_CUDA(cudaMemcpyAsync(A_inout, d_A, KK * sizeof(double), cudaMemcpyDeviceToHost, s));
+    // the new adjacency becomes the context's A (device to device; the masked tables are rebuilt below)
+    if (ctx->has_A) ADJ_CUDA(cudaMemcpyAsync(ctx->d_A, d_A, KK * sizeof(double), cudaMemcpyDeviceToDevice, s));
     ADJ_CUDA(cudaStreamSynchronize(s));
 #undef ADJ_CUDA
     fin(NHP_OK);
-    // the new adjacency becomes the context's A: rebuild the masked tables
-    std::vector<double> l0(K);
-    NHP_CUDA(ctx, cudaMemcpy(l0.data(), ctx->d_lambda0, K * sizeof(double), cudaMemcpyDeviceToHost));
     if (ctx->has_A) {
-        std::vector<double> W(KK), p1(KK), p2(KK);
-        NHP_CUDA(ctx, cudaMemcpy(W.data(), ctx->d_W, KK * sizeof(double), cudaMemcpyDeviceToHost));
-        NHP_CUDA(ctx, cudaMemcpy(p1.data(), ctx->d_p1, KK * sizeof(double), cudaMemcpyDeviceToHost));
-        if (ctx->kind == NHP_LOGITNORMAL) NHP_CUDA(ctx, cudaMemcpy(p2.data(), ctx->d_p2, KK * sizeof(double), cudaMemcpyDeviceToHost));
-        return nhp_cont_params_set(ctx, ctx->kind, K, l0.data(), W.data(), A_inout, p1.data(), ctx->kind == NHP_LOGITNORMAL ? p2.data() : nullptr, ctx->dtmax);
+        ctx->cont_set = false;
+        ctx->sweep_ll_valid = false;
+        NHP_TRY(nhp_cont_params_refresh(ctx));
+        ctx->cont_set = true;
     }
     return NHP_OK;
 }

@@ -1,0 +1,197 @@
+// cont_conjugate.cu -- the conjugate parameter draws of one Gibbs sweep on the device, so that `resample!`
+// (continuous.jl:202-208 / 350-358) can stay on the GPU between sweeps: the K^2 sufficient statistics never travel to
+// the host and the parameter tables are rebuilt in place.  SURVEY.md section 8f ("next": device-side conjugate draws).
+//   baseline  lambda0[k] ~ Gamma(alpha0 + M0[k], 1/(beta0 + T))                                     baselines.jl:72-77
+//   weights   W[p,c]     ~ Gamma(kappa + Mnm[p,c], 1/(nu + Mn[p]))  (also where A == 0, quirk Q14)   weights.jl:59-64
+//   Exponential   theta  ~ Gamma(alpha + Mnm, 1/(beta + Mnm Xnm)),  Mnm Xnm = S1                      impulses.jl:68-73
+//   LogitNormal   tau    ~ Gamma(alpha0 + Mnm/2, 1/b),  b = S2/2 + Mnm kmu/(Mnm + kmu) (Xnm - mumu)^2/2, NaN -> beta0 (Q5)
+//                 mu     ~ Normal((kmu mumu + Mnm Xnm)/(kmu + Mnm) [NaN -> mumu], 1/sqrt((kmu + Mnm) tau))   impulses.jl:204-214
+// Random numbers: Philox4x32-10 with key seed ^ "CONJUGAT", counter words (element, draw block | parameter id, sweep
+// counter): every rank of a multi-GPU job that holds the same (all-reduced) statistics draws the same parameters.
+// Gamma: Marsaglia & Tsang (2000) with the shape < 1 boost; Normal: Box-Muller.  Parity with the reference is
+// distributional (Julia's own samplers are not reproducible from uniforms): tests check the moments.
+#include "nhp_internal.cuh"
+#include <cmath>
+#include <vector>
+
+struct PhiloxStream {
+    uint32_t k0, k1, c0, c1, c2, c3;
+    uint32_t buf[4];
+    int have;
+    __device__ PhiloxStream(uint64_t seed, uint32_t element, uint32_t param, uint64_t counter) {
+        const uint64_t key = seed ^ 0x434F4E4A55474154ull;
+        k0 = (uint32_t)key; k1 = (uint32_t)(key >> 32);
+        c0 = element; c1 = param << 24; c2 = (uint32_t)counter; c3 = (uint32_t)(counter >> 32);
+        have = 0;
+    }
+    __device__ double uniform() {  // (0, 1): 53 bits, never exactly 0
+        if (have == 0) { philox4x32_10(c0, c1, c2, c3, k0, k1, buf); c1++; have = 2; }
+        have--;
+        const uint64_t x = (((uint64_t)buf[2 * have] << 32) | (uint64_t)buf[2 * have + 1]) >> 11;
+        return ((double)x + 0.5) * 1.1102230246251565e-16;
+    }
+    __device__ double normal() {
+        const double u1 = uniform(), u2 = uniform();
+        return sqrt(-2.0 * log(u1)) * cospi(2.0 * u2);
+    }
+    __device__ double gamma(double shape, double scale) {
+        if (!(shape > 0.0) || !(scale > 0.0)) return nan("");
+        double boost = 1.0;
+        if (shape < 1.0) { boost = pow(uniform(), 1.0 / shape); shape += 1.0; }
+        const double d = shape - 1.0 / 3.0, c = 1.0 / sqrt(9.0 * d);
+        for (int it = 0; it < 1000; it++) {
+            const double x = normal();
+            double v = 1.0 + c * x;
+            if (v <= 0.0) continue;
+            v = v * v * v;
+            const double u = uniform();
+            const double x2 = x * x;
+            if (u < 1.0 - 0.0331 * x2 * x2 || log(u) < 0.5 * x2 + d * (1.0 - v + log(v))) return fmax(d * v * boost * scale, 1e-300);
+        }
+        return fmax(d * boost * scale, 1e-300);  // unreachable in practice (acceptance > 95 % per trial)
+    }
+};
+
+struct ConjArgs {
+    int K, kind;
+    uint64_t seed, counter;
+    double T;
+    double a0l, b0l, kappa, nu;       // baseline, weights
+    double h0, h1, h2, h3;            // EX: alpha, beta;  LN: mumu, kappamu, alpha0, beta0
+    const double *M0, *Mn, *Mnm, *S1, *S2;
+    double *lambda0, *W, *p1, *p2;
+};
+
+__global__ void k_conjugate(const ConjArgs a) {
+    const int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const int64_t KK = (int64_t)a.K * a.K;
+    if (e < a.K) {
+        PhiloxStream r(a.seed, (uint32_t)e, 0u, a.counter);
+        a.lambda0[e] = r.gamma(a.a0l + a.M0[e], 1.0 / (a.b0l + a.T));
+    }
+    if (e >= KK) return;
+    const int p = (int)(e % a.K);
+    const double m = a.Mnm[e];
+    {
+        PhiloxStream r(a.seed, (uint32_t)e, 1u, a.counter);
+        a.W[e] = r.gamma(a.kappa + m, 1.0 / (a.nu + a.Mn[p]));
+    }
+    PhiloxStream r(a.seed, (uint32_t)e, 2u, a.counter);
+    if (a.kind == NHP_EXPONENTIAL) {
+        a.p1[e] = r.gamma(a.h0 + m, 1.0 / (a.h1 + a.S1[e]));  // Mnm * Xnm = S1 (0 where Mnm == 0)
+    } else {
+        const double mumu = a.h0, kmu = a.h1, alpha0 = a.h2, beta0 = a.h3;
+        const double X = a.S1[e] / m;  // NaN where Mnm == 0, as in the reference
+        double b = 0.5 * a.S2[e] + m * kmu / (m + kmu) * (X - mumu) * (X - mumu) * 0.5;
+        if (isnan(b)) b = beta0;
+        const double tau = r.gamma(alpha0 + 0.5 * m, 1.0 / b);
+        double mun = (kmu * mumu + m * X) / (kmu + m);
+        if (isnan(mun)) mun = mumu;
+        a.p2[e] = tau;
+        a.p1[e] = mun + r.normal() / sqrt((kmu + m) * tau);
+    }
+}
+
+// scalars the host keeps about the parameters: [lambda0 min, lambda0 sum, theta min, max |w theta|, #non-zero effective weights]
+__global__ void k_param_scan(int K, int kind, const double *__restrict__ lambda0, const double *__restrict__ W, const double *__restrict__ A,
+                             const double *__restrict__ p1, double *__restrict__ out) {
+    __shared__ double s_min[256], s_sum[256], s_tmin[256], s_wmax[256], s_nnz[256];
+    double l0min = INFINITY, l0sum = 0.0, tmin = INFINITY, wmax = 0.0, nnz = 0.0;
+    const int64_t KK = (int64_t)K * K;
+    for (int64_t e = threadIdx.x; e < KK; e += blockDim.x) {
+        if (e < K) { l0min = fmin(l0min, lambda0[e]); l0sum += lambda0[e]; }
+        const double w = A ? A[e] * W[e] : W[e];
+        if (w != 0.0) {
+            nnz += 1.0;
+            if (kind == NHP_EXPONENTIAL) { tmin = fmin(tmin, p1[e]); wmax = fmax(wmax, fabs(w * p1[e])); }
+        }
+    }
+    s_min[threadIdx.x] = l0min; s_sum[threadIdx.x] = l0sum; s_tmin[threadIdx.x] = tmin; s_wmax[threadIdx.x] = wmax; s_nnz[threadIdx.x] = nnz;
+    __syncthreads();
+    for (int s = blockDim.x / 2; s > 0; s >>= 1) {
+        if ((int)threadIdx.x < s) {
+            s_min[threadIdx.x] = fmin(s_min[threadIdx.x], s_min[threadIdx.x + s]);
+            s_sum[threadIdx.x] += s_sum[threadIdx.x + s];
+            s_tmin[threadIdx.x] = fmin(s_tmin[threadIdx.x], s_tmin[threadIdx.x + s]);
+            s_wmax[threadIdx.x] = fmax(s_wmax[threadIdx.x], s_wmax[threadIdx.x + s]);
+            s_nnz[threadIdx.x] += s_nnz[threadIdx.x + s];
+        }
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) { out[0] = s_min[0]; out[1] = s_sum[0]; out[2] = s_tmin[0]; out[3] = s_wmax[0]; out[4] = s_nnz[0]; }
+}
+
+int nhp_cont_derive_tables(nhp_ctx *ctx);  // nhp_context.cu: masked tables, bit rows, row sums from the device-resident raw parameters
+
+// refresh the host-side scalars from the device-resident parameters and rebuild the derived tables
+int nhp_cont_params_refresh(nhp_ctx *ctx) {
+    cudaStream_t s = ctx->stream;
+    const int64_t K = ctx->K;
+    void *scratch;
+    NHP_TRY(nhp_partials(ctx, 8, (double **)&scratch));
+    k_param_scan<<<1, 256, 0, s>>>((int)K, ctx->kind, ctx->d_lambda0, ctx->d_W, ctx->has_A ? ctx->d_A : nullptr, ctx->d_p1, (double *)scratch);
+    NHP_LAUNCHED(ctx);
+    double h[5];
+    NHP_CUDA(ctx, cudaMemcpyAsync(h, scratch, sizeof(h), cudaMemcpyDeviceToHost, s));
+    NHP_TRY(nhp_cont_derive_tables(ctx));
+    NHP_CUDA(ctx, cudaStreamSynchronize(s));
+    ctx->lambda0_min = h[0]; ctx->lambda0_sum = h[1]; ctx->theta_min = h[2]; ctx->wt_max = h[3];
+    ctx->density = h[4] / (double)(K * K);
+    return NHP_OK;
+}
+
+extern "C" int nhp_cont_resample_params(nhp_ctx *ctx, nhp_events *ev, uint64_t seed, uint64_t counter, double duration, const double *hyper, int n_hyper,
+                                        int flags) {
+    NHP_CHECK(ctx, ctx != nullptr, NHP_ERR_INVALID, "ctx is NULL");
+    NHP_CHECK(ctx, ctx->cont_set, NHP_ERR_STATE, "continuous parameters not set (call nhp_cont_params_set)");
+    NHP_CHECK(ctx, ctx->parents_valid, NHP_ERR_STATE, "nhp_cont_resample_params: no parent assignment (call nhp_cont_resample_parents first)");
+    const int need = ctx->kind == NHP_LOGITNORMAL ? 8 : 6;
+    NHP_CHECK(ctx, hyper != nullptr && n_hyper == need, NHP_ERR_INVALID, "nhp_cont_resample_params: expected %d hyper-parameters, got %d", need, n_hyper);
+    for (int i = 0; i < n_hyper; i++) NHP_CHECK(ctx, std::isfinite(hyper[i]), NHP_ERR_INVALID, "nhp_cont_resample_params: hyper-parameter %d is not finite", i);
+    NHP_CHECK(ctx, duration > 0.0, NHP_ERR_INVALID, "nhp_cont_resample_params: duration must be positive");
+    NHP_CUDA(ctx, cudaSetDevice(ctx->device));
+    if (flags & 1) {
+        NHP_CHECK(ctx, ev != nullptr, NHP_ERR_INVALID, "nhp_cont_resample_params: events handle is NULL");
+        NHP_TRY(nhp_cont_suffstats_second_pass(ctx, ev));
+    }
+    const int64_t K = ctx->K, KK = K * K;
+    const StatsLayout sl{K};
+    ConjArgs a;
+    a.K = (int)K; a.kind = ctx->kind; a.seed = seed; a.counter = counter; a.T = duration;
+    a.a0l = hyper[0]; a.b0l = hyper[1]; a.kappa = hyper[2]; a.nu = hyper[3];
+    a.h0 = hyper[4]; a.h1 = hyper[5]; a.h2 = need == 8 ? hyper[6] : 0.0; a.h3 = need == 8 ? hyper[7] : 0.0;
+    a.M0 = ctx->d_stats0 + sl.off_M0(); a.Mn = ctx->d_stats0 + sl.off_Mn(); a.Mnm = ctx->d_stats0 + sl.off_Mnm(); a.S1 = ctx->d_stats0 + sl.off_S1();
+    a.S2 = ctx->d_stats1;
+    a.lambda0 = ctx->d_lambda0; a.W = ctx->d_W; a.p1 = ctx->d_p1; a.p2 = ctx->d_p2;
+    NHP_TRY(nhp_timer_begin(ctx));
+    k_conjugate<<<(unsigned)((KK + 127) / 128), 128, 0, ctx->stream>>>(a);
+    NHP_LAUNCHED(ctx);
+    NHP_CUDA(ctx, cudaGetLastError());
+    ctx->cont_set = false;
+    ctx->sweep_ll_valid = false;
+    NHP_TRY(nhp_cont_params_refresh(ctx));
+    NHP_TRY(nhp_timer_end(ctx));
+    ctx->cont_set = true;
+    return NHP_OK;
+}
+
+extern "C" int nhp_cont_params_get(nhp_ctx *ctx, double *lambda0, double *W, double *A, double *p1, double *p2) {
+    NHP_CHECK(ctx, ctx != nullptr, NHP_ERR_INVALID, "ctx is NULL");
+    NHP_CHECK(ctx, ctx->cont_set, NHP_ERR_STATE, "continuous parameters not set");
+    NHP_CUDA(ctx, cudaSetDevice(ctx->device));
+    const int64_t K = ctx->K, KK = K * K;
+    cudaStream_t s = ctx->stream;
+    if (lambda0) NHP_CUDA(ctx, cudaMemcpyAsync(lambda0, ctx->d_lambda0, (size_t)K * sizeof(double), cudaMemcpyDeviceToHost, s));
+    if (W) NHP_CUDA(ctx, cudaMemcpyAsync(W, ctx->d_W, (size_t)KK * sizeof(double), cudaMemcpyDeviceToHost, s));
+    if (A) {
+        NHP_CHECK(ctx, ctx->has_A, NHP_ERR_STATE, "nhp_cont_params_get: the process has no adjacency matrix");
+        NHP_CUDA(ctx, cudaMemcpyAsync(A, ctx->d_A, (size_t)KK * sizeof(double), cudaMemcpyDeviceToHost, s));
+    }
+    if (p1) NHP_CUDA(ctx, cudaMemcpyAsync(p1, ctx->d_p1, (size_t)KK * sizeof(double), cudaMemcpyDeviceToHost, s));
+    if (p2) {
+        NHP_CHECK(ctx, ctx->kind == NHP_LOGITNORMAL, NHP_ERR_STATE, "nhp_cont_params_get: the Exponential impulse has no second parameter");
+        NHP_CUDA(ctx, cudaMemcpyAsync(p2, ctx->d_p2, (size_t)KK * sizeof(double), cudaMemcpyDeviceToHost, s));
+    }
+    NHP_CUDA(ctx, cudaStreamSynchronize(s));
+    return NHP_OK;
+}

@@ -298,6 +298,24 @@ __global__ void k_rowsums(int K, const double *__restrict__ W, const double *__r
     rsw[p] = sw;
 }
 
+// masked parameter table, adjacency bit rows and row sums from the device-resident raw parameters (stream-ordered)
+int nhp_cont_derive_tables(nhp_ctx *ctx) {
+    const int64_t K = ctx->K, KK = K * K;
+    cudaStream_t s = ctx->stream;
+    NHP_CUDA(ctx, cudaMemsetAsync(ctx->d_abits, 0, (size_t)(K * ctx->abits_words) * sizeof(uint32_t), s));
+    unsigned blocks = (unsigned)((KK + 255) / 256);
+    const double *dA = ctx->has_A ? ctx->d_A : nullptr;
+    if (ctx->kind == NHP_LOGITNORMAL)
+        k_build_table_ln<<<blocks, 256, 0, s>>>((int)K, ctx->d_W, dA, ctx->d_p1, ctx->d_p2, ctx->dtmax, (EntryLN *)ctx->d_table, ctx->d_abits, (int)ctx->abits_words);
+    else
+        k_build_table_ex<<<blocks, 256, 0, s>>>((int)K, ctx->d_W, dA, ctx->d_p1, (EntryEX *)ctx->d_table, ctx->d_abits, (int)ctx->abits_words);
+    NHP_LAUNCHED(ctx);
+    k_rowsums<<<(unsigned)((K + 127) / 128), 128, 0, s>>>((int)K, ctx->d_W, dA, ctx->d_rowsum, ctx->d_rowsum_w);
+    NHP_LAUNCHED(ctx);
+    NHP_CUDA(ctx, cudaGetLastError());
+    return NHP_OK;
+}
+
 extern "C" int nhp_cont_params_set(nhp_ctx *ctx, int kind, int64_t K, const double *lambda0, const double *W, const double *A,
                                    const double *p1, const double *p2, double dtmax) {
     NHP_CHECK(ctx, ctx != nullptr, NHP_ERR_INVALID, "nhp_cont_params_set: ctx is NULL");
@@ -358,17 +376,7 @@ extern "C" int nhp_cont_params_set(nhp_ctx *ctx, int kind, int64_t K, const doub
     if (A) NHP_CUDA(ctx, cudaMemcpyAsync(ctx->d_A, A, (size_t)KK * sizeof(double), cudaMemcpyHostToDevice, s));
     NHP_CUDA(ctx, cudaMemcpyAsync(ctx->d_p1, p1, (size_t)KK * sizeof(double), cudaMemcpyHostToDevice, s));
     if (p2) NHP_CUDA(ctx, cudaMemcpyAsync(ctx->d_p2, p2, (size_t)KK * sizeof(double), cudaMemcpyHostToDevice, s));
-    NHP_CUDA(ctx, cudaMemsetAsync(ctx->d_abits, 0, (size_t)(K * ctx->abits_words) * sizeof(uint32_t), s));
-    unsigned blocks = (unsigned)((KK + 255) / 256);
-    const double *dA = A ? ctx->d_A : nullptr;
-    if (kind == NHP_LOGITNORMAL)
-        k_build_table_ln<<<blocks, 256, 0, s>>>((int)K, ctx->d_W, dA, ctx->d_p1, ctx->d_p2, dtmax, (EntryLN *)ctx->d_table, ctx->d_abits, (int)ctx->abits_words);
-    else
-        k_build_table_ex<<<blocks, 256, 0, s>>>((int)K, ctx->d_W, dA, ctx->d_p1, (EntryEX *)ctx->d_table, ctx->d_abits, (int)ctx->abits_words);
-    NHP_LAUNCHED(ctx);
-    k_rowsums<<<(unsigned)((K + 127) / 128), 128, 0, s>>>((int)K, ctx->d_W, dA, ctx->d_rowsum, ctx->d_rowsum_w);
-    NHP_LAUNCHED(ctx);
-    NHP_CUDA(ctx, cudaGetLastError());
+    NHP_TRY(nhp_cont_derive_tables(ctx));
     NHP_CUDA(ctx, cudaStreamSynchronize(s)); // host arrays may be reused by the caller after return
     ctx->cont_set = true;
     return NHP_OK;

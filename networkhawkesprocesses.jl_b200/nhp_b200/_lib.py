@@ -48,6 +48,8 @@ PROTOTYPES = {
     "nhp_cont_stats_dev": (c_int, [c_void_p, c_int, POINTER(c_void_p), c_int64_p]),
     "nhp_cont_suffstats_second_pass": (c_int, [c_void_p, c_void_p]),
     "nhp_cont_suffstats_read": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]),
+    "nhp_cont_resample_params": (c_int, [c_void_p, c_void_p, c_uint64, c_uint64, c_double, c_void_p, c_int, c_int]),
+    "nhp_cont_params_get": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]),
     "nhp_cont_loglik_dev": (c_int, [c_void_p, c_void_p, c_int]),
     "nhp_disc_upload": (c_int, [c_void_p, c_void_p, c_int64, c_int64, c_int64, POINTER(c_void_p)]),
     "nhp_disc_free": (c_int, [c_void_p, c_void_p]),

@@ -484,14 +484,73 @@ class MarkovChainMonteCarlo:  # inference.jl:22-31
         self.samples, self.elapsed = samples, elapsed
 
 
-def mcmc_(process, data, nsteps=1000, log_freq=100, verbose=False, seed=0):
-    """`mcmc!` (inference.jl:49-70): data is uploaded once and stays on the device."""
+def _hyper(process):
+    """Hyper-parameters in the order nhp_cont_resample_params expects."""
+    b, w, imp = process.baseline, process.weights, process.impulses
+    if imp.kind == NHP_EXPONENTIAL:
+        return _f64([b.alpha0, b.beta0, w.kappa, w.nu, imp.alpha, imp.beta])
+    return _f64([b.alpha0, b.beta0, w.kappa, w.nu, imp.mumu, imp.kappamu, imp.alpha0, imp.beta0])
+
+
+def pull_params_(process, ctx=None):
+    """Copy the device-resident parameters (nhp_cont_params_get) into the host-side component objects."""
+    ctx = ctx or process._ctx()
+    K = process.ndims()
+    lam, W, p1 = np.empty(K), np.empty(K * K), np.empty(K * K)
+    p2 = np.empty(K * K) if process.impulses.p2() is not None else None
+    ctx.check(ctx.lib.nhp_cont_params_get(ctx.h, _ptr(lam), _ptr(W), None, _ptr(p1), _ptr(p2)))
+    unf = lambda v: v.reshape(K, K).T.copy()
+    process.baseline.lam = lam
+    process.weights.W = unf(W)
+    if process.impulses.kind == NHP_EXPONENTIAL:
+        process.impulses.theta = unf(p1)
+    else:
+        process.impulses.mu, process.impulses.tau = unf(p1), unf(p2)
+    return process.params()
+
+
+def resample_on_device_(process, data, rng, seed=0, counter=0, push=True, pull=True):
+    """One Gibbs sweep with the conjugate draws on the GPU (nhp_cont_resample_params): parent sweep + fused statistics,
+    second pass, draws of baseline / weights / impulses and the table rebuild never leave the device.  `push=False`
+    continues from the parameters already on the device (a chain); `pull=False` leaves the host objects untouched.
+    The network's adjacency sweep and the scalar Beta draw of rho keep their host round trip."""
+    ctx = process._ctx()
+    d, tmp = process._data(data)
+    try:
+        if push:
+            process._push(ctx)
+        _resample_parents(ctx, d, seed, counter, None, False)
+        hy = _hyper(process)
+        ctx.check(ctx.lib.nhp_cont_resample_params(ctx.h, d.h, int(seed), int(counter), float(d.duration), _ptr(hy), hy.size, 1))
+        if process.adjacency_matrix is not None:
+            K = process.ndims()
+            rho = _fmat(process.network.link_probability())
+            A = _fmat(process.adjacency_matrix).copy()
+            ctx.check(ctx.lib.nhp_cont_resample_adjacency_cols(ctx.h, d.h, _ptr(rho), int(seed), int(counter + (1 << 40)), None, _ptr(A), 0, 1))
+            process.adjacency_matrix = A.reshape(K, K).T.copy()
+            process.network.resample_(process.adjacency_matrix, rng)
+        return pull_params_(process, ctx) if pull else None
+    finally:
+        if tmp:
+            d.free()
+
+
+def mcmc_(process, data, nsteps=1000, log_freq=100, verbose=False, seed=0, device_draws=False, store_every=1):
+    """`mcmc!` (inference.jl:49-70): data is uploaded once and stays on the device.  `device_draws=True` keeps the whole
+    sweep on the GPU (resample_on_device_): parameters are pushed once and pulled every `store_every` sweeps (and at the
+    end), so neither the K^2 statistics nor the K^2 parameters cross PCIe in between."""
     rng = np.random.default_rng(seed)
     d = process.upload(data)
     t0 = time.time()
     samples = []
     for step in range(nsteps):
-        samples.append(resample_(process, d, rng, seed=seed, counter=step))
+        if device_draws:
+            keep = (step + 1) % store_every == 0 or step == nsteps - 1
+            x = resample_on_device_(process, d, rng, seed=seed, counter=step, push=(step == 0), pull=keep)
+            if keep:
+                samples.append(x)
+        else:
+            samples.append(resample_(process, d, rng, seed=seed, counter=step))
         if verbose and (step + 1) % log_freq == 0:
             print(f" > step: {step + 1}, elapsed: {time.time() - t0:.3f}")
     return MarkovChainMonteCarlo(samples, time.time() - t0)
