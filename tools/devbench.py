@@ -146,6 +146,22 @@ if __name__ == "__main__":
             ctx.check(ctx.lib.nhp_cont_loglik_grad_dev(ctx.h, d.h, 1)); ctx.lib.nhp_cont_loglik_grad_read(ctx.h, d.h, None, None, None, None, None); k_g = ctx.last_kernel_ms
             print(f"grad {kind} K={K} n={n:.1e} dens={dens}: loglik {k_ll:.2f} ms, loglik+gradient {k_g:.2f} ms = {n/k_g/1e3:.1f} Mev/s (x{k_g/k_ll:.1f} of a loglik; finite differences: x{2*(K+(2 if kind=='exp' else 3)*K*K)} )", flush=True)
         sys.exit(0)
+    if which == "mcmc":  # mcmc K n rate density nsweeps : full Gibbs sweeps, host draws vs device draws
+        K, n, rate, dens, ns = int(sys.argv[2]), int(float(sys.argv[3])), float(sys.argv[4]), (None if sys.argv[5] == "none" else float(sys.argv[5])), int(sys.argv[6])
+        t, nodes, T = synth.poisson_stream(n, K, rate, 1)
+        lam0, W, mu, tau, A = synth.ln_params(K, 2, density=dens)
+        for dev in (False, True):
+            if A is None:
+                proc = nhp.ContinuousStandardHawkesProcess(nhp.HomogeneousProcess(lam0), nhp.LogitNormalImpulseResponse(mu, tau, 1.0), nhp.DenseWeightModel(W))
+            else:
+                proc = nhp.ContinuousNetworkHawkesProcess(nhp.HomogeneousProcess(lam0), nhp.LogitNormalImpulseResponse(mu, tau, 1.0), nhp.DenseWeightModel(W), A.copy(), nhp.BernoulliNetworkModel(dens, K))
+            d = proc.upload((t, nodes, T))
+            nhp.mcmc_(proc, d, nsteps=2, seed=1, device_draws=dev, store_every=10**9)
+            t0 = time.perf_counter()
+            nhp.mcmc_(proc, d, nsteps=ns, seed=2, device_draws=dev, store_every=10**9)
+            dt = (time.perf_counter() - t0) / ns
+            print(f"mcmc K={K} n={n:.1e} dens={dens} device_draws={dev}: {1e3*dt:.1f} ms per full Gibbs sweep = {n/dt/1e6:.1f} Mev/s", flush=True)
+        sys.exit(0)
     if which == "cfg1":  # README example: K=2 exponential, T=1000: per-call latency of loglikelihood (params pushed each call, as mle! does)
         sys.path.insert(0, os.path.join(ROOT, "oracle"))
         import oracle_ffi as orc
