@@ -416,10 +416,23 @@ def run_ours(args, rank, world, local_rank):
             ctx.check(lib.nhp_cont_sweep_loglik(ctx.h, ev3, ctypes.byref(llf)))
             f1.record(stream); f1.synchronize()
             fused.append(f0.elapsed_time(f1))
-        lib.nhp_events_free(ctx.h, ev3)
         ctx.check(lib.nhp_set_option(ctx.h, 1, 0))
         line["detail"]["fused_loglik_and_gibbs_sweep_ms"] = float(np.median(fused[1:]))
         line["detail"]["fused_loglik_and_gibbs_sweep_events_per_s"] = n / (float(np.median(fused[1:])) * 1e-3)
+        # whole Gibbs sweep on the device: parent sweep + statistics + second pass + conjugate draws of lambda0 / W / (mu, tau) +
+        # table rebuild (nhp_cont_resample_params); the chain continues from the drawn parameters, so this goes last
+        hyper = np.array([1.0, 1.0, 1.0, 1.0, 1.0, 1.0, 1.0, 1.0])
+        full = []
+        for r in range(4):
+            f0 = torch.cuda.Event(enable_timing=True); f1 = torch.cuda.Event(enable_timing=True)
+            f0.record(stream)
+            ctx.check(lib.nhp_cont_resample_parents(ctx.h, ev3, 20261018, 700 + r, None, None, None))
+            ctx.check(lib.nhp_cont_resample_params(ctx.h, ev3, 20261018, 700 + r, float(duration), _ptr(hyper), hyper.size, 1))
+            f1.record(stream); f1.synchronize()
+            full.append(f0.elapsed_time(f1))
+        lib.nhp_events_free(ctx.h, ev3)
+        line["detail"]["gibbs_sweep_with_device_conjugate_draws_ms"] = float(np.median(full[1:]))
+        set_params()  # restore the workload's parameters for whatever follows
 
     if world == 1 and args.adjacency:
         # continuous.jl:444-519 on the same resident data (not part of the timed step; reported for completeness)

@@ -143,6 +143,29 @@ function resample_adjacency_matrix!(process::ContinuousNetworkHawkesProcess, dat
     return nothing
 end
 
+# ---- optional: the conjugate draws of resample!(process, data) (continuous.jl:202-208) on the device ---------------
+# baselines.jl:72-77, weights.jl:59-64, impulses.jl:68-73 / 204-214; the process's arrays are refreshed from the device.
+function resample_on_device!(process::ContinuousHawkesProcess, data)
+    ev = device_events(process, data)
+    push_params!(process)
+    SWEEP[] += 1
+    seed = rand(UInt64)
+    check(ccall((:nhp_cont_resample_parents, LIB[]), Cint, (Ptr{Cvoid}, Ptr{Cvoid}, UInt64, UInt64, Ptr{Float64}, Ptr{Int64}, Ptr{Int64}),
+        CTX[], ev.h, seed, SWEEP[], C_NULL, C_NULL, C_NULL))
+    b, w, imp = process.baseline, process.weights, process.impulses
+    hyper = imp isa ExponentialImpulseResponse ? Float64[b.α0, b.β0, w.κ, w.ν, imp.α, imp.β] :
+                                                  Float64[b.α0, b.β0, w.κ, w.ν, imp.μμ, imp.κμ, imp.α0, imp.β0]
+    check(ccall((:nhp_cont_resample_params, LIB[]), Cint, (Ptr{Cvoid}, Ptr{Cvoid}, UInt64, UInt64, Float64, Ptr{Float64}, Cint, Cint),
+        CTX[], ev.h, seed, SWEEP[], Float64(data[3]), hyper, length(hyper), 1))
+    K = ndims(process)
+    λ = Vector{Float64}(undef, K); W = Matrix{Float64}(undef, K, K); q1 = Matrix{Float64}(undef, K, K); q2 = Matrix{Float64}(undef, K, K)
+    check(ccall((:nhp_cont_params_get, LIB[]), Cint, (Ptr{Cvoid}, Ptr{Float64}, Ptr{Float64}, Ptr{Float64}, Ptr{Float64}, Ptr{Float64}),
+        CTX[], λ, W, C_NULL, q1, imp isa ExponentialImpulseResponse ? C_NULL : q2))
+    b.λ .= λ; w.W .= W
+    if imp isa ExponentialImpulseResponse; imp.θ .= q1 else imp.μ .= q1; imp.τ .= q2 end
+    return nothing
+end
+
 # ---- discrete path (discrete.jl:86-151; parents.jl:82-177) ------------------------------------------------
 mutable struct DeviceCounts
     h::Ptr{Cvoid}
