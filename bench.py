@@ -378,7 +378,7 @@ def run_ours(args, rank, world, local_rank):
     if os.path.exists(prof) and pj.get("l1_lsu_wavefront_pct_of_peak") and n == pj.get("events"):
         lsu_frac = pj["l1_lsu_wavefront_pct_of_peak"] / 100.0 * (pj["duration_ms_under_ncu"] * 1e-3) / secs
         lsu_view.update({"achieved": lsu_frac, "frac": lsu_frac,
-                         "source": "l1tex__data_pipe_lsu_wavefronts %% of peak from profiles/r01_ncu_dominant_kernel.json x (ncu duration / live duration)"})
+                         "source": "l1tex__data_pipe_lsu_wavefronts % of peak from profiles/r01_ncu_dominant_kernel.json x (ncu duration / live duration)"})
     roofline = {"kernel": "k_sweep_sparse<LOGITNORMAL, %s>" % ("LOGLIK" if dom == "loglik" else "PARENTS"),
                 "bound": "hbm", "achieved": gbs, "peak": hbm_peak, "unit": "GB/s", "frac": gbs / hbm_peak, "traffic": traffic,
                 "peak_source": hbm_src, "algorithmic_bytes_per_launch": bytes_alg,
