@@ -68,3 +68,58 @@ def test_mle_with_analytic_gradient_matches_finite_difference_mle():
         res[mode] = nhp.mle_(proc, data, guess=np.full(proc.params().size, 0.5), gradient=mode, max_iter=300)
     assert res["analytic"].maximum == pytest.approx(res["finite"].maximum, abs=1e-3)
     assert res["analytic"].maximum >= nhp.loglikelihood(true, data) - 1e-6
+
+
+def _grad_close(g, og, tol=G_TOL):
+    for name, a, b in (("lambda0", g["lambda0"], og[1]), ("W", g["W"], og[2]), ("p1", g["p1"], og[3])) + ((("p2", g["p2"], og[4]),) if g["p2"] is not None else ()):
+        assert np.max(np.abs(a - b)) <= tol * max(np.max(np.abs(b)), 1.0), name
+
+
+@pytest.mark.parametrize("n", [0, 1, 2, 257])
+def test_gradient_edge_sizes(n):
+    K = 4
+    t, nodes, T = synth.poisson_stream(max(n, 1), K, 20.0, 50 + n)
+    t, nodes = t[:n], nodes[:n]
+    for proc, om, rec in (make_ln(K, 3, density=0.5, wmax=0.2) + (False,), make_exp(K, 3, wmax=0.2) + (True,)):
+        ll, g = nhp.loglikelihood_gradient(proc, (t, nodes, T), recursive=rec)
+        og = om.loglik_grad(t, nodes, T, recursive=rec)
+        assert ll == pytest.approx(og[0], rel=1e-10)
+        _grad_close(g, og)
+
+
+def test_gradient_single_node_ties_and_empty_network():
+    t, nodes, T = synth.poisson_stream(2000, 1, 30.0, 7)
+    proc, om = make_ln(1, 5, wmax=0.5)
+    _grad_close(nhp.loglikelihood_gradient(proc, (t, nodes, T))[1], om.loglik_grad(t, nodes, T))
+    # simultaneous events: dt = 0 contributes theta * w for the Exponential (quirk Q9) and its derivative terms
+    K = 3
+    tt = np.full(120, 1.25)
+    nn = (np.arange(120) % K + 1).astype(np.int64)
+    pe, oe = make_exp(K, 8, wmax=0.3, dtmax=2.0)
+    _grad_close(nhp.loglikelihood_gradient(pe, (tt, nn, 3.0), recursive=False)[1], oe.loglik_grad(tt, nn, 3.0, recursive=False))
+    # a network without links: only the compensator terms remain (dW = 0 where A = 0, dlambda0 = sum 1/lambda0 - T)
+    lam0, W, mu, tau, _ = synth.ln_params(K, 4)
+    A = np.zeros((K, K))
+    pn = nhp.ContinuousNetworkHawkesProcess(nhp.HomogeneousProcess(lam0), nhp.LogitNormalImpulseResponse(mu, tau, 1.0), nhp.DenseWeightModel(W), A,
+                                            nhp.BernoulliNetworkModel(0.5, K))
+    t3, n3, T3 = synth.poisson_stream(500, K, 10.0, 3)
+    ll, g = nhp.loglikelihood_gradient(pn, (t3, n3, T3))
+    assert np.all(g["W"] == 0.0) and np.all(g["p1"] == 0.0) and np.all(g["p2"] == 0.0)
+    cnt = np.bincount(n3 - 1, minlength=K)
+    np.testing.assert_allclose(g["lambda0"], cnt / lam0 - T3, rtol=1e-12)
+
+
+def test_gradient_null_outputs_and_state():
+    import ctypes
+    K = 3
+    proc, _ = make_ln(K, 1)
+    ctx = proc._ctx()
+    d = proc.upload(synth.poisson_stream(300, K, 10.0, 1))
+    proc._push(ctx)
+    ll = ctypes.c_double()
+    ctx.check(ctx.lib.nhp_cont_loglik_grad(ctx.h, d.h, 0, ctypes.byref(ll), None, None, None, None))
+    assert ll.value == pytest.approx(nhp.loglikelihood(proc, d), rel=1e-12)
+    # the gradient planes share the statistics buffers: a parent sweep invalidates them
+    nhp.resample_parents(proc, d, seed=1)
+    with pytest.raises(nhp.NHPError):
+        ctx.check(ctx.lib.nhp_cont_loglik_grad_read(ctx.h, d.h, ctypes.byref(ll), None, None, None, None))
