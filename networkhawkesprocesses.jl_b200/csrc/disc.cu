@@ -10,6 +10,7 @@
 #include "nhp_internal.cuh"
 #include <cub/cub.cuh>
 #include <algorithm>
+#include <vector>
 
 struct DiscExtra {  // hangs off nhp_disc (kept here so the public struct stays small)
     int64_t nnz = 0;
@@ -344,6 +345,12 @@ __global__ void k_bump(int N, int B, const double *__restrict__ W, const double 
     bumpM[(int64_t)k * N + c] = v;
 }
 
+// btc[i] = bumpT[c][klist[i]] for the entries of child c
+__global__ void k_compact_bump(int NB, const double *__restrict__ bumpT, const int *__restrict__ klist, const int *__restrict__ kptr, double *__restrict__ btc) {
+    const int c = blockIdx.x;
+    for (int i = kptr[c] + threadIdx.x; i < kptr[c + 1]; i += blockDim.x) btc[i] = bumpT[(int64_t)c * NB + klist[i]];
+}
+
 extern "C" int nhp_disc_params_set(nhp_ctx *ctx, int64_t N, int64_t B, const double *lambda0, const double *W, const double *A, const double *theta, double dt) {
     NHP_CHECK(ctx, ctx != nullptr, NHP_ERR_INVALID, "ctx is NULL");
     NHP_CHECK(ctx, N >= 1 && B >= 1 && lambda0 && W && theta && dt > 0.0, NHP_ERR_INVALID, "nhp_disc_params_set: bad argument");
@@ -360,6 +367,11 @@ extern "C" int nhp_disc_params_set(nhp_ctx *ctx, int64_t N, int64_t B, const dou
         DCUDA(ctx, cudaMalloc(&ctx->dd_A, (size_t)NN * sizeof(double)));
         DCUDA(ctx, cudaMalloc(&ctx->dd_theta, (size_t)(NN * B) * sizeof(double)));
         DCUDA(ctx, cudaMalloc(&ctx->dd_bump, (size_t)(2 * NB * N) * sizeof(double)));
+        cudaFree(ctx->dd_klist); cudaFree(ctx->dd_kptr); cudaFree(ctx->dd_btc);
+        ctx->dd_klist = ctx->dd_kptr = nullptr; ctx->dd_btc = nullptr;
+        DCUDA(ctx, cudaMalloc(&ctx->dd_klist, (size_t)(NB * N) * sizeof(int)));
+        DCUDA(ctx, cudaMalloc(&ctx->dd_kptr, (size_t)(N + 1) * sizeof(int)));
+        DCUDA(ctx, cudaMalloc(&ctx->dd_btc, (size_t)(NB * N) * sizeof(double)));
         ctx->dN = N; ctx->dB = B;
     }
     ctx->disc_set = false;
@@ -370,6 +382,30 @@ extern "C" int nhp_disc_params_set(nhp_ctx *ctx, int64_t N, int64_t B, const dou
     DCUDA(ctx, cudaMemcpyAsync(ctx->dd_theta, theta, (size_t)(NN * B) * sizeof(double), cudaMemcpyHostToDevice, s));
     k_bump<<<(unsigned)((NB * N + 255) / 256), 256, 0, s>>>((int)N, (int)B, ctx->dd_W, A ? ctx->dd_A : nullptr, ctx->dd_theta, dt, ctx->dd_bump, ctx->dd_bump + NB * N);
     NHP_LAUNCHED(ctx);
+    // compact per-child lists of the structurally non-zero (parent, basis) entries: k = p*B + b with [A]W[p,c] != 0
+    {
+        std::vector<int> kptr(N + 1, 0), klist;
+        int64_t maxNA = 0;
+        for (int64_t c = 0; c < N; c++) {
+            kptr[c] = (int)klist.size();
+            for (int64_t pp = 0; pp < N; pp++) {
+                const double w = A ? A[pp + N * c] * W[pp + N * c] : W[pp + N * c];
+                if (w != 0.0) for (int64_t b = 0; b < B; b++) klist.push_back((int)(pp * B + b));
+            }
+            maxNA = std::max<int64_t>(maxNA, (int64_t)klist.size() - kptr[c]);
+        }
+        kptr[N] = (int)klist.size();
+        ctx->dd_density = (double)klist.size() / (double)(NB * N);
+        ctx->dd_maxNA = maxNA;
+        if (!klist.empty()) {
+            DCUDA(ctx, cudaMemcpyAsync(ctx->dd_kptr, kptr.data(), (size_t)(N + 1) * sizeof(int), cudaMemcpyHostToDevice, s));
+            DCUDA(ctx, cudaMemcpyAsync(ctx->dd_klist, klist.data(), klist.size() * sizeof(int), cudaMemcpyHostToDevice, s));
+            k_compact_bump<<<(unsigned)N, 256, 0, s>>>((int)NB, ctx->dd_bump + NB * N, ctx->dd_klist, ctx->dd_kptr, ctx->dd_btc);
+            NHP_LAUNCHED(ctx);
+        }
+        DCUDA(ctx, cudaGetLastError());
+        DCUDA(ctx, cudaStreamSynchronize(s));  // kptr / klist are stack-owned host vectors
+    }
     DCUDA(ctx, cudaGetLastError());
     DCUDA(ctx, cudaStreamSynchronize(s));
     ctx->disc_set = true;
@@ -765,27 +801,46 @@ __global__ void __launch_bounds__(256) k_disc_vb(const double *__restrict__ conv
 // ---------------------------------------------------------------------------------------
 // warp-per-bin variants (no block barriers in the bin loop): used whenever the per-warp buffers fit shared memory
 // ---------------------------------------------------------------------------------------
+// Work decomposition of the warp-per-bin kernels: CTA = (time block, child).  All children of a time block are resident
+// together (blockIdx.x = block * N + child), so the block's conv rows are fetched from HBM once and served from L2 to
+// the other children (the earlier (child, slab) split streamed every row once per child: 63 GB of DRAM reads at
+// config 3 against 9.6 GB of rows).  A child's bins are time-sorted, so its share of a block is a binary search.
+__device__ __forceinline__ int nz_lower_bound(const int *__restrict__ nz_t, int lo, int hi, int t) {
+    while (lo < hi) {
+        const int mid = (lo + hi) >> 1;
+        if (nz_t[mid] < t) lo = mid + 1; else hi = mid;
+    }
+    return lo;
+}
+
 // Gibbs: the warp stores the NB weights of a bin in its shared-memory buffer, every lane sums a contiguous chunk,
 // a warp scan of the chunk sums gives the cdf at chunk granularity, and the lane owning the target walks its chunk.
 __global__ void __launch_bounds__(256) k_disc_gibbs_warp(const double *__restrict__ convT, const double *__restrict__ bumpT, const double *__restrict__ lambda0, double dt,
                                                          int N, int NB, const int *__restrict__ nz_t, const int *__restrict__ nz_s, const int64_t *__restrict__ nz_off,
-                                                         const int *__restrict__ child_ptr, int slabs, const double *__restrict__ u, uint64_t seed, uint64_t counter,
-                                                         double *__restrict__ counts, int *__restrict__ flag) {
+                                                         const int *__restrict__ child_ptr, int tb, const double *__restrict__ u, uint64_t seed, uint64_t counter,
+                                                         double *__restrict__ counts, int *__restrict__ flag, const int *__restrict__ klist,
+                                                         const int *__restrict__ kptr, const double *__restrict__ btc, int maxNA) {
+    // klist != NULL: sparse effective weights -- only the child's structurally non-zero (parent, basis) entries are
+    // gathered from the conv row (compact list klist[kptr[c] .. kptr[c+1]) ascending, values btc); zero entries can never
+    // be drawn and do not move the cumulative sum, so skipping them is exact.
     extern __shared__ double s_buf[];  // [8 warps][NBP]
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const int L = ((NB + 31) / 32) | 1;  // odd chunk length: conflict-free strided reads
+    const int c = blockIdx.x % N, blk = blockIdx.x / N;
+    const int k0 = klist ? kptr[c] : 0;
+    const int NA = klist ? kptr[c + 1] - k0 : NB;           // entries of this child
+    const int L = (((klist ? maxNA : NB) + 31) / 32) | 1;   // odd chunk length: conflict-free strided reads
     const int NBP = 32 * L;
     double *w = s_buf + (size_t)warp * NBP;
-    const int c = blockIdx.x / slabs, slab = blockIdx.x % slabs;
     const int e0 = child_ptr[c], e1 = child_ptr[c + 1];
-    const int per = (e1 - e0 + slabs - 1) / slabs;
-    const int b0 = e0 + slab * per, b1 = min(e1, b0 + per);
+    const int b0 = nz_lower_bound(nz_t, e0, e1, blk * tb), b1 = nz_lower_bound(nz_t, b0, e1, (blk + 1) * tb);
+    if (b0 == b1) return;
     const double *bt = bumpT + (int64_t)c * NB;
     const double mu0 = lambda0[c] * dt;
     for (int e = b0 + warp; e < b1; e += 8) {
         const int t = nz_t[e], s = nz_s[e];
         const double *row = convT + (int64_t)t * NB;
-        for (int k = lane; k < NBP; k += 32) w[k] = k < NB ? __ldg(row + k) * __ldg(bt + k) : 0.0;
+        if (klist) for (int k = lane; k < NBP; k += 32) w[k] = k < NA ? __ldg(row + __ldg(klist + k0 + k)) * __ldg(btc + k0 + k) : 0.0;
+        else for (int k = lane; k < NBP; k += 32) w[k] = k < NB ? __ldg(row + k) * __ldg(bt + k) : 0.0;
         __syncwarp();
         double cs = 0.0;
         const double *mine = w + lane * L;
@@ -812,7 +867,7 @@ __global__ void __launch_bounds__(256) k_disc_gibbs_warp(const double *__restric
                         double cum = incl - cs;
                         for (int m = 0; m < L; m++) {
                             cum += mine[m];
-                            if (cum > target) { found = 1 + lane * L + m; break; }
+                            if (cum > target) { const int q = lane * L + m; found = q < NA ? 1 + (klist ? __ldg(klist + k0 + q) : q) : NB; break; }
                         }
                         if (found > NB) found = NB;
                     }
@@ -827,15 +882,15 @@ __global__ void __launch_bounds__(256) k_disc_gibbs_warp(const double *__restric
 
 // VB: Z and the gamma accumulators per warp; the child's exp-expectation row is shared by the CTA.
 __global__ void __launch_bounds__(256) k_disc_vb_warp(const double *__restrict__ convT, const double *__restrict__ ET, const double *__restrict__ e0, int N, int NB,
-                                                      const int *__restrict__ nz_t, const int *__restrict__ nz_s, const int *__restrict__ child_ptr, int slabs,
+                                                      const int *__restrict__ nz_t, const int *__restrict__ nz_s, const int *__restrict__ child_ptr, int tb,
                                                       double *__restrict__ alpha_sum, double *__restrict__ gammaT) {
     extern __shared__ double s_buf[];  // [NB] ET row | [8][NB] per-warp accumulators
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     double *et = s_buf, *acc = s_buf + NB + (size_t)warp * NB;
-    const int c = blockIdx.x / slabs, slab = blockIdx.x % slabs;
+    const int c = blockIdx.x % N, blk = blockIdx.x / N;
     const int ei0 = child_ptr[c], e1 = child_ptr[c + 1];
-    const int per = (e1 - ei0 + slabs - 1) / slabs;
-    const int b0 = ei0 + slab * per, b1 = min(e1, b0 + per);
+    const int b0 = nz_lower_bound(nz_t, ei0, e1, blk * tb), b1 = nz_lower_bound(nz_t, b0, e1, (blk + 1) * tb);
+    if (b0 == b1) return;  // block-uniform
     for (int k = threadIdx.x; k < NB; k += 256) et[k] = ET[(int64_t)c * NB + k];
     for (int k = lane; k < NB; k += 32) acc[k] = 0.0;
     __syncthreads();
@@ -858,6 +913,19 @@ __global__ void __launch_bounds__(256) k_disc_vb_warp(const double *__restrict__
         if (g != 0.0) atomicAdd(&gammaT[(int64_t)c * NB + k], g);
     }
     if (lane == 0 && asum != 0.0) atomicAdd(&alpha_sum[c], asum);
+}
+
+// bins per time block for the (time block, child) kernels: the rows of the ~(resident CTAs / N) blocks in flight should fit in
+// about half of L2, and an item should carry enough non-zero bins to amortise its set-up
+static int pick_time_block(nhp_ctx *ctx, const nhp_disc *dd, int64_t nnz) {
+    const int64_t N = dd->N, NB = N * dd->B, own = dd->T - dd->t_halo;
+    const double inflight = std::max(1.0, (double)ctx->sm_count * 8.0 / (double)N);
+    double tb = 64e6 / ((double)NB * 8.0 * inflight);
+    const double per_bin = (double)nnz / (double)std::max<int64_t>(N * own, 1);  // non-zero fraction
+    tb = std::max(tb, 128.0 / std::max(per_bin, 1e-9));
+    const char *env = getenv("NHP_DISC_TB");
+    if (env && atoi(env) > 0) tb = atoi(env);
+    return (int)std::min<double>(std::max(tb, 32.0), (double)std::max<int64_t>(dd->T, 32));
 }
 
 static int pick_slabs(nhp_ctx *ctx, int64_t N, int64_t nnz) {
@@ -884,12 +952,18 @@ extern "C" int nhp_disc_gibbs_counts(nhp_ctx *ctx, nhp_disc *dd, uint64_t seed, 
     NHP_TRY(nhp_timer_begin(ctx));
     if (ex->nnz > 0) {
         int slabs = pick_slabs(ctx, N, ex->nnz);
-        const size_t wsmem = (size_t)8 * 32 * (((NB + 31) / 32) | 1) * sizeof(double);
+        const char *envs = getenv("NHP_DISC_SPARSE");
+        const bool sparse = ctx->dd_klist && ctx->dd_density <= 0.5 && !(envs && atoi(envs) == 0);
+        const int64_t wid = sparse ? ctx->dd_maxNA : NB;
+        const size_t wsmem = (size_t)8 * 32 * (((wid + 31) / 32) | 1) * sizeof(double);
         const char *envw = getenv("NHP_DISC_WARP");
         if (wsmem <= (size_t)ctx->smem_optin - 4096 && !(envw && atoi(envw) == 0)) {
             DCUDA(ctx, cudaFuncSetAttribute(k_disc_gibbs_warp, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)wsmem));
-            k_disc_gibbs_warp<<<(unsigned)(N * slabs), 256, wsmem, s>>>(dd->d_conv, ctx->dd_bump + NB * N, ctx->dd_lambda0, ctx->ddt, (int)N, (int)NB, ex->nz_t, ex->nz_s,
-                                                                         ex->nz_off, ex->child_ptr, slabs, d_u, seed, counter, d_counts, ctx->d_flag);
+            const int tb = pick_time_block(ctx, dd, ex->nnz);
+            const int64_t nblk = (dd->T + tb - 1) / tb;
+            k_disc_gibbs_warp<<<(unsigned)(N * nblk), 256, wsmem, s>>>(dd->d_conv, ctx->dd_bump + NB * N, ctx->dd_lambda0, ctx->ddt, (int)N, (int)NB, ex->nz_t, ex->nz_s,
+                                                                        ex->nz_off, ex->child_ptr, tb, d_u, seed, counter, d_counts, ctx->d_flag,
+                                                                        sparse ? ctx->dd_klist : nullptr, ctx->dd_kptr, ctx->dd_btc, (int)ctx->dd_maxNA);
         } else {
         size_t smem = (size_t)(NB + 1) * sizeof(double);
         if (smem > 48 * 1024) DCUDA(ctx, cudaFuncSetAttribute(k_disc_gibbs, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
@@ -960,7 +1034,9 @@ extern "C" int nhp_disc_vb_stats(nhp_ctx *ctx, nhp_disc *dd, const double *e0, c
         const char *envw = getenv("NHP_DISC_WARP");
         if (wsmem <= (size_t)ctx->smem_optin - 4096 && !(envw && atoi(envw) == 0)) {
             DCUDA(ctx, cudaFuncSetAttribute(k_disc_vb_warp, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)wsmem));
-            k_disc_vb_warp<<<(unsigned)(N * slabs), 256, wsmem, s>>>(dd->d_conv, d_ET, d_e0, (int)N, (int)NB, ex->nz_t, ex->nz_s, ex->child_ptr, slabs, d_alpha, d_gT);
+            const int tb = pick_time_block(ctx, dd, ex->nnz);
+            const int64_t nblk = (dd->T + tb - 1) / tb;
+            k_disc_vb_warp<<<(unsigned)(N * nblk), 256, wsmem, s>>>(dd->d_conv, d_ET, d_e0, (int)N, (int)NB, ex->nz_t, ex->nz_s, ex->child_ptr, tb, d_alpha, d_gT);
         } else
         k_disc_vb<<<(unsigned)(N * slabs), 256, 0, s>>>(dd->d_conv, d_ET, d_e0, (int)N, (int)NB, ex->nz_t, ex->nz_s, ex->child_ptr, slabs, d_alpha, d_gT);
         NHP_LAUNCHED(ctx);

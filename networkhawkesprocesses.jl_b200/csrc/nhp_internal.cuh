@@ -148,6 +148,10 @@ struct nhp_ctx {
     bool d_has_A = false;
     double *dd_lambda0 = nullptr, *dd_W = nullptr, *dd_A = nullptr, *dd_theta = nullptr;
     double *dd_bump = nullptr;    // [N*B][N] row k=(p*B+b), col c: [A]W theta dt
+    int *dd_klist = nullptr, *dd_kptr = nullptr;  // per child: ascending k = p*B+b of the structurally non-zero entries
+    double *dd_btc = nullptr;     // bumpT values at dd_klist
+    double dd_density = 1.0;
+    int64_t dd_maxNA = 0;
 };
 
 // launch bookkeeping
