@@ -244,6 +244,7 @@ extern "C" int nhp_events_free(nhp_ctx *ctx, nhp_events *ev) {
         cudaFree(ev->d_t); cudaFree(ev->d_c); cudaFree(ev->d_poff); cudaFree(ev->d_Mn); cudaFree(ev->d_tile_lo); cudaFree(ev->d_wlen);
     }
     cudaFree(ev->d_order); cudaFree(ev->d_node_ptr); cudaFree(ev->d_item_node); cudaFree(ev->d_item_e0);
+    cudaFree(ev->d_adj_i); cudaFree(ev->d_adj_dt); cudaFree(ev->d_adj_boff); cudaFree(ev->d_adj_col);
     delete ev;
     return NHP_OK;
 }

@@ -82,6 +82,14 @@ struct nhp_events {
     // by-node order of the own events + work items of the child-major sweep (cont_child.cu), built on first use
     int *d_order = nullptr, *d_node_ptr = nullptr, *d_item_node = nullptr, *d_item_e0 = nullptr;
     int64_t n_items = 0;
+    // cached structure of the adjacency sampler (cont_adjacency.cu): every (child event, window predecessor) pair, grouped by child
+    // column and bucketed by parent node; depends on the data and the look-back horizon only, so it survives across Gibbs sweeps
+    double adj_horizon = -1.0;
+    unsigned *d_adj_i = nullptr;     // [adj_total] child event index inside its column | bit 31: the (event, parent) pair occurs more than once
+    double *d_adj_dt = nullptr;      // [adj_total] t_i - t_j
+    int *d_adj_boff = nullptr;       // [K][K+1] bucket offsets inside a column
+    int64_t *d_adj_col = nullptr;    // [K+1] first entry of every column
+    int64_t adj_total = 0, adj_max_bucket = 0, adj_max_col = 0;
     int64_t max_win = 0;        // max over boundaries of (i0 - lo)
     double mean_win = 0.0;
 };

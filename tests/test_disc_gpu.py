@@ -61,6 +61,35 @@ def test_gibbs_counts_match_given_uniforms(N, T, B, L, network, warp, monkeypatc
     assert np.count_nonzero(counts != ref) == 0
 
 
+@pytest.mark.parametrize("tb", ["", "37", "100000"])
+def test_gibbs_counts_sparse_network_and_time_blocks(tb, monkeypatch):
+    """Sparse-network path (compact non-zero parent lists) incl. a child without any parent, for several time-block sizes
+    of the (time block, child) decomposition; bit-exact against the oracle given the uniforms."""
+    if tb:
+        monkeypatch.setenv("NHP_DISC_TB", tb)
+    N, T, B, L = 24, 2500, 4, 6
+    rng = np.random.default_rng(77)
+    lam0 = rng.uniform(0.5, 1.5, N) * 0.1
+    A = (rng.random((N, N)) < 0.12).astype(np.float64)
+    A[:, 5] = 0.0   # child 5: baseline only
+    A[:, 9] = 1.0   # child 9: every parent
+    W = rng.uniform(0.0, 2.0 / N, (N, N))
+    theta = rng.dirichlet(np.ones(B), (N, N))
+    data = rng.poisson(0.15, (N, T)).astype(np.int64)
+    proc = D.DiscreteNetworkHawkesProcess(D.DiscreteHomogeneousProcess(lam0), D.DiscreteGaussianImpulseResponse(theta, L), nhp.DenseWeightModel(W), A,
+                                          nhp.BernoulliNetworkModel(0.12, N))
+    om = orc.Disc(lam0, W, theta, dt=1.0, A=A)
+    d = proc.upload(data)
+    D.convolve(proc, d, export=False)
+    oconv = orc.disc_convolve(data, orc.disc_basis(L, B))
+    u = np.random.default_rng(6).random(int(data.sum()))
+    for sparse in ("1", "0"):
+        monkeypatch.setenv("NHP_DISC_SPARSE", sparse)
+        counts = D.resample_parents(proc, d, u=u)
+        assert np.count_nonzero(counts != om.gibbs_counts(data, oconv, u)) == 0
+    assert np.all(counts[5, 1:] == 0) and counts[5, 0] == data[5].sum()
+
+
 def test_gibbs_counts_distribution():
     """Size-independent property: summed over many sweeps the counts follow the expected attribution mass."""
     proc, om, data = make(4, 600, 3, 4, 21, False, rate=0.3)
