@@ -255,10 +255,10 @@ struct AdjSweepArgs {
     int col_begin, col_stride;
 };
 
-template <int KIND> __global__ void __launch_bounds__(256) k_adj_sweep(const AdjSweepArgs a) {
+template <int KIND> __global__ void __launch_bounds__(1024) k_adj_sweep(const AdjSweepArgs a) {
     typedef typename EntryOf<KIND>::type E;
     __shared__ FastTables s_ft;
-    __shared__ double s_red[8];
+    __shared__ double s_red[32];
     __shared__ double s_anew;
     fast_tables_load(&s_ft);
     const FastTables *ft = &s_ft;
@@ -320,7 +320,7 @@ template <int KIND> __global__ void __launch_bounds__(256) k_adj_sweep(const Adj
             }
             if (threadIdx.x == 0) {
                 double sum = 0.0;
-                if (b1 > b0) for (int w = 0; w < 8; w++) sum += s_red[w];
+                if (b1 > b0) for (int w = 0; w < (int)(blockDim.x >> 5); w++) sum += s_red[w];
                 const double rho = a.rho[kk];
                 // ll1 - ll0 (continuous.jl:477-483): integrated-intensity difference, log-intensity difference, prior
                 const double delta = -a.W[kk] * a.Mn[p] + sum + (log(rho) - log(1.0 - rho));
@@ -527,6 +527,18 @@ extern "C" int nhp_cont_resample_adjacency_cols(nhp_ctx *ctx, nhp_events *ev, co
     if (cached) {
         const int64_t mb = std::max<int64_t>(ev->adj_max_bucket, 1);
         const size_t per_cta = (size_t)(2 * mc + mb) * sizeof(double);
+        // Threads per column: the per-column intensity array lam[] (8 B per child event) is gathered at random once per entry.
+        // With 256-thread CTAs ~8 columns share an SM; once their arrays exceed L2 many times over (1e8 events at K = 1000:
+        // 1.9 GB) every gather is a DRAM sector and fewer, larger CTAs win (measured: 163 vs 216 ms); below that the
+        // 256-thread CTAs are faster (1e7 events: 17 vs 30 ms).
+        int bs = 256;
+        {
+            const double lam_bytes = (double)mc * 16.0;  // lam + gacc
+            if (lam_bytes * ctx->sm_count * 8 > 1e9) bs = 1024;
+            const char *envb = getenv("NHP_ADJ_BLOCK");
+            if (envb && (atoi(envb) == 256 || atoi(envb) == 512 || atoi(envb) == 1024)) bs = atoi(envb);
+            grid = (int)std::min<int64_t>(grid, (int64_t)ctx->sm_count * (2048 / bs));
+        }
         while (grid > 1 && (size_t)grid * per_cta > free_b / 2) grid = (grid + 1) / 2;
         ADJ_CUDA(cudaMalloc(&d_lam, (size_t)grid * mc * sizeof(double)));
         ADJ_CUDA(cudaMalloc(&d_gacc, (size_t)grid * mc * sizeof(double)));
@@ -537,8 +549,8 @@ extern "C" int nhp_cont_resample_adjacency_cols(nhp_ctx *ctx, nhp_events *ev, co
         w.lam = d_lam; w.gacc = d_gacc; w.vbuf = d_ent_v; w.max_col = mc; w.max_bucket = mb; w.flag = ctx->d_flag; w.col_begin = (int)col_begin; w.col_stride = (int)col_stride;
         rc = nhp_timer_begin(ctx);
         if (rc != NHP_OK) return fin(rc);
-        if (ctx->kind == NHP_LOGITNORMAL) k_adj_sweep<NHP_LOGITNORMAL><<<grid, 256, 0, s>>>(w);
-        else k_adj_sweep<NHP_EXPONENTIAL><<<grid, 256, 0, s>>>(w);
+        if (ctx->kind == NHP_LOGITNORMAL) k_adj_sweep<NHP_LOGITNORMAL><<<grid, bs, 0, s>>>(w);
+        else k_adj_sweep<NHP_EXPONENTIAL><<<grid, bs, 0, s>>>(w);
     } else {
     // bound the scratch area: entries cost 12 B per CTA slot
     while (grid > 1 && (size_t)grid * ((size_t)cap * 12 + (size_t)mc * 16) > free_b / 2) grid = (grid + 1) / 2;
