@@ -1123,6 +1123,103 @@ __global__ void __launch_bounds__(256) k_disc_adjacency(const double *__restrict
     }
 }
 
+// Streaming variant (default when the scratch fits): the candidate contributions G_p[e] = sum_b conv[t_e,(p,b)] W theta dt do not
+// depend on the decisions, so they are computed for ALL (bin, parent) pairs first, by the whole GPU:
+//   phase A (k_disc_adj_gather): CTA = 32 consecutive non-zero bins of a child; a warp takes a bin and its lanes take consecutive
+//     parents, so the warp reads the bin's conv row as one contiguous stream (full DRAM bursts); the 32 x N tile is transposed
+//     through shared memory and written parent-major (G[p][e], 256-byte runs); the bins' current intensities fall out of the same pass.
+//   phase B (k_disc_adj_steps): one CTA per column runs the N sequential Bernoulli steps on coalesced reads of one G row each.
+// HBM traffic per sweep: rows once (nnz * N * B * 8 B) + G written and read once (nnz * N * 8 B each), against one scattered
+// 32-byte sector per (bin, parent) per pass in k_disc_adjacency (ncu at config 3: 290 GB, 17 % of the warps active).
+constexpr int ADJ_TE = 32;  // bins per phase-A tile
+
+__global__ void __launch_bounds__(256) k_disc_adj_gather(const double *__restrict__ convT, const double *__restrict__ lambda0, const double *__restrict__ W,
+                                                         const double *__restrict__ theta, double dt, const double *__restrict__ A, int N, int B,
+                                                         const int *__restrict__ nz_t, const int *__restrict__ child_ptr, double *__restrict__ lam_scratch,
+                                                         double *__restrict__ g_scratch) {
+    extern __shared__ double s_dynd[];  // [N*B] coefficients | [N][ADJ_TE + 1] tile
+    const int c = blockIdx.y;
+    const int NB = N * B;
+    const int e0 = child_ptr[c], ne = child_ptr[c + 1] - e0;
+    const int t0 = blockIdx.x * ADJ_TE;
+    if (t0 >= ne) return;
+    double *s_coef = s_dynd, *tile = s_dynd + NB;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    for (int k = threadIdx.x; k < NB; k += 256) {
+        const int p = k / B, b = k % B;
+        s_coef[k] = W[p + (int64_t)N * c] * theta[p + (int64_t)N * (c + (int64_t)N * b)] * dt;
+    }
+    __syncthreads();
+    const int nt = min(ADJ_TE, ne - t0);
+    for (int el = warp; el < nt; el += 8) {
+        const double *row = convT + (int64_t)nz_t[e0 + t0 + el] * NB;
+        double v = 0.0;
+        for (int p = lane; p < N; p += 32) {
+            double g = 0.0;
+            for (int b = 0; b < B; b++) g += __ldg(row + p * B + b) * s_coef[p * B + b];
+            tile[p * (ADJ_TE + 1) + el] = g;
+            if (A[p + (int64_t)N * c] != 0.0) v += g;
+        }
+        v = warp_sum_d(v);
+        if (lane == 0) lam_scratch[e0 + t0 + el] = lambda0[c] * dt + v;
+    }
+    __syncthreads();
+    double *G = g_scratch + (int64_t)e0 * N;  // [N][ne]
+    for (int k = threadIdx.x; k < N * ADJ_TE; k += 256) {
+        const int p = k / ADJ_TE, el = k % ADJ_TE;
+        if (el < nt) G[(int64_t)p * ne + t0 + el] = tile[p * (ADJ_TE + 1) + el];
+    }
+}
+
+__global__ void __launch_bounds__(1024) k_disc_adj_steps(const double *__restrict__ csum, const double *__restrict__ W, const double *__restrict__ theta, double dt,
+                                                         double *__restrict__ A, const double *__restrict__ rho, const double *__restrict__ u, uint64_t seed,
+                                                         uint64_t counter, int N, int B, const int *__restrict__ nz_s, const int *__restrict__ child_ptr,
+                                                         double *__restrict__ lam_scratch, const double *__restrict__ g_scratch, int *__restrict__ flag) {
+    __shared__ double red[32];
+    __shared__ double s_anew;
+    const int c = blockIdx.x;
+    const int e0 = child_ptr[c], e1 = child_ptr[c + 1], ne = e1 - e0;
+    double *lam = lam_scratch + e0;
+    const double *G = g_scratch + (int64_t)e0 * N;
+    for (int p = 0; p < N; p++) {
+        const int64_t kk = p + (int64_t)N * c;
+        const double a_old = A[kk], w = W[kk];
+        double gsum = 0.0;  // sum over all own bins of G_p
+        for (int b = 0; b < B; b++) gsum += csum[p * B + b] * (w * theta[kk + (int64_t)N * N * b] * dt);
+        const double *Gp = G + (int64_t)p * ne;
+        double part = 0.0;
+        for (int e = threadIdx.x; e < ne; e += blockDim.x) {
+            const double g = Gp[e];
+            if (g != 0.0) {
+                const double l = lam[e];
+                const double base = a_old != 0.0 ? l - g : l;
+                part += (double)nz_s[e0 + e] * log((base + g) / base);
+            }
+        }
+        part = warp_sum_d(part);
+        if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = part;
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            double sum = 0.0;
+            for (int wv = 0; wv < (int)(blockDim.x >> 5); wv++) sum += red[wv];
+            const double r = rho[kk];
+            const double delta = sum - gsum + (log(r) - log(1.0 - r));
+            double p1 = delta >= 0.0 ? 1.0 / (1.0 + exp(-delta)) : exp(delta) / (1.0 + exp(delta));
+            if (delta != delta) { atomicOr(flag, 64); p1 = 0.0; }
+            const double uu = u ? u[kk] : philox_uniform(seed, (uint64_t)kk, counter);
+            const double an = uu <= p1 ? 1.0 : 0.0;
+            A[kk] = an;
+            s_anew = an;
+        }
+        __syncthreads();
+        const double an = s_anew;
+        if (an != a_old) {
+            for (int e = threadIdx.x; e < ne; e += blockDim.x) lam[e] += an != 0.0 ? Gp[e] : -Gp[e];
+        }
+        __syncthreads();
+    }
+}
+
 extern "C" int nhp_disc_resample_adjacency(nhp_ctx *ctx, nhp_disc *dd, const double *rho, uint64_t seed, uint64_t counter, const double *u, double *A_inout) {
     NHP_TRY(disc_ready(ctx, dd, "nhp_disc_resample_adjacency"));
     NHP_CHECK(ctx, rho && A_inout, NHP_ERR_INVALID, "nhp_disc_resample_adjacency: NULL rho/A");
@@ -1131,14 +1228,37 @@ extern "C" int nhp_disc_resample_adjacency(nhp_ctx *ctx, nhp_disc *dd, const dou
     const int64_t N = dd->N, B = dd->B, NN = N * N;
     cudaStream_t s = ctx->stream;
     void *scratch;
-    size_t tot = (size_t)(3 * NN + std::max<int64_t>(ex->nnz, 1)) * sizeof(double);
+    const int64_t nnz1 = std::max<int64_t>(ex->nnz, 1);
+    size_t tot = (size_t)(3 * NN + nnz1) * sizeof(double);
+    // streaming variant: + G[p][e] for every (parent, non-zero bin)
+    const size_t g_bytes = (size_t)nnz1 * (size_t)N * sizeof(double), coef_smem = (size_t)(N * B + N * (ADJ_TE + 1)) * sizeof(double);
+    size_t free_b = 0, total_b = 0;
+    cudaMemGetInfo(&free_b, &total_b);
+    const char *envt = getenv("NHP_DISC_ADJ_STREAM");
+    const bool stream_variant = !(envt && atoi(envt) == 0) && coef_smem <= (size_t)ctx->smem_optin - 4096 && g_bytes <= free_b / 2 + ctx->scratch_cap;
+    if (stream_variant) tot += g_bytes;
     NHP_TRY(nhp_scratch(ctx, tot, &scratch));
-    double *d_A = (double *)scratch, *d_rho = d_A + NN, *d_u = d_rho + NN, *d_lam = d_u + NN;
+    double *d_A = (double *)scratch, *d_rho = d_A + NN, *d_u = d_rho + NN, *d_lam = d_u + NN, *d_G = d_lam + nnz1;
     DCUDA(ctx, cudaMemcpyAsync(d_A, A_inout, (size_t)NN * sizeof(double), cudaMemcpyHostToDevice, s));
     DCUDA(ctx, cudaMemcpyAsync(d_rho, rho, (size_t)NN * sizeof(double), cudaMemcpyHostToDevice, s));
     if (u) DCUDA(ctx, cudaMemcpyAsync(d_u, u, (size_t)NN * sizeof(double), cudaMemcpyHostToDevice, s));
     DCUDA(ctx, cudaMemsetAsync(ctx->d_flag, 0, sizeof(int), s));
     NHP_TRY(nhp_timer_begin(ctx));
+    if (stream_variant) {
+        std::vector<int> cp(N + 1);
+        DCUDA(ctx, cudaMemcpyAsync(cp.data(), ex->child_ptr, (size_t)(N + 1) * sizeof(int), cudaMemcpyDeviceToHost, s));
+        DCUDA(ctx, cudaStreamSynchronize(s));
+        int max_ne = 0;
+        for (int64_t c = 0; c < N; c++) max_ne = std::max(max_ne, cp[c + 1] - cp[c]);
+        if (max_ne > 0) {
+            if (coef_smem > 32 * 1024) DCUDA(ctx, cudaFuncSetAttribute(k_disc_adj_gather, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)coef_smem));
+            dim3 gg((unsigned)((max_ne + ADJ_TE - 1) / ADJ_TE), (unsigned)N);
+            k_disc_adj_gather<<<gg, 256, coef_smem, s>>>(dd->d_conv, ctx->dd_lambda0, ctx->dd_W, ctx->dd_theta, ctx->ddt, d_A, (int)N, (int)B, ex->nz_t, ex->child_ptr, d_lam, d_G);
+            NHP_LAUNCHED(ctx);
+        }
+        k_disc_adj_steps<<<(unsigned)N, 1024, 0, s>>>(ex->csum, ctx->dd_W, ctx->dd_theta, ctx->ddt, d_A, d_rho, u ? d_u : nullptr, seed, counter, (int)N, (int)B, ex->nz_s,
+                                                       ex->child_ptr, d_lam, d_G, ctx->d_flag);
+    } else
     k_disc_adjacency<<<(unsigned)N, 256, 0, s>>>(dd->d_conv, ex->csum, ctx->dd_lambda0, ctx->dd_W, ctx->dd_theta, ctx->ddt, d_A, d_rho, u ? d_u : nullptr, seed, counter,
                                                  (int)N, (int)B, ex->nz_t, ex->nz_s, ex->child_ptr, d_lam, ctx->d_flag);
     NHP_LAUNCHED(ctx);
