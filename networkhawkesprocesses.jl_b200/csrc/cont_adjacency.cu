@@ -540,13 +540,14 @@ extern "C" int nhp_cont_resample_adjacency_cols(nhp_ctx *ctx, nhp_events *ev, co
             grid = (int)std::min<int64_t>(grid, (int64_t)ctx->sm_count * (2048 / bs));
         }
         while (grid > 1 && (size_t)grid * per_cta > free_b / 2) grid = (grid + 1) / 2;
-        ADJ_CUDA(cudaMalloc(&d_lam, (size_t)grid * mc * sizeof(double)));
-        ADJ_CUDA(cudaMalloc(&d_gacc, (size_t)grid * mc * sizeof(double)));
-        ADJ_CUDA(cudaMalloc(&d_ent_v, (size_t)grid * mb * sizeof(double)));  // vbuf
+        // per-CTA work areas from the context's persistent scratch buffer (no allocation per sweep)
+        void *sc = nullptr;
+        { int rcs = nhp_scratch(ctx, (size_t)grid * per_cta, &sc); if (rcs != NHP_OK) return fin(rcs); }
+        double *w_lam = (double *)sc, *w_gacc = w_lam + (size_t)grid * mc, *w_vbuf = w_gacc + (size_t)grid * mc;
         AdjSweepArgs w;
         w.node_ptr = ev->d_node_ptr; w.Mn = ev->d_Mn; w.K = (int)K; w.table_w = d_tw; w.lambda0 = ctx->d_lambda0; w.W = ctx->d_W; w.A = d_A; w.rho = d_rho; w.u = d_u;
         w.seed = seed; w.counter = counter; w.D = ctx->dtmax; w.col = ev->d_adj_col; w.boff = ev->d_adj_boff; w.ent_i = ev->d_adj_i; w.ent_dt = ev->d_adj_dt;
-        w.lam = d_lam; w.gacc = d_gacc; w.vbuf = d_ent_v; w.max_col = mc; w.max_bucket = mb; w.flag = ctx->d_flag; w.col_begin = (int)col_begin; w.col_stride = (int)col_stride;
+        w.lam = w_lam; w.gacc = w_gacc; w.vbuf = w_vbuf; w.max_col = mc; w.max_bucket = mb; w.flag = ctx->d_flag; w.col_begin = (int)col_begin; w.col_stride = (int)col_stride;
         rc = nhp_timer_begin(ctx);
         if (rc != NHP_OK) return fin(rc);
         if (ctx->kind == NHP_LOGITNORMAL) k_adj_sweep<NHP_LOGITNORMAL><<<grid, bs, 0, s>>>(w);
