@@ -561,16 +561,20 @@ class MaximumLikelihood:  # inference.jl:1-12
         self.maximizer, self.maximum, self.steps, self.elapsed, self.status = maximizer, maximum, steps, elapsed, status
 
 
-def mle_(process, data, regularize=False, guess=None, f_abstol=1e-6, max_iter=200, seed=0, gradient="analytic"):
+def mle_(process, data, regularize=False, guess=None, f_abstol=1e-6, max_iter=200, seed=0, gradient="auto"):
     """`mle!` (continuous.jl:144-198): box-constrained quasi-Newton on [1e-6, 10]; every objective evaluation is one GPU
     log-likelihood on the resident data (SciPy L-BFGS-B stands in for Optim's Fminbox(BFGS())).  `gradient="finite"` is
-    the reference's behaviour (finite differences: ~2P sweeps per gradient); the default `"analytic"` uses the gradient
-    sweep (nhp_cont_loglik_grad: two sweeps per objective + gradient).  With `regularize` the log-prior is differentiated
-    numerically on the host (it costs no sweep)."""
+    the reference's behaviour (finite differences: ~2P sweeps per gradient); `"analytic"` uses the gradient sweep
+    (nhp_cont_loglik_grad: two sweeps per objective + gradient).  The default `"auto"` takes the analytic gradient once the
+    model has more than 64 parameters (K >= 6): below that 2P tiny log-likelihood launches are cheaper than the scatter
+    sweep, whose shared-memory atomics collide when there are only a handful of parent nodes (README example, K = 2:
+    0.5 s vs 1.3 s).  With `regularize` the log-prior is differentiated numerically on the host (it costs no sweep)."""
     from scipy.optimize import approx_fprime, minimize
     d = process.upload(data)
     rng = np.random.default_rng(seed)
     x0 = rng.random(process.params().size) if guess is None else np.asarray(guess, dtype=np.float64)
+    if gradient == "auto":
+        gradient = "analytic" if process.params().size > 64 else "finite"
     analytic = gradient == "analytic" and isinstance(process, ContinuousStandardHawkesProcess)
 
     def prior(x):
