@@ -2,14 +2,15 @@
 // Bernoulli adjacency, continuous.jl:315-321, 521-525): a pair contributes a*w*pdf, which is exactly 0
 // wherever A[p,c]*W[p,c] == 0, so only the active pairs need the FP64 impulse evaluation.
 //
-// Per CTA (tile of TE consecutive child events, window staged by TMA exactly as the dense sweep):
-//   1. filter  -- four threads per child event, each walking a contiguous quarter of the window
-//                 most-recent-first and testing one adjacency bit per predecessor.  The bit-rows of the
-//                 tile's children are staged in shared memory by coalesced warp loads (row of event e
-//                 at [e*words .. ), rows are 16-byte multiples); the hits are flagged in a 64-bit register mask.
-//   2. compact -- block exclusive scan of the hit counts -> contiguous, ordered segment per event.
+// Per CTA (tile of STE = 256 / SG consecutive child events, window staged by TMA exactly as the dense sweep):
+//   0. gather  -- thread tid owns child event tid % STE and window share tid / STE, so a warp holds 32 consecutive
+//                 events; each lane copies its child's adjacency bit row (256-bit loads) into its OWN shared-memory
+//                 bank (word w of lane l at [w * 32 + l]) while the TMA transfer is in flight; one mbarrier covers both.
+//   1. filter  -- SG (2 or 4) threads per child event, each walking a contiguous share of the window most-recent-first,
+//                 eight probes per trip (node id -> row word -> bit, all bank-conflict free); hits go to a 64-bit mask.
+//   2. compact -- block exclusive scan of the hit counts -> contiguous, ordered segment per (event, share).
 //   3. evaluate-- all threads stride over the dense hit list: table gather (L2) + FP64 impulse.
-//   4. combine -- one thread per event folds its segment in window order: log-likelihood term, or the
+//   4. combine -- one thread per event folds its segments in window order: log-likelihood term, or the
 //                 inverse-cdf parent draw of parents.jl:25-46 (zero-weight entries can never be drawn and
 //                 do not move the cumulative sum, so skipping them is exact) + fused statistics.
 // Events whose window share exceeds the 64-bit mask, tiles with more hits than the list holds, and tiles
