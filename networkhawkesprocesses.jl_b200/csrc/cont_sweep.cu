@@ -450,6 +450,7 @@ static int fill_args(nhp_ctx *ctx, nhp_events *ev, int recursive, SweepArgs &a, 
 
 int nhp_cont_try_sparse(nhp_ctx *ctx, const nhp_events *ev, SweepArgs &a, int mode, int *grid_out);  // cont_sparse.cu
 int nhp_cont_try_child(nhp_ctx *ctx, nhp_events *ev, SweepArgs &a, int mode, int *grid_out);          // cont_child.cu
+int nhp_cont_try_exp_scan(nhp_ctx *ctx, nhp_events *ev, SweepArgs &a, int *grid_out);                  // cont_exp_scan.cu
 
 // sparse-adjacency sweep if it applies, else the child-major sweep for large tables; 1 = neither (time-tiled dense sweep)
 static int try_special(nhp_ctx *ctx, nhp_events *ev, SweepArgs &a, int mode, int *grid_out) {
@@ -465,7 +466,9 @@ int nhp_cont_run_loglik(nhp_ctx *ctx, nhp_events *ev, int recursive) {
     if (p.tiles == 0) { NHP_CUDA(ctx, cudaMemsetAsync(ctx->d_stats0, 0, 2 * sizeof(double), ctx->stream)); return NHP_OK; }
     NHP_TRY(nhp_partials(ctx, 2 * (int64_t)ctx->sm_count * 32, &a.partials));  // one partial per persistent CTA
     int sgrid = 0;
-    int sp = try_special(ctx, ev, a, 0, &sgrid);
+    // recursive Exponential on unsharded data: the chunked scan when it beats the cut-off window (cont_exp_scan.cu)
+    int sp = (recursive && ctx->kind == NHP_EXPONENTIAL) ? nhp_cont_try_exp_scan(ctx, ev, a, &sgrid) : 1;
+    if (sp == 1) sp = try_special(ctx, ev, a, 0, &sgrid);
     if (sp < 0) return sp;
     if (sp == NHP_OK) p.grid = sgrid;
     else if (ctx->kind == NHP_LOGITNORMAL) NHP_TRY((dispatch_sweep<NHP_LOGITNORMAL, MODE_LOGLIK>(ctx, p, a)));

@@ -231,3 +231,19 @@ def test_halo_shards_reproduce_unsharded():
     assert total == pytest.approx(ref, rel=1e-12)
     np.testing.assert_array_equal(np.concatenate(pars), par_ref)
     np.testing.assert_array_equal(Mnm, st_ref["Mnm"])
+
+
+@pytest.mark.parametrize("K,n,rate,density", [(2, 3000, 30.0, None), (12, 20000, 200.0, None), (12, 20000, 200.0, 0.4), (40, 30000, 500.0, None)])
+def test_recursive_exponential_chunked_scan_matches_oracle_recursion(K, n, rate, density, monkeypatch):
+    """recursive_loglikelihood (continuous.jl:241-276 / 407-442): the chunked-scan formulation (cont_exp_scan.cu, forced here)
+    and the cut-off-horizon window sweep both reproduce the oracle's sequential recursion, incl. events at t == 0 (quirk Q6)."""
+    proc, om = make_exp(K, 5, density=density, wmax=0.6 / K)
+    t, nodes, T = synth.poisson_stream(n, K, rate, 12)
+    t[:3] = 0.0  # leading events at exactly 0.0 never act as parents
+    ref = om.loglik(t, nodes, T, recursive=True)
+    d = proc.upload((t, nodes, T))
+    for mode in ("1", "0"):
+        monkeypatch.setenv("NHP_EXP_SCAN", mode)
+        assert nhp.loglikelihood(proc, d, recursive=True) == pytest.approx(ref, rel=LL_RTOL), mode
+    monkeypatch.delenv("NHP_EXP_SCAN")
+    assert nhp.loglikelihood(proc, d, recursive=True) == pytest.approx(ref, rel=LL_RTOL)
