@@ -203,17 +203,27 @@ static __device__ __noinline__ double slow_pair_ln(double cf, double mu, double 
     double la = log(dt), lb = log(D - dt), dz = (la - lb) - mu;
     return cf * exp(-h * dz * dz - (la + lb));
 }
+// x in [2^-500, 2^500)?  (one integer compare on the high word; products and squares of such values stay normal)
+__device__ __forceinline__ bool in_mid_range(double x) { return (unsigned)(__double2hiint(x) - 0x20B00000) < 0x3E800000u; }
+// 1/x for mid-range x: MUFU seed (20 bits) + two Newton steps (full double precision, ~1 ulp)
+__device__ __forceinline__ double fast_rcp_mid(double x) {
+    double y;
+    asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(x));
+    double e = fma(-x, y, 1.0);
+    y = fma(y, e, y);
+    e = fma(-x, y, 1.0);
+    return fma(y, e, y);
+}
 __device__ __forceinline__ double pair_value(const EntryLN &e, double dt, double D, const FastTables *ft) {
     // Distributions.pdf(LogitNormal(mu, tau^-1/2), dt/D): zero outside 0 < x < 1 (impulses.jl:174-178)
-    //   = cf exp(-h (z - mu)^2 - log dt - log(D - dt)),  z = log dt - log(D - dt),  cf carries D^2
+    //   = cf exp(-h (z - mu)^2) / (dt (D - dt)),  z = logit(dt/D) = log(dt / (D - dt)),  cf carries D^2.
+    // One reciprocal q = 1/(dt b) serves both the Jacobian and the logit argument dt/b = dt^2 q, so the pair costs one
+    // table-driven log and one exp (the two-log form needed a second shared-memory table look-up per pair).
     const double b = D - dt;
-    // dt and D - dt both positive normal  =>  0 < dt < D and both logs are on the table-driven path
-    if (is_pos_normal(dt) && is_pos_normal(b)) {
-        const double la = fast_log_n(dt, ft), lb = fast_log_n(b, ft);
-        const double dz = (la - lb) - e.mu;
-        const double arg = fma(-(e.h * dz), dz, -(la + lb));
-        if (__double2hiint(arg) >= 0x40862800) return e.cf * slow_exp(arg);  // arg >= 709 (or NaN): only for sub-1e-300 gaps
-        return e.cf * fast_exp_c(arg, ft);
+    if (in_mid_range(dt) && in_mid_range(b)) {  // => 0 < dt < D
+        const double q = fast_rcp_mid(dt * b);
+        const double dz = fast_log_n(dt * dt * q, ft) - e.mu;
+        return e.cf * q * fast_exp_c(-(e.h * dz) * dz, ft);  // the exponent is <= 0: no overflow branch
     }
     return slow_pair_ln(e.cf, e.mu, e.h, dt, D);
 }
