@@ -59,14 +59,17 @@ template <int KIND> __device__ __forceinline__ bool pair_terms(const GEntry &en,
     }
     const double b = D - dt;
     if (!(dt > 0.0 && b > 0.0)) return false;  // pdf is zero outside 0 < x < 1
-    double la, lb;
-    if (is_pos_normal(dt) && is_pos_normal(b)) { la = fast_log_n(dt, ft); lb = fast_log_n(b, ft); }
-    else { la = log(dt); lb = log(b); }
-    const double dz = (la - lb) - en.p1;
-    const double arg = fma(-(0.5 * en.p2) * dz, dz, -(la + lb));
-    const double ex = (__double2hiint(arg) >= 0x40862800) ? exp(arg) : fast_exp_c(arg, ft);
-    const double ha = en.c0 * ex * inv;  // a h / lambda_i
-    const double v = en.w * ha;          // a W h / lambda_i
+    double dz, pj;  // z - mu and the Jacobian 1 / (dt b), as pair_value(EntryLN)
+    if (in_mid_range(dt) && in_mid_range(b)) {
+        pj = fast_rcp_mid(dt * b);
+        dz = fast_log_n(dt * dt * pj, ft) - en.p1;
+    } else {
+        pj = 1.0 / (dt * b);
+        dz = (log(dt) - log(b)) - en.p1;
+    }
+    const double ex = fast_exp(-(0.5 * en.p2) * dz * dz, ft);
+    const double ha = en.c0 * pj * ex * inv;  // a h / lambda_i
+    const double v = en.w * ha;               // a W h / lambda_i
     tw = ha;
     t1 = v * en.p2 * dz;
     t2 = v * (0.5 / en.p2 - 0.5 * dz * dz);
