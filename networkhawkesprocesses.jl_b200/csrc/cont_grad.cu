@@ -200,6 +200,7 @@ extern "C" int nhp_cont_loglik_grad_dev(nhp_ctx *ctx, nhp_events *ev, int recurs
         const size_t lim = (size_t)ctx->smem_optin - 8192;
         size_t smem = (size_t)K * (sizeof(GEntry) + np * sizeof(double));
         ga.acc_smem = smem <= lim;
+        { const char *eg = getenv("NHP_GRAD_SMEM"); if (eg && atoi(eg) == 0) ga.acc_smem = 0; }  // A/B: accumulate with global RED.ADD.F64 instead
         if (!ga.acc_smem) smem = (size_t)K * sizeof(GEntry);
         NHP_CHECK(ctx, smem <= lim, NHP_ERR_INVALID, "nhp_cont_loglik_grad: K=%lld needs %zu bytes of shared memory per CTA (limit %zu)", (long long)K, smem, lim);
         NHP_TRY(nhp_partials(ctx, 2 * (int64_t)ctx->sm_count * 32, &ga.s.partials));

@@ -38,8 +38,8 @@ def _check_gamma(x, shape, rate, name, nsig=5.0):
     mean, var = shape / rate, shape / rate ** 2
     se = np.sqrt(var / x.shape[0])
     assert np.all(np.abs(x.mean(axis=0) - mean) < nsig * se + 1e-12), name
-    # variance of the sample variance of a Gamma: use a loose 35 % band at R = 600
-    assert np.all(np.abs(x.var(axis=0, ddof=1) / var - 1.0) < 0.35), name + " variance"
+    # sd of the sample-variance ratio is sqrt((2 + 6/shape) / R) <= 0.115 at R = 600: a 50 % band is > 4 sigma
+    assert np.all(np.abs(x.var(axis=0, ddof=1) / var - 1.0) < 0.5), name + " variance"
 
 
 def test_exponential_posterior_moments():
@@ -69,7 +69,7 @@ def test_logitnormal_posterior_moments():
     mun = (imp.kappamu * imp.mumu + m * X) / (imp.kappamu + m)
     var_mu = bb / ((imp.kappamu + m) * (a - 1.0))  # E[1 / (kappa tau)]
     assert np.all(np.abs(mu.mean(axis=0) - mun) < 5.0 * np.sqrt(var_mu / R)), "mu"
-    assert np.all(np.abs(mu.var(axis=0, ddof=1) / var_mu - 1.0) < 0.35), "mu variance"
+    assert np.all(np.abs(mu.var(axis=0, ddof=1) / var_mu - 1.0) < 0.5), "mu variance"
 
 
 def test_draws_are_keyed_by_seed_and_counter():
