@@ -367,11 +367,6 @@ extern "C" int nhp_disc_params_set(nhp_ctx *ctx, int64_t N, int64_t B, const dou
         DCUDA(ctx, cudaMalloc(&ctx->dd_A, (size_t)NN * sizeof(double)));
         DCUDA(ctx, cudaMalloc(&ctx->dd_theta, (size_t)(NN * B) * sizeof(double)));
         DCUDA(ctx, cudaMalloc(&ctx->dd_bump, (size_t)(2 * NB * N) * sizeof(double)));
-        cudaFree(ctx->dd_klist); cudaFree(ctx->dd_kptr); cudaFree(ctx->dd_btc);
-        ctx->dd_klist = ctx->dd_kptr = nullptr; ctx->dd_btc = nullptr;
-        DCUDA(ctx, cudaMalloc(&ctx->dd_klist, (size_t)(NB * N) * sizeof(int)));
-        DCUDA(ctx, cudaMalloc(&ctx->dd_kptr, (size_t)(N + 1) * sizeof(int)));
-        DCUDA(ctx, cudaMalloc(&ctx->dd_btc, (size_t)(NB * N) * sizeof(double)));
         ctx->dN = N; ctx->dB = B;
     }
     ctx->disc_set = false;
@@ -382,29 +377,39 @@ extern "C" int nhp_disc_params_set(nhp_ctx *ctx, int64_t N, int64_t B, const dou
     DCUDA(ctx, cudaMemcpyAsync(ctx->dd_theta, theta, (size_t)(NN * B) * sizeof(double), cudaMemcpyHostToDevice, s));
     k_bump<<<(unsigned)((NB * N + 255) / 256), 256, 0, s>>>((int)N, (int)B, ctx->dd_W, A ? ctx->dd_A : nullptr, ctx->dd_theta, dt, ctx->dd_bump, ctx->dd_bump + NB * N);
     NHP_LAUNCHED(ctx);
-    // compact per-child lists of the structurally non-zero (parent, basis) entries: k = p*B + b with [A]W[p,c] != 0
+    // compact per-child lists of the structurally non-zero (parent, basis) entries: k = p*B + b with [A]W[p,c] != 0.
+    // Built only for sparse effective weights (<= 50 % non-zero); dense models keep the full parent scan.
     {
-        std::vector<int> kptr(N + 1, 0), klist;
-        int64_t maxNA = 0;
-        for (int64_t c = 0; c < N; c++) {
-            kptr[c] = (int)klist.size();
-            for (int64_t pp = 0; pp < N; pp++) {
-                const double w = A ? A[pp + N * c] * W[pp + N * c] : W[pp + N * c];
-                if (w != 0.0) for (int64_t b = 0; b < B; b++) klist.push_back((int)(pp * B + b));
+        int64_t nnzw = 0;
+        for (int64_t e = 0; e < NN; e++) nnzw += ((A ? A[e] * W[e] : W[e]) != 0.0);
+        ctx->dd_density = (double)nnzw / (double)NN;
+        ctx->dd_maxNA = 0;
+        cudaFree(ctx->dd_klist); cudaFree(ctx->dd_kptr); cudaFree(ctx->dd_btc);
+        ctx->dd_klist = ctx->dd_kptr = nullptr; ctx->dd_btc = nullptr;
+        if (nnzw > 0 && ctx->dd_density <= 0.5) {
+            std::vector<int> kptr(N + 1, 0), klist;
+            klist.reserve((size_t)(nnzw * B));
+            int64_t maxNA = 0;
+            for (int64_t c = 0; c < N; c++) {
+                kptr[c] = (int)klist.size();
+                for (int64_t pp = 0; pp < N; pp++) {
+                    const double w = A ? A[pp + N * c] * W[pp + N * c] : W[pp + N * c];
+                    if (w != 0.0) for (int64_t b = 0; b < B; b++) klist.push_back((int)(pp * B + b));
+                }
+                maxNA = std::max<int64_t>(maxNA, (int64_t)klist.size() - kptr[c]);
             }
-            maxNA = std::max<int64_t>(maxNA, (int64_t)klist.size() - kptr[c]);
-        }
-        kptr[N] = (int)klist.size();
-        ctx->dd_density = (double)klist.size() / (double)(NB * N);
-        ctx->dd_maxNA = maxNA;
-        if (!klist.empty()) {
+            kptr[N] = (int)klist.size();
+            ctx->dd_maxNA = maxNA;
+            DCUDA(ctx, cudaMalloc(&ctx->dd_klist, klist.size() * sizeof(int)));
+            DCUDA(ctx, cudaMalloc(&ctx->dd_kptr, (size_t)(N + 1) * sizeof(int)));
+            DCUDA(ctx, cudaMalloc(&ctx->dd_btc, klist.size() * sizeof(double)));
             DCUDA(ctx, cudaMemcpyAsync(ctx->dd_kptr, kptr.data(), (size_t)(N + 1) * sizeof(int), cudaMemcpyHostToDevice, s));
             DCUDA(ctx, cudaMemcpyAsync(ctx->dd_klist, klist.data(), klist.size() * sizeof(int), cudaMemcpyHostToDevice, s));
             k_compact_bump<<<(unsigned)N, 256, 0, s>>>((int)NB, ctx->dd_bump + NB * N, ctx->dd_klist, ctx->dd_kptr, ctx->dd_btc);
             NHP_LAUNCHED(ctx);
+            DCUDA(ctx, cudaGetLastError());
+            DCUDA(ctx, cudaStreamSynchronize(s));  // kptr / klist are stack-owned host vectors
         }
-        DCUDA(ctx, cudaGetLastError());
-        DCUDA(ctx, cudaStreamSynchronize(s));  // kptr / klist are stack-owned host vectors
     }
     DCUDA(ctx, cudaGetLastError());
     DCUDA(ctx, cudaStreamSynchronize(s));
@@ -1276,6 +1281,10 @@ extern "C" int nhp_disc_resample_adjacency(nhp_ctx *ctx, nhp_disc *dd, const dou
         k_bump<<<(unsigned)((NB * N + 255) / 256), 256, 0, s>>>((int)N, (int)B, ctx->dd_W, ctx->dd_A, ctx->dd_theta, ctx->ddt, ctx->dd_bump, ctx->dd_bump + NB * N);
         NHP_LAUNCHED(ctx);
         DCUDA(ctx, cudaStreamSynchronize(s));
+        // the compact non-zero parent lists describe the old adjacency: drop them (dense parent scan until the next nhp_disc_params_set)
+        cudaFree(ctx->dd_klist); cudaFree(ctx->dd_kptr); cudaFree(ctx->dd_btc);
+        ctx->dd_klist = ctx->dd_kptr = nullptr; ctx->dd_btc = nullptr;
+        ctx->dd_maxNA = 0;
     }
     return NHP_OK;
 }

@@ -185,3 +185,29 @@ def test_time_shards_with_lag_halo_reproduce_unsharded():
     np.testing.assert_allclose(kappa, vb_ref["kappa_sum"], rtol=1e-11, atol=1e-13)
     np.testing.assert_allclose(alpha, vb_ref["alpha_sum"], rtol=1e-11)
     assert total == cnt_ref == data.sum()
+
+
+def test_gibbs_counts_after_adjacency_resample_use_the_new_adjacency():
+    """The C-ABI sequence resample_adjacency -> gibbs_counts without a parameter push in between must see the NEW links
+    (the compact parent lists of the old adjacency are dropped)."""
+    import ctypes
+    from nhp_b200.core import _fmat, _ptr
+    N, T, B, L = 10, 1500, 3, 5
+    rng = np.random.default_rng(3)
+    lam0 = rng.uniform(0.05, 0.15, N)
+    A = (rng.random((N, N)) < 0.2).astype(np.float64)
+    W, theta = rng.uniform(0.2 / N, 2.0 / N, (N, N)), rng.dirichlet(np.ones(B), (N, N))
+    data = rng.poisson(0.15, (N, T)).astype(np.int64)
+    proc = D.DiscreteNetworkHawkesProcess(D.DiscreteHomogeneousProcess(lam0), D.DiscreteGaussianImpulseResponse(theta, L), nhp.DenseWeightModel(W), A,
+                                          nhp.BernoulliNetworkModel(0.5, N))
+    d = proc.upload(data)
+    oconv = orc.disc_convolve(data, orc.disc_basis(L, B))
+    D.convolve(proc, d, export=False)
+    A_new = D.resample_adjacency_matrix_(proc, d, seed=4).copy()
+    assert not np.array_equal(A_new, A)
+    ctx = proc._ctx()
+    u = np.random.default_rng(8).random(int(data.sum()))
+    counts = np.empty(N * (1 + N * B))
+    ctx.check(ctx.lib.nhp_disc_gibbs_counts(ctx.h, d.h, 0, 0, _ptr(u), u.size, _ptr(counts)))  # no params_set in between
+    ref = orc.Disc(lam0, W, theta, dt=1.0, A=A_new).gibbs_counts(data, oconv, u)
+    assert np.array_equal(counts.reshape(1 + N * B, N).T, ref)
