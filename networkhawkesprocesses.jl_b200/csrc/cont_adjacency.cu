@@ -458,8 +458,14 @@ extern "C" int nhp_cont_resample_adjacency_cols(nhp_ctx *ctx, nhp_events *ev, co
     { int rc = nhp_events_build_node_index(ctx, ev); if (rc != NHP_OK) return fin(rc); }
     const char *envc = getenv("NHP_ADJ_CACHE");
     bool cached = n > 0 && !(envc && atoi(envc) == 0);
-    const double key = horizon + 1e-3 * (double)col_begin / (double)col_stride + 1e-6 * (double)col_stride;  // horizon and partition in one number
-    const bool have_cache = cached && ev->d_adj_i && ev->adj_horizon == key;
+    // The cached structure stays valid for any horizon it covers: extra pairs beyond the requested cut-off are genuine
+    // predecessors whose (tiny) contributions are simply included.  With a parameter-dependent horizon (Exponential cut-off,
+    // which moves with every conjugate draw) it is built with a 25 % margin so that a chain does not rebuild it every sweep.
+    const bool moving = ctx->kind == NHP_EXPONENTIAL && horizon < ctx->dtmax;
+    const bool have_cache = cached && ev->d_adj_i && ev->adj_cb == (int)col_begin && ev->adj_cs == (int)col_stride &&
+                            (moving ? (ev->adj_horizon >= horizon && ev->adj_horizon <= 2.0 * horizon) : ev->adj_horizon == horizon);
+    if (cached && !have_cache && moving) horizon = std::min(ctx->dtmax, 1.25 * horizon);
+    else if (have_cache) horizon = ev->adj_horizon;
     if (n > 0) {
         std::vector<double> mn(K);
         ADJ_CUDA(cudaMemcpyAsync(mn.data(), ev->d_Mn, K * sizeof(double), cudaMemcpyDeviceToHost, s));
@@ -515,7 +521,8 @@ extern "C" int nhp_cont_resample_adjacency_cols(nhp_ctx *ctx, nhp_events *ev, co
             ADJ_CUDA(cudaMemcpyAsync(&mb, d_cc, sizeof(mb), cudaMemcpyDeviceToHost, s));
             ADJ_CUDA(cudaStreamSynchronize(s));
             ADJ_CUDA(cudaGetLastError());
-            ev->adj_total = tot; ev->adj_max_bucket = (int64_t)mb; ev->adj_max_col = mc; ev->adj_horizon = key;
+            ev->adj_total = tot; ev->adj_max_bucket = (int64_t)mb; ev->adj_max_col = mc; ev->adj_horizon = horizon;
+            ev->adj_cb = (int)col_begin; ev->adj_cs = (int)col_stride;
             cudaMemGetInfo(&free_b, &total_b);
         }
     }

@@ -84,7 +84,8 @@ struct nhp_events {
     int64_t n_items = 0;
     // cached structure of the adjacency sampler (cont_adjacency.cu): every (child event, window predecessor) pair, grouped by child
     // column and bucketed by parent node; depends on the data and the look-back horizon only, so it survives across Gibbs sweeps
-    double adj_horizon = -1.0;
+    double adj_horizon = -1.0;       // horizon the structure was built with
+    int adj_cb = 0, adj_cs = 1;      // column partition it was built for
     unsigned *d_adj_i = nullptr;     // [adj_total] child event index inside its column | bit 31: the (event, parent) pair occurs more than once
     double *d_adj_dt = nullptr;      // [adj_total] t_i - t_j
     int *d_adj_boff = nullptr;       // [K][K+1] bucket offsets inside a column

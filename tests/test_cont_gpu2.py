@@ -118,3 +118,23 @@ def test_adjacency_column_partition_reproduces_full_sweep():
         merged[:, r::R] = part[:, r::R]
     np.testing.assert_array_equal(merged, full)
     np.testing.assert_array_equal(full, om.resample_adjacency(A0, np.full((K, K), 0.3), t, nodes, T, u))
+
+
+def test_adjacency_cache_survives_a_moving_exponential_horizon(monkeypatch):
+    """Exponential with dtmax = Inf: the cut-off horizon moves with the parameters, the cached pair structure (built with a
+    margin) is reused on one resident data handle, and the matrices still equal the oracle's (full history) given the uniforms."""
+    K, n, rho = 5, 900, 0.4
+    t, nodes, T = synth.poisson_stream(n, K, 15.0, 31)
+    proc, _ = make_exp(K, 7, density=0.5, wmax=1.5 / K)   # dtmax = Inf
+    proc.network = nhp.BernoulliNetworkModel(rho, K)
+    d = proc.upload((t, nodes, T))
+    A0 = proc.adjacency_matrix.copy()
+    theta0 = proc.impulses.theta.copy()
+    for rep, scale in enumerate((1.0, 1.1, 0.95, 1.3)):   # theta changes => horizon changes (within and beyond the margin)
+        proc.impulses.theta = theta0 * scale
+        proc.adjacency_matrix = A0.copy()
+        u = np.random.default_rng(200 + rep).random((K, K))
+        A_gpu = nhp.resample_adjacency_matrix_(proc, d, u=u).copy()
+        om = orc.Cont(0, proc.baseline.lam, proc.weights.W, proc.impulses.theta, A=A0, dtmax=np.inf)
+        A_ref = om.resample_adjacency(A0, np.full((K, K), rho), t, nodes, T, u)
+        assert np.array_equal(A_gpu, A_ref), rep
