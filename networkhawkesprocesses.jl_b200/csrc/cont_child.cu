@@ -21,6 +21,7 @@ struct ChildArgs {
     const int *item_e0;     // [nitems] first position in `order`
     int64_t nitems;
     int mode;               // 0 loglik, 1 intensity, 2 parents
+    const unsigned short *wlen;  // [n_own] cached window length per own event (65535 = saturated)
 };
 
 __global__ void k_child_iota(int *v, int64_t n, int first) {
@@ -28,14 +29,15 @@ __global__ void k_child_iota(int *v, int64_t n, int first) {
     if (i < n) v[i] = first + (int)i;
 }
 
-template <int KIND> __global__ void __launch_bounds__(NHP_BLOCK) k_child_sweep(const ChildArgs ca) {
+template <int KIND> __global__ void __launch_bounds__(1024) k_child_sweep(const ChildArgs ca) {
     typedef typename EntryOf<KIND>::type E;
     const SweepArgs &a = ca.s;
     extern __shared__ __align__(128) unsigned char smem[];
     __shared__ FastTables s_ft;
-    __shared__ double red[16];
+    __shared__ double red[64];
+    const int BS = blockDim.x;  // 256 .. 1024: as many warps per column as the column's shared-memory footprint leaves room for
     E *col = reinterpret_cast<E *>(smem);                                        // [K] table column of the current child
-    double *s_v = reinterpret_cast<double *>(smem + (size_t)a.K * sizeof(E));   // [CR * NHP_BLOCK] parent-sweep weight cache
+    double *s_v = reinterpret_cast<double *>(smem + (size_t)a.K * sizeof(E));   // [CR * BS] parent-sweep weight cache
     fast_tables_load(&s_ft);
     const FastTables *ft = &s_ft;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -50,14 +52,14 @@ template <int KIND> __global__ void __launch_bounds__(NHP_BLOCK) k_child_sweep(c
         if (c != cur) {
             __syncthreads();
             const E *src = reinterpret_cast<const E *>(a.table) + (size_t)c * a.K;
-            for (int k = threadIdx.x; k < a.K; k += NHP_BLOCK) col[k] = load_entry(src + k);
+            for (int k = threadIdx.x; k < a.K; k += BS) col[k] = load_entry(src + k);
             cur = c;
             __syncthreads();
         }
         const int e0 = ca.item_e0[item], e1 = min(e0 + CH_EVENTS, ca.node_ptr[c + 1]);
         const double lam0 = __ldg(a.lambda0 + c);
         int m0 = 0;
-        for (int e = e0 + warp; e < e1; e += NHP_BLOCK / 32) {
+        for (int e = e0 + warp; e < e1; e += BS / 32) {
             const int i = ca.order[e];
             const double ti = __ldg(a.t + i);
             const double thr = ti - a.horizon;
@@ -65,12 +67,26 @@ template <int KIND> __global__ void __launch_bounds__(NHP_BLOCK) k_child_sweep(c
             // pass 1: window weights, most recent first, lanes striding the window (coalesced stream reads)
             double acc = 0.0;
             int nr = 0;
-            for (int j = i - 1 - lane; j >= jlo; j -= 32, nr++) {
-                const double tj = __ldg(a.t + j);
-                if (!(tj > thr)) break;
-                const double v = pair_value(col[__ldg(a.c + j)], ti - tj, a.D, ft);
-                acc += v;
-                if (ca.mode == 2 && nr < CR) my_v[nr * NHP_BLOCK] = v;
+            const int wraw = (int)__ldg(ca.wlen + (i - a.first));
+            if (wraw < 65535) {
+                // window length known up front: no data-dependent exit, so the loads of several trips are in flight together
+                // (child events of one node are ~K events apart in the stream: every window is a cold DRAM read)
+                const int w = min(wraw, i - jlo);
+#pragma unroll 4
+                for (int k = lane; k < w; k += 32, nr++) {
+                    const int j = i - 1 - k;
+                    const double v = pair_value(col[__ldg(a.c + j)], ti - __ldg(a.t + j), a.D, ft);
+                    acc += v;
+                    if (ca.mode == 2 && nr < CR) my_v[nr * BS] = v;
+                }
+            } else {
+                for (int j = i - 1 - lane; j >= jlo; j -= 32, nr++) {
+                    const double tj = __ldg(a.t + j);
+                    if (!(tj > thr)) break;
+                    const double v = pair_value(col[__ldg(a.c + j)], ti - tj, a.D, ft);
+                    acc += v;
+                    if (ca.mode == 2 && nr < CR) my_v[nr * BS] = v;
+                }
             }
             const double S = warp_sum(acc) + lam0;
             if (ca.mode == 0) { if (lane == 0) { sum_log += log(S); sum_row += __ldg(a.rowsum + c); } }
@@ -85,7 +101,7 @@ template <int KIND> __global__ void __launch_bounds__(NHP_BLOCK) k_child_sweep(c
                 for (int r = 0; r < nrows; r++) {
                     double v = 0.0;
                     if (r < nr) {
-                        if (r < CR) v = my_v[r * NHP_BLOCK];
+                        if (r < CR) v = my_v[r * BS];
                         else {
                             const int jj = i - 1 - lane - r * 32;
                             v = pair_value(col[__ldg(a.c + jj)], ti - __ldg(a.t + jj), a.D, ft);
@@ -115,7 +131,7 @@ template <int KIND> __global__ void __launch_bounds__(NHP_BLOCK) k_child_sweep(c
         if (ca.mode == 2 && lane == 0 && m0) red_add_f64(a.stats + sl.off_M0() + c, (double)m0);
     }
     if (ca.mode == 0 || ca.mode == 2) {
-        block_sum2(sum_log, sum_row, red);
+        block_sum2_any(sum_log, sum_row, red);
         if (threadIdx.x == 0) { a.partials[2 * (size_t)blockIdx.x] = sum_log; a.partials[2 * (size_t)blockIdx.x + 1] = sum_row; }
     }
 }
@@ -173,7 +189,13 @@ int nhp_cont_try_child(nhp_ctx *ctx, nhp_events *ev, SweepArgs &a, int mode, int
     const bool force = env && atoi(env) == 1;
     const int64_t K = ctx->K, own = ev->n - ev->n_halo;
     const size_t esz = ctx->kind == NHP_LOGITNORMAL ? sizeof(EntryLN) : sizeof(EntryEX);
-    const size_t smem = (size_t)K * esz + (mode == 2 ? (size_t)CR * NHP_BLOCK * sizeof(double) : 0);
+    // threads per CTA: the column (K entries) is the CTA's fixed shared-memory cost, so large columns leave room for few CTAs
+    // per SM; give those CTAs more warps (the per-event window reads are cold DRAM: latency is hidden by warps in flight)
+    const size_t col_bytes = (size_t)K * esz;
+    const int fit = (int)std::max<size_t>(1, ((size_t)ctx->smem_optin - 8192) / std::max<size_t>(col_bytes, 1));
+    int block = fit >= 8 ? 256 : (fit >= 4 ? 512 : 1024);
+    { const char *eb = getenv("NHP_CHILD_BLOCK"); if (eb && (atoi(eb) == 256 || atoi(eb) == 512 || atoi(eb) == 1024)) block = atoi(eb); }
+    const size_t smem = col_bytes + (mode == 2 ? (size_t)CR * block * sizeof(double) : 0);
     if (smem > (size_t)ctx->smem_optin - 8192 || own == 0) return 1;
     // worthwhile when the table no longer sits comfortably in L2 and every column is amortised over enough pairs
     const bool big_table = (double)K * K * esz > 96e6;  // beyond L2 (126 MB): measured crossover (K = 1000 LN, 32 MB: time-tiled 5.1 ms vs child-major 7.7 ms per 1e7 events; K = 5000 Exp, 400 MB: 140 ms vs 61 ms per 2e7)
@@ -184,15 +206,15 @@ int nhp_cont_try_child(nhp_ctx *ctx, nhp_events *ev, SweepArgs &a, int mode, int
     NHP_CUDA(ctx, fast_tables_upload(ctx->stream));
     ChildArgs ca;
     ca.s = a; ca.order = ev->d_order; ca.node_ptr = ev->d_node_ptr; ca.item_node = ev->d_item_node; ca.item_e0 = ev->d_item_e0;
-    ca.nitems = ev->n_items; ca.mode = mode;
+    ca.nitems = ev->n_items; ca.mode = mode; ca.wlen = ev->d_wlen;
     auto launch = [&](auto kernel) -> int {
         if (smem > 32 * 1024) NHP_CUDA(ctx, cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));  // static + dynamic may exceed the 48 KB default
         NHP_CUDA(ctx, cudaFuncSetAttribute(kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
         int per_sm = 1;
-        NHP_CUDA(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, NHP_BLOCK, smem));
+        NHP_CUDA(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, block, smem));
         int grid = (int)std::min<int64_t>(ev->n_items, (int64_t)ctx->sm_count * std::max(per_sm, 1));
         *grid_out = grid;
-        kernel<<<grid, NHP_BLOCK, smem, ctx->stream>>>(ca);
+        kernel<<<grid, block, smem, ctx->stream>>>(ca);
         NHP_LAUNCHED(ctx);
         NHP_CUDA(ctx, cudaGetLastError());
         return NHP_OK;

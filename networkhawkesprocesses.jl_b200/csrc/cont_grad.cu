@@ -34,6 +34,7 @@ struct GradArgs {
     const double *lam;              // [n_own] total intensity at every own event (sweep 1)
     double *g_l0, *g_w, *g_p1, *g_p2;
     int acc_smem;                   // accumulators in shared memory (else straight to the global planes)
+    const unsigned short *wlen;     // [n_own] cached window length per own event (65535 = saturated)
 };
 
 template <int KIND> __device__ __forceinline__ GEntry make_entry(const GradArgs &ga, int64_t k, double D) {
@@ -76,11 +77,12 @@ template <int KIND> __device__ __forceinline__ bool pair_terms(const GEntry &en,
     return true;
 }
 
-template <int KIND> __global__ void __launch_bounds__(NHP_BLOCK) k_child_grad(const GradArgs ga) {
+template <int KIND> __global__ void __launch_bounds__(1024) k_child_grad(const GradArgs ga) {
     const SweepArgs &a = ga.s;
     extern __shared__ __align__(128) unsigned char smem[];
     __shared__ FastTables s_ft;
-    __shared__ double red[16];
+    __shared__ double red[64];
+    const int BS = blockDim.x;
     constexpr int NP = KIND == NHP_LOGITNORMAL ? 3 : 2;
     GEntry *col = reinterpret_cast<GEntry *>(smem);                                    // [K] raw parameters of column c
     double *acc = reinterpret_cast<double *>(smem + (size_t)a.K * sizeof(GEntry));    // [NP][K] when acc_smem
@@ -94,7 +96,7 @@ template <int KIND> __global__ void __launch_bounds__(NHP_BLOCK) k_child_grad(co
     auto flush = [&](int c) {  // accumulated columns -> global planes (several CTAs may share a child)
         if (!ga.acc_smem || c < 0) return;
         __syncthreads();
-        for (int k = threadIdx.x; k < a.K; k += NHP_BLOCK) {
+        for (int k = threadIdx.x; k < a.K; k += BS) {
             const int64_t o = k + (int64_t)a.K * c;
             double v = acc[k];
             if (v != 0.0) { red_add_f64(ga.g_w + o, v); acc[k] = 0.0; }
@@ -106,19 +108,19 @@ template <int KIND> __global__ void __launch_bounds__(NHP_BLOCK) k_child_grad(co
             }
         }
     };
-    if (ga.acc_smem) for (int k = threadIdx.x; k < NP * a.K; k += NHP_BLOCK) acc[k] = 0.0;
+    if (ga.acc_smem) for (int k = threadIdx.x; k < NP * a.K; k += BS) acc[k] = 0.0;
     for (int64_t item = it0; item < it1; item++) {
         const int c = ga.item_node[item];
         if (c != cur) {
             flush(cur);
             __syncthreads();
-            for (int k = threadIdx.x; k < a.K; k += NHP_BLOCK) col[k] = make_entry<KIND>(ga, k + (int64_t)a.K * c, a.D);
+            for (int k = threadIdx.x; k < a.K; k += BS) col[k] = make_entry<KIND>(ga, k + (int64_t)a.K * c, a.D);
             cur = c;
             __syncthreads();
         }
         const int e0 = ga.item_e0[item], e1 = min(e0 + GR_EVENTS, ga.node_ptr[c + 1]);
         double inv_sum = 0.0;
-        for (int e = e0 + warp; e < e1; e += NHP_BLOCK / 32) {
+        for (int e = e0 + warp; e < e1; e += BS / 32) {
             const int i = ga.order[e];
             const double ti = __ldg(a.t + i);
             const double thr = ti - a.horizon;
@@ -126,9 +128,13 @@ template <int KIND> __global__ void __launch_bounds__(NHP_BLOCK) k_child_grad(co
             const double lam = __ldg(ga.lam + (i - a.first));
             const double inv = 1.0 / lam;
             if (lane == 0) { sum_log += log(lam); inv_sum += inv; }
-            for (int j = i - 1 - lane; j >= jlo; j -= 32) {
+            const int wraw = (int)__ldg(ga.wlen + (i - a.first));
+            const int w = wraw < 65535 ? min(wraw, i - jlo) : i - jlo;  // known trip count: loads of several trips in flight
+#pragma unroll 2
+            for (int k = lane; k < w; k += 32) {
+                const int j = i - 1 - k;
                 const double tj = __ldg(a.t + j);
-                if (!(tj > thr)) break;
+                if (wraw >= 65535 && !(tj > thr)) break;
                 const int p = __ldg(a.c + j);
                 double tw, t1, t2;
                 if (!pair_terms<KIND>(col[p], ti - tj, a.D, inv, ft, tw, t1, t2)) continue;
@@ -147,7 +153,7 @@ template <int KIND> __global__ void __launch_bounds__(NHP_BLOCK) k_child_grad(co
         if (lane == 0 && inv_sum != 0.0) red_add_f64(ga.g_l0 + c, inv_sum);
     }
     flush(cur);
-    block_sum2(sum_log, sum_row, red);
+    block_sum2_any(sum_log, sum_row, red);
     if (threadIdx.x == 0) { a.partials[2 * (size_t)blockIdx.x] = sum_log; a.partials[2 * (size_t)blockIdx.x + 1] = 0.0; }
 }
 
@@ -195,7 +201,7 @@ extern "C" int nhp_cont_loglik_grad_dev(nhp_ctx *ctx, nhp_events *ev, int recurs
         GradArgs ga;
         ga.s = a; ga.order = ev->d_order; ga.node_ptr = ev->d_node_ptr; ga.item_node = ev->d_item_node; ga.item_e0 = ev->d_item_e0; ga.nitems = ev->n_items;
         ga.W = ctx->d_W; ga.A = ctx->has_A ? ctx->d_A : nullptr; ga.p1 = ctx->d_p1; ga.p2 = ctx->d_p2; ga.lam = (const double *)scratch;
-        ga.g_l0 = g_l0; ga.g_w = g_w; ga.g_p1 = g_p1; ga.g_p2 = g_p2;
+        ga.g_l0 = g_l0; ga.g_w = g_w; ga.g_p1 = g_p1; ga.g_p2 = g_p2; ga.wlen = ev->d_wlen;
         const int np = ctx->kind == NHP_LOGITNORMAL ? 3 : 2;
         const size_t lim = (size_t)ctx->smem_optin - 8192;
         size_t smem = (size_t)K * (sizeof(GEntry) + np * sizeof(double));
@@ -209,9 +215,11 @@ extern "C" int nhp_cont_loglik_grad_dev(nhp_ctx *ctx, nhp_events *ev, int recurs
             if (smem > 32 * 1024) NHP_CUDA(ctx, cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
             NHP_CUDA(ctx, cudaFuncSetAttribute(kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
             int per_sm = 1;
-            NHP_CUDA(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, NHP_BLOCK, smem));
+            const int fit = (int)std::max<size_t>(1, lim / std::max<size_t>(smem, 1));
+            const int block = fit >= 8 ? 256 : (fit >= 4 ? 512 : 1024);  // big columns leave room for few CTAs per SM: give them more warps
+            NHP_CUDA(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, block, smem));
             grid = (int)std::min<int64_t>(ev->n_items, (int64_t)ctx->sm_count * std::max(per_sm, 1));
-            kernel<<<grid, NHP_BLOCK, smem, s>>>(ga);
+            kernel<<<grid, block, smem, s>>>(ga);
             NHP_LAUNCHED(ctx);
             NHP_CUDA(ctx, cudaGetLastError());
             return NHP_OK;

@@ -228,6 +228,19 @@ __device__ __forceinline__ double warp_sum(double v) {
     return v;
 }
 // deterministic block reduction of two accumulators; result valid in thread 0
+// the same for any CTA size up to 1024 threads (red: [64] smem)
+__device__ __forceinline__ void block_sum2_any(double &x, double &y, double *red) {
+    x = warp_sum(x);
+    y = warp_sum(y);
+    const int w = threadIdx.x >> 5, l = threadIdx.x & 31, nw = blockDim.x >> 5;
+    if (l == 0) { red[w] = x; red[32 + w] = y; }
+    __syncthreads();
+    if (w == 0) {
+        double xs = l < nw ? red[l] : 0.0, ys = l < nw ? red[32 + l] : 0.0;
+        x = warp_sum(xs);
+        y = warp_sum(ys);
+    }
+}
 __device__ __forceinline__ void block_sum2(double &x, double &y, double *red /* [16] smem */) {
     x = warp_sum(x);
     y = warp_sum(y);
