@@ -101,3 +101,25 @@ def test_discrete_params_layout():
     x = p.params()  # [lambda0; vec(W .* theta)]  discrete.jl:174-182
     assert x.size == 2 + 12
     assert x[2 + 1] == pytest.approx(W[1, 0] * th[1, 0, 0])
+
+
+@pytest.mark.parametrize("kind", ["ln", "exp"])
+def test_gradient_vector_follows_params_order(kind):
+    """gradient_vector flattens d/d(lambda0, impulse params, W) in the order of params(process) (continuous.jl:116-119), so
+    x + eps * gradient_vector(...) perturbs exactly the entries the gradient belongs to."""
+    from nhp_b200.continuous import gradient_vector, _hyper
+    K = 3
+    p = _std(K, kind)
+    rng = np.random.default_rng(2)
+    g = dict(lambda0=rng.normal(size=K), W=rng.normal(size=(K, K)), p1=rng.normal(size=(K, K)), p2=rng.normal(size=(K, K)) if kind == "ln" else None)
+    v = gradient_vector(p, g)
+    assert v.size == p.params().size
+    q = _std(K, kind)
+    q.params_(v)  # reading the flattened gradient back through params_ must put every block where it came from
+    np.testing.assert_array_equal(q.baseline.lam, g["lambda0"])
+    np.testing.assert_array_equal(q.weights.W, g["W"])
+    np.testing.assert_array_equal(q.impulses.p1(), g["p1"])
+    if kind == "ln":
+        np.testing.assert_array_equal(q.impulses.p2(), g["p2"])
+    h = _hyper(p)  # [alpha0, beta0, kappa, nu, impulse hyper-parameters] as nhp_cont_resample_params expects
+    assert h.size == (8 if kind == "ln" else 6) and np.all(h[:4] == [p.baseline.alpha0, p.baseline.beta0, p.weights.kappa, p.weights.nu])
