@@ -159,3 +159,18 @@ def test_gradient_oracle_matches_finite_differences(kind, network, recursive):
     ana = np.concatenate([g0, gW.ravel(), g1.ravel()] + ([] if p2 is None else [g2.ravel()]))
     num = _fd_grad(make, x0, lambda m: m.loglik(ev, nd, T, recursive=recursive))
     np.testing.assert_allclose(ana, num, rtol=2e-6, atol=2e-6)
+
+
+def test_gradient_oracle_closed_form_two_events():
+    """K = 1, two events at t = 1, 2, Exponential impulse: lambda_2 = lambda0 + W theta exp(-theta);
+    ll = log lambda0 + log lambda_2 - lambda0 T - 2 W (the compensator counts W once per event, continuous.jl:219-221)."""
+    lam0, W, th, T = 0.7, 0.4, 1.3, 5.0
+    om = orc.Cont(0, np.array([lam0]), np.array([[W]]), np.array([[th]]))
+    ev, nd = np.array([1.0, 2.0]), np.array([1, 1])
+    l2 = lam0 + W * th * np.exp(-th)
+    for rec in (True, False):
+        ll, g0, gW, g1, _ = om.loglik_grad(ev, nd, T, recursive=rec)
+        assert ll == pytest.approx(np.log(lam0) + np.log(l2) - lam0 * T - 2 * W, rel=1e-14)
+        assert g0[0] == pytest.approx(1 / lam0 + 1 / l2 - T, rel=1e-14)
+        assert gW[0, 0] == pytest.approx(th * np.exp(-th) / l2 - 2.0, rel=1e-14)
+        assert g1[0, 0] == pytest.approx(W * np.exp(-th) * (1 - th) / l2, rel=1e-14)
