@@ -123,3 +123,18 @@ def test_gradient_null_outputs_and_state():
     nhp.resample_parents(proc, d, seed=1)
     with pytest.raises(nhp.NHPError):
         ctx.check(ctx.lib.nhp_cont_loglik_grad_read(ctx.h, d.h, ctypes.byref(ll), None, None, None, None))
+
+
+def test_gradient_closed_form_two_events():
+    """Same known answer as tests/test_oracle.py::test_gradient_oracle_closed_form_two_events, through the C ABI."""
+    lam0, W, th, T = 0.7, 0.4, 1.3, 5.0
+    proc = nhp.ContinuousStandardHawkesProcess(nhp.HomogeneousProcess(np.array([lam0])), nhp.ExponentialImpulseResponse(np.array([[th]])),
+                                               nhp.DenseWeightModel(np.array([[W]])))
+    data = (np.array([1.0, 2.0]), np.array([1, 1]), T)
+    l2 = lam0 + W * th * np.exp(-th)
+    for rec in (True, False):
+        ll, g = nhp.loglikelihood_gradient(proc, data, recursive=rec)
+        assert ll == pytest.approx(np.log(lam0) + np.log(l2) - lam0 * T - 2 * W, rel=1e-12)
+        assert g["lambda0"][0] == pytest.approx(1 / lam0 + 1 / l2 - T, rel=1e-12)
+        assert g["W"][0, 0] == pytest.approx(th * np.exp(-th) / l2 - 2.0, rel=1e-12)
+        assert g["p1"][0, 0] == pytest.approx(W * np.exp(-th) * (1 - th) / l2, rel=1e-12)
