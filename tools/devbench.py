@@ -1,4 +1,13 @@
-"""Developer micro-benchmark (not the driver's bench.py): times the continuous sweeps on synthetic streams."""
+"""Developer micro-benchmark (not the driver's bench.py): times single entry points on synthetic streams.
+
+modes:  main | all | g                      dense / sparse / exponential sweeps at the config-2 / config-4 shapes
+        one K n rate density [kind] [reps]  one shape
+        cfg5 n | cfg1                       config-5 shape log-likelihood; README example latency (vs the oracle)
+        grad kind K n rate [density]        log-likelihood + analytic gradient
+        mcmc K n rate density nsweeps       full Gibbs sweeps, host draws vs device draws
+        adj K n rate density                adjacency sampler
+        disc N T B L rate                   discrete path (convolve, contraction, Gibbs, VB, adjacency)
+        query K n rate nq | upload | peaks  intensity at query times; upload; roofline micro-benchmarks"""
 import os
 import sys
 import time
