@@ -45,8 +45,6 @@ int nhp_create(int device, nhp_ctx **out);
 int nhp_destroy(nhp_ctx *ctx);
 const char *nhp_last_error(const nhp_ctx *ctx); /* ctx may be NULL: last error of a failed nhp_create */
 int nhp_version(void);
-/* kernels launched by this context since creation (bench.py's gpu_launches claim) */
-int64_t nhp_launch_count(const nhp_ctx *ctx);
 /* device-time (CUDA events on the context stream) of the kernels of the most recent call, ms */
 double nhp_last_kernel_ms(const nhp_ctx *ctx);
 
@@ -57,14 +55,6 @@ int nhp_set_option(nhp_ctx *ctx, int option, int64_t value);
  * void*; NULL restores the context's own stream), e.g. torch.cuda.current_stream().cuda_stream so
  * that the caller's CUDA events and NCCL collectives order with the library's kernels. */
 int nhp_set_stream(nhp_ctx *ctx, void *cuda_stream);
-/* Roofline denominators measured on this device: which = 0 FP64 FMA peak [TFLOP/s],
- * 1 LogitNormal / 2 Exponential register-resident impulse evaluations [pairs/s], 3 FP64 tensor-core
- * (mma.sync m8n8k4.f64) peak [TFLOP/s]. */
-int nhp_bench_fp64(nhp_ctx *ctx, int which, double *result);
-/* Test hook for the table-driven FP64 log (which = 0) / exp (which = 1) the impulse evaluation uses:
- * out[i] = f(x[i]), host pointers. */
-int nhp_test_fastmath(nhp_ctx *ctx, int which, const double *x, int64_t n, double *out);
-
 /* ---- continuous data: data = (events, nodes, duration) of continuous.jl:14 ------------- */
 /* Upload once; mle!/mcmc! call the likelihood thousands of times on the same data
  * (continuous.jl:146-149, inference.jl:55-62).
@@ -151,6 +141,18 @@ int nhp_cont_resample_adjacency(nhp_ctx *ctx, nhp_events *ev, const double *rho,
  * owned columns (allgather / masked allreduce).  col_begin = 0, col_stride = 1 is the full sweep. */
 int nhp_cont_resample_adjacency_cols(nhp_ctx *ctx, nhp_events *ev, const double *rho, uint64_t seed, uint64_t counter,
                                      const double *u, double *A_inout, int64_t col_begin, int64_t col_stride);
+/* Device-resident form for chains (`resample!` of a network process, continuous.jl:350-358, without the K^2 matrices crossing
+ * PCIe): the sweep runs in place on the context's adjacency matrix with the scalar link probability `rho` of a
+ * BernoulliNetworkModel (networks.jl:65-68; rho < 0: the value kept by nhp_cont_network_set / nhp_cont_resample_network) and
+ * Philox uniforms.  commit != 0 rebuilds the masked tables afterwards; a multi-GPU caller passes 0, exchanges the owned
+ * columns (nhp_comm_allgather_adjacency) and commits once. */
+int nhp_cont_resample_adjacency_dev(nhp_ctx *ctx, nhp_events *ev, double rho, uint64_t seed, uint64_t counter, int64_t col_begin,
+                                    int64_t col_stride, int commit);
+int nhp_cont_adjacency_commit(nhp_ctx *ctx);
+/* resample!(network::BernoulliNetworkModel, data)  networks.jl:72-78: rho ~ Beta(alpha + sum(A), beta + K^2 - sum(A)) from the
+ * device-resident adjacency matrix (Philox: seed, counter); the value stays with the context and is returned in *rho_out. */
+int nhp_cont_network_set(nhp_ctx *ctx, double rho);
+int nhp_cont_resample_network(nhp_ctx *ctx, uint64_t seed, uint64_t counter, double alpha, double beta, double *rho_out);
 
 /* Device-side conjugate draws of one Gibbs sweep (the `resample!` of baseline, weights and impulses:
  * baselines.jl:72-77, weights.jl:59-64, impulses.jl:68-73 / 204-214) from the statistics of the last parent sweep,

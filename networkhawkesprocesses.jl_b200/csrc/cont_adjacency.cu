@@ -7,17 +7,25 @@
 //     ll1 - ll0 = -W[p,c] n_p + sum_{i on c, G_i[p] > 0} [ log(lambda_i^{-p} + G_i[p]) - log(lambda_i^{-p}) ]
 //                 + log rho - log(1 - rho),          A[p,c] ~ Bernoulli(exp(ll1 - logsumexp(ll0, ll1))),
 // p = 1..K sequentially inside a column, columns independent (the reference's Threads.@threads axis).
-// One CTA owns a column: (A) it walks the windows of the column's child events once and buckets the
-// (event, G) entries by parent node in a per-CTA scratch area (counting sort, shared-memory
-// histogram), (B) then runs the K sequential Bernoulli steps, each a block-wide reduction over one
-// bucket.  Same conditional distribution, O(N w) work per sweep instead of O(K^2 N).
+// Same conditional distribution, O(N w) work per sweep instead of O(K^2 N).
 //
-// Cached variant (default when it fits in memory): the bucketed structure -- which (child event, window predecessor) pairs
-// exist, grouped by column and parent node, with their lags t_i - t_j -- depends on the data and the look-back horizon only.
-// It is built once per events handle (k_adj_build: 12 B per pair) and every sweep then streams it (k_adj_sweep): the
-// impulse value of an entry is evaluated on the fly with the (p, c) parameters held in registers for the whole bucket,
-// there is no per-sweep bucketing, no scattered entry writes and no table gather.  (event, parent) pairs that occur once
-// (almost all of them) skip the duplicate-aggregation pass through a flag set at build time.
+// Cached form (default; k_adj_build + k_adj_sweep).  WHICH (child event, window predecessor) pairs exist, and their
+// lags, depends on the data and the look-back horizon only, so the pairs are bucketed once per events handle:
+//   virtual column = (child column c, time chunk g of at most `chunk_cap` of the column's events), buckets by parent
+//   node p inside it, entries stably ordered by (child event, window position); 10 B per pair (u16 event index inside
+//   the chunk + f64 lag); entries of one (event, parent) that repeat sit next to each other, flagged.
+// A Gibbs sweep streams that structure.  One 1024-thread CTA owns a column at a time and keeps the intensities
+// lambda_i of the current chunk in SHARED MEMORY (up to 26 624 events = 208 KB), so the per-entry gather that bound the
+// first version (one DRAM sector per entry, profiles/r02_adjacency.md) is an LDS.  The K sequential Bernoulli steps
+// are run speculatively in batches of S <= 32 buckets: a step only changes lambda when its link flips, which is
+// rare once a chain has mixed, so the S sums are evaluated in parallel (a group of 32/S warps per bucket) from the
+// current lambda, the decisions are then taken in order, and the first flip (if any) is applied and the batch
+// restarts behind it (S halves after a flip, doubles after a clean batch).  The result is exactly that of the sequential
+// sweep.  The log terms are accumulated as products (one log per lane and batch instead of one per entry).
+// Columns larger than one chunk keep lambda in global memory between batches and stream their chunks per batch.
+// Everything is order-deterministic: no atomics, fixed reduction trees.
+//
+// Uncached form (k_adjacency): the structure is re-bucketed inside every sweep; used when it does not fit in memory.
 #include "cont_sweep.cuh"
 int nhp_cont_params_refresh(nhp_ctx *ctx);  // cont_conjugate.cu
 #include <cub/cub.cuh>
@@ -127,7 +135,7 @@ template <int KIND> __global__ void __launch_bounds__(256) k_adjacency(const Adj
                     if (v > 0.0) {
                         const int ii = ent_i[e];
                         const double g = gacc[ii], l = lam[ii];
-                        const double base = a_old != 0.0 ? l - g : l;
+                        const double base = a_old != 0.0 ? fmax(l - g, lam0) : l;  // the other parents' share is at least lambda0
                         const double term = log((base + g) / base);
                         part += (v == g) ? term : term * (v / g);
                     }
@@ -172,219 +180,366 @@ template <int KIND> __global__ void __launch_bounds__(256) k_adjacency(const Adj
 // ---------------------------------------------------------------------------------------
 // cached structure: build once, sweep many times
 // ---------------------------------------------------------------------------------------
-constexpr int ADJ_WMAX = 256;  // window entries per event checked exactly for repeated parents (longer windows: all flagged)
+constexpr int ADJ_CHUNK_MAX = 26624;   // child events per chunk: 208 KB of shared-memory intensities
+constexpr int ADJ_THREADS = 1024;      // sweep CTA: one per SM
+constexpr int ADJ_SMAX = 32, ADJ_SMIN = 4;  // speculative batch size (buckets per batch): halves after a flip, doubles after a clean batch
+
+// a column's ne child events are split into G chunks of this many events (the last one may be shorter)
+__host__ __device__ inline int adj_chunk_size(int ne, int G) { return G > 0 ? (ne + G - 1) / G : 0; }
+
+// entries per virtual column: every child event adds its window length
+__global__ void k_adj_count(const double *__restrict__ t, const int *__restrict__ c, const int *__restrict__ order, const int *__restrict__ node_ptr,
+                            const int *__restrict__ vstart, int64_t n_own, double horizon, int cb, int cs, unsigned long long *__restrict__ vcount) {
+    const int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (e >= n_own) return;
+    const int i = order[e], col = c[i];
+    if (col % cs != cb) return;
+    const int le = (int)(e - node_ptr[col]), ne = node_ptr[col + 1] - node_ptr[col], G = vstart[col + 1] - vstart[col];
+    const int v = vstart[col] + le / adj_chunk_size(ne, G);
+    const int lo = lo_of_event(t, i, horizon);
+    if (i > lo) atomicAdd(&vcount[v], (unsigned long long)(i - lo));
+}
 
 struct AdjBuildArgs {
-    const double *t; const int *c;
-    const int *order, *node_ptr;
+    const double *t; const int *c; const int *order, *node_ptr;
     int K; double horizon;
-    const int64_t *col;      // [K+1] first entry of every column
-    int *boff;               // [K][K+1]
-    unsigned *ent_i; double *ent_dt;
-    int col_begin, col_stride;
+    const int *vstart, *vnode; const int64_t *vbase;
+    int *boff; unsigned short *ent_i; double *ent_dt;
+    int nv, nw;      // virtual columns; warps per CTA
+    int *next, *flag;
 };
 
-__global__ void __launch_bounds__(256) k_adj_build(const AdjBuildArgs a) {
-    extern __shared__ int s_dyn[];  // [K+1] bucket offsets, [K] cursors, [8][ADJ_WMAX] window nodes per warp
-    int *s_off = s_dyn, *s_cur = s_dyn + a.K + 1, *s_win = s_dyn + 2 * a.K + 2;
-    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5, nw = blockDim.x >> 5;
-    int *win = s_win + wid * ADJ_WMAX;
-    for (int c = a.col_begin + blockIdx.x * a.col_stride; c < a.K; c += gridDim.x * a.col_stride) {
-        const int e0 = a.node_ptr[c], e1 = a.node_ptr[c + 1];
-        unsigned *ent_i = a.ent_i + a.col[c];
-        double *ent_dt = a.ent_dt + a.col[c];
-        for (int k = threadIdx.x; k <= a.K; k += blockDim.x) s_off[k] = 0;
+// Stable counting sort of one virtual column's (child event, window predecessor) pairs by parent node.  Warp w owns a contiguous
+// range of the chunk's events and private per-parent cursors, so a bucket is ordered by (event, window position) whatever the
+// scheduling; entries of one (event, parent) are adjacent and all but the first carry the continuation bit.
+__global__ void __launch_bounds__(512) k_adj_build(const AdjBuildArgs a) {
+    extern __shared__ int s_dyn[];
+    __shared__ int s_v;
+    const int K = a.K, nw = a.nw;
+    int *s_off = s_dyn;                                           // [K+1] bucket offsets
+    unsigned *s_w = reinterpret_cast<unsigned *>(s_dyn + K + 1);  // per warp: cur[K], cnt[K], run[K]
+    const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+    unsigned *cur = s_w + (size_t)wid * 3 * K, *cnt = cur + K, *run = cnt + K;
+    const unsigned lt = (1u << lane) - 1u;
+    for (int k = tid; k < nw * 3 * K; k += blockDim.x) s_w[k] = 0u;
+    for (;;) {
         __syncthreads();
-        for (int e = e0 + wid; e < e1; e += nw) {
+        if (tid == 0) s_v = atomicAdd(a.next, 1);
+        __syncthreads();
+        const int v = s_v;
+        if (v >= a.nv) break;
+        const int col = a.vnode[v], g = v - a.vstart[col], G = a.vstart[col + 1] - a.vstart[col];
+        const int ne = a.node_ptr[col + 1] - a.node_ptr[col], csz = adj_chunk_size(ne, G);
+        const int eb = a.node_ptr[col] + g * csz, ee = min(a.node_ptr[col] + ne, eb + csz);  // positions in the by-node order
+        const int per = (ee - eb + nw - 1) / nw;
+        const int ws = min(ee, eb + wid * per), we = min(ee, ws + per);
+        for (int k = lane; k < K; k += 32) cur[k] = 0u;
+        __syncwarp();
+        // ---- A: per-(warp, parent) counts
+        for (int e = ws; e < we; e++) {
             const int i = a.order[e];
-            const double thr = a.t[i] - a.horizon;
-            for (int j = i - 1 - lane; j >= 0; j -= 32) {
-                if (!(__ldg(a.t + j) > thr)) break;
-                atomicAdd(&s_off[__ldg(a.c + j) + 1], 1);
+            const int wl = i - lo_of_event(a.t, i, a.horizon);
+            for (int r0 = 0; r0 < wl; r0 += 32) {
+                const int k = r0 + lane;
+                const bool valid = k < wl;
+                const int p = valid ? __ldg(a.c + (i - 1 - k)) : -1;
+                const unsigned m = __match_any_sync(0xffffffffu, p);
+                if (valid && lane == __ffs(m) - 1) cur[p] += __popc(m);
+                __syncwarp();
             }
         }
         __syncthreads();
-        if (threadIdx.x == 0) {
-            int run = 0;
-            for (int k = 0; k < a.K; k++) { int v = s_off[k + 1]; s_off[k] = run; s_cur[k] = run; run += v; }
-            s_off[a.K] = run;
+        // ---- bucket offsets; every warp's cursor starts behind the earlier warps' entries of the same parent
+        for (int p = tid; p < K; p += blockDim.x) {
+            unsigned r = 0;
+            for (int w = 0; w < nw; w++) { unsigned *cw = s_w + (size_t)w * 3 * K; const unsigned x = cw[p]; cw[p] = r; r += x; }
+            s_off[p + 1] = (int)r;
+        }
+        if (tid == 0) s_off[0] = 0;
+        __syncthreads();
+        if (tid == 0) {
+            int r = 0;
+            for (int p = 0; p < K; p++) { r += s_off[p + 1]; s_off[p + 1] = r; }
+            if ((int64_t)r != a.vbase[v + 1] - a.vbase[v]) atomicOr(a.flag, 128);
         }
         __syncthreads();
-        for (int k = threadIdx.x; k <= a.K; k += blockDim.x) a.boff[(int64_t)c * (a.K + 1) + k] = s_off[k];
-        for (int e = e0 + wid; e < e1; e += nw) {
+        for (int p = tid; p <= K; p += blockDim.x) a.boff[(int64_t)v * (K + 1) + p] = s_off[p];
+        for (int p = tid; p < K; p += blockDim.x)
+            for (int w = 0; w < nw; w++) s_w[(size_t)w * 3 * K + p] += (unsigned)s_off[p];
+        __syncthreads();
+        // ---- B: scatter
+        unsigned short *ei = a.ent_i + a.vbase[v];
+        double *ed = a.ent_dt + a.vbase[v];
+        for (int e = ws; e < we; e++) {
             const int i = a.order[e];
-            const double ti = a.t[i], thr = ti - a.horizon;
-            // the window's parent nodes into the warp's buffer (as far as it reaches) for the exact repeat check
-            int wl = 0;
-            for (int j0 = i - 1; j0 >= 0; j0 -= 32) {
-                const int j = j0 - lane;
-                const bool in = j >= 0 && __ldg(a.t + j) > thr;
-                const int p = in ? __ldg(a.c + j) : -1;
-                if (wl + lane < ADJ_WMAX) win[wl + lane] = p;
-                const unsigned m = __ballot_sync(0xffffffffu, in);
-                wl += __popc(m);
-                if (m != 0xffffffffu) break;
+            const double ti = a.t[i];
+            const int wl = i - lo_of_event(a.t, i, a.horizon);
+            const unsigned le = (unsigned)(e - eb);
+            for (int r0 = 0; r0 < wl; r0 += 32) {  // multiplicity of every parent node in this window
+                const int k = r0 + lane;
+                const bool valid = k < wl;
+                const int p = valid ? __ldg(a.c + (i - 1 - k)) : -1;
+                const unsigned m = __match_any_sync(0xffffffffu, p);
+                if (valid && lane == __ffs(m) - 1) cnt[p] += __popc(m);
+                __syncwarp();
             }
-            __syncwarp();
-            const bool exact = wl <= ADJ_WMAX;
-            for (int k = lane; k < wl; k += 32) {
-                const int j = i - 1 - k;
-                const int p = __ldg(a.c + j);
-                bool dup = !exact;
-                if (exact) for (int m = 0; m < wl; m++) dup |= (m != k) & (win[m] == p);
-                const int pos = atomicAdd(&s_cur[p], 1);
-                ent_i[pos] = (unsigned)(e - e0) | (dup ? 0x80000000u : 0u);
-                ent_dt[pos] = ti - __ldg(a.t + j);
+            for (int r0 = 0; r0 < wl; r0 += 32) {  // positions: the (event, parent) run is contiguous, window order inside it
+                const int k = r0 + lane;
+                const bool valid = k < wl;
+                const int p = valid ? __ldg(a.c + (i - 1 - k)) : -1;
+                const unsigned m = __match_any_sync(0xffffffffu, p);
+                const unsigned rank = __popc(m & lt);
+                const unsigned seen = valid ? run[p] : 0u;
+                __syncwarp();
+                if (valid) {
+                    const unsigned pos = cur[p] + seen + rank;
+                    ei[pos] = (unsigned short)(le | ((seen + rank) ? 0x8000u : 0u));
+                    ed[pos] = ti - __ldg(a.t + (i - 1 - k));
+                    if (lane == __ffs(m) - 1) run[p] = seen + __popc(m);
+                }
+                __syncwarp();
             }
-            __syncwarp();
+            for (int r0 = 0; r0 < wl; r0 += 32) {  // advance the cursors, clear the per-event counters
+                const int k = r0 + lane;
+                const bool valid = k < wl;
+                const int p = valid ? __ldg(a.c + (i - 1 - k)) : -1;
+                const unsigned m = __match_any_sync(0xffffffffu, p);
+                if (valid && lane == __ffs(m) - 1 && cnt[p]) { cur[p] += cnt[p]; cnt[p] = 0u; run[p] = 0u; }
+                __syncwarp();
+            }
         }
-        __syncthreads();
     }
 }
 
 struct AdjSweepArgs {
     const int *node_ptr; const double *Mn;
     int K; const void *table_w;
-    const double *lambda0; const double *W; double *A;
-    const double *rho; const double *u; uint64_t seed, counter;
+    const double *lambda0; const double *W; double *A;   // A: [K*K] parent-major, device, updated in place
+    const double *rho; double rho_scalar; const double *u; uint64_t seed, counter;
     double D;
-    const int64_t *col; const int *boff; const unsigned *ent_i; const double *ent_dt;
-    double *lam, *gacc, *vbuf;          // per-CTA scratch: [max_col], [max_col], [max_bucket]
-    int64_t max_col, max_bucket;
-    int *flag;
-    int col_begin, col_stride;
+    const int *vstart; const int64_t *vbase; const int *boff; const unsigned short *ent_i; const double *ent_dt;
+    double *lam;           // [n] by-node order
+    int chunk_max;         // doubles of shared memory in front of the adjacency bit row
+    int *flag, *next; unsigned long long *stat;
+    int col_begin, col_stride, ncols;
+    int s0;
 };
 
-template <int KIND> __global__ void __launch_bounds__(1024) k_adj_sweep(const AdjSweepArgs a) {
+// One group of 32 consecutive entries [eb, eb + 32) of a bucket that ends at b1, one entry per lane: the impulse value of
+// every entry and, for the first entry of each (event, parent) run (the "head"), the run's total.  Returns head.
+template <int KIND>
+__device__ __forceinline__ bool adj_group(const typename EntryOf<KIND>::type &en, const unsigned short *__restrict__ ei, const double *__restrict__ ed,
+                                          int eb, int b1, int lane, unsigned ii, double dt, double D, const FastTables *ft, double &gsum) {
+    const bool valid = eb + lane < b1;
+    double v = pair_value(en, dt, D, ft);
+    if (!valid) v = 0.0;
+    const bool cont = valid && (ii & 0x8000u);
+    const unsigned contmask = __ballot_sync(0xffffffffu, cont);
+    const unsigned fol = lane == 31 ? 0u : (contmask >> (lane + 1));
+    const int runlen = __ffs(~fol) - 1;  // entries behind this one that continue its run (inside the group)
+    const bool head = valid && !cont;
+    const int mr = __reduce_max_sync(0xffffffffu, head ? runlen : 0);
+    gsum = v;
+    for (int d = 1; d <= mr; d++) {
+        const double vv = __shfl_down_sync(0xffffffffu, v, d);
+        if (d <= runlen) gsum += vv;
+    }
+    if (head && lane + runlen == 31)  // the run may go on in the bucket's next group
+        for (int e2 = eb + 32; e2 < b1 && (__ldg(ei + e2) & 0x8000u); e2++) gsum += pair_value(en, __ldg(ed + e2), D, ft);
+    return head;
+}
+
+// log((base + g) / base) accumulated as a running quotient of products: one log per fold instead of one per entry
+__device__ __forceinline__ void adj_accumulate(double hi, double base, double &num, double &den, double &acc) {
+    if (in_mid_range(hi) && in_mid_range(base)) {
+        num *= hi; den *= base;  // both factors in [2^-500, 2^500): no overflow before the range test
+        if (!(in_mid_range(num) && in_mid_range(den))) { acc += log(num) - log(den); num = 1.0; den = 1.0; }
+    } else acc += log(hi / base);
+}
+
+template <int KIND> __global__ void __launch_bounds__(ADJ_THREADS, 1) k_adj_sweep(const AdjSweepArgs a) {
     typedef typename EntryOf<KIND>::type E;
+    extern __shared__ __align__(16) double lam_s[];  // [chunk_max] intensities of the resident chunk | adjacency bits of the column
     __shared__ FastTables s_ft;
-    __shared__ double s_red[32];
-    __shared__ double s_anew;
+    __shared__ double s_part[32];
+    __shared__ double s_sgn;
+    __shared__ int s_col, s_first;
     fast_tables_load(&s_ft);
     const FastTables *ft = &s_ft;
-    double *lam = a.lam + (size_t)blockIdx.x * a.max_col;
-    double *gacc = a.gacc + (size_t)blockIdx.x * a.max_col;
-    double *vbuf = a.vbuf + (size_t)blockIdx.x * a.max_bucket;
-    __syncthreads();
-    for (int c = a.col_begin + blockIdx.x * a.col_stride; c < a.K; c += gridDim.x * a.col_stride) {
-        const int ne = a.node_ptr[c + 1] - a.node_ptr[c];
-        const E *col = reinterpret_cast<const E *>(a.table_w) + (size_t)c * a.K;
-        const int *boff = a.boff + (int64_t)c * (a.K + 1);
-        const unsigned *ent_i = a.ent_i + a.col[c];
-        const double *ent_dt = a.ent_dt + a.col[c];
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int K = a.K;
+    unsigned *s_ab = reinterpret_cast<unsigned *>(lam_s + a.chunk_max);  // [(K + 31) / 32]
+    const int abw = (K + 31) >> 5;
+    unsigned long long n_steps = 0, n_batches = 0, n_flips = 0, n_redo = 0;
+    for (;;) {
+        __syncthreads();
+        if (tid == 0) s_col = atomicAdd(a.next, 1);
+        __syncthreads();
+        const int ci = s_col;
+        if (ci >= a.ncols) break;
+        const int c = a.col_begin + ci * a.col_stride;
+        const int e0 = a.node_ptr[c], ne = a.node_ptr[c + 1] - e0;
+        const int v0 = a.vstart[c], G = a.vstart[c + 1] - v0;
+        const int csz = adj_chunk_size(ne, G);
+        const E *col = reinterpret_cast<const E *>(a.table_w) + (size_t)c * K;
         const double lam0 = a.lambda0[c];
-        for (int e = threadIdx.x; e < ne; e += blockDim.x) { lam[e] = lam0; gacc[e] = 0.0; }
-        __syncthreads();
-        // current intensities: contributions of the links that are on
-        for (int p = 0; p < a.K; p++) {
-            if (a.A[p + (int64_t)a.K * c] == 0.0) continue;  // block-uniform
-            const E en = load_entry(col + p);
-            for (int e = boff[p] + threadIdx.x; e < boff[p + 1]; e += blockDim.x) {
-                const double v = pair_value(en, __ldg(ent_dt + e), a.D, ft);
-                if (v > 0.0) red_add_f64(&lam[__ldg(ent_i + e) & 0x7fffffffu], v);
-            }
+        double *lamg = a.lam + e0;
+        double *Acol = a.A + (size_t)K * c;
+        // adjacency bits of the column
+        for (int w = warp; w < abw; w += ADJ_THREADS / 32) {
+            const int p = w * 32 + lane;
+            const unsigned m = __ballot_sync(0xffffffffu, p < K && Acol[p] != 0.0);
+            if (lane == 0) s_ab[w] = m;
         }
-        __syncthreads();
-        // K sequential Bernoulli steps
-        for (int p = 0; p < a.K; p++) {
-            const int b0 = boff[p], b1 = boff[p + 1];
-            const int64_t kk = p + (int64_t)a.K * c;
-            const double a_old = a.A[kk];
-            double part = 0.0;
-            int anydup = 0;
-            if (b1 > b0) {
-                const E en = load_entry(col + p);
-                bool mydup = false;
-                for (int e = b0 + threadIdx.x; e < b1; e += blockDim.x) {
-                    const unsigned ii = __ldg(ent_i + e);
-                    const double v = pair_value(en, __ldg(ent_dt + e), a.D, ft);
-                    vbuf[e - b0] = v;
-                    if ((ii & 0x80000000u) && v > 0.0) { red_add_f64(&gacc[ii & 0x7fffffffu], v); mydup = true; }
-                }
-                anydup = __syncthreads_or(mydup);  // the aggregated G_i[p] must be complete before it is read
-                for (int e = b0 + threadIdx.x; e < b1; e += blockDim.x) {
-                    const double v = vbuf[e - b0];
-                    if (v > 0.0) {
-                        const unsigned ii = __ldg(ent_i + e);
-                        const bool dup = (ii & 0x80000000u) != 0u;
-                        const int ie = (int)(ii & 0x7fffffffu);
-                        const double g = dup ? gacc[ie] : v, l = lam[ie];
-                        const double base = a_old != 0.0 ? l - g : l;
-                        const double term = log((base + g) / base);
-                        part += (v == g) ? term : term * (v / g);  // an entry carries its share v/g of the event's term
+        // ---- current intensities: lambda0 + the links that are on
+        for (int g = 0; g < G; g++) {
+            const int len = min(csz, ne - g * csz);
+            for (int e = tid; e < len; e += ADJ_THREADS) lam_s[e] = lam0;
+            __syncthreads();
+            const int *bo = a.boff + (int64_t)(v0 + g) * (K + 1);
+            const unsigned short *ei = a.ent_i + a.vbase[v0 + g];
+            const double *ed = a.ent_dt + a.vbase[v0 + g];
+            for (int w = 0; w < abw; w++) {
+                unsigned bits = s_ab[w];
+                while (bits) {  // block-uniform
+                    const int p = w * 32 + __ffs(bits) - 1;
+                    bits &= bits - 1;
+                    const int b0 = bo[p], b1 = bo[p + 1];
+                    if (b1 == b0) continue;
+                    const E en = load_entry(col + p);
+                    for (int eb = b0 + warp * 32; eb < b1; eb += ADJ_THREADS) {
+                        const bool valid = eb + lane < b1;
+                        const unsigned ii = valid ? (unsigned)__ldg(ei + eb + lane) : 0u;
+                        const double dt = valid ? __ldg(ed + eb + lane) : 1.0;
+                        double gs;
+                        if (adj_group<KIND>(en, ei, ed, eb, b1, lane, ii, dt, a.D, ft, gs) && gs > 0.0) lam_s[ii & 0x7fffu] += gs;  // one head per event and bucket
                     }
+                    __syncthreads();  // the next parent may touch the same events
                 }
-                part = warp_sum(part);
-                if ((threadIdx.x & 31) == 0) s_red[threadIdx.x >> 5] = part;
+            }
+            if (G > 1) {
+                for (int e = tid; e < len; e += ADJ_THREADS) lamg[(size_t)g * csz + e] = lam_s[e];
                 __syncthreads();
             }
-            if (threadIdx.x == 0) {
+        }
+        // ---- K Bernoulli steps in speculative batches
+        int p = 0, S = a.s0;
+        while (p < K) {
+            const int Sc = min(S, K - p);
+            const int lg = 31 - __clz(S);
+            const int qi = warp & (S - 1), sub = warp >> lg, nsub = 32 >> lg;
+            const int q = p + qi;
+            const bool act = qi < Sc;
+            // the deciding lanes fetch their inputs before the batch so that the latency hides behind it
+            double d_w = 0.0, d_mn = 0.0, d_rho = 0.5, d_u = 2.0;
+            if (warp == 0 && lane < Sc) {
+                const int64_t kk = (p + lane) + (int64_t)K * c;
+                d_w = a.W[kk]; d_mn = a.Mn[p + lane];
+                d_rho = a.rho ? a.rho[kk] : a.rho_scalar;
+                d_u = a.u ? a.u[kk] : philox_uniform(a.seed, (uint64_t)kk, a.counter);
+            }
+            E en = E();
+            bool on = false;
+            if (act) { en = load_entry(col + q); on = (s_ab[q >> 5] >> (q & 31)) & 1u; }
+            double acc = 0.0, num = 1.0, den = 1.0;
+            for (int g = 0; g < G; g++) {
+                if (G > 1) {
+                    const int len = min(csz, ne - g * csz);
+                    __syncthreads();
+                    for (int e = tid; e < len; e += ADJ_THREADS) lam_s[e] = __ldcg(lamg + (size_t)g * csz + e);  // written by this CTA: read through L2
+                    __syncthreads();
+                }
+                if (act) {
+                    const int *bo = a.boff + (int64_t)(v0 + g) * (K + 1);
+                    const int b0 = bo[q], b1 = bo[q + 1];
+                    const unsigned short *ei = a.ent_i + a.vbase[v0 + g];
+                    const double *ed = a.ent_dt + a.vbase[v0 + g];
+                    int eb = b0 + sub * 32;
+                    unsigned ii_n = 0u;
+                    double dt_n = 1.0;
+                    if (eb + lane < b1) { ii_n = __ldg(ei + eb + lane); dt_n = __ldg(ed + eb + lane); }
+                    while (eb < b1) {
+                        const unsigned ii = ii_n;
+                        const double dt = dt_n;
+                        const int ebn = eb + nsub * 32;
+                        if (ebn + lane < b1) { ii_n = __ldg(ei + ebn + lane); dt_n = __ldg(ed + ebn + lane); }  // next group in flight
+                        double gs;
+                        if (adj_group<KIND>(en, ei, ed, eb, b1, lane, ii, dt, a.D, ft, gs) && gs > 0.0) {
+                            const double l = lam_s[ii & 0x7fffu];
+                            const double base = on ? fmax(l - gs, lam0) : l;  // intensity without parent q: at least lambda0
+                            adj_accumulate(base + gs, base, num, den, acc);
+                        }
+                        eb = ebn;
+                    }
+                }
+            }
+            acc += log(num) - log(den);
+            acc = warp_sum(acc);
+            if (lane == 0) s_part[warp] = acc;
+            __syncthreads();
+            if (warp == 0) {
+                const bool have = lane < Sc;
                 double sum = 0.0;
-                if (b1 > b0) for (int w = 0; w < (int)(blockDim.x >> 5); w++) sum += s_red[w];
-                const double rho = a.rho[kk];
+                if (have) for (int s = 0; s < nsub; s++) sum += s_part[lane + (s << lg)];
+                const int qq = p + lane;
+                const bool old_on = have && ((s_ab[qq >> 5] >> (qq & 31)) & 1u);
                 // ll1 - ll0 (continuous.jl:477-483): integrated-intensity difference, log-intensity difference, prior
-                const double delta = -a.W[kk] * a.Mn[p] + sum + (log(rho) - log(1.0 - rho));
+                const double delta = -d_w * d_mn + sum + (log(d_rho) - log(1.0 - d_rho));
                 double p1 = delta >= 0.0 ? 1.0 / (1.0 + exp(-delta)) : exp(delta) / (1.0 + exp(delta));
-                if (delta != delta) { atomicOr(a.flag, 64); p1 = 0.0; }
-                const double uu = a.u ? a.u[kk] : philox_uniform(a.seed, (uint64_t)kk, a.counter);
-                const double an = uu <= p1 ? 1.0 : 0.0;  // rand(Bernoulli(p)) = rand() <= p
-                a.A[kk] = an;
-                s_anew = an;
+                if (have && delta != delta) { atomicOr(a.flag, 64); p1 = 0.0; }
+                const bool new_on = d_u <= p1;  // rand(Bernoulli(p)) = rand() <= p
+                const unsigned flipmask = __ballot_sync(0xffffffffu, have && new_on != old_on);
+                const int first = flipmask ? __ffs(flipmask) - 1 : Sc;
+                if (lane == 0) s_first = first;
+                if (lane == first && have) {
+                    Acol[qq] = new_on ? 1.0 : 0.0;
+                    s_sgn = new_on ? 1.0 : -1.0;
+                    s_ab[qq >> 5] ^= 1u << (qq & 31);
+                }
             }
             __syncthreads();
-            if (b1 > b0) {
-                const double sgn = s_anew - a_old;  // +1 link switched on, -1 switched off, 0 unchanged
-                if (sgn != 0.0 || anydup) {
-                    for (int e = b0 + threadIdx.x; e < b1; e += blockDim.x) {
-                        const double v = vbuf[e - b0];
-                        if (v > 0.0) {
-                            const unsigned ii = __ldg(ent_i + e);
-                            if (sgn != 0.0) red_add_f64(&lam[ii & 0x7fffffffu], sgn * v);
-                            if (ii & 0x80000000u) gacc[ii & 0x7fffffffu] = 0.0;
+            const int first = s_first;
+            n_batches++;
+            if (first < Sc) {
+                // the link of bucket qf flipped: move its contribution into / out of the intensities, restart behind it
+                const int qf = p + first;
+                const double sgn = s_sgn;
+                const E enf = load_entry(col + qf);
+                for (int g = 0; g < G; g++) {
+                    const int *bo = a.boff + (int64_t)(v0 + g) * (K + 1);
+                    const int b0 = bo[qf], b1 = bo[qf + 1];
+                    const unsigned short *ei = a.ent_i + a.vbase[v0 + g];
+                    const double *ed = a.ent_dt + a.vbase[v0 + g];
+                    for (int eb = b0 + warp * 32; eb < b1; eb += ADJ_THREADS) {
+                        const bool valid = eb + lane < b1;
+                        const unsigned ii = valid ? (unsigned)__ldg(ei + eb + lane) : 0u;
+                        const double dt = valid ? __ldg(ed + eb + lane) : 1.0;
+                        double gs;
+                        if (adj_group<KIND>(enf, ei, ed, eb, b1, lane, ii, dt, a.D, ft, gs) && gs > 0.0) {
+                            if (G == 1) lam_s[ii & 0x7fffu] += sgn * gs;
+                            else lamg[(size_t)g * csz + (ii & 0x7fffu)] += sgn * gs;
                         }
                     }
                 }
                 __syncthreads();
+                n_steps += first + 1; n_flips++; n_redo += Sc - 1 - first;
+                p = qf + 1;
+                S = max(S >> 1, ADJ_SMIN);
+            } else {
+                n_steps += Sc;
+                p += Sc;
+                S = min(S << 1, ADJ_SMAX);
             }
         }
-        __syncthreads();
     }
-}
-
-// per-column totals -> exclusive scan (K values; single thread) and the largest bucket of every column
-__global__ void k_adj_scan(const unsigned long long *__restrict__ colcount, int K, int col_begin, int col_stride, int64_t *__restrict__ col) {
-    if (threadIdx.x == 0 && blockIdx.x == 0) {
-        int64_t run = 0;
-        for (int k = 0; k < K; k++) { col[k] = run; if (k % col_stride == col_begin) run += (int64_t)colcount[k]; }  // owned columns only
-        col[K] = run;
+    if (tid == 0 && a.stat) {
+        atomicAdd(a.stat + 0, n_steps); atomicAdd(a.stat + 1, n_batches); atomicAdd(a.stat + 2, n_flips); atomicAdd(a.stat + 3, n_redo);
     }
-}
-__global__ void k_adj_max_bucket(const int *__restrict__ boff, int K, unsigned long long *__restrict__ out) {
-    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= (int64_t)K * K) return;
-    const int c = (int)(i / K), p = (int)(i % K);
-    const int len = boff[(int64_t)c * (K + 1) + p + 1] - boff[(int64_t)c * (K + 1) + p];
-    if (len > 0) atomicMax(out, (unsigned long long)len);
-}
-
-// per-column entry totals: colcount[c_i] += window length of event i
-__global__ void k_adj_count(const double *__restrict__ t, const int *__restrict__ c, int64_t n, double horizon, unsigned long long *__restrict__ colcount) {
-    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= n) return;
-    int lo = lo_of_event(t, i, horizon);
-    if (i > lo) atomicAdd(&colcount[c[i]], (unsigned long long)(i - lo));
 }
 
 __global__ void k_iota(int *v, int64_t n) {
     int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i < n) v[i] = (int)i;
-}
-__global__ void k_node_ptr(const double *__restrict__ Mn, int K, int *__restrict__ ptr) {
-    if (threadIdx.x == 0 && blockIdx.x == 0) {
-        int run = 0;
-        for (int k = 0; k < K; k++) { ptr[k] = run; run += (int)Mn[k]; }
-        ptr[K] = run;
-    }
 }
 
 // table without the adjacency factor (the sampler needs W h for both values of A[p,c])
@@ -408,6 +563,292 @@ __global__ void k_table_noA_ex(int K, const double *__restrict__ W, const double
     table[e] = en;
 }
 
+// Look-back horizon of the sampler.  It evaluates W h for links that are currently off as well, so the Exponential cut-off is
+// taken from ALL entries with W != 0 (the sweeps' horizon only looks at the active links).
+static double adj_horizon_value(const nhp_ctx *ctx, int64_t n_total) {
+    double h = ctx->dtmax;
+    if (ctx->kind != NHP_EXPONENTIAL) return h;
+    if (ctx->wt_max_all <= 0.0) return std::min(h, 1e-300);
+    if (ctx->theta_min_all > 0.0 && std::isfinite(ctx->theta_min_all) && ctx->lambda0_min > 0.0 && n_total > 0) {
+        const double cut = log((double)n_total * ctx->wt_max_all / (1e-14 * ctx->lambda0_min)) / ctx->theta_min_all;
+        if (cut > 0.0 && cut < h) h = cut;
+    }
+    return h;
+}
+
+#define ADJ_CUDA(call) do { cudaError_t e__ = (call); if (e__ != cudaSuccess) return nhp_fail(ctx, NHP_ERR_CUDA, "%s failed: %s (%s:%d)", #call, cudaGetErrorString(e__), __FILE__, __LINE__); } while (0)
+
+static int adj_ensure_ctx(nhp_ctx *ctx) {
+    const size_t KK = (size_t)ctx->K * ctx->K;
+    if (!ctx->d_adj_tw) ADJ_CUDA(cudaMalloc(&ctx->d_adj_tw, KK * sizeof(EntryLN)));
+    if (!ctx->d_adj_rho) ADJ_CUDA(cudaMalloc(&ctx->d_adj_rho, KK * sizeof(double)));
+    if (!ctx->d_adj_u) ADJ_CUDA(cudaMalloc(&ctx->d_adj_u, KK * sizeof(double)));
+    if (!ctx->d_adj_A) ADJ_CUDA(cudaMalloc(&ctx->d_adj_A, KK * sizeof(double)));
+    if (!ctx->d_adj_ctl) ADJ_CUDA(cudaMalloc(&ctx->d_adj_ctl, 8 * sizeof(int)));
+    if (!ctx->d_adj_stat) ADJ_CUDA(cudaMalloc(&ctx->d_adj_stat, 8 * sizeof(unsigned long long)));
+    return NHP_OK;
+}
+
+// (Re)build the cached structure of `ev` for this horizon / column partition.  Returns 1 when it does not fit (uncached sweep).
+static int adj_build_structure(nhp_ctx *ctx, nhp_events *ev, double horizon, int cb, int cs, int chunk_cap) {
+    const int64_t K = ctx->K, n = ev->n;
+    cudaStream_t s = ctx->stream;
+    nhp_events_free_adjacency(ev);
+    std::vector<double> mn(K);
+    ADJ_CUDA(cudaMemcpyAsync(mn.data(), ev->d_Mn, K * sizeof(double), cudaMemcpyDeviceToHost, s));
+    ADJ_CUDA(cudaStreamSynchronize(s));
+    // virtual columns: owned columns are cut into chunks of at most chunk_cap events
+    std::vector<int> vstart(K + 1), vnode;
+    int chunk_max = 1;
+    for (int64_t c = 0; c < K; c++) {
+        vstart[c] = (int)vnode.size();
+        if (c % cs != cb) continue;
+        const int ne = (int)mn[c];
+        const int G = std::max(1, (ne + chunk_cap - 1) / chunk_cap);
+        chunk_max = std::max(chunk_max, adj_chunk_size(ne, G));
+        for (int g = 0; g < G; g++) vnode.push_back((int)c);
+    }
+    vstart[K] = (int)vnode.size();
+    const int64_t nv = (int64_t)vnode.size();
+    if (nv == 0) return 1;
+    int *d_vstart = nullptr, *d_vnode = nullptr;
+    unsigned long long *d_vcount = nullptr;
+    auto drop = [&](int rc) { cudaFree(d_vstart); cudaFree(d_vnode); cudaFree(d_vcount); return rc; };
+#define ADJ_B(call) do { cudaError_t e__ = (call); if (e__ != cudaSuccess) return drop(nhp_fail(ctx, NHP_ERR_CUDA, "%s failed: %s (%s:%d)", #call, cudaGetErrorString(e__), __FILE__, __LINE__)); } while (0)
+    ADJ_B(cudaMalloc(&d_vstart, (size_t)(K + 1) * sizeof(int)));
+    ADJ_B(cudaMalloc(&d_vnode, (size_t)nv * sizeof(int)));
+    ADJ_B(cudaMalloc(&d_vcount, (size_t)nv * sizeof(unsigned long long)));
+    ADJ_B(cudaMemcpyAsync(d_vstart, vstart.data(), (size_t)(K + 1) * sizeof(int), cudaMemcpyHostToDevice, s));
+    ADJ_B(cudaMemcpyAsync(d_vnode, vnode.data(), (size_t)nv * sizeof(int), cudaMemcpyHostToDevice, s));
+    ADJ_B(cudaMemsetAsync(d_vcount, 0, (size_t)nv * sizeof(unsigned long long), s));
+    if (n > 0) {
+        k_adj_count<<<(unsigned)((n + 255) / 256), 256, 0, s>>>(ev->d_t, ev->d_c, ev->d_order, ev->d_node_ptr, d_vstart, n, horizon, cb, cs, d_vcount);
+        NHP_LAUNCHED(ctx);
+    }
+    std::vector<unsigned long long> vc(nv);
+    ADJ_B(cudaMemcpyAsync(vc.data(), d_vcount, (size_t)nv * sizeof(unsigned long long), cudaMemcpyDeviceToHost, s));
+    ADJ_B(cudaStreamSynchronize(s));
+    std::vector<int64_t> vbase(nv + 1);
+    int64_t tot = 0;
+    for (int64_t v = 0; v < nv; v++) {
+        vbase[v] = tot;
+        if (vc[v] >= 0x7fffffffull) return drop(nhp_fail(ctx, NHP_ERR_UNSUPPORTED, "adjacency sampler: a column chunk has %llu window entries (limit 2^31)", vc[v]));
+        tot += (int64_t)vc[v];
+    }
+    vbase[nv] = tot;
+    // room: the structure, the bucket offsets, the per-event intensities; keep a quarter of the free memory for everything else
+    size_t free_b = 0, total_b = 0;
+    cudaMemGetInfo(&free_b, &total_b);
+    const size_t need = (size_t)tot * 10 + (size_t)nv * (K + 1) * sizeof(int) + (size_t)(nv + 1) * sizeof(int64_t) + (size_t)n * sizeof(double);
+    // build kernel: [K+1] offsets + per warp 3 K counters
+    int nw = (int)std::min<int64_t>(16, ((int64_t)ctx->smem_optin - 2048 - (K + 1) * 4) / (12 * K));
+    if (need > free_b / 4 * 3 || nw < 1) return drop(1);
+    cudaFree(d_vcount); d_vcount = nullptr;
+    ev->d_adj_vstart = d_vstart; ev->d_adj_vnode = d_vnode; d_vstart = d_vnode = nullptr;  // owned by the handle from here on
+    auto fail = [&](int rc) { nhp_events_free_adjacency(ev); return rc; };
+#define ADJ_S(call) do { cudaError_t e__ = (call); if (e__ != cudaSuccess) return fail(nhp_fail(ctx, NHP_ERR_CUDA, "%s failed: %s (%s:%d)", #call, cudaGetErrorString(e__), __FILE__, __LINE__)); } while (0)
+    ADJ_S(cudaMalloc(&ev->d_adj_vbase, (size_t)(nv + 1) * sizeof(int64_t)));
+    ADJ_S(cudaMalloc(&ev->d_adj_boff, (size_t)nv * (K + 1) * sizeof(int)));
+    ADJ_S(cudaMalloc(&ev->d_adj_i, std::max<size_t>((size_t)tot, 1) * sizeof(unsigned short)));
+    ADJ_S(cudaMalloc(&ev->d_adj_dt, std::max<size_t>((size_t)tot, 1) * sizeof(double)));
+    ADJ_S(cudaMalloc(&ev->d_adj_lam, std::max<size_t>((size_t)n, 1) * sizeof(double)));
+    ADJ_S(cudaMemcpyAsync(ev->d_adj_vbase, vbase.data(), (size_t)(nv + 1) * sizeof(int64_t), cudaMemcpyHostToDevice, s));
+    ADJ_S(cudaMemsetAsync(ctx->d_adj_ctl, 0, 8 * sizeof(int), s));
+    AdjBuildArgs b;
+    b.t = ev->d_t; b.c = ev->d_c; b.order = ev->d_order; b.node_ptr = ev->d_node_ptr; b.K = (int)K; b.horizon = horizon;
+    b.vstart = ev->d_adj_vstart; b.vnode = ev->d_adj_vnode; b.vbase = ev->d_adj_vbase; b.boff = ev->d_adj_boff; b.ent_i = ev->d_adj_i; b.ent_dt = ev->d_adj_dt;
+    b.nv = (int)nv; b.nw = nw; b.next = ctx->d_adj_ctl; b.flag = ctx->d_flag;
+    const size_t bsmem = (size_t)(K + 1) * sizeof(int) + (size_t)nw * 3 * K * sizeof(unsigned);
+    ADJ_S(cudaFuncSetAttribute(k_adj_build, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)std::max<size_t>(bsmem, 1024)));
+    int per_sm = 1;
+    ADJ_S(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_adj_build, nw * 32, bsmem));
+    const int grid = (int)std::min<int64_t>(nv, (int64_t)ctx->sm_count * std::max(per_sm, 1));
+    cudaEvent_t b0, b1;
+    ADJ_S(cudaEventCreate(&b0)); ADJ_S(cudaEventCreate(&b1));
+    cudaEventRecord(b0, s);
+    k_adj_build<<<grid, nw * 32, bsmem, s>>>(b);
+    NHP_LAUNCHED(ctx);
+    cudaEventRecord(b1, s);
+    int flag = 0;
+    ADJ_S(cudaMemcpyAsync(&flag, ctx->d_flag, sizeof(int), cudaMemcpyDeviceToHost, s));
+    ADJ_S(cudaStreamSynchronize(s));
+    ADJ_S(cudaGetLastError());
+    float bms = 0.f;
+    cudaEventElapsedTime(&bms, b0, b1);
+    cudaEventDestroy(b0); cudaEventDestroy(b1);
+    if (flag & 128) return fail(nhp_fail(ctx, NHP_ERR_CUDA, "adjacency sampler: structure build disagrees with its own count (internal error)"));
+    ev->adj_total = tot; ev->adj_nv = nv; ev->adj_horizon = horizon; ev->adj_cb = cb; ev->adj_cs = cs;
+    ev->adj_chunk_cap = chunk_cap; ev->adj_chunk_max = chunk_max;
+    ctx->adj_info[7] = bms;
+    return NHP_OK;
+#undef ADJ_B
+#undef ADJ_S
+}
+
+// the uncached sweep: per-call scratch, re-bucketing inside the kernel
+static int adj_run_uncached(nhp_ctx *ctx, nhp_events *ev, double horizon, const double *d_rho, const double *d_u, uint64_t seed, uint64_t counter,
+                            double *d_A, int cb, int cs) {
+    const int64_t K = ctx->K, n = ev->n;
+    cudaStream_t s = ctx->stream;
+    unsigned long long *d_cc = nullptr;
+    int *d_ent_i = nullptr; double *d_ent_v = nullptr, *d_lam = nullptr, *d_gacc = nullptr;
+    auto fin = [&](int rc) {
+        cudaStreamSynchronize(s);
+        cudaFree(d_cc); cudaFree(d_ent_i); cudaFree(d_ent_v); cudaFree(d_lam); cudaFree(d_gacc);
+        return rc;
+    };
+#define ADJ_U(call) do { cudaError_t e__ = (call); if (e__ != cudaSuccess) return fin(nhp_fail(ctx, NHP_ERR_CUDA, "%s failed: %s (%s:%d)", #call, cudaGetErrorString(e__), __FILE__, __LINE__)); } while (0)
+    // per-column window totals size the buckets: one "virtual column" per column
+    std::vector<int> vstart(K + 1);
+    for (int64_t c = 0; c <= K; c++) vstart[c] = (int)c;
+    ADJ_U(cudaMalloc(&d_cc, (size_t)(K + 1) * sizeof(unsigned long long)));
+    int *d_vstart = nullptr;
+    ADJ_U(cudaMalloc(&d_vstart, (size_t)(K + 1) * sizeof(int)));
+    auto fin2 = [&](int rc) { cudaFree(d_vstart); return fin(rc); };
+    if (cudaMemcpyAsync(d_vstart, vstart.data(), (size_t)(K + 1) * sizeof(int), cudaMemcpyHostToDevice, s) != cudaSuccess ||
+        cudaMemsetAsync(d_cc, 0, (size_t)K * sizeof(unsigned long long), s) != cudaSuccess)
+        return fin2(nhp_fail(ctx, NHP_ERR_CUDA, "adjacency sampler: %s", cudaGetErrorString(cudaGetLastError())));
+    if (n > 0) {
+        k_adj_count<<<(unsigned)((n + 255) / 256), 256, 0, s>>>(ev->d_t, ev->d_c, ev->d_order, ev->d_node_ptr, d_vstart, n, horizon, 0, 1, d_cc);
+        NHP_LAUNCHED(ctx);
+    }
+    std::vector<unsigned long long> cc(K);
+    std::vector<double> mn(K);
+    if (cudaMemcpyAsync(cc.data(), d_cc, K * sizeof(unsigned long long), cudaMemcpyDeviceToHost, s) != cudaSuccess ||
+        cudaMemcpyAsync(mn.data(), ev->d_Mn, K * sizeof(double), cudaMemcpyDeviceToHost, s) != cudaSuccess || cudaStreamSynchronize(s) != cudaSuccess)
+        return fin2(nhp_fail(ctx, NHP_ERR_CUDA, "adjacency sampler: %s", cudaGetErrorString(cudaGetLastError())));
+    cudaFree(d_vstart); d_vstart = nullptr;
+    int64_t cap = 1, mc = 1;
+    for (int64_t k = 0; k < K; k++) { cap = std::max<int64_t>(cap, (int64_t)cc[k]); mc = std::max<int64_t>(mc, (int64_t)mn[k]); }
+    if (cap >= (int64_t)0x3fffffff) return fin(nhp_fail(ctx, NHP_ERR_UNSUPPORTED, "adjacency sampler: a column has %lld window entries (limit 2^30)", (long long)cap));
+    int grid = (int)std::min<int64_t>(K, (int64_t)ctx->sm_count * 8);
+    size_t free_b = 0, total_b = 0;
+    cudaMemGetInfo(&free_b, &total_b);
+    while (grid > 1 && (size_t)grid * ((size_t)cap * 12 + (size_t)mc * 16) > free_b / 2) grid = (grid + 1) / 2;
+    if ((size_t)grid * ((size_t)cap * 12 + (size_t)mc * 16) > free_b / 2)
+        return fin(nhp_fail(ctx, NHP_ERR_UNSUPPORTED, "adjacency sampler: one column needs %lld window entries, more than the free device memory holds", (long long)cap));
+    ADJ_U(cudaMalloc(&d_ent_i, (size_t)grid * cap * sizeof(int)));
+    ADJ_U(cudaMalloc(&d_ent_v, (size_t)grid * cap * sizeof(double)));
+    ADJ_U(cudaMalloc(&d_lam, (size_t)grid * mc * sizeof(double)));
+    ADJ_U(cudaMalloc(&d_gacc, (size_t)grid * mc * sizeof(double)));
+    AdjArgs a;
+    a.t = ev->d_t; a.c = ev->d_c; a.n = n; a.order = ev->d_order; a.node_ptr = ev->d_node_ptr; a.Mn = ev->d_Mn; a.K = (int)K; a.table_w = ctx->d_adj_tw;
+    a.lambda0 = ctx->d_lambda0; a.W = ctx->d_W; a.A = d_A; a.rho = d_rho; a.u = d_u; a.seed = seed; a.counter = counter;
+    a.D = ctx->dtmax; a.horizon = horizon; a.duration = ev->duration; a.flag = ctx->d_flag; a.col_begin = cb; a.col_stride = cs;
+    a.cap = cap; a.ent_i = d_ent_i; a.ent_v = d_ent_v; a.lam = d_lam; a.gacc = d_gacc; a.max_col = mc;
+    const size_t smem = (size_t)(2 * K + 2) * sizeof(int);
+    if (ctx->kind == NHP_LOGITNORMAL) {
+        ADJ_U(cudaFuncSetAttribute(k_adjacency<NHP_LOGITNORMAL>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)std::max<size_t>(smem, 1024)));
+        k_adjacency<NHP_LOGITNORMAL><<<grid, 256, smem, s>>>(a);
+    } else {
+        ADJ_U(cudaFuncSetAttribute(k_adjacency<NHP_EXPONENTIAL>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)std::max<size_t>(smem, 1024)));
+        k_adjacency<NHP_EXPONENTIAL><<<grid, 256, smem, s>>>(a);
+    }
+    NHP_LAUNCHED(ctx);
+    ADJ_U(cudaGetLastError());
+    return fin(NHP_OK);
+#undef ADJ_U
+}
+
+// One adjacency Gibbs sweep over the owned columns of the device-resident matrix d_A (in place).  d_rho: per-link
+// probabilities on the device, or NULL for the scalar rho_scalar; d_u: uniforms on the device or NULL (Philox).
+static int adj_run(nhp_ctx *ctx, nhp_events *ev, const double *d_rho, double rho_scalar, const double *d_u, uint64_t seed, uint64_t counter,
+                   double *d_A, int64_t col_begin, int64_t col_stride) {
+    NHP_CHECK(ctx, col_stride >= 1 && col_begin >= 0 && col_begin < col_stride, NHP_ERR_INVALID, "adjacency sampler: need 0 <= col_begin < col_stride");
+    NHP_CHECK(ctx, ctx->cont_set, NHP_ERR_STATE, "continuous parameters not set (call nhp_cont_params_set)");
+    NHP_CHECK(ctx, ev != nullptr && ev->K == ctx->K, NHP_ERR_INVALID, "adjacency sampler: bad events handle");
+    NHP_CHECK(ctx, ev->n_halo == 0 && ev->index_base == 0, NHP_ERR_UNSUPPORTED,
+              "the adjacency sampler works on unsharded data (multi-GPU partitions the columns, not the time axis)");
+    NHP_CUDA(ctx, cudaSetDevice(ctx->device));
+    NHP_CUDA(ctx, fast_tables_upload(ctx->stream));
+    NHP_TRY(adj_ensure_ctx(ctx));
+    const int64_t K = ctx->K, KK = K * K, n = ev->n;
+    cudaStream_t s = ctx->stream;
+    const unsigned kb = (unsigned)((KK + 255) / 256);
+    if (ctx->kind == NHP_LOGITNORMAL) k_table_noA_ln<<<kb, 256, 0, s>>>((int)K, ctx->d_W, ctx->d_p1, ctx->d_p2, ctx->dtmax, (EntryLN *)ctx->d_adj_tw);
+    else k_table_noA_ex<<<kb, 256, 0, s>>>((int)K, ctx->d_W, ctx->d_p1, (EntryEX *)ctx->d_adj_tw);
+    NHP_LAUNCHED(ctx);
+    NHP_CUDA(ctx, cudaMemsetAsync(ctx->d_flag, 0, sizeof(int), s));
+    for (int i = 0; i < 7; i++) ctx->adj_info[i] = 0.0;
+    NHP_TRY(nhp_events_build_node_index(ctx, ev));
+    double horizon = adj_horizon_value(ctx, n);
+    const char *envc = getenv("NHP_ADJ_CACHE");
+    bool cached = !(envc && atoi(envc) == 0);
+    int chunk_cap = ADJ_CHUNK_MAX;
+    { const char *e = getenv("NHP_ADJ_CHUNK"); if (e && atoi(e) >= 1 && atoi(e) <= ADJ_CHUNK_MAX) chunk_cap = atoi(e); }
+    // The cached structure stays valid for any horizon it covers: extra pairs beyond the requested cut-off are genuine
+    // predecessors whose (tiny) contributions are simply included.  With a parameter-dependent horizon (Exponential cut-off,
+    // which moves with every conjugate draw) it is built with a 25 % margin so that a chain does not rebuild it every sweep.
+    const bool moving = ctx->kind == NHP_EXPONENTIAL && horizon < ctx->dtmax;
+    const bool have_cache = cached && ev->d_adj_i && ev->adj_cb == (int)col_begin && ev->adj_cs == (int)col_stride && ev->adj_chunk_cap == chunk_cap &&
+                            (moving ? (ev->adj_horizon >= horizon && ev->adj_horizon <= 2.0 * horizon) : ev->adj_horizon == horizon);
+    if (cached && !have_cache) {
+        if (moving) horizon = std::min(ctx->dtmax, 1.25 * horizon);
+        const int rc = adj_build_structure(ctx, ev, horizon, (int)col_begin, (int)col_stride, chunk_cap);
+        if (rc < 0) return rc;
+        if (rc == 1) cached = false;
+    } else if (have_cache) horizon = ev->adj_horizon;
+    NHP_TRY(nhp_timer_begin(ctx));
+    if (cached) {
+        AdjSweepArgs w;
+        w.node_ptr = ev->d_node_ptr; w.Mn = ev->d_Mn; w.K = (int)K; w.table_w = ctx->d_adj_tw; w.lambda0 = ctx->d_lambda0; w.W = ctx->d_W; w.A = d_A;
+        w.rho = d_rho; w.rho_scalar = rho_scalar; w.u = d_u; w.seed = seed; w.counter = counter; w.D = ctx->dtmax;
+        w.vstart = ev->d_adj_vstart; w.vbase = ev->d_adj_vbase; w.boff = ev->d_adj_boff; w.ent_i = ev->d_adj_i; w.ent_dt = ev->d_adj_dt; w.lam = ev->d_adj_lam;
+        w.chunk_max = (ev->adj_chunk_max + 1) & ~1;
+        w.flag = ctx->d_flag; w.next = ctx->d_adj_ctl; w.stat = ctx->d_adj_stat;
+        w.col_begin = (int)col_begin; w.col_stride = (int)col_stride;
+        w.ncols = (int)((K - col_begin + col_stride - 1) / col_stride);
+        w.s0 = ADJ_SMAX;
+        { const char *e = getenv("NHP_ADJ_S0"); if (e && (atoi(e) == 4 || atoi(e) == 8 || atoi(e) == 16 || atoi(e) == 32)) w.s0 = atoi(e); }
+        const size_t smem = (size_t)w.chunk_max * sizeof(double) + (size_t)((K + 31) / 32) * sizeof(unsigned) + 16;
+        NHP_CHECK(ctx, smem <= (size_t)ctx->smem_optin - 2048, NHP_ERR_UNSUPPORTED, "adjacency sampler: K=%lld needs more shared memory than the device has", (long long)K);
+        NHP_CUDA(ctx, cudaMemsetAsync(ctx->d_adj_ctl, 0, 8 * sizeof(int), s));
+        NHP_CUDA(ctx, cudaMemsetAsync(ctx->d_adj_stat, 0, 8 * sizeof(unsigned long long), s));
+        const int grid = (int)std::min<int64_t>(w.ncols, ctx->sm_count);
+        if (grid <= 0) {}
+        else if (ctx->kind == NHP_LOGITNORMAL) {
+            NHP_CUDA(ctx, cudaFuncSetAttribute(k_adj_sweep<NHP_LOGITNORMAL>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            k_adj_sweep<NHP_LOGITNORMAL><<<grid, ADJ_THREADS, smem, s>>>(w);
+        } else {
+            NHP_CUDA(ctx, cudaFuncSetAttribute(k_adj_sweep<NHP_EXPONENTIAL>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            k_adj_sweep<NHP_EXPONENTIAL><<<grid, ADJ_THREADS, smem, s>>>(w);
+        }
+        NHP_LAUNCHED(ctx);
+        NHP_CUDA(ctx, cudaGetLastError());
+    } else {
+        // the uncached kernel wants per-link probabilities and the matrix it updates on the device
+        const double *rho_dev = d_rho;
+        if (!rho_dev) {
+            std::vector<double> r((size_t)KK, rho_scalar);
+            NHP_CUDA(ctx, cudaMemcpyAsync(ctx->d_adj_rho, r.data(), (size_t)KK * sizeof(double), cudaMemcpyHostToDevice, s));
+            NHP_CUDA(ctx, cudaStreamSynchronize(s));
+            rho_dev = ctx->d_adj_rho;
+        }
+        NHP_TRY(adj_run_uncached(ctx, ev, horizon, rho_dev, d_u, seed, counter, d_A, (int)col_begin, (int)col_stride));
+    }
+    int flag = 0;
+    unsigned long long st[4] = {0, 0, 0, 0};
+    NHP_CUDA(ctx, cudaMemcpyAsync(&flag, ctx->d_flag, sizeof(int), cudaMemcpyDeviceToHost, s));
+    if (cached) NHP_CUDA(ctx, cudaMemcpyAsync(st, ctx->d_adj_stat, sizeof(st), cudaMemcpyDeviceToHost, s));
+    NHP_TRY(nhp_timer_end(ctx));
+    NHP_CHECK(ctx, !(flag & 32), NHP_ERR_CUDA, "adjacency sampler: scratch overflow (internal error)");
+    NHP_CHECK(ctx, !(flag & 64), NHP_ERR_NUMERIC, "adjacency sampler: NaN log-likelihood difference");
+    ctx->adj_info[0] = (double)st[0]; ctx->adj_info[1] = (double)st[1]; ctx->adj_info[2] = (double)st[2]; ctx->adj_info[3] = (double)st[3];
+    ctx->adj_info[4] = cached ? (double)ev->adj_total : 0.0; ctx->adj_info[5] = cached ? (double)ev->adj_nv : 0.0; ctx->adj_info[6] = ctx->last_ms;
+    return NHP_OK;
+}
+
+static int adj_commit(nhp_ctx *ctx) {  // the masked tables, bit rows and row sums follow the new matrix
+    if (!ctx->has_A) return NHP_OK;
+    const double ms = ctx->last_ms;
+    ctx->cont_set = false;
+    ctx->sweep_ll_valid = false;
+    NHP_TRY(nhp_cont_params_refresh(ctx));
+    ctx->cont_set = true;
+    ctx->last_ms = ms;
+    return NHP_OK;
+}
+
 extern "C" int nhp_cont_resample_adjacency(nhp_ctx *ctx, nhp_events *ev, const double *rho, uint64_t seed, uint64_t counter, const double *u,
                                            double *A_inout) {
     return nhp_cont_resample_adjacency_cols(ctx, ev, rho, seed, counter, u, A_inout, 0, 1);
@@ -416,189 +857,43 @@ extern "C" int nhp_cont_resample_adjacency(nhp_ctx *ctx, nhp_events *ev, const d
 extern "C" int nhp_cont_resample_adjacency_cols(nhp_ctx *ctx, nhp_events *ev, const double *rho, uint64_t seed, uint64_t counter, const double *u,
                                                 double *A_inout, int64_t col_begin, int64_t col_stride) {
     NHP_CHECK(ctx, ctx != nullptr, NHP_ERR_INVALID, "ctx is NULL");
-    NHP_CHECK(ctx, col_stride >= 1 && col_begin >= 0 && col_begin < col_stride, NHP_ERR_INVALID, "nhp_cont_resample_adjacency_cols: need 0 <= col_begin < col_stride");
     NHP_CHECK(ctx, ctx->cont_set, NHP_ERR_STATE, "continuous parameters not set (call nhp_cont_params_set)");
-    NHP_CHECK(ctx, ev != nullptr && ev->K == ctx->K, NHP_ERR_INVALID, "nhp_cont_resample_adjacency: bad events handle");
     NHP_CHECK(ctx, rho && A_inout, NHP_ERR_INVALID, "nhp_cont_resample_adjacency: NULL rho/A");
-    NHP_CHECK(ctx, ev->n_halo == 0 && ev->index_base == 0, NHP_ERR_UNSUPPORTED,
-              "nhp_cont_resample_adjacency works on unsharded data (multi-GPU partitions the columns, not the time axis)");
     NHP_CUDA(ctx, cudaSetDevice(ctx->device));
-    NHP_CUDA(ctx, fast_tables_upload(ctx->stream));
-    const int64_t K = ctx->K, KK = K * K, n = ev->n;
+    NHP_TRY(adj_ensure_ctx(ctx));
+    const size_t KK = (size_t)ctx->K * ctx->K;
     cudaStream_t s = ctx->stream;
-    double horizon = nhp_cont_horizon_value(ctx, n, 0);
-    // ---- device buffers (freed at the end; the sampler is called once per Gibbs sweep)
-    double *d_rho = nullptr, *d_u = nullptr, *d_A = nullptr;
-    void *d_tw = nullptr, *d_sort = nullptr;
-    int *d_keys = nullptr, *d_vals = nullptr, *d_order = nullptr, *d_ptr = nullptr, *d_ckeys = nullptr;
-    unsigned long long *d_cc = nullptr;
-    int *d_ent_i = nullptr; double *d_ent_v = nullptr, *d_lam = nullptr, *d_gacc = nullptr;
-    auto fin = [&](int rc) {
-        cudaStreamSynchronize(s);
-        cudaFree(d_rho); cudaFree(d_u); cudaFree(d_A); cudaFree(d_tw); cudaFree(d_sort); cudaFree(d_keys); cudaFree(d_vals); cudaFree(d_order);
-        cudaFree(d_ptr); cudaFree(d_ckeys); cudaFree(d_cc); cudaFree(d_ent_i); cudaFree(d_ent_v); cudaFree(d_lam); cudaFree(d_gacc);
-        return rc;
-    };
-#define ADJ_CUDA(call) do { cudaError_t e__ = (call); if (e__ != cudaSuccess) return fin(nhp_fail(ctx, NHP_ERR_CUDA, "%s failed: %s", #call, cudaGetErrorString(e__))); } while (0)
-    ADJ_CUDA(cudaMalloc(&d_rho, KK * sizeof(double)));
-    ADJ_CUDA(cudaMalloc(&d_A, KK * sizeof(double)));
-    ADJ_CUDA(cudaMalloc(&d_tw, KK * sizeof(EntryLN)));
-    ADJ_CUDA(cudaMalloc(&d_ptr, (K + 1) * sizeof(int)));
-    ADJ_CUDA(cudaMalloc(&d_cc, K * sizeof(unsigned long long)));
-    ADJ_CUDA(cudaMemcpyAsync(d_rho, rho, KK * sizeof(double), cudaMemcpyHostToDevice, s));
-    ADJ_CUDA(cudaMemcpyAsync(d_A, A_inout, KK * sizeof(double), cudaMemcpyHostToDevice, s));
-    if (u) { ADJ_CUDA(cudaMalloc(&d_u, KK * sizeof(double))); ADJ_CUDA(cudaMemcpyAsync(d_u, u, KK * sizeof(double), cudaMemcpyHostToDevice, s)); }
-    unsigned kb = (unsigned)((KK + 255) / 256);
-    if (ctx->kind == NHP_LOGITNORMAL) k_table_noA_ln<<<kb, 256, 0, s>>>((int)K, ctx->d_W, ctx->d_p1, ctx->d_p2, ctx->dtmax, (EntryLN *)d_tw);
-    else k_table_noA_ex<<<kb, 256, 0, s>>>((int)K, ctx->d_W, ctx->d_p1, (EntryEX *)d_tw);
-    NHP_LAUNCHED(ctx);
-    ADJ_CUDA(cudaMemsetAsync(ctx->d_flag, 0, sizeof(int), s));
-    int64_t max_entries = 0, max_col = 0;
-    // ---- child events grouped by node, time order kept: the cached by-node index of the events handle
-    { int rc = nhp_events_build_node_index(ctx, ev); if (rc != NHP_OK) return fin(rc); }
-    const char *envc = getenv("NHP_ADJ_CACHE");
-    bool cached = n > 0 && !(envc && atoi(envc) == 0);
-    // The cached structure stays valid for any horizon it covers: extra pairs beyond the requested cut-off are genuine
-    // predecessors whose (tiny) contributions are simply included.  With a parameter-dependent horizon (Exponential cut-off,
-    // which moves with every conjugate draw) it is built with a 25 % margin so that a chain does not rebuild it every sweep.
-    const bool moving = ctx->kind == NHP_EXPONENTIAL && horizon < ctx->dtmax;
-    const bool have_cache = cached && ev->d_adj_i && ev->adj_cb == (int)col_begin && ev->adj_cs == (int)col_stride &&
-                            (moving ? (ev->adj_horizon >= horizon && ev->adj_horizon <= 2.0 * horizon) : ev->adj_horizon == horizon);
-    if (cached && !have_cache && moving) horizon = std::min(ctx->dtmax, 1.25 * horizon);
-    else if (have_cache) horizon = ev->adj_horizon;
-    if (n > 0) {
-        std::vector<double> mn(K);
-        ADJ_CUDA(cudaMemcpyAsync(mn.data(), ev->d_Mn, K * sizeof(double), cudaMemcpyDeviceToHost, s));
-        if (!have_cache) {  // per-column window totals: only needed to size the buckets
-            ADJ_CUDA(cudaMemsetAsync(d_cc, 0, K * sizeof(unsigned long long), s));
-            k_adj_count<<<(unsigned)((n + 255) / 256), 256, 0, s>>>(ev->d_t, ev->d_c, n, horizon, d_cc);
-            NHP_LAUNCHED(ctx);
-            std::vector<unsigned long long> cc(K);
-            ADJ_CUDA(cudaMemcpyAsync(cc.data(), d_cc, K * sizeof(unsigned long long), cudaMemcpyDeviceToHost, s));
-            ADJ_CUDA(cudaStreamSynchronize(s));
-            for (int64_t k = 0; k < K; k++) max_entries = std::max<int64_t>(max_entries, (int64_t)cc[k]);
-            if (max_entries >= (int64_t)0x3fffffff) return fin(nhp_fail(ctx, NHP_ERR_UNSUPPORTED, "adjacency sampler: a column has %lld window entries (limit 2^30)", (long long)max_entries));
-        }
-        ADJ_CUDA(cudaStreamSynchronize(s));
-        for (int64_t k = 0; k < K; k++) max_col = std::max<int64_t>(max_col, (int64_t)mn[k]);
-    }
-    int grid = (int)std::min<int64_t>(K, (int64_t)ctx->sm_count * 8);  // latency-bound phases: as many columns in flight as the scratch area allows
-    size_t free_b = 0, total_b = 0;
-    cudaMemGetInfo(&free_b, &total_b);
-    int64_t cap = std::max<int64_t>(max_entries, 1), mc = std::max<int64_t>(max_col, 1);
-    // ---- cached structure: (re)build when the data handle has none for this horizon / column partition
-    if (cached && !have_cache) {
-        cudaFree(ev->d_adj_i); cudaFree(ev->d_adj_dt); cudaFree(ev->d_adj_boff); cudaFree(ev->d_adj_col);
-        ev->d_adj_i = nullptr; ev->d_adj_dt = nullptr; ev->d_adj_boff = nullptr; ev->d_adj_col = nullptr; ev->adj_horizon = -1.0;
-        cudaMemGetInfo(&free_b, &total_b);
-        int64_t tot = 0;
-        {
-            std::vector<unsigned long long> cc(K);
-            ADJ_CUDA(cudaMemcpy(cc.data(), d_cc, K * sizeof(unsigned long long), cudaMemcpyDeviceToHost));
-            for (int64_t k = 0; k < K; k++) if (k % col_stride == col_begin) tot += (int64_t)cc[k];
-        }
-        const size_t need = (size_t)tot * 12 + (size_t)K * (K + 1) * sizeof(int) + (size_t)(K + 1) * sizeof(int64_t);
-        const size_t bsmem = (size_t)(2 * K + 2 + 8 * ADJ_WMAX) * sizeof(int);
-        if (need > free_b / 2 + free_b / 4 || bsmem > (size_t)ctx->smem_optin - 1024) cached = false;  // keep room for the sweep's scratch: fall back to the uncached kernel
-        else {
-            ADJ_CUDA(cudaMalloc(&ev->d_adj_i, std::max<size_t>((size_t)tot, 1) * sizeof(unsigned)));
-            ADJ_CUDA(cudaMalloc(&ev->d_adj_dt, std::max<size_t>((size_t)tot, 1) * sizeof(double)));
-            ADJ_CUDA(cudaMalloc(&ev->d_adj_boff, (size_t)K * (K + 1) * sizeof(int)));
-            ADJ_CUDA(cudaMalloc(&ev->d_adj_col, (size_t)(K + 1) * sizeof(int64_t)));
-            ADJ_CUDA(cudaMemsetAsync(ev->d_adj_boff, 0, (size_t)K * (K + 1) * sizeof(int), s));
-            k_adj_scan<<<1, 32, 0, s>>>(d_cc, (int)K, (int)col_begin, (int)col_stride, ev->d_adj_col);
-            NHP_LAUNCHED(ctx);
-            AdjBuildArgs b;
-            b.t = ev->d_t; b.c = ev->d_c; b.order = ev->d_order; b.node_ptr = ev->d_node_ptr; b.K = (int)K; b.horizon = horizon;
-            b.col = ev->d_adj_col; b.boff = ev->d_adj_boff; b.ent_i = ev->d_adj_i; b.ent_dt = ev->d_adj_dt; b.col_begin = (int)col_begin; b.col_stride = (int)col_stride;
-            if (bsmem > 48 * 1024) ADJ_CUDA(cudaFuncSetAttribute(k_adj_build, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bsmem));
-            k_adj_build<<<grid, 256, bsmem, s>>>(b);
-            NHP_LAUNCHED(ctx);
-            ADJ_CUDA(cudaMemsetAsync(d_cc, 0, sizeof(unsigned long long), s));
-            k_adj_max_bucket<<<(unsigned)((KK + 255) / 256), 256, 0, s>>>(ev->d_adj_boff, (int)K, d_cc);
-            NHP_LAUNCHED(ctx);
-            unsigned long long mb = 0;
-            ADJ_CUDA(cudaMemcpyAsync(&mb, d_cc, sizeof(mb), cudaMemcpyDeviceToHost, s));
-            ADJ_CUDA(cudaStreamSynchronize(s));
-            ADJ_CUDA(cudaGetLastError());
-            ev->adj_total = tot; ev->adj_max_bucket = (int64_t)mb; ev->adj_max_col = mc; ev->adj_horizon = horizon;
-            ev->adj_cb = (int)col_begin; ev->adj_cs = (int)col_stride;
-            cudaMemGetInfo(&free_b, &total_b);
-        }
-    }
-    AdjArgs a;
-    a.t = ev->d_t; a.c = ev->d_c; a.n = n; a.order = ev->d_order; a.node_ptr = ev->d_node_ptr; a.Mn = ev->d_Mn; a.K = (int)K; a.table_w = d_tw;
-    a.lambda0 = ctx->d_lambda0; a.W = ctx->d_W; a.A = d_A; a.rho = d_rho; a.u = d_u; a.seed = seed; a.counter = counter;
-    a.D = ctx->dtmax; a.horizon = horizon; a.duration = ev->duration; a.flag = ctx->d_flag; a.col_begin = (int)col_begin; a.col_stride = (int)col_stride;
-    int rc = NHP_OK;
-    if (cached) {
-        const int64_t mb = std::max<int64_t>(ev->adj_max_bucket, 1);
-        const size_t per_cta = (size_t)(2 * mc + mb) * sizeof(double);
-        // Threads per column: the per-column intensity array lam[] (8 B per child event) is gathered at random once per entry.
-        // With 256-thread CTAs ~8 columns share an SM; once their arrays exceed L2 many times over (1e8 events at K = 1000:
-        // 1.9 GB) every gather is a DRAM sector and fewer, larger CTAs win (measured: 163 vs 216 ms); below that the
-        // 256-thread CTAs are faster (1e7 events: 17 vs 30 ms).
-        int bs = 256;
-        {
-            const double lam_bytes = (double)mc * 16.0;  // lam + gacc
-            if (lam_bytes * ctx->sm_count * 8 > 1e9) bs = 1024;
-            const char *envb = getenv("NHP_ADJ_BLOCK");
-            if (envb && (atoi(envb) == 256 || atoi(envb) == 512 || atoi(envb) == 1024)) bs = atoi(envb);
-            grid = (int)std::min<int64_t>(grid, (int64_t)ctx->sm_count * (2048 / bs));
-        }
-        while (grid > 1 && (size_t)grid * per_cta > free_b / 2) grid = (grid + 1) / 2;
-        // per-CTA work areas from the context's persistent scratch buffer (no allocation per sweep)
-        void *sc = nullptr;
-        { int rcs = nhp_scratch(ctx, (size_t)grid * per_cta, &sc); if (rcs != NHP_OK) return fin(rcs); }
-        double *w_lam = (double *)sc, *w_gacc = w_lam + (size_t)grid * mc, *w_vbuf = w_gacc + (size_t)grid * mc;
-        AdjSweepArgs w;
-        w.node_ptr = ev->d_node_ptr; w.Mn = ev->d_Mn; w.K = (int)K; w.table_w = d_tw; w.lambda0 = ctx->d_lambda0; w.W = ctx->d_W; w.A = d_A; w.rho = d_rho; w.u = d_u;
-        w.seed = seed; w.counter = counter; w.D = ctx->dtmax; w.col = ev->d_adj_col; w.boff = ev->d_adj_boff; w.ent_i = ev->d_adj_i; w.ent_dt = ev->d_adj_dt;
-        w.lam = w_lam; w.gacc = w_gacc; w.vbuf = w_vbuf; w.max_col = mc; w.max_bucket = mb; w.flag = ctx->d_flag; w.col_begin = (int)col_begin; w.col_stride = (int)col_stride;
-        rc = nhp_timer_begin(ctx);
-        if (rc != NHP_OK) return fin(rc);
-        if (ctx->kind == NHP_LOGITNORMAL) k_adj_sweep<NHP_LOGITNORMAL><<<grid, bs, 0, s>>>(w);
-        else k_adj_sweep<NHP_EXPONENTIAL><<<grid, bs, 0, s>>>(w);
-    } else {
-    // bound the scratch area: entries cost 12 B per CTA slot
-    while (grid > 1 && (size_t)grid * ((size_t)cap * 12 + (size_t)mc * 16) > free_b / 2) grid = (grid + 1) / 2;
-    if ((size_t)grid * ((size_t)cap * 12 + (size_t)mc * 16) > free_b / 2)
-        return fin(nhp_fail(ctx, NHP_ERR_UNSUPPORTED, "adjacency sampler: one column needs %lld window entries, more than the free device memory holds", (long long)cap));
-    ADJ_CUDA(cudaMalloc(&d_ent_i, (size_t)grid * cap * sizeof(int)));
-    ADJ_CUDA(cudaMalloc(&d_ent_v, (size_t)grid * cap * sizeof(double)));
-    ADJ_CUDA(cudaMalloc(&d_lam, (size_t)grid * mc * sizeof(double)));
-    ADJ_CUDA(cudaMalloc(&d_gacc, (size_t)grid * mc * sizeof(double)));
-    a.cap = cap; a.ent_i = d_ent_i; a.ent_v = d_ent_v; a.lam = d_lam; a.gacc = d_gacc; a.max_col = mc;
-    size_t smem = (size_t)(2 * K + 2) * sizeof(int);
-    rc = nhp_timer_begin(ctx);
-    if (rc != NHP_OK) return fin(rc);
-    if (ctx->kind == NHP_LOGITNORMAL) {
-        if (smem > 48 * 1024) ADJ_CUDA(cudaFuncSetAttribute(k_adjacency<NHP_LOGITNORMAL>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        k_adjacency<NHP_LOGITNORMAL><<<grid, 256, smem, s>>>(a);
-    } else {
-        if (smem > 48 * 1024) ADJ_CUDA(cudaFuncSetAttribute(k_adjacency<NHP_EXPONENTIAL>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        k_adjacency<NHP_EXPONENTIAL><<<grid, 256, smem, s>>>(a);
-    }
-    }
-    NHP_LAUNCHED(ctx);
-    ADJ_CUDA(cudaGetLastError());
-    int flag = 0;
-    ADJ_CUDA(cudaMemcpyAsync(&flag, ctx->d_flag, sizeof(int), cudaMemcpyDeviceToHost, s));
-    rc = nhp_timer_end(ctx);
-    if (rc != NHP_OK) return fin(rc);
-    if (flag & 32) return fin(nhp_fail(ctx, NHP_ERR_CUDA, "adjacency sampler: scratch overflow (internal error)"));
-    if (flag & 64) return fin(nhp_fail(ctx, NHP_ERR_NUMERIC, "adjacency sampler: NaN log-likelihood difference"));
-    ADJ_CUDA(cudaMemcpyAsync(A_inout, d_A, KK * sizeof(double), cudaMemcpyDeviceToHost, s));
-    // the new adjacency becomes the context's A (device to device; the masked tables are rebuilt below)
-    if (ctx->has_A) ADJ_CUDA(cudaMemcpyAsync(ctx->d_A, d_A, KK * sizeof(double), cudaMemcpyDeviceToDevice, s));
-    ADJ_CUDA(cudaStreamSynchronize(s));
-#undef ADJ_CUDA
-    fin(NHP_OK);
-    if (ctx->has_A) {
-        ctx->cont_set = false;
-        ctx->sweep_ll_valid = false;
-        NHP_TRY(nhp_cont_params_refresh(ctx));
-        ctx->cont_set = true;
-    }
+    NHP_CUDA(ctx, cudaMemcpyAsync(ctx->d_adj_rho, rho, KK * sizeof(double), cudaMemcpyHostToDevice, s));
+    NHP_CUDA(ctx, cudaMemcpyAsync(ctx->d_adj_A, A_inout, KK * sizeof(double), cudaMemcpyHostToDevice, s));
+    if (u) NHP_CUDA(ctx, cudaMemcpyAsync(ctx->d_adj_u, u, KK * sizeof(double), cudaMemcpyHostToDevice, s));
+    NHP_TRY(adj_run(ctx, ev, ctx->d_adj_rho, 0.0, u ? ctx->d_adj_u : nullptr, seed, counter, ctx->d_adj_A, col_begin, col_stride));
+    NHP_CUDA(ctx, cudaMemcpyAsync(A_inout, ctx->d_adj_A, KK * sizeof(double), cudaMemcpyDeviceToHost, s));
+    // the new adjacency becomes the context's A (device to device; the masked tables are rebuilt)
+    if (ctx->has_A) NHP_CUDA(ctx, cudaMemcpyAsync(ctx->d_A, ctx->d_adj_A, KK * sizeof(double), cudaMemcpyDeviceToDevice, s));
+    NHP_CUDA(ctx, cudaStreamSynchronize(s));
+    return adj_commit(ctx);
+}
+
+extern "C" int nhp_cont_resample_adjacency_dev(nhp_ctx *ctx, nhp_events *ev, double rho, uint64_t seed, uint64_t counter, int64_t col_begin, int64_t col_stride,
+                                               int commit) {
+    NHP_CHECK(ctx, ctx != nullptr, NHP_ERR_INVALID, "ctx is NULL");
+    NHP_CHECK(ctx, ctx->cont_set, NHP_ERR_STATE, "continuous parameters not set (call nhp_cont_params_set)");
+    NHP_CHECK(ctx, ctx->has_A, NHP_ERR_STATE, "nhp_cont_resample_adjacency_dev: the process has no adjacency matrix");
+    if (rho < 0.0) rho = ctx->rho;
+    NHP_CHECK(ctx, rho >= 0.0 && rho <= 1.0, NHP_ERR_INVALID, "nhp_cont_resample_adjacency_dev: link probability outside [0, 1] (set it, or call nhp_cont_resample_network first)");
+    NHP_TRY(adj_run(ctx, ev, nullptr, rho, nullptr, seed, counter, ctx->d_A, col_begin, col_stride));
+    return commit ? adj_commit(ctx) : NHP_OK;
+}
+
+extern "C" int nhp_cont_adjacency_commit(nhp_ctx *ctx) {
+    NHP_CHECK(ctx, ctx != nullptr, NHP_ERR_INVALID, "ctx is NULL");
+    NHP_CHECK(ctx, ctx->cont_set && ctx->has_A, NHP_ERR_STATE, "nhp_cont_adjacency_commit: no network process parameters on the device");
+    NHP_CUDA(ctx, cudaSetDevice(ctx->device));
+    return adj_commit(ctx);
+}
+
+extern "C" int nhp_cont_adjacency_info(const nhp_ctx *ctx, double *out8) {
+    if (!ctx || !out8) return NHP_ERR_INVALID;
+    for (int i = 0; i < 8; i++) out8[i] = ctx->adj_info[i];
     return NHP_OK;
 }

@@ -143,9 +143,17 @@ int nhp_events_build_node_index(nhp_ctx *ctx, nhp_events *ev) {
     cudaStream_t s = ctx->stream;
     int *d_vals = nullptr, *d_keys = nullptr;
     void *d_tmp = nullptr;
-    NHP_CUDA(ctx, cudaMalloc(&ev->d_order, (size_t)std::max<int64_t>(own, 1) * sizeof(int)));
-    NHP_CUDA(ctx, cudaMalloc(&d_vals, (size_t)std::max<int64_t>(own, 1) * sizeof(int)));
-    NHP_CUDA(ctx, cudaMalloc(&d_keys, (size_t)std::max<int64_t>(own, 1) * sizeof(int)));
+    // every failure path releases the temporaries and leaves the handle without a (partial) index
+    auto fail = [&](cudaError_t e, const char *what) {
+        cudaFree(d_vals); cudaFree(d_keys); cudaFree(d_tmp);
+        cudaFree(ev->d_order); cudaFree(ev->d_node_ptr); cudaFree(ev->d_item_node); cudaFree(ev->d_item_e0);
+        ev->d_order = ev->d_node_ptr = ev->d_item_node = ev->d_item_e0 = nullptr;
+        return nhp_fail(ctx, NHP_ERR_CUDA, "node index: %s failed: %s", what, cudaGetErrorString(e));
+    };
+#define NI_CUDA(call) do { cudaError_t e__ = (call); if (e__ != cudaSuccess) return fail(e__, #call); } while (0)
+    NI_CUDA(cudaMalloc(&ev->d_order, (size_t)std::max<int64_t>(own, 1) * sizeof(int)));
+    NI_CUDA(cudaMalloc(&d_vals, (size_t)std::max<int64_t>(own, 1) * sizeof(int)));
+    NI_CUDA(cudaMalloc(&d_keys, (size_t)std::max<int64_t>(own, 1) * sizeof(int)));
     if (own > 0) {
         k_child_iota<<<(unsigned)((own + 255) / 256), 256, 0, s>>>(d_vals, own, (int)ev->n_halo);
         NHP_LAUNCHED(ctx);
@@ -153,14 +161,15 @@ int nhp_events_build_node_index(nhp_ctx *ctx, nhp_events *ev) {
         while ((1 << bits) < K) bits++;
         size_t tb = 0;
         cub::DeviceRadixSort::SortPairs(nullptr, tb, ev->d_c + ev->n_halo, d_keys, d_vals, ev->d_order, (int)own, 0, bits, s);
-        NHP_CUDA(ctx, cudaMalloc(&d_tmp, tb));
-        NHP_CUDA(ctx, cub::DeviceRadixSort::SortPairs(d_tmp, tb, ev->d_c + ev->n_halo, d_keys, d_vals, ev->d_order, (int)own, 0, bits, s));  // stable
+        NI_CUDA(cudaMalloc(&d_tmp, tb));
+        NI_CUDA(cub::DeviceRadixSort::SortPairs(d_tmp, tb, ev->d_c + ev->n_halo, d_keys, d_vals, ev->d_order, (int)own, 0, bits, s));  // stable
         NHP_LAUNCHED(ctx);
     }
     std::vector<double> mn(K);
-    NHP_CUDA(ctx, cudaMemcpyAsync(mn.data(), ev->d_Mn, (size_t)K * sizeof(double), cudaMemcpyDeviceToHost, s));
-    NHP_CUDA(ctx, cudaStreamSynchronize(s));
+    NI_CUDA(cudaMemcpyAsync(mn.data(), ev->d_Mn, (size_t)K * sizeof(double), cudaMemcpyDeviceToHost, s));
+    NI_CUDA(cudaStreamSynchronize(s));
     cudaFree(d_vals); cudaFree(d_keys); cudaFree(d_tmp);
+    d_vals = d_keys = nullptr; d_tmp = nullptr;
     std::vector<int> ptr(K + 1), inode, ie0;
     int run = 0;
     for (int64_t k = 0; k < K; k++) {
@@ -171,14 +180,15 @@ int nhp_events_build_node_index(nhp_ctx *ctx, nhp_events *ev) {
     }
     ptr[K] = run;
     ev->n_items = (int64_t)inode.size();
-    NHP_CUDA(ctx, cudaMalloc(&ev->d_node_ptr, (size_t)(K + 1) * sizeof(int)));
-    NHP_CUDA(ctx, cudaMalloc(&ev->d_item_node, std::max<size_t>(inode.size(), 1) * sizeof(int)));
-    NHP_CUDA(ctx, cudaMalloc(&ev->d_item_e0, std::max<size_t>(inode.size(), 1) * sizeof(int)));
-    NHP_CUDA(ctx, cudaMemcpy(ev->d_node_ptr, ptr.data(), (size_t)(K + 1) * sizeof(int), cudaMemcpyHostToDevice));
+    NI_CUDA(cudaMalloc(&ev->d_node_ptr, (size_t)(K + 1) * sizeof(int)));
+    NI_CUDA(cudaMalloc(&ev->d_item_node, std::max<size_t>(inode.size(), 1) * sizeof(int)));
+    NI_CUDA(cudaMalloc(&ev->d_item_e0, std::max<size_t>(inode.size(), 1) * sizeof(int)));
+    NI_CUDA(cudaMemcpy(ev->d_node_ptr, ptr.data(), (size_t)(K + 1) * sizeof(int), cudaMemcpyHostToDevice));
     if (!inode.empty()) {
-        NHP_CUDA(ctx, cudaMemcpy(ev->d_item_node, inode.data(), inode.size() * sizeof(int), cudaMemcpyHostToDevice));
-        NHP_CUDA(ctx, cudaMemcpy(ev->d_item_e0, ie0.data(), ie0.size() * sizeof(int), cudaMemcpyHostToDevice));
+        NI_CUDA(cudaMemcpy(ev->d_item_node, inode.data(), inode.size() * sizeof(int), cudaMemcpyHostToDevice));
+        NI_CUDA(cudaMemcpy(ev->d_item_e0, ie0.data(), ie0.size() * sizeof(int), cudaMemcpyHostToDevice));
     }
+#undef NI_CUDA
     return NHP_OK;
 }
 
@@ -208,7 +218,7 @@ int nhp_cont_try_child(nhp_ctx *ctx, nhp_events *ev, SweepArgs &a, int mode, int
     ca.s = a; ca.order = ev->d_order; ca.node_ptr = ev->d_node_ptr; ca.item_node = ev->d_item_node; ca.item_e0 = ev->d_item_e0;
     ca.nitems = ev->n_items; ca.mode = mode; ca.wlen = ev->d_wlen;
     auto launch = [&](auto kernel) -> int {
-        if (smem > 32 * 1024) NHP_CUDA(ctx, cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));  // static + dynamic may exceed the 48 KB default
+        NHP_CUDA(ctx, cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)std::max<size_t>(smem, 1024)));  // always: static + dynamic may exceed the 48 KB default even when the dynamic part is small
         NHP_CUDA(ctx, cudaFuncSetAttribute(kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
         int per_sm = 1;
         NHP_CUDA(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, block, smem));

@@ -11,6 +11,7 @@
 // Gamma: Marsaglia & Tsang (2000) with the shape < 1 boost; Normal: Box-Muller.  Parity with the reference is
 // distributional (Julia's own samplers are not reproducible from uniforms): tests check the moments.
 #include "nhp_internal.cuh"
+#include <algorithm>
 #include <cmath>
 #include <vector>
 
@@ -92,33 +93,50 @@ __global__ void k_conjugate(const ConjArgs a) {
     }
 }
 
-// scalars the host keeps about the parameters: [lambda0 min, lambda0 sum, theta min, max |w theta|, #non-zero effective weights]
-__global__ void k_param_scan(int K, int kind, const double *__restrict__ lambda0, const double *__restrict__ W, const double *__restrict__ A,
-                             const double *__restrict__ p1, double *__restrict__ out) {
-    __shared__ double s_min[256], s_sum[256], s_tmin[256], s_wmax[256], s_nnz[256];
-    double l0min = INFINITY, l0sum = 0.0, tmin = INFINITY, wmax = 0.0, nnz = 0.0;
+// scalars the host keeps about the parameters: [lambda0 min, lambda0 sum, theta min, max |w theta|, #non-zero effective weights,
+// theta min and max |W theta| over all entries with W != 0 (adjacency sampler), sum of A]; one partial row of 8 per block
+constexpr int PS_BLOCKS = 128;
+__global__ void __launch_bounds__(256) k_param_scan(int K, int kind, const double *__restrict__ lambda0, const double *__restrict__ W, const double *__restrict__ A,
+                                                    const double *__restrict__ p1, double *__restrict__ part) {
+    __shared__ double s_v[8][256];
+    double l0min = INFINITY, l0sum = 0.0, tmin = INFINITY, wmax = 0.0, nnz = 0.0, tmin_all = INFINITY, wmax_all = 0.0, asum = 0.0;
     const int64_t KK = (int64_t)K * K;
-    for (int64_t e = threadIdx.x; e < KK; e += blockDim.x) {
+    for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < KK; e += (int64_t)gridDim.x * blockDim.x) {
         if (e < K) { l0min = fmin(l0min, lambda0[e]); l0sum += lambda0[e]; }
-        const double w = A ? A[e] * W[e] : W[e];
+        const double w0 = W[e], a = A ? A[e] : 1.0;
+        const double w = a * w0;
+        asum += a;
         if (w != 0.0) {
             nnz += 1.0;
             if (kind == NHP_EXPONENTIAL) { tmin = fmin(tmin, p1[e]); wmax = fmax(wmax, fabs(w * p1[e])); }
         }
+        if (kind == NHP_EXPONENTIAL && w0 != 0.0) { tmin_all = fmin(tmin_all, p1[e]); wmax_all = fmax(wmax_all, fabs(w0 * p1[e])); }
     }
-    s_min[threadIdx.x] = l0min; s_sum[threadIdx.x] = l0sum; s_tmin[threadIdx.x] = tmin; s_wmax[threadIdx.x] = wmax; s_nnz[threadIdx.x] = nnz;
+    const int t = threadIdx.x;
+    s_v[0][t] = l0min; s_v[1][t] = l0sum; s_v[2][t] = tmin; s_v[3][t] = wmax; s_v[4][t] = nnz; s_v[5][t] = tmin_all; s_v[6][t] = wmax_all; s_v[7][t] = asum;
     __syncthreads();
     for (int s = blockDim.x / 2; s > 0; s >>= 1) {
-        if ((int)threadIdx.x < s) {
-            s_min[threadIdx.x] = fmin(s_min[threadIdx.x], s_min[threadIdx.x + s]);
-            s_sum[threadIdx.x] += s_sum[threadIdx.x + s];
-            s_tmin[threadIdx.x] = fmin(s_tmin[threadIdx.x], s_tmin[threadIdx.x + s]);
-            s_wmax[threadIdx.x] = fmax(s_wmax[threadIdx.x], s_wmax[threadIdx.x + s]);
-            s_nnz[threadIdx.x] += s_nnz[threadIdx.x + s];
+        if (t < s) {
+            s_v[0][t] = fmin(s_v[0][t], s_v[0][t + s]); s_v[1][t] += s_v[1][t + s];
+            s_v[2][t] = fmin(s_v[2][t], s_v[2][t + s]); s_v[3][t] = fmax(s_v[3][t], s_v[3][t + s]);
+            s_v[4][t] += s_v[4][t + s];
+            s_v[5][t] = fmin(s_v[5][t], s_v[5][t + s]); s_v[6][t] = fmax(s_v[6][t], s_v[6][t + s]);
+            s_v[7][t] += s_v[7][t + s];
         }
         __syncthreads();
     }
-    if (threadIdx.x == 0) { out[0] = s_min[0]; out[1] = s_sum[0]; out[2] = s_tmin[0]; out[3] = s_wmax[0]; out[4] = s_nnz[0]; }
+    if (t < 8) part[(size_t)blockIdx.x * 8 + t] = s_v[t][0];
+}
+__global__ void k_param_scan_final(const double *__restrict__ part, int nb, double *__restrict__ out) {
+    const int t = threadIdx.x;  // 8 threads, one per scalar; fixed order => deterministic
+    if (t >= 8) return;
+    const bool is_min = t == 0 || t == 2 || t == 5, is_max = t == 3 || t == 6;
+    double v = is_min ? INFINITY : 0.0;
+    for (int b = 0; b < nb; b++) {
+        const double x = part[(size_t)b * 8 + t];
+        v = is_min ? fmin(v, x) : (is_max ? fmax(v, x) : v + x);
+    }
+    out[t] = v;
 }
 
 int nhp_cont_derive_tables(nhp_ctx *ctx);  // nhp_context.cu: masked tables, bit rows, row sums from the device-resident raw parameters
@@ -127,16 +145,21 @@ int nhp_cont_derive_tables(nhp_ctx *ctx);  // nhp_context.cu: masked tables, bit
 int nhp_cont_params_refresh(nhp_ctx *ctx) {
     cudaStream_t s = ctx->stream;
     const int64_t K = ctx->K;
-    void *scratch;
-    NHP_TRY(nhp_partials(ctx, 8, (double **)&scratch));
-    k_param_scan<<<1, 256, 0, s>>>((int)K, ctx->kind, ctx->d_lambda0, ctx->d_W, ctx->has_A ? ctx->d_A : nullptr, ctx->d_p1, (double *)scratch);
+    double *scratch;
+    NHP_TRY(nhp_partials(ctx, 8 * (PS_BLOCKS + 1), &scratch));
+    const int nb = (int)std::min<int64_t>(PS_BLOCKS, (K * K + 255) / 256);
+    k_param_scan<<<nb, 256, 0, s>>>((int)K, ctx->kind, ctx->d_lambda0, ctx->d_W, ctx->has_A ? ctx->d_A : nullptr, ctx->d_p1, scratch + 8);
     NHP_LAUNCHED(ctx);
-    double h[5];
+    k_param_scan_final<<<1, 32, 0, s>>>(scratch + 8, nb, scratch);
+    NHP_LAUNCHED(ctx);
+    double h[8];
     NHP_CUDA(ctx, cudaMemcpyAsync(h, scratch, sizeof(h), cudaMemcpyDeviceToHost, s));
     NHP_TRY(nhp_cont_derive_tables(ctx));
     NHP_CUDA(ctx, cudaStreamSynchronize(s));
     ctx->lambda0_min = h[0]; ctx->lambda0_sum = h[1]; ctx->theta_min = h[2]; ctx->wt_max = h[3];
     ctx->density = h[4] / (double)(K * K);
+    ctx->theta_min_all = h[5]; ctx->wt_max_all = h[6];
+    ctx->a_sum = ctx->has_A ? h[7] : (double)(K * K);
     return NHP_OK;
 }
 
@@ -193,5 +216,73 @@ extern "C" int nhp_cont_params_get(nhp_ctx *ctx, double *lambda0, double *W, dou
         NHP_CUDA(ctx, cudaMemcpyAsync(p2, ctx->d_p2, (size_t)KK * sizeof(double), cudaMemcpyDeviceToHost, s));
     }
     NHP_CUDA(ctx, cudaStreamSynchronize(s));
+    return NHP_OK;
+}
+
+// rho ~ Beta(alpha + sum(A), beta + K^2 - sum(A))  (networks.jl:72-78) as a ratio of two Gamma draws, on the device so that every
+// rank of a multi-GPU chain draws the same value from the same (seed, counter); out[0] = rho
+__global__ void k_network_draw(uint64_t seed, uint64_t counter, double a, double b, double *out) {
+    if (threadIdx.x != 0 || blockIdx.x != 0) return;
+    PhiloxStream r(seed, 0u, 3u, counter);
+    const double x = r.gamma(a, 1.0), y = r.gamma(b, 1.0);
+    out[0] = x / (x + y);
+}
+
+extern "C" int nhp_cont_resample_network(nhp_ctx *ctx, uint64_t seed, uint64_t counter, double alpha, double beta, double *rho_out) {
+    NHP_CHECK(ctx, ctx != nullptr, NHP_ERR_INVALID, "ctx is NULL");
+    NHP_CHECK(ctx, ctx->cont_set && ctx->has_A, NHP_ERR_STATE, "nhp_cont_resample_network: no network process parameters on the device");
+    NHP_CHECK(ctx, alpha > 0.0 && beta > 0.0, NHP_ERR_INVALID, "nhp_cont_resample_network: alpha and beta must be positive");
+    NHP_CUDA(ctx, cudaSetDevice(ctx->device));
+    double *scratch;
+    NHP_TRY(nhp_partials(ctx, 8, &scratch));
+    const double KK = (double)ctx->K * (double)ctx->K;
+    k_network_draw<<<1, 32, 0, ctx->stream>>>(seed, counter, alpha + ctx->a_sum, beta + KK - ctx->a_sum, scratch);
+    NHP_LAUNCHED(ctx);
+    double rho = 0.0;
+    NHP_CUDA(ctx, cudaMemcpyAsync(&rho, scratch, sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+    NHP_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    ctx->rho = rho;
+    if (rho_out) *rho_out = rho;
+    return NHP_OK;
+}
+
+extern "C" int nhp_cont_network_set(nhp_ctx *ctx, double rho) {
+    NHP_CHECK(ctx, ctx != nullptr, NHP_ERR_INVALID, "ctx is NULL");
+    NHP_CHECK(ctx, rho >= 0.0 && rho <= 1.0, NHP_ERR_INVALID, "BernoulliNetworkModel: link probability must be in [0, 1]");
+    ctx->rho = rho;
+    return NHP_OK;
+}
+
+// ---- development hooks (include/nhp_devel.h): device-side snapshot of the parameters
+extern "C" int nhp_cont_params_save(nhp_ctx *ctx) {
+    NHP_CHECK(ctx, ctx != nullptr, NHP_ERR_INVALID, "ctx is NULL");
+    NHP_CHECK(ctx, ctx->cont_set, NHP_ERR_STATE, "continuous parameters not set");
+    NHP_CUDA(ctx, cudaSetDevice(ctx->device));
+    const size_t K = (size_t)ctx->K, KK = K * K;
+    if (!ctx->d_save) NHP_CUDA(ctx, cudaMalloc(&ctx->d_save, (K + 4 * KK) * sizeof(double)));
+    cudaStream_t s = ctx->stream;
+    NHP_CUDA(ctx, cudaMemcpyAsync(ctx->d_save, ctx->d_lambda0, K * sizeof(double), cudaMemcpyDeviceToDevice, s));
+    NHP_CUDA(ctx, cudaMemcpyAsync(ctx->d_save + K, ctx->d_W, KK * sizeof(double), cudaMemcpyDeviceToDevice, s));
+    NHP_CUDA(ctx, cudaMemcpyAsync(ctx->d_save + K + KK, ctx->d_A, KK * sizeof(double), cudaMemcpyDeviceToDevice, s));
+    NHP_CUDA(ctx, cudaMemcpyAsync(ctx->d_save + K + 2 * KK, ctx->d_p1, KK * sizeof(double), cudaMemcpyDeviceToDevice, s));
+    NHP_CUDA(ctx, cudaMemcpyAsync(ctx->d_save + K + 3 * KK, ctx->d_p2, KK * sizeof(double), cudaMemcpyDeviceToDevice, s));
+    NHP_CUDA(ctx, cudaStreamSynchronize(s));
+    return NHP_OK;
+}
+extern "C" int nhp_cont_params_restore(nhp_ctx *ctx) {
+    NHP_CHECK(ctx, ctx != nullptr, NHP_ERR_INVALID, "ctx is NULL");
+    NHP_CHECK(ctx, ctx->cont_set && ctx->d_save, NHP_ERR_STATE, "nhp_cont_params_restore: nothing saved");
+    NHP_CUDA(ctx, cudaSetDevice(ctx->device));
+    const size_t K = (size_t)ctx->K, KK = K * K;
+    cudaStream_t s = ctx->stream;
+    NHP_CUDA(ctx, cudaMemcpyAsync(ctx->d_lambda0, ctx->d_save, K * sizeof(double), cudaMemcpyDeviceToDevice, s));
+    NHP_CUDA(ctx, cudaMemcpyAsync(ctx->d_W, ctx->d_save + K, KK * sizeof(double), cudaMemcpyDeviceToDevice, s));
+    NHP_CUDA(ctx, cudaMemcpyAsync(ctx->d_A, ctx->d_save + K + KK, KK * sizeof(double), cudaMemcpyDeviceToDevice, s));
+    NHP_CUDA(ctx, cudaMemcpyAsync(ctx->d_p1, ctx->d_save + K + 2 * KK, KK * sizeof(double), cudaMemcpyDeviceToDevice, s));
+    NHP_CUDA(ctx, cudaMemcpyAsync(ctx->d_p2, ctx->d_save + K + 3 * KK, KK * sizeof(double), cudaMemcpyDeviceToDevice, s));
+    ctx->cont_set = false;
+    ctx->sweep_ll_valid = false;
+    NHP_TRY(nhp_cont_params_refresh(ctx));
+    ctx->cont_set = true;
     return NHP_OK;
 }

@@ -128,13 +128,13 @@ int nhp_cont_try_exp_scan(nhp_ctx *ctx, nhp_events *ev, SweepArgs &a, int *grid_
     x.S = (double *)scratch;
     cudaStream_t s = ctx->stream;
     if (x.nchunks > 1) {
-        if (smem_agg > 32 * 1024) NHP_CUDA(ctx, cudaFuncSetAttribute(k_exp_chunk_aggregate, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_agg));
+        NHP_CUDA(ctx, cudaFuncSetAttribute(k_exp_chunk_aggregate, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_agg));
         k_exp_chunk_aggregate<<<(unsigned)(x.nchunks - 1), 256, smem_agg, s>>>(x);
         NHP_LAUNCHED(ctx);
     }
     k_exp_chunk_scan<<<(unsigned)((K * K + 127) / 128), 128, 0, s>>>(x);
     NHP_LAUNCHED(ctx);
-    if (smem_ll > 32 * 1024) NHP_CUDA(ctx, cudaFuncSetAttribute(k_exp_chunk_loglik, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_ll));
+    NHP_CUDA(ctx, cudaFuncSetAttribute(k_exp_chunk_loglik, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_ll));
     const int grid = (int)std::min<int64_t>(x.nchunks, (int64_t)ctx->sm_count * 8);
     k_exp_chunk_loglik<<<grid, 256, smem_ll, s>>>(x);
     NHP_LAUNCHED(ctx);

@@ -212,7 +212,7 @@ extern "C" int nhp_cont_loglik_grad_dev(nhp_ctx *ctx, nhp_events *ev, int recurs
         NHP_TRY(nhp_partials(ctx, 2 * (int64_t)ctx->sm_count * 32, &ga.s.partials));
         int grid = 0;
         auto launch = [&](auto kernel) -> int {
-            if (smem > 32 * 1024) NHP_CUDA(ctx, cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            NHP_CUDA(ctx, cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)std::max<size_t>(smem, 1024)));
             NHP_CUDA(ctx, cudaFuncSetAttribute(kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
             int per_sm = 1;
             const int fit = (int)std::max<size_t>(1, lim / std::max<size_t>(smem, 1));

@@ -370,7 +370,7 @@ static LaunchPlan make_plan(nhp_ctx *ctx, const nhp_events *ev) {
 // persistent launch: one resident wave of CTAs looping over the tiles
 template <typename KernelT, typename... Extra>
 static int launch_persistent(nhp_ctx *ctx, KernelT kernel, LaunchPlan &p, size_t smem, const SweepArgs &a, Extra... extra) {
-    if (smem > 32 * 1024) NHP_CUDA(ctx, cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));  // static + dynamic may exceed the 48 KB default
+    NHP_CUDA(ctx, cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)std::max<size_t>(smem, 1024)));  // always: static + dynamic may exceed the 48 KB default even when the dynamic part is small
     NHP_CUDA(ctx, cudaFuncSetAttribute(kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
     int per_sm = 1;
     NHP_CUDA(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, NHP_BLOCK, smem));

@@ -971,7 +971,7 @@ extern "C" int nhp_disc_gibbs_counts(nhp_ctx *ctx, nhp_disc *dd, uint64_t seed, 
                                                                         sparse ? ctx->dd_klist : nullptr, ctx->dd_kptr, ctx->dd_btc, (int)ctx->dd_maxNA);
         } else {
         size_t smem = (size_t)(NB + 1) * sizeof(double);
-        if (smem > 48 * 1024) DCUDA(ctx, cudaFuncSetAttribute(k_disc_gibbs, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        DCUDA(ctx, cudaFuncSetAttribute(k_disc_gibbs, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         k_disc_gibbs<<<(unsigned)(N * slabs), 256, smem, s>>>(dd->d_conv, ctx->dd_bump + NB * N, ctx->dd_lambda0, ctx->ddt, (int)N, (int)NB, ex->nz_t, ex->nz_s, ex->nz_off,
                                                                ex->child_ptr, slabs, d_u, seed, counter, d_counts, ctx->d_flag);
         }
@@ -1256,7 +1256,7 @@ extern "C" int nhp_disc_resample_adjacency(nhp_ctx *ctx, nhp_disc *dd, const dou
         int max_ne = 0;
         for (int64_t c = 0; c < N; c++) max_ne = std::max(max_ne, cp[c + 1] - cp[c]);
         if (max_ne > 0) {
-            if (coef_smem > 32 * 1024) DCUDA(ctx, cudaFuncSetAttribute(k_disc_adj_gather, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)coef_smem));
+            DCUDA(ctx, cudaFuncSetAttribute(k_disc_adj_gather, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)coef_smem));
             dim3 gg((unsigned)((max_ne + ADJ_TE - 1) / ADJ_TE), (unsigned)N);
             k_disc_adj_gather<<<gg, 256, coef_smem, s>>>(dd->d_conv, ctx->dd_lambda0, ctx->dd_W, ctx->dd_theta, ctx->ddt, d_A, (int)N, (int)B, ex->nz_t, ex->child_ptr, d_lam, d_G);
             NHP_LAUNCHED(ctx);

@@ -65,6 +65,9 @@ static void free_cont(nhp_ctx *ctx) {
     cudaFree(ctx->d_lambda0); cudaFree(ctx->d_W); cudaFree(ctx->d_A); cudaFree(ctx->d_p1); cudaFree(ctx->d_p2);
     cudaFree(ctx->d_table); cudaFree(ctx->d_rowsum); cudaFree(ctx->d_rowsum_w); cudaFree(ctx->d_abits);
     cudaFree(ctx->d_stats0); cudaFree(ctx->d_stats1); cudaFree(ctx->d_xbar);
+    cudaFree(ctx->d_adj_tw); cudaFree(ctx->d_adj_rho); cudaFree(ctx->d_adj_u); cudaFree(ctx->d_adj_A); cudaFree(ctx->d_save);
+    ctx->d_save = nullptr;
+    ctx->d_adj_tw = nullptr; ctx->d_adj_rho = ctx->d_adj_u = ctx->d_adj_A = nullptr;
     ctx->d_lambda0 = ctx->d_W = ctx->d_A = ctx->d_p1 = ctx->d_p2 = ctx->d_rowsum = ctx->d_rowsum_w = nullptr;
     ctx->d_table = nullptr; ctx->d_abits = nullptr; ctx->d_stats0 = ctx->d_stats1 = ctx->d_xbar = nullptr;
     ctx->cap_K = 0;
@@ -78,6 +81,7 @@ extern "C" int nhp_destroy(nhp_ctx *ctx) {
     cudaFree(ctx->d_partials); cudaFree(ctx->d_scratch); cudaFree(ctx->d_flag); cudaFree(ctx->d_winstat);
     cudaFree(ctx->dd_lambda0); cudaFree(ctx->dd_W); cudaFree(ctx->dd_A); cudaFree(ctx->dd_theta); cudaFree(ctx->dd_bump);
     cudaFree(ctx->dd_klist); cudaFree(ctx->dd_kptr); cudaFree(ctx->dd_btc);
+    cudaFree(ctx->d_adj_ctl); cudaFree(ctx->d_adj_stat);
     cudaEventDestroy(ctx->ev0); cudaEventDestroy(ctx->ev1);
     cudaStreamDestroy(ctx->own_stream);
     delete ctx;
@@ -229,6 +233,15 @@ extern "C" int nhp_events_upload(nhp_ctx *ctx, const double *times, const int64_
     return NHP_OK;
 }
 
+// cached structure of the adjacency sampler (cont_adjacency.cu)
+void nhp_events_free_adjacency(nhp_events *ev) {
+    cudaFree(ev->d_adj_vstart); cudaFree(ev->d_adj_vnode); cudaFree(ev->d_adj_vbase); cudaFree(ev->d_adj_boff);
+    cudaFree(ev->d_adj_i); cudaFree(ev->d_adj_dt); cudaFree(ev->d_adj_lam);
+    ev->d_adj_vstart = ev->d_adj_vnode = ev->d_adj_boff = nullptr; ev->d_adj_vbase = nullptr; ev->d_adj_i = nullptr;
+    ev->d_adj_dt = ev->d_adj_lam = nullptr;
+    ev->adj_horizon = -1.0; ev->adj_total = 0; ev->adj_nv = 0;
+}
+
 extern "C" int nhp_events_free(nhp_ctx *ctx, nhp_events *ev) {
     if (!ev) return NHP_OK;
     if (ctx) {
@@ -244,7 +257,7 @@ extern "C" int nhp_events_free(nhp_ctx *ctx, nhp_events *ev) {
         cudaFree(ev->d_t); cudaFree(ev->d_c); cudaFree(ev->d_poff); cudaFree(ev->d_Mn); cudaFree(ev->d_tile_lo); cudaFree(ev->d_wlen);
     }
     cudaFree(ev->d_order); cudaFree(ev->d_node_ptr); cudaFree(ev->d_item_node); cudaFree(ev->d_item_e0);
-    cudaFree(ev->d_adj_i); cudaFree(ev->d_adj_dt); cudaFree(ev->d_adj_boff); cudaFree(ev->d_adj_col);
+    nhp_events_free_adjacency(ev);
     delete ev;
     return NHP_OK;
 }
@@ -336,7 +349,7 @@ extern "C" int nhp_cont_params_set(nhp_ctx *ctx, int kind, int64_t K, const doub
         l0min = std::min(l0min, lambda0[k]);
         l0sum += lambda0[k];
     }
-    double thmin = std::numeric_limits<double>::infinity(), wtmax = 0.0;
+    double thmin = std::numeric_limits<double>::infinity(), wtmax = 0.0, thmin_all = thmin, wtmax_all = 0.0;
     int64_t nnz = 0;
     for (int64_t e = 0; e < KK; e++) {
         double w = A ? A[e] * W[e] : W[e];
@@ -344,6 +357,8 @@ extern "C" int nhp_cont_params_set(nhp_ctx *ctx, int kind, int64_t K, const doub
             nnz++;
             if (kind == NHP_EXPONENTIAL) { thmin = std::min(thmin, p1[e]); wtmax = std::max(wtmax, fabs(w * p1[e])); }
         }
+        // the adjacency sampler also evaluates the links that are currently off (continuous.jl:477-483)
+        if (kind == NHP_EXPONENTIAL && W[e] != 0.0) { thmin_all = std::min(thmin_all, p1[e]); wtmax_all = std::max(wtmax_all, fabs(W[e] * p1[e])); }
     }
     if (ctx->cap_K != K) {
         NHP_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
@@ -372,6 +387,8 @@ extern "C" int nhp_cont_params_set(nhp_ctx *ctx, int kind, int64_t K, const doub
     ctx->kind = kind; ctx->K = K; ctx->dtmax = dtmax; ctx->has_A = (A != nullptr);
     ctx->density = (double)nnz / (double)KK;
     ctx->theta_min = thmin; ctx->wt_max = wtmax; ctx->lambda0_min = l0min; ctx->lambda0_sum = l0sum;
+    ctx->theta_min_all = thmin_all; ctx->wt_max_all = wtmax_all;
+    { double as = 0.0; if (A) for (int64_t e = 0; e < KK; e++) as += A[e]; ctx->a_sum = A ? as : (double)KK; }
     cudaStream_t s = ctx->stream;
     NHP_CUDA(ctx, cudaMemcpyAsync(ctx->d_lambda0, lambda0, (size_t)K * sizeof(double), cudaMemcpyHostToDevice, s));
     NHP_CUDA(ctx, cudaMemcpyAsync(ctx->d_W, W, (size_t)KK * sizeof(double), cudaMemcpyHostToDevice, s));

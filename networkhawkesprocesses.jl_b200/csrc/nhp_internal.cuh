@@ -6,6 +6,7 @@
 #include <string>
 #include <vector>
 #include "../../include/nhp.h"
+#include "../../include/nhp_devel.h"
 #include "fastmath.cuh"
 
 #define NHP_VERSION 100
@@ -82,15 +83,22 @@ struct nhp_events {
     // by-node order of the own events + work items of the child-major sweep (cont_child.cu), built on first use
     int *d_order = nullptr, *d_node_ptr = nullptr, *d_item_node = nullptr, *d_item_e0 = nullptr;
     int64_t n_items = 0;
-    // cached structure of the adjacency sampler (cont_adjacency.cu): every (child event, window predecessor) pair, grouped by child
-    // column and bucketed by parent node; depends on the data and the look-back horizon only, so it survives across Gibbs sweeps
+    // cached structure of the adjacency sampler (cont_adjacency.cu): every (child event, window predecessor) pair, grouped by
+    // virtual column = (child column, time chunk of at most adj_chunk_cap of the column's events) and bucketed by parent node,
+    // stably ordered (event, window position) inside a bucket; depends on the data and the look-back horizon only
     double adj_horizon = -1.0;       // horizon the structure was built with
     int adj_cb = 0, adj_cs = 1;      // column partition it was built for
-    unsigned *d_adj_i = nullptr;     // [adj_total] child event index inside its column | bit 31: the (event, parent) pair occurs more than once
+    int adj_chunk_cap = 0;           // chunk capacity (child events) it was built with
+    int adj_chunk_max = 0;           // largest chunk actually present (sizes the sweep's shared memory)
+    int64_t adj_nv = 0;              // number of virtual columns
+    int *d_adj_vstart = nullptr;     // [K+1] first virtual column of every column
+    int *d_adj_vnode = nullptr;      // [nv] child column of every virtual column
+    int64_t *d_adj_vbase = nullptr;  // [nv+1] first entry of every virtual column
+    int *d_adj_boff = nullptr;       // [nv][K+1] bucket offsets inside a virtual column
+    unsigned short *d_adj_i = nullptr;  // [adj_total] child event index inside its chunk | bit 15: same (event, parent) as the previous entry
     double *d_adj_dt = nullptr;      // [adj_total] t_i - t_j
-    int *d_adj_boff = nullptr;       // [K][K+1] bucket offsets inside a column
-    int64_t *d_adj_col = nullptr;    // [K+1] first entry of every column
-    int64_t adj_total = 0, adj_max_bucket = 0, adj_max_col = 0;
+    double *d_adj_lam = nullptr;     // [n] per-event intensity in by-node order (work array of the sweep)
+    int64_t adj_total = 0;
     int64_t max_win = 0;        // max over boundaries of (i0 - lo)
     double mean_win = 0.0;
 };
@@ -123,8 +131,10 @@ struct nhp_ctx {
     bool has_A = false;
     bool grad_valid = false;    // the statistics buffers hold a gradient (nhp_cont_loglik_grad_dev)
     double density = 1.0;       // fraction of non-zero effective weights
-    double theta_min = 0.0, wt_max = 0.0, lambda0_min = 0.0; // Exponential cut-off horizon inputs
+    double theta_min = 0.0, wt_max = 0.0, lambda0_min = 0.0; // Exponential cut-off horizon inputs (links with A*W != 0)
+    double theta_min_all = 0.0, wt_max_all = 0.0;            // the same over all K^2 entries with W != 0 (adjacency sampler: it evaluates inactive links too)
     double lambda0_sum = 0.0;
+    double a_sum = 0.0;           // sum of the adjacency matrix (number of links), refreshed with the tables
     double *d_lambda0 = nullptr;  // [K]
     double *d_W = nullptr, *d_A = nullptr, *d_p1 = nullptr, *d_p2 = nullptr; // raw [K*K] parent-major as passed
     void *d_table = nullptr;      // EntryLN/EntryEX [K*K] child-major
@@ -133,6 +143,14 @@ struct nhp_ctx {
     uint32_t *d_abits = nullptr;  // adjacency/non-zero bitmask, child-major rows of abits_words words
     int64_t abits_words = 0;
     int64_t cap_K = 0;            // allocated for this K
+    // adjacency sampler work buffers (allocated on first use, sized by cap_K)
+    void *d_adj_tw = nullptr;     // EntryLN/EntryEX [K*K] child-major, without the adjacency factor
+    double *d_adj_rho = nullptr, *d_adj_u = nullptr, *d_adj_A = nullptr;  // [K*K] staging of host arguments
+    int *d_adj_ctl = nullptr;     // [8] dynamic work counters of the build / sweep kernels
+    unsigned long long *d_adj_stat = nullptr;  // [8] sweep diagnostics (steps, batches, flips, recomputed steps)
+    double *d_save = nullptr;     // nhp_cont_params_save: [K + 4 K^2] copy of lambda0, W, A, p1, p2
+    double rho = -1.0;            // link probability of the Bernoulli network kept with the context (nhp_cont_resample_network)
+    double adj_info[8] = {0};     // last adjacency sweep: steps, batches, flips, recomputed steps, entries, chunks, kernel ms, build ms
 
     // ---- statistics
     double *d_stats0 = nullptr;   // StatsLayout
@@ -246,3 +264,4 @@ int nhp_cont_prepare_windows(nhp_ctx *ctx, nhp_events *ev, double horizon);
 int nhp_cont_run_loglik(nhp_ctx *ctx, nhp_events *ev, int recursive);
 double nhp_cont_horizon_value(const nhp_ctx *ctx, int64_t n_total, int recursive);
 int nhp_events_build_node_index(nhp_ctx *ctx, nhp_events *ev);  // d_order / d_node_ptr (cont_child.cu)
+void nhp_events_free_adjacency(nhp_events *ev);                 // cached structure of the adjacency sampler (nhp_context.cu)

@@ -16,7 +16,7 @@ NHP_OPT_SWEEP_LOGLIK = 1
 c_double_p = POINTER(c_double)
 c_int64_p = POINTER(c_int64)
 
-# name -> (restype, argtypes); mirrors include/nhp.h one to one
+# name -> (restype, argtypes); mirrors include/nhp.h (the boundary) and include/nhp_devel.h (measurement / test hooks) one to one
 PROTOTYPES = {
     "nhp_create": (c_int, [c_int, POINTER(c_void_p)]),
     "nhp_destroy": (c_int, [c_void_p]),
@@ -45,6 +45,13 @@ PROTOTYPES = {
     "nhp_cont_suffstats": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]),
     "nhp_cont_resample_adjacency": (c_int, [c_void_p, c_void_p, c_void_p, c_uint64, c_uint64, c_void_p, c_void_p]),
     "nhp_cont_resample_adjacency_cols": (c_int, [c_void_p, c_void_p, c_void_p, c_uint64, c_uint64, c_void_p, c_void_p, c_int64, c_int64]),
+    "nhp_cont_resample_adjacency_dev": (c_int, [c_void_p, c_void_p, c_double, c_uint64, c_uint64, c_int64, c_int64, c_int]),
+    "nhp_cont_adjacency_commit": (c_int, [c_void_p]),
+    "nhp_cont_network_set": (c_int, [c_void_p, c_double]),
+    "nhp_cont_resample_network": (c_int, [c_void_p, c_uint64, c_uint64, c_double, c_double, c_double_p]),
+    "nhp_cont_adjacency_info": (c_int, [c_void_p, c_double_p]),
+    "nhp_cont_params_save": (c_int, [c_void_p]),
+    "nhp_cont_params_restore": (c_int, [c_void_p]),
     "nhp_cont_stats_dev": (c_int, [c_void_p, c_int, POINTER(c_void_p), c_int64_p]),
     "nhp_cont_suffstats_second_pass": (c_int, [c_void_p, c_void_p]),
     "nhp_cont_suffstats_read": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]),

@@ -498,8 +498,11 @@ def pull_params_(process, ctx=None):
     K = process.ndims()
     lam, W, p1 = np.empty(K), np.empty(K * K), np.empty(K * K)
     p2 = np.empty(K * K) if process.impulses.p2() is not None else None
-    ctx.check(ctx.lib.nhp_cont_params_get(ctx.h, _ptr(lam), _ptr(W), None, _ptr(p1), _ptr(p2)))
+    A = np.empty(K * K) if process.adjacency_matrix is not None else None
+    ctx.check(ctx.lib.nhp_cont_params_get(ctx.h, _ptr(lam), _ptr(W), _ptr(A), _ptr(p1), _ptr(p2)))
     unf = lambda v: v.reshape(K, K).T.copy()
+    if A is not None:
+        process.adjacency_matrix = unf(A)
     process.baseline.lam = lam
     process.weights.W = unf(W)
     if process.impulses.kind == NHP_EXPONENTIAL:
@@ -509,30 +512,43 @@ def pull_params_(process, ctx=None):
     return process.params()
 
 
-def resample_on_device_(process, data, rng, seed=0, counter=0, push=True, pull=True):
-    """One Gibbs sweep with the conjugate draws on the GPU (nhp_cont_resample_params): parent sweep + fused statistics,
-    second pass, draws of baseline / weights / impulses and the table rebuild never leave the device.  `push=False`
-    continues from the parameters already on the device (a chain); `pull=False` leaves the host objects untouched.
-    The network's adjacency sweep and the scalar Beta draw of rho keep their host round trip."""
+def resample_on_device_(process, data, rng=None, seed=0, counter=0, push=True, pull=True):
+    """One Gibbs sweep that never leaves the GPU: parent sweep + fused statistics, second pass, the conjugate draws of
+    baseline / weights / impulses (nhp_cont_resample_params), and for a network process the adjacency sweep on the
+    device-resident matrix (nhp_cont_resample_adjacency_dev) and the Beta draw of rho (nhp_cont_resample_network), with
+    every table rebuilt in place.  `push=False` continues from the parameters already on the device (a chain);
+    `pull=False` leaves the host objects untouched.  `rng` is unused (kept for the signature of `resample_`)."""
     ctx = process._ctx()
     d, tmp = process._data(data)
     try:
+        net = process.adjacency_matrix is not None
         if push:
             process._push(ctx)
+            if net and isinstance(process.network, BernoulliNetworkModel):
+                ctx.check(ctx.lib.nhp_cont_network_set(ctx.h, float(process.network.rho)))
         _resample_parents(ctx, d, seed, counter, None, False)
         hy = _hyper(process)
         ctx.check(ctx.lib.nhp_cont_resample_params(ctx.h, d.h, int(seed), int(counter), float(d.duration), _ptr(hy), hy.size, 1))
-        if process.adjacency_matrix is not None:
-            K = process.ndims()
-            rho = _fmat(process.network.link_probability())
-            A = _fmat(process.adjacency_matrix).copy()
-            ctx.check(ctx.lib.nhp_cont_resample_adjacency_cols(ctx.h, d.h, _ptr(rho), int(seed), int(counter + (1 << 40)), None, _ptr(A), 0, 1))
-            process.adjacency_matrix = A.reshape(K, K).T.copy()
-            process.network.resample_(process.adjacency_matrix, rng)
+        if net:
+            bern = isinstance(process.network, BernoulliNetworkModel)
+            ctx.check(ctx.lib.nhp_cont_resample_adjacency_dev(ctx.h, d.h, -1.0 if bern else 1.0, int(seed), int(counter + (1 << 40)), 0, 1, 1))
+            if bern:
+                rho = ctypes.c_double()
+                ctx.check(ctx.lib.nhp_cont_resample_network(ctx.h, int(seed), int(counter), process.network.alpha, process.network.beta, ctypes.byref(rho)))
+                process.network.rho = rho.value
         return pull_params_(process, ctx) if pull else None
     finally:
         if tmp:
             d.free()
+
+
+def adjacency_info(ctx=None):
+    """Diagnostics of the context's last adjacency sweep (nhp_cont_adjacency_info)."""
+    ctx = ctx or default_context()
+    out = np.zeros(8)
+    ctx.lib.nhp_cont_adjacency_info(ctx.h, out.ctypes.data_as(ctypes.POINTER(ctypes.c_double)))
+    keys = ("steps", "batches", "flips", "recomputed_steps", "pairs", "virtual_columns", "sweep_ms", "build_ms")
+    return dict(zip(keys, out.tolist()))
 
 
 def mcmc_(process, data, nsteps=1000, log_freq=100, verbose=False, seed=0, device_draws=False, store_every=1):

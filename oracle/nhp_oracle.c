@@ -401,14 +401,17 @@ static double adj_sum_log_intensity(const orc_cont_model *m, int64_t node1, cons
 }
 
 /* continuous.jl:444-487.  Bernoulli draw: rand() <= p (Distributions). */
-int orc_cont_resample_adjacency(const orc_cont_model *m0, double *A, const double *rho, const double *events, const int64_t *nodes, int64_t n, double duration, const double *u) {
+/* columns c with c % col_stride == col_begin only (continuous.jl:462-464: columns are independent, so a subset is the
+ * same computation restricted to those columns; the full sweep is col_begin = 0, col_stride = 1) */
+int orc_cont_resample_adjacency_cols(const orc_cont_model *m0, double *A, const double *rho, const double *events, const int64_t *nodes, int64_t n, double duration, const double *u,
+                                     int64_t col_begin, int64_t col_stride) {
     int64_t K = m0->K;
     double *counts = (double *)malloc((size_t)K * sizeof(double));
     orc_node_counts(nodes, n, K, counts);
     orc_cont_model m = *m0;
     m.A = A;
 #pragma omp parallel for schedule(dynamic, 1) if (g_threads > 1) num_threads(g_threads)
-    for (int64_t c = 0; c < K; c++) {
+    for (int64_t c = col_begin; c < K; c += col_stride) {
         for (int64_t p = 0; p < K; p++) {
             int64_t k = p + K * c;
             A[k] = 0.0;
@@ -425,6 +428,9 @@ int orc_cont_resample_adjacency(const orc_cont_model *m0, double *A, const doubl
     }
     free(counts);
     return 0;
+}
+int orc_cont_resample_adjacency(const orc_cont_model *m0, double *A, const double *rho, const double *events, const int64_t *nodes, int64_t n, double duration, const double *u) {
+    return orc_cont_resample_adjacency_cols(m0, A, rho, events, nodes, n, duration, u, 0, 1);
 }
 
 /* ------------------------------------------------------------------ discrete path */

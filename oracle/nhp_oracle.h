@@ -68,6 +68,8 @@ void orc_log_duration_variation(const double *Xbar, const double *events, const 
 
 /* adjacency Gibbs: A is mutated in place, u[p + K*c] are the Bernoulli uniforms, rho[p + K*c] link probabilities */
 int orc_cont_resample_adjacency(const orc_cont_model *m, double *A_inout, const double *rho, const double *events, const int64_t *nodes, int64_t n, double duration, const double *u); /* continuous.jl:444-519 */
+int orc_cont_resample_adjacency_cols(const orc_cont_model *m, double *A_inout, const double *rho, const double *events, const int64_t *nodes, int64_t n, double duration, const double *u,
+                                     int64_t col_begin, int64_t col_stride); /* the columns c % col_stride == col_begin of the same sweep (continuous.jl:462-464) */
 
 /* discrete path */
 void orc_disc_basis(int64_t L, int64_t B, double dt, double *phi /* [L*B] col-major phi[l + L*b] */);   /* impulses.jl:321-335 */

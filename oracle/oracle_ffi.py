@@ -107,10 +107,11 @@ class Cont:
             raise ValueError("Categorical: the probability vector is invalid")
         return par, pn
 
-    def resample_adjacency(self, A, rho, events, nodes, duration, u):
+    def resample_adjacency(self, A, rho, events, nodes, duration, u, col_begin=0, col_stride=1):
         ev, nd = self._ev(events, nodes)
         Af, rf, uf = fmat(A).copy(), fmat(rho), fmat(u)
-        lib().orc_cont_resample_adjacency(ctypes.byref(self.m), _p(Af), _p(rf), _p(ev), _p(nd), c_int64(ev.size), c_double(duration), _p(uf))
+        lib().orc_cont_resample_adjacency_cols(ctypes.byref(self.m), _p(Af), _p(rf), _p(ev), _p(nd), c_int64(ev.size), c_double(duration), _p(uf),
+                                               c_int64(col_begin), c_int64(col_stride))
         return unf(Af, self.K)
 
 

@@ -9,10 +9,19 @@ import pytest
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 
-def header_functions():
-    src = open(os.path.join(ROOT, "include", "nhp.h")).read()
-    src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
-    return sorted(set(re.findall(r"\b(nhp_[a-z0-9_]+)\s*\(", src)))
+def header_functions(names=("nhp.h", "nhp_devel.h")):
+    found = set()
+    for name in names:
+        src = open(os.path.join(ROOT, "include", name)).read()
+        src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
+        found |= set(re.findall(r"\b(nhp_[a-z0-9_]+)\s*\(", src))
+    return sorted(found)
+
+
+def test_boundary_header_holds_no_measurement_hooks():
+    boundary = header_functions(("nhp.h",))
+    for hook in ("nhp_bench_fp64", "nhp_test_fastmath", "nhp_launch_count", "nhp_cont_params_save"):
+        assert hook not in boundary
 
 
 def test_library_exports_every_declared_symbol():

@@ -89,10 +89,17 @@ if __name__ == "__main__":
                                                   nhp.BernoulliNetworkModel(dens, K))
         d = proc.upload((t, nodes, T))
         ctx = proc._ctx()
-        for rep in range(3):
+        reset = len(sys.argv) > 6 and sys.argv[6] == "reset"  # every sweep starts from the initial matrix (all its links flip on surrogate data)
+        A0 = proc.adjacency_matrix.copy()
+        for rep in range(4):
+            if reset:
+                proc.adjacency_matrix = A0.copy()
             t0 = time.perf_counter()
             nhp.resample_adjacency_matrix_(proc, d, seed=1, counter=rep)
-            print(f"adjacency K={K} n={n:.1e}: kernel {ctx.last_kernel_ms:.2f} ms, call {1e3*(time.perf_counter()-t0):.1f} ms, links {int(proc.adjacency_matrix.sum())}", flush=True)
+            info = nhp.adjacency_info(ctx)
+            print(f"adjacency K={K} n={n:.1e}: kernel {ctx.last_kernel_ms:.2f} ms, call {1e3*(time.perf_counter()-t0):.1f} ms, links {int(proc.adjacency_matrix.sum())}, "
+                  f"pairs {info['pairs']:.3g} ({info['pairs'] / max(ctx.last_kernel_ms, 1e-9) / 1e6:.1f} Gpair/s), batches {info['batches']:.0f}, flips {info['flips']:.0f}, "
+                  f"recomputed {info['recomputed_steps']:.0f}, vcols {info['virtual_columns']:.0f}, build {info['build_ms']:.0f} ms", flush=True)
         sys.exit(0)
     if which == "disc":  # disc N T B L rate
         from nhp_b200 import discrete as D
