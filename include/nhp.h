@@ -67,6 +67,15 @@ int nhp_events_upload(nhp_ctx *ctx, const double *times, const int64_t *nodes, i
                       int64_t n_halo, int64_t index_base, int flags, nhp_events **out);
 int nhp_events_free(nhp_ctx *ctx, nhp_events *ev);
 int64_t nhp_events_count(const nhp_events *ev);
+/* rand(process, duration)  continuous.jl:16-37, 131-142, 335-348: one sample of the process whose parameters the context
+ * holds (nhp_cont_params_set), simulated on the device generation by generation (cluster representation: baseline events
+ * baselines.jl:67-70, Poisson(W[p,c]) children per event and child node weights.jl:25-27, lags from the impulse response
+ * impulses.jl:63-66, 196-202, truncated at `duration`), sorted by time and left device resident as an events handle -- no host
+ * round trip for 1e8-event samples.  Philox keyed by `seed`; parity with the reference is distributional.  Fails when the
+ * sample would exceed max_events.  nhp_events_download copies (events, nodes) of a handle to the host in Julia's conventions
+ * (any pointer may be NULL). */
+int nhp_cont_rand(nhp_ctx *ctx, double duration, uint64_t seed, int64_t max_events, nhp_events **out);
+int nhp_events_download(nhp_ctx *ctx, nhp_events *ev, double *times, int64_t *nodes, double *duration);
 
 /* ---- continuous parameters --------------------------------------------------------------
  * lambda0[K]  HomogeneousProcess.lambda (baselines.jl:27-39);  W[K*K] weights.W (weights.jl:47-55);
@@ -167,12 +176,33 @@ int nhp_cont_resample_params(nhp_ctx *ctx, nhp_events *ev, uint64_t seed, uint64
 /* Current parameters in the layouts of nhp_cont_params_set; any pointer may be NULL. */
 int nhp_cont_params_get(nhp_ctx *ctx, double *lambda0, double *W, double *A, double *p1, double *p2);
 
-/* ---- multi-GPU plumbing (one process per GPU; the host allreduces with NCCL) -------------
- * Device pointer + length (in doubles) of the contiguous reduction buffer
+/* ---- multi-GPU (one process and one context per GPU; NCCL over NVLink, loaded with dlopen) ---------------------
+ * SURVEY.md section 8e.  Time shards (nhp_events_upload with n_halo / index_base) carry the log-likelihood, the parent
+ * sweep and the statistics; the adjacency sampler partitions the child columns over the ranks on a replicated stream.
+ * The host distributes the 128-byte id of rank 0 (nhp_comm_unique_id) by any means it has (MPI.jl, Distributed.jl, a
+ * file) and every rank calls nhp_comm_init; the collectives below then run on the context's stream.  On a context
+ * without a communicator they are no-ops, so one call sequence serves 1..N GPUs:
+ *   resample_parents -> nhp_comm_allreduce_stats(0) -> nhp_cont_suffstats_second_pass -> nhp_comm_allreduce_stats(1)
+ *   -> nhp_cont_resample_params(flags = 0) | nhp_cont_suffstats_read
+ *   -> nhp_cont_resample_adjacency_dev(col_begin = rank, col_stride = nranks, commit = 0) -> nhp_comm_allgather_adjacency
+ * nhp_cont_gibbs_sweep runs exactly that sequence (the whole `resample!` of continuous.jl:202-208 / 350-358).
+ * Statistics buffers (device, contiguous doubles):
  *   [ ll_logsum, ll_rowsum, M0[K], Mn[K], Mnm[K*K], S1[K*K] ]   (phase 0)
- *   [ S2[K*K] ]                                                 (phase 1)
- * Protocol: resample_parents -> allreduce(phase 0) -> nhp_cont_suffstats_second_pass ->
- * allreduce(phase 1) -> nhp_cont_suffstats_read. */
+ *   [ S2[K*K] ]                                                 (phase 1) */
+int nhp_comm_unique_id(void *id128);
+int nhp_comm_init(nhp_ctx *ctx, const void *id128, int rank, int nranks);
+int nhp_comm_destroy(nhp_ctx *ctx);
+int nhp_comm_rank(const nhp_ctx *ctx, int *rank, int *nranks);
+int nhp_comm_allreduce_stats(nhp_ctx *ctx, int phase);
+/* sum of a small host vector over the ranks (log-likelihood shares of nhp_cont_loglik, ...) */
+int nhp_comm_allreduce_host(nhp_ctx *ctx, double *inout, int64_t n);
+int nhp_comm_allgather_adjacency(nhp_ctx *ctx);
+/* hyper as for nhp_cont_resample_params; net_alpha > 0: BernoulliNetworkModel with rho ~ Beta(net_alpha, net_beta) prior
+ * (networks.jl:45-54, 72-78), else link probability 1 (DenseNetworkModel).  ev_full (the unsharded stream, replicated on
+ * every rank) is only used by network processes; pass ev_shard itself on a single GPU. */
+int nhp_cont_gibbs_sweep(nhp_ctx *ctx, nhp_events *ev_shard, nhp_events *ev_full, uint64_t seed, uint64_t counter, double duration,
+                         const double *hyper, int n_hyper, double net_alpha, double net_beta);
+/* Device pointer + length (in doubles) of a statistics buffer, for hosts that run their own collectives. */
 int nhp_cont_stats_dev(nhp_ctx *ctx, int phase, void **ptr_dev, int64_t *count);
 int nhp_cont_suffstats_second_pass(nhp_ctx *ctx, nhp_events *ev);
 int nhp_cont_suffstats_read(nhp_ctx *ctx, double *M0, double *Mn, double *Mnm, double *S1, double *S2);

@@ -44,10 +44,45 @@ template <typename E> __global__ void __launch_bounds__(256) k_pair_peak(double 
     if (acc == 12345.678) out[0] = acc;
 }
 
+// Adjacency-bit probe rate of the sparse sweep's filter with nothing around it: every thread owns a 1024-bit row in its own
+// shared-memory bank (word w of lane l at [w * 32 + l], as in k_sweep_sparse) and walks a shared window of node ids eight
+// probes per trip: one LDS for the node id, one LDS for the row word, shift / mask / merge -- the instruction sequence of
+// cont_sparse.cu's phase 1.  probes/s of this loop is the ceiling the sweep's filter phase is compared with.
+__global__ void __launch_bounds__(256) k_probe_peak(unsigned long long *out, int iters, unsigned seed) {
+    __shared__ uint32_t rows[8 * 32 * 32];  // [warp][word][lane]
+    __shared__ int sc[512 + 8];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    uint32_t x = seed ^ (threadIdx.x * 2654435761u) ^ (blockIdx.x * 40503u);
+    for (int w = 0; w < 32; w++) { x = x * 1664525u + 1013904223u; rows[(warp * 32 + w) * 32 + lane] = x & (x >> 3) & (x >> 7) & (x >> 11); }  // ~6 % of the bits set
+    for (int i = threadIdx.x; i < 520; i += 256) { x = x * 1664525u + 1013904223u; sc[i] = (int)((x >> 8) & 1023u); }
+    __syncthreads();
+    const uint32_t *myrow = rows + warp * 32 * 32 + lane;
+    unsigned long long acc = 0ull;
+    int pos = 64 + (threadIdx.x & 63);
+    for (int it = 0; it < iters; it++) {
+        unsigned long long hits = 0ull;
+        const int *src = sc + pos;
+#pragma unroll 1
+        for (int m = 0; m < 64; m += 8) {
+            const int p0 = src[-m], p1 = src[-m - 1], p2 = src[-m - 2], p3 = src[-m - 3];
+            const int p4 = src[-m - 4], p5 = src[-m - 5], p6 = src[-m - 6], p7 = src[-m - 7];
+            const uint32_t w0 = myrow[p0 & ~31], w1 = myrow[p1 & ~31], w2 = myrow[p2 & ~31], w3 = myrow[p3 & ~31];
+            const uint32_t w4 = myrow[p4 & ~31], w5 = myrow[p5 & ~31], w6 = myrow[p6 & ~31], w7 = myrow[p7 & ~31];
+            const uint32_t b8 = ((w0 >> (p0 & 31)) & 1u) | (((w1 >> (p1 & 31)) & 1u) << 1) | (((w2 >> (p2 & 31)) & 1u) << 2) |
+                                (((w3 >> (p3 & 31)) & 1u) << 3) | (((w4 >> (p4 & 31)) & 1u) << 4) | (((w5 >> (p5 & 31)) & 1u) << 5) |
+                                (((w6 >> (p6 & 31)) & 1u) << 6) | (((w7 >> (p7 & 31)) & 1u) << 7);
+            hits |= (unsigned long long)b8 << m;
+        }
+        acc += __popcll(hits);
+        pos = 64 + ((pos + 37 + (int)(hits & 7ull)) & 255);
+    }
+    if (acc == 0x7fffffffffffull) out[0] = acc;
+}
+
 // which: 0 = DFMA TFLOP/s (2 flops per FMA), 1 = LogitNormal pairs/s, 2 = Exponential pairs/s, 3 = DMMA m8n8k4 TFLOP/s
 extern "C" int nhp_bench_fp64(nhp_ctx *ctx, int which, double *result) {
     NHP_CHECK(ctx, ctx != nullptr, NHP_ERR_INVALID, "ctx is NULL");
-    NHP_CHECK(ctx, result != nullptr && which >= 0 && which <= 3, NHP_ERR_INVALID, "nhp_bench_fp64: bad argument");
+    NHP_CHECK(ctx, result != nullptr && which >= 0 && which <= 4, NHP_ERR_INVALID, "nhp_bench_fp64: bad argument");
     NHP_CUDA(ctx, cudaSetDevice(ctx->device));
     void *scratch;
     NHP_TRY(nhp_scratch(ctx, 64, &scratch));
@@ -58,6 +93,7 @@ extern "C" int nhp_bench_fp64(nhp_ctx *ctx, int which, double *result) {
         NHP_TRY(nhp_timer_begin(ctx));
         if (which == 0) k_dfma_peak<<<blocks, 256, 0, ctx->stream>>>((double *)scratch, iters, 0.999999, 1e-9);
         else if (which == 3) k_dmma_peak<<<blocks, 256, 0, ctx->stream>>>((double *)scratch, iters);
+        else if (which == 4) k_probe_peak<<<blocks, 256, 0, ctx->stream>>>((unsigned long long *)scratch, iters, 12345u);
         else if (which == 1) { EntryLN e{0.3, 0.1, 0.6, 0.0}; k_pair_peak<EntryLN><<<blocks, 256, 0, ctx->stream>>>((double *)scratch, iters, e, 1.0); }
         else { EntryEX e{0.3, 1.1}; k_pair_peak<EntryEX><<<blocks, 256, 0, ctx->stream>>>((double *)scratch, iters, e, 1.0); }
         NHP_LAUNCHED(ctx);
@@ -66,6 +102,7 @@ extern "C" int nhp_bench_fp64(nhp_ctx *ctx, int which, double *result) {
     }
     double work = (double)blocks * 256.0 * iters * (which == 0 ? 16.0 : 2.0);
     if (which == 3) work = (double)blocks * 8.0 * iters * 4.0 * 512.0;  // 8 warps x 4 DMMA x (8*8*4*2 flops)
+    if (which == 4) work = (double)blocks * 256.0 * iters * 64.0;       // 64 probes per thread and iteration
     *result = work / (best * 1e-3) / ((which == 0 || which == 3) ? 1e12 : 1.0);
     return NHP_OK;
 }

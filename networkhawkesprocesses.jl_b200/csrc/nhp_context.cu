@@ -77,6 +77,7 @@ extern "C" int nhp_destroy(nhp_ctx *ctx) {
     if (!ctx) return NHP_OK;
     cudaSetDevice(ctx->device);
     cudaStreamSynchronize(ctx->stream);
+    nhp_comm_destroy(ctx);
     free_cont(ctx);
     cudaFree(ctx->d_partials); cudaFree(ctx->d_scratch); cudaFree(ctx->d_flag); cudaFree(ctx->d_winstat);
     cudaFree(ctx->dd_lambda0); cudaFree(ctx->dd_W); cudaFree(ctx->dd_A); cudaFree(ctx->dd_theta); cudaFree(ctx->dd_bump);
@@ -229,6 +230,57 @@ extern "C" int nhp_events_upload(nhp_ctx *ctx, const double *times, const int64_
     int64_t z = 0;
     while (z < n && times[z] == 0.0) z++;
     ev->n_t0 = z;
+    *out = ev;
+    return NHP_OK;
+}
+
+// An events handle around device-resident (times, 0-based nodes) arrays, e.g. the sample of nhp_cont_rand: the arrays are copied
+// (device to device) into the handle's own padded buffers; times must be ascending and non-negative (validated).
+__global__ void k_validate_sorted(const double *__restrict__ t, const int *__restrict__ c, int64_t n, int64_t K, int *flag, unsigned long long *n_t0) {
+    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const double ti = t[i];
+    if (c[i] < 0 || c[i] >= K) atomicOr(flag, 1);
+    if (!(ti >= 0.0)) atomicOr(flag, 4);
+    if (i + 1 < n && !(t[i + 1] >= ti)) atomicOr(flag, 2);
+    if (ti == 0.0) atomicAdd(n_t0, 1ull);
+}
+int nhp_events_from_device(nhp_ctx *ctx, const double *d_t, const int *d_c, int64_t n, double duration, int64_t K, nhp_events **out) {
+    *out = nullptr;
+    NHP_CHECK(ctx, n >= 0 && n < (int64_t)2147483000, NHP_ERR_INVALID, "events: n=%lld outside [0, 2^31)", (long long)n);
+    nhp_events *ev = new nhp_events();
+    ev->n = n; ev->n_halo = 0; ev->index_base = 0; ev->flags = 1; ev->duration = duration; ev->K = K;
+    const int64_t pad = 64;
+    cudaStream_t as = ctx->stream;
+    auto cleanup = [&](int code) { nhp_events_free(ctx, ev); return code; };
+    if (cudaMallocAsync(&ev->d_t, (size_t)(n + pad) * sizeof(double), as) != cudaSuccess || cudaMallocAsync(&ev->d_c, (size_t)(n + pad) * sizeof(int), as) != cudaSuccess ||
+        cudaMallocAsync(&ev->d_poff, (size_t)(n + pad) * sizeof(int), as) != cudaSuccess || cudaMallocAsync(&ev->d_Mn, (size_t)K * sizeof(double), as) != cudaSuccess)
+        return cleanup(nhp_fail(ctx, NHP_ERR_CUDA, "events: cudaMalloc failed: %s", cudaGetErrorString(cudaGetLastError())));
+    cudaMemsetAsync(ev->d_t + n, 0, pad * sizeof(double), as);
+    cudaMemsetAsync(ev->d_c + n, 0, pad * sizeof(int), as);
+    cudaMemsetAsync(ev->d_poff, 0xFF, (size_t)(n + pad) * sizeof(int), as);
+    cudaMemsetAsync(ev->d_Mn, 0, (size_t)K * sizeof(double), as);
+    cudaMemsetAsync(ctx->d_flag, 0, sizeof(int), as);
+    cudaMemsetAsync(ctx->d_winstat, 0, 2 * sizeof(int64_t), as);
+    if (n > 0) {
+        cudaMemcpyAsync(ev->d_t, d_t, (size_t)n * sizeof(double), cudaMemcpyDeviceToDevice, as);
+        cudaMemcpyAsync(ev->d_c, d_c, (size_t)n * sizeof(int), cudaMemcpyDeviceToDevice, as);
+        k_validate_sorted<<<(unsigned)((n + 255) / 256), 256, 0, as>>>(ev->d_t, ev->d_c, n, K, ctx->d_flag, (unsigned long long *)ctx->d_winstat);
+        NHP_LAUNCHED(ctx);
+        int hb = (int)std::min<int64_t>((n + 255) / 256, (int64_t)ctx->sm_count * 8);
+        size_t sm = K <= 8192 ? (size_t)K * sizeof(int) : 0;
+        k_node_counts<<<hb, 256, sm, as>>>(ev->d_c, 0, n, (int)K, ev->d_Mn);
+        NHP_LAUNCHED(ctx);
+    }
+    int flag = 0;
+    unsigned long long nt0 = 0;
+    if (cudaMemcpyAsync(&flag, ctx->d_flag, sizeof(int), cudaMemcpyDeviceToHost, as) != cudaSuccess ||
+        cudaMemcpyAsync(&nt0, ctx->d_winstat, sizeof(nt0), cudaMemcpyDeviceToHost, as) != cudaSuccess || cudaStreamSynchronize(as) != cudaSuccess)
+        return cleanup(nhp_fail(ctx, NHP_ERR_CUDA, "events: %s", cudaGetErrorString(cudaGetLastError())));
+    if (flag & 1) return cleanup(nhp_fail(ctx, NHP_ERR_INVALID, "events: node outside 1..K"));
+    if (flag & 2) return cleanup(nhp_fail(ctx, NHP_ERR_INVALID, "events: event times are not ascending"));
+    if (flag & 4) return cleanup(nhp_fail(ctx, NHP_ERR_INVALID, "events: negative or NaN event time (baselines.jl:116)"));
+    ev->n_t0 = (int64_t)nt0;  // ascending times: the events at exactly t = 0 lead (quirk Q6)
     *out = ev;
     return NHP_OK;
 }

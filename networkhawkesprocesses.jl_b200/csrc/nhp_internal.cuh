@@ -150,6 +150,7 @@ struct nhp_ctx {
     unsigned long long *d_adj_stat = nullptr;  // [8] sweep diagnostics (steps, batches, flips, recomputed steps)
     double *d_save = nullptr;     // nhp_cont_params_save: [K + 4 K^2] copy of lambda0, W, A, p1, p2
     double rho = -1.0;            // link probability of the Bernoulli network kept with the context (nhp_cont_resample_network)
+    double sweep_info[8] = {0};   // last nhp_cont_gibbs_sweep: ms of the parent sweep, of (second pass + draws + tables), of the adjacency kernel
     double adj_info[8] = {0};     // last adjacency sweep: steps, batches, flips, recomputed steps, entries, chunks, kernel ms, build ms
 
     // ---- statistics
@@ -167,6 +168,12 @@ struct nhp_ctx {
     void *d_scratch = nullptr;
     size_t scratch_cap = 0;
     int64_t *d_winstat = nullptr; // [2]: max window, sum window
+
+    // ---- multi-GPU (comm.cu): NCCL communicator of this rank, staging buffer
+    void *comm = nullptr;
+    int rank = 0, nranks = 1;
+    double *d_comm_buf = nullptr;
+    size_t comm_buf_cap = 0;
 
     // ---- discrete parameters
     bool disc_set = false;

@@ -31,6 +31,8 @@ PROTOTYPES = {
     "nhp_events_upload": (c_int, [c_void_p, c_void_p, c_void_p, c_int64, c_double, c_int64, c_int64, c_int64, c_int, POINTER(c_void_p)]),
     "nhp_events_free": (c_int, [c_void_p, c_void_p]),
     "nhp_events_count": (c_int64, [c_void_p]),
+    "nhp_cont_rand": (c_int, [c_void_p, c_double, c_uint64, c_int64, POINTER(c_void_p)]),
+    "nhp_events_download": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_double_p]),
     "nhp_cont_params_set": (c_int, [c_void_p, c_int, c_int64, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_double]),
     "nhp_cont_horizon": (c_int, [c_void_p, c_int64, c_int, c_double_p]),
     "nhp_cont_loglik": (c_int, [c_void_p, c_void_p, c_int, c_double_p]),
@@ -50,8 +52,17 @@ PROTOTYPES = {
     "nhp_cont_network_set": (c_int, [c_void_p, c_double]),
     "nhp_cont_resample_network": (c_int, [c_void_p, c_uint64, c_uint64, c_double, c_double, c_double_p]),
     "nhp_cont_adjacency_info": (c_int, [c_void_p, c_double_p]),
+    "nhp_cont_sweep_info": (c_int, [c_void_p, c_double_p]),
     "nhp_cont_params_save": (c_int, [c_void_p]),
     "nhp_cont_params_restore": (c_int, [c_void_p]),
+    "nhp_comm_unique_id": (c_int, [c_void_p]),
+    "nhp_comm_init": (c_int, [c_void_p, c_void_p, c_int, c_int]),
+    "nhp_comm_destroy": (c_int, [c_void_p]),
+    "nhp_comm_rank": (c_int, [c_void_p, POINTER(c_int), POINTER(c_int)]),
+    "nhp_comm_allreduce_stats": (c_int, [c_void_p, c_int]),
+    "nhp_comm_allreduce_host": (c_int, [c_void_p, c_void_p, c_int64]),
+    "nhp_comm_allgather_adjacency": (c_int, [c_void_p]),
+    "nhp_cont_gibbs_sweep": (c_int, [c_void_p, c_void_p, c_void_p, c_uint64, c_uint64, c_double, c_void_p, c_int, c_double, c_double]),
     "nhp_cont_stats_dev": (c_int, [c_void_p, c_int, POINTER(c_void_p), c_int64_p]),
     "nhp_cont_suffstats_second_pass": (c_int, [c_void_p, c_void_p]),
     "nhp_cont_suffstats_read": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]),

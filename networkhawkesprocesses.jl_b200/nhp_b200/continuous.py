@@ -615,8 +615,23 @@ def mle_(process, data, regularize=False, guess=None, f_abstol=1e-6, max_iter=20
 
 
 # ------------------------------------------------------------------------------------------
-# rand (host side; the reference's cluster simulator, continuous.jl:16-37, 131-142, 335-348)
+# rand: on the device (nhp_cont_rand) or on the host (the reference's recursive cluster simulator,
+# continuous.jl:16-37, 131-142, 335-348; kept for tiny samples and as an independent check of the device one)
 # ------------------------------------------------------------------------------------------
+def rand_device(process, duration, seed=0, max_events=None):
+    """`rand(process, duration)` simulated on the GPU; returns device-resident data (`.download()` gives the host tuple)."""
+    ctx = process._ctx()
+    process._push(ctx)
+    if max_events is None:  # stationary mean (I - W^T)^-1 lambda0 T with head room
+        Weff = process.weights.W if process.adjacency_matrix is None else process.adjacency_matrix * process.weights.W
+        rad = float(np.max(np.sum(Weff, axis=1))) if Weff.size else 0.0
+        mean = float(np.sum(process.baseline.lam)) * duration / max(1.0 - min(rad, 0.95), 0.05)
+        max_events = int(min(2.1e9, 2.0 * mean + 10.0 * np.sqrt(mean) + 1000))
+    h = ctypes.c_void_p()
+    ctx.check(ctx.lib.nhp_cont_rand(ctx.h, float(duration), int(seed), int(max_events), ctypes.byref(h)))
+    return ContinuousData.from_handle(ctx, h, process.ndims())
+
+
 def rand(process, duration, rng=None):
     rng = rng or np.random.default_rng()
     K = process.ndims()

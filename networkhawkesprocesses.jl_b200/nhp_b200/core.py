@@ -80,5 +80,23 @@ class ContinuousData:
         self.K = int(K)
         self._fin = weakref.finalize(self, ctx.lib.nhp_events_free, ctx.h, h)
 
+    @classmethod
+    def from_handle(cls, ctx, h, K):
+        """Wrap an events handle the library created on the device (nhp_cont_rand)."""
+        self = cls.__new__(cls)
+        self.ctx, self.h, self.K = ctx, h, int(K)
+        dur = ctypes.c_double()
+        ctx.check(ctx.lib.nhp_events_download(ctx.h, h, None, None, ctypes.byref(dur)))
+        self.n = self.n_own = int(ctx.lib.nhp_events_count(h))
+        self.n_halo, self.index_base, self.duration = 0, 0, dur.value
+        self._fin = weakref.finalize(self, ctx.lib.nhp_events_free, ctx.h, h)
+        return self
+
+    def download(self):
+        """(events, nodes, duration) on the host, in the reference's conventions (1-based Int64 nodes)."""
+        t, c = np.empty(self.n_own, dtype=np.float64), np.empty(self.n_own, dtype=np.int64)
+        self.ctx.check(self.ctx.lib.nhp_events_download(self.ctx.h, self.h, _ptr(t), _ptr(c), None))
+        return t, c, self.duration
+
     def free(self):
         self._fin()

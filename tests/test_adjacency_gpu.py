@@ -61,10 +61,11 @@ def test_uncached_fallback_matches_oracle(monkeypatch):
 def test_exponential_sampler_starting_from_an_empty_network():
     """with A = 0 the sweeps' cut-off horizon collapses (no active link), but the sampler evaluates W h for
     links that are off: its horizon comes from all K^2 entries, so the data can switch links on."""
-    K, n, rho = 5, 1200, 0.5
-    proc, _ = make_exp(K, 7, density=0.5, wmax=2.0 / K)  # dtmax = Inf
+    K, rho = 5, 0.5
+    proc, _ = make_exp(K, 7, density=0.5, wmax=1.0 / K)  # dtmax = Inf; branching ratio ~ 0.5 with every link on
     proc.adjacency_matrix = np.ones((K, K))
-    t, nodes, T = nhp.rand(proc, n / 8.0, np.random.default_rng(3))  # excitation present in the data
+    t, nodes, T = nhp.rand(proc, 120.0, np.random.default_rng(3))  # excitation present in the data
+    assert 300 < t.size < 5000
     proc.network = nhp.BernoulliNetworkModel(rho, K)
     A0 = np.zeros((K, K))
     om = orc.Cont(0, proc.baseline.lam, proc.weights.W, proc.impulses.theta, A=A0, dtmax=np.inf)
