@@ -11,19 +11,22 @@
 //
 // Cached form (default; k_adj_build + k_adj_sweep).  WHICH (child event, window predecessor) pairs exist, and their
 // lags, depends on the data and the look-back horizon only, so the pairs are bucketed once per events handle:
-//   virtual column = (child column c, time chunk g of at most `chunk_cap` of the column's events), buckets by parent
-//   node p inside it, entries stably ordered by (child event, window position); 10 B per pair (u16 event index inside
-//   the chunk + f64 lag); entries of one (event, parent) that repeat sit next to each other, flagged.
-// A Gibbs sweep streams that structure.  One 1024-thread CTA owns a column at a time and keeps the intensities
-// lambda_i of the current chunk in SHARED MEMORY (up to 26 624 events = 208 KB), so the per-entry gather that bound the
-// first version (one DRAM sector per entry, profiles/r02_adjacency.md) is an LDS.  The K sequential Bernoulli steps
-// are run speculatively in batches of S <= 32 buckets: a step only changes lambda when its link flips, which is
-// rare once a chain has mixed, so the S sums are evaluated in parallel (a group of 32/S warps per bucket) from the
-// current lambda, the decisions are then taken in order, and the first flip (if any) is applied and the batch
-// restarts behind it (S halves after a flip, doubles after a clean batch).  The result is exactly that of the sequential
-// sweep.  The log terms are accumulated as products (one log per lane and batch instead of one per entry).
-// Columns larger than one chunk keep lambda in global memory between batches and stream their chunks per batch.
-// Everything is order-deterministic: no atomics, fixed reduction trees.
+//   virtual column = (child column c, time chunk g of the column's events), buckets by parent node p inside it, entries
+//   stably ordered by (child event, window position); per pair a u16 event index inside the chunk and either the f64 lag
+//   (10 B) or -- LogitNormal, memory permitting -- the parameter-free part of the impulse, logit(dt/D) and 1/(dt (D-dt))
+//   (18 B), so that a sweep pays one exp per pair; entries of one (event, parent) that repeat sit next to each other, flagged.
+// A Gibbs sweep streams that structure.  The intensities lambda_i of a column stay in SHARED MEMORY for the whole column: a
+// thread-block CLUSTER of 1, 2, 4 or 8 CTAs (1024 threads each, one per SM) owns a column, CTA r holding chunk r (up to
+// 26 624 events = 208 KB each), so the per-entry gather that bound the first version (one DRAM sector per entry) is an LDS
+// and a flip never leaves the chip.  The K sequential Bernoulli steps run speculatively in batches of S <= 32 buckets: a
+// step only changes lambda when its link flips, so the S sums are evaluated in parallel (32/S warps per bucket) from the
+// current lambda, every CTA's partial sums travel through distributed shared memory to all CTAs of the cluster (one cluster
+// barrier per batch), each CTA then takes the same decisions in order, and the first flip (if any) is applied and the batch
+// restarts behind it (S halves after a flip -- down to 1, the plain sequential sweep, when a chain flips a third of its
+// links per sweep -- and doubles after a clean batch).  The result is exactly that of the sequential sweep.  The log terms are
+// accumulated as a quotient of running products (one log per lane and batch instead of one per entry).
+// Columns too large for a cluster's shared memory keep lambda in global memory between batches and stream their chunks
+// per batch through one CTA.  Everything is order-deterministic: no atomics, fixed reduction trees.
 //
 // Uncached form (k_adjacency): the structure is re-bucketed inside every sweep; used when it does not fit in memory.
 #include "cont_sweep.cuh"
@@ -182,7 +185,8 @@ template <int KIND> __global__ void __launch_bounds__(256) k_adjacency(const Adj
 // ---------------------------------------------------------------------------------------
 constexpr int ADJ_CHUNK_MAX = 26624;   // child events per chunk: 208 KB of shared-memory intensities
 constexpr int ADJ_THREADS = 1024;      // sweep CTA: one per SM
-constexpr int ADJ_SMAX = 32, ADJ_SMIN = 4;  // speculative batch size (buckets per batch): halves after a flip, doubles after a clean batch
+constexpr int ADJ_SMAX = 32;           // speculative batch size (buckets per batch): halves after a flip (down to 1), doubles after a clean batch
+constexpr int ADJ_CLUSTER_MAX = 8;     // portable cluster size limit
 
 // a column's ne child events are split into G chunks of this many events (the last one may be shorter)
 __host__ __device__ inline int adj_chunk_size(int ne, int G) { return G > 0 ? (ne + G - 1) / G : 0; }
@@ -202,9 +206,9 @@ __global__ void k_adj_count(const double *__restrict__ t, const int *__restrict_
 
 struct AdjBuildArgs {
     const double *t; const int *c; const int *order, *node_ptr;
-    int K; double horizon;
+    int K; double horizon, D;
     const int *vstart, *vnode; const int64_t *vbase;
-    int *boff; unsigned short *ent_i; double *ent_dt;
+    int *boff; unsigned short *ent_i; double *ent_x, *ent_y;   // ent_y != NULL: LogitNormal payload (logit, Jacobian) instead of the lag
     int nv, nw;      // virtual columns; warps per CTA
     int *next, *flag;
 };
@@ -212,6 +216,9 @@ struct AdjBuildArgs {
 // Stable counting sort of one virtual column's (child event, window predecessor) pairs by parent node.  Warp w owns a contiguous
 // range of the chunk's events and private per-parent cursors, so a bucket is ordered by (event, window position) whatever the
 // scheduling; entries of one (event, parent) are adjacent and all but the first carry the continuation bit.
+// Payload per entry: the lag t_i - t_j, or -- LogitNormal, when memory allows -- what the impulse needs of it and what does not
+// depend on the parameters: z = logit(dt / D) and q = 1 / (dt (D - dt)), so that a sweep evaluates one exp per pair instead of
+// a log, a reciprocal and an exp (pairs outside the support get q = 0).
 __global__ void __launch_bounds__(512) k_adj_build(const AdjBuildArgs a) {
     extern __shared__ int s_dyn[];
     __shared__ int s_v;
@@ -231,7 +238,7 @@ __global__ void __launch_bounds__(512) k_adj_build(const AdjBuildArgs a) {
         const int col = a.vnode[v], g = v - a.vstart[col], G = a.vstart[col + 1] - a.vstart[col];
         const int ne = a.node_ptr[col + 1] - a.node_ptr[col], csz = adj_chunk_size(ne, G);
         const int eb = a.node_ptr[col] + g * csz, ee = min(a.node_ptr[col] + ne, eb + csz);  // positions in the by-node order
-        const int per = (ee - eb + nw - 1) / nw;
+        const int per = (max(ee - eb, 0) + nw - 1) / nw;
         const int ws = min(ee, eb + wid * per), we = min(ee, ws + per);
         for (int k = lane; k < K; k += 32) cur[k] = 0u;
         __syncwarp();
@@ -269,7 +276,8 @@ __global__ void __launch_bounds__(512) k_adj_build(const AdjBuildArgs a) {
         __syncthreads();
         // ---- B: scatter
         unsigned short *ei = a.ent_i + a.vbase[v];
-        double *ed = a.ent_dt + a.vbase[v];
+        double *ex = a.ent_x + a.vbase[v];
+        double *ey = a.ent_y ? a.ent_y + a.vbase[v] : nullptr;
         for (int e = ws; e < we; e++) {
             const int i = a.order[e];
             const double ti = a.t[i];
@@ -293,8 +301,18 @@ __global__ void __launch_bounds__(512) k_adj_build(const AdjBuildArgs a) {
                 __syncwarp();
                 if (valid) {
                     const unsigned pos = cur[p] + seen + rank;
+                    const double dt = ti - __ldg(a.t + (i - 1 - k));
                     ei[pos] = (unsigned short)(le | ((seen + rank) ? 0x8000u : 0u));
-                    ed[pos] = ti - __ldg(a.t + (i - 1 - k));
+                    if (ey) {
+                        const double b = a.D - dt;
+                        double z = 0.0, q = 0.0;
+                        if (dt > 0.0 && b > 0.0) {  // Distributions.pdf(LogitNormal, x) is zero outside 0 < x < 1 (impulses.jl:174-178)
+                            q = 1.0 / (dt * b);
+                            z = log(dt / b);
+                            if (!(q <= 1.7976931348623157e308) || !(fabs(z) <= 1.7976931348623157e308)) { z = 0.0; q = 0.0; }  // lag so small that the pdf underflows
+                        }
+                        ex[pos] = z; ey[pos] = q;
+                    } else ex[pos] = dt;
                     if (lane == __ffs(m) - 1) run[p] = seen + __popc(m);
                 }
                 __syncwarp();
@@ -317,51 +335,80 @@ struct AdjSweepArgs {
     const double *lambda0; const double *W; double *A;   // A: [K*K] parent-major, device, updated in place
     const double *rho; double rho_scalar; const double *u; uint64_t seed, counter;
     double D;
-    const int *vstart; const int64_t *vbase; const int *boff; const unsigned short *ent_i; const double *ent_dt;
-    double *lam;           // [n] by-node order
+    const int *vstart; const int64_t *vbase; const int *boff; const unsigned short *ent_i; const double *ent_x, *ent_y;
+    double *lam;           // [n] by-node order (only used when a column's chunks do not all sit in shared memory)
     int chunk_max;         // doubles of shared memory in front of the adjacency bit row
     int *flag, *next; unsigned long long *stat;
     int col_begin, col_stride, ncols;
     int s0;
 };
 
+// thread-block cluster primitives (distributed shared memory of the CTAs that share a column)
+__device__ __forceinline__ unsigned cluster_ctarank() { unsigned r; asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r)); return r; }
+__device__ __forceinline__ unsigned cluster_nctarank() { unsigned r; asm volatile("mov.u32 %0, %%cluster_nctarank;" : "=r"(r)); return r; }
+__device__ __forceinline__ void cluster_sync_all() {
+    asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void st_cluster_f64(double *local_smem, unsigned rank, double v) {
+    unsigned ra;
+    asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(ra) : "r"(smem_u32(local_smem)), "r"(rank));
+    asm volatile("st.shared::cluster.f64 [%0], %1;" ::"r"(ra), "d"(v) : "memory");
+}
+
+// impulse value of one cached pair.  PRE = 0: x is the lag.  PRE = 1 (LogitNormal): x = logit(dt / D), y = 1 / (dt (D - dt)) from the
+// structure, so the pair costs one exp: cf y exp(-h (x - mu)^2)   (cf carries W sqrt(tau / 2 pi) D^2; y = 0 outside the support)
+template <int KIND, int PRE>
+__device__ __forceinline__ double adj_value(const typename EntryOf<KIND>::type &en, double x, double y, double D, const FastTables *ft);
+template <> __device__ __forceinline__ double adj_value<NHP_EXPONENTIAL, 0>(const EntryEX &en, double x, double, double D, const FastTables *ft) { return pair_value(en, x, D, ft); }
+template <> __device__ __forceinline__ double adj_value<NHP_LOGITNORMAL, 0>(const EntryLN &en, double x, double, double D, const FastTables *ft) { return pair_value(en, x, D, ft); }
+template <> __device__ __forceinline__ double adj_value<NHP_LOGITNORMAL, 1>(const EntryLN &en, double x, double y, double, const FastTables *ft) {
+    const double dz = x - en.mu;
+    return (en.cf * y) * fast_exp_c(-(en.h * dz) * dz, ft);  // exponent <= 0: no overflow branch; flushes to 0 below -707
+}
+
 // One group of 32 consecutive entries [eb, eb + 32) of a bucket that ends at b1, one entry per lane: the impulse value of
 // every entry and, for the first entry of each (event, parent) run (the "head"), the run's total.  Returns head.
-template <int KIND>
-__device__ __forceinline__ bool adj_group(const typename EntryOf<KIND>::type &en, const unsigned short *__restrict__ ei, const double *__restrict__ ed,
-                                          int eb, int b1, int lane, unsigned ii, double dt, double D, const FastTables *ft, double &gsum) {
+template <int KIND, int PRE>
+__device__ __forceinline__ bool adj_group(const typename EntryOf<KIND>::type &en, const unsigned short *__restrict__ ei, const double *__restrict__ ex,
+                                          const double *__restrict__ ey, int eb, int b1, int lane, unsigned ii, double x, double y, double D,
+                                          const FastTables *ft, double &gsum) {
     const bool valid = eb + lane < b1;
-    double v = pair_value(en, dt, D, ft);
-    if (!valid) v = 0.0;
-    const bool cont = valid && (ii & 0x8000u);
-    const unsigned contmask = __ballot_sync(0xffffffffu, cont);
-    const unsigned fol = lane == 31 ? 0u : (contmask >> (lane + 1));
-    const int runlen = __ffs(~fol) - 1;  // entries behind this one that continue its run (inside the group)
-    const bool head = valid && !cont;
-    const int mr = __reduce_max_sync(0xffffffffu, head ? runlen : 0);
+    double v = adj_value<KIND, PRE>(en, x, y, D, ft);
+    v = valid ? v : 0.0;
+    const unsigned contmask = __ballot_sync(0xffffffffu, valid && (ii & 0x8000u));
+    const bool head = valid && !((contmask >> lane) & 1u);
+    int runlen = 0;
     gsum = v;
-    for (int d = 1; d <= mr; d++) {
-        const double vv = __shfl_down_sync(0xffffffffu, v, d);
-        if (d <= runlen) gsum += vv;
+    if (contmask) {  // warp-uniform: some run has more than one entry in this group
+        const unsigned fol = (contmask >> lane) >> 1;
+        runlen = __ffs(~fol) - 1;  // entries behind this one that continue its run (inside the group)
+        const int mr = __reduce_max_sync(0xffffffffu, head ? runlen : 0);
+        for (int d = 1; d <= mr; d++) {
+            const double vv = __shfl_down_sync(0xffffffffu, v, d);
+            if (d <= runlen) gsum += vv;
+        }
     }
-    if (head && lane + runlen == 31)  // the run may go on in the bucket's next group
-        for (int e2 = eb + 32; e2 < b1 && (__ldg(ei + e2) & 0x8000u); e2++) gsum += pair_value(en, __ldg(ed + e2), D, ft);
+    if (eb + 32 < b1) {  // warp-uniform: does the run that reaches lane 31 go on in the bucket's next group?  (one broadcast load)
+        if (__ldg(ei + eb + 32) & 0x8000u) {
+            if (head && lane + runlen == 31)
+                for (int e2 = eb + 32; e2 < b1 && (__ldg(ei + e2) & 0x8000u); e2++) gsum += adj_value<KIND, PRE>(en, __ldg(ex + e2), PRE ? __ldg(ey + e2) : 0.0, D, ft);
+        }
+    }
     return head;
 }
 
-// log((base + g) / base) accumulated as a running quotient of products: one log per fold instead of one per entry
-__device__ __forceinline__ void adj_accumulate(double hi, double base, double &num, double &den, double &acc) {
-    if (in_mid_range(hi) && in_mid_range(base)) {
-        num *= hi; den *= base;  // both factors in [2^-500, 2^500): no overflow before the range test
-        if (!(in_mid_range(num) && in_mid_range(den))) { acc += log(num) - log(den); num = 1.0; den = 1.0; }
-    } else acc += log(hi / base);
-}
+__device__ __forceinline__ bool below_2p500(double x) { return __double2hiint(x) < 0x5F300000; }   // 0 < x < 2^500
+__device__ __forceinline__ bool above_2m500(double x) { return __double2hiint(x) >= 0x20B00000; }  // x >= 2^-500 (x > 0)
 
-template <int KIND> __global__ void __launch_bounds__(ADJ_THREADS, 1) k_adj_sweep(const AdjSweepArgs a) {
+// CL: the CTAs of a thread-block cluster share a column -- CTA r keeps chunk r's intensities in its shared memory for the whole column,
+// partial sums are exchanged through distributed shared memory, one cluster barrier per batch.  Without CL a single CTA owns the
+// column and, when it has several chunks, streams them through shared memory once per batch (intensities in global memory in between).
+template <int KIND, int PRE, bool CL> __global__ void __launch_bounds__(ADJ_THREADS, 1) k_adj_sweep(const AdjSweepArgs a) {
     typedef typename EntryOf<KIND>::type E;
     extern __shared__ __align__(16) double lam_s[];  // [chunk_max] intensities of the resident chunk | adjacency bits of the column
     __shared__ FastTables s_ft;
     __shared__ double s_part[32];
+    __shared__ double s_cl[2][ADJ_CLUSTER_MAX][32];  // [batch parity][source CTA][bucket of the batch]
     __shared__ double s_sgn;
     __shared__ int s_col, s_first;
     fast_tables_load(&s_ft);
@@ -370,21 +417,28 @@ template <int KIND> __global__ void __launch_bounds__(ADJ_THREADS, 1) k_adj_swee
     const int K = a.K;
     unsigned *s_ab = reinterpret_cast<unsigned *>(lam_s + a.chunk_max);  // [(K + 31) / 32]
     const int abw = (K + 31) >> 5;
-    unsigned long long n_steps = 0, n_batches = 0, n_flips = 0, n_redo = 0;
-    for (;;) {
-        __syncthreads();
-        if (tid == 0) s_col = atomicAdd(a.next, 1);
-        __syncthreads();
-        const int ci = s_col;
+    const unsigned crank = CL ? cluster_ctarank() : 0u, csize = CL ? cluster_nctarank() : 1u;
+    const int ncl = CL ? (int)(gridDim.x / csize) : (int)gridDim.x, cid = CL ? (int)(blockIdx.x / csize) : (int)blockIdx.x;
+    unsigned n_steps = 0, n_batches = 0, n_flips = 0, n_redo = 0, parity = 0;
+    for (int ci = cid;; ci += ncl) {
+        if (!CL) {  // a single CTA per column: dynamic scheduling
+            __syncthreads();
+            if (tid == 0) s_col = atomicAdd(a.next, 1);
+            __syncthreads();
+            ci = s_col;
+        }
         if (ci >= a.ncols) break;
         const int c = a.col_begin + ci * a.col_stride;
         const int e0 = a.node_ptr[c], ne = a.node_ptr[c + 1] - e0;
-        const int v0 = a.vstart[c], G = a.vstart[c + 1] - v0;
+        const int v0 = a.vstart[c], G = a.vstart[c + 1] - v0;  // CL: G == cluster size
         const int csz = adj_chunk_size(ne, G);
+        const int g_lo = CL ? (int)crank : 0, g_hi = CL ? (int)crank + 1 : G;
+        const bool resident = CL || G == 1;
         const E *col = reinterpret_cast<const E *>(a.table_w) + (size_t)c * K;
         const double lam0 = a.lambda0[c];
         double *lamg = a.lam + e0;
         double *Acol = a.A + (size_t)K * c;
+        __syncthreads();
         // adjacency bits of the column
         for (int w = warp; w < abw; w += ADJ_THREADS / 32) {
             const int p = w * 32 + lane;
@@ -392,13 +446,14 @@ template <int KIND> __global__ void __launch_bounds__(ADJ_THREADS, 1) k_adj_swee
             if (lane == 0) s_ab[w] = m;
         }
         // ---- current intensities: lambda0 + the links that are on
-        for (int g = 0; g < G; g++) {
-            const int len = min(csz, ne - g * csz);
+        for (int g = g_lo; g < g_hi; g++) {
+            const int len = max(0, min(csz, ne - g * csz));
             for (int e = tid; e < len; e += ADJ_THREADS) lam_s[e] = lam0;
             __syncthreads();
             const int *bo = a.boff + (int64_t)(v0 + g) * (K + 1);
-            const unsigned short *ei = a.ent_i + a.vbase[v0 + g];
-            const double *ed = a.ent_dt + a.vbase[v0 + g];
+            const int64_t vb = a.vbase[v0 + g];
+            const unsigned short *ei = a.ent_i + vb;
+            const double *ex = a.ent_x + vb, *ey = PRE ? a.ent_y + vb : nullptr;
             for (int w = 0; w < abw; w++) {
                 unsigned bits = s_ab[w];
                 while (bits) {  // block-uniform
@@ -410,14 +465,14 @@ template <int KIND> __global__ void __launch_bounds__(ADJ_THREADS, 1) k_adj_swee
                     for (int eb = b0 + warp * 32; eb < b1; eb += ADJ_THREADS) {
                         const bool valid = eb + lane < b1;
                         const unsigned ii = valid ? (unsigned)__ldg(ei + eb + lane) : 0u;
-                        const double dt = valid ? __ldg(ed + eb + lane) : 1.0;
+                        const double x = valid ? __ldg(ex + eb + lane) : 1.0, y = (PRE && valid) ? __ldg(ey + eb + lane) : 0.0;
                         double gs;
-                        if (adj_group<KIND>(en, ei, ed, eb, b1, lane, ii, dt, a.D, ft, gs) && gs > 0.0) lam_s[ii & 0x7fffu] += gs;  // one head per event and bucket
+                        if (adj_group<KIND, PRE>(en, ei, ex, ey, eb, b1, lane, ii, x, y, a.D, ft, gs) && gs > 0.0) lam_s[ii & 0x7fffu] += gs;  // one head per event and bucket
                     }
                     __syncthreads();  // the next parent may touch the same events
                 }
             }
-            if (G > 1) {
+            if (!resident) {
                 for (int e = tid; e < len; e += ADJ_THREADS) lamg[(size_t)g * csz + e] = lam_s[e];
                 __syncthreads();
             }
@@ -442,9 +497,9 @@ template <int KIND> __global__ void __launch_bounds__(ADJ_THREADS, 1) k_adj_swee
             bool on = false;
             if (act) { en = load_entry(col + q); on = (s_ab[q >> 5] >> (q & 31)) & 1u; }
             double acc = 0.0, num = 1.0, den = 1.0;
-            for (int g = 0; g < G; g++) {
-                if (G > 1) {
-                    const int len = min(csz, ne - g * csz);
+            for (int g = g_lo; g < g_hi; g++) {
+                if (!resident) {
+                    const int len = max(0, min(csz, ne - g * csz));
                     __syncthreads();
                     for (int e = tid; e < len; e += ADJ_THREADS) lam_s[e] = __ldcg(lamg + (size_t)g * csz + e);  // written by this CTA: read through L2
                     __syncthreads();
@@ -452,23 +507,33 @@ template <int KIND> __global__ void __launch_bounds__(ADJ_THREADS, 1) k_adj_swee
                 if (act) {
                     const int *bo = a.boff + (int64_t)(v0 + g) * (K + 1);
                     const int b0 = bo[q], b1 = bo[q + 1];
-                    const unsigned short *ei = a.ent_i + a.vbase[v0 + g];
-                    const double *ed = a.ent_dt + a.vbase[v0 + g];
+                    const int64_t vb = a.vbase[v0 + g];
+                    const unsigned short *ei = a.ent_i + vb;
+                    const double *ex = a.ent_x + vb, *ey = PRE ? a.ent_y + vb : nullptr;
                     int eb = b0 + sub * 32;
                     unsigned ii_n = 0u;
-                    double dt_n = 1.0;
-                    if (eb + lane < b1) { ii_n = __ldg(ei + eb + lane); dt_n = __ldg(ed + eb + lane); }
+                    double x_n = 1.0, y_n = 0.0;
+                    if (eb + lane < b1) { ii_n = __ldg(ei + eb + lane); x_n = __ldg(ex + eb + lane); if (PRE) y_n = __ldg(ey + eb + lane); }
                     while (eb < b1) {
                         const unsigned ii = ii_n;
-                        const double dt = dt_n;
+                        const double x = x_n, y = y_n;
                         const int ebn = eb + nsub * 32;
-                        if (ebn + lane < b1) { ii_n = __ldg(ei + ebn + lane); dt_n = __ldg(ed + ebn + lane); }  // next group in flight
+                        if (ebn + lane < b1) { ii_n = __ldg(ei + ebn + lane); x_n = __ldg(ex + ebn + lane); if (PRE) y_n = __ldg(ey + ebn + lane); }  // next group in flight
                         double gs;
-                        if (adj_group<KIND>(en, ei, ed, eb, b1, lane, ii, dt, a.D, ft, gs) && gs > 0.0) {
+                        const bool head = adj_group<KIND, PRE>(en, ei, ex, ey, eb, b1, lane, ii, x, y, a.D, ft, gs) && gs > 0.0;
+                        // log((base + g) / base) accumulated as a running quotient of products: one log per lane and fold instead of one per entry
+                        double base = 1.0, hi = 1.0;
+                        if (head) {
                             const double l = lam_s[ii & 0x7fffu];
-                            const double base = on ? fmax(l - gs, lam0) : l;  // intensity without parent q: at least lambda0
-                            adj_accumulate(base + gs, base, num, den, acc);
+                            base = on ? fmax(l - gs, lam0) : l;  // intensity without parent q: at least lambda0
+                            hi = base + gs;
                         }
+                        const bool okf = above_2m500(base) && below_2p500(hi);  // hi >= base > 0: both factors in [2^-500, 2^500)
+                        if (__any_sync(0xffffffffu, !okf)) {  // warp-uniform, rare: an extreme (or non-positive) intensity takes the direct route
+                            if (!okf) { acc += log(hi / base); base = 1.0; hi = 1.0; }
+                        }
+                        num *= hi; den *= base;  // num >= den > 0
+                        if (__any_sync(0xffffffffu, !(above_2m500(den) && below_2p500(num)))) { acc += log(num) - log(den); num = 1.0; den = 1.0; }  // fold (rare)
                         eb = ebn;
                     }
                 }
@@ -477,10 +542,21 @@ template <int KIND> __global__ void __launch_bounds__(ADJ_THREADS, 1) k_adj_swee
             acc = warp_sum(acc);
             if (lane == 0) s_part[warp] = acc;
             __syncthreads();
+            if (CL) {  // this CTA's share of every bucket of the batch goes to all CTAs of the cluster
+                if (warp == 0 && lane < Sc) {
+                    double mine = 0.0;
+                    for (int s = 0; s < nsub; s++) mine += s_part[lane + (s << lg)];
+                    for (unsigned r = 0; r < csize; r++) st_cluster_f64(&s_cl[parity][crank][lane], r, mine);
+                }
+                cluster_sync_all();
+            }
             if (warp == 0) {
                 const bool have = lane < Sc;
                 double sum = 0.0;
-                if (have) for (int s = 0; s < nsub; s++) sum += s_part[lane + (s << lg)];
+                if (have) {
+                    if (CL) for (unsigned r = 0; r < csize; r++) sum += s_cl[parity][r][lane];  // fixed order: every CTA of the cluster takes the same decision
+                    else for (int s = 0; s < nsub; s++) sum += s_part[lane + (s << lg)];
+                }
                 const int qq = p + lane;
                 const bool old_on = have && ((s_ab[qq >> 5] >> (qq & 31)) & 1u);
                 // ll1 - ll0 (continuous.jl:477-483): integrated-intensity difference, log-intensity difference, prior
@@ -492,12 +568,13 @@ template <int KIND> __global__ void __launch_bounds__(ADJ_THREADS, 1) k_adj_swee
                 const int first = flipmask ? __ffs(flipmask) - 1 : Sc;
                 if (lane == 0) s_first = first;
                 if (lane == first && have) {
-                    Acol[qq] = new_on ? 1.0 : 0.0;
+                    if (crank == 0) Acol[qq] = new_on ? 1.0 : 0.0;
                     s_sgn = new_on ? 1.0 : -1.0;
                     s_ab[qq >> 5] ^= 1u << (qq & 31);
                 }
             }
             __syncthreads();
+            parity ^= 1u;
             const int first = s_first;
             n_batches++;
             if (first < Sc) {
@@ -505,18 +582,19 @@ template <int KIND> __global__ void __launch_bounds__(ADJ_THREADS, 1) k_adj_swee
                 const int qf = p + first;
                 const double sgn = s_sgn;
                 const E enf = load_entry(col + qf);
-                for (int g = 0; g < G; g++) {
+                for (int g = g_lo; g < g_hi; g++) {
                     const int *bo = a.boff + (int64_t)(v0 + g) * (K + 1);
                     const int b0 = bo[qf], b1 = bo[qf + 1];
-                    const unsigned short *ei = a.ent_i + a.vbase[v0 + g];
-                    const double *ed = a.ent_dt + a.vbase[v0 + g];
+                    const int64_t vb = a.vbase[v0 + g];
+                    const unsigned short *ei = a.ent_i + vb;
+                    const double *ex = a.ent_x + vb, *ey = PRE ? a.ent_y + vb : nullptr;
                     for (int eb = b0 + warp * 32; eb < b1; eb += ADJ_THREADS) {
                         const bool valid = eb + lane < b1;
                         const unsigned ii = valid ? (unsigned)__ldg(ei + eb + lane) : 0u;
-                        const double dt = valid ? __ldg(ed + eb + lane) : 1.0;
+                        const double x = valid ? __ldg(ex + eb + lane) : 1.0, y = (PRE && valid) ? __ldg(ey + eb + lane) : 0.0;
                         double gs;
-                        if (adj_group<KIND>(enf, ei, ed, eb, b1, lane, ii, dt, a.D, ft, gs) && gs > 0.0) {
-                            if (G == 1) lam_s[ii & 0x7fffu] += sgn * gs;
+                        if (adj_group<KIND, PRE>(enf, ei, ex, ey, eb, b1, lane, ii, x, y, a.D, ft, gs) && gs > 0.0) {
+                            if (resident) lam_s[ii & 0x7fffu] += sgn * gs;
                             else lamg[(size_t)g * csz + (ii & 0x7fffu)] += sgn * gs;
                         }
                     }
@@ -524,7 +602,7 @@ template <int KIND> __global__ void __launch_bounds__(ADJ_THREADS, 1) k_adj_swee
                 __syncthreads();
                 n_steps += first + 1; n_flips++; n_redo += Sc - 1 - first;
                 p = qf + 1;
-                S = max(S >> 1, ADJ_SMIN);
+                S = max(S >> 1, 1);
             } else {
                 n_steps += Sc;
                 p += Sc;
@@ -532,8 +610,9 @@ template <int KIND> __global__ void __launch_bounds__(ADJ_THREADS, 1) k_adj_swee
             }
         }
     }
-    if (tid == 0 && a.stat) {
-        atomicAdd(a.stat + 0, n_steps); atomicAdd(a.stat + 1, n_batches); atomicAdd(a.stat + 2, n_flips); atomicAdd(a.stat + 3, n_redo);
+    if (tid == 0 && crank == 0 && a.stat) {
+        atomicAdd(a.stat + 0, (unsigned long long)n_steps); atomicAdd(a.stat + 1, (unsigned long long)n_batches);
+        atomicAdd(a.stat + 2, (unsigned long long)n_flips); atomicAdd(a.stat + 3, (unsigned long long)n_redo);
     }
 }
 
@@ -597,14 +676,22 @@ static int adj_build_structure(nhp_ctx *ctx, nhp_events *ev, double horizon, int
     std::vector<double> mn(K);
     ADJ_CUDA(cudaMemcpyAsync(mn.data(), ev->d_Mn, K * sizeof(double), cudaMemcpyDeviceToHost, s));
     ADJ_CUDA(cudaStreamSynchronize(s));
-    // virtual columns: owned columns are cut into chunks of at most chunk_cap events
+    // Virtual columns.  When the largest owned column fits the shared memory of a thread-block cluster (<= 8 CTAs), EVERY owned
+    // column is cut into `cluster` chunks, one per CTA of the cluster that will sweep it; otherwise columns are cut into chunks of at
+    // most chunk_cap events and a single CTA streams them.
+    int max_col = 0;
+    for (int64_t c = cb; c < K; c += cs) max_col = std::max(max_col, (int)mn[c]);
+    int cluster = 1;
+    while (cluster < ADJ_CLUSTER_MAX && (int64_t)cluster * chunk_cap < max_col) cluster *= 2;
+    if ((int64_t)cluster * chunk_cap < max_col) cluster = 0;  // too large for a cluster: single-CTA streaming form
+    { const char *e = getenv("NHP_ADJ_CLUSTER"); if (e && atoi(e) == 0) cluster = 0; }
     std::vector<int> vstart(K + 1), vnode;
     int chunk_max = 1;
     for (int64_t c = 0; c < K; c++) {
         vstart[c] = (int)vnode.size();
         if (c % cs != cb) continue;
         const int ne = (int)mn[c];
-        const int G = std::max(1, (ne + chunk_cap - 1) / chunk_cap);
+        const int G = cluster > 0 ? cluster : std::max(1, (ne + chunk_cap - 1) / chunk_cap);
         chunk_max = std::max(chunk_max, adj_chunk_size(ne, G));
         for (int g = 0; g < G; g++) vnode.push_back((int)c);
     }
@@ -636,13 +723,17 @@ static int adj_build_structure(nhp_ctx *ctx, nhp_events *ev, double horizon, int
         tot += (int64_t)vc[v];
     }
     vbase[nv] = tot;
-    // room: the structure, the bucket offsets, the per-event intensities; keep a quarter of the free memory for everything else
+    // room: the structure (10 B per pair, or 18 B with the LogitNormal payload), the bucket offsets, the per-event intensities;
+    // a quarter (payload: a third) of the free memory stays free for everything else
     size_t free_b = 0, total_b = 0;
     cudaMemGetInfo(&free_b, &total_b);
-    const size_t need = (size_t)tot * 10 + (size_t)nv * (K + 1) * sizeof(int) + (size_t)(nv + 1) * sizeof(int64_t) + (size_t)n * sizeof(double);
+    const size_t fixed = (size_t)nv * (K + 1) * sizeof(int) + (size_t)(nv + 1) * sizeof(int64_t) + (size_t)n * sizeof(double);
+    bool pre = ctx->kind == NHP_LOGITNORMAL && (double)tot * 18.0 + (double)fixed <= 0.72 * (double)free_b;
+    { const char *e = getenv("NHP_ADJ_PRE"); if (e) pre = pre && atoi(e) != 0; }
+    const size_t need = (size_t)tot * (pre ? 18 : 10) + fixed;
     // build kernel: [K+1] offsets + per warp 3 K counters
     int nw = (int)std::min<int64_t>(16, ((int64_t)ctx->smem_optin - 2048 - (K + 1) * 4) / (12 * K));
-    if (need > free_b / 4 * 3 || nw < 1) return drop(1);
+    if ((double)need > 0.75 * (double)free_b || nw < 1) return drop(1);
     cudaFree(d_vcount); d_vcount = nullptr;
     ev->d_adj_vstart = d_vstart; ev->d_adj_vnode = d_vnode; d_vstart = d_vnode = nullptr;  // owned by the handle from here on
     auto fail = [&](int rc) { nhp_events_free_adjacency(ev); return rc; };
@@ -651,12 +742,14 @@ static int adj_build_structure(nhp_ctx *ctx, nhp_events *ev, double horizon, int
     ADJ_S(cudaMalloc(&ev->d_adj_boff, (size_t)nv * (K + 1) * sizeof(int)));
     ADJ_S(cudaMalloc(&ev->d_adj_i, std::max<size_t>((size_t)tot, 1) * sizeof(unsigned short)));
     ADJ_S(cudaMalloc(&ev->d_adj_dt, std::max<size_t>((size_t)tot, 1) * sizeof(double)));
+    if (pre) ADJ_S(cudaMalloc(&ev->d_adj_q, std::max<size_t>((size_t)tot, 1) * sizeof(double)));
     ADJ_S(cudaMalloc(&ev->d_adj_lam, std::max<size_t>((size_t)n, 1) * sizeof(double)));
     ADJ_S(cudaMemcpyAsync(ev->d_adj_vbase, vbase.data(), (size_t)(nv + 1) * sizeof(int64_t), cudaMemcpyHostToDevice, s));
     ADJ_S(cudaMemsetAsync(ctx->d_adj_ctl, 0, 8 * sizeof(int), s));
     AdjBuildArgs b;
-    b.t = ev->d_t; b.c = ev->d_c; b.order = ev->d_order; b.node_ptr = ev->d_node_ptr; b.K = (int)K; b.horizon = horizon;
-    b.vstart = ev->d_adj_vstart; b.vnode = ev->d_adj_vnode; b.vbase = ev->d_adj_vbase; b.boff = ev->d_adj_boff; b.ent_i = ev->d_adj_i; b.ent_dt = ev->d_adj_dt;
+    b.t = ev->d_t; b.c = ev->d_c; b.order = ev->d_order; b.node_ptr = ev->d_node_ptr; b.K = (int)K; b.horizon = horizon; b.D = ctx->dtmax;
+    b.vstart = ev->d_adj_vstart; b.vnode = ev->d_adj_vnode; b.vbase = ev->d_adj_vbase; b.boff = ev->d_adj_boff; b.ent_i = ev->d_adj_i; b.ent_x = ev->d_adj_dt;
+    b.ent_y = pre ? ev->d_adj_q : nullptr;
     b.nv = (int)nv; b.nw = nw; b.next = ctx->d_adj_ctl; b.flag = ctx->d_flag;
     const size_t bsmem = (size_t)(K + 1) * sizeof(int) + (size_t)nw * 3 * K * sizeof(unsigned);
     ADJ_S(cudaFuncSetAttribute(k_adj_build, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)std::max<size_t>(bsmem, 1024)));
@@ -678,7 +771,7 @@ static int adj_build_structure(nhp_ctx *ctx, nhp_events *ev, double horizon, int
     cudaEventDestroy(b0); cudaEventDestroy(b1);
     if (flag & 128) return fail(nhp_fail(ctx, NHP_ERR_CUDA, "adjacency sampler: structure build disagrees with its own count (internal error)"));
     ev->adj_total = tot; ev->adj_nv = nv; ev->adj_horizon = horizon; ev->adj_cb = cb; ev->adj_cs = cs;
-    ev->adj_chunk_cap = chunk_cap; ev->adj_chunk_max = chunk_max;
+    ev->adj_chunk_cap = chunk_cap; ev->adj_chunk_max = chunk_max; ev->adj_cluster = cluster; ev->adj_kind = pre ? 1 : 0;
     ctx->adj_info[7] = bms;
     return NHP_OK;
 #undef ADJ_B
@@ -691,33 +784,30 @@ static int adj_run_uncached(nhp_ctx *ctx, nhp_events *ev, double horizon, const 
     const int64_t K = ctx->K, n = ev->n;
     cudaStream_t s = ctx->stream;
     unsigned long long *d_cc = nullptr;
+    int *d_vstart = nullptr;
     int *d_ent_i = nullptr; double *d_ent_v = nullptr, *d_lam = nullptr, *d_gacc = nullptr;
     auto fin = [&](int rc) {
         cudaStreamSynchronize(s);
-        cudaFree(d_cc); cudaFree(d_ent_i); cudaFree(d_ent_v); cudaFree(d_lam); cudaFree(d_gacc);
+        cudaFree(d_cc); cudaFree(d_vstart); cudaFree(d_ent_i); cudaFree(d_ent_v); cudaFree(d_lam); cudaFree(d_gacc);
         return rc;
     };
 #define ADJ_U(call) do { cudaError_t e__ = (call); if (e__ != cudaSuccess) return fin(nhp_fail(ctx, NHP_ERR_CUDA, "%s failed: %s (%s:%d)", #call, cudaGetErrorString(e__), __FILE__, __LINE__)); } while (0)
     // per-column window totals size the buckets: one "virtual column" per column
     std::vector<int> vstart(K + 1);
     for (int64_t c = 0; c <= K; c++) vstart[c] = (int)c;
-    ADJ_U(cudaMalloc(&d_cc, (size_t)(K + 1) * sizeof(unsigned long long)));
-    int *d_vstart = nullptr;
+    ADJ_U(cudaMalloc(&d_cc, (size_t)K * sizeof(unsigned long long)));
     ADJ_U(cudaMalloc(&d_vstart, (size_t)(K + 1) * sizeof(int)));
-    auto fin2 = [&](int rc) { cudaFree(d_vstart); return fin(rc); };
-    if (cudaMemcpyAsync(d_vstart, vstart.data(), (size_t)(K + 1) * sizeof(int), cudaMemcpyHostToDevice, s) != cudaSuccess ||
-        cudaMemsetAsync(d_cc, 0, (size_t)K * sizeof(unsigned long long), s) != cudaSuccess)
-        return fin2(nhp_fail(ctx, NHP_ERR_CUDA, "adjacency sampler: %s", cudaGetErrorString(cudaGetLastError())));
+    ADJ_U(cudaMemcpyAsync(d_vstart, vstart.data(), (size_t)(K + 1) * sizeof(int), cudaMemcpyHostToDevice, s));
+    ADJ_U(cudaMemsetAsync(d_cc, 0, (size_t)K * sizeof(unsigned long long), s));
     if (n > 0) {
         k_adj_count<<<(unsigned)((n + 255) / 256), 256, 0, s>>>(ev->d_t, ev->d_c, ev->d_order, ev->d_node_ptr, d_vstart, n, horizon, 0, 1, d_cc);
         NHP_LAUNCHED(ctx);
     }
     std::vector<unsigned long long> cc(K);
     std::vector<double> mn(K);
-    if (cudaMemcpyAsync(cc.data(), d_cc, K * sizeof(unsigned long long), cudaMemcpyDeviceToHost, s) != cudaSuccess ||
-        cudaMemcpyAsync(mn.data(), ev->d_Mn, K * sizeof(double), cudaMemcpyDeviceToHost, s) != cudaSuccess || cudaStreamSynchronize(s) != cudaSuccess)
-        return fin2(nhp_fail(ctx, NHP_ERR_CUDA, "adjacency sampler: %s", cudaGetErrorString(cudaGetLastError())));
-    cudaFree(d_vstart); d_vstart = nullptr;
+    ADJ_U(cudaMemcpyAsync(cc.data(), d_cc, K * sizeof(unsigned long long), cudaMemcpyDeviceToHost, s));
+    ADJ_U(cudaMemcpyAsync(mn.data(), ev->d_Mn, K * sizeof(double), cudaMemcpyDeviceToHost, s));
+    ADJ_U(cudaStreamSynchronize(s));
     int64_t cap = 1, mc = 1;
     for (int64_t k = 0; k < K; k++) { cap = std::max<int64_t>(cap, (int64_t)cc[k]); mc = std::max<int64_t>(mc, (int64_t)mn[k]); }
     if (cap >= (int64_t)0x3fffffff) return fin(nhp_fail(ctx, NHP_ERR_UNSUPPORTED, "adjacency sampler: a column has %lld window entries (limit 2^30)", (long long)cap));
@@ -748,6 +838,35 @@ static int adj_run_uncached(nhp_ctx *ctx, nhp_events *ev, double horizon, const 
     ADJ_U(cudaGetLastError());
     return fin(NHP_OK);
 #undef ADJ_U
+}
+
+// launch the cached sweep: one CTA per column, or one thread-block cluster per column (cluster dimension as a launch attribute)
+template <int KIND, int PRE> static int adj_launch_sweep(nhp_ctx *ctx, const AdjSweepArgs &w, size_t smem, int cluster) {
+    cudaStream_t s = ctx->stream;
+    if (cluster <= 1) {
+        auto kernel = k_adj_sweep<KIND, PRE, false>;
+        NHP_CUDA(ctx, cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        const int grid = (int)std::min<int64_t>(w.ncols, ctx->sm_count);
+        kernel<<<grid, ADJ_THREADS, smem, s>>>(w);
+    } else {
+        auto kernel = k_adj_sweep<KIND, PRE, true>;
+        NHP_CUDA(ctx, cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        cudaLaunchConfig_t cfg = {};
+        cudaLaunchAttribute attr[1];
+        attr[0].id = cudaLaunchAttributeClusterDimension;
+        attr[0].val.clusterDim.x = (unsigned)cluster; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+        cfg.blockDim = dim3(ADJ_THREADS); cfg.dynamicSmemBytes = smem; cfg.stream = s; cfg.attrs = attr; cfg.numAttrs = 1;
+        cfg.gridDim = dim3((unsigned)(ctx->sm_count / cluster * cluster));
+        int nclusters = 0;
+        NHP_CUDA(ctx, cudaOccupancyMaxActiveClusters(&nclusters, kernel, &cfg));
+        NHP_CHECK(ctx, nclusters >= 1, NHP_ERR_UNSUPPORTED, "adjacency sampler: no cluster of %d CTAs with %zu B of shared memory fits on this device", cluster, smem);
+        nclusters = (int)std::min<int64_t>(nclusters, w.ncols);
+        cfg.gridDim = dim3((unsigned)(nclusters * cluster));
+        NHP_CUDA(ctx, cudaLaunchKernelEx(&cfg, kernel, w));
+    }
+    NHP_LAUNCHED(ctx);
+    NHP_CUDA(ctx, cudaGetLastError());
+    return NHP_OK;
 }
 
 // One adjacency Gibbs sweep over the owned columns of the device-resident matrix d_A (in place).  d_rho: per-link
@@ -793,28 +912,24 @@ static int adj_run(nhp_ctx *ctx, nhp_events *ev, const double *d_rho, double rho
         AdjSweepArgs w;
         w.node_ptr = ev->d_node_ptr; w.Mn = ev->d_Mn; w.K = (int)K; w.table_w = ctx->d_adj_tw; w.lambda0 = ctx->d_lambda0; w.W = ctx->d_W; w.A = d_A;
         w.rho = d_rho; w.rho_scalar = rho_scalar; w.u = d_u; w.seed = seed; w.counter = counter; w.D = ctx->dtmax;
-        w.vstart = ev->d_adj_vstart; w.vbase = ev->d_adj_vbase; w.boff = ev->d_adj_boff; w.ent_i = ev->d_adj_i; w.ent_dt = ev->d_adj_dt; w.lam = ev->d_adj_lam;
+        w.vstart = ev->d_adj_vstart; w.vbase = ev->d_adj_vbase; w.boff = ev->d_adj_boff; w.ent_i = ev->d_adj_i; w.ent_x = ev->d_adj_dt; w.ent_y = ev->d_adj_q;
+        w.lam = ev->d_adj_lam;
         w.chunk_max = (ev->adj_chunk_max + 1) & ~1;
         w.flag = ctx->d_flag; w.next = ctx->d_adj_ctl; w.stat = ctx->d_adj_stat;
         w.col_begin = (int)col_begin; w.col_stride = (int)col_stride;
         w.ncols = (int)((K - col_begin + col_stride - 1) / col_stride);
         w.s0 = ADJ_SMAX;
-        { const char *e = getenv("NHP_ADJ_S0"); if (e && (atoi(e) == 4 || atoi(e) == 8 || atoi(e) == 16 || atoi(e) == 32)) w.s0 = atoi(e); }
+        { const char *e = getenv("NHP_ADJ_S0"); if (e && atoi(e) >= 1 && atoi(e) <= 32 && (atoi(e) & (atoi(e) - 1)) == 0) w.s0 = atoi(e); }
         const size_t smem = (size_t)w.chunk_max * sizeof(double) + (size_t)((K + 31) / 32) * sizeof(unsigned) + 16;
-        NHP_CHECK(ctx, smem <= (size_t)ctx->smem_optin - 2048, NHP_ERR_UNSUPPORTED, "adjacency sampler: K=%lld needs more shared memory than the device has", (long long)K);
+        NHP_CHECK(ctx, smem <= (size_t)ctx->smem_optin - 4096, NHP_ERR_UNSUPPORTED, "adjacency sampler: K=%lld needs more shared memory than the device has", (long long)K);
         NHP_CUDA(ctx, cudaMemsetAsync(ctx->d_adj_ctl, 0, 8 * sizeof(int), s));
         NHP_CUDA(ctx, cudaMemsetAsync(ctx->d_adj_stat, 0, 8 * sizeof(unsigned long long), s));
-        const int grid = (int)std::min<int64_t>(w.ncols, ctx->sm_count);
-        if (grid <= 0) {}
-        else if (ctx->kind == NHP_LOGITNORMAL) {
-            NHP_CUDA(ctx, cudaFuncSetAttribute(k_adj_sweep<NHP_LOGITNORMAL>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-            k_adj_sweep<NHP_LOGITNORMAL><<<grid, ADJ_THREADS, smem, s>>>(w);
-        } else {
-            NHP_CUDA(ctx, cudaFuncSetAttribute(k_adj_sweep<NHP_EXPONENTIAL>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-            k_adj_sweep<NHP_EXPONENTIAL><<<grid, ADJ_THREADS, smem, s>>>(w);
+        if (w.ncols > 0) {
+            const int cl = ev->adj_cluster;
+            if (ctx->kind == NHP_EXPONENTIAL) NHP_TRY((adj_launch_sweep<NHP_EXPONENTIAL, 0>(ctx, w, smem, cl)));
+            else if (ev->adj_kind == 1) NHP_TRY((adj_launch_sweep<NHP_LOGITNORMAL, 1>(ctx, w, smem, cl)));
+            else NHP_TRY((adj_launch_sweep<NHP_LOGITNORMAL, 0>(ctx, w, smem, cl)));
         }
-        NHP_LAUNCHED(ctx);
-        NHP_CUDA(ctx, cudaGetLastError());
     } else {
         // the uncached kernel wants per-link probabilities and the matrix it updates on the device
         const double *rho_dev = d_rho;
@@ -834,7 +949,9 @@ static int adj_run(nhp_ctx *ctx, nhp_events *ev, const double *d_rho, double rho
     NHP_CHECK(ctx, !(flag & 32), NHP_ERR_CUDA, "adjacency sampler: scratch overflow (internal error)");
     NHP_CHECK(ctx, !(flag & 64), NHP_ERR_NUMERIC, "adjacency sampler: NaN log-likelihood difference");
     ctx->adj_info[0] = (double)st[0]; ctx->adj_info[1] = (double)st[1]; ctx->adj_info[2] = (double)st[2]; ctx->adj_info[3] = (double)st[3];
-    ctx->adj_info[4] = cached ? (double)ev->adj_total : 0.0; ctx->adj_info[5] = cached ? (double)ev->adj_nv : 0.0; ctx->adj_info[6] = ctx->last_ms;
+    ctx->adj_info[4] = cached ? (double)ev->adj_total : 0.0;
+    ctx->adj_info[5] = cached ? (double)ev->adj_nv + 1e-3 * ev->adj_cluster + 1e-6 * (ev->adj_kind ? 18 : 10) : 0.0;  // virtual columns . cluster size, bytes per pair
+    ctx->adj_info[6] = ctx->last_ms;
     return NHP_OK;
 }
 

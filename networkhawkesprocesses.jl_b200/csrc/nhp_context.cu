@@ -288,9 +288,9 @@ int nhp_events_from_device(nhp_ctx *ctx, const double *d_t, const int *d_c, int6
 // cached structure of the adjacency sampler (cont_adjacency.cu)
 void nhp_events_free_adjacency(nhp_events *ev) {
     cudaFree(ev->d_adj_vstart); cudaFree(ev->d_adj_vnode); cudaFree(ev->d_adj_vbase); cudaFree(ev->d_adj_boff);
-    cudaFree(ev->d_adj_i); cudaFree(ev->d_adj_dt); cudaFree(ev->d_adj_lam);
+    cudaFree(ev->d_adj_i); cudaFree(ev->d_adj_dt); cudaFree(ev->d_adj_q); cudaFree(ev->d_adj_lam);
     ev->d_adj_vstart = ev->d_adj_vnode = ev->d_adj_boff = nullptr; ev->d_adj_vbase = nullptr; ev->d_adj_i = nullptr;
-    ev->d_adj_dt = ev->d_adj_lam = nullptr;
+    ev->d_adj_dt = ev->d_adj_q = ev->d_adj_lam = nullptr;
     ev->adj_horizon = -1.0; ev->adj_total = 0; ev->adj_nv = 0;
 }
 

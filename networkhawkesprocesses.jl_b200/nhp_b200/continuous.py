@@ -548,7 +548,11 @@ def adjacency_info(ctx=None):
     out = np.zeros(8)
     ctx.lib.nhp_cont_adjacency_info(ctx.h, out.ctypes.data_as(ctypes.POINTER(ctypes.c_double)))
     keys = ("steps", "batches", "flips", "recomputed_steps", "pairs", "virtual_columns", "sweep_ms", "build_ms")
-    return dict(zip(keys, out.tolist()))
+    d = dict(zip(keys, out.tolist()))
+    nv = np.floor(d["virtual_columns"] + 1e-9)
+    frac = d["virtual_columns"] - nv  # .CCCBBB: cluster size (CTAs per column; 0 = single-CTA streaming form), bytes per cached pair
+    d["virtual_columns"], d["cluster"], d["bytes_per_pair"] = nv, int(round(frac * 1e3 - 0.4)) if frac > 0 else 0, int(round((frac * 1e3 % 1.0) * 1e3)) if frac > 0 else 0
+    return d
 
 
 def mcmc_(process, data, nsteps=1000, log_freq=100, verbose=False, seed=0, device_draws=False, store_every=1):

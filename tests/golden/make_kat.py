@@ -143,6 +143,177 @@ for t in range(T):
 out["E"] = dict(L=L, B=B, dt=dt, phi=phi.tolist(), data=data.tolist(), lambda0=lam0.tolist(), W=Wd.tolist(),
                 conv=conv.tolist(), lam=lam.tolist(), ll=float(ll))
 
+# ------------------------------------------------------------------------------------------------------------------------
+# Round-2 vectors for the rows that had none (a5, a9, Q3, a12, a13, a14): literal numpy restatements of the cited Julia,
+# written without looking at oracle/.
+# ------------------------------------------------------------------------------------------------------------------------
+# KAT-F: intensity(process, data, times) (continuous.jl:76-96): window time - dtmax < t_j < time, STRICT on both sides, so
+# a query at an event's own time excludes that event, and an event exactly dtmax back is excluded as well
+evF, ndF = out["B"]["events"], out["B"]["nodes"]
+lam0F, WF, AF = out["B"]["lambda0"], out["B"]["W"], out["B"]["A"]
+timesF = [0.0, 0.05, 0.4, 0.9, 1.35, 1.4, 2.55, 2.6, 3.0]  # 0.4 / 0.9 / 2.6 are event times; 1.4 - 1.0 = 0.4 sits on the window edge
+
+
+def intensity_at(time, A):
+    lam = [0.0, 0.0]
+    for c in range(2):
+        for tj, p in zip(evF, ndF):
+            if time - 1.0 < tj < time:
+                a = 1.0 if A is None else A[p - 1][c]
+                lam[c] += a * WF[p - 1][c] * ln_pdf(1.0, 1.0, (time - tj) / 1.0)
+    return [lam0F[c] + lam[c] for c in range(2)]
+
+
+out["F"] = dict(times=timesF, standard=[intensity_at(t, None) for t in timesF], network=[intensity_at(t, AF) for t in timesF])
+
+# KAT-G: resample_adjacency_matrix! on KAT-B (continuous.jl:444-519), uniforms given: A[p,c] = (u[p,c] <= exp(ll1 - logsumexp(ll0, ll1))),
+# columns independent, p sequential, sum_log_intensity skipping the log term of event 1 (quirk Q4)
+from scipy.special import logsumexp
+
+
+def sum_log_intensity(node, A):  # continuous.jl:500-519
+    S = 0.0
+    for index in range(1, len(evF) + 1):
+        if ndF[index - 1] != node:
+            continue
+        lam = lam0F[node - 1]
+        if index == 1:
+            continue
+        pi = index - 1
+        while evF[pi - 1] > evF[index - 1] - 1.0:
+            pn = ndF[pi - 1]
+            lam += A[pn - 1][node - 1] * WF[pn - 1][node - 1] * ln_pdf(1.0, 1.0, evF[index - 1] - evF[pi - 1])
+            pi -= 1
+            if pi == 0:
+                break
+        S += np.log(lam)
+    return S
+
+
+def integrated(node, A, counts, T):  # continuous.jl:489-498
+    return lam0F[node - 1] * T + sum(A[p][node - 1] * WF[p][node - 1] * counts[p] for p in range(2))
+
+
+def adjacency_sweep(A0, rho, u, T=3.0):
+    A = [row[:] for row in A0]
+    counts = [sum(1 for x in ndF if x == k + 1) for k in range(2)]
+    probs = [[0.0, 0.0], [0.0, 0.0]]
+    for node in (1, 2):
+        for p in (1, 2):
+            A[p - 1][node - 1] = 0.0
+            ll0 = -integrated(node, A, counts, T) + sum_log_intensity(node, A) + np.log(1.0 - rho)
+            A[p - 1][node - 1] = 1.0
+            ll1 = -integrated(node, A, counts, T) + sum_log_intensity(node, A) + np.log(rho)
+            pr = float(np.exp(ll1 - logsumexp([ll0, ll1])))
+            probs[p - 1][node - 1] = pr
+            A[p - 1][node - 1] = 1.0 if u[p - 1][node - 1] <= pr else 0.0
+    return A, probs
+
+
+casesG = []
+for rho, u in ((0.5, [[0.5, 0.5], [0.5, 0.5]]), (0.3, [[0.1, 0.9], [0.35, 0.2]]), (0.7, [[0.95, 0.05], [0.6, 0.65]])):
+    Aout, probs = adjacency_sweep(AF, rho, u)
+    casesG.append(dict(rho=rho, u=u, A=Aout, p1=probs))
+out["G"] = dict(A0=AF, cases=casesG)
+
+# KAT-H: recursive_loglikelihood of the NETWORK process (continuous.jl:407-442): Exponential impulse, full history; the integral
+# term sums W WITHOUT the adjacency matrix (quirk Q3), the intensities use effective weights A .* W
+evH, ndH, TH = [0.5, 1.0, 1.5, 3.0, 3.2], [1, 2, 1, 2, 2], 4.0
+lam0H, WH, AH, thH = [1.0, 0.5], [[0.1, 0.3], [0.2, 0.4]], [[1.0, 0.0], [1.0, 1.0]], [[1.0, 2.0], [0.5, 1.5]]
+llH = -sum(l * TH for l in lam0H)
+for p in ndH:
+    llH -= sum(WH[p - 1])
+lamH = []
+for i, (t, c) in enumerate(zip(evH, ndH)):
+    v = lam0H[c - 1]
+    for j in range(i):
+        p = ndH[j]
+        v += AH[p - 1][c - 1] * WH[p - 1][c - 1] * thH[p - 1][c - 1] * np.exp(-thH[p - 1][c - 1] * (t - evH[j]))
+    lamH.append(v)
+llH += sum(np.log(lamH))
+llH_windowed = -sum(l * TH for l in lam0H) - sum(sum(AH[p - 1][c] * WH[p - 1][c] for c in range(2)) for p in ndH) + sum(np.log(lamH))
+out["H"] = dict(events=evH, nodes=ndH, duration=TH, lambda0=lam0H, W=WH, A=AH, theta=thH, intensities=lamH, ll_recursive=float(llH),
+                ll_windowed=float(llH_windowed))
+
+# KAT-I: discrete Gibbs parents on KAT-E (parents.jl:82-117): per (t, c) Multinomial(data[c,t], mu), mu = [lambda0_c dt; vec(lambda[b,p])] / sum,
+# realised as data[c,t] categorical inverse-cdf draws (Distributions' rand(Categorical): first k with cp > u) consuming one
+# uniform each in (t outer, c inner, draw) order; only sum_t parents[t,c,:] is used downstream (parents.jl:124-134)
+data1, conv1, T1 = data, conv, T
+data = np.array([[1, 0, 2, 1, 0, 0, 3, 1, 0, 1, 2, 0], [0, 1, 1, 0, 2, 0, 1, 0, 1, 1, 0, 2]])  # a busier 2 x 12 matrix for KAT-I/J/K
+N, T = data.shape
+conv = np.zeros((T, N, B))
+for b in range(B):
+    for n in range(N):
+        full = np.convolve(data[n].astype(float), np.concatenate([[0.0], phi[:, b]]))
+        conv[:, n, b] = np.maximum(full[:T], 0.0)
+thetaI = np.array([[[0.2, 0.3, 0.5], [0.6, 0.3, 0.1]], [[1 / 3, 1 / 3, 1 / 3], [0.1, 0.1, 0.8]]])  # [p, c, b]
+WI = np.array([[0.3, 0.6], [0.9, 0.2]])
+lam0I = np.array([0.4, 0.7])
+uI = [0.05, 0.62, 0.97, 0.33, 0.81, 0.18, 0.44, 0.71, 0.09, 0.56, 0.93, 0.27, 0.38, 0.66, 0.02, 0.85, 0.49, 0.74, 0.13, 0.91, 0.58, 0.30]
+countsI = np.zeros((N, 1 + N * B))
+muI = []
+iu = 0
+for t in range(T):
+    for c in range(N):
+        s = int(data[c, t])
+        if s == 0:
+            continue
+        mu = [lam0I[c] * dt] + [conv[t, p_, b] * WI[p_, c] * thetaI[p_, c, b] * dt for p_ in range(N) for b in range(B)]
+        mu = np.array(mu) / np.sum(mu)
+        muI.append(dict(t=t + 1, c=c + 1, mu=mu.tolist()))
+        for _ in range(s):
+            countsI[c, categorical(mu, uI[iu])] += 1
+            iu += 1
+assert iu == int(data.sum())
+out["I"] = dict(data=data.tolist(), conv=conv.tolist(), lambda0=lam0I.tolist(), W=WI.tolist(), theta=thetaI.tolist(), u=uI[:iu], counts=countsI.tolist(), mu=muI)
+
+# KAT-J: VB statistics on KAT-E (parents.jl:136-177 update_parents; baselines.jl:444-452, weights.jl:70-91, impulses.jl:355-371):
+# u[t,c,:] = [e0_c; conv[t,p,b] E[p,c,b]] / Z;  alpha_sum_c = sum_t u[t,c,1] data[c,t];  gamma_sum[p,c,b] = sum_t data[c,t] u[t,c,1+(p-1)B+b];
+# kappa_sum[p,c] = sum_b gamma_sum[p,c,b];  nu_sum[p,c] = sum_t data[p,t]
+e0J = np.array([0.8, 1.7])
+EJ = np.array([[[0.11, 0.23, 0.05], [0.31, 0.07, 0.19]], [[0.13, 0.29, 0.17], [0.02, 0.37, 0.41]]])  # [p, c, b]
+aJ, gJ = np.zeros(N), np.zeros((N, N, B))
+for t in range(T):
+    for c in range(N):
+        uu = np.array([e0J[c]] + [conv[t, p_, b] * EJ[p_, c, b] for p_ in range(N) for b in range(B)])
+        uu = uu / uu.sum()
+        aJ[c] += uu[0] * data[c, t]
+        for p_ in range(N):
+            for b in range(B):
+                gJ[p_, c, b] += data[c, t] * uu[1 + p_ * B + b]
+out["J"] = dict(e0=e0J.tolist(), E=EJ.tolist(), alpha_sum=aJ.tolist(), gamma_sum=gJ.tolist(), kappa_sum=gJ.sum(axis=2).tolist(),
+                nu_sum=np.tile(data.sum(axis=1)[:, None].astype(float), (1, N)).tolist())
+
+# KAT-K: discrete adjacency sweep on KAT-E (discrete.jl:426-480), uniforms given; conditional_loglikelihood recomputes the whole column
+AK0 = np.array([[1.0, 0.0], [1.0, 1.0]])
+
+
+def cond_ll(A, value, pidx, cidx):  # discrete.jl:462-480
+    ll = 0.0
+    for t in range(T):
+        lam_ = lam0I[cidx] * dt
+        for p_ in range(N):
+            a = value if p_ == pidx else A[p_, cidx]
+            for b in range(B):
+                lam_ += conv[t, p_, b] * a * WI[p_, cidx] * thetaI[p_, cidx, b] * dt
+        ll += stats.poisson(lam_).logpmf(data[cidx, t])
+    return ll
+
+
+casesK = []
+for rho, u in ((0.5, [[0.5, 0.5], [0.5, 0.5]]), (0.2, [[0.05, 0.4], [0.9, 0.1]])):
+    A = AK0.copy()
+    pr = np.zeros((N, N))
+    for c in range(N):
+        for p_ in range(N):
+            l0 = cond_ll(A, 0.0, p_, c) + np.log(1 - rho)
+            l1 = cond_ll(A, 1.0, p_, c) + np.log(rho)
+            pr[p_, c] = np.exp(l1 - logsumexp([l0, l1]))
+            A[p_, c] = 1.0 if u[p_][c] <= pr[p_, c] else 0.0
+    casesK.append(dict(rho=rho, u=u, A=A.tolist(), p1=pr.tolist()))
+out["K"] = dict(A0=AK0.tolist(), cases=casesK)
+data, conv, T = data1, conv1, T1
+
 # peripheral fixtures the reference's own tests hold (test/baselines.jl:10-23, 77-78)
 out["ref_tests"] = dict(
     node_counts=[dict(nodes=[1, 1, 2, 2], parentnodes=[0, 1, 0, 2], K=2, expect=[1.0, 1.0]),

@@ -20,8 +20,8 @@ def run_both(proc, om, data, rho, u, A0, **kw):
     return A_gpu, A_ref
 
 
-@pytest.mark.parametrize("chunk", [None, 7, 64])
-@pytest.mark.parametrize("s0", [None, 4])
+@pytest.mark.parametrize("chunk", [None, 7, 64])   # 64: thread-block clusters of 4 (8) CTAs per column; 7: too many chunks for a cluster -> streaming form
+@pytest.mark.parametrize("s0", [None, 1])
 @pytest.mark.parametrize("kind,K,n,rate,rho", [("ln", 4, 900, 14.0, 0.5), ("ln", 37, 6000, 80.0, 0.2), ("exp", 6, 1500, 20.0, 0.4)])
 def test_chunked_speculative_sweep_matches_oracle(monkeypatch, kind, K, n, rate, rho, chunk, s0):
     """Small chunks force several chunks per column (intensities streamed through global memory between batches); few nodes and
@@ -44,6 +44,28 @@ def test_chunked_speculative_sweep_matches_oracle(monkeypatch, kind, K, n, rate,
     assert info["steps"] == K * K and info["pairs"] > 0
     if chunk is not None:
         assert info["virtual_columns"] > K
+
+
+@pytest.mark.parametrize("chunk,cluster", [(None, None), (64, None), (64, "0")])
+def test_lag_payload_and_forced_streaming_form_match_oracle(monkeypatch, chunk, cluster):
+    """LogitNormal with the 10-byte lag payload (what a tight memory budget selects) and the single-CTA streaming form forced on
+    data that would fit a cluster."""
+    monkeypatch.setenv("NHP_ADJ_PRE", "0")
+    if chunk is not None:
+        monkeypatch.setenv("NHP_ADJ_CHUNK", str(chunk))
+    if cluster is not None:
+        monkeypatch.setenv("NHP_ADJ_CLUSTER", cluster)
+    K, n, rho = 11, 4000, 0.3
+    t, nodes, T = synth.poisson_stream(n, K, 60.0, 77)
+    proc, om = make_ln(K, 7, density=0.5, wmax=1.5 / K)
+    proc.network = nhp.BernoulliNetworkModel(rho, K)
+    A0 = proc.adjacency_matrix.copy()
+    u = np.random.default_rng(5).random((K, K))
+    A_gpu, A_ref = run_both(proc, om, (t, nodes, T), rho, u, A0)
+    np.testing.assert_array_equal(A_gpu, A_ref)
+    info = nhp.adjacency_info()
+    assert info["bytes_per_pair"] == 10
+    assert info["cluster"] == (0 if cluster == "0" else (1 if chunk is None else 8))
 
 
 def test_uncached_fallback_matches_oracle(monkeypatch):

@@ -174,3 +174,62 @@ def test_gradient_oracle_closed_form_two_events():
         assert g0[0] == pytest.approx(1 / lam0 + 1 / l2 - T, rel=1e-14)
         assert gW[0, 0] == pytest.approx(th * np.exp(-th) / l2 - 2.0, rel=1e-14)
         assert g1[0, 0] == pytest.approx(W * np.exp(-th) * (1 - th) / l2, rel=1e-14)
+
+
+# ---------------------------------------------------------------------------- round-2 vectors (KAT-F..K): rows a5, a9, Q3, a12, a13, a14
+def _kat_b_models(kat):
+    k = kat["B"]
+    W, mu, tau = np.array(k["W"]), np.full((2, 2), k["mu"]), np.full((2, 2), k["tau"])
+    return k, orc.Cont(1, k["lambda0"], W, mu, tau, dtmax=k["dtmax"]), orc.Cont(1, k["lambda0"], W, mu, tau, A=np.array(k["A"]), dtmax=k["dtmax"])
+
+
+def test_kat_f_intensity_at_query_times_strict_window(kat):
+    k, std, net = _kat_b_models(kat)
+    tq = np.array(kat["F"]["times"])
+    np.testing.assert_allclose(std.intensity(k["events"], k["nodes"], tq), kat["F"]["standard"], rtol=RTOL)
+    np.testing.assert_allclose(net.intensity(k["events"], k["nodes"], tq), kat["F"]["network"], rtol=RTOL)
+
+
+def test_kat_g_adjacency_sweep_given_uniforms(kat):
+    k, _, net = _kat_b_models(kat)
+    for case in kat["G"]["cases"]:
+        A = net.resample_adjacency(np.array(kat["G"]["A0"]), np.full((2, 2), case["rho"]), k["events"], k["nodes"], k["duration"], np.array(case["u"]))
+        np.testing.assert_array_equal(A, case["A"])
+
+
+def test_kat_h_recursive_network_loglik_quirk_q3(kat):
+    k = kat["H"]
+    m = orc.Cont(0, k["lambda0"], np.array(k["W"]), np.array(k["theta"]), A=np.array(k["A"]))
+    np.testing.assert_allclose(m.event_intensity(k["events"], k["nodes"]), k["intensities"], rtol=RTOL)
+    assert m.loglik(k["events"], k["nodes"], k["duration"], recursive=True) == pytest.approx(k["ll_recursive"], rel=RTOL)
+    assert m.loglik(k["events"], k["nodes"], k["duration"], recursive=False) == pytest.approx(k["ll_windowed"], rel=RTOL)
+    assert k["ll_recursive"] != k["ll_windowed"]  # the compensator of the recursive form ignores A
+
+
+def _kat_i_model(kat, A=None):
+    k = kat["I"]
+    return k, np.array(k["data"], dtype=np.int64), np.array(k["conv"]), orc.Disc(k["lambda0"], np.array(k["W"]), np.array(k["theta"]), dt=1.0, A=A)
+
+
+def test_kat_i_discrete_gibbs_counts_given_uniforms(kat):
+    k, data, conv, m = _kat_i_model(kat)
+    np.testing.assert_allclose(orc.disc_convolve(data, orc.disc_basis(4, 3, 1.0)), conv, rtol=RTOL, atol=1e-300)
+    np.testing.assert_array_equal(m.gibbs_counts(data, conv, np.array(k["u"])), k["counts"])
+
+
+def test_kat_j_vb_statistics(kat):
+    k, data, conv, _ = _kat_i_model(kat)
+    j = kat["J"]
+    st = orc.disc_vb_stats(data, conv, np.array(j["e0"]), np.array(j["E"]))
+    np.testing.assert_allclose(st["alpha_sum"], j["alpha_sum"], rtol=RTOL)
+    np.testing.assert_allclose(st["gamma_sum"], j["gamma_sum"], rtol=RTOL, atol=1e-300)
+    np.testing.assert_allclose(st["kappa_sum"], j["kappa_sum"], rtol=RTOL)
+    np.testing.assert_array_equal(st["nu_sum"], j["nu_sum"])
+
+
+def test_kat_k_discrete_adjacency_given_uniforms(kat):
+    A0 = np.array(kat["K"]["A0"])
+    k, data, conv, m = _kat_i_model(kat, A=A0)
+    for case in kat["K"]["cases"]:
+        A = m.resample_adjacency(A0, np.full((2, 2), case["rho"]), data, conv, np.array(case["u"]))
+        np.testing.assert_array_equal(A, case["A"])
