@@ -18,7 +18,8 @@ keeps 1e8 events per GPU instead.
 
 Data: `--data hawkes` (default) draws the stream from the model itself with the device branching simulator (nhp_cont_rand), so the
 chain runs on data that carry the network (few links flip per sweep once mixed, as in a real `mcmc!` run); `--data surrogate` is
-round 1's Poisson surrogate (iid gaps, uniform nodes) with the parameters rewound before every step.
+round 1's Poisson surrogate (iid gaps, uniform nodes).  Every step starts from the workload's parameters
+(`--chain rewind`, default; `--chain free` lets the chain keep its state).
 
   python bench.py [--gpus N] [--steps K] [--warmup W]           (torchrun launches N > 1)
   python bench.py --impl reference ...                          (CPU oracle arm, all host threads)
@@ -61,6 +62,8 @@ def parse():
     ap.add_argument("--nodes", type=int, default=1000)
     ap.add_argument("--scaling", default="strong", choices=["strong", "weak"])
     ap.add_argument("--data", default="hawkes", choices=["hawkes", "surrogate"])
+    ap.add_argument("--chain", default="rewind", choices=["rewind", "free"],
+                    help="rewind: every step is one sweep from the workload's parameters (stationary, reproducible timing); free: the chain keeps its state")
     ap.add_argument("--cpu-sample", type=float, default=1e6, help="events of the CPU-baseline sample (log-likelihood + parent sweep)")
     ap.add_argument("--cpu-adj-sample", type=float, default=1e5, help="events of the CPU-baseline sample of the adjacency sweep")
     ap.add_argument("--no-cpu-baseline", action="store_true")
@@ -203,7 +206,7 @@ def workload_config(args, world, n_total, n_shard):
     return {"workload": "cfg4: continuous LogitNormal network Hawkes, Bernoulli(rho=0.05) adjacency, K=%d, %.3g events, rate 64/s, dtmax=1 (mean window 64); "
                         "step = loglikelihood + full Gibbs sweep (parents + fused statistics + conjugate draws + adjacency sweep + rho draw)" % (args.nodes, n_total),
             "K": args.nodes, "global_events": int(n_total), "events_per_gpu": int(n_shard), "mean_window": RATE * DTMAX, "rho": RHO,
-            "data_mode": args.data,
+            "data_mode": args.data, "chain": args.chain,
             "sharding": ("contiguous time shards + dtmax halo (log-likelihood, parent sweep, statistics); child columns c % N == rank on the replicated stream "
                          "(adjacency sweep)") if world > 1 else "single GPU",
             "l2_policy": "inputs (1.2 GB of events, 64 GB of cached adjacency pairs) are larger than the 126 MB L2; no explicit flush"}
@@ -386,15 +389,20 @@ def run_ours(args, rank, world, local_rank):
             h_full = upload(0, n_total, 0, 1)
         ev_shard = upload_shard()
     ev_full = h_full
-    if args.data == "surrogate":
+    if args.chain == "rewind":
         ctx.check(lib.nhp_cont_params_save(ctx.h))
 
     op_ms = {"loglik": [], "parents": [], "draws": [], "adjacency": [], "step": []}
     adj_rows = []
 
     def step(counter, record=False):
-        if args.data == "surrogate":
-            ctx.check(lib.nhp_cont_params_restore(ctx.h))  # the surrogate carries no network: rewind the chain to the workload's parameters
+        if args.chain == "rewind":
+            # Every step is one sweep from the workload's parameters (device-to-device copy + table rebuild, ~0.5 ms, inside the timed region).
+            # Left alone, the chain does not stay at cfg4's 5 % density: the model resamples W from its prior where A = 0 (weights.jl:59-64,
+            # quirk Q14), so uninformative links switch on with probability ~rho, rho follows (networks.jl:72-78), and A fills up sweep by
+            # sweep -- a property of the reference's sampler, kept as is, but not a stationary workload to time.
+            ctx.check(lib.nhp_cont_params_restore(ctx.h))
+            ctx.check(lib.nhp_cont_network_set(ctx.h, RHO))
         e0 = torch.cuda.Event(enable_timing=True); e1 = torch.cuda.Event(enable_timing=True)
         e0.record(stream)
         ll = ctypes.c_double()
@@ -429,7 +437,7 @@ def run_ours(args, rank, world, local_rank):
     if world == 1 and not args.no_cpu_baseline:
         parity, cpu_sample = parity_check(args, ctx, (lam0, W, mu, tau, A), h_t, h_c)
         set_params()
-        if args.data == "surrogate":
+        if args.chain == "rewind":
             ctx.check(lib.nhp_cont_params_save(ctx.h))
 
     for w in range(args.warmup):

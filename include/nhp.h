@@ -125,6 +125,9 @@ int nhp_cont_resample_parents(nhp_ctx *ctx, nhp_events *ev, uint64_t seed, uint6
  * returns that log-likelihood (same value as nhp_cont_loglik with recursive = 0) without a second pass over the events.  For a shard: the shard's additive share; the terms
  * also sit in slots 0..1 of the phase-0 statistics buffer, so the multi-GPU all-reduce carries them. */
 int nhp_cont_sweep_loglik(nhp_ctx *ctx, nhp_events *ev, double *ll);
+/* The assignment the device currently holds, in the reference's format (parents.jl:1-23): what a caller that destructures
+ * `parents, parentnodes = resample_parents(process, data)` gets, exported on demand.  Either pointer may be NULL. */
+int nhp_cont_parents_get(nhp_ctx *ctx, nhp_events *ev, int64_t *parents, int64_t *parentnodes);
 /* Import a parent assignment (1-based global indices, 0 = baseline) and rebuild the fused
  * statistics from it: the "statistics given identical parent assignments" entry. */
 int nhp_cont_parents_set(nhp_ctx *ctx, nhp_events *ev, const int64_t *parents);
@@ -161,6 +164,7 @@ int nhp_cont_adjacency_commit(nhp_ctx *ctx);
 /* resample!(network::BernoulliNetworkModel, data)  networks.jl:72-78: rho ~ Beta(alpha + sum(A), beta + K^2 - sum(A)) from the
  * device-resident adjacency matrix (Philox: seed, counter); the value stays with the context and is returned in *rho_out. */
 int nhp_cont_network_set(nhp_ctx *ctx, double rho);
+int nhp_cont_network_get(const nhp_ctx *ctx, double *rho);
 int nhp_cont_resample_network(nhp_ctx *ctx, uint64_t seed, uint64_t counter, double alpha, double beta, double *rho_out);
 
 /* Device-side conjugate draws of one Gibbs sweep (the `resample!` of baseline, weights and impulses:
@@ -219,6 +223,8 @@ int nhp_disc_basis(int64_t L, int64_t B, double dt, double *phi);
 /* convolve(process, data)  discrete.jl:146-151; result stays on the device; conv_out (T*N*B,
  * conv[t + T*(n + N*b)]) may be NULL */
 int nhp_disc_convolve(nhp_ctx *ctx, nhp_disc *dd, const double *phi, int64_t L, int64_t B, double *conv_out);
+/* the device-resident convolution in the reference's layout conv[t + T*(n + N*b)], for host code that indexes `convolved` */
+int nhp_disc_conv_export(nhp_ctx *ctx, nhp_disc *dd, double *conv_out);
 /* lambda0[N], W[N*N], A[N*N]|NULL, theta[N*N*B] (theta[p + N*(c + N*b)]), dt   discrete.jl:161-170, 395-402 */
 int nhp_disc_params_set(nhp_ctx *ctx, int64_t N, int64_t B, const double *lambda0, const double *W, const double *A,
                         const double *theta, double dt);

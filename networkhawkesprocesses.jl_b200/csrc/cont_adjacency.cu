@@ -185,7 +185,7 @@ template <int KIND> __global__ void __launch_bounds__(256) k_adjacency(const Adj
 // ---------------------------------------------------------------------------------------
 constexpr int ADJ_CHUNK_MAX = 26624;   // child events per chunk: 208 KB of shared-memory intensities
 constexpr int ADJ_THREADS = 1024;      // sweep CTA: one per SM
-constexpr int ADJ_SMAX = 32;           // speculative batch size (buckets per batch): halves after a flip (down to 1), doubles after a clean batch
+constexpr int ADJ_SMAX = 32;           // largest speculative batch (buckets per batch); the size follows the observed flip rate, down to 1
 constexpr int ADJ_CLUSTER_MAX = 8;     // portable cluster size limit
 
 // a column's ne child events are split into G chunks of this many events (the last one may be shorter)
@@ -420,6 +420,11 @@ template <int KIND, int PRE, bool CL> __global__ void __launch_bounds__(ADJ_THRE
     const unsigned crank = CL ? cluster_ctarank() : 0u, csize = CL ? cluster_nctarank() : 1u;
     const int ncl = CL ? (int)(gridDim.x / csize) : (int)gridDim.x, cid = CL ? (int)(blockIdx.x / csize) : (int)blockIdx.x;
     unsigned n_steps = 0, n_batches = 0, n_flips = 0, n_redo = 0, parity = 0;
+    // Batch size policy: with a flip probability f per step a batch of S buckets costs c0 + S c1 and gets (1 - (1-f)^S) / f steps accepted,
+    // which is cheapest near S ~ 2 / sqrt(f) for the measured c0 / c1 ~ 2; f is an exponentially weighted estimate carried across columns
+    // (the same arithmetic in every CTA of a cluster, so they agree on S).
+    float fw_steps = 64.f, fw_flips = 64.f * fmaxf(4.f / (float)(a.s0 * a.s0) - 1e-3f, 0.f);
+    int S = a.s0;
     for (int ci = cid;; ci += ncl) {
         if (!CL) {  // a single CTA per column: dynamic scheduling
             __syncthreads();
@@ -478,7 +483,7 @@ template <int KIND, int PRE, bool CL> __global__ void __launch_bounds__(ADJ_THRE
             }
         }
         // ---- K Bernoulli steps in speculative batches
-        int p = 0, S = a.s0;
+        int p = 0;
         while (p < K) {
             const int Sc = min(S, K - p);
             const int lg = 31 - __clz(S);
@@ -496,6 +501,19 @@ template <int KIND, int PRE, bool CL> __global__ void __launch_bounds__(ADJ_THRE
             E en = E();
             bool on = false;
             if (act) { en = load_entry(col + q); on = (s_ab[q >> 5] >> (q & 31)) & 1u; }
+            if (S <= 4 && resident) {
+                // short batches are latency bound: pull the entries of the buckets that can come next (they follow in memory) into L2 now
+                const int g = g_lo;
+                const int *bo = a.boff + (int64_t)(v0 + g) * (K + 1);
+                const int q0 = min(p + Sc, K), q1 = min(p + Sc + 2 * S + 2, K);
+                const int64_t vb = a.vbase[v0 + g];
+                const int f0 = bo[q0], f1 = bo[q1];
+                for (int e = f0 + tid * 16; e < f1; e += ADJ_THREADS * 16) {  // 16 entries = one 128-byte line of the f64 payload
+                    asm volatile("prefetch.global.L2 [%0];" ::"l"(a.ent_x + vb + e));
+                    if (PRE) asm volatile("prefetch.global.L2 [%0];" ::"l"(a.ent_y + vb + e));
+                    if ((e & 63) == (f0 & 63)) asm volatile("prefetch.global.L2 [%0];" ::"l"(a.ent_i + vb + e));
+                }
+            }
             double acc = 0.0, num = 1.0, den = 1.0;
             for (int g = g_lo; g < g_hi; g++) {
                 if (!resident) {
@@ -602,11 +620,16 @@ template <int KIND, int PRE, bool CL> __global__ void __launch_bounds__(ADJ_THRE
                 __syncthreads();
                 n_steps += first + 1; n_flips++; n_redo += Sc - 1 - first;
                 p = qf + 1;
-                S = max(S >> 1, 1);
+                fw_steps = 0.9f * fw_steps + (float)(first + 1); fw_flips = 0.9f * fw_flips + 1.f;
             } else {
                 n_steps += Sc;
                 p += Sc;
-                S = min(S << 1, ADJ_SMAX);
+                fw_steps = 0.9f * fw_steps + (float)Sc; fw_flips = 0.9f * fw_flips;
+            }
+            {
+                const float target = 2.f * rsqrtf(fw_flips / fw_steps + 1e-3f);
+                const int l2 = min(5, max(0, __float2int_rn(__log2f(target))));
+                S = 1 << l2;
             }
         }
     }

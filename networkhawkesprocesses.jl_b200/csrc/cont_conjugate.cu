@@ -246,6 +246,12 @@ extern "C" int nhp_cont_resample_network(nhp_ctx *ctx, uint64_t seed, uint64_t c
     return NHP_OK;
 }
 
+extern "C" int nhp_cont_network_get(const nhp_ctx *ctx, double *rho) {
+    if (!ctx || !rho) return NHP_ERR_INVALID;
+    *rho = ctx->rho;
+    return NHP_OK;
+}
+
 extern "C" int nhp_cont_network_set(nhp_ctx *ctx, double rho) {
     NHP_CHECK(ctx, ctx != nullptr, NHP_ERR_INVALID, "ctx is NULL");
     NHP_CHECK(ctx, rho >= 0.0 && rho <= 1.0, NHP_ERR_INVALID, "BernoulliNetworkModel: link probability must be in [0, 1]");

@@ -611,6 +611,15 @@ extern "C" int nhp_cont_resample_parents(nhp_ctx *ctx, nhp_events *ev, uint64_t 
     return export_parents(ctx, ev, parents, parentnodes);
 }
 
+// (parents, parentnodes) of the assignment the device currently holds (the last sweep, or nhp_cont_parents_set), in the reference's format
+extern "C" int nhp_cont_parents_get(nhp_ctx *ctx, nhp_events *ev, int64_t *parents, int64_t *parentnodes) {
+    NHP_CHECK(ctx, ctx != nullptr, NHP_ERR_INVALID, "ctx is NULL");
+    NHP_CHECK(ctx, ev != nullptr, NHP_ERR_INVALID, "nhp_cont_parents_get: events handle is NULL");
+    NHP_CHECK(ctx, ctx->parents_valid, NHP_ERR_STATE, "nhp_cont_parents_get: no parent assignment (call nhp_cont_resample_parents or nhp_cont_parents_set)");
+    NHP_CUDA(ctx, cudaSetDevice(ctx->device));
+    return export_parents(ctx, ev, parents, parentnodes);
+}
+
 // log-likelihood of the parameters used by the most recent parent sweep, from the terms that sweep accumulated
 extern "C" int nhp_cont_sweep_loglik(nhp_ctx *ctx, nhp_events *ev, double *ll) {
     NHP_CHECK(ctx, ctx != nullptr, NHP_ERR_INVALID, "ctx is NULL");

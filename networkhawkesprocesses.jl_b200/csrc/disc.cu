@@ -328,6 +328,25 @@ extern "C" int nhp_disc_convolve(nhp_ctx *ctx, nhp_disc *dd, const double *phi, 
     return NHP_OK;
 }
 
+// the device-resident convolution of a handle in the reference's layout conv[t + T*(n + N*b)] (what `convolve` returns in Julia);
+// only needed when host code looks inside it -- the sweeps read it on the device
+extern "C" int nhp_disc_conv_export(nhp_ctx *ctx, nhp_disc *dd, double *conv_out) {
+    NHP_CHECK(ctx, ctx != nullptr, NHP_ERR_INVALID, "ctx is NULL");
+    NHP_CHECK(ctx, dd != nullptr && conv_out != nullptr, NHP_ERR_INVALID, "nhp_disc_conv_export: NULL argument");
+    NHP_CHECK(ctx, dd->d_conv != nullptr && dd->B > 0, NHP_ERR_STATE, "nhp_disc_conv_export: call nhp_disc_convolve first");
+    NHP_CUDA(ctx, cudaSetDevice(ctx->device));
+    cudaStream_t s = ctx->stream;
+    const int64_t NB = dd->N * dd->B;
+    void *scratch;
+    NHP_TRY(nhp_scratch(ctx, (size_t)dd->T * NB * sizeof(double), &scratch));
+    dim3 g((unsigned)((dd->T + 31) / 32), (unsigned)((NB + 31) / 32)), b(32, 8);
+    k_conv_export<<<g, b, 0, s>>>(dd->d_conv, (int)dd->N, (int)dd->B, dd->T, (double *)scratch);
+    NHP_LAUNCHED(ctx);
+    DCUDA(ctx, cudaMemcpyAsync(conv_out, scratch, (size_t)dd->T * NB * sizeof(double), cudaMemcpyDeviceToHost, s));
+    DCUDA(ctx, cudaStreamSynchronize(s));
+    return NHP_OK;
+}
+
 // ---------------------------------------------------------------------------------------
 // parameters: bump[p,c,b] = [A] W theta dt  (discrete.jl:381-385, 511-516)
 // ---------------------------------------------------------------------------------------

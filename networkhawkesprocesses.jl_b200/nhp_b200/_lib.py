@@ -49,6 +49,9 @@ PROTOTYPES = {
     "nhp_cont_resample_adjacency_cols": (c_int, [c_void_p, c_void_p, c_void_p, c_uint64, c_uint64, c_void_p, c_void_p, c_int64, c_int64]),
     "nhp_cont_resample_adjacency_dev": (c_int, [c_void_p, c_void_p, c_double, c_uint64, c_uint64, c_int64, c_int64, c_int]),
     "nhp_cont_adjacency_commit": (c_int, [c_void_p]),
+    "nhp_cont_network_get": (c_int, [c_void_p, c_double_p]),
+    "nhp_cont_parents_get": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p]),
+    "nhp_disc_conv_export": (c_int, [c_void_p, c_void_p, c_void_p]),
     "nhp_cont_network_set": (c_int, [c_void_p, c_double]),
     "nhp_cont_resample_network": (c_int, [c_void_p, c_uint64, c_uint64, c_double, c_double, c_double_p]),
     "nhp_cont_adjacency_info": (c_int, [c_void_p, c_double_p]),
