@@ -407,10 +407,10 @@ template <int KIND, int PRE, bool CL> __global__ void __launch_bounds__(ADJ_THRE
     typedef typename EntryOf<KIND>::type E;
     extern __shared__ __align__(16) double lam_s[];  // [chunk_max] intensities of the resident chunk | adjacency bits of the column
     __shared__ FastTables s_ft;
-    __shared__ double s_part[32];
-    __shared__ double s_cl[2][ADJ_CLUSTER_MAX][32];  // [batch parity][source CTA][bucket of the batch]
-    __shared__ double s_sgn;
+    __shared__ double s_part[32], s_pmax[32];
+    __shared__ double s_cl[2][ADJ_CLUSTER_MAX][32], s_cm[2][ADJ_CLUSTER_MAX][32];  // [batch parity][source CTA][bucket of the batch]: sums, largest contributions
     __shared__ int s_col, s_first;
+    __shared__ unsigned s_mask, s_onmask;
     fast_tables_load(&s_ft);
     const FastTables *ft = &s_ft;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -491,12 +491,14 @@ template <int KIND, int PRE, bool CL> __global__ void __launch_bounds__(ADJ_THRE
             const int q = p + qi;
             const bool act = qi < Sc;
             // the deciding lanes fetch their inputs before the batch so that the latency hides behind it
-            double d_w = 0.0, d_mn = 0.0, d_rho = 0.5, d_u = 2.0;
+            double d_w = 0.0, d_mn = 0.0, d_lrho = 0.0, d_u = 2.0, d_lu = 0.0;
             if (warp == 0 && lane < Sc) {
                 const int64_t kk = (p + lane) + (int64_t)K * c;
                 d_w = a.W[kk]; d_mn = a.Mn[p + lane];
-                d_rho = a.rho ? a.rho[kk] : a.rho_scalar;
+                const double rho = a.rho ? a.rho[kk] : a.rho_scalar;
+                d_lrho = log(rho) - log(1.0 - rho);
                 d_u = a.u ? a.u[kk] : philox_uniform(a.seed, (uint64_t)kk, a.counter);
+                d_lu = log(d_u) - log(1.0 - d_u);  // logit(u): delta - logit(u) is the margin by which the decision u <= sigmoid(delta) holds
             }
             E en = E();
             bool on = false;
@@ -514,7 +516,7 @@ template <int KIND, int PRE, bool CL> __global__ void __launch_bounds__(ADJ_THRE
                     if ((e & 63) == (f0 & 63)) asm volatile("prefetch.global.L2 [%0];" ::"l"(a.ent_i + vb + e));
                 }
             }
-            double acc = 0.0, num = 1.0, den = 1.0;
+            double acc = 0.0, num = 1.0, den = 1.0, gmx = 0.0;
             for (int g = g_lo; g < g_hi; g++) {
                 if (!resident) {
                     const int len = max(0, min(csz, ne - g * csz));
@@ -545,6 +547,7 @@ template <int KIND, int PRE, bool CL> __global__ void __launch_bounds__(ADJ_THRE
                             const double l = lam_s[ii & 0x7fffu];
                             base = on ? fmax(l - gs, lam0) : l;  // intensity without parent q: at least lambda0
                             hi = base + gs;
+                            gmx = fmax(gmx, gs);
                         }
                         const bool okf = above_2m500(base) && below_2p500(hi);  // hi >= base > 0: both factors in [2^-500, 2^500)
                         if (__any_sync(0xffffffffu, !okf)) {  // warp-uniform, rare: an extreme (or non-positive) intensity takes the direct route
@@ -558,47 +561,75 @@ template <int KIND, int PRE, bool CL> __global__ void __launch_bounds__(ADJ_THRE
             }
             acc += log(num) - log(den);
             acc = warp_sum(acc);
-            if (lane == 0) s_part[warp] = acc;
+#pragma unroll
+            for (int d = 16; d >= 1; d >>= 1) gmx = fmax(gmx, __shfl_xor_sync(0xffffffffu, gmx, d));
+            if (lane == 0) { s_part[warp] = acc; s_pmax[warp] = gmx; }
             __syncthreads();
             if (CL) {  // this CTA's share of every bucket of the batch goes to all CTAs of the cluster
                 if (warp == 0 && lane < Sc) {
-                    double mine = 0.0;
-                    for (int s = 0; s < nsub; s++) mine += s_part[lane + (s << lg)];
-                    for (unsigned r = 0; r < csize; r++) st_cluster_f64(&s_cl[parity][crank][lane], r, mine);
+                    double mine = 0.0, mmax = 0.0;
+                    for (int s = 0; s < nsub; s++) { mine += s_part[lane + (s << lg)]; mmax = fmax(mmax, s_pmax[lane + (s << lg)]); }
+                    for (unsigned r = 0; r < csize; r++) { st_cluster_f64(&s_cl[parity][crank][lane], r, mine); st_cluster_f64(&s_cm[parity][crank][lane], r, mmax); }
                 }
                 cluster_sync_all();
             }
             if (warp == 0) {
                 const bool have = lane < Sc;
-                double sum = 0.0;
+                double sum = 0.0, gmax = 0.0;  // log-intensity difference of the bucket; largest change a flip of its link makes to any intensity
                 if (have) {
-                    if (CL) for (unsigned r = 0; r < csize; r++) sum += s_cl[parity][r][lane];  // fixed order: every CTA of the cluster takes the same decision
-                    else for (int s = 0; s < nsub; s++) sum += s_part[lane + (s << lg)];
+                    if (CL) for (unsigned r = 0; r < csize; r++) { sum += s_cl[parity][r][lane]; gmax = fmax(gmax, s_cm[parity][r][lane]); }  // fixed order: every CTA decides alike
+                    else for (int s = 0; s < nsub; s++) { sum += s_part[lane + (s << lg)]; gmax = fmax(gmax, s_pmax[lane + (s << lg)]); }
                 }
                 const int qq = p + lane;
                 const bool old_on = have && ((s_ab[qq >> 5] >> (qq & 31)) & 1u);
                 // ll1 - ll0 (continuous.jl:477-483): integrated-intensity difference, log-intensity difference, prior
-                const double delta = -d_w * d_mn + sum + (log(d_rho) - log(1.0 - d_rho));
+                const double delta = -d_w * d_mn + sum + d_lrho;
                 double p1 = delta >= 0.0 ? 1.0 / (1.0 + exp(-delta)) : exp(delta) / (1.0 + exp(delta));
                 if (have && delta != delta) { atomicOr(a.flag, 64); p1 = 0.0; }
                 const bool new_on = d_u <= p1;  // rand(Bernoulli(p)) = rand() <= p
                 const unsigned flipmask = __ballot_sync(0xffffffffu, have && new_on != old_on);
-                const int first = flipmask ? __ffs(flipmask) - 1 : Sc;
-                if (lane == 0) s_first = first;
-                if (lane == first && have) {
+                // Certified speculation.  The sums of this batch were taken with the intensities as they stood at its start.  A flip of
+                // bucket j moves every intensity by at most gmax_j, and a term log((b + g) / b) of a later bucket moves by at most
+                // 4 term dlam / lambda0 while dlam <= lambda0 / 2 (d term / d b = -(g / (b + g)) / b, g / (b + g) <= term, b >= lambda0; the
+                // factor 4 covers a decreasing b), so a later sum S moves by at most 4 S cum / lambda0, cum = the gmax of the flips so far.
+                // A decision whose margin |delta - logit(u)| exceeds that bound (plus rounding slack) is the decision the sequential sweep
+                // takes; the batch is accepted up to the first bucket that cannot be certified, and restarts there.
+                const double margin = fabs(delta - d_lu), slack = 1e-7 + 1e-10 * fabs(delta);
+                const double inv_l0 = 4.0 / lam0;
+                double cum = 0.0;
+                int stop = Sc;
+                unsigned acc_mask = 0u;
+                for (int j = 0; j < Sc; j++) {  // the same values in every lane (and every CTA of the cluster)
+                    const double Sj = fabs(__shfl_sync(0xffffffffu, sum, j)), mj = __shfl_sync(0xffffffffu, margin, j);
+                    const double gj = __shfl_sync(0xffffffffu, gmax, j), sj = __shfl_sync(0xffffffffu, slack, j);
+                    if (cum > 0.0 && !(mj > Sj * cum * inv_l0 + sj)) { stop = j; break; }
+                    if ((flipmask >> j) & 1u) {
+                        acc_mask |= 1u << j;
+                        if (!(gj <= 0.5 * lam0)) { stop = j + 1; break; }  // too large a change to bound: nothing behind it is certified
+                        cum += gj;
+                    }
+                }
+                if (lane == 0) { s_first = stop; s_mask = acc_mask; }
+                const unsigned onmask = __ballot_sync(0xffffffffu, new_on);
+                if (lane == 0) s_onmask = onmask;
+                if (have && ((acc_mask >> lane) & 1u)) {
                     if (crank == 0) Acol[qq] = new_on ? 1.0 : 0.0;
-                    s_sgn = new_on ? 1.0 : -1.0;
-                    s_ab[qq >> 5] ^= 1u << (qq & 31);
+                    atomicXor(&s_ab[qq >> 5], 1u << (qq & 31));
                 }
             }
             __syncthreads();
             parity ^= 1u;
-            const int first = s_first;
+            const int stop = s_first;
+            unsigned fm = s_mask;
+            const unsigned onm = s_onmask;
             n_batches++;
-            if (first < Sc) {
-                // the link of bucket qf flipped: move its contribution into / out of the intensities, restart behind it
-                const int qf = p + first;
-                const double sgn = s_sgn;
+            n_steps += stop; n_flips += __popc(fm); n_redo += Sc - stop;
+            while (fm) {
+                // the link of bucket qf flipped: move its contribution into / out of the intensities
+                const int j = __ffs(fm) - 1;
+                fm &= fm - 1;
+                const int qf = p + j;
+                const double sgn = ((onm >> j) & 1u) ? 1.0 : -1.0;
                 const E enf = load_entry(col + qf);
                 for (int g = g_lo; g < g_hi; g++) {
                     const int *bo = a.boff + (int64_t)(v0 + g) * (K + 1);
@@ -617,15 +648,10 @@ template <int KIND, int PRE, bool CL> __global__ void __launch_bounds__(ADJ_THRE
                         }
                     }
                 }
-                __syncthreads();
-                n_steps += first + 1; n_flips++; n_redo += Sc - 1 - first;
-                p = qf + 1;
-                fw_steps = 0.9f * fw_steps + (float)(first + 1); fw_flips = 0.9f * fw_flips + 1.f;
-            } else {
-                n_steps += Sc;
-                p += Sc;
-                fw_steps = 0.9f * fw_steps + (float)Sc; fw_flips = 0.9f * fw_flips;
+                __syncthreads();  // the next flipped bucket may touch the same events
             }
+            p += stop;
+            fw_steps = 0.9f * fw_steps + (float)stop; fw_flips = 0.9f * fw_flips + (stop < Sc ? 1.f : 0.f);  // "flip" = a batch cut short
             {
                 const float target = 2.f * rsqrtf(fw_flips / fw_steps + 1e-3f);
                 const int l2 = min(5, max(0, __float2int_rn(__log2f(target))));
@@ -705,7 +731,7 @@ static int adj_build_structure(nhp_ctx *ctx, nhp_events *ev, double horizon, int
     int max_col = 0;
     for (int64_t c = cb; c < K; c += cs) max_col = std::max(max_col, (int)mn[c]);
     int cluster = 1;
-    while (cluster < ADJ_CLUSTER_MAX && (int64_t)cluster * chunk_cap < max_col) cluster *= 2;
+    while (cluster < ADJ_CLUSTER_MAX && (int64_t)cluster * chunk_cap < max_col) cluster++;
     if ((int64_t)cluster * chunk_cap < max_col) cluster = 0;  // too large for a cluster: single-CTA streaming form
     { const char *e = getenv("NHP_ADJ_CLUSTER"); if (e && atoi(e) == 0) cluster = 0; }
     std::vector<int> vstart(K + 1), vnode;
