@@ -224,11 +224,11 @@ __global__ void __launch_bounds__(512) k_adj_build(const AdjBuildArgs a) {
     __shared__ int s_v;
     const int K = a.K, nw = a.nw;
     int *s_off = s_dyn;                                           // [K+1] bucket offsets
-    unsigned *s_w = reinterpret_cast<unsigned *>(s_dyn + K + 1);  // per warp: cur[K], cnt[K], run[K]
+    unsigned *s_w = reinterpret_cast<unsigned *>(s_dyn + K + 1);  // per warp: cur[K] cursors, stamp[K] (last event that held the parent)
     const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
-    unsigned *cur = s_w + (size_t)wid * 3 * K, *cnt = cur + K, *run = cnt + K;
+    unsigned *cur = s_w + (size_t)wid * 2 * K, *stamp = cur + K;
     const unsigned lt = (1u << lane) - 1u;
-    for (int k = tid; k < nw * 3 * K; k += blockDim.x) s_w[k] = 0u;
+    for (int k = tid; k < nw * 2 * K; k += blockDim.x) s_w[k] = 0xffffffffu;
     for (;;) {
         __syncthreads();
         if (tid == 0) s_v = atomicAdd(a.next, 1);
@@ -259,7 +259,7 @@ __global__ void __launch_bounds__(512) k_adj_build(const AdjBuildArgs a) {
         // ---- bucket offsets; every warp's cursor starts behind the earlier warps' entries of the same parent
         for (int p = tid; p < K; p += blockDim.x) {
             unsigned r = 0;
-            for (int w = 0; w < nw; w++) { unsigned *cw = s_w + (size_t)w * 3 * K; const unsigned x = cw[p]; cw[p] = r; r += x; }
+            for (int w = 0; w < nw; w++) { unsigned *cw = s_w + (size_t)w * 2 * K; const unsigned x = cw[p]; cw[p] = r; r += x; }
             s_off[p + 1] = (int)r;
         }
         if (tid == 0) s_off[0] = 0;
@@ -272,9 +272,11 @@ __global__ void __launch_bounds__(512) k_adj_build(const AdjBuildArgs a) {
         __syncthreads();
         for (int p = tid; p <= K; p += blockDim.x) a.boff[(int64_t)v * (K + 1) + p] = s_off[p];
         for (int p = tid; p < K; p += blockDim.x)
-            for (int w = 0; w < nw; w++) s_w[(size_t)w * 3 * K + p] += (unsigned)s_off[p];
+            for (int w = 0; w < nw; w++) s_w[(size_t)w * 2 * K + p] += (unsigned)s_off[p];
         __syncthreads();
-        // ---- B: scatter
+        // ---- B: scatter, one pass over every window: an entry goes to its parent's cursor, the cursor moves on at once (the warp owns
+        //      its cursors, the rounds of a window are taken in order, so a run of one (event, parent) stays contiguous and in window
+        //      order); the stamp tells whether the parent was already seen in this event's window (continuation bit)
         unsigned short *ei = a.ent_i + a.vbase[v];
         double *ex = a.ent_x + a.vbase[v];
         double *ey = a.ent_y ? a.ent_y + a.vbase[v] : nullptr;
@@ -283,26 +285,19 @@ __global__ void __launch_bounds__(512) k_adj_build(const AdjBuildArgs a) {
             const double ti = a.t[i];
             const int wl = i - lo_of_event(a.t, i, a.horizon);
             const unsigned le = (unsigned)(e - eb);
-            for (int r0 = 0; r0 < wl; r0 += 32) {  // multiplicity of every parent node in this window
-                const int k = r0 + lane;
-                const bool valid = k < wl;
-                const int p = valid ? __ldg(a.c + (i - 1 - k)) : -1;
-                const unsigned m = __match_any_sync(0xffffffffu, p);
-                if (valid && lane == __ffs(m) - 1) cnt[p] += __popc(m);
-                __syncwarp();
-            }
-            for (int r0 = 0; r0 < wl; r0 += 32) {  // positions: the (event, parent) run is contiguous, window order inside it
+            for (int r0 = 0; r0 < wl; r0 += 32) {
                 const int k = r0 + lane;
                 const bool valid = k < wl;
                 const int p = valid ? __ldg(a.c + (i - 1 - k)) : -1;
                 const unsigned m = __match_any_sync(0xffffffffu, p);
                 const unsigned rank = __popc(m & lt);
-                const unsigned seen = valid ? run[p] : 0u;
+                unsigned pos = 0u;
+                bool seen = false;
+                if (valid) { pos = cur[p] + rank; seen = stamp[p] == (unsigned)e; }
                 __syncwarp();
                 if (valid) {
-                    const unsigned pos = cur[p] + seen + rank;
                     const double dt = ti - __ldg(a.t + (i - 1 - k));
-                    ei[pos] = (unsigned short)(le | ((seen + rank) ? 0x8000u : 0u));
+                    ei[pos] = (unsigned short)(le | ((seen || rank) ? 0x8000u : 0u));
                     if (ey) {
                         const double b = a.D - dt;
                         double z = 0.0, q = 0.0;
@@ -313,16 +308,8 @@ __global__ void __launch_bounds__(512) k_adj_build(const AdjBuildArgs a) {
                         }
                         ex[pos] = z; ey[pos] = q;
                     } else ex[pos] = dt;
-                    if (lane == __ffs(m) - 1) run[p] = seen + __popc(m);
+                    if (lane == __ffs(m) - 1) { cur[p] += __popc(m); stamp[p] = (unsigned)e; }
                 }
-                __syncwarp();
-            }
-            for (int r0 = 0; r0 < wl; r0 += 32) {  // advance the cursors, clear the per-event counters
-                const int k = r0 + lane;
-                const bool valid = k < wl;
-                const int p = valid ? __ldg(a.c + (i - 1 - k)) : -1;
-                const unsigned m = __match_any_sync(0xffffffffu, p);
-                if (valid && lane == __ffs(m) - 1 && cnt[p]) { cur[p] += cnt[p]; cnt[p] = 0u; run[p] = 0u; }
                 __syncwarp();
             }
         }
@@ -780,8 +767,8 @@ static int adj_build_structure(nhp_ctx *ctx, nhp_events *ev, double horizon, int
     bool pre = ctx->kind == NHP_LOGITNORMAL && (double)tot * 18.0 + (double)fixed <= 0.72 * (double)free_b;
     { const char *e = getenv("NHP_ADJ_PRE"); if (e) pre = pre && atoi(e) != 0; }
     const size_t need = (size_t)tot * (pre ? 18 : 10) + fixed;
-    // build kernel: [K+1] offsets + per warp 3 K counters
-    int nw = (int)std::min<int64_t>(16, ((int64_t)ctx->smem_optin - 2048 - (K + 1) * 4) / (12 * K));
+    // build kernel: [K+1] offsets + per warp 2 K words (cursors, stamps)
+    int nw = (int)std::min<int64_t>(16, ((int64_t)ctx->smem_optin - 2048 - (K + 1) * 4) / (8 * K));
     if ((double)need > 0.75 * (double)free_b || nw < 1) return drop(1);
     cudaFree(d_vcount); d_vcount = nullptr;
     ev->d_adj_vstart = d_vstart; ev->d_adj_vnode = d_vnode; d_vstart = d_vnode = nullptr;  // owned by the handle from here on
@@ -800,7 +787,7 @@ static int adj_build_structure(nhp_ctx *ctx, nhp_events *ev, double horizon, int
     b.vstart = ev->d_adj_vstart; b.vnode = ev->d_adj_vnode; b.vbase = ev->d_adj_vbase; b.boff = ev->d_adj_boff; b.ent_i = ev->d_adj_i; b.ent_x = ev->d_adj_dt;
     b.ent_y = pre ? ev->d_adj_q : nullptr;
     b.nv = (int)nv; b.nw = nw; b.next = ctx->d_adj_ctl; b.flag = ctx->d_flag;
-    const size_t bsmem = (size_t)(K + 1) * sizeof(int) + (size_t)nw * 3 * K * sizeof(unsigned);
+    const size_t bsmem = (size_t)(K + 1) * sizeof(int) + (size_t)nw * 2 * K * sizeof(unsigned);
     ADJ_S(cudaFuncSetAttribute(k_adj_build, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)std::max<size_t>(bsmem, 1024)));
     int per_sm = 1;
     ADJ_S(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_adj_build, nw * 32, bsmem));
