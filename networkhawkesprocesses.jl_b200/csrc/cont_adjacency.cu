@@ -191,9 +191,10 @@ constexpr int ADJ_CLUSTER_MAX = 8;     // portable cluster size limit
 // a column's ne child events are split into G chunks of this many events (the last one may be shorter)
 __host__ __device__ inline int adj_chunk_size(int ne, int G) { return G > 0 ? (ne + G - 1) / G : 0; }
 
-// entries per virtual column: every child event adds its window length
+// entries per virtual column: every child event adds its window length; the window start of every owned event is kept for the build
 __global__ void k_adj_count(const double *__restrict__ t, const int *__restrict__ c, const int *__restrict__ order, const int *__restrict__ node_ptr,
-                            const int *__restrict__ vstart, int64_t n_own, double horizon, int cb, int cs, unsigned long long *__restrict__ vcount) {
+                            const int *__restrict__ vstart, int64_t n_own, double horizon, int cb, int cs, unsigned long long *__restrict__ vcount,
+                            int *__restrict__ lo_out, int *__restrict__ max_win) {
     const int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (e >= n_own) return;
     const int i = order[e], col = c[i];
@@ -201,21 +202,42 @@ __global__ void k_adj_count(const double *__restrict__ t, const int *__restrict_
     const int le = (int)(e - node_ptr[col]), ne = node_ptr[col + 1] - node_ptr[col], G = vstart[col + 1] - vstart[col];
     const int v = vstart[col] + le / adj_chunk_size(ne, G);
     const int lo = lo_of_event(t, i, horizon);
-    if (i > lo) atomicAdd(&vcount[v], (unsigned long long)(i - lo));
+    if (lo_out) lo_out[i] = lo;
+    if (i > lo) {
+        atomicAdd(&vcount[v], (unsigned long long)(i - lo));
+        if (max_win) atomicMax(max_win, i - lo);
+    }
+}
+
+// Per event: node | distance to the previous event of the same node | distance to the next one (22 bits each, saturated).  With it
+// the build knows, from the predecessor alone, whether a window holds the predecessor's node more than once.
+constexpr int ADJ_LINK_BITS = 22, ADJ_NODE_BITS = 20;
+constexpr unsigned ADJ_LINK_SAT = (1u << ADJ_LINK_BITS) - 1u;
+__global__ void k_adj_links(const int *__restrict__ order, const int *__restrict__ node_ptr, const int *__restrict__ c, int64_t n,
+                            unsigned long long *__restrict__ pk) {
+    const int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (e >= n) return;
+    const int i = order[e], col = c[i];
+    unsigned dp = ADJ_LINK_SAT, dn = ADJ_LINK_SAT;
+    if (e > node_ptr[col]) dp = min(ADJ_LINK_SAT, (unsigned)(i - order[e - 1]));
+    if (e + 1 < node_ptr[col + 1]) dn = min(ADJ_LINK_SAT, (unsigned)(order[e + 1] - i));
+    pk[i] = (unsigned long long)(unsigned)col | ((unsigned long long)dp << ADJ_NODE_BITS) | ((unsigned long long)dn << (ADJ_NODE_BITS + ADJ_LINK_BITS));
 }
 
 struct AdjBuildArgs {
-    const double *t; const int *c; const int *order, *node_ptr;
-    int K; double horizon, D;
+    const double *t; const unsigned long long *pk; const int *lo; const int *order, *node_ptr;
+    int K; double D;
     const int *vstart, *vnode; const int64_t *vbase;
     int *boff; unsigned short *ent_i; double *ent_x, *ent_y;   // ent_y != NULL: LogitNormal payload (logit, Jacobian) instead of the lag
     int nv, nw;      // virtual columns; warps per CTA
     int *next, *flag;
 };
 
-// Stable counting sort of one virtual column's (child event, window predecessor) pairs by parent node.  Warp w owns a contiguous
-// range of the chunk's events and private per-parent cursors, so a bucket is ordered by (event, window position) whatever the
-// scheduling; entries of one (event, parent) are adjacent and all but the first carry the continuation bit.
+// Stable counting sort of one virtual column's (child event, window predecessor) pairs by parent node.  A parent's bucket has two
+// sections: first the SINGLES -- pairs whose (event, parent) occurs once in the event's window (94 % at config 4), which a sweep
+// streams with no bookkeeping at all -- then the RUNS: the entries of one (event, parent) next to each other in window order, all but
+// the first carrying the continuation bit.  Warp w owns a contiguous range of the chunk's events and private per-parent cursors, so
+// both sections are ordered by (event, window position) whatever the scheduling.
 // Payload per entry: the lag t_i - t_j, or -- LogitNormal, when memory allows -- what the impulse needs of it and what does not
 // depend on the parameters: z = logit(dt / D) and q = 1 / (dt (D - dt)), so that a sweep evaluates one exp per pair instead of
 // a log, a reciprocal and an exp (pairs outside the support get q = 0).
@@ -223,12 +245,12 @@ __global__ void __launch_bounds__(512) k_adj_build(const AdjBuildArgs a) {
     extern __shared__ int s_dyn[];
     __shared__ int s_v;
     const int K = a.K, nw = a.nw;
-    int *s_off = s_dyn;                                           // [K+1] bucket offsets
-    unsigned *s_w = reinterpret_cast<unsigned *>(s_dyn + K + 1);  // per warp: cur[K] cursors, stamp[K] (last event that held the parent)
+    int *s_off = s_dyn;                                               // [2K+1] section offsets: singles of p, runs of p, ...
+    unsigned *s_w = reinterpret_cast<unsigned *>(s_dyn + 2 * K + 1);  // per warp: curS[K], curM[K]
     const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
-    unsigned *cur = s_w + (size_t)wid * 2 * K, *stamp = cur + K;
+    unsigned *curS = s_w + (size_t)wid * 2 * K, *curM = curS + K;
     const unsigned lt = (1u << lane) - 1u;
-    for (int k = tid; k < nw * 2 * K; k += blockDim.x) s_w[k] = 0xffffffffu;
+    const unsigned nmask = (1u << ADJ_NODE_BITS) - 1u;
     for (;;) {
         __syncthreads();
         if (tid == 0) s_v = atomicAdd(a.next, 1);
@@ -240,87 +262,129 @@ __global__ void __launch_bounds__(512) k_adj_build(const AdjBuildArgs a) {
         const int eb = a.node_ptr[col] + g * csz, ee = min(a.node_ptr[col] + ne, eb + csz);  // positions in the by-node order
         const int per = (max(ee - eb, 0) + nw - 1) / nw;
         const int ws = min(ee, eb + wid * per), we = min(ee, ws + per);
-        for (int k = lane; k < K; k += 32) cur[k] = 0u;
+        for (int k = lane; k < 2 * K; k += 32) curS[k] = 0u;
         __syncwarp();
-        // ---- A: per-(warp, parent) counts
-        for (int e = ws; e < we; e++) {
-            const int i = a.order[e];
-            const int wl = i - lo_of_event(a.t, i, a.horizon);
-            for (int r0 = 0; r0 < wl; r0 += 32) {
-                const int k = r0 + lane;
-                const bool valid = k < wl;
-                const int p = valid ? __ldg(a.c + (i - 1 - k)) : -1;
-                const unsigned m = __match_any_sync(0xffffffffu, p);
-                if (valid && lane == __ffs(m) - 1) cur[p] += __popc(m);
-                __syncwarp();
+        // ---- A: per-(warp, parent) counts of singles and of run entries
+        for (int e0 = ws; e0 < we; e0 += 32) {
+            int my_i = 0, my_lo = 0;
+            if (e0 + lane < we) { my_i = a.order[e0 + lane]; my_lo = a.lo[my_i]; }  // 32 events' headers in one round trip
+            const int cnt = min(32, we - e0);
+            for (int s = 0; s < cnt; s++) {
+                const int i = __shfl_sync(0xffffffffu, my_i, s), lo = __shfl_sync(0xffffffffu, my_lo, s);
+                for (int j = i - 1 - lane; j >= lo; j -= 32) {
+                    const unsigned long long pk = __ldg(a.pk + j);
+                    const int p = (int)((unsigned)pk & nmask);
+                    const int dp = (int)((unsigned)(pk >> ADJ_NODE_BITS) & ADJ_LINK_SAT), dn = (int)(pk >> (ADJ_NODE_BITS + ADJ_LINK_BITS));
+                    const bool multi = (j - dp >= lo) || ((int64_t)j + dn < (int64_t)i);
+                    atomicAdd(multi ? &curM[p] : &curS[p], 1u);
+                }
             }
         }
         __syncthreads();
-        // ---- bucket offsets; every warp's cursor starts behind the earlier warps' entries of the same parent
-        for (int p = tid; p < K; p += blockDim.x) {
+        // ---- section sizes; every warp's cursor starts behind the earlier warps' entries of the same section
+        for (int k = tid; k < 2 * K; k += blockDim.x) {  // k = section of warp-row layout: [0,K) singles, [K,2K) runs
             unsigned r = 0;
-            for (int w = 0; w < nw; w++) { unsigned *cw = s_w + (size_t)w * 2 * K; const unsigned x = cw[p]; cw[p] = r; r += x; }
-            s_off[p + 1] = (int)r;
+            for (int w = 0; w < nw; w++) { unsigned *cw = s_w + (size_t)w * 2 * K; const unsigned x = cw[k]; cw[k] = r; r += x; }
+            const int p = k < K ? k : k - K;
+            s_off[2 * p + (k < K ? 0 : 1) + 1] = (int)((r + 31u) & ~31u);  // every section is padded to whole groups of 32 entries
         }
         if (tid == 0) s_off[0] = 0;
         __syncthreads();
         if (tid == 0) {
             int r = 0;
-            for (int p = 0; p < K; p++) { r += s_off[p + 1]; s_off[p + 1] = r; }
-            if ((int64_t)r != a.vbase[v + 1] - a.vbase[v]) atomicOr(a.flag, 128);
+            for (int k = 0; k < 2 * K; k++) { r += s_off[k + 1]; s_off[k + 1] = r; }
+            if ((int64_t)r > a.vbase[v + 1] - a.vbase[v]) atomicOr(a.flag, 128);
         }
         __syncthreads();
-        for (int p = tid; p <= K; p += blockDim.x) a.boff[(int64_t)v * (K + 1) + p] = s_off[p];
-        for (int p = tid; p < K; p += blockDim.x)
-            for (int w = 0; w < nw; w++) s_w[(size_t)w * 2 * K + p] += (unsigned)s_off[p];
+        for (int k = tid; k <= 2 * K; k += blockDim.x) a.boff[(int64_t)v * (2 * K + 1) + k] = s_off[k];
+        for (int k = tid; k < 2 * K; k += blockDim.x) {
+            const int p = k < K ? k : k - K;
+            const unsigned o = (unsigned)s_off[2 * p + (k < K ? 0 : 1)];
+            for (int w = 0; w < nw; w++) s_w[(size_t)w * 2 * K + k] += o;
+        }
         __syncthreads();
-        // ---- B: scatter, one pass over every window: an entry goes to its parent's cursor, the cursor moves on at once (the warp owns
-        //      its cursors, the rounds of a window are taken in order, so a run of one (event, parent) stays contiguous and in window
-        //      order); the stamp tells whether the parent was already seen in this event's window (continuation bit)
+        // ---- B: scatter, one pass over every window.  A single goes to its section's cursor (no other lane of the event holds that
+        //      parent); run entries of one round are ranked among the lanes that hold the same parent, rounds are taken in order.
         unsigned short *ei = a.ent_i + a.vbase[v];
         double *ex = a.ent_x + a.vbase[v];
         double *ey = a.ent_y ? a.ent_y + a.vbase[v] : nullptr;
-        for (int e = ws; e < we; e++) {
-            const int i = a.order[e];
-            const double ti = a.t[i];
-            const int wl = i - lo_of_event(a.t, i, a.horizon);
-            const unsigned le = (unsigned)(e - eb);
-            for (int r0 = 0; r0 < wl; r0 += 32) {
-                const int k = r0 + lane;
-                const bool valid = k < wl;
-                const int p = valid ? __ldg(a.c + (i - 1 - k)) : -1;
-                const unsigned m = __match_any_sync(0xffffffffu, p);
-                const unsigned rank = __popc(m & lt);
-                unsigned pos = 0u;
-                bool seen = false;
-                if (valid) { pos = cur[p] + rank; seen = stamp[p] == (unsigned)e; }
-                __syncwarp();
-                if (valid) {
-                    const double dt = ti - __ldg(a.t + (i - 1 - k));
-                    ei[pos] = (unsigned short)(le | ((seen || rank) ? 0x8000u : 0u));
-                    if (ey) {
-                        const double b = a.D - dt;
-                        double z = 0.0, q = 0.0;
-                        if (dt > 0.0 && b > 0.0) {  // Distributions.pdf(LogitNormal, x) is zero outside 0 < x < 1 (impulses.jl:174-178)
-                            q = 1.0 / (dt * b);
-                            z = log(dt / b);
-                            if (!(q <= 1.7976931348623157e308) || !(fabs(z) <= 1.7976931348623157e308)) { z = 0.0; q = 0.0; }  // lag so small that the pdf underflows
-                        }
-                        ex[pos] = z; ey[pos] = q;
-                    } else ex[pos] = dt;
-                    if (lane == __ffs(m) - 1) { cur[p] += __popc(m); stamp[p] = (unsigned)e; }
+        for (int e0 = ws; e0 < we; e0 += 32) {
+            int my_i = 0, my_lo = 0;
+            double my_t = 0.0;
+            if (e0 + lane < we) { my_i = a.order[e0 + lane]; my_lo = a.lo[my_i]; my_t = a.t[my_i]; }
+            const int cnt = min(32, we - e0);
+            for (int s = 0; s < cnt; s++) {
+                const int i = __shfl_sync(0xffffffffu, my_i, s), lo = __shfl_sync(0xffffffffu, my_lo, s);
+                const double ti = __shfl_sync(0xffffffffu, my_t, s);
+                const unsigned le = (unsigned)(e0 + s - eb);
+                for (int j0 = i - 1; j0 >= lo; j0 -= 32) {
+                    const int j = j0 - lane;
+                    const bool valid = j >= lo;
+                    int p = -1 - lane;
+                    bool multi = false, cont = false;
+                    double dt = 0.0;
+                    if (valid) {
+                        const unsigned long long pk = __ldg(a.pk + j);
+                        p = (int)((unsigned)pk & nmask);
+                        const int dp = (int)((unsigned)(pk >> ADJ_NODE_BITS) & ADJ_LINK_SAT), dn = (int)(pk >> (ADJ_NODE_BITS + ADJ_LINK_BITS));
+                        cont = (int64_t)j + dn < (int64_t)i;  // a more recent event of the same node sits in the window: this entry continues its run
+                        multi = cont || (j - dp >= lo);
+                        dt = ti - __ldg(a.t + j);
+                    }
+                    unsigned pos = 0u;
+                    if (valid && !multi) { pos = curS[p]; curS[p] = pos + 1u; }
+                    if (__any_sync(0xffffffffu, multi)) {
+                        const unsigned m = __match_any_sync(0xffffffffu, multi ? p : -1 - lane);
+                        if (multi) pos = curM[p] + __popc(m & lt);
+                        __syncwarp();
+                        if (multi && (m & lt) == 0u) curM[p] += __popc(m);
+                    }
+                    if (valid) {
+                        ei[pos] = (unsigned short)(le | (cont ? 0x8000u : 0u));
+                        if (ey) {
+                            const double b = a.D - dt;
+                            double z = 0.0, q = 0.0;
+                            if (dt > 0.0 && b > 0.0) {  // Distributions.pdf(LogitNormal, x) is zero outside 0 < x < 1 (impulses.jl:174-178)
+                                q = 1.0 / (dt * b);
+                                z = log(dt / b);
+                                if (!(q <= 1.7976931348623157e308) || !(fabs(z) <= 1.7976931348623157e308)) { z = 0.0; q = 0.0; }  // lag so small that the pdf underflows
+                            }
+                            ex[pos] = z; ey[pos] = q;
+                        } else ex[pos] = dt;
+                    }
+                    __syncwarp();
                 }
-                __syncwarp();
+            }
+        }
+        __syncthreads();
+        // ---- padding: entries that evaluate to exactly zero (event 0, q = 0 | lag -1), so the sweeps read whole groups unconditionally
+        for (int k = tid; k < 2 * K; k += blockDim.x) {
+            const int p = k < K ? k : k - K;
+            const int end = s_off[2 * p + (k < K ? 0 : 1) + 1];
+            for (int e = (int)s_w[(size_t)(nw - 1) * 2 * K + k]; e < end; e++) {  // the last warp's cursor is the section's true end
+                ei[e] = 0;
+                if (ey) { ex[e] = 0.0; ey[e] = 0.0; } else ex[e] = -1.0;
             }
         }
     }
 }
 
+// Inputs of the K^2 Bernoulli decisions, computed ahead of the sweep so that the deciding lanes only load them:
+// ll1 - ll0 = -W[p,c] Mn[p] + (log-intensity difference) + logit(rho)  (continuous.jl:477-483), the uniform and its logit
+__global__ void k_adj_prep(int K, const double *__restrict__ W, const double *__restrict__ Mn, const double *__restrict__ rho, double rho_scalar,
+                           const double *__restrict__ u, uint64_t seed, uint64_t counter, double4 *__restrict__ dec) {
+    const int64_t kk = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (kk >= (int64_t)K * K) return;
+    const double r = rho ? rho[kk] : rho_scalar;
+    const double uu = u ? u[kk] : philox_uniform(seed, (uint64_t)kk, counter);
+    dec[kk] = make_double4(W[kk] * Mn[kk % K], log(r) - log(1.0 - r), uu, log(uu) - log(1.0 - uu));
+}
+
 struct AdjSweepArgs {
-    const int *node_ptr; const double *Mn;
+    const int *node_ptr;
     int K; const void *table_w;
-    const double *lambda0; const double *W; double *A;   // A: [K*K] parent-major, device, updated in place
-    const double *rho; double rho_scalar; const double *u; uint64_t seed, counter;
+    const double *lambda0; double *A;   // A: [K*K] parent-major, device, updated in place
+    const double4 *dec;    // [K*K] per link: W Mn[p], logit(rho), u, logit(u)  (k_adj_prep)
     double D;
     const int *vstart; const int64_t *vbase; const int *boff; const unsigned short *ent_i; const double *ent_x, *ent_y;
     double *lam;           // [n] by-node order (only used when a column's chunks do not all sit in shared memory)
@@ -353,7 +417,7 @@ template <> __device__ __forceinline__ double adj_value<NHP_LOGITNORMAL, 1>(cons
     return (en.cf * y) * fast_exp_c(-(en.h * dz) * dz, ft);  // exponent <= 0: no overflow branch; flushes to 0 below -707
 }
 
-// One group of 32 consecutive entries [eb, eb + 32) of a bucket that ends at b1, one entry per lane: the impulse value of
+// One group of 32 consecutive entries [eb, eb + 32) of a run section that ends at b1, one entry per lane: the impulse value of
 // every entry and, for the first entry of each (event, parent) run (the "head"), the run's total.  Returns head.
 template <int KIND, int PRE>
 __device__ __forceinline__ bool adj_group(const typename EntryOf<KIND>::type &en, const unsigned short *__restrict__ ei, const double *__restrict__ ex,
@@ -375,7 +439,7 @@ __device__ __forceinline__ bool adj_group(const typename EntryOf<KIND>::type &en
             if (d <= runlen) gsum += vv;
         }
     }
-    if (eb + 32 < b1) {  // warp-uniform: does the run that reaches lane 31 go on in the bucket's next group?  (one broadcast load)
+    if (eb + 32 < b1) {  // warp-uniform: does the run that reaches lane 31 go on in the section's next group?  (one broadcast load)
         if (__ldg(ei + eb + 32) & 0x8000u) {
             if (head && lane + runlen == 31)
                 for (int e2 = eb + 32; e2 < b1 && (__ldg(ei + e2) & 0x8000u); e2++) gsum += adj_value<KIND, PRE>(en, __ldg(ex + e2), PRE ? __ldg(ey + e2) : 0.0, D, ft);
@@ -384,8 +448,157 @@ __device__ __forceinline__ bool adj_group(const typename EntryOf<KIND>::type &en
     return head;
 }
 
-__device__ __forceinline__ bool below_2p500(double x) { return __double2hiint(x) < 0x5F300000; }   // 0 < x < 2^500
-__device__ __forceinline__ bool above_2m500(double x) { return __double2hiint(x) >= 0x20B00000; }  // x >= 2^-500 (x > 0)
+// The log terms log((base + g) / base) of a bucket are accumulated as a quotient of running products -- one pair of logs per lane and
+// bucket instead of one log per entry.  The exponents are taken out of the products every ADJ_RENORM factors (integer work); the
+// smallest base and the largest base + g are tracked through their high words, and a bucket whose factors leave [2^-100, 2^100]
+// (which the products could not hold) is redone with direct logs (adj_direct).
+constexpr int ADJ_RENORM = 8;
+struct AdjAcc {
+    double num, den;  // running products of (base + g) and of base, both in [2^-801, 2^801)
+    int bal;          // binary exponents taken out so far: log ratio = log(num) - log(den) + bal ln 2
+    int mn, mx, gm;   // high words of the smallest base, the largest base + g, the largest g
+};
+__device__ __forceinline__ void acc_init(AdjAcc &A) { A.num = 1.0; A.den = 1.0; A.bal = 0; A.mn = 0x7fffffff; A.mx = 0; A.gm = 0; }
+__device__ __forceinline__ void acc_renorm(AdjAcc &A) {
+    const int hn = __double2hiint(A.num), hd = __double2hiint(A.den);
+    const int en = (hn >> 20) - 1023, ed = (hd >> 20) - 1023;
+    A.num = __hiloint2double(hn - (en << 20), __double2loint(A.num));
+    A.den = __hiloint2double(hd - (ed << 20), __double2loint(A.den));
+    A.bal += en - ed;
+}
+__device__ __forceinline__ bool acc_in_range(const AdjAcc &A) { return A.mn >= 0x39B00000 && A.mx < 0x46300000; }  // 2^-100 <= base, base + g < 2^100
+__device__ __forceinline__ void acc_factor(AdjAcc &A, double v, double l, double onf, double floor_) {
+    const double t = fma(-onf, v, l);                 // intensity without this parent (link on: l - g; off: l)
+    const double base = t > floor_ ? t : floor_;      // link on: at least lambda0; off: floor = -inf
+    const double hi = base + v;
+    A.num *= hi; A.den *= base;
+    A.mn = min(A.mn, __double2hiint(base)); A.mx = max(A.mx, __double2hiint(hi)); A.gm = max(A.gm, __double2hiint(v));
+}
+
+__device__ __forceinline__ void acc_factor2(AdjAcc &A, double v0, double l0, double v1, double l1, double onf, double floor_) {
+    const double t0 = fma(-onf, v0, l0), t1 = fma(-onf, v1, l1);
+    const double b0 = t0 > floor_ ? t0 : floor_, b1 = t1 > floor_ ? t1 : floor_;
+    const double h0 = b0 + v0, h1 = b1 + v1;
+    A.num *= h0 * h1; A.den *= b0 * b1;
+    A.mn = min(A.mn, min(__double2hiint(b0), __double2hiint(b1)));
+    A.mx = max(A.mx, max(__double2hiint(h0), __double2hiint(h1)));
+    A.gm = max(A.gm, max(__double2hiint(v0), __double2hiint(v1)));
+}
+
+// singles of one bucket: this warp takes the blocks of 64 entries that start at gb, gb + stride, ... below s1 (sections are whole groups
+// of 32 entries, 32-entry aligned: a lane reads entries 2 lane, 2 lane + 1 of its block with one 32-bit and two 128-bit loads; the last
+// block may be half a block); one block ahead in flight.  Padding entries evaluate to zero and contribute the factor 1.
+// L2 prefetch of the 64-entry block that starts at entry kb: lanes 0-1 take the two 64-byte halves of the indices, lanes 2-9 / 10-17 the
+// 64-byte pieces of the two payload arrays (one instruction per block; the arrays carry slack behind their last entry)
+struct AdjPf { const char *base; int scale; };
+__device__ __forceinline__ AdjPf adj_pf_setup(const unsigned short *ei, const double *ex, const double *ey, int lane) {
+    AdjPf f;
+    f.base = nullptr; f.scale = 0;
+    if (lane < 2) { f.base = reinterpret_cast<const char *>(ei) + lane * 64; f.scale = 2; }
+    else if (lane < 10) { f.base = reinterpret_cast<const char *>(ex) + (lane - 2) * 64; f.scale = 8; }
+    else if (lane < 18 && ey) { f.base = reinterpret_cast<const char *>(ey) + (lane - 10) * 64; f.scale = 8; }
+    return f;
+}
+__device__ __forceinline__ void adj_pf(const AdjPf &f, int kb) {
+    if (f.base) asm volatile("prefetch.global.L2 [%0];" ::"l"(f.base + (int64_t)kb * f.scale));
+}
+
+template <int KIND, int PRE>
+__device__ __forceinline__ void adj_singles(const typename EntryOf<KIND>::type &en, const unsigned short *__restrict__ ei, const double *__restrict__ ex,
+                                            const double *__restrict__ ey, int gb, const int s1, const int stride, const int lane, const double onf,
+                                            const double floor_, const double D, const double *lam_s, const FastTables *ft, const AdjPf &pf, AdjAcc &A) {
+    const double xdef = PRE ? 0.0 : -1.0;
+    adj_pf(pf, gb + stride); adj_pf(pf, gb + 2 * stride);
+    int k = gb + 2 * lane;
+    unsigned iw = 0u;
+    double2 xw = make_double2(xdef, xdef), yw = make_double2(0.0, 0.0);
+    if (k < s1) {
+        iw = __ldg(reinterpret_cast<const unsigned *>(ei + k)); xw = __ldg(reinterpret_cast<const double2 *>(ex + k));
+        if (PRE) yw = __ldg(reinterpret_cast<const double2 *>(ey + k));
+    }
+    while (gb < s1) {
+#pragma unroll 1
+        for (int u = 0; u < ADJ_RENORM / 2; u++) {
+            const unsigned ii = iw;
+            const double2 x = xw, y = yw;
+            adj_pf(pf, gb + 3 * stride);  // in L2 by the time the register load two blocks later asks for it
+            k += stride;
+            iw = 0u; xw = make_double2(xdef, xdef); yw = make_double2(0.0, 0.0);
+            if (k < s1) {
+                iw = __ldg(reinterpret_cast<const unsigned *>(ei + k)); xw = __ldg(reinterpret_cast<const double2 *>(ex + k));
+                if (PRE) yw = __ldg(reinterpret_cast<const double2 *>(ey + k));
+            }
+            const double v0 = adj_value<KIND, PRE>(en, x.x, y.x, D, ft), v1 = adj_value<KIND, PRE>(en, x.y, y.y, D, ft);
+            acc_factor2(A, v0, lam_s[ii & 0xffffu], v1, lam_s[ii >> 16], onf, floor_);
+            gb += stride;
+            if (gb >= s1) break;
+        }
+        acc_renorm(A);
+    }
+}
+
+// run section of one bucket (general form: several entries of one (event, parent))
+template <int KIND, int PRE>
+__device__ __forceinline__ void adj_runs(const typename EntryOf<KIND>::type &en, const unsigned short *__restrict__ ei, const double *__restrict__ ex,
+                                         const double *__restrict__ ey, int eb, const int b1, const int stride, const int lane, const double onf,
+                                         const double floor_, const double D, const double *lam_s, const FastTables *ft, AdjAcc &A) {
+    const double xdef = PRE ? 0.0 : -1.0;
+    while (eb < b1) {
+#pragma unroll 1
+        for (int u = 0; u < ADJ_RENORM; u++) {
+            const bool valid = eb + lane < b1;
+            const unsigned ii = valid ? (unsigned)__ldg(ei + eb + lane) : 0u;
+            const double x = valid ? __ldg(ex + eb + lane) : xdef, y = (PRE && valid) ? __ldg(ey + eb + lane) : 0.0;
+            double gs;
+            const bool head = adj_group<KIND, PRE>(en, ei, ex, ey, eb, b1, lane, ii, x, y, D, ft, gs);
+            acc_factor(A, head ? gs : 0.0, lam_s[ii & 0x7fffu], onf, floor_);
+            eb += stride;
+            if (eb >= b1) break;
+        }
+        acc_renorm(A);
+    }
+}
+
+// direct route (rare): the same share of a bucket -- groups eb, eb + stride, ... of [.., b1), singles and runs alike, a single is a
+// run of one -- with one log per event; extreme or non-positive intensities end up here and a NaN surfaces as NHP_ERR_NUMERIC
+template <int KIND, int PRE>
+__device__ __noinline__ double2 adj_direct(const typename EntryOf<KIND>::type en, const unsigned short *__restrict__ ei, const double *__restrict__ ex,
+                                           const double *__restrict__ ey, int eb, const int b1, const int stride, const int lane, const double onf,
+                                           const double floor_, const double D, const double *lam_s, const FastTables *ft) {  // (sum of log terms, largest contribution)
+    const double xdef = PRE ? 0.0 : -1.0;
+    double acc = 0.0, gmx = 0.0;
+    for (; eb < b1; eb += stride) {
+        const bool valid = eb + lane < b1;
+        const unsigned ii = valid ? (unsigned)__ldg(ei + eb + lane) : 0u;
+        const double x = valid ? __ldg(ex + eb + lane) : xdef, y = (PRE && valid) ? __ldg(ey + eb + lane) : 0.0;
+        double gs;
+        if (adj_group<KIND, PRE>(en, ei, ex, ey, eb, b1, lane, ii, x, y, D, ft, gs) && gs > 0.0) {
+            const double l = lam_s[ii & 0x7fffu], t = fma(-onf, gs, l), base = t > floor_ ? t : floor_;
+            acc += log((base + gs) / base);
+            gmx = fmax(gmx, gs);
+        }
+    }
+    return make_double2(acc, gmx);
+}
+
+// add sgn * (this parent's contribution) to the intensities of a bucket's events: all warps of the CTA, groups warp, warp + 32, ...
+template <int KIND, int PRE>
+__device__ __forceinline__ void adj_apply(const typename EntryOf<KIND>::type &en, const unsigned short *__restrict__ ei, const double *__restrict__ ex,
+                                          const double *__restrict__ ey, const int s0, const int sm, const int s1, const int warp, const int lane,
+                                          const double sgn, double *lam, const double D, const FastTables *ft) {
+    for (int k = s0 + warp * 32 + lane; k < sm; k += ADJ_THREADS) {  // singles: distinct events, no bookkeeping
+        const unsigned ii = __ldg(ei + k);
+        const double v = adj_value<KIND, PRE>(en, __ldg(ex + k), PRE ? __ldg(ey + k) : 0.0, D, ft);
+        if (v > 0.0) lam[ii] += sgn * v;
+    }
+    for (int eb = sm + warp * 32; eb < s1; eb += ADJ_THREADS) {      // runs: the head carries the run's total
+        const bool valid = eb + lane < s1;
+        const unsigned ii = valid ? (unsigned)__ldg(ei + eb + lane) : 0u;
+        const double x = valid ? __ldg(ex + eb + lane) : (PRE ? 0.0 : -1.0), y = (PRE && valid) ? __ldg(ey + eb + lane) : 0.0;
+        double gs;
+        if (adj_group<KIND, PRE>(en, ei, ex, ey, eb, s1, lane, ii, x, y, D, ft, gs) && gs > 0.0) lam[ii & 0x7fffu] += sgn * gs;
+    }
+}
 
 // CL: the CTAs of a thread-block cluster share a column -- CTA r keeps chunk r's intensities in its shared memory for the whole column,
 // partial sums are exchanged through distributed shared memory, one cluster barrier per batch.  Without CL a single CTA owns the
@@ -401,7 +614,7 @@ template <int KIND, int PRE, bool CL> __global__ void __launch_bounds__(ADJ_THRE
     fast_tables_load(&s_ft);
     const FastTables *ft = &s_ft;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const int K = a.K;
+    const int K = a.K, brow = 2 * K + 1;
     unsigned *s_ab = reinterpret_cast<unsigned *>(lam_s + a.chunk_max);  // [(K + 31) / 32]
     const int abw = (K + 31) >> 5;
     const unsigned crank = CL ? cluster_ctarank() : 0u, csize = CL ? cluster_nctarank() : 1u;
@@ -442,27 +655,45 @@ template <int KIND, int PRE, bool CL> __global__ void __launch_bounds__(ADJ_THRE
             const int len = max(0, min(csz, ne - g * csz));
             for (int e = tid; e < len; e += ADJ_THREADS) lam_s[e] = lam0;
             __syncthreads();
-            const int *bo = a.boff + (int64_t)(v0 + g) * (K + 1);
+            const int *bo = a.boff + (int64_t)(v0 + g) * brow;
             const int64_t vb = a.vbase[v0 + g];
             const unsigned short *ei = a.ent_i + vb;
             const double *ex = a.ent_x + vb, *ey = PRE ? a.ent_y + vb : nullptr;
-            for (int w = 0; w < abw; w++) {
-                unsigned bits = s_ab[w];
-                while (bits) {  // block-uniform
-                    const int p = w * 32 + __ffs(bits) - 1;
-                    bits &= bits - 1;
-                    const int b0 = bo[p], b1 = bo[p + 1];
-                    if (b1 == b0) continue;
-                    const E en = load_entry(col + p);
-                    for (int eb = b0 + warp * 32; eb < b1; eb += ADJ_THREADS) {
-                        const bool valid = eb + lane < b1;
-                        const unsigned ii = valid ? (unsigned)__ldg(ei + eb + lane) : 0u;
-                        const double x = valid ? __ldg(ex + eb + lane) : 1.0, y = (PRE && valid) ? __ldg(ey + eb + lane) : 0.0;
-                        double gs;
-                        if (adj_group<KIND, PRE>(en, ei, ex, ey, eb, b1, lane, ii, x, y, a.D, ft, gs) && gs > 0.0) lam_s[ii & 0x7fffu] += gs;  // one head per event and bucket
+            // the links that are on, listed (the exchange buffers are idle here) so that the bucket two links ahead can be pulled into L2
+            // (the half the peers do not write before the next cluster barrier: they fill [parity] at the end of their first batch)
+            int *s_on = reinterpret_cast<int *>(&s_cl[parity ^ 1u][0][0]);
+            constexpr int ON_CAP = (int)(sizeof(s_cl) / 2 / sizeof(int));
+            for (int w0 = 0; w0 < abw;) {
+                int non = 0, w1 = w0;
+                for (; w1 < abw && non + __popc(s_ab[w1]) <= ON_CAP; w1++) non += __popc(s_ab[w1]);  // block-uniform
+                if (tid < w1 - w0) {
+                    int o = 0;
+                    for (int w = w0; w < w0 + tid; w++) o += __popc(s_ab[w]);
+                    for (unsigned bits = s_ab[w0 + tid]; bits; bits &= bits - 1) s_on[o++] = (w0 + tid) * 32 + __ffs(bits) - 1;
+                }
+                __syncthreads();
+                for (int j = 0; j < non; j++) {
+                    if (j + 2 < non || j == 0) {
+                        const int pn = s_on[min(j + 2, non - 1)], pa = j == 0 ? s_on[min(1, non - 1)] : pn;
+                        for (int r = 0; r < (j == 0 ? 2 : 1); r++) {
+                            const int pp = r == 0 ? pn : pa;
+                            const int f0 = bo[2 * pp], f1 = bo[2 * pp + 2];
+                            for (int e = f0 + tid * 16; e < f1; e += ADJ_THREADS * 16) {  // 16 entries = one 128-byte line of an f64 payload
+                                asm volatile("prefetch.global.L2 [%0];" ::"l"(ex + e));
+                                if (PRE) asm volatile("prefetch.global.L2 [%0];" ::"l"(ey + e));
+                                if ((e & 63) == (f0 & 63)) asm volatile("prefetch.global.L2 [%0];" ::"l"(ei + e));
+                            }
+                        }
+                    }
+                    const int p = s_on[j];
+                    const int b0 = bo[2 * p], bm = bo[2 * p + 1], b1 = bo[2 * p + 2];
+                    if (b1 != b0) {
+                        const E en = load_entry(col + p);
+                        adj_apply<KIND, PRE>(en, ei, ex, ey, b0, bm, b1, warp, lane, 1.0, lam_s, a.D, ft);  // one head per event and bucket
                     }
                     __syncthreads();  // the next parent may touch the same events
                 }
+                w0 = w1;
             }
             if (!resident) {
                 for (int e = tid; e < len; e += ADJ_THREADS) lamg[(size_t)g * csz + e] = lam_s[e];
@@ -478,32 +709,29 @@ template <int KIND, int PRE, bool CL> __global__ void __launch_bounds__(ADJ_THRE
             const int q = p + qi;
             const bool act = qi < Sc;
             // the deciding lanes fetch their inputs before the batch so that the latency hides behind it
-            double d_w = 0.0, d_mn = 0.0, d_lrho = 0.0, d_u = 2.0, d_lu = 0.0;
+            double d_wmn = 0.0, d_lrho = 0.0, d_u = 2.0, d_lu = 0.0;  // logit(u): delta - logit(u) is the margin by which the decision u <= sigmoid(delta) holds
             if (warp == 0 && lane < Sc) {
-                const int64_t kk = (p + lane) + (int64_t)K * c;
-                d_w = a.W[kk]; d_mn = a.Mn[p + lane];
-                const double rho = a.rho ? a.rho[kk] : a.rho_scalar;
-                d_lrho = log(rho) - log(1.0 - rho);
-                d_u = a.u ? a.u[kk] : philox_uniform(a.seed, (uint64_t)kk, a.counter);
-                d_lu = log(d_u) - log(1.0 - d_u);  // logit(u): delta - logit(u) is the margin by which the decision u <= sigmoid(delta) holds
+                const double *dp = reinterpret_cast<const double *>(a.dec + ((p + lane) + (int64_t)K * c));
+                asm("ld.global.nc.v4.f64 {%0,%1,%2,%3}, [%4];" : "=d"(d_wmn), "=d"(d_lrho), "=d"(d_u), "=d"(d_lu) : "l"(dp));
             }
             E en = E();
             bool on = false;
             if (act) { en = load_entry(col + q); on = (s_ab[q >> 5] >> (q & 31)) & 1u; }
+            const double onf = on ? 1.0 : 0.0, floor_ = on ? lam0 : -__longlong_as_double(0x7ff0000000000000LL);
             if (S <= 4 && resident) {
                 // short batches are latency bound: pull the entries of the buckets that can come next (they follow in memory) into L2 now
                 const int g = g_lo;
-                const int *bo = a.boff + (int64_t)(v0 + g) * (K + 1);
+                const int *bo = a.boff + (int64_t)(v0 + g) * brow;
                 const int q0 = min(p + Sc, K), q1 = min(p + Sc + 2 * S + 2, K);
                 const int64_t vb = a.vbase[v0 + g];
-                const int f0 = bo[q0], f1 = bo[q1];
+                const int f0 = bo[2 * q0], f1 = bo[2 * q1];
                 for (int e = f0 + tid * 16; e < f1; e += ADJ_THREADS * 16) {  // 16 entries = one 128-byte line of the f64 payload
                     asm volatile("prefetch.global.L2 [%0];" ::"l"(a.ent_x + vb + e));
                     if (PRE) asm volatile("prefetch.global.L2 [%0];" ::"l"(a.ent_y + vb + e));
                     if ((e & 63) == (f0 & 63)) asm volatile("prefetch.global.L2 [%0];" ::"l"(a.ent_i + vb + e));
                 }
             }
-            double acc = 0.0, num = 1.0, den = 1.0, gmx = 0.0;
+            double acc = 0.0, gmx = 0.0;
             for (int g = g_lo; g < g_hi; g++) {
                 if (!resident) {
                     const int len = max(0, min(csz, ne - g * csz));
@@ -512,41 +740,32 @@ template <int KIND, int PRE, bool CL> __global__ void __launch_bounds__(ADJ_THRE
                     __syncthreads();
                 }
                 if (act) {
-                    const int *bo = a.boff + (int64_t)(v0 + g) * (K + 1);
-                    const int b0 = bo[q], b1 = bo[q + 1];
+                    const int *bo = a.boff + (int64_t)(v0 + g) * brow;
+                    const int b0 = bo[2 * q], bm = bo[2 * q + 1], b1 = bo[2 * q + 2];
                     const int64_t vb = a.vbase[v0 + g];
                     const unsigned short *ei = a.ent_i + vb;
                     const double *ex = a.ent_x + vb, *ey = PRE ? a.ent_y + vb : nullptr;
-                    int eb = b0 + sub * 32;
-                    unsigned ii_n = 0u;
-                    double x_n = 1.0, y_n = 0.0;
-                    if (eb + lane < b1) { ii_n = __ldg(ei + eb + lane); x_n = __ldg(ex + eb + lane); if (PRE) y_n = __ldg(ey + eb + lane); }
-                    while (eb < b1) {
-                        const unsigned ii = ii_n;
-                        const double x = x_n, y = y_n;
-                        const int ebn = eb + nsub * 32;
-                        if (ebn + lane < b1) { ii_n = __ldg(ei + ebn + lane); x_n = __ldg(ex + ebn + lane); if (PRE) y_n = __ldg(ey + ebn + lane); }  // next group in flight
-                        double gs;
-                        const bool head = adj_group<KIND, PRE>(en, ei, ex, ey, eb, b1, lane, ii, x, y, a.D, ft, gs) && gs > 0.0;
-                        // log((base + g) / base) accumulated as a running quotient of products: one log per lane and fold instead of one per entry
-                        double base = 1.0, hi = 1.0;
-                        if (head) {
-                            const double l = lam_s[ii & 0x7fffu];
-                            base = on ? fmax(l - gs, lam0) : l;  // intensity without parent q: at least lambda0
-                            hi = base + gs;
-                            gmx = fmax(gmx, gs);
-                        }
-                        const bool okf = above_2m500(base) && below_2p500(hi);  // hi >= base > 0: both factors in [2^-500, 2^500)
-                        if (__any_sync(0xffffffffu, !okf)) {  // warp-uniform, rare: an extreme (or non-positive) intensity takes the direct route
-                            if (!okf) { acc += log(hi / base); base = 1.0; hi = 1.0; }
-                        }
-                        num *= hi; den *= base;  // num >= den > 0
-                        if (__any_sync(0xffffffffu, !(above_2m500(den) && below_2p500(num)))) { acc += log(num) - log(den); num = 1.0; den = 1.0; }  // fold (rare)
-                        eb = ebn;
+                    const AdjPf pf = adj_pf_setup(ei, ex, ey, lane);
+                    if (q + Sc < K) {  // the bucket this warp takes if the whole batch is accepted: its first blocks go to L2 now
+                        const int nb = bo[2 * (q + Sc)] + sub * 64;
+                        adj_pf(pf, nb); adj_pf(pf, nb + nsub * 64);
+                    }
+                    AdjAcc A;
+                    acc_init(A);
+                    adj_singles<KIND, PRE>(en, ei, ex, ey, b0 + sub * 64, bm, nsub * 64, lane, onf, floor_, a.D, lam_s, ft, pf, A);
+                    adj_runs<KIND, PRE>(en, ei, ex, ey, bm + sub * 32, b1, nsub * 32, lane, onf, floor_, a.D, lam_s, ft, A);
+                    if (__all_sync(0xffffffffu, acc_in_range(A))) {
+                        acc += (fast_log_n(A.num, ft) - fast_log_n(A.den, ft)) + (double)A.bal * 0.6931471805599453;
+                        if (A.gm > 0) gmx = fmax(gmx, __hiloint2double(A.gm + 1, 0));  // upper bound of the largest contribution
+                    } else {  // warp-uniform, rare
+                        const double2 d0 = adj_direct<KIND, PRE>(en, ei, ex, ey, b0 + sub * 64, bm, nsub * 64, lane, onf, floor_, a.D, lam_s, ft);  // the same blocks, half by half
+                        const double2 d1 = adj_direct<KIND, PRE>(en, ei, ex, ey, b0 + sub * 64 + 32, bm, nsub * 64, lane, onf, floor_, a.D, lam_s, ft);
+                        const double2 d2 = adj_direct<KIND, PRE>(en, ei, ex, ey, bm + sub * 32, b1, nsub * 32, lane, onf, floor_, a.D, lam_s, ft);
+                        acc += d0.x + d1.x + d2.x;
+                        gmx = fmax(gmx, fmax(d0.y, fmax(d1.y, d2.y)));
                     }
                 }
             }
-            acc += log(num) - log(den);
             acc = warp_sum(acc);
 #pragma unroll
             for (int d = 16; d >= 1; d >>= 1) gmx = fmax(gmx, __shfl_xor_sync(0xffffffffu, gmx, d));
@@ -570,7 +789,7 @@ template <int KIND, int PRE, bool CL> __global__ void __launch_bounds__(ADJ_THRE
                 const int qq = p + lane;
                 const bool old_on = have && ((s_ab[qq >> 5] >> (qq & 31)) & 1u);
                 // ll1 - ll0 (continuous.jl:477-483): integrated-intensity difference, log-intensity difference, prior
-                const double delta = -d_w * d_mn + sum + d_lrho;
+                const double delta = -d_wmn + sum + d_lrho;
                 double p1 = delta >= 0.0 ? 1.0 / (1.0 + exp(-delta)) : exp(delta) / (1.0 + exp(delta));
                 if (have && delta != delta) { atomicOr(a.flag, 64); p1 = 0.0; }
                 const bool new_on = d_u <= p1;  // rand(Bernoulli(p)) = rand() <= p
@@ -619,21 +838,12 @@ template <int KIND, int PRE, bool CL> __global__ void __launch_bounds__(ADJ_THRE
                 const double sgn = ((onm >> j) & 1u) ? 1.0 : -1.0;
                 const E enf = load_entry(col + qf);
                 for (int g = g_lo; g < g_hi; g++) {
-                    const int *bo = a.boff + (int64_t)(v0 + g) * (K + 1);
-                    const int b0 = bo[qf], b1 = bo[qf + 1];
+                    const int *bo = a.boff + (int64_t)(v0 + g) * brow;
+                    const int b0 = bo[2 * qf], bm = bo[2 * qf + 1], b1 = bo[2 * qf + 2];
                     const int64_t vb = a.vbase[v0 + g];
                     const unsigned short *ei = a.ent_i + vb;
                     const double *ex = a.ent_x + vb, *ey = PRE ? a.ent_y + vb : nullptr;
-                    for (int eb = b0 + warp * 32; eb < b1; eb += ADJ_THREADS) {
-                        const bool valid = eb + lane < b1;
-                        const unsigned ii = valid ? (unsigned)__ldg(ei + eb + lane) : 0u;
-                        const double x = valid ? __ldg(ex + eb + lane) : 1.0, y = (PRE && valid) ? __ldg(ey + eb + lane) : 0.0;
-                        double gs;
-                        if (adj_group<KIND, PRE>(enf, ei, ex, ey, eb, b1, lane, ii, x, y, a.D, ft, gs) && gs > 0.0) {
-                            if (resident) lam_s[ii & 0x7fffu] += sgn * gs;
-                            else lamg[(size_t)g * csz + (ii & 0x7fffu)] += sgn * gs;
-                        }
-                    }
+                    adj_apply<KIND, PRE>(enf, ei, ex, ey, b0, bm, b1, warp, lane, sgn, resident ? lam_s : lamg + (size_t)g * csz, a.D, ft);
                 }
                 __syncthreads();  // the next flipped bucket may touch the same events
             }
@@ -698,6 +908,7 @@ static int adj_ensure_ctx(nhp_ctx *ctx) {
     if (!ctx->d_adj_tw) ADJ_CUDA(cudaMalloc(&ctx->d_adj_tw, KK * sizeof(EntryLN)));
     if (!ctx->d_adj_rho) ADJ_CUDA(cudaMalloc(&ctx->d_adj_rho, KK * sizeof(double)));
     if (!ctx->d_adj_u) ADJ_CUDA(cudaMalloc(&ctx->d_adj_u, KK * sizeof(double)));
+    if (!ctx->d_adj_dec) ADJ_CUDA(cudaMalloc(&ctx->d_adj_dec, KK * sizeof(double4)));
     if (!ctx->d_adj_A) ADJ_CUDA(cudaMalloc(&ctx->d_adj_A, KK * sizeof(double)));
     if (!ctx->d_adj_ctl) ADJ_CUDA(cudaMalloc(&ctx->d_adj_ctl, 8 * sizeof(int)));
     if (!ctx->d_adj_stat) ADJ_CUDA(cudaMalloc(&ctx->d_adj_stat, 8 * sizeof(unsigned long long)));
@@ -734,60 +945,76 @@ static int adj_build_structure(nhp_ctx *ctx, nhp_events *ev, double horizon, int
     vstart[K] = (int)vnode.size();
     const int64_t nv = (int64_t)vnode.size();
     if (nv == 0) return 1;
-    int *d_vstart = nullptr, *d_vnode = nullptr;
-    unsigned long long *d_vcount = nullptr;
-    auto drop = [&](int rc) { cudaFree(d_vstart); cudaFree(d_vnode); cudaFree(d_vcount); return rc; };
+    int *d_vstart = nullptr, *d_vnode = nullptr, *d_lo = nullptr;
+    unsigned long long *d_vcount = nullptr, *d_pk = nullptr;
+    auto drop = [&](int rc) { cudaFree(d_vstart); cudaFree(d_vnode); cudaFree(d_vcount); cudaFree(d_lo); cudaFree(d_pk); return rc; };
 #define ADJ_B(call) do { cudaError_t e__ = (call); if (e__ != cudaSuccess) return drop(nhp_fail(ctx, NHP_ERR_CUDA, "%s failed: %s (%s:%d)", #call, cudaGetErrorString(e__), __FILE__, __LINE__)); } while (0)
     ADJ_B(cudaMalloc(&d_vstart, (size_t)(K + 1) * sizeof(int)));
     ADJ_B(cudaMalloc(&d_vnode, (size_t)nv * sizeof(int)));
     ADJ_B(cudaMalloc(&d_vcount, (size_t)nv * sizeof(unsigned long long)));
+    ADJ_B(cudaMalloc(&d_lo, std::max<size_t>((size_t)n, 1) * sizeof(int)));
+    ADJ_B(cudaMemsetAsync(ctx->d_adj_ctl, 0, 8 * sizeof(int), s));
     ADJ_B(cudaMemcpyAsync(d_vstart, vstart.data(), (size_t)(K + 1) * sizeof(int), cudaMemcpyHostToDevice, s));
     ADJ_B(cudaMemcpyAsync(d_vnode, vnode.data(), (size_t)nv * sizeof(int), cudaMemcpyHostToDevice, s));
     ADJ_B(cudaMemsetAsync(d_vcount, 0, (size_t)nv * sizeof(unsigned long long), s));
     if (n > 0) {
-        k_adj_count<<<(unsigned)((n + 255) / 256), 256, 0, s>>>(ev->d_t, ev->d_c, ev->d_order, ev->d_node_ptr, d_vstart, n, horizon, cb, cs, d_vcount);
+        k_adj_count<<<(unsigned)((n + 255) / 256), 256, 0, s>>>(ev->d_t, ev->d_c, ev->d_order, ev->d_node_ptr, d_vstart, n, horizon, cb, cs, d_vcount, d_lo,
+                                                                 ctx->d_adj_ctl + 4);
         NHP_LAUNCHED(ctx);
     }
     std::vector<unsigned long long> vc(nv);
+    int max_win = 0;
+    ADJ_B(cudaMemcpyAsync(&max_win, ctx->d_adj_ctl + 4, sizeof(int), cudaMemcpyDeviceToHost, s));
     ADJ_B(cudaMemcpyAsync(vc.data(), d_vcount, (size_t)nv * sizeof(unsigned long long), cudaMemcpyDeviceToHost, s));
     ADJ_B(cudaStreamSynchronize(s));
+    // room per virtual column: its pairs plus the padding of its 2 K sections to whole groups of 32 entries (an upper bound; the regions
+    // start on group boundaries so that the sweeps' paired loads are aligned)
     std::vector<int64_t> vbase(nv + 1);
-    int64_t tot = 0;
+    int64_t tot = 0, pairs = 0;
     for (int64_t v = 0; v < nv; v++) {
         vbase[v] = tot;
-        if (vc[v] >= 0x7fffffffull) return drop(nhp_fail(ctx, NHP_ERR_UNSUPPORTED, "adjacency sampler: a column chunk has %llu window entries (limit 2^31)", vc[v]));
-        tot += (int64_t)vc[v];
+        const unsigned long long room = vc[v] + std::min<unsigned long long>(62ull * (unsigned long long)K, 31ull * vc[v]);
+        if (room >= 0x7fffffffull) return drop(nhp_fail(ctx, NHP_ERR_UNSUPPORTED, "adjacency sampler: a column chunk has %llu window entries (limit 2^31)", vc[v]));
+        pairs += (int64_t)vc[v];
+        tot += (int64_t)((room + 31ull) & ~31ull);
     }
     vbase[nv] = tot;
     // room: the structure (10 B per pair, or 18 B with the LogitNormal payload), the bucket offsets, the per-event intensities;
     // a quarter (payload: a third) of the free memory stays free for everything else
     size_t free_b = 0, total_b = 0;
     cudaMemGetInfo(&free_b, &total_b);
-    const size_t fixed = (size_t)nv * (K + 1) * sizeof(int) + (size_t)(nv + 1) * sizeof(int64_t) + (size_t)n * sizeof(double);
+    const size_t fixed = (size_t)nv * (2 * K + 1) * sizeof(int) + (size_t)(nv + 1) * sizeof(int64_t) + (size_t)n * (sizeof(double) + sizeof(unsigned long long));
     bool pre = ctx->kind == NHP_LOGITNORMAL && (double)tot * 18.0 + (double)fixed <= 0.72 * (double)free_b;
     { const char *e = getenv("NHP_ADJ_PRE"); if (e) pre = pre && atoi(e) != 0; }
     const size_t need = (size_t)tot * (pre ? 18 : 10) + fixed;
-    // build kernel: [K+1] offsets + per warp 2 K words (cursors, stamps)
-    int nw = (int)std::min<int64_t>(16, ((int64_t)ctx->smem_optin - 2048 - (K + 1) * 4) / (8 * K));
-    if ((double)need > 0.75 * (double)free_b || nw < 1) return drop(1);
+    // build kernel: [2K+1] section offsets + per warp 2 K cursors (singles, runs)
+    int nw = (int)std::min<int64_t>(16, ((int64_t)ctx->smem_optin - 2048 - (2 * K + 1) * 4) / (8 * K));
+    // the packed predecessor record holds 20 bits of node and 22 bits of same-node distances: longer windows take the uncached sweep
+    if ((double)need > 0.75 * (double)free_b || nw < 1 || K > (1 << ADJ_NODE_BITS) || max_win >= (int)ADJ_LINK_SAT) return drop(1);
     cudaFree(d_vcount); d_vcount = nullptr;
+    ADJ_B(cudaMalloc(&d_pk, std::max<size_t>((size_t)n, 1) * sizeof(unsigned long long)));
+    if (n > 0) {
+        k_adj_links<<<(unsigned)((n + 255) / 256), 256, 0, s>>>(ev->d_order, ev->d_node_ptr, ev->d_c, n, d_pk);
+        NHP_LAUNCHED(ctx);
+    }
     ev->d_adj_vstart = d_vstart; ev->d_adj_vnode = d_vnode; d_vstart = d_vnode = nullptr;  // owned by the handle from here on
-    auto fail = [&](int rc) { nhp_events_free_adjacency(ev); return rc; };
+    auto fail = [&](int rc) { cudaFree(d_lo); cudaFree(d_pk); nhp_events_free_adjacency(ev); return rc; };
 #define ADJ_S(call) do { cudaError_t e__ = (call); if (e__ != cudaSuccess) return fail(nhp_fail(ctx, NHP_ERR_CUDA, "%s failed: %s (%s:%d)", #call, cudaGetErrorString(e__), __FILE__, __LINE__)); } while (0)
     ADJ_S(cudaMalloc(&ev->d_adj_vbase, (size_t)(nv + 1) * sizeof(int64_t)));
-    ADJ_S(cudaMalloc(&ev->d_adj_boff, (size_t)nv * (K + 1) * sizeof(int)));
-    ADJ_S(cudaMalloc(&ev->d_adj_i, std::max<size_t>((size_t)tot, 1) * sizeof(unsigned short)));
-    ADJ_S(cudaMalloc(&ev->d_adj_dt, std::max<size_t>((size_t)tot, 1) * sizeof(double)));
-    if (pre) ADJ_S(cudaMalloc(&ev->d_adj_q, std::max<size_t>((size_t)tot, 1) * sizeof(double)));
+    ADJ_S(cudaMalloc(&ev->d_adj_boff, (size_t)nv * (2 * K + 1) * sizeof(int)));
+    const size_t slack = 64 * 1024;  // entries: the sweeps' L2 prefetches run a few blocks ahead of the block they read
+    ADJ_S(cudaMalloc(&ev->d_adj_i, ((size_t)tot + slack) * sizeof(unsigned short)));
+    ADJ_S(cudaMalloc(&ev->d_adj_dt, ((size_t)tot + slack) * sizeof(double)));
+    if (pre) ADJ_S(cudaMalloc(&ev->d_adj_q, ((size_t)tot + slack) * sizeof(double)));
     ADJ_S(cudaMalloc(&ev->d_adj_lam, std::max<size_t>((size_t)n, 1) * sizeof(double)));
     ADJ_S(cudaMemcpyAsync(ev->d_adj_vbase, vbase.data(), (size_t)(nv + 1) * sizeof(int64_t), cudaMemcpyHostToDevice, s));
     ADJ_S(cudaMemsetAsync(ctx->d_adj_ctl, 0, 8 * sizeof(int), s));
     AdjBuildArgs b;
-    b.t = ev->d_t; b.c = ev->d_c; b.order = ev->d_order; b.node_ptr = ev->d_node_ptr; b.K = (int)K; b.horizon = horizon; b.D = ctx->dtmax;
+    b.t = ev->d_t; b.pk = d_pk; b.lo = d_lo; b.order = ev->d_order; b.node_ptr = ev->d_node_ptr; b.K = (int)K; b.D = ctx->dtmax;
     b.vstart = ev->d_adj_vstart; b.vnode = ev->d_adj_vnode; b.vbase = ev->d_adj_vbase; b.boff = ev->d_adj_boff; b.ent_i = ev->d_adj_i; b.ent_x = ev->d_adj_dt;
     b.ent_y = pre ? ev->d_adj_q : nullptr;
     b.nv = (int)nv; b.nw = nw; b.next = ctx->d_adj_ctl; b.flag = ctx->d_flag;
-    const size_t bsmem = (size_t)(K + 1) * sizeof(int) + (size_t)nw * 2 * K * sizeof(unsigned);
+    const size_t bsmem = (size_t)(2 * K + 1) * sizeof(int) + (size_t)nw * 2 * K * sizeof(unsigned);
     ADJ_S(cudaFuncSetAttribute(k_adj_build, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)std::max<size_t>(bsmem, 1024)));
     int per_sm = 1;
     ADJ_S(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_adj_build, nw * 32, bsmem));
@@ -805,8 +1032,9 @@ static int adj_build_structure(nhp_ctx *ctx, nhp_events *ev, double horizon, int
     float bms = 0.f;
     cudaEventElapsedTime(&bms, b0, b1);
     cudaEventDestroy(b0); cudaEventDestroy(b1);
+    cudaFree(d_lo); cudaFree(d_pk); d_lo = nullptr; d_pk = nullptr;
     if (flag & 128) return fail(nhp_fail(ctx, NHP_ERR_CUDA, "adjacency sampler: structure build disagrees with its own count (internal error)"));
-    ev->adj_total = tot; ev->adj_nv = nv; ev->adj_horizon = horizon; ev->adj_cb = cb; ev->adj_cs = cs;
+    ev->adj_total = tot; ev->adj_pairs = pairs; ev->adj_nv = nv; ev->adj_horizon = horizon; ev->adj_cb = cb; ev->adj_cs = cs;
     ev->adj_chunk_cap = chunk_cap; ev->adj_chunk_max = chunk_max; ev->adj_cluster = cluster; ev->adj_kind = pre ? 1 : 0;
     ctx->adj_info[7] = bms;
     return NHP_OK;
@@ -836,7 +1064,7 @@ static int adj_run_uncached(nhp_ctx *ctx, nhp_events *ev, double horizon, const 
     ADJ_U(cudaMemcpyAsync(d_vstart, vstart.data(), (size_t)(K + 1) * sizeof(int), cudaMemcpyHostToDevice, s));
     ADJ_U(cudaMemsetAsync(d_cc, 0, (size_t)K * sizeof(unsigned long long), s));
     if (n > 0) {
-        k_adj_count<<<(unsigned)((n + 255) / 256), 256, 0, s>>>(ev->d_t, ev->d_c, ev->d_order, ev->d_node_ptr, d_vstart, n, horizon, 0, 1, d_cc);
+        k_adj_count<<<(unsigned)((n + 255) / 256), 256, 0, s>>>(ev->d_t, ev->d_c, ev->d_order, ev->d_node_ptr, d_vstart, n, horizon, 0, 1, d_cc, nullptr, nullptr);
         NHP_LAUNCHED(ctx);
     }
     std::vector<unsigned long long> cc(K);
@@ -946,8 +1174,10 @@ static int adj_run(nhp_ctx *ctx, nhp_events *ev, const double *d_rho, double rho
     NHP_TRY(nhp_timer_begin(ctx));
     if (cached) {
         AdjSweepArgs w;
-        w.node_ptr = ev->d_node_ptr; w.Mn = ev->d_Mn; w.K = (int)K; w.table_w = ctx->d_adj_tw; w.lambda0 = ctx->d_lambda0; w.W = ctx->d_W; w.A = d_A;
-        w.rho = d_rho; w.rho_scalar = rho_scalar; w.u = d_u; w.seed = seed; w.counter = counter; w.D = ctx->dtmax;
+        w.node_ptr = ev->d_node_ptr; w.K = (int)K; w.table_w = ctx->d_adj_tw; w.lambda0 = ctx->d_lambda0; w.A = d_A;
+        k_adj_prep<<<kb, 256, 0, s>>>((int)K, ctx->d_W, ev->d_Mn, d_rho, rho_scalar, d_u, seed, counter, ctx->d_adj_dec);
+        NHP_LAUNCHED(ctx);
+        w.dec = ctx->d_adj_dec; w.D = ctx->dtmax;
         w.vstart = ev->d_adj_vstart; w.vbase = ev->d_adj_vbase; w.boff = ev->d_adj_boff; w.ent_i = ev->d_adj_i; w.ent_x = ev->d_adj_dt; w.ent_y = ev->d_adj_q;
         w.lam = ev->d_adj_lam;
         w.chunk_max = (ev->adj_chunk_max + 1) & ~1;
@@ -985,7 +1215,7 @@ static int adj_run(nhp_ctx *ctx, nhp_events *ev, const double *d_rho, double rho
     NHP_CHECK(ctx, !(flag & 32), NHP_ERR_CUDA, "adjacency sampler: scratch overflow (internal error)");
     NHP_CHECK(ctx, !(flag & 64), NHP_ERR_NUMERIC, "adjacency sampler: NaN log-likelihood difference");
     ctx->adj_info[0] = (double)st[0]; ctx->adj_info[1] = (double)st[1]; ctx->adj_info[2] = (double)st[2]; ctx->adj_info[3] = (double)st[3];
-    ctx->adj_info[4] = cached ? (double)ev->adj_total : 0.0;
+    ctx->adj_info[4] = cached ? (double)ev->adj_pairs : 0.0;
     ctx->adj_info[5] = cached ? (double)ev->adj_nv + 1e-3 * ev->adj_cluster + 1e-6 * (ev->adj_kind ? 18 : 10) : 0.0;  // virtual columns . cluster size, bytes per pair
     ctx->adj_info[6] = ctx->last_ms;
     return NHP_OK;

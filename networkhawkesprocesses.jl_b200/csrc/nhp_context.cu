@@ -65,7 +65,7 @@ static void free_cont(nhp_ctx *ctx) {
     cudaFree(ctx->d_lambda0); cudaFree(ctx->d_W); cudaFree(ctx->d_A); cudaFree(ctx->d_p1); cudaFree(ctx->d_p2);
     cudaFree(ctx->d_table); cudaFree(ctx->d_rowsum); cudaFree(ctx->d_rowsum_w); cudaFree(ctx->d_abits);
     cudaFree(ctx->d_stats0); cudaFree(ctx->d_stats1); cudaFree(ctx->d_xbar);
-    cudaFree(ctx->d_adj_tw); cudaFree(ctx->d_adj_rho); cudaFree(ctx->d_adj_u); cudaFree(ctx->d_adj_A); cudaFree(ctx->d_save);
+    cudaFree(ctx->d_adj_tw); cudaFree(ctx->d_adj_dec); ctx->d_adj_dec = nullptr; cudaFree(ctx->d_adj_rho); cudaFree(ctx->d_adj_u); cudaFree(ctx->d_adj_A); cudaFree(ctx->d_save);
     ctx->d_save = nullptr;
     ctx->d_adj_tw = nullptr; ctx->d_adj_rho = ctx->d_adj_u = ctx->d_adj_A = nullptr;
     ctx->d_lambda0 = ctx->d_W = ctx->d_A = ctx->d_p1 = ctx->d_p2 = ctx->d_rowsum = ctx->d_rowsum_w = nullptr;

@@ -94,14 +94,15 @@ struct nhp_events {
     int *d_adj_vstart = nullptr;     // [K+1] first virtual column of every column
     int *d_adj_vnode = nullptr;      // [nv] child column of every virtual column
     int64_t *d_adj_vbase = nullptr;  // [nv+1] first entry of every virtual column
-    int *d_adj_boff = nullptr;       // [nv][K+1] bucket offsets inside a virtual column
+    int *d_adj_boff = nullptr;       // [nv][2K+1] section offsets inside a virtual column: singles of parent p at [2p], its runs at [2p+1]
     unsigned short *d_adj_i = nullptr;  // [adj_total] child event index inside its chunk | bit 15: same (event, parent) as the previous entry
     double *d_adj_dt = nullptr;      // [adj_total] t_i - t_j, or logit(dt / D) with the LogitNormal payload
     double *d_adj_q = nullptr;       // [adj_total] LogitNormal payload: 1 / (dt (D - dt)), 0 outside the support
     int adj_cluster = 0;             // CTAs per column (thread-block cluster size; 0: single-CTA streaming form)
     int adj_kind = 0;                // 1: LogitNormal payload
     double *d_adj_lam = nullptr;     // [n] per-event intensity in by-node order (work array of the sweep)
-    int64_t adj_total = 0;
+    int64_t adj_total = 0;           // entries allocated (pairs + section padding)
+    int64_t adj_pairs = 0;           // (child event, window predecessor) pairs
     int64_t max_win = 0;        // max over boundaries of (i0 - lo)
     double mean_win = 0.0;
 };
@@ -149,6 +150,7 @@ struct nhp_ctx {
     // adjacency sampler work buffers (allocated on first use, sized by cap_K)
     void *d_adj_tw = nullptr;     // EntryLN/EntryEX [K*K] child-major, without the adjacency factor
     double *d_adj_rho = nullptr, *d_adj_u = nullptr, *d_adj_A = nullptr;  // [K*K] staging of host arguments
+    double4 *d_adj_dec = nullptr; // [K*K] decision inputs of the adjacency sweep (k_adj_prep)
     int *d_adj_ctl = nullptr;     // [8] dynamic work counters of the build / sweep kernels
     unsigned long long *d_adj_stat = nullptr;  // [8] sweep diagnostics (steps, batches, flips, recomputed steps)
     double *d_save = nullptr;     // nhp_cont_params_save: [K + 4 K^2] copy of lambda0, W, A, p1, p2
