@@ -790,9 +790,16 @@ template <int KIND, int PRE, bool CL> __global__ void __launch_bounds__(ADJ_THRE
                 const bool old_on = have && ((s_ab[qq >> 5] >> (qq & 31)) & 1u);
                 // ll1 - ll0 (continuous.jl:477-483): integrated-intensity difference, log-intensity difference, prior
                 const double delta = -d_wmn + sum + d_lrho;
-                double p1 = delta >= 0.0 ? 1.0 / (1.0 + exp(-delta)) : exp(delta) / (1.0 + exp(delta));
-                if (have && delta != delta) { atomicOr(a.flag, 64); p1 = 0.0; }
-                const bool new_on = d_u <= p1;  // rand(Bernoulli(p)) = rand() <= p
+                // rand(Bernoulli(p1)) = rand() <= p1 with p1 = sigmoid(delta).  u <= sigmoid(delta) <=> logit(u) <= delta, and the two sides
+                // are known to ~1e-14, so a clear margin decides without the exp and the division; a close call takes the reference's form
+                const double margin = fabs(delta - d_lu);
+                bool new_on = d_lu <= delta;
+                if (__any_sync(0xffffffffu, have && !(margin > 1e-6 * (1.0 + fabs(delta))))) {  // warp-uniform, rare
+                    double p1 = delta >= 0.0 ? 1.0 / (1.0 + exp(-delta)) : exp(delta) / (1.0 + exp(delta));
+                    if (delta != delta) p1 = 0.0;
+                    new_on = d_u <= p1;
+                }
+                if (have && delta != delta) atomicOr(a.flag, 64);
                 const unsigned flipmask = __ballot_sync(0xffffffffu, have && new_on != old_on);
                 // Certified speculation.  The sums of this batch were taken with the intensities as they stood at its start.  A flip of
                 // bucket j moves every intensity by at most gmax_j, and a term log((b + g) / b) of a later bucket moves by at most
@@ -800,21 +807,25 @@ template <int KIND, int PRE, bool CL> __global__ void __launch_bounds__(ADJ_THRE
                 // factor 4 covers a decreasing b), so a later sum S moves by at most 4 S cum / lambda0, cum = the gmax of the flips so far.
                 // A decision whose margin |delta - logit(u)| exceeds that bound (plus rounding slack) is the decision the sequential sweep
                 // takes; the batch is accepted up to the first bucket that cannot be certified, and restarts there.
-                const double margin = fabs(delta - d_lu), slack = 1e-7 + 1e-10 * fabs(delta);
-                const double inv_l0 = 4.0 / lam0;
-                double cum = 0.0;
-                int stop = Sc;
-                unsigned acc_mask = 0u;
-                for (int j = 0; j < Sc; j++) {  // the same values in every lane (and every CTA of the cluster)
-                    const double Sj = fabs(__shfl_sync(0xffffffffu, sum, j)), mj = __shfl_sync(0xffffffffu, margin, j);
-                    const double gj = __shfl_sync(0xffffffffu, gmax, j), sj = __shfl_sync(0xffffffffu, slack, j);
-                    if (cum > 0.0 && !(mj > Sj * cum * inv_l0 + sj)) { stop = j; break; }
-                    if ((flipmask >> j) & 1u) {
-                        acc_mask |= 1u << j;
-                        if (!(gj <= 0.5 * lam0)) { stop = j + 1; break; }  // too large a change to bound: nothing behind it is certified
-                        cum += gj;
-                    }
+                // cum = exclusive prefix sum over the flips (warp scan: the same values in every CTA of the cluster); a flip whose change is
+                // too large to bound (> lambda0 / 2) ends the batch behind itself.
+                const bool flip = (flipmask >> lane) & 1u;
+                double inc = flip ? gmax : 0.0;
+#pragma unroll
+                for (int d = 1; d < 32; d <<= 1) {
+                    const double t = __shfl_up_sync(0xffffffffu, inc, d);
+                    if (lane >= d) inc += t;
                 }
+                double cum = __shfl_up_sync(0xffffffffu, inc, 1);
+                if (lane == 0) cum = 0.0;
+                const double slack = 1e-7 + 1e-10 * fabs(delta);
+                const bool uncertified = have && cum > 0.0 && !(margin > fabs(sum) * cum * (4.0 / lam0) + slack);
+                const bool toobig = flip && !(gmax <= 0.5 * lam0);
+                const unsigned um = __ballot_sync(0xffffffffu, uncertified), bm = __ballot_sync(0xffffffffu, toobig);
+                int stop = Sc;
+                if (um) stop = min(stop, __ffs(um) - 1);
+                if (bm) stop = min(stop, __ffs(bm));
+                const unsigned acc_mask = stop >= 32 ? flipmask : (flipmask & ((1u << stop) - 1u));
                 if (lane == 0) { s_first = stop; s_mask = acc_mask; }
                 const unsigned onmask = __ballot_sync(0xffffffffu, new_on);
                 if (lane == 0) s_onmask = onmask;
@@ -830,6 +841,19 @@ template <int KIND, int PRE, bool CL> __global__ void __launch_bounds__(ADJ_THRE
             const unsigned onm = s_onmask;
             n_batches++;
             n_steps += stop; n_flips += __popc(fm); n_redo += Sc - stop;
+            if (resident && (fm & (fm - 1))) {  // several flips: all their buckets start towards L2 now, the first one's latency covers the others
+                const int *bo = a.boff + (int64_t)(v0 + g_lo) * brow;
+                const int64_t vb = a.vbase[v0 + g_lo];
+                for (unsigned f2 = fm & (fm - 1); f2; f2 &= f2 - 1) {
+                    const int qf = p + __ffs(f2) - 1;
+                    const int f0 = bo[2 * qf], f1 = bo[2 * qf + 2];
+                    for (int e = f0 + tid * 16; e < f1; e += ADJ_THREADS * 16) {
+                        asm volatile("prefetch.global.L2 [%0];" ::"l"(a.ent_x + vb + e));
+                        if (PRE) asm volatile("prefetch.global.L2 [%0];" ::"l"(a.ent_y + vb + e));
+                        if ((e & 63) == (f0 & 63)) asm volatile("prefetch.global.L2 [%0];" ::"l"(a.ent_i + vb + e));
+                    }
+                }
+            }
             while (fm) {
                 // the link of bucket qf flipped: move its contribution into / out of the intensities
                 const int j = __ffs(fm) - 1;
@@ -931,7 +955,7 @@ static int adj_build_structure(nhp_ctx *ctx, nhp_events *ev, double horizon, int
     int cluster = 1;
     while (cluster < ADJ_CLUSTER_MAX && (int64_t)cluster * chunk_cap < max_col) cluster++;
     if ((int64_t)cluster * chunk_cap < max_col) cluster = 0;  // too large for a cluster: single-CTA streaming form
-    { const char *e = getenv("NHP_ADJ_CLUSTER"); if (e && atoi(e) == 0) cluster = 0; }
+    { const char *e = getenv("NHP_ADJ_CLUSTER"); if (e && atoi(e) == 0) cluster = 0; else if (e && cluster > 0 && atoi(e) > cluster && atoi(e) <= ADJ_CLUSTER_MAX) cluster = atoi(e); }
     std::vector<int> vstart(K + 1), vnode;
     int chunk_max = 1;
     for (int64_t c = 0; c < K; c++) {
