@@ -194,14 +194,16 @@ __host__ __device__ inline int adj_chunk_size(int ne, int G) { return G > 0 ? (n
 // entries per virtual column: every child event adds its window length; the window start of every owned event is kept for the build
 __global__ void k_adj_count(const double *__restrict__ t, const int *__restrict__ c, const int *__restrict__ order, const int *__restrict__ node_ptr,
                             const int *__restrict__ vstart, int64_t n_own, double horizon, int cb, int cs, unsigned long long *__restrict__ vcount,
-                            int *__restrict__ lo_out, int *__restrict__ max_win) {
+                            int *__restrict__ lo_out, int *__restrict__ max_win, const unsigned short *__restrict__ wlen) {
     const int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (e >= n_own) return;
     const int i = order[e], col = c[i];
     if (col % cs != cb) return;
     const int le = (int)(e - node_ptr[col]), ne = node_ptr[col + 1] - node_ptr[col], G = vstart[col + 1] - vstart[col];
     const int v = vstart[col] + le / adj_chunk_size(ne, G);
-    const int lo = lo_of_event(t, i, horizon);
+    // the sweeps' cached window length when it was taken with this horizon (saturated values are searched)
+    const unsigned wl = wlen ? (unsigned)wlen[i] : 65535u;
+    const int lo = wl < 65535u ? i - (int)wl : lo_of_event(t, i, horizon);
     if (lo_out) lo_out[i] = lo;
     if (i > lo) {
         atomicAdd(&vcount[v], (unsigned long long)(i - lo));
@@ -233,24 +235,35 @@ struct AdjBuildArgs {
     int *next, *flag;
 };
 
-// Stable counting sort of one virtual column's (child event, window predecessor) pairs by parent node.  A parent's bucket has two
+// Counting sort of one virtual column's (child event, window predecessor) pairs by parent node.  A parent's bucket has two
 // sections: first the SINGLES -- pairs whose (event, parent) occurs once in the event's window (94 % at config 4), which a sweep
 // streams with no bookkeeping at all -- then the RUNS: the entries of one (event, parent) next to each other in window order, all but
-// the first carrying the continuation bit.  Warp w owns a contiguous range of the chunk's events and private per-parent cursors, so
-// both sections are ordered by (event, window position) whatever the scheduling.
+// the first carrying the continuation bit.
+// Singles take their slot from ONE cursor per (parent) shared by the CTA's warps (shared-memory atomics): a section then fills
+// front to back, the partially written sectors of a column's 2 K sections stay few enough to sit in L2 until they are complete, and
+// DRAM sees whole sectors (per-warp cursors multiplied the open sectors by the warp count: 570 GB written for 116 GB of payload);
+// their order inside a section follows the scheduling, which only moves the rounding of a bucket's sum.  Run entries keep private
+// per-warp cursors (warp w owns a contiguous range of the chunk's events), so a run is contiguous and in window order.
 // Payload per entry: the lag t_i - t_j, or -- LogitNormal, when memory allows -- what the impulse needs of it and what does not
 // depend on the parameters: z = logit(dt / D) and q = 1 / (dt (D - dt)), so that a sweep evaluates one exp per pair instead of
 // a log, a reciprocal and an exp (pairs outside the support get q = 0).
+__device__ __forceinline__ void adj_pk_decode(unsigned long long pk, int j, int i, int lo, int &p, bool &multi, bool &cont) {
+    p = (int)((unsigned)pk & ((1u << ADJ_NODE_BITS) - 1u));
+    const int dp = (int)((unsigned)(pk >> ADJ_NODE_BITS) & ADJ_LINK_SAT), dn = (int)(pk >> (ADJ_NODE_BITS + ADJ_LINK_BITS));
+    cont = (int64_t)j + dn < (int64_t)i;  // a more recent event of the same node sits in the window: this entry continues its run
+    multi = cont || (j - dp >= lo);
+}
+
 __global__ void __launch_bounds__(512) k_adj_build(const AdjBuildArgs a) {
     extern __shared__ int s_dyn[];
     __shared__ int s_v;
     const int K = a.K, nw = a.nw;
     int *s_off = s_dyn;                                               // [2K+1] section offsets: singles of p, runs of p, ...
-    unsigned *s_w = reinterpret_cast<unsigned *>(s_dyn + 2 * K + 1);  // per warp: curS[K], curM[K]
+    unsigned *s_curS = reinterpret_cast<unsigned *>(s_dyn + 2 * K + 1);  // [K] singles: count, then the CTA-wide cursor
+    unsigned *s_w = s_curS + K;                                       // per warp: curM[K] run entries: count, then the warp's cursor
     const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
-    unsigned *curS = s_w + (size_t)wid * 2 * K, *curM = curS + K;
+    unsigned *curM = s_w + (size_t)wid * K;
     const unsigned lt = (1u << lane) - 1u;
-    const unsigned nmask = (1u << ADJ_NODE_BITS) - 1u;
     for (;;) {
         __syncthreads();
         if (tid == 0) s_v = atomicAdd(a.next, 1);
@@ -262,49 +275,59 @@ __global__ void __launch_bounds__(512) k_adj_build(const AdjBuildArgs a) {
         const int eb = a.node_ptr[col] + g * csz, ee = min(a.node_ptr[col] + ne, eb + csz);  // positions in the by-node order
         const int per = (max(ee - eb, 0) + nw - 1) / nw;
         const int ws = min(ee, eb + wid * per), we = min(ee, ws + per);
-        for (int k = lane; k < 2 * K; k += 32) curS[k] = 0u;
-        __syncwarp();
-        // ---- A: per-(warp, parent) counts of singles and of run entries
+        for (int k = tid; k < (nw + 1) * K; k += blockDim.x) s_curS[k] = 0u;
+        __syncthreads();
+        // ---- A: counts (singles per CTA, run entries per warp)
         for (int e0 = ws; e0 < we; e0 += 32) {
             int my_i = 0, my_lo = 0;
             if (e0 + lane < we) { my_i = a.order[e0 + lane]; my_lo = a.lo[my_i]; }  // 32 events' headers in one round trip
             const int cnt = min(32, we - e0);
             for (int s = 0; s < cnt; s++) {
                 const int i = __shfl_sync(0xffffffffu, my_i, s), lo = __shfl_sync(0xffffffffu, my_lo, s);
-                for (int j = i - 1 - lane; j >= lo; j -= 32) {
-                    const unsigned long long pk = __ldg(a.pk + j);
-                    const int p = (int)((unsigned)pk & nmask);
-                    const int dp = (int)((unsigned)(pk >> ADJ_NODE_BITS) & ADJ_LINK_SAT), dn = (int)(pk >> (ADJ_NODE_BITS + ADJ_LINK_BITS));
-                    const bool multi = (j - dp >= lo) || ((int64_t)j + dn < (int64_t)i);
-                    atomicAdd(multi ? &curM[p] : &curS[p], 1u);
+                for (int j = i - 1 - lane; j >= lo; j -= 64) {  // two rounds in flight
+                    const int j2 = j - 32;
+                    const unsigned long long pk = __ldg(a.pk + j), pk2 = j2 >= lo ? __ldg(a.pk + j2) : 0ull;
+                    int p; bool multi, cont;
+                    adj_pk_decode(pk, j, i, lo, p, multi, cont);
+                    atomicAdd(multi ? &curM[p] : &s_curS[p], 1u);
+                    if (j2 >= lo) {
+                        adj_pk_decode(pk2, j2, i, lo, p, multi, cont);
+                        atomicAdd(multi ? &curM[p] : &s_curS[p], 1u);
+                    }
                 }
             }
         }
         __syncthreads();
-        // ---- section sizes; every warp's cursor starts behind the earlier warps' entries of the same section
-        for (int k = tid; k < 2 * K; k += blockDim.x) {  // k = section of warp-row layout: [0,K) singles, [K,2K) runs
+        // ---- section sizes (padded to whole groups of 32 entries); a warp's run cursor starts behind the earlier warps' entries
+        for (int p = tid; p < K; p += blockDim.x) {
             unsigned r = 0;
-            for (int w = 0; w < nw; w++) { unsigned *cw = s_w + (size_t)w * 2 * K; const unsigned x = cw[k]; cw[k] = r; r += x; }
-            const int p = k < K ? k : k - K;
-            s_off[2 * p + (k < K ? 0 : 1) + 1] = (int)((r + 31u) & ~31u);  // every section is padded to whole groups of 32 entries
+            for (int w = 0; w < nw; w++) { unsigned *cw = s_w + (size_t)w * K; const unsigned x = cw[p]; cw[p] = r; r += x; }
+            s_off[2 * p + 1] = (int)((s_curS[p] + 31u) & ~31u);
+            s_off[2 * p + 2] = (int)((r + 31u) & ~31u);
         }
         if (tid == 0) s_off[0] = 0;
         __syncthreads();
-        if (tid == 0) {
-            int r = 0;
-            for (int k = 0; k < 2 * K; k++) { r += s_off[k + 1]; s_off[k + 1] = r; }
-            if ((int64_t)r > a.vbase[v + 1] - a.vbase[v]) atomicOr(a.flag, 128);
+        if (tid < 32) {  // exclusive scan of the 2 K section sizes by one warp
+            int carry = 0;
+            for (int k0 = 0; k0 < 2 * K; k0 += 32) {
+                const int k = k0 + lane;
+                int x = k < 2 * K ? s_off[k + 1] : 0;
+#pragma unroll
+                for (int d = 1; d < 32; d <<= 1) { const int y = __shfl_up_sync(0xffffffffu, x, d); if (lane >= d) x += y; }
+                if (k < 2 * K) s_off[k + 1] = carry + x;
+                carry += __shfl_sync(0xffffffffu, x, 31);
+            }
+            if (lane == 0 && (int64_t)carry > a.vbase[v + 1] - a.vbase[v]) atomicOr(a.flag, 128);
         }
         __syncthreads();
         for (int k = tid; k <= 2 * K; k += blockDim.x) a.boff[(int64_t)v * (2 * K + 1) + k] = s_off[k];
-        for (int k = tid; k < 2 * K; k += blockDim.x) {
-            const int p = k < K ? k : k - K;
-            const unsigned o = (unsigned)s_off[2 * p + (k < K ? 0 : 1)];
-            for (int w = 0; w < nw; w++) s_w[(size_t)w * 2 * K + k] += o;
+        for (int p = tid; p < K; p += blockDim.x) {
+            s_curS[p] = (unsigned)s_off[2 * p];
+            const unsigned o = (unsigned)s_off[2 * p + 1];
+            for (int w = 0; w < nw; w++) s_w[(size_t)w * K + p] += o;
         }
         __syncthreads();
-        // ---- B: scatter, one pass over every window.  A single goes to its section's cursor (no other lane of the event holds that
-        //      parent); run entries of one round are ranked among the lanes that hold the same parent, rounds are taken in order.
+        // ---- B: scatter, one pass over every window
         unsigned short *ei = a.ent_i + a.vbase[v];
         double *ex = a.ent_x + a.vbase[v];
         double *ey = a.ent_y ? a.ent_y + a.vbase[v] : nullptr;
@@ -317,27 +340,30 @@ __global__ void __launch_bounds__(512) k_adj_build(const AdjBuildArgs a) {
                 const int i = __shfl_sync(0xffffffffu, my_i, s), lo = __shfl_sync(0xffffffffu, my_lo, s);
                 const double ti = __shfl_sync(0xffffffffu, my_t, s);
                 const unsigned le = (unsigned)(e0 + s - eb);
+                // the next round's loads are issued before this round is scattered
+                int j = i - 1 - lane;
+                unsigned long long pk = 0ull;
+                double tj = 0.0;
+                if (j >= lo) { pk = __ldg(a.pk + j); tj = __ldg(a.t + j); }
                 for (int j0 = i - 1; j0 >= lo; j0 -= 32) {
-                    const int j = j0 - lane;
-                    const bool valid = j >= lo;
+                    const int jc = j;
+                    const unsigned long long pkc = pk;
+                    const double tjc = tj;
+                    j -= 32;
+                    if (j >= lo) { pk = __ldg(a.pk + j); tj = __ldg(a.t + j); }
+                    const bool valid = jc >= lo;
                     int p = -1 - lane;
                     bool multi = false, cont = false;
-                    double dt = 0.0;
-                    if (valid) {
-                        const unsigned long long pk = __ldg(a.pk + j);
-                        p = (int)((unsigned)pk & nmask);
-                        const int dp = (int)((unsigned)(pk >> ADJ_NODE_BITS) & ADJ_LINK_SAT), dn = (int)(pk >> (ADJ_NODE_BITS + ADJ_LINK_BITS));
-                        cont = (int64_t)j + dn < (int64_t)i;  // a more recent event of the same node sits in the window: this entry continues its run
-                        multi = cont || (j - dp >= lo);
-                        dt = ti - __ldg(a.t + j);
-                    }
+                    if (valid) adj_pk_decode(pkc, jc, i, lo, p, multi, cont);
+                    const double dt = ti - tjc;
                     unsigned pos = 0u;
-                    if (valid && !multi) { pos = curS[p]; curS[p] = pos + 1u; }
-                    if (__any_sync(0xffffffffu, multi)) {
+                    if (valid && !multi) pos = atomicAdd(&s_curS[p], 1u);
+                    if (__any_sync(0xffffffffu, multi)) {  // entries of this round that belong to runs: ranked among the lanes with the same parent
                         const unsigned m = __match_any_sync(0xffffffffu, multi ? p : -1 - lane);
                         if (multi) pos = curM[p] + __popc(m & lt);
                         __syncwarp();
                         if (multi && (m & lt) == 0u) curM[p] += __popc(m);
+                        __syncwarp();
                     }
                     if (valid) {
                         ei[pos] = (unsigned short)(le | (cont ? 0x8000u : 0u));
@@ -352,16 +378,15 @@ __global__ void __launch_bounds__(512) k_adj_build(const AdjBuildArgs a) {
                             ex[pos] = z; ey[pos] = q;
                         } else ex[pos] = dt;
                     }
-                    __syncwarp();
                 }
             }
         }
         __syncthreads();
         // ---- padding: entries that evaluate to exactly zero (event 0, q = 0 | lag -1), so the sweeps read whole groups unconditionally
         for (int k = tid; k < 2 * K; k += blockDim.x) {
-            const int p = k < K ? k : k - K;
-            const int end = s_off[2 * p + (k < K ? 0 : 1) + 1];
-            for (int e = (int)s_w[(size_t)(nw - 1) * 2 * K + k]; e < end; e++) {  // the last warp's cursor is the section's true end
+            const int p = k >> 1;
+            const int beg = (k & 1) ? (int)s_w[(size_t)(nw - 1) * K + p] : (int)s_curS[p];  // true end: the CTA cursor | the last warp's cursor
+            for (int e = beg; e < s_off[k + 1]; e++) {
                 ei[e] = 0;
                 if (ey) { ex[e] = 0.0; ey[e] = 0.0; } else ex[e] = -1.0;
             }
@@ -925,6 +950,20 @@ static double adj_horizon_value(const nhp_ctx *ctx, int64_t n_total) {
     return h;
 }
 
+// NHP_TIMING=1: wall-clock phases of the structure build on stderr (development aid)
+#include <chrono>
+struct AdjPhaseTimer {
+    bool on; cudaStream_t s; std::chrono::steady_clock::time_point t0;
+    AdjPhaseTimer(cudaStream_t st) : on(getenv("NHP_TIMING") && atoi(getenv("NHP_TIMING"))), s(st), t0(std::chrono::steady_clock::now()) {}
+    void lap(const char *what) {
+        if (!on) return;
+        cudaStreamSynchronize(s);
+        const auto t1 = std::chrono::steady_clock::now();
+        fprintf(stderr, "[nhp timing] %-28s %9.3f ms\n", what, std::chrono::duration<double, std::milli>(t1 - t0).count());
+        t0 = t1;
+    }
+};
+
 #define ADJ_CUDA(call) do { cudaError_t e__ = (call); if (e__ != cudaSuccess) return nhp_fail(ctx, NHP_ERR_CUDA, "%s failed: %s (%s:%d)", #call, cudaGetErrorString(e__), __FILE__, __LINE__); } while (0)
 
 static int adj_ensure_ctx(nhp_ctx *ctx) {
@@ -943,7 +982,9 @@ static int adj_ensure_ctx(nhp_ctx *ctx) {
 static int adj_build_structure(nhp_ctx *ctx, nhp_events *ev, double horizon, int cb, int cs, int chunk_cap) {
     const int64_t K = ctx->K, n = ev->n;
     cudaStream_t s = ctx->stream;
+    AdjPhaseTimer tm(s);
     nhp_events_free_adjacency(ev);
+    tm.lap("free old structure");
     std::vector<double> mn(K);
     ADJ_CUDA(cudaMemcpyAsync(mn.data(), ev->d_Mn, K * sizeof(double), cudaMemcpyDeviceToHost, s));
     ADJ_CUDA(cudaStreamSynchronize(s));
@@ -983,9 +1024,10 @@ static int adj_build_structure(nhp_ctx *ctx, nhp_events *ev, double horizon, int
     ADJ_B(cudaMemsetAsync(d_vcount, 0, (size_t)nv * sizeof(unsigned long long), s));
     if (n > 0) {
         k_adj_count<<<(unsigned)((n + 255) / 256), 256, 0, s>>>(ev->d_t, ev->d_c, ev->d_order, ev->d_node_ptr, d_vstart, n, horizon, cb, cs, d_vcount, d_lo,
-                                                                 ctx->d_adj_ctl + 4);
+                                                                 ctx->d_adj_ctl + 4, (ev->cache_horizon == horizon && ev->n_halo == 0) ? ev->d_wlen : nullptr);
         NHP_LAUNCHED(ctx);
     }
+    tm.lap("virtual columns + count");
     std::vector<unsigned long long> vc(nv);
     int max_win = 0;
     ADJ_B(cudaMemcpyAsync(&max_win, ctx->d_adj_ctl + 4, sizeof(int), cudaMemcpyDeviceToHost, s));
@@ -1011,8 +1053,9 @@ static int adj_build_structure(nhp_ctx *ctx, nhp_events *ev, double horizon, int
     bool pre = ctx->kind == NHP_LOGITNORMAL && (double)tot * 18.0 + (double)fixed <= 0.72 * (double)free_b;
     { const char *e = getenv("NHP_ADJ_PRE"); if (e) pre = pre && atoi(e) != 0; }
     const size_t need = (size_t)tot * (pre ? 18 : 10) + fixed;
-    // build kernel: [2K+1] section offsets + per warp 2 K cursors (singles, runs)
-    int nw = (int)std::min<int64_t>(16, ((int64_t)ctx->smem_optin - 2048 - (2 * K + 1) * 4) / (8 * K));
+    // build kernel: [2K+1] section offsets + K shared cursors (singles) + per warp K cursors (runs); two CTAs per SM when they fit
+    int nw = (int)std::min<int64_t>(16, ((int64_t)ctx->smem_optin / 2 - 2048 - (3 * K + 1) * 4) / (4 * K));
+    if (nw < 4) nw = (int)std::min<int64_t>(16, ((int64_t)ctx->smem_optin - 2048 - (3 * K + 1) * 4) / (4 * K));
     // the packed predecessor record holds 20 bits of node and 22 bits of same-node distances: longer windows take the uncached sweep
     if ((double)need > 0.75 * (double)free_b || nw < 1 || K > (1 << ADJ_NODE_BITS) || max_win >= (int)ADJ_LINK_SAT) return drop(1);
     cudaFree(d_vcount); d_vcount = nullptr;
@@ -1031,6 +1074,7 @@ static int adj_build_structure(nhp_ctx *ctx, nhp_events *ev, double horizon, int
     ADJ_S(cudaMalloc(&ev->d_adj_dt, ((size_t)tot + slack) * sizeof(double)));
     if (pre) ADJ_S(cudaMalloc(&ev->d_adj_q, ((size_t)tot + slack) * sizeof(double)));
     ADJ_S(cudaMalloc(&ev->d_adj_lam, std::max<size_t>((size_t)n, 1) * sizeof(double)));
+    tm.lap("links + allocation");
     ADJ_S(cudaMemcpyAsync(ev->d_adj_vbase, vbase.data(), (size_t)(nv + 1) * sizeof(int64_t), cudaMemcpyHostToDevice, s));
     ADJ_S(cudaMemsetAsync(ctx->d_adj_ctl, 0, 8 * sizeof(int), s));
     AdjBuildArgs b;
@@ -1038,7 +1082,7 @@ static int adj_build_structure(nhp_ctx *ctx, nhp_events *ev, double horizon, int
     b.vstart = ev->d_adj_vstart; b.vnode = ev->d_adj_vnode; b.vbase = ev->d_adj_vbase; b.boff = ev->d_adj_boff; b.ent_i = ev->d_adj_i; b.ent_x = ev->d_adj_dt;
     b.ent_y = pre ? ev->d_adj_q : nullptr;
     b.nv = (int)nv; b.nw = nw; b.next = ctx->d_adj_ctl; b.flag = ctx->d_flag;
-    const size_t bsmem = (size_t)(2 * K + 1) * sizeof(int) + (size_t)nw * 2 * K * sizeof(unsigned);
+    const size_t bsmem = (size_t)(2 * K + 1) * sizeof(int) + (size_t)(nw + 1) * K * sizeof(unsigned);
     ADJ_S(cudaFuncSetAttribute(k_adj_build, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)std::max<size_t>(bsmem, 1024)));
     int per_sm = 1;
     ADJ_S(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_adj_build, nw * 32, bsmem));
@@ -1056,7 +1100,9 @@ static int adj_build_structure(nhp_ctx *ctx, nhp_events *ev, double horizon, int
     float bms = 0.f;
     cudaEventElapsedTime(&bms, b0, b1);
     cudaEventDestroy(b0); cudaEventDestroy(b1);
+    tm.lap("build kernel");
     cudaFree(d_lo); cudaFree(d_pk); d_lo = nullptr; d_pk = nullptr;
+    tm.lap("free temporaries");
     if (flag & 128) return fail(nhp_fail(ctx, NHP_ERR_CUDA, "adjacency sampler: structure build disagrees with its own count (internal error)"));
     ev->adj_total = tot; ev->adj_pairs = pairs; ev->adj_nv = nv; ev->adj_horizon = horizon; ev->adj_cb = cb; ev->adj_cs = cs;
     ev->adj_chunk_cap = chunk_cap; ev->adj_chunk_max = chunk_max; ev->adj_cluster = cluster; ev->adj_kind = pre ? 1 : 0;
@@ -1088,7 +1134,7 @@ static int adj_run_uncached(nhp_ctx *ctx, nhp_events *ev, double horizon, const 
     ADJ_U(cudaMemcpyAsync(d_vstart, vstart.data(), (size_t)(K + 1) * sizeof(int), cudaMemcpyHostToDevice, s));
     ADJ_U(cudaMemsetAsync(d_cc, 0, (size_t)K * sizeof(unsigned long long), s));
     if (n > 0) {
-        k_adj_count<<<(unsigned)((n + 255) / 256), 256, 0, s>>>(ev->d_t, ev->d_c, ev->d_order, ev->d_node_ptr, d_vstart, n, horizon, 0, 1, d_cc, nullptr, nullptr);
+        k_adj_count<<<(unsigned)((n + 255) / 256), 256, 0, s>>>(ev->d_t, ev->d_c, ev->d_order, ev->d_node_ptr, d_vstart, n, horizon, 0, 1, d_cc, nullptr, nullptr, nullptr);
         NHP_LAUNCHED(ctx);
     }
     std::vector<unsigned long long> cc(K);
@@ -1177,7 +1223,9 @@ static int adj_run(nhp_ctx *ctx, nhp_events *ev, const double *d_rho, double rho
     NHP_LAUNCHED(ctx);
     NHP_CUDA(ctx, cudaMemsetAsync(ctx->d_flag, 0, sizeof(int), s));
     for (int i = 0; i < 7; i++) ctx->adj_info[i] = 0.0;
+    AdjPhaseTimer tr(s);
     NHP_TRY(nhp_events_build_node_index(ctx, ev));
+    tr.lap("node index");
     double horizon = adj_horizon_value(ctx, n);
     const char *envc = getenv("NHP_ADJ_CACHE");
     bool cached = !(envc && atoi(envc) == 0);
