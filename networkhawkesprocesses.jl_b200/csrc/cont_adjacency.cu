@@ -247,6 +247,35 @@ struct AdjBuildArgs {
 // Payload per entry: the lag t_i - t_j, or -- LogitNormal, when memory allows -- what the impulse needs of it and what does not
 // depend on the parameters: z = logit(dt / D) and q = 1 / (dt (D - dt)), so that a sweep evaluates one exp per pair instead of
 // a log, a reciprocal and an exp (pairs outside the support get q = 0).
+// cache policy of the build: the event stream is read once per pass (evict first), the half-written output sectors should stay in
+// L2 until their neighbours arrive (evict last)
+__device__ __forceinline__ unsigned long long l2_policy_evict_first() {
+    unsigned long long pol;
+    asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(pol));
+    return pol;
+}
+__device__ __forceinline__ unsigned long long l2_policy_evict_last() {
+    unsigned long long pol;
+    asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(pol));
+    return pol;
+}
+__device__ __forceinline__ unsigned long long ldg_stream_u64(const unsigned long long *p, unsigned long long pol) {
+    unsigned long long v;
+    asm volatile("ld.global.nc.L1::no_allocate.L2::cache_hint.u64 %0, [%1], %2;" : "=l"(v) : "l"(p), "l"(pol));
+    return v;
+}
+__device__ __forceinline__ double ldg_stream_f64(const double *p, unsigned long long pol) {
+    double v;
+    asm volatile("ld.global.nc.L1::no_allocate.L2::cache_hint.f64 %0, [%1], %2;" : "=d"(v) : "l"(p), "l"(pol));
+    return v;
+}
+__device__ __forceinline__ void st_keep_f64(double *p, double v, unsigned long long pol) {
+    asm volatile("st.global.L2::cache_hint.f64 [%0], %1, %2;" ::"l"(p), "d"(v), "l"(pol) : "memory");
+}
+__device__ __forceinline__ void st_keep_u16(unsigned short *p, unsigned short v, unsigned long long pol) {
+    asm volatile("st.global.L2::cache_hint.u16 [%0], %1, %2;" ::"l"(p), "h"(v), "l"(pol) : "memory");
+}
+
 __device__ __forceinline__ void adj_pk_decode(unsigned long long pk, int j, int i, int lo, int &p, bool &multi, bool &cont) {
     p = (int)((unsigned)pk & ((1u << ADJ_NODE_BITS) - 1u));
     const int dp = (int)((unsigned)(pk >> ADJ_NODE_BITS) & ADJ_LINK_SAT), dn = (int)(pk >> (ADJ_NODE_BITS + ADJ_LINK_BITS));
@@ -264,6 +293,7 @@ __global__ void __launch_bounds__(512) k_adj_build(const AdjBuildArgs a) {
     const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
     unsigned *curM = s_w + (size_t)wid * K;
     const unsigned lt = (1u << lane) - 1u;
+    const unsigned long long pol_rd = l2_policy_evict_first(), pol_wr = l2_policy_evict_last();
     for (;;) {
         __syncthreads();
         if (tid == 0) s_v = atomicAdd(a.next, 1);
@@ -280,13 +310,16 @@ __global__ void __launch_bounds__(512) k_adj_build(const AdjBuildArgs a) {
         // ---- A: counts (singles per CTA, run entries per warp)
         for (int e0 = ws; e0 < we; e0 += 32) {
             int my_i = 0, my_lo = 0;
-            if (e0 + lane < we) { my_i = a.order[e0 + lane]; my_lo = a.lo[my_i]; }  // 32 events' headers in one round trip
+            if (e0 + lane < we) {  // 32 events' headers in one round trip; their windows start towards L2
+                my_i = a.order[e0 + lane]; my_lo = a.lo[my_i];
+                for (int j = my_lo & ~15; j < my_i; j += 16) asm volatile("prefetch.global.L2 [%0];" ::"l"(a.pk + j));
+            }
             const int cnt = min(32, we - e0);
             for (int s = 0; s < cnt; s++) {
                 const int i = __shfl_sync(0xffffffffu, my_i, s), lo = __shfl_sync(0xffffffffu, my_lo, s);
                 for (int j = i - 1 - lane; j >= lo; j -= 64) {  // two rounds in flight
                     const int j2 = j - 32;
-                    const unsigned long long pk = __ldg(a.pk + j), pk2 = j2 >= lo ? __ldg(a.pk + j2) : 0ull;
+                    const unsigned long long pk = ldg_stream_u64(a.pk + j, pol_rd), pk2 = j2 >= lo ? ldg_stream_u64(a.pk + j2, pol_rd) : 0ull;
                     int p; bool multi, cont;
                     adj_pk_decode(pk, j, i, lo, p, multi, cont);
                     atomicAdd(multi ? &curM[p] : &s_curS[p], 1u);
@@ -334,7 +367,13 @@ __global__ void __launch_bounds__(512) k_adj_build(const AdjBuildArgs a) {
         for (int e0 = ws; e0 < we; e0 += 32) {
             int my_i = 0, my_lo = 0;
             double my_t = 0.0;
-            if (e0 + lane < we) { my_i = a.order[e0 + lane]; my_lo = a.lo[my_i]; my_t = a.t[my_i]; }
+            if (e0 + lane < we) {
+                my_i = a.order[e0 + lane]; my_lo = a.lo[my_i]; my_t = a.t[my_i];
+                for (int j = my_lo & ~15; j < my_i; j += 16) {
+                    asm volatile("prefetch.global.L2 [%0];" ::"l"(a.pk + j));
+                    asm volatile("prefetch.global.L2 [%0];" ::"l"(a.t + j));
+                }
+            }
             const int cnt = min(32, we - e0);
             for (int s = 0; s < cnt; s++) {
                 const int i = __shfl_sync(0xffffffffu, my_i, s), lo = __shfl_sync(0xffffffffu, my_lo, s);
@@ -344,13 +383,13 @@ __global__ void __launch_bounds__(512) k_adj_build(const AdjBuildArgs a) {
                 int j = i - 1 - lane;
                 unsigned long long pk = 0ull;
                 double tj = 0.0;
-                if (j >= lo) { pk = __ldg(a.pk + j); tj = __ldg(a.t + j); }
+                if (j >= lo) { pk = ldg_stream_u64(a.pk + j, pol_rd); tj = ldg_stream_f64(a.t + j, pol_rd); }
                 for (int j0 = i - 1; j0 >= lo; j0 -= 32) {
                     const int jc = j;
                     const unsigned long long pkc = pk;
                     const double tjc = tj;
                     j -= 32;
-                    if (j >= lo) { pk = __ldg(a.pk + j); tj = __ldg(a.t + j); }
+                    if (j >= lo) { pk = ldg_stream_u64(a.pk + j, pol_rd); tj = ldg_stream_f64(a.t + j, pol_rd); }
                     const bool valid = jc >= lo;
                     int p = -1 - lane;
                     bool multi = false, cont = false;
@@ -366,7 +405,7 @@ __global__ void __launch_bounds__(512) k_adj_build(const AdjBuildArgs a) {
                         __syncwarp();
                     }
                     if (valid) {
-                        ei[pos] = (unsigned short)(le | (cont ? 0x8000u : 0u));
+                        st_keep_u16(ei + pos, (unsigned short)(le | (cont ? 0x8000u : 0u)), pol_wr);
                         if (ey) {
                             const double b = a.D - dt;
                             double z = 0.0, q = 0.0;
@@ -375,8 +414,8 @@ __global__ void __launch_bounds__(512) k_adj_build(const AdjBuildArgs a) {
                                 z = log(dt / b);
                                 if (!(q <= 1.7976931348623157e308) || !(fabs(z) <= 1.7976931348623157e308)) { z = 0.0; q = 0.0; }  // lag so small that the pdf underflows
                             }
-                            ex[pos] = z; ey[pos] = q;
-                        } else ex[pos] = dt;
+                            st_keep_f64(ex + pos, z, pol_wr); st_keep_f64(ey + pos, q, pol_wr);
+                        } else st_keep_f64(ex + pos, dt, pol_wr);
                     }
                 }
             }
