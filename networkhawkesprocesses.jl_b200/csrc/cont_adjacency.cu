@@ -1022,7 +1022,7 @@ static int adj_build_structure(nhp_ctx *ctx, nhp_events *ev, double horizon, int
     const int64_t K = ctx->K, n = ev->n;
     cudaStream_t s = ctx->stream;
     AdjPhaseTimer tm(s);
-    nhp_events_free_adjacency(ev);
+    nhp_events_free_adjacency(ev, s);
     tm.lap("free old structure");
     std::vector<double> mn(K);
     ADJ_CUDA(cudaMemcpyAsync(mn.data(), ev->d_Mn, K * sizeof(double), cudaMemcpyDeviceToHost, s));
@@ -1051,12 +1051,12 @@ static int adj_build_structure(nhp_ctx *ctx, nhp_events *ev, double horizon, int
     if (nv == 0) return 1;
     int *d_vstart = nullptr, *d_vnode = nullptr, *d_lo = nullptr;
     unsigned long long *d_vcount = nullptr, *d_pk = nullptr;
-    auto drop = [&](int rc) { cudaFree(d_vstart); cudaFree(d_vnode); cudaFree(d_vcount); cudaFree(d_lo); cudaFree(d_pk); return rc; };
+    auto drop = [&](int rc) { cudaFreeAsync(d_vstart, s); cudaFreeAsync(d_vnode, s); cudaFreeAsync(d_vcount, s); cudaFreeAsync(d_lo, s); cudaFreeAsync(d_pk, s); return rc; };
 #define ADJ_B(call) do { cudaError_t e__ = (call); if (e__ != cudaSuccess) return drop(nhp_fail(ctx, NHP_ERR_CUDA, "%s failed: %s (%s:%d)", #call, cudaGetErrorString(e__), __FILE__, __LINE__)); } while (0)
-    ADJ_B(cudaMalloc(&d_vstart, (size_t)(K + 1) * sizeof(int)));
-    ADJ_B(cudaMalloc(&d_vnode, (size_t)nv * sizeof(int)));
-    ADJ_B(cudaMalloc(&d_vcount, (size_t)nv * sizeof(unsigned long long)));
-    ADJ_B(cudaMalloc(&d_lo, std::max<size_t>((size_t)n, 1) * sizeof(int)));
+    ADJ_B(cudaMallocAsync(&d_vstart, (size_t)(K + 1) * sizeof(int), s));
+    ADJ_B(cudaMallocAsync(&d_vnode, (size_t)nv * sizeof(int), s));
+    ADJ_B(cudaMallocAsync(&d_vcount, (size_t)nv * sizeof(unsigned long long), s));
+    ADJ_B(cudaMallocAsync(&d_lo, std::max<size_t>((size_t)n, 1) * sizeof(int), s));
     ADJ_B(cudaMemsetAsync(ctx->d_adj_ctl, 0, 8 * sizeof(int), s));
     ADJ_B(cudaMemcpyAsync(d_vstart, vstart.data(), (size_t)(K + 1) * sizeof(int), cudaMemcpyHostToDevice, s));
     ADJ_B(cudaMemcpyAsync(d_vnode, vnode.data(), (size_t)nv * sizeof(int), cudaMemcpyHostToDevice, s));
@@ -1088,6 +1088,14 @@ static int adj_build_structure(nhp_ctx *ctx, nhp_events *ev, double horizon, int
     // a quarter (payload: a third) of the free memory stays free for everything else
     size_t free_b = 0, total_b = 0;
     cudaMemGetInfo(&free_b, &total_b);
+    {   // blocks the stream-ordered pool keeps for reuse (a freed structure of the previous data set) are available to this one
+        cudaMemPool_t pool;
+        unsigned long long reserved = 0, used = 0;
+        if (cudaDeviceGetDefaultMemPool(&pool, ctx->device) == cudaSuccess &&
+            cudaMemPoolGetAttribute(pool, cudaMemPoolAttrReservedMemCurrent, &reserved) == cudaSuccess &&
+            cudaMemPoolGetAttribute(pool, cudaMemPoolAttrUsedMemCurrent, &used) == cudaSuccess && reserved > used)
+            free_b += (size_t)(reserved - used);
+    }
     const size_t fixed = (size_t)nv * (2 * K + 1) * sizeof(int) + (size_t)(nv + 1) * sizeof(int64_t) + (size_t)n * (sizeof(double) + sizeof(unsigned long long));
     bool pre = ctx->kind == NHP_LOGITNORMAL && (double)tot * 18.0 + (double)fixed <= 0.72 * (double)free_b;
     { const char *e = getenv("NHP_ADJ_PRE"); if (e) pre = pre && atoi(e) != 0; }
@@ -1097,22 +1105,22 @@ static int adj_build_structure(nhp_ctx *ctx, nhp_events *ev, double horizon, int
     if (nw < 4) nw = (int)std::min<int64_t>(16, ((int64_t)ctx->smem_optin - 2048 - (3 * K + 1) * 4) / (4 * K));
     // the packed predecessor record holds 20 bits of node and 22 bits of same-node distances: longer windows take the uncached sweep
     if ((double)need > 0.75 * (double)free_b || nw < 1 || K > (1 << ADJ_NODE_BITS) || max_win >= (int)ADJ_LINK_SAT) return drop(1);
-    cudaFree(d_vcount); d_vcount = nullptr;
-    ADJ_B(cudaMalloc(&d_pk, std::max<size_t>((size_t)n, 1) * sizeof(unsigned long long)));
+    cudaFreeAsync(d_vcount, s); d_vcount = nullptr;
+    ADJ_B(cudaMallocAsync(&d_pk, std::max<size_t>((size_t)n, 1) * sizeof(unsigned long long), s));
     if (n > 0) {
         k_adj_links<<<(unsigned)((n + 255) / 256), 256, 0, s>>>(ev->d_order, ev->d_node_ptr, ev->d_c, n, d_pk);
         NHP_LAUNCHED(ctx);
     }
     ev->d_adj_vstart = d_vstart; ev->d_adj_vnode = d_vnode; d_vstart = d_vnode = nullptr;  // owned by the handle from here on
-    auto fail = [&](int rc) { cudaFree(d_lo); cudaFree(d_pk); nhp_events_free_adjacency(ev); return rc; };
+    auto fail = [&](int rc) { cudaFreeAsync(d_lo, s); cudaFreeAsync(d_pk, s); nhp_events_free_adjacency(ev, s); return rc; };
 #define ADJ_S(call) do { cudaError_t e__ = (call); if (e__ != cudaSuccess) return fail(nhp_fail(ctx, NHP_ERR_CUDA, "%s failed: %s (%s:%d)", #call, cudaGetErrorString(e__), __FILE__, __LINE__)); } while (0)
-    ADJ_S(cudaMalloc(&ev->d_adj_vbase, (size_t)(nv + 1) * sizeof(int64_t)));
-    ADJ_S(cudaMalloc(&ev->d_adj_boff, (size_t)nv * (2 * K + 1) * sizeof(int)));
+    ADJ_S(cudaMallocAsync(&ev->d_adj_vbase, (size_t)(nv + 1) * sizeof(int64_t), s));
+    ADJ_S(cudaMallocAsync(&ev->d_adj_boff, (size_t)nv * (2 * K + 1) * sizeof(int), s));
     const size_t slack = 64 * 1024;  // entries: the sweeps' L2 prefetches run a few blocks ahead of the block they read
-    ADJ_S(cudaMalloc(&ev->d_adj_i, ((size_t)tot + slack) * sizeof(unsigned short)));
-    ADJ_S(cudaMalloc(&ev->d_adj_dt, ((size_t)tot + slack) * sizeof(double)));
-    if (pre) ADJ_S(cudaMalloc(&ev->d_adj_q, ((size_t)tot + slack) * sizeof(double)));
-    ADJ_S(cudaMalloc(&ev->d_adj_lam, std::max<size_t>((size_t)n, 1) * sizeof(double)));
+    ADJ_S(cudaMallocAsync(&ev->d_adj_i, ((size_t)tot + slack) * sizeof(unsigned short), s));
+    ADJ_S(cudaMallocAsync(&ev->d_adj_dt, ((size_t)tot + slack) * sizeof(double), s));
+    if (pre) ADJ_S(cudaMallocAsync(&ev->d_adj_q, ((size_t)tot + slack) * sizeof(double), s));
+    ADJ_S(cudaMallocAsync(&ev->d_adj_lam, std::max<size_t>((size_t)n, 1) * sizeof(double), s));
     tm.lap("links + allocation");
     ADJ_S(cudaMemcpyAsync(ev->d_adj_vbase, vbase.data(), (size_t)(nv + 1) * sizeof(int64_t), cudaMemcpyHostToDevice, s));
     ADJ_S(cudaMemsetAsync(ctx->d_adj_ctl, 0, 8 * sizeof(int), s));
@@ -1140,7 +1148,7 @@ static int adj_build_structure(nhp_ctx *ctx, nhp_events *ev, double horizon, int
     cudaEventElapsedTime(&bms, b0, b1);
     cudaEventDestroy(b0); cudaEventDestroy(b1);
     tm.lap("build kernel");
-    cudaFree(d_lo); cudaFree(d_pk); d_lo = nullptr; d_pk = nullptr;
+    cudaFreeAsync(d_lo, s); cudaFreeAsync(d_pk, s); d_lo = nullptr; d_pk = nullptr;
     tm.lap("free temporaries");
     if (flag & 128) return fail(nhp_fail(ctx, NHP_ERR_CUDA, "adjacency sampler: structure build disagrees with its own count (internal error)"));
     ev->adj_total = tot; ev->adj_pairs = pairs; ev->adj_nv = nv; ev->adj_horizon = horizon; ev->adj_cb = cb; ev->adj_cs = cs;

@@ -145,15 +145,15 @@ int nhp_events_build_node_index(nhp_ctx *ctx, nhp_events *ev) {
     void *d_tmp = nullptr;
     // every failure path releases the temporaries and leaves the handle without a (partial) index
     auto fail = [&](cudaError_t e, const char *what) {
-        cudaFree(d_vals); cudaFree(d_keys); cudaFree(d_tmp);
-        cudaFree(ev->d_order); cudaFree(ev->d_node_ptr); cudaFree(ev->d_item_node); cudaFree(ev->d_item_e0);
+        cudaFreeAsync(d_vals, s); cudaFreeAsync(d_keys, s); cudaFreeAsync(d_tmp, s);
+        cudaFreeAsync(ev->d_order, s); cudaFreeAsync(ev->d_node_ptr, s); cudaFreeAsync(ev->d_item_node, s); cudaFreeAsync(ev->d_item_e0, s);
         ev->d_order = ev->d_node_ptr = ev->d_item_node = ev->d_item_e0 = nullptr;
         return nhp_fail(ctx, NHP_ERR_CUDA, "node index: %s failed: %s", what, cudaGetErrorString(e));
     };
 #define NI_CUDA(call) do { cudaError_t e__ = (call); if (e__ != cudaSuccess) return fail(e__, #call); } while (0)
-    NI_CUDA(cudaMalloc(&ev->d_order, (size_t)std::max<int64_t>(own, 1) * sizeof(int)));
-    NI_CUDA(cudaMalloc(&d_vals, (size_t)std::max<int64_t>(own, 1) * sizeof(int)));
-    NI_CUDA(cudaMalloc(&d_keys, (size_t)std::max<int64_t>(own, 1) * sizeof(int)));
+    NI_CUDA(cudaMallocAsync(&ev->d_order, (size_t)std::max<int64_t>(own, 1) * sizeof(int), s));
+    NI_CUDA(cudaMallocAsync(&d_vals, (size_t)std::max<int64_t>(own, 1) * sizeof(int), s));
+    NI_CUDA(cudaMallocAsync(&d_keys, (size_t)std::max<int64_t>(own, 1) * sizeof(int), s));
     if (own > 0) {
         k_child_iota<<<(unsigned)((own + 255) / 256), 256, 0, s>>>(d_vals, own, (int)ev->n_halo);
         NHP_LAUNCHED(ctx);
@@ -161,14 +161,14 @@ int nhp_events_build_node_index(nhp_ctx *ctx, nhp_events *ev) {
         while ((1 << bits) < K) bits++;
         size_t tb = 0;
         cub::DeviceRadixSort::SortPairs(nullptr, tb, ev->d_c + ev->n_halo, d_keys, d_vals, ev->d_order, (int)own, 0, bits, s);
-        NI_CUDA(cudaMalloc(&d_tmp, tb));
+        NI_CUDA(cudaMallocAsync(&d_tmp, tb, s));
         NI_CUDA(cub::DeviceRadixSort::SortPairs(d_tmp, tb, ev->d_c + ev->n_halo, d_keys, d_vals, ev->d_order, (int)own, 0, bits, s));  // stable
         NHP_LAUNCHED(ctx);
     }
     std::vector<double> mn(K);
     NI_CUDA(cudaMemcpyAsync(mn.data(), ev->d_Mn, (size_t)K * sizeof(double), cudaMemcpyDeviceToHost, s));
     NI_CUDA(cudaStreamSynchronize(s));
-    cudaFree(d_vals); cudaFree(d_keys); cudaFree(d_tmp);
+    cudaFreeAsync(d_vals, s); cudaFreeAsync(d_keys, s); cudaFreeAsync(d_tmp, s);  // stream-ordered pool: no device synchronisation
     d_vals = d_keys = nullptr; d_tmp = nullptr;
     std::vector<int> ptr(K + 1), inode, ie0;
     int run = 0;
@@ -180,14 +180,15 @@ int nhp_events_build_node_index(nhp_ctx *ctx, nhp_events *ev) {
     }
     ptr[K] = run;
     ev->n_items = (int64_t)inode.size();
-    NI_CUDA(cudaMalloc(&ev->d_node_ptr, (size_t)(K + 1) * sizeof(int)));
-    NI_CUDA(cudaMalloc(&ev->d_item_node, std::max<size_t>(inode.size(), 1) * sizeof(int)));
-    NI_CUDA(cudaMalloc(&ev->d_item_e0, std::max<size_t>(inode.size(), 1) * sizeof(int)));
-    NI_CUDA(cudaMemcpy(ev->d_node_ptr, ptr.data(), (size_t)(K + 1) * sizeof(int), cudaMemcpyHostToDevice));
+    NI_CUDA(cudaMallocAsync(&ev->d_node_ptr, (size_t)(K + 1) * sizeof(int), s));
+    NI_CUDA(cudaMallocAsync(&ev->d_item_node, std::max<size_t>(inode.size(), 1) * sizeof(int), s));
+    NI_CUDA(cudaMallocAsync(&ev->d_item_e0, std::max<size_t>(inode.size(), 1) * sizeof(int), s));
+    NI_CUDA(cudaMemcpyAsync(ev->d_node_ptr, ptr.data(), (size_t)(K + 1) * sizeof(int), cudaMemcpyHostToDevice, s));
     if (!inode.empty()) {
-        NI_CUDA(cudaMemcpy(ev->d_item_node, inode.data(), inode.size() * sizeof(int), cudaMemcpyHostToDevice));
-        NI_CUDA(cudaMemcpy(ev->d_item_e0, ie0.data(), ie0.size() * sizeof(int), cudaMemcpyHostToDevice));
+        NI_CUDA(cudaMemcpyAsync(ev->d_item_node, inode.data(), inode.size() * sizeof(int), cudaMemcpyHostToDevice, s));
+        NI_CUDA(cudaMemcpyAsync(ev->d_item_e0, ie0.data(), ie0.size() * sizeof(int), cudaMemcpyHostToDevice, s));
     }
+    NI_CUDA(cudaStreamSynchronize(s));  // the host vectors go out of scope
 #undef NI_CUDA
     return NHP_OK;
 }

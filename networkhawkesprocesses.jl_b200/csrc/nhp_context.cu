@@ -286,9 +286,10 @@ int nhp_events_from_device(nhp_ctx *ctx, const double *d_t, const int *d_c, int6
 }
 
 // cached structure of the adjacency sampler (cont_adjacency.cu)
-void nhp_events_free_adjacency(nhp_events *ev) {
-    cudaFree(ev->d_adj_vstart); cudaFree(ev->d_adj_vnode); cudaFree(ev->d_adj_vbase); cudaFree(ev->d_adj_boff);
-    cudaFree(ev->d_adj_i); cudaFree(ev->d_adj_dt); cudaFree(ev->d_adj_q); cudaFree(ev->d_adj_lam);
+void nhp_events_free_adjacency(nhp_events *ev, cudaStream_t s) {
+    // stream-ordered: the blocks (up to 100+ GB) go back to the pool without a device synchronisation and serve the next structure
+    void *blocks[] = {ev->d_adj_vstart, ev->d_adj_vnode, ev->d_adj_vbase, ev->d_adj_boff, ev->d_adj_i, ev->d_adj_dt, ev->d_adj_q, ev->d_adj_lam};
+    for (void *b : blocks) if (b) cudaFreeAsync(b, s);
     ev->d_adj_vstart = ev->d_adj_vnode = ev->d_adj_boff = nullptr; ev->d_adj_vbase = nullptr; ev->d_adj_i = nullptr;
     ev->d_adj_dt = ev->d_adj_q = ev->d_adj_lam = nullptr;
     ev->adj_horizon = -1.0; ev->adj_total = 0; ev->adj_nv = 0;
@@ -308,8 +309,12 @@ extern "C" int nhp_events_free(nhp_ctx *ctx, nhp_events *ev) {
     } else {
         cudaFree(ev->d_t); cudaFree(ev->d_c); cudaFree(ev->d_poff); cudaFree(ev->d_Mn); cudaFree(ev->d_tile_lo); cudaFree(ev->d_wlen);
     }
-    cudaFree(ev->d_order); cudaFree(ev->d_node_ptr); cudaFree(ev->d_item_node); cudaFree(ev->d_item_e0);
-    nhp_events_free_adjacency(ev);
+    {
+        cudaStream_t as = ctx ? ctx->stream : nullptr;
+        void *blocks[] = {ev->d_order, ev->d_node_ptr, ev->d_item_node, ev->d_item_e0};
+        for (void *b : blocks) if (b) cudaFreeAsync(b, as);
+    }
+    nhp_events_free_adjacency(ev, ctx ? ctx->stream : nullptr);
     delete ev;
     return NHP_OK;
 }

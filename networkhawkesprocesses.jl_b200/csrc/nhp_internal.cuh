@@ -276,4 +276,4 @@ int nhp_cont_prepare_windows(nhp_ctx *ctx, nhp_events *ev, double horizon);
 int nhp_cont_run_loglik(nhp_ctx *ctx, nhp_events *ev, int recursive);
 double nhp_cont_horizon_value(const nhp_ctx *ctx, int64_t n_total, int recursive);
 int nhp_events_build_node_index(nhp_ctx *ctx, nhp_events *ev);  // d_order / d_node_ptr (cont_child.cu)
-void nhp_events_free_adjacency(nhp_events *ev);                 // cached structure of the adjacency sampler (nhp_context.cu)
+void nhp_events_free_adjacency(nhp_events *ev, cudaStream_t s);                 // cached structure of the adjacency sampler (nhp_context.cu)
