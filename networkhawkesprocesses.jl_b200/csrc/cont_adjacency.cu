@@ -230,7 +230,7 @@ struct AdjBuildArgs {
     const double *t; const unsigned long long *pk; const int *lo; const int *order, *node_ptr;
     int K; double D;
     const int *vstart, *vnode; const int64_t *vbase;
-    int *boff; unsigned short *ent_i; double *ent_x, *ent_y;   // ent_y != NULL: LogitNormal payload (logit, Jacobian) instead of the lag
+    int *boff; unsigned short *ent_i; double *ent_x; int pre;   // pre: LogitNormal payload (logit, Jacobian), one 16-byte record per entry, instead of the lag
     int nv, nw;      // virtual columns; warps per CTA
     int *next, *flag;
 };
@@ -271,6 +271,9 @@ __device__ __forceinline__ double ldg_stream_f64(const double *p, unsigned long 
 }
 __device__ __forceinline__ void st_keep_f64(double *p, double v, unsigned long long pol) {
     asm volatile("st.global.L2::cache_hint.f64 [%0], %1, %2;" ::"l"(p), "d"(v), "l"(pol) : "memory");
+}
+__device__ __forceinline__ void st_keep_f64x2(double *p, double v0, double v1, unsigned long long pol) {
+    asm volatile("st.global.L2::cache_hint.v2.f64 [%0], {%1, %2}, %3;" ::"l"(p), "d"(v0), "d"(v1), "l"(pol) : "memory");
 }
 __device__ __forceinline__ void st_keep_u16(unsigned short *p, unsigned short v, unsigned long long pol) {
     asm volatile("st.global.L2::cache_hint.u16 [%0], %1, %2;" ::"l"(p), "h"(v), "l"(pol) : "memory");
@@ -362,8 +365,7 @@ __global__ void __launch_bounds__(512) k_adj_build(const AdjBuildArgs a) {
         __syncthreads();
         // ---- B: scatter, one pass over every window
         unsigned short *ei = a.ent_i + a.vbase[v];
-        double *ex = a.ent_x + a.vbase[v];
-        double *ey = a.ent_y ? a.ent_y + a.vbase[v] : nullptr;
+        double *ex = a.ent_x + (a.pre ? 2 : 1) * a.vbase[v];
         for (int e0 = ws; e0 < we; e0 += 32) {
             int my_i = 0, my_lo = 0;
             double my_t = 0.0;
@@ -406,7 +408,7 @@ __global__ void __launch_bounds__(512) k_adj_build(const AdjBuildArgs a) {
                     }
                     if (valid) {
                         st_keep_u16(ei + pos, (unsigned short)(le | (cont ? 0x8000u : 0u)), pol_wr);
-                        if (ey) {
+                        if (a.pre) {
                             const double b = a.D - dt;
                             double z = 0.0, q = 0.0;
                             if (dt > 0.0 && b > 0.0) {  // Distributions.pdf(LogitNormal, x) is zero outside 0 < x < 1 (impulses.jl:174-178)
@@ -414,7 +416,7 @@ __global__ void __launch_bounds__(512) k_adj_build(const AdjBuildArgs a) {
                                 z = log(dt / b);
                                 if (!(q <= 1.7976931348623157e308) || !(fabs(z) <= 1.7976931348623157e308)) { z = 0.0; q = 0.0; }  // lag so small that the pdf underflows
                             }
-                            st_keep_f64(ex + pos, z, pol_wr); st_keep_f64(ey + pos, q, pol_wr);
+                            st_keep_f64x2(ex + 2 * (size_t)pos, z, q, pol_wr);
                         } else st_keep_f64(ex + pos, dt, pol_wr);
                     }
                 }
@@ -427,7 +429,7 @@ __global__ void __launch_bounds__(512) k_adj_build(const AdjBuildArgs a) {
             const int beg = (k & 1) ? (int)s_w[(size_t)(nw - 1) * K + p] : (int)s_curS[p];  // true end: the CTA cursor | the last warp's cursor
             for (int e = beg; e < s_off[k + 1]; e++) {
                 ei[e] = 0;
-                if (ey) { ex[e] = 0.0; ey[e] = 0.0; } else ex[e] = -1.0;
+                if (a.pre) { ex[2 * (size_t)e] = 0.0; ex[2 * (size_t)e + 1] = 0.0; } else ex[e] = -1.0;
             }
         }
     }
@@ -450,7 +452,7 @@ struct AdjSweepArgs {
     const double *lambda0; double *A;   // A: [K*K] parent-major, device, updated in place
     const double4 *dec;    // [K*K] per link: W Mn[p], logit(rho), u, logit(u)  (k_adj_prep)
     double D;
-    const int *vstart; const int64_t *vbase; const int *boff; const unsigned short *ent_i; const double *ent_x, *ent_y;
+    const int *vstart; const int64_t *vbase; const int *boff; const unsigned short *ent_i; const double *ent_x;   // PRE: ent_x holds (logit, Jacobian) pairs
     double *lam;           // [n] by-node order (only used when a column's chunks do not all sit in shared memory)
     int chunk_max;         // doubles of shared memory in front of the adjacency bit row
     int *flag, *next; unsigned long long *stat;
@@ -481,11 +483,30 @@ template <> __device__ __forceinline__ double adj_value<NHP_LOGITNORMAL, 1>(cons
     return (en.cf * y) * fast_exp_c(-(en.h * dz) * dz, ft);  // exponent <= 0: no overflow branch; flushes to 0 below -707
 }
 
+// payload of entry k.  PRE: the 16-byte record (x, y) at ex[2k], one 128-bit load; else the lag at ex[k]
+template <int PRE> __device__ __forceinline__ void adj_ld(const double *__restrict__ ex, int k, double &x, double &y) {
+    if (PRE) { const double2 v = __ldg(reinterpret_cast<const double2 *>(ex) + k); x = v.x; y = v.y; }
+    else { x = __ldg(ex + k); y = 0.0; }
+}
+// payloads of the entries k (even) and k + 1: one 256-bit (PRE) or 128-bit load
+template <int PRE> __device__ __forceinline__ void adj_ld2(const double *__restrict__ ex, int k, double2 &x, double2 &y) {
+    if (PRE) asm("ld.global.nc.v4.f64 {%0,%1,%2,%3}, [%4];" : "=d"(x.x), "=d"(y.x), "=d"(x.y), "=d"(y.y) : "l"(ex + 2 * (size_t)k));
+    else x = __ldg(reinterpret_cast<const double2 *>(ex + k));
+}
+// L2 prefetch of the entries [f0, f1) of one virtual column by the whole CTA (one 128-byte line per thread and step)
+template <int PRE> __device__ __forceinline__ void adj_pf_range(const unsigned short *ei, const double *ex, int f0, int f1, int tid) {
+    constexpr int per = PRE ? 8 : 16;  // entries per line of the payload
+    for (int e = f0 + tid * per; e < f1; e += ADJ_THREADS * per) {
+        asm volatile("prefetch.global.L2 [%0];" ::"l"(ex + (PRE ? 2 : 1) * (size_t)e));
+        if (((e - f0) & 63) == 0) asm volatile("prefetch.global.L2 [%0];" ::"l"(ei + e));
+    }
+}
+
 // One group of 32 consecutive entries [eb, eb + 32) of a run section that ends at b1, one entry per lane: the impulse value of
 // every entry and, for the first entry of each (event, parent) run (the "head"), the run's total.  Returns head.
 template <int KIND, int PRE>
 __device__ __forceinline__ bool adj_group(const typename EntryOf<KIND>::type &en, const unsigned short *__restrict__ ei, const double *__restrict__ ex,
-                                          const double *__restrict__ ey, int eb, int b1, int lane, unsigned ii, double x, double y, double D,
+                                          int eb, int b1, int lane, unsigned ii, double x, double y, double D,
                                           const FastTables *ft, double &gsum) {
     const bool valid = eb + lane < b1;
     double v = adj_value<KIND, PRE>(en, x, y, D, ft);
@@ -506,7 +527,7 @@ __device__ __forceinline__ bool adj_group(const typename EntryOf<KIND>::type &en
     if (eb + 32 < b1) {  // warp-uniform: does the run that reaches lane 31 go on in the section's next group?  (one broadcast load)
         if (__ldg(ei + eb + 32) & 0x8000u) {
             if (head && lane + runlen == 31)
-                for (int e2 = eb + 32; e2 < b1 && (__ldg(ei + e2) & 0x8000u); e2++) gsum += adj_value<KIND, PRE>(en, __ldg(ex + e2), PRE ? __ldg(ey + e2) : 0.0, D, ft);
+                for (int e2 = eb + 32; e2 < b1 && (__ldg(ei + e2) & 0x8000u); e2++) { double x2, y2; adj_ld<PRE>(ex, e2, x2, y2); gsum += adj_value<KIND, PRE>(en, x2, y2, D, ft); }
         }
     }
     return head;
@@ -552,15 +573,14 @@ __device__ __forceinline__ void acc_factor2(AdjAcc &A, double v0, double l0, dou
 // singles of one bucket: this warp takes the blocks of 64 entries that start at gb, gb + stride, ... below s1 (sections are whole groups
 // of 32 entries, 32-entry aligned: a lane reads entries 2 lane, 2 lane + 1 of its block with one 32-bit and two 128-bit loads; the last
 // block may be half a block); one block ahead in flight.  Padding entries evaluate to zero and contribute the factor 1.
-// L2 prefetch of the 64-entry block that starts at entry kb: lanes 0-1 take the two 64-byte halves of the indices, lanes 2-9 / 10-17 the
-// 64-byte pieces of the two payload arrays (one instruction per block; the arrays carry slack behind their last entry)
+// L2 prefetch of the 64-entry block that starts at entry kb: lanes 0-1 take the two 64-byte halves of the indices, lanes 2-9 (2-17 with
+// the 16-byte payload) the 64-byte pieces of the payload (one instruction per block; the arrays carry slack behind their last entry)
 struct AdjPf { const char *base; int scale; };
-__device__ __forceinline__ AdjPf adj_pf_setup(const unsigned short *ei, const double *ex, const double *ey, int lane) {
+template <int PRE> __device__ __forceinline__ AdjPf adj_pf_setup(const unsigned short *ei, const double *ex, int lane) {
     AdjPf f;
     f.base = nullptr; f.scale = 0;
     if (lane < 2) { f.base = reinterpret_cast<const char *>(ei) + lane * 64; f.scale = 2; }
-    else if (lane < 10) { f.base = reinterpret_cast<const char *>(ex) + (lane - 2) * 64; f.scale = 8; }
-    else if (lane < 18 && ey) { f.base = reinterpret_cast<const char *>(ey) + (lane - 10) * 64; f.scale = 8; }
+    else if (lane < (PRE ? 18 : 10)) { f.base = reinterpret_cast<const char *>(ex) + (lane - 2) * 64; f.scale = PRE ? 16 : 8; }
     return f;
 }
 __device__ __forceinline__ void adj_pf(const AdjPf &f, int kb) {
@@ -569,17 +589,14 @@ __device__ __forceinline__ void adj_pf(const AdjPf &f, int kb) {
 
 template <int KIND, int PRE>
 __device__ __forceinline__ void adj_singles(const typename EntryOf<KIND>::type &en, const unsigned short *__restrict__ ei, const double *__restrict__ ex,
-                                            const double *__restrict__ ey, int gb, const int s1, const int stride, const int lane, const double onf,
+                                            int gb, const int s1, const int stride, const int lane, const double onf,
                                             const double floor_, const double D, const double *lam_s, const FastTables *ft, const AdjPf &pf, AdjAcc &A) {
     const double xdef = PRE ? 0.0 : -1.0;
     adj_pf(pf, gb + stride); adj_pf(pf, gb + 2 * stride);
     int k = gb + 2 * lane;
     unsigned iw = 0u;
     double2 xw = make_double2(xdef, xdef), yw = make_double2(0.0, 0.0);
-    if (k < s1) {
-        iw = __ldg(reinterpret_cast<const unsigned *>(ei + k)); xw = __ldg(reinterpret_cast<const double2 *>(ex + k));
-        if (PRE) yw = __ldg(reinterpret_cast<const double2 *>(ey + k));
-    }
+    if (k < s1) { iw = __ldg(reinterpret_cast<const unsigned *>(ei + k)); adj_ld2<PRE>(ex, k, xw, yw); }
     while (gb < s1) {
 #pragma unroll 1
         for (int u = 0; u < ADJ_RENORM / 2; u++) {
@@ -588,10 +605,7 @@ __device__ __forceinline__ void adj_singles(const typename EntryOf<KIND>::type &
             adj_pf(pf, gb + 3 * stride);  // in L2 by the time the register load two blocks later asks for it
             k += stride;
             iw = 0u; xw = make_double2(xdef, xdef); yw = make_double2(0.0, 0.0);
-            if (k < s1) {
-                iw = __ldg(reinterpret_cast<const unsigned *>(ei + k)); xw = __ldg(reinterpret_cast<const double2 *>(ex + k));
-                if (PRE) yw = __ldg(reinterpret_cast<const double2 *>(ey + k));
-            }
+            if (k < s1) { iw = __ldg(reinterpret_cast<const unsigned *>(ei + k)); adj_ld2<PRE>(ex, k, xw, yw); }
             const double v0 = adj_value<KIND, PRE>(en, x.x, y.x, D, ft), v1 = adj_value<KIND, PRE>(en, x.y, y.y, D, ft);
             acc_factor2(A, v0, lam_s[ii & 0xffffu], v1, lam_s[ii >> 16], onf, floor_);
             gb += stride;
@@ -604,7 +618,7 @@ __device__ __forceinline__ void adj_singles(const typename EntryOf<KIND>::type &
 // run section of one bucket (general form: several entries of one (event, parent))
 template <int KIND, int PRE>
 __device__ __forceinline__ void adj_runs(const typename EntryOf<KIND>::type &en, const unsigned short *__restrict__ ei, const double *__restrict__ ex,
-                                         const double *__restrict__ ey, int eb, const int b1, const int stride, const int lane, const double onf,
+                                         int eb, const int b1, const int stride, const int lane, const double onf,
                                          const double floor_, const double D, const double *lam_s, const FastTables *ft, AdjAcc &A) {
     const double xdef = PRE ? 0.0 : -1.0;
     while (eb < b1) {
@@ -612,9 +626,10 @@ __device__ __forceinline__ void adj_runs(const typename EntryOf<KIND>::type &en,
         for (int u = 0; u < ADJ_RENORM; u++) {
             const bool valid = eb + lane < b1;
             const unsigned ii = valid ? (unsigned)__ldg(ei + eb + lane) : 0u;
-            const double x = valid ? __ldg(ex + eb + lane) : xdef, y = (PRE && valid) ? __ldg(ey + eb + lane) : 0.0;
+            double x = xdef, y = 0.0;
+            if (valid) adj_ld<PRE>(ex, eb + lane, x, y);
             double gs;
-            const bool head = adj_group<KIND, PRE>(en, ei, ex, ey, eb, b1, lane, ii, x, y, D, ft, gs);
+            const bool head = adj_group<KIND, PRE>(en, ei, ex, eb, b1, lane, ii, x, y, D, ft, gs);
             acc_factor(A, head ? gs : 0.0, lam_s[ii & 0x7fffu], onf, floor_);
             eb += stride;
             if (eb >= b1) break;
@@ -627,16 +642,17 @@ __device__ __forceinline__ void adj_runs(const typename EntryOf<KIND>::type &en,
 // run of one -- with one log per event; extreme or non-positive intensities end up here and a NaN surfaces as NHP_ERR_NUMERIC
 template <int KIND, int PRE>
 __device__ __noinline__ double2 adj_direct(const typename EntryOf<KIND>::type en, const unsigned short *__restrict__ ei, const double *__restrict__ ex,
-                                           const double *__restrict__ ey, int eb, const int b1, const int stride, const int lane, const double onf,
+                                           int eb, const int b1, const int stride, const int lane, const double onf,
                                            const double floor_, const double D, const double *lam_s, const FastTables *ft) {  // (sum of log terms, largest contribution)
     const double xdef = PRE ? 0.0 : -1.0;
     double acc = 0.0, gmx = 0.0;
     for (; eb < b1; eb += stride) {
         const bool valid = eb + lane < b1;
         const unsigned ii = valid ? (unsigned)__ldg(ei + eb + lane) : 0u;
-        const double x = valid ? __ldg(ex + eb + lane) : xdef, y = (PRE && valid) ? __ldg(ey + eb + lane) : 0.0;
+        double x = xdef, y = 0.0;
+        if (valid) adj_ld<PRE>(ex, eb + lane, x, y);
         double gs;
-        if (adj_group<KIND, PRE>(en, ei, ex, ey, eb, b1, lane, ii, x, y, D, ft, gs) && gs > 0.0) {
+        if (adj_group<KIND, PRE>(en, ei, ex, eb, b1, lane, ii, x, y, D, ft, gs) && gs > 0.0) {
             const double l = lam_s[ii & 0x7fffu], t = fma(-onf, gs, l), base = t > floor_ ? t : floor_;
             acc += log((base + gs) / base);
             gmx = fmax(gmx, gs);
@@ -648,19 +664,22 @@ __device__ __noinline__ double2 adj_direct(const typename EntryOf<KIND>::type en
 // add sgn * (this parent's contribution) to the intensities of a bucket's events: all warps of the CTA, groups warp, warp + 32, ...
 template <int KIND, int PRE>
 __device__ __forceinline__ void adj_apply(const typename EntryOf<KIND>::type &en, const unsigned short *__restrict__ ei, const double *__restrict__ ex,
-                                          const double *__restrict__ ey, const int s0, const int sm, const int s1, const int warp, const int lane,
+                                          const int s0, const int sm, const int s1, const int warp, const int lane,
                                           const double sgn, double *lam, const double D, const FastTables *ft) {
     for (int k = s0 + warp * 32 + lane; k < sm; k += ADJ_THREADS) {  // singles: distinct events, no bookkeeping
         const unsigned ii = __ldg(ei + k);
-        const double v = adj_value<KIND, PRE>(en, __ldg(ex + k), PRE ? __ldg(ey + k) : 0.0, D, ft);
+        double x, y;
+        adj_ld<PRE>(ex, k, x, y);
+        const double v = adj_value<KIND, PRE>(en, x, y, D, ft);
         if (v > 0.0) lam[ii] += sgn * v;
     }
     for (int eb = sm + warp * 32; eb < s1; eb += ADJ_THREADS) {      // runs: the head carries the run's total
         const bool valid = eb + lane < s1;
         const unsigned ii = valid ? (unsigned)__ldg(ei + eb + lane) : 0u;
-        const double x = valid ? __ldg(ex + eb + lane) : (PRE ? 0.0 : -1.0), y = (PRE && valid) ? __ldg(ey + eb + lane) : 0.0;
+        double x = PRE ? 0.0 : -1.0, y = 0.0;
+        if (valid) adj_ld<PRE>(ex, eb + lane, x, y);
         double gs;
-        if (adj_group<KIND, PRE>(en, ei, ex, ey, eb, s1, lane, ii, x, y, D, ft, gs) && gs > 0.0) lam[ii & 0x7fffu] += sgn * gs;
+        if (adj_group<KIND, PRE>(en, ei, ex, eb, s1, lane, ii, x, y, D, ft, gs) && gs > 0.0) lam[ii & 0x7fffu] += sgn * gs;
     }
 }
 
@@ -722,7 +741,7 @@ template <int KIND, int PRE, bool CL> __global__ void __launch_bounds__(ADJ_THRE
             const int *bo = a.boff + (int64_t)(v0 + g) * brow;
             const int64_t vb = a.vbase[v0 + g];
             const unsigned short *ei = a.ent_i + vb;
-            const double *ex = a.ent_x + vb, *ey = PRE ? a.ent_y + vb : nullptr;
+            const double *ex = a.ent_x + (PRE ? 2 : 1) * vb;
             // the links that are on, listed (the exchange buffers are idle here) so that the bucket two links ahead can be pulled into L2
             // (the half the peers do not write before the next cluster barrier: they fill [parity] at the end of their first batch)
             int *s_on = reinterpret_cast<int *>(&s_cl[parity ^ 1u][0][0]);
@@ -742,18 +761,14 @@ template <int KIND, int PRE, bool CL> __global__ void __launch_bounds__(ADJ_THRE
                         for (int r = 0; r < (j == 0 ? 2 : 1); r++) {
                             const int pp = r == 0 ? pn : pa;
                             const int f0 = bo[2 * pp], f1 = bo[2 * pp + 2];
-                            for (int e = f0 + tid * 16; e < f1; e += ADJ_THREADS * 16) {  // 16 entries = one 128-byte line of an f64 payload
-                                asm volatile("prefetch.global.L2 [%0];" ::"l"(ex + e));
-                                if (PRE) asm volatile("prefetch.global.L2 [%0];" ::"l"(ey + e));
-                                if ((e & 63) == (f0 & 63)) asm volatile("prefetch.global.L2 [%0];" ::"l"(ei + e));
-                            }
+                            adj_pf_range<PRE>(ei, ex, f0, f1, tid);
                         }
                     }
                     const int p = s_on[j];
                     const int b0 = bo[2 * p], bm = bo[2 * p + 1], b1 = bo[2 * p + 2];
                     if (b1 != b0) {
                         const E en = load_entry(col + p);
-                        adj_apply<KIND, PRE>(en, ei, ex, ey, b0, bm, b1, warp, lane, 1.0, lam_s, a.D, ft);  // one head per event and bucket
+                        adj_apply<KIND, PRE>(en, ei, ex, b0, bm, b1, warp, lane, 1.0, lam_s, a.D, ft);  // one head per event and bucket
                     }
                     __syncthreads();  // the next parent may touch the same events
                 }
@@ -789,11 +804,7 @@ template <int KIND, int PRE, bool CL> __global__ void __launch_bounds__(ADJ_THRE
                 const int q0 = min(p + Sc, K), q1 = min(p + Sc + 2 * S + 2, K);
                 const int64_t vb = a.vbase[v0 + g];
                 const int f0 = bo[2 * q0], f1 = bo[2 * q1];
-                for (int e = f0 + tid * 16; e < f1; e += ADJ_THREADS * 16) {  // 16 entries = one 128-byte line of the f64 payload
-                    asm volatile("prefetch.global.L2 [%0];" ::"l"(a.ent_x + vb + e));
-                    if (PRE) asm volatile("prefetch.global.L2 [%0];" ::"l"(a.ent_y + vb + e));
-                    if ((e & 63) == (f0 & 63)) asm volatile("prefetch.global.L2 [%0];" ::"l"(a.ent_i + vb + e));
-                }
+                adj_pf_range<PRE>(a.ent_i + vb, a.ent_x + (PRE ? 2 : 1) * vb, f0, f1, tid);
             }
             double acc = 0.0, gmx = 0.0;
             for (int g = g_lo; g < g_hi; g++) {
@@ -808,23 +819,23 @@ template <int KIND, int PRE, bool CL> __global__ void __launch_bounds__(ADJ_THRE
                     const int b0 = bo[2 * q], bm = bo[2 * q + 1], b1 = bo[2 * q + 2];
                     const int64_t vb = a.vbase[v0 + g];
                     const unsigned short *ei = a.ent_i + vb;
-                    const double *ex = a.ent_x + vb, *ey = PRE ? a.ent_y + vb : nullptr;
-                    const AdjPf pf = adj_pf_setup(ei, ex, ey, lane);
+                    const double *ex = a.ent_x + (PRE ? 2 : 1) * vb;
+                    const AdjPf pf = adj_pf_setup<PRE>(ei, ex, lane);
                     if (q + Sc < K) {  // the bucket this warp takes if the whole batch is accepted: its first blocks go to L2 now
                         const int nb = bo[2 * (q + Sc)] + sub * 64;
                         adj_pf(pf, nb); adj_pf(pf, nb + nsub * 64);
                     }
                     AdjAcc A;
                     acc_init(A);
-                    adj_singles<KIND, PRE>(en, ei, ex, ey, b0 + sub * 64, bm, nsub * 64, lane, onf, floor_, a.D, lam_s, ft, pf, A);
-                    adj_runs<KIND, PRE>(en, ei, ex, ey, bm + sub * 32, b1, nsub * 32, lane, onf, floor_, a.D, lam_s, ft, A);
+                    adj_singles<KIND, PRE>(en, ei, ex, b0 + sub * 64, bm, nsub * 64, lane, onf, floor_, a.D, lam_s, ft, pf, A);
+                    adj_runs<KIND, PRE>(en, ei, ex, bm + sub * 32, b1, nsub * 32, lane, onf, floor_, a.D, lam_s, ft, A);
                     if (__all_sync(0xffffffffu, acc_in_range(A))) {
                         acc += (fast_log_n(A.num, ft) - fast_log_n(A.den, ft)) + (double)A.bal * 0.6931471805599453;
                         if (A.gm > 0) gmx = fmax(gmx, __hiloint2double(A.gm + 1, 0));  // upper bound of the largest contribution
                     } else {  // warp-uniform, rare
-                        const double2 d0 = adj_direct<KIND, PRE>(en, ei, ex, ey, b0 + sub * 64, bm, nsub * 64, lane, onf, floor_, a.D, lam_s, ft);  // the same blocks, half by half
-                        const double2 d1 = adj_direct<KIND, PRE>(en, ei, ex, ey, b0 + sub * 64 + 32, bm, nsub * 64, lane, onf, floor_, a.D, lam_s, ft);
-                        const double2 d2 = adj_direct<KIND, PRE>(en, ei, ex, ey, bm + sub * 32, b1, nsub * 32, lane, onf, floor_, a.D, lam_s, ft);
+                        const double2 d0 = adj_direct<KIND, PRE>(en, ei, ex, b0 + sub * 64, bm, nsub * 64, lane, onf, floor_, a.D, lam_s, ft);  // the same blocks, half by half
+                        const double2 d1 = adj_direct<KIND, PRE>(en, ei, ex, b0 + sub * 64 + 32, bm, nsub * 64, lane, onf, floor_, a.D, lam_s, ft);
+                        const double2 d2 = adj_direct<KIND, PRE>(en, ei, ex, bm + sub * 32, b1, nsub * 32, lane, onf, floor_, a.D, lam_s, ft);
                         acc += d0.x + d1.x + d2.x;
                         gmx = fmax(gmx, fmax(d0.y, fmax(d1.y, d2.y)));
                     }
@@ -911,11 +922,7 @@ template <int KIND, int PRE, bool CL> __global__ void __launch_bounds__(ADJ_THRE
                 for (unsigned f2 = fm & (fm - 1); f2; f2 &= f2 - 1) {
                     const int qf = p + __ffs(f2) - 1;
                     const int f0 = bo[2 * qf], f1 = bo[2 * qf + 2];
-                    for (int e = f0 + tid * 16; e < f1; e += ADJ_THREADS * 16) {
-                        asm volatile("prefetch.global.L2 [%0];" ::"l"(a.ent_x + vb + e));
-                        if (PRE) asm volatile("prefetch.global.L2 [%0];" ::"l"(a.ent_y + vb + e));
-                        if ((e & 63) == (f0 & 63)) asm volatile("prefetch.global.L2 [%0];" ::"l"(a.ent_i + vb + e));
-                    }
+                    adj_pf_range<PRE>(a.ent_i + vb, a.ent_x + (PRE ? 2 : 1) * vb, f0, f1, tid);
                 }
             }
             while (fm) {
@@ -930,8 +937,8 @@ template <int KIND, int PRE, bool CL> __global__ void __launch_bounds__(ADJ_THRE
                     const int b0 = bo[2 * qf], bm = bo[2 * qf + 1], b1 = bo[2 * qf + 2];
                     const int64_t vb = a.vbase[v0 + g];
                     const unsigned short *ei = a.ent_i + vb;
-                    const double *ex = a.ent_x + vb, *ey = PRE ? a.ent_y + vb : nullptr;
-                    adj_apply<KIND, PRE>(enf, ei, ex, ey, b0, bm, b1, warp, lane, sgn, resident ? lam_s : lamg + (size_t)g * csz, a.D, ft);
+                    const double *ex = a.ent_x + (PRE ? 2 : 1) * vb;
+                    adj_apply<KIND, PRE>(enf, ei, ex, b0, bm, b1, warp, lane, sgn, resident ? lam_s : lamg + (size_t)g * csz, a.D, ft);
                 }
                 __syncthreads();  // the next flipped bucket may touch the same events
             }
@@ -1118,8 +1125,7 @@ static int adj_build_structure(nhp_ctx *ctx, nhp_events *ev, double horizon, int
     ADJ_S(cudaMallocAsync(&ev->d_adj_boff, (size_t)nv * (2 * K + 1) * sizeof(int), s));
     const size_t slack = 64 * 1024;  // entries: the sweeps' L2 prefetches run a few blocks ahead of the block they read
     ADJ_S(cudaMallocAsync(&ev->d_adj_i, ((size_t)tot + slack) * sizeof(unsigned short), s));
-    ADJ_S(cudaMallocAsync(&ev->d_adj_dt, ((size_t)tot + slack) * sizeof(double), s));
-    if (pre) ADJ_S(cudaMallocAsync(&ev->d_adj_q, ((size_t)tot + slack) * sizeof(double), s));
+    ADJ_S(cudaMallocAsync(&ev->d_adj_dt, ((size_t)tot + slack) * (pre ? 2 : 1) * sizeof(double), s));
     ADJ_S(cudaMallocAsync(&ev->d_adj_lam, std::max<size_t>((size_t)n, 1) * sizeof(double), s));
     tm.lap("links + allocation");
     ADJ_S(cudaMemcpyAsync(ev->d_adj_vbase, vbase.data(), (size_t)(nv + 1) * sizeof(int64_t), cudaMemcpyHostToDevice, s));
@@ -1127,7 +1133,7 @@ static int adj_build_structure(nhp_ctx *ctx, nhp_events *ev, double horizon, int
     AdjBuildArgs b;
     b.t = ev->d_t; b.pk = d_pk; b.lo = d_lo; b.order = ev->d_order; b.node_ptr = ev->d_node_ptr; b.K = (int)K; b.D = ctx->dtmax;
     b.vstart = ev->d_adj_vstart; b.vnode = ev->d_adj_vnode; b.vbase = ev->d_adj_vbase; b.boff = ev->d_adj_boff; b.ent_i = ev->d_adj_i; b.ent_x = ev->d_adj_dt;
-    b.ent_y = pre ? ev->d_adj_q : nullptr;
+    b.pre = pre ? 1 : 0;
     b.nv = (int)nv; b.nw = nw; b.next = ctx->d_adj_ctl; b.flag = ctx->d_flag;
     const size_t bsmem = (size_t)(2 * K + 1) * sizeof(int) + (size_t)(nw + 1) * K * sizeof(unsigned);
     ADJ_S(cudaFuncSetAttribute(k_adj_build, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)std::max<size_t>(bsmem, 1024)));
@@ -1297,7 +1303,7 @@ static int adj_run(nhp_ctx *ctx, nhp_events *ev, const double *d_rho, double rho
         k_adj_prep<<<kb, 256, 0, s>>>((int)K, ctx->d_W, ev->d_Mn, d_rho, rho_scalar, d_u, seed, counter, ctx->d_adj_dec);
         NHP_LAUNCHED(ctx);
         w.dec = ctx->d_adj_dec; w.D = ctx->dtmax;
-        w.vstart = ev->d_adj_vstart; w.vbase = ev->d_adj_vbase; w.boff = ev->d_adj_boff; w.ent_i = ev->d_adj_i; w.ent_x = ev->d_adj_dt; w.ent_y = ev->d_adj_q;
+        w.vstart = ev->d_adj_vstart; w.vbase = ev->d_adj_vbase; w.boff = ev->d_adj_boff; w.ent_i = ev->d_adj_i; w.ent_x = ev->d_adj_dt;
         w.lam = ev->d_adj_lam;
         w.chunk_max = (ev->adj_chunk_max + 1) & ~1;
         w.flag = ctx->d_flag; w.next = ctx->d_adj_ctl; w.stat = ctx->d_adj_stat;

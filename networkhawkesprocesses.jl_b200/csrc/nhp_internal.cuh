@@ -96,8 +96,8 @@ struct nhp_events {
     int64_t *d_adj_vbase = nullptr;  // [nv+1] first entry of every virtual column
     int *d_adj_boff = nullptr;       // [nv][2K+1] section offsets inside a virtual column: singles of parent p at [2p], its runs at [2p+1]
     unsigned short *d_adj_i = nullptr;  // [adj_total] child event index inside its chunk | bit 15: same (event, parent) as the previous entry
-    double *d_adj_dt = nullptr;      // [adj_total] t_i - t_j, or logit(dt / D) with the LogitNormal payload
-    double *d_adj_q = nullptr;       // [adj_total] LogitNormal payload: 1 / (dt (D - dt)), 0 outside the support
+    double *d_adj_dt = nullptr;      // [adj_total] t_i - t_j, or [2 adj_total] with the LogitNormal payload: (logit(dt / D), 1 / (dt (D - dt))) per entry, (0, 0) outside the support
+    double *d_adj_q = nullptr;       // unused (the payload is interleaved in d_adj_dt)
     int adj_cluster = 0;             // CTAs per column (thread-block cluster size; 0: single-CTA streaming form)
     int adj_kind = 0;                // 1: LogitNormal payload
     double *d_adj_lam = nullptr;     // [n] per-event intensity in by-node order (work array of the sweep)
