@@ -279,23 +279,36 @@ __device__ __forceinline__ void st_keep_u16(unsigned short *p, unsigned short v,
     asm volatile("st.global.L2::cache_hint.u16 [%0], %1, %2;" ::"l"(p), "h"(v), "l"(pol) : "memory");
 }
 
+__device__ __forceinline__ int adj_pk_dprev(unsigned long long pk) { return (int)((unsigned)(pk >> ADJ_NODE_BITS) & ADJ_LINK_SAT); }
 __device__ __forceinline__ void adj_pk_decode(unsigned long long pk, int j, int i, int lo, int &p, bool &multi, bool &cont) {
     p = (int)((unsigned)pk & ((1u << ADJ_NODE_BITS) - 1u));
-    const int dp = (int)((unsigned)(pk >> ADJ_NODE_BITS) & ADJ_LINK_SAT), dn = (int)(pk >> (ADJ_NODE_BITS + ADJ_LINK_BITS));
+    const int dp = adj_pk_dprev(pk), dn = (int)(pk >> (ADJ_NODE_BITS + ADJ_LINK_BITS));
     cont = (int64_t)j + dn < (int64_t)i;  // a more recent event of the same node sits in the window: this entry continues its run
     multi = cont || (j - dp >= lo);
 }
+// one entry: index word + payload (the lag, or the parameter-free part of the LogitNormal impulse)
+__device__ __forceinline__ void adj_store_entry(unsigned short *ei, double *ex, int pre, unsigned pos, unsigned tag, double dt, double D, unsigned long long pol) {
+    st_keep_u16(ei + pos, (unsigned short)tag, pol);
+    if (pre) {
+        const double b = D - dt;
+        double z = 0.0, q = 0.0;
+        if (dt > 0.0 && b > 0.0) {  // Distributions.pdf(LogitNormal, x) is zero outside 0 < x < 1 (impulses.jl:174-178)
+            q = 1.0 / (dt * b);
+            z = log(dt / b);
+            if (!(q <= 1.7976931348623157e308) || !(fabs(z) <= 1.7976931348623157e308)) { z = 0.0; q = 0.0; }  // lag so small that the pdf underflows
+        }
+        st_keep_f64x2(ex + 2 * (size_t)pos, z, q, pol);
+    } else st_keep_f64(ex + pos, dt, pol);
+}
 
-__global__ void __launch_bounds__(512) k_adj_build(const AdjBuildArgs a) {
+__global__ void __launch_bounds__(1024) k_adj_build(const AdjBuildArgs a) {
     extern __shared__ int s_dyn[];
     __shared__ int s_v;
-    const int K = a.K, nw = a.nw;
-    int *s_off = s_dyn;                                               // [2K+1] section offsets: singles of p, runs of p, ...
+    const int K = a.K;
+    int *s_off = s_dyn;                                                  // [2K+1] section offsets: singles of p, runs of p, ...
     unsigned *s_curS = reinterpret_cast<unsigned *>(s_dyn + 2 * K + 1);  // [K] singles: count, then the CTA-wide cursor
-    unsigned *s_w = s_curS + K;                                       // per warp: curM[K] run entries: count, then the warp's cursor
-    const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
-    unsigned *curM = s_w + (size_t)wid * K;
-    const unsigned lt = (1u << lane) - 1u;
+    unsigned *s_curM = s_curS + K;                                       // [K] run entries: count, then the CTA-wide cursor (a run is reserved whole)
+    const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5, nw = blockDim.x >> 5;
     const unsigned long long pol_rd = l2_policy_evict_first(), pol_wr = l2_policy_evict_last();
     for (;;) {
         __syncthreads();
@@ -306,18 +319,16 @@ __global__ void __launch_bounds__(512) k_adj_build(const AdjBuildArgs a) {
         const int col = a.vnode[v], g = v - a.vstart[col], G = a.vstart[col + 1] - a.vstart[col];
         const int ne = a.node_ptr[col + 1] - a.node_ptr[col], csz = adj_chunk_size(ne, G);
         const int eb = a.node_ptr[col] + g * csz, ee = min(a.node_ptr[col] + ne, eb + csz);  // positions in the by-node order
-        const int per = (max(ee - eb, 0) + nw - 1) / nw;
-        const int ws = min(ee, eb + wid * per), we = min(ee, ws + per);
-        for (int k = tid; k < (nw + 1) * K; k += blockDim.x) s_curS[k] = 0u;
+        for (int k = tid; k < 2 * K; k += blockDim.x) s_curS[k] = 0u;
         __syncthreads();
-        // ---- A: counts (singles per CTA, run entries per warp)
-        for (int e0 = ws; e0 < we; e0 += 32) {
+        // ---- A: counts.  Warps take blocks of 32 events round robin.
+        for (int e0 = eb + wid * 32; e0 < ee; e0 += nw * 32) {
             int my_i = 0, my_lo = 0;
-            if (e0 + lane < we) {  // 32 events' headers in one round trip; their windows start towards L2
+            if (e0 + lane < ee) {  // 32 events' headers in one round trip; their windows start towards L2
                 my_i = a.order[e0 + lane]; my_lo = a.lo[my_i];
                 for (int j = my_lo & ~15; j < my_i; j += 16) asm volatile("prefetch.global.L2 [%0];" ::"l"(a.pk + j));
             }
-            const int cnt = min(32, we - e0);
+            const int cnt = min(32, ee - e0);
             for (int s = 0; s < cnt; s++) {
                 const int i = __shfl_sync(0xffffffffu, my_i, s), lo = __shfl_sync(0xffffffffu, my_lo, s);
                 for (int j = i - 1 - lane; j >= lo; j -= 64) {  // two rounds in flight
@@ -325,21 +336,19 @@ __global__ void __launch_bounds__(512) k_adj_build(const AdjBuildArgs a) {
                     const unsigned long long pk = ldg_stream_u64(a.pk + j, pol_rd), pk2 = j2 >= lo ? ldg_stream_u64(a.pk + j2, pol_rd) : 0ull;
                     int p; bool multi, cont;
                     adj_pk_decode(pk, j, i, lo, p, multi, cont);
-                    atomicAdd(multi ? &curM[p] : &s_curS[p], 1u);
+                    atomicAdd(multi ? &s_curM[p] : &s_curS[p], 1u);
                     if (j2 >= lo) {
                         adj_pk_decode(pk2, j2, i, lo, p, multi, cont);
-                        atomicAdd(multi ? &curM[p] : &s_curS[p], 1u);
+                        atomicAdd(multi ? &s_curM[p] : &s_curS[p], 1u);
                     }
                 }
             }
         }
         __syncthreads();
-        // ---- section sizes (padded to whole groups of 32 entries); a warp's run cursor starts behind the earlier warps' entries
+        // ---- section sizes (padded to whole groups of 32 entries)
         for (int p = tid; p < K; p += blockDim.x) {
-            unsigned r = 0;
-            for (int w = 0; w < nw; w++) { unsigned *cw = s_w + (size_t)w * K; const unsigned x = cw[p]; cw[p] = r; r += x; }
             s_off[2 * p + 1] = (int)((s_curS[p] + 31u) & ~31u);
-            s_off[2 * p + 2] = (int)((r + 31u) & ~31u);
+            s_off[2 * p + 2] = (int)((s_curM[p] + 31u) & ~31u);
         }
         if (tid == 0) s_off[0] = 0;
         __syncthreads();
@@ -357,67 +366,51 @@ __global__ void __launch_bounds__(512) k_adj_build(const AdjBuildArgs a) {
         }
         __syncthreads();
         for (int k = tid; k <= 2 * K; k += blockDim.x) a.boff[(int64_t)v * (2 * K + 1) + k] = s_off[k];
-        for (int p = tid; p < K; p += blockDim.x) {
-            s_curS[p] = (unsigned)s_off[2 * p];
-            const unsigned o = (unsigned)s_off[2 * p + 1];
-            for (int w = 0; w < nw; w++) s_w[(size_t)w * K + p] += o;
-        }
+        for (int p = tid; p < K; p += blockDim.x) { s_curS[p] = (unsigned)s_off[2 * p]; s_curM[p] = (unsigned)s_off[2 * p + 1]; }
         __syncthreads();
-        // ---- B: scatter, one pass over every window
+        // ---- B: scatter, one pass over every window.  A single takes the next slot of its section.  The most recent entry of a run (its
+        //      head) follows the same-node links back through the window, reserves the run's slots at once and writes the run in window order.
         unsigned short *ei = a.ent_i + a.vbase[v];
         double *ex = a.ent_x + (a.pre ? 2 : 1) * a.vbase[v];
-        for (int e0 = ws; e0 < we; e0 += 32) {
+        for (int e0 = eb + wid * 32; e0 < ee; e0 += nw * 32) {
             int my_i = 0, my_lo = 0;
             double my_t = 0.0;
-            if (e0 + lane < we) {
+            if (e0 + lane < ee) {
                 my_i = a.order[e0 + lane]; my_lo = a.lo[my_i]; my_t = a.t[my_i];
                 for (int j = my_lo & ~15; j < my_i; j += 16) {
                     asm volatile("prefetch.global.L2 [%0];" ::"l"(a.pk + j));
                     asm volatile("prefetch.global.L2 [%0];" ::"l"(a.t + j));
                 }
             }
-            const int cnt = min(32, we - e0);
+            const int cnt = min(32, ee - e0);
             for (int s = 0; s < cnt; s++) {
                 const int i = __shfl_sync(0xffffffffu, my_i, s), lo = __shfl_sync(0xffffffffu, my_lo, s);
                 const double ti = __shfl_sync(0xffffffffu, my_t, s);
                 const unsigned le = (unsigned)(e0 + s - eb);
-                // the next round's loads are issued before this round is scattered
-                int j = i - 1 - lane;
-                unsigned long long pk = 0ull;
-                double tj = 0.0;
-                if (j >= lo) { pk = ldg_stream_u64(a.pk + j, pol_rd); tj = ldg_stream_f64(a.t + j, pol_rd); }
-                for (int j0 = i - 1; j0 >= lo; j0 -= 32) {
-                    const int jc = j;
-                    const unsigned long long pkc = pk;
-                    const double tjc = tj;
-                    j -= 32;
-                    if (j >= lo) { pk = ldg_stream_u64(a.pk + j, pol_rd); tj = ldg_stream_f64(a.t + j, pol_rd); }
-                    const bool valid = jc >= lo;
-                    int p = -1 - lane;
-                    bool multi = false, cont = false;
-                    if (valid) adj_pk_decode(pkc, jc, i, lo, p, multi, cont);
-                    const double dt = ti - tjc;
-                    unsigned pos = 0u;
-                    if (valid && !multi) pos = atomicAdd(&s_curS[p], 1u);
-                    if (__any_sync(0xffffffffu, multi)) {  // entries of this round that belong to runs: ranked among the lanes with the same parent
-                        const unsigned m = __match_any_sync(0xffffffffu, multi ? p : -1 - lane);
-                        if (multi) pos = curM[p] + __popc(m & lt);
-                        __syncwarp();
-                        if (multi && (m & lt) == 0u) curM[p] += __popc(m);
-                        __syncwarp();
-                    }
-                    if (valid) {
-                        st_keep_u16(ei + pos, (unsigned short)(le | (cont ? 0x8000u : 0u)), pol_wr);
-                        if (a.pre) {
-                            const double b = a.D - dt;
-                            double z = 0.0, q = 0.0;
-                            if (dt > 0.0 && b > 0.0) {  // Distributions.pdf(LogitNormal, x) is zero outside 0 < x < 1 (impulses.jl:174-178)
-                                q = 1.0 / (dt * b);
-                                z = log(dt / b);
-                                if (!(q <= 1.7976931348623157e308) || !(fabs(z) <= 1.7976931348623157e308)) { z = 0.0; q = 0.0; }  // lag so small that the pdf underflows
+                for (int j = i - 1 - lane; j >= lo; j -= 64) {  // two rounds in flight
+                    const int j2 = j - 32;
+                    const bool has2 = j2 >= lo;
+                    const unsigned long long pk = ldg_stream_u64(a.pk + j, pol_rd), pk2 = has2 ? ldg_stream_u64(a.pk + j2, pol_rd) : 0ull;
+                    const double tj = ldg_stream_f64(a.t + j, pol_rd), tj2 = has2 ? ldg_stream_f64(a.t + j2, pol_rd) : 0.0;
+#pragma unroll
+                    for (int r = 0; r < 2; r++) {
+                        if (r == 1 && !has2) break;
+                        const int jc = r ? j2 : j;
+                        const unsigned long long pkc = r ? pk2 : pk;
+                        const double dt = ti - (r ? tj2 : tj);
+                        int p; bool multi, cont;
+                        adj_pk_decode(pkc, jc, i, lo, p, multi, cont);
+                        if (!multi) adj_store_entry(ei, ex, a.pre, atomicAdd(&s_curS[p], 1u), le, dt, a.D, pol_wr);
+                        else if (!cont) {
+                            int len = 1;
+                            for (int jj = jc - adj_pk_dprev(pkc); jj >= lo; len++) jj -= adj_pk_dprev(__ldg(a.pk + jj));
+                            unsigned pos = atomicAdd(&s_curM[p], (unsigned)len);
+                            adj_store_entry(ei, ex, a.pre, pos, le, dt, a.D, pol_wr);
+                            for (int jj = jc - adj_pk_dprev(pkc); jj >= lo;) {
+                                adj_store_entry(ei, ex, a.pre, ++pos, le | 0x8000u, ti - __ldg(a.t + jj), a.D, pol_wr);
+                                jj -= adj_pk_dprev(__ldg(a.pk + jj));
                             }
-                            st_keep_f64x2(ex + 2 * (size_t)pos, z, q, pol_wr);
-                        } else st_keep_f64(ex + pos, dt, pol_wr);
+                        }
                     }
                 }
             }
@@ -426,8 +419,7 @@ __global__ void __launch_bounds__(512) k_adj_build(const AdjBuildArgs a) {
         // ---- padding: entries that evaluate to exactly zero (event 0, q = 0 | lag -1), so the sweeps read whole groups unconditionally
         for (int k = tid; k < 2 * K; k += blockDim.x) {
             const int p = k >> 1;
-            const int beg = (k & 1) ? (int)s_w[(size_t)(nw - 1) * K + p] : (int)s_curS[p];  // true end: the CTA cursor | the last warp's cursor
-            for (int e = beg; e < s_off[k + 1]; e++) {
+            for (int e = (k & 1) ? (int)s_curM[p] : (int)s_curS[p]; e < s_off[k + 1]; e++) {  // from the section's true end (its cursor)
                 ei[e] = 0;
                 if (a.pre) { ex[2 * (size_t)e] = 0.0; ex[2 * (size_t)e + 1] = 0.0; } else ex[e] = -1.0;
             }
@@ -1107,11 +1099,12 @@ static int adj_build_structure(nhp_ctx *ctx, nhp_events *ev, double horizon, int
     bool pre = ctx->kind == NHP_LOGITNORMAL && (double)tot * 18.0 + (double)fixed <= 0.72 * (double)free_b;
     { const char *e = getenv("NHP_ADJ_PRE"); if (e) pre = pre && atoi(e) != 0; }
     const size_t need = (size_t)tot * (pre ? 18 : 10) + fixed;
-    // build kernel: [2K+1] section offsets + K shared cursors (singles) + per warp K cursors (runs); two CTAs per SM when they fit
-    int nw = (int)std::min<int64_t>(16, ((int64_t)ctx->smem_optin / 2 - 2048 - (3 * K + 1) * 4) / (4 * K));
-    if (nw < 4) nw = (int)std::min<int64_t>(16, ((int64_t)ctx->smem_optin - 2048 - (3 * K + 1) * 4) / (4 * K));
+    // build kernel: [2K+1] section offsets + 2 K CTA-wide cursors (singles, runs); one CTA of 32 warps per SM
+    int nw = 32;
+    { const char *e = getenv("NHP_ADJ_BUILD_NW"); if (e && atoi(e) >= 1 && atoi(e) <= 32) nw = atoi(e); }
+    const bool fits = (size_t)(4 * K + 1) * sizeof(int) + 2048 <= (size_t)ctx->smem_optin;
     // the packed predecessor record holds 20 bits of node and 22 bits of same-node distances: longer windows take the uncached sweep
-    if ((double)need > 0.75 * (double)free_b || nw < 1 || K > (1 << ADJ_NODE_BITS) || max_win >= (int)ADJ_LINK_SAT) return drop(1);
+    if ((double)need > 0.75 * (double)free_b || !fits || K > (1 << ADJ_NODE_BITS) || max_win >= (int)ADJ_LINK_SAT) return drop(1);
     cudaFreeAsync(d_vcount, s); d_vcount = nullptr;
     ADJ_B(cudaMallocAsync(&d_pk, std::max<size_t>((size_t)n, 1) * sizeof(unsigned long long), s));
     if (n > 0) {
@@ -1135,7 +1128,7 @@ static int adj_build_structure(nhp_ctx *ctx, nhp_events *ev, double horizon, int
     b.vstart = ev->d_adj_vstart; b.vnode = ev->d_adj_vnode; b.vbase = ev->d_adj_vbase; b.boff = ev->d_adj_boff; b.ent_i = ev->d_adj_i; b.ent_x = ev->d_adj_dt;
     b.pre = pre ? 1 : 0;
     b.nv = (int)nv; b.nw = nw; b.next = ctx->d_adj_ctl; b.flag = ctx->d_flag;
-    const size_t bsmem = (size_t)(2 * K + 1) * sizeof(int) + (size_t)(nw + 1) * K * sizeof(unsigned);
+    const size_t bsmem = (size_t)(4 * K + 1) * sizeof(int);
     ADJ_S(cudaFuncSetAttribute(k_adj_build, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)std::max<size_t>(bsmem, 1024)));
     int per_sm = 1;
     ADJ_S(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_adj_build, nw * 32, bsmem));
