@@ -47,7 +47,8 @@ RATE, DTMAX, RHO, BRANCHING = 64.0, 1.0, 0.05, 0.5
 FLOPS_PER_LN_PAIR, FLOPS_PER_EVENT = 96.0, 40.0   # nominal FP64 flops (libdevice-class accuracy)
 BYTES_LOGLIK, BYTES_PARENTS = 12.0, 12.0          # per event: 8 B time + 4 B node (parents stay on the device as fused statistics)
 BYTES_EXTRA_WLEN, BYTES_EXTRA_POFF = 2.0, 4.0     # implementation extras, stated separately: cached window length read, parent offset written
-BYTES_PER_ADJ_PAIR = 10.0                         # cached adjacency structure: u16 event index + f64 lag per (child event, window predecessor)
+BYTES_PER_ADJ_PAIR = 10.0                         # cached adjacency structure: u16 event index + f64 lag per (child event, window predecessor);
+                                                  # 18 B with the LogitNormal payload (u16 + logit + Jacobian) -- the form the library reports is used
 SEED = 20261018
 
 
@@ -540,13 +541,19 @@ def run_ours(args, rank, world, local_rank):
     probes = n * RATE * DTMAX
     active_pairs = probes * density
     adj_s = med["adjacency"] * 1e-3
-    adj_bytes = pairs * BYTES_PER_ADJ_PAIR
+    frac5 = float(arow[5]) * 1e3 % 1.0   # adjacency_info[5] = virtual columns + 1e-3 cluster size + 1e-6 bytes per pair
+    bpp = float(round(frac5 * 1e3)) if arow[5] > 0 else BYTES_PER_ADJ_PAIR
+    if bpp not in (10.0, 18.0):
+        bpp = BYTES_PER_ADJ_PAIR
+    adj_bytes = pairs * bpp
     dom = "adjacency" if med["adjacency"] >= max(med["loglik"], med["parents"]) else ("parents" if med["parents"] >= med["loglik"] else "loglik")
     if dom == "adjacency":
         roofline = {"kernel": "k_adj_sweep<LOGITNORMAL> (adjacency Gibbs sweep, continuous.jl:444-519)", "bound": "hbm", "achieved": adj_bytes / adj_s / 1e9, "peak": hbm,
                     "unit": "GB/s", "frac": adj_bytes / adj_s / 1e9 / hbm, "traffic": None, "peak_source": hbm_src, "algorithmic_bytes_per_launch": adj_bytes,
-                    "algorithmic_unit": "%.0f B per cached (child event, window predecessor) pair x %.4g pairs" % (BYTES_PER_ADJ_PAIR, pairs),
-                    "binding_resource": "FP64 pipe: every pair costs one LogitNormal impulse evaluation (table-driven log + exp); see fp64_view",
+                    "algorithmic_unit": "%.0f B per cached (child event, window predecessor) pair (u16 event index + %s) x %.4g pairs, streamed once per sweep"
+                                        % (bpp, "f64 logit + f64 Jacobian of the lag" if bpp == 18.0 else "f64 lag", pairs),
+                    "binding_resource": "HBM stream of the cached pairs plus instruction issue: one table-driven exp, one shared-memory intensity look-up and two "
+                                        "running products per pair (profiles/r02_ncu_adj_sweep.md); fp64_view compares with full LogitNormal pair evaluations",
                     "fp64_view": {"bound": "fp64 impulse evaluations", "achieved": pairs / adj_s, "peak": peaks["ln_pairs_per_s"], "unit": "pairs/s",
                                   "frac": pairs / adj_s / peaks["ln_pairs_per_s"],
                                   "peak_source": "register-resident LogitNormal pair evaluations measured in this run (nhp_bench_fp64 which=1); FP64 FMA peak %.1f TFLOP/s" % peaks["fp64_fma_tflops"]},

@@ -195,19 +195,32 @@ __host__ __device__ inline int adj_chunk_size(int ne, int G) { return G > 0 ? (n
 __global__ void k_adj_count(const double *__restrict__ t, const int *__restrict__ c, const int *__restrict__ order, const int *__restrict__ node_ptr,
                             const int *__restrict__ vstart, int64_t n_own, double horizon, int cb, int cs, unsigned long long *__restrict__ vcount,
                             int *__restrict__ lo_out, int *__restrict__ max_win, const unsigned short *__restrict__ wlen) {
-    const int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (e >= n_own) return;
-    const int i = order[e], col = c[i];
-    if (col % cs != cb) return;
-    const int le = (int)(e - node_ptr[col]), ne = node_ptr[col + 1] - node_ptr[col], G = vstart[col + 1] - vstart[col];
-    const int v = vstart[col] + le / adj_chunk_size(ne, G);
-    // the sweeps' cached window length when it was taken with this horizon (saturated values are searched)
-    const unsigned wl = wlen ? (unsigned)wlen[i] : 65535u;
-    const int lo = wl < 65535u ? i - (int)wl : lo_of_event(t, i, horizon);
-    if (lo_out) lo_out[i] = lo;
-    if (i > lo) {
-        atomicAdd(&vcount[v], (unsigned long long)(i - lo));
-        if (max_win) atomicMax(max_win, i - lo);
+    const int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;  // blockDim.x is a multiple of 32: whole warps reach the votes below
+    int v = -1;
+    unsigned w = 0u;
+    if (e < n_own) {
+        const int i = order[e], col = c[i];
+        if (col % cs == cb) {
+            const int le = (int)(e - node_ptr[col]), ne = node_ptr[col + 1] - node_ptr[col], G = vstart[col + 1] - vstart[col];
+            v = vstart[col] + le / adj_chunk_size(ne, G);
+            // the sweeps' cached window length when it was taken with this horizon (saturated values are searched)
+            const unsigned wl = wlen ? (unsigned)wlen[i] : 65535u;
+            const int lo = wl < 65535u ? i - (int)wl : lo_of_event(t, i, horizon);
+            if (lo_out) lo_out[i] = lo;
+            w = (unsigned)(i - lo);
+        }
+    }
+    // consecutive events of the by-node order share their virtual column: one atomic per warp instead of 32 on the same address
+    const int v0 = __shfl_sync(0xffffffffu, v, 0);
+    if (__all_sync(0xffffffffu, v == v0 && w < (1u << 26))) {
+        const unsigned tot = __reduce_add_sync(0xffffffffu, w), mx = __reduce_max_sync(0xffffffffu, w);
+        if ((threadIdx.x & 31) == 0 && v0 >= 0 && tot > 0u) {
+            atomicAdd(&vcount[v0], (unsigned long long)tot);
+            if (max_win) atomicMax(max_win, (int)mx);
+        }
+    } else if (v >= 0 && w > 0u) {
+        atomicAdd(&vcount[v], (unsigned long long)w);
+        if (max_win) atomicMax(max_win, (int)min(w, 0x7fffffffu));
     }
 }
 
@@ -287,23 +300,36 @@ __device__ __forceinline__ void adj_pk_decode(unsigned long long pk, int j, int 
     multi = cont || (j - dp >= lo);
 }
 // one entry: index word + payload (the lag, or the parameter-free part of the LogitNormal impulse)
-__device__ __forceinline__ void adj_store_entry(unsigned short *ei, double *ex, int pre, unsigned pos, unsigned tag, double dt, double D, unsigned long long pol) {
+static __device__ __noinline__ double2 adj_payload_slow(double dt, double D) {  // lags at the edge of the support (or outside it)
+    const double b = D - dt;
+    double z = 0.0, q = 0.0;
+    if (dt > 0.0 && b > 0.0) {  // Distributions.pdf(LogitNormal, x) is zero outside 0 < x < 1 (impulses.jl:174-178)
+        q = 1.0 / (dt * b);
+        z = log(dt / b);
+        if (!(q <= 1.7976931348623157e308) || !(fabs(z) <= 1.7976931348623157e308)) { z = 0.0; q = 0.0; }  // lag so small that the pdf underflows
+    }
+    return make_double2(z, q);
+}
+__device__ __forceinline__ void adj_store_entry(unsigned short *ei, double *ex, int pre, unsigned pos, unsigned tag, double dt, double D, unsigned long long pol,
+                                                const FastTables *ft) {
     st_keep_u16(ei + pos, (unsigned short)tag, pol);
     if (pre) {
         const double b = D - dt;
-        double z = 0.0, q = 0.0;
-        if (dt > 0.0 && b > 0.0) {  // Distributions.pdf(LogitNormal, x) is zero outside 0 < x < 1 (impulses.jl:174-178)
-            q = 1.0 / (dt * b);
-            z = log(dt / b);
-            if (!(q <= 1.7976931348623157e308) || !(fabs(z) <= 1.7976931348623157e308)) { z = 0.0; q = 0.0; }  // lag so small that the pdf underflows
-        }
-        st_keep_f64x2(ex + 2 * (size_t)pos, z, q, pol);
+        double2 zq;
+        if (in_mid_range(dt) && in_mid_range(b)) {  // the arithmetic of pair_value: one reciprocal serves the Jacobian and the logit argument
+            zq.y = fast_rcp_mid(dt * b);
+            zq.x = fast_log_n(dt * dt * zq.y, ft);
+        } else zq = adj_payload_slow(dt, D);
+        st_keep_f64x2(ex + 2 * (size_t)pos, zq.x, zq.y, pol);
     } else st_keep_f64(ex + pos, dt, pol);
 }
 
 __global__ void __launch_bounds__(1024) k_adj_build(const AdjBuildArgs a) {
     extern __shared__ int s_dyn[];
     __shared__ int s_v;
+    __shared__ FastTables s_ft;
+    fast_tables_load(&s_ft);
+    const FastTables *ft = &s_ft;
     const int K = a.K;
     int *s_off = s_dyn;                                                  // [2K+1] section offsets: singles of p, runs of p, ...
     unsigned *s_curS = reinterpret_cast<unsigned *>(s_dyn + 2 * K + 1);  // [K] singles: count, then the CTA-wide cursor
@@ -400,14 +426,14 @@ __global__ void __launch_bounds__(1024) k_adj_build(const AdjBuildArgs a) {
                         const double dt = ti - (r ? tj2 : tj);
                         int p; bool multi, cont;
                         adj_pk_decode(pkc, jc, i, lo, p, multi, cont);
-                        if (!multi) adj_store_entry(ei, ex, a.pre, atomicAdd(&s_curS[p], 1u), le, dt, a.D, pol_wr);
+                        if (!multi) adj_store_entry(ei, ex, a.pre, atomicAdd(&s_curS[p], 1u), le, dt, a.D, pol_wr, ft);
                         else if (!cont) {
                             int len = 1;
                             for (int jj = jc - adj_pk_dprev(pkc); jj >= lo; len++) jj -= adj_pk_dprev(__ldg(a.pk + jj));
                             unsigned pos = atomicAdd(&s_curM[p], (unsigned)len);
-                            adj_store_entry(ei, ex, a.pre, pos, le, dt, a.D, pol_wr);
+                            adj_store_entry(ei, ex, a.pre, pos, le, dt, a.D, pol_wr, ft);
                             for (int jj = jc - adj_pk_dprev(pkc); jj >= lo;) {
-                                adj_store_entry(ei, ex, a.pre, ++pos, le | 0x8000u, ti - __ldg(a.t + jj), a.D, pol_wr);
+                                adj_store_entry(ei, ex, a.pre, ++pos, le | 0x8000u, ti - __ldg(a.t + jj), a.D, pol_wr, ft);
                                 jj -= adj_pk_dprev(__ldg(a.pk + jj));
                             }
                         }
@@ -1021,7 +1047,7 @@ static int adj_build_structure(nhp_ctx *ctx, nhp_events *ev, double horizon, int
     const int64_t K = ctx->K, n = ev->n;
     cudaStream_t s = ctx->stream;
     AdjPhaseTimer tm(s);
-    nhp_events_free_adjacency(ev, s);
+    nhp_events_free_adjacency(ctx, ev, s);
     tm.lap("free old structure");
     std::vector<double> mn(K);
     ADJ_CUDA(cudaMemcpyAsync(mn.data(), ev->d_Mn, K * sizeof(double), cudaMemcpyDeviceToHost, s));
@@ -1087,13 +1113,14 @@ static int adj_build_structure(nhp_ctx *ctx, nhp_events *ev, double horizon, int
     // a quarter (payload: a third) of the free memory stays free for everything else
     size_t free_b = 0, total_b = 0;
     cudaMemGetInfo(&free_b, &total_b);
-    {   // blocks the stream-ordered pool keeps for reuse (a freed structure of the previous data set) are available to this one
+    {   // what the context's block cache and the stream-ordered pool keep for reuse (a freed structure of the previous data set) is available
         cudaMemPool_t pool;
         unsigned long long reserved = 0, used = 0;
         if (cudaDeviceGetDefaultMemPool(&pool, ctx->device) == cudaSuccess &&
             cudaMemPoolGetAttribute(pool, cudaMemPoolAttrReservedMemCurrent, &reserved) == cudaSuccess &&
             cudaMemPoolGetAttribute(pool, cudaMemPoolAttrUsedMemCurrent, &used) == cudaSuccess && reserved > used)
             free_b += (size_t)(reserved - used);
+        free_b += nhp_big_cached_bytes(ctx);
     }
     const size_t fixed = (size_t)nv * (2 * K + 1) * sizeof(int) + (size_t)(nv + 1) * sizeof(int64_t) + (size_t)n * (sizeof(double) + sizeof(unsigned long long));
     bool pre = ctx->kind == NHP_LOGITNORMAL && (double)tot * 18.0 + (double)fixed <= 0.72 * (double)free_b;
@@ -1112,13 +1139,16 @@ static int adj_build_structure(nhp_ctx *ctx, nhp_events *ev, double horizon, int
         NHP_LAUNCHED(ctx);
     }
     ev->d_adj_vstart = d_vstart; ev->d_adj_vnode = d_vnode; d_vstart = d_vnode = nullptr;  // owned by the handle from here on
-    auto fail = [&](int rc) { cudaFreeAsync(d_lo, s); cudaFreeAsync(d_pk, s); nhp_events_free_adjacency(ev, s); return rc; };
+    auto fail = [&](int rc) { cudaFreeAsync(d_lo, s); cudaFreeAsync(d_pk, s); nhp_events_free_adjacency(ctx, ev, s); return rc; };
 #define ADJ_S(call) do { cudaError_t e__ = (call); if (e__ != cudaSuccess) return fail(nhp_fail(ctx, NHP_ERR_CUDA, "%s failed: %s (%s:%d)", #call, cudaGetErrorString(e__), __FILE__, __LINE__)); } while (0)
     ADJ_S(cudaMallocAsync(&ev->d_adj_vbase, (size_t)(nv + 1) * sizeof(int64_t), s));
     ADJ_S(cudaMallocAsync(&ev->d_adj_boff, (size_t)nv * (2 * K + 1) * sizeof(int), s));
     const size_t slack = 64 * 1024;  // entries: the sweeps' L2 prefetches run a few blocks ahead of the block they read
-    ADJ_S(cudaMallocAsync(&ev->d_adj_i, ((size_t)tot + slack) * sizeof(unsigned short), s));
-    ADJ_S(cudaMallocAsync(&ev->d_adj_dt, ((size_t)tot + slack) * (pre ? 2 : 1) * sizeof(double), s));
+    ev->adj_bytes_i = ((size_t)tot + slack) * sizeof(unsigned short);
+    ev->adj_bytes_dt = ((size_t)tot + slack) * (pre ? 2 : 1) * sizeof(double);
+    ev->d_adj_i = (unsigned short *)nhp_big_alloc(ctx, ev->adj_bytes_i);
+    ev->d_adj_dt = (double *)nhp_big_alloc(ctx, ev->adj_bytes_dt);
+    if (!ev->d_adj_i || !ev->d_adj_dt) return fail(nhp_fail(ctx, NHP_ERR_CUDA, "adjacency sampler: cannot allocate %.1f GB for the cached pair structure", 1e-9 * (double)(ev->adj_bytes_i + ev->adj_bytes_dt)));
     ADJ_S(cudaMallocAsync(&ev->d_adj_lam, std::max<size_t>((size_t)n, 1) * sizeof(double), s));
     tm.lap("links + allocation");
     ADJ_S(cudaMemcpyAsync(ev->d_adj_vbase, vbase.data(), (size_t)(nv + 1) * sizeof(int64_t), cudaMemcpyHostToDevice, s));

@@ -78,6 +78,7 @@ extern "C" int nhp_destroy(nhp_ctx *ctx) {
     cudaSetDevice(ctx->device);
     cudaStreamSynchronize(ctx->stream);
     nhp_comm_destroy(ctx);
+    nhp_big_flush(ctx);
     free_cont(ctx);
     cudaFree(ctx->d_partials); cudaFree(ctx->d_scratch); cudaFree(ctx->d_flag); cudaFree(ctx->d_winstat);
     cudaFree(ctx->dd_lambda0); cudaFree(ctx->dd_W); cudaFree(ctx->dd_A); cudaFree(ctx->dd_theta); cudaFree(ctx->dd_bump);
@@ -286,9 +287,49 @@ int nhp_events_from_device(nhp_ctx *ctx, const double *d_t, const int *d_c, int6
 }
 
 // cached structure of the adjacency sampler (cont_adjacency.cu)
-void nhp_events_free_adjacency(nhp_events *ev, cudaStream_t s) {
-    // stream-ordered: the blocks (up to 100+ GB) go back to the pool without a device synchronisation and serve the next structure
-    void *blocks[] = {ev->d_adj_vstart, ev->d_adj_vnode, ev->d_adj_vbase, ev->d_adj_boff, ev->d_adj_i, ev->d_adj_dt, ev->d_adj_q, ev->d_adj_lam};
+void *nhp_big_alloc(nhp_ctx *ctx, size_t bytes) {
+    // the smallest cached block that holds the request without wasting more than half of itself
+    int best = -1;
+    for (int k = 0; k < (int)ctx->big_cache.size(); k++) {
+        const size_t b = ctx->big_cache[k].second;
+        if (b >= bytes && b <= bytes + bytes / 2 + (1u << 20) && (best < 0 || b < ctx->big_cache[best].second)) best = k;
+    }
+    if (best >= 0) {
+        void *p = ctx->big_cache[best].first;
+        ctx->big_cache.erase(ctx->big_cache.begin() + best);
+        return p;
+    }
+    void *p = nullptr;
+    if (cudaMalloc(&p, bytes) == cudaSuccess) return p;
+    cudaGetLastError();
+    nhp_big_flush(ctx);  // the cache itself may be what is in the way
+    if (cudaMalloc(&p, bytes) == cudaSuccess) return p;
+    cudaGetLastError();
+    return nullptr;
+}
+void nhp_big_free(nhp_ctx *ctx, void *p, size_t bytes) {
+    if (!p) return;
+    if (!ctx || bytes == 0 || ctx->big_cache.size() >= 8) { cudaFree(p); return; }
+    ctx->big_cache.emplace_back(p, bytes);  // kernels that still use it run on the context's stream, as will its next user
+}
+size_t nhp_big_cached_bytes(const nhp_ctx *ctx) {
+    size_t t = 0;
+    for (const auto &b : ctx->big_cache) t += b.second;
+    return t;
+}
+void nhp_big_flush(nhp_ctx *ctx) {
+    if (ctx->big_cache.empty()) return;
+    cudaStreamSynchronize(ctx->stream);
+    for (auto &b : ctx->big_cache) cudaFree(b.first);
+    ctx->big_cache.clear();
+}
+
+void nhp_events_free_adjacency(nhp_ctx *ctx, nhp_events *ev, cudaStream_t s) {
+    // the two entry arrays (up to 100+ GB) go to the context's block cache, the rest back to the stream-ordered pool: no device-wide
+    // synchronisation, and the next structure of a similar size starts from warm memory
+    nhp_big_free(ctx, ev->d_adj_i, ev->adj_bytes_i); nhp_big_free(ctx, ev->d_adj_dt, ev->adj_bytes_dt);
+    ev->adj_bytes_i = ev->adj_bytes_dt = 0;
+    void *blocks[] = {ev->d_adj_vstart, ev->d_adj_vnode, ev->d_adj_vbase, ev->d_adj_boff, ev->d_adj_lam};
     for (void *b : blocks) if (b) cudaFreeAsync(b, s);
     ev->d_adj_vstart = ev->d_adj_vnode = ev->d_adj_boff = nullptr; ev->d_adj_vbase = nullptr; ev->d_adj_i = nullptr;
     ev->d_adj_dt = ev->d_adj_q = ev->d_adj_lam = nullptr;
@@ -314,7 +355,7 @@ extern "C" int nhp_events_free(nhp_ctx *ctx, nhp_events *ev) {
         void *blocks[] = {ev->d_order, ev->d_node_ptr, ev->d_item_node, ev->d_item_e0};
         for (void *b : blocks) if (b) cudaFreeAsync(b, as);
     }
-    nhp_events_free_adjacency(ev, ctx ? ctx->stream : nullptr);
+    nhp_events_free_adjacency(ctx, ev, ctx ? ctx->stream : nullptr);
     delete ev;
     return NHP_OK;
 }

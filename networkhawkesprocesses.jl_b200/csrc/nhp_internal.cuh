@@ -101,6 +101,7 @@ struct nhp_events {
     int adj_cluster = 0;             // CTAs per column (thread-block cluster size; 0: single-CTA streaming form)
     int adj_kind = 0;                // 1: LogitNormal payload
     double *d_adj_lam = nullptr;     // [n] per-event intensity in by-node order (work array of the sweep)
+    size_t adj_bytes_i = 0, adj_bytes_dt = 0;  // sizes of the two entry arrays (they come from, and return to, the context's block cache)
     int64_t adj_total = 0;           // entries allocated (pairs + section padding)
     int64_t adj_pairs = 0;           // (child event, window predecessor) pairs
     int64_t max_win = 0;        // max over boundaries of (i0 - lo)
@@ -126,6 +127,9 @@ struct nhp_ctx {
     double last_ms = 0.0;
     int sm_count = 148;
     int smem_optin = 0;
+    // multi-GB blocks (adjacency structure) kept across events handles: cudaMalloc / cudaFree of 100 GB cost 0.1-0.7 s and a device-wide
+    // synchronisation each, a first-time cudaMallocAsync of that size several seconds; a freed block serves the next structure
+    std::vector<std::pair<void *, size_t>> big_cache;
 
     // ---- continuous parameters
     bool cont_set = false;
@@ -276,4 +280,8 @@ int nhp_cont_prepare_windows(nhp_ctx *ctx, nhp_events *ev, double horizon);
 int nhp_cont_run_loglik(nhp_ctx *ctx, nhp_events *ev, int recursive);
 double nhp_cont_horizon_value(const nhp_ctx *ctx, int64_t n_total, int recursive);
 int nhp_events_build_node_index(nhp_ctx *ctx, nhp_events *ev);  // d_order / d_node_ptr (cont_child.cu)
-void nhp_events_free_adjacency(nhp_events *ev, cudaStream_t s);                 // cached structure of the adjacency sampler (nhp_context.cu)
+void nhp_events_free_adjacency(nhp_ctx *ctx, nhp_events *ev, cudaStream_t s);
+void *nhp_big_alloc(nhp_ctx *ctx, size_t bytes);              // nullptr when the device cannot provide it
+void nhp_big_free(nhp_ctx *ctx, void *p, size_t bytes);       // ctx == nullptr: cudaFree
+size_t nhp_big_cached_bytes(const nhp_ctx *ctx);
+void nhp_big_flush(nhp_ctx *ctx);                 // cached structure of the adjacency sampler (nhp_context.cu)
