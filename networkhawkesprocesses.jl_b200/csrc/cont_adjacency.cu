@@ -324,6 +324,7 @@ __device__ __forceinline__ void adj_store_entry(unsigned short *ei, double *ex, 
     } else st_keep_f64(ex + pos, dt, pol);
 }
 
+constexpr int ADJ_BUILD_PF = 4;  // events of look-ahead of the L2 prefetch (windows longer than 32 / 16 lines are covered in part)
 __global__ void __launch_bounds__(1024) k_adj_build(const AdjBuildArgs a) {
     extern __shared__ int s_dyn[];
     __shared__ int s_v;
@@ -350,13 +351,16 @@ __global__ void __launch_bounds__(1024) k_adj_build(const AdjBuildArgs a) {
         // ---- A: counts.  Warps take blocks of 32 events round robin.
         for (int e0 = eb + wid * 32; e0 < ee; e0 += nw * 32) {
             int my_i = 0, my_lo = 0;
-            if (e0 + lane < ee) {  // 32 events' headers in one round trip; their windows start towards L2
-                my_i = a.order[e0 + lane]; my_lo = a.lo[my_i];
-                for (int j = my_lo & ~15; j < my_i; j += 16) asm volatile("prefetch.global.L2 [%0];" ::"l"(a.pk + j));
-            }
+            if (e0 + lane < ee) { my_i = a.order[e0 + lane]; my_lo = a.lo[my_i]; }  // 32 events' headers in one round trip
             const int cnt = min(32, ee - e0);
             for (int s = 0; s < cnt; s++) {
                 const int i = __shfl_sync(0xffffffffu, my_i, s), lo = __shfl_sync(0xffffffffu, my_lo, s);
+                {   // the window of the event ADJ_BUILD_PF places ahead starts towards L2 (one 128-byte line per lane)
+                    const int sp = min(s + ADJ_BUILD_PF, cnt - 1);
+                    const int ip = __shfl_sync(0xffffffffu, my_i, sp), lp = __shfl_sync(0xffffffffu, my_lo, sp);
+                    const int j = (lp & ~15) + lane * 16;
+                    if (s + ADJ_BUILD_PF < cnt && j < ip) asm volatile("prefetch.global.L2 [%0];" ::"l"(a.pk + j));
+                }
                 for (int j = i - 1 - lane; j >= lo; j -= 64) {  // two rounds in flight
                     const int j2 = j - 32;
                     const unsigned long long pk = ldg_stream_u64(a.pk + j, pol_rd), pk2 = j2 >= lo ? ldg_stream_u64(a.pk + j2, pol_rd) : 0ull;
@@ -401,16 +405,19 @@ __global__ void __launch_bounds__(1024) k_adj_build(const AdjBuildArgs a) {
         for (int e0 = eb + wid * 32; e0 < ee; e0 += nw * 32) {
             int my_i = 0, my_lo = 0;
             double my_t = 0.0;
-            if (e0 + lane < ee) {
-                my_i = a.order[e0 + lane]; my_lo = a.lo[my_i]; my_t = a.t[my_i];
-                for (int j = my_lo & ~15; j < my_i; j += 16) {
-                    asm volatile("prefetch.global.L2 [%0];" ::"l"(a.pk + j));
-                    asm volatile("prefetch.global.L2 [%0];" ::"l"(a.t + j));
-                }
-            }
+            if (e0 + lane < ee) { my_i = a.order[e0 + lane]; my_lo = a.lo[my_i]; my_t = a.t[my_i]; }
             const int cnt = min(32, ee - e0);
             for (int s = 0; s < cnt; s++) {
                 const int i = __shfl_sync(0xffffffffu, my_i, s), lo = __shfl_sync(0xffffffffu, my_lo, s);
+                {   // lanes 0-15: the packed records, lanes 16-31: the times of the window ADJ_BUILD_PF events ahead
+                    const int sp = min(s + ADJ_BUILD_PF, cnt - 1);
+                    const int ip = __shfl_sync(0xffffffffu, my_i, sp), lp = __shfl_sync(0xffffffffu, my_lo, sp);
+                    const int j = (lp & ~15) + (lane & 15) * 16;
+                    if (s + ADJ_BUILD_PF < cnt && j < ip) {
+                        if (lane < 16) asm volatile("prefetch.global.L2 [%0];" ::"l"(a.pk + j));
+                        else asm volatile("prefetch.global.L2 [%0];" ::"l"(a.t + j));
+                    }
+                }
                 const double ti = __shfl_sync(0xffffffffu, my_t, s);
                 const unsigned le = (unsigned)(e0 + s - eb);
                 for (int j = i - 1 - lane; j >= lo; j -= 64) {  // two rounds in flight
