@@ -547,9 +547,17 @@ def run_ours(args, rank, world, local_rank):
         bpp = BYTES_PER_ADJ_PAIR
     adj_bytes = pairs * bpp
     dom = "adjacency" if med["adjacency"] >= max(med["loglik"], med["parents"]) else ("parents" if med["parents"] >= med["loglik"] else "loglik")
+    # DRAM bytes per launch of the dominant kernel from the committed `ncu --set full` capture of this command (same workload: pair counts agree)
+    traffic = None
+    try:
+        cap = json.load(open(os.path.join(ROOT, "profiles", "r02_ncu_dominant_kernel.json")))
+        if world == 1 and abs(cap["pairs"] - pairs) <= 0.02 * pairs:
+            traffic = cap["dram_bytes_per_launch"]
+    except (OSError, KeyError, ValueError):
+        pass
     if dom == "adjacency":
         roofline = {"kernel": "k_adj_sweep<LOGITNORMAL> (adjacency Gibbs sweep, continuous.jl:444-519)", "bound": "hbm", "achieved": adj_bytes / adj_s / 1e9, "peak": hbm,
-                    "unit": "GB/s", "frac": adj_bytes / adj_s / 1e9 / hbm, "traffic": None, "peak_source": hbm_src, "algorithmic_bytes_per_launch": adj_bytes,
+                    "unit": "GB/s", "frac": adj_bytes / adj_s / 1e9 / hbm, "traffic": traffic, "peak_source": hbm_src, "algorithmic_bytes_per_launch": adj_bytes,
                     "algorithmic_unit": "%.0f B per cached (child event, window predecessor) pair (u16 event index + %s) x %.4g pairs, streamed once per sweep"
                                         % (bpp, "f64 logit + f64 Jacobian of the lag" if bpp == 18.0 else "f64 lag", pairs),
                     "binding_resource": "HBM stream of the cached pairs plus instruction issue: one table-driven exp, one shared-memory intensity look-up and two "
