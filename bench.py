@@ -499,8 +499,13 @@ def run_ours(args, rank, world, local_rank):
         w0 = time.perf_counter()
         set_params()
         w1 = time.perf_counter()
-        evf = upload(0, n_total, 0, 1)
-        evs = evf if world == 1 else upload_shard()
+        if world == 1:
+            evf = upload(0, n_total, 0, 1)
+            evs = evf
+        else:  # every rank uploads its own shard only; the replicated stream of the adjacency sweep is gathered over NVLink
+            evs = upload_shard()
+            evf = ctypes.c_void_p()
+            ctx.check(lib.nhp_comm_allgather_events(ctx.h, evs, ctypes.byref(evf)))
         w2 = time.perf_counter()
         ll = ctypes.c_double()
         ctx.check(lib.nhp_cont_loglik(ctx.h, evs, 0, ctypes.byref(ll)))
@@ -523,7 +528,7 @@ def run_ours(args, rank, world, local_rank):
     if world > 1:
         dist.all_reduce(e2e_ms, op=dist.ReduceOp.MAX)
     e2e_value = n_total * e2e_steps / (float(e2e_ms.item()) * 1e-3)
-    h2d = (n_total + (0 if world == 1 else n + n_halo)) * 16 + (K + 4 * K2) * 8
+    h2d = (n_total if world == 1 else n + n_halo) * 16 + (K + 4 * K2) * 8  # per rank
     d2h = 8 + (K + 4 * K2) * 8
 
     if rank != 0:
@@ -588,8 +593,9 @@ def run_ours(args, rank, world, local_rank):
             "ms_per_step": ms_step, "higher_is_better": True, "scaling": args.scaling, "vs_baseline": None, "dtype": "f64",
             "data": "synthetic", "config": workload_config(args, world, n_total, n), "clocks": sampler.summary(),
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "steps": e2e_steps,
-                    "what": "nhp_cont_params_set + nhp_events_upload (pinned host buffers) + nhp_cont_loglik + nhp_cont_gibbs_sweep (builds the adjacency "
-                            "structure of the fresh handle) + nhp_cont_params_get (the sample)",
+                    "what": "nhp_cont_params_set + nhp_events_upload (pinned host buffers; N > 1: this rank's time shard, then nhp_comm_allgather_events over "
+                            "NVLink for the replicated stream) + nhp_cont_loglik + nhp_cont_gibbs_sweep (builds the adjacency structure of the fresh handle) + "
+                            "nhp_cont_params_get (the sample); bytes are per rank",
                     "host_ms_per_step": e2e_parts,
                     "data_resident": {"value": e2e_once_value, "unit": UNIT, "h2d_bytes_per_step": (K + 4 * K2) * 8, "d2h_bytes_per_step": d2h, "steps": once_steps,
                                       "what": "the events stay on the device (as in mcmc!: data is uploaded once); per step nhp_cont_params_set from host "

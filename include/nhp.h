@@ -201,6 +201,11 @@ int nhp_comm_allreduce_stats(nhp_ctx *ctx, int phase);
 /* sum of a small host vector over the ranks (log-likelihood shares of nhp_cont_loglik, ...) */
 int nhp_comm_allreduce_host(nhp_ctx *ctx, double *inout, int64_t n);
 int nhp_comm_allgather_adjacency(nhp_ctx *ctx);
+/* The replicated stream from the time shards: every rank passes the shard it uploaded (consecutive pieces of one stream:
+ * index_base of rank r = number of own events of the ranks before it) and receives an ordinary unsharded events handle with all
+ * events -- the own events of the shards travel over NVLink (ncclBroadcast per rank) instead of every rank uploading the whole
+ * stream through PCIe.  Needs a communicator; a single GPU uses its handle as is. */
+int nhp_comm_allgather_events(nhp_ctx *ctx, nhp_events *ev_shard, nhp_events **out);
 /* hyper as for nhp_cont_resample_params; net_alpha > 0: BernoulliNetworkModel with rho ~ Beta(net_alpha, net_beta) prior
  * (networks.jl:45-54, 72-78), else link probability 1 (DenseNetworkModel).  ev_full (the unsharded stream, replicated on
  * every rank) is only used by network processes; pass ev_shard itself on a single GPU. */

@@ -21,6 +21,9 @@ struct NcclApi {
     ncclResult_t (*CommDestroy)(ncclComm_t) = nullptr;
     ncclResult_t (*AllReduce)(const void *, void *, size_t, ncclDataType_t, ncclRedOp_t, ncclComm_t, cudaStream_t) = nullptr;
     ncclResult_t (*AllGather)(const void *, void *, size_t, ncclDataType_t, ncclComm_t, cudaStream_t) = nullptr;
+    ncclResult_t (*Broadcast)(const void *, void *, size_t, ncclDataType_t, int, ncclComm_t, cudaStream_t) = nullptr;
+    ncclResult_t (*GroupStart)() = nullptr;
+    ncclResult_t (*GroupEnd)() = nullptr;
     const char *(*GetErrorString)(ncclResult_t) = nullptr;
 };
 static NcclApi g_nccl;
@@ -39,7 +42,10 @@ static int nccl_load(nhp_ctx *ctx) {
     a.AllReduce = (decltype(a.AllReduce))dlsym(h, "ncclAllReduce");
     a.AllGather = (decltype(a.AllGather))dlsym(h, "ncclAllGather");
     a.GetErrorString = (decltype(a.GetErrorString))dlsym(h, "ncclGetErrorString");
-    if (!a.GetUniqueId || !a.CommInitRank || !a.CommDestroy || !a.AllReduce || !a.AllGather || !a.GetErrorString)
+    a.Broadcast = (decltype(a.Broadcast))dlsym(h, "ncclBroadcast");
+    a.GroupStart = (decltype(a.GroupStart))dlsym(h, "ncclGroupStart");
+    a.GroupEnd = (decltype(a.GroupEnd))dlsym(h, "ncclGroupEnd");
+    if (!a.GetUniqueId || !a.CommInitRank || !a.CommDestroy || !a.AllReduce || !a.AllGather || !a.GetErrorString || !a.Broadcast || !a.GroupStart || !a.GroupEnd)
         return nhp_fail(ctx, NHP_ERR_UNSUPPORTED, "nhp_comm: libnccl.so.2 lacks a required symbol");
     g_nccl = a;
     return NHP_OK;
@@ -171,6 +177,50 @@ extern "C" int nhp_comm_allgather_adjacency(nhp_ctx *ctx) {
         NHP_CUDA(ctx, cudaGetLastError());
     }
     return nhp_cont_adjacency_commit(ctx);
+}
+
+// The replicated stream of the adjacency sweep from the time shards: every rank has uploaded its own shard (events_upload with
+// n_halo / index_base), the shards' own events travel over NVLink (one ncclBroadcast per rank and array, grouped) instead of
+// every rank pulling the whole stream through PCIe.  The result is an ordinary unsharded events handle on every rank.
+int nhp_events_from_device(nhp_ctx *ctx, const double *d_t, const int *d_c, int64_t n, double duration, int64_t K, nhp_events **out);  // nhp_context.cu
+extern "C" int nhp_comm_allgather_events(nhp_ctx *ctx, nhp_events *ev_shard, nhp_events **out) {
+    NHP_CHECK(ctx, ctx != nullptr, NHP_ERR_INVALID, "ctx is NULL");
+    NHP_CHECK(ctx, ev_shard != nullptr && out != nullptr, NHP_ERR_INVALID, "nhp_comm_allgather_events: NULL argument");
+    *out = nullptr;
+    NHP_CHECK(ctx, ctx->comm != nullptr && ctx->nranks > 1, NHP_ERR_STATE, "nhp_comm_allgather_events: the context has no communicator (a single GPU uses its handle as is)");
+    NHP_CUDA(ctx, cudaSetDevice(ctx->device));
+    const int R = ctx->nranks, r = ctx->rank;
+    std::vector<double> cnt((size_t)R + 1, 0.0);
+    cnt[r] = (double)(ev_shard->n - ev_shard->n_halo);
+    cnt[R] = r == 0 ? (double)(ev_shard->index_base + ev_shard->n_halo) : 0.0;  // index_base counts from the first passed (halo) event
+    NHP_TRY(nhp_comm_allreduce_host(ctx, cnt.data(), R + 1));
+    std::vector<int64_t> off((size_t)R + 1, 0);
+    for (int q = 0; q < R; q++) off[q + 1] = off[q] + (int64_t)cnt[q];
+    const int64_t n_total = off[R];
+    NHP_CHECK(ctx, cnt[R] == 0.0 && ev_shard->index_base + ev_shard->n_halo == off[r], NHP_ERR_INVALID,
+              "nhp_comm_allgather_events: the shards are not the consecutive pieces of one stream (rank %d: first own event %lld, expected %lld)", r,
+              (long long)(ev_shard->index_base + ev_shard->n_halo), (long long)off[r]);
+    NHP_CHECK(ctx, n_total < (int64_t)2147483000, NHP_ERR_INVALID, "nhp_comm_allgather_events: %lld events in total (limit 2^31)", (long long)n_total);
+    cudaStream_t s = ctx->stream;
+    double *d_t = nullptr;
+    int *d_c = nullptr;
+    NHP_CUDA(ctx, cudaMallocAsync(&d_t, (size_t)std::max<int64_t>(n_total, 1) * sizeof(double), s));
+    if (cudaMallocAsync(&d_c, (size_t)std::max<int64_t>(n_total, 1) * sizeof(int), s) != cudaSuccess) {
+        cudaFreeAsync(d_t, s);
+        return nhp_fail(ctx, NHP_ERR_CUDA, "nhp_comm_allgather_events: cudaMallocAsync failed");
+    }
+    auto fin = [&](int rc) { cudaFreeAsync(d_t, s); cudaFreeAsync(d_c, s); return rc; };
+    ncclResult_t nr = g_nccl.GroupStart();
+    for (int q = 0; q < R && nr == ncclSuccess; q++) {
+        const size_t m = (size_t)(off[q + 1] - off[q]);
+        if (m == 0) continue;
+        nr = g_nccl.Broadcast(ev_shard->d_t + ev_shard->n_halo, d_t + off[q], m, ncclFloat64, q, (ncclComm_t)ctx->comm, s);
+        if (nr == ncclSuccess) nr = g_nccl.Broadcast(ev_shard->d_c + ev_shard->n_halo, d_c + off[q], m, ncclInt32, q, (ncclComm_t)ctx->comm, s);
+    }
+    const ncclResult_t ne = g_nccl.GroupEnd();
+    if (nr != ncclSuccess || ne != ncclSuccess)
+        return fin(nhp_fail(ctx, NHP_ERR_CUDA, "nhp_comm_allgather_events: NCCL broadcast failed: %s", g_nccl.GetErrorString(nr != ncclSuccess ? nr : ne)));
+    return fin(nhp_events_from_device(ctx, d_t, d_c, n_total, ev_shard->duration, ev_shard->K, out));
 }
 
 // One whole Gibbs sweep of `resample!` (continuous.jl:202-208 / 350-358) on the device, for 1..N GPUs with one call

@@ -65,6 +65,7 @@ PROTOTYPES = {
     "nhp_comm_allreduce_stats": (c_int, [c_void_p, c_int]),
     "nhp_comm_allreduce_host": (c_int, [c_void_p, c_void_p, c_int64]),
     "nhp_comm_allgather_adjacency": (c_int, [c_void_p]),
+    "nhp_comm_allgather_events": (c_int, [c_void_p, c_void_p, ctypes.POINTER(c_void_p)]),
     "nhp_cont_gibbs_sweep": (c_int, [c_void_p, c_void_p, c_void_p, c_uint64, c_uint64, c_double, c_void_p, c_int, c_double, c_double]),
     "nhp_cont_stats_dev": (c_int, [c_void_p, c_int, POINTER(c_void_p), c_int64_p]),
     "nhp_cont_suffstats_second_pass": (c_int, [c_void_p, c_void_p]),

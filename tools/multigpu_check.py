@@ -75,6 +75,20 @@ def main():
     res["S2_max_rel_err"] = float(np.max(np.abs(ref[4] - got[4]) / np.maximum(1.0, np.abs(ref[4]))))
     ok &= res["count_mismatches"] == 0 and res["S1_max_rel_err"] < 1e-11 and res["S2_max_rel_err"] < 1e-9
 
+    # the replicated stream gathered from the shards over NVLink == the uploaded full stream
+    if world > 1:
+        gathered = ctypes.c_void_p()
+        ctx.check(lib.nhp_comm_allgather_events(ctx.h, shard.h, ctypes.byref(gathered)))
+        tg, cg = np.empty(n), np.empty(n, dtype=np.int64)
+        Tg = ctypes.c_double()
+        ctx.check(lib.nhp_events_download(ctx.h, gathered, _ptr(tg), cg.ctypes.data_as(ctypes.c_void_p), ctypes.byref(Tg)))
+        ll_g = ctypes.c_double()
+        ctx.check(lib.nhp_cont_loglik(ctx.h, gathered, 0, ctypes.byref(ll_g)))
+        res["gathered_stream_mismatches"] = int(np.count_nonzero(tg != t) + np.count_nonzero(cg != nodes)) + int(lib.nhp_events_count(gathered) != n)
+        res["gathered_loglik_rel_err"] = abs(ll_g.value - ll_full.value) / abs(ll_full.value)
+        ok &= res["gathered_stream_mismatches"] == 0 and res["gathered_loglik_rel_err"] < 1e-14
+        lib.nhp_events_free(ctx.h, gathered)
+
     # adjacency: full sweep on this GPU vs column partition + all-gather
     def get_A():
         out = np.empty(K * K)
