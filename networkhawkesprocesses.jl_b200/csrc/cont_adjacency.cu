@@ -532,7 +532,7 @@ template <int PRE> __device__ __forceinline__ void adj_pf_range(const unsigned s
 template <int KIND, int PRE>
 __device__ __forceinline__ bool adj_group(const typename EntryOf<KIND>::type &en, const unsigned short *__restrict__ ei, const double *__restrict__ ex,
                                           int eb, int b1, int lane, unsigned ii, double x, double y, double D,
-                                          const FastTables *ft, double &gsum) {
+                                          const FastTables *ft, double &gsum, int next_first = -1) {  // next_first: index word of entry eb + 32 when the caller already holds it
     const bool valid = eb + lane < b1;
     double v = adj_value<KIND, PRE>(en, x, y, D, ft);
     v = valid ? v : 0.0;
@@ -550,7 +550,7 @@ __device__ __forceinline__ bool adj_group(const typename EntryOf<KIND>::type &en
         }
     }
     if (eb + 32 < b1) {  // warp-uniform: does the run that reaches lane 31 go on in the section's next group?  (one broadcast load)
-        if (__ldg(ei + eb + 32) & 0x8000u) {
+        if ((next_first >= 0 ? (unsigned)next_first : (unsigned)__ldg(ei + eb + 32)) & 0x8000u) {
             if (head && lane + runlen == 31)
                 for (int e2 = eb + 32; e2 < b1 && (__ldg(ei + e2) & 0x8000u); e2++) { double x2, y2; adj_ld<PRE>(ex, e2, x2, y2); gsum += adj_value<KIND, PRE>(en, x2, y2, D, ft); }
         }
@@ -689,8 +689,8 @@ __device__ __noinline__ double2 adj_direct(const typename EntryOf<KIND>::type en
 // add sgn * (this parent's contribution) to the intensities of a bucket's events: all warps of the CTA, groups warp, warp + 32, ...
 template <int KIND, int PRE>
 __device__ __forceinline__ void adj_apply(const typename EntryOf<KIND>::type &en, const unsigned short *__restrict__ ei, const double *__restrict__ ex,
-                                          const int s0, const int sm, const int s1, const int warp, const int lane,
-                                          const double sgn, double *lam, const double D, const FastTables *ft) {
+                                          const int s0, const int sm, const int rs, const int s1, const int warp, const int lane,
+                                          const double sgn, double *lam, const double D, const FastTables *ft) {  // singles [s0, sm), run groups from rs (a group boundary) to s1
     for (int k = s0 + warp * 32 + lane; k < sm; k += ADJ_THREADS) {  // singles: distinct events, no bookkeeping
         const unsigned ii = __ldg(ei + k);
         double x, y;
@@ -698,7 +698,7 @@ __device__ __forceinline__ void adj_apply(const typename EntryOf<KIND>::type &en
         const double v = adj_value<KIND, PRE>(en, x, y, D, ft);
         if (v > 0.0) lam[ii] += sgn * v;
     }
-    for (int eb = sm + warp * 32; eb < s1; eb += ADJ_THREADS) {      // runs: the head carries the run's total
+    for (int eb = rs + warp * 32; eb < s1; eb += ADJ_THREADS) {      // runs: the head carries the run's total
         const bool valid = eb + lane < s1;
         const unsigned ii = valid ? (unsigned)__ldg(ei + eb + lane) : 0u;
         double x = PRE ? 0.0 : -1.0, y = 0.0;
@@ -793,7 +793,7 @@ template <int KIND, int PRE, bool CL> __global__ void __launch_bounds__(ADJ_THRE
                     const int b0 = bo[2 * p], bm = bo[2 * p + 1], b1 = bo[2 * p + 2];
                     if (b1 != b0) {
                         const E en = load_entry(col + p);
-                        adj_apply<KIND, PRE>(en, ei, ex, b0, bm, b1, warp, lane, 1.0, lam_s, a.D, ft);  // one head per event and bucket
+                        adj_apply<KIND, PRE>(en, ei, ex, b0, bm, bm, b1, warp, lane, 1.0, lam_s, a.D, ft);  // one head per event and bucket
                     }
                     __syncthreads();  // the next parent may touch the same events
                 }
@@ -963,7 +963,7 @@ template <int KIND, int PRE, bool CL> __global__ void __launch_bounds__(ADJ_THRE
                     const int64_t vb = a.vbase[v0 + g];
                     const unsigned short *ei = a.ent_i + vb;
                     const double *ex = a.ent_x + (PRE ? 2 : 1) * vb;
-                    adj_apply<KIND, PRE>(enf, ei, ex, b0, bm, b1, warp, lane, sgn, resident ? lam_s : lamg + (size_t)g * csz, a.D, ft);
+                    adj_apply<KIND, PRE>(enf, ei, ex, b0, bm, bm, b1, warp, lane, sgn, resident ? lam_s : lamg + (size_t)g * csz, a.D, ft);
                 }
                 __syncthreads();  // the next flipped bucket may touch the same events
             }
@@ -980,6 +980,121 @@ template <int KIND, int PRE, bool CL> __global__ void __launch_bounds__(ADJ_THRE
         atomicAdd(a.stat + 0, (unsigned long long)n_steps); atomicAdd(a.stat + 1, (unsigned long long)n_batches);
         atomicAdd(a.stat + 2, (unsigned long long)n_flips); atomicAdd(a.stat + 3, (unsigned long long)n_redo);
     }
+}
+
+// ---------------------------------------------------------------------------------------
+// log-likelihood of a network process from the cached structure
+// ---------------------------------------------------------------------------------------
+// lambda_i = lambda0 + sum over the links that are ON of the bucket's contributions: with the pairs already bucketed by
+// (child column, parent node) a sparse network touches only the buckets of its active links -- 5 % of the structure at config 4
+// (5.8 GB instead of 64 probes per event over the whole stream).  One CTA per virtual column (chunks are independent here), the
+// chunk's intensities in shared memory, buckets applied one after the other (two ahead prefetched to L2), then sum log lambda in
+// a fixed order.  The compensator comes from the per-node counts as in the window sweeps.
+struct AdjLoglikArgs {
+    const int *node_ptr; int K; const void *table; const double *lambda0; const uint32_t *abits; int words; double D;
+    const int *vstart, *vnode; const int64_t *vbase; const int *boff; const unsigned short *ent_i; const double *ent_x;
+    int nv, chunk_max; double *partials; int *flag;
+};
+template <int KIND, int PRE> __global__ void __launch_bounds__(ADJ_THREADS, 1) k_adj_loglik(const AdjLoglikArgs a) {
+    typedef typename EntryOf<KIND>::type E;
+    extern __shared__ __align__(16) double lam_s[];  // [chunk_max] intensities | [K] active parents of the column
+    __shared__ FastTables s_ft;
+    __shared__ double s_red[ADJ_THREADS / 32];
+    __shared__ int s_non;
+    fast_tables_load(&s_ft);
+    const FastTables *ft = &s_ft;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int K = a.K, brow = 2 * K + 1;
+    int *s_on = reinterpret_cast<int *>(lam_s + a.chunk_max);
+    double total = 0.0;  // thread 0: this CTA's running sum (static round-robin over the virtual columns: a fixed order)
+    for (int v = blockIdx.x; v < a.nv; v += gridDim.x) {
+        const int c = a.vnode[v], g = v - a.vstart[c], G = a.vstart[c + 1] - a.vstart[c];
+        const int ne = a.node_ptr[c + 1] - a.node_ptr[c], csz = adj_chunk_size(ne, G);
+        const int len = max(0, min(csz, ne - g * csz));
+        const double lam0 = a.lambda0[c];
+        __syncthreads();
+        for (int e = tid; e < len; e += ADJ_THREADS) lam_s[e] = lam0;
+        if (warp == 0) {  // the column's active parents, in order
+            int non = 0;
+            const uint32_t *row = a.abits + (size_t)c * a.words;
+            for (int w0 = 0; w0 < a.words; w0 += 32) {
+                const uint32_t bits = w0 + lane < a.words ? row[w0 + lane] : 0u;
+                int x = __popc(bits);
+#pragma unroll
+                for (int d = 1; d < 32; d <<= 1) { const int y = __shfl_up_sync(0xffffffffu, x, d); if (lane >= d) x += y; }
+                int o = non + x - __popc(bits);
+                for (uint32_t b = bits; b; b &= b - 1) { const int p = (w0 + lane) * 32 + __ffs(b) - 1; if (p < K) s_on[o++] = p; }
+                non += __shfl_sync(0xffffffffu, x, 31);
+            }
+            if (lane == 0) s_non = non;
+        }
+        __syncthreads();
+        const int non = s_non;
+        const int *bo = a.boff + (int64_t)v * brow;
+        const int64_t vb = a.vbase[v];
+        const unsigned short *ei = a.ent_i + vb;
+        const double *ex = a.ent_x + (PRE ? 2 : 1) * vb;
+        const E *col = reinterpret_cast<const E *>(a.table) + (size_t)c * K;
+        // the active buckets one after the other, the two behind the current one on their way to L2
+        for (int j = 0; j < min(2, non); j++) adj_pf_range<PRE>(ei, ex, bo[2 * s_on[j]], bo[2 * s_on[j] + 2], tid);
+        for (int j = 0; j < non; j++) {
+            if (j + 2 < non) adj_pf_range<PRE>(ei, ex, bo[2 * s_on[j + 2]], bo[2 * s_on[j + 2] + 2], tid);
+            const int p = s_on[j];
+            const int b0 = bo[2 * p], bm = bo[2 * p + 1], b1 = bo[2 * p + 2];
+            if (b1 != b0) {
+                const E en = load_entry(col + p);
+                adj_apply<KIND, PRE>(en, ei, ex, b0, bm, bm, b1, warp, lane, 1.0, lam_s, a.D, ft);  // one head per event and bucket
+            }
+            __syncthreads();  // the next parent may touch the same events
+        }
+        double acc = 0.0;
+        for (int e = tid; e < len; e += ADJ_THREADS) {
+            const double l = lam_s[e];
+            if (!(l > 0.0) || l > 1.7976931348623157e308) atomicOr(a.flag, 8);
+            acc += fast_log(l, ft);
+        }
+        acc = warp_sum(acc);
+        if (lane == 0) s_red[warp] = acc;
+        __syncthreads();
+        if (tid == 0) {
+            double r = 0.0;
+            for (int w = 0; w < ADJ_THREADS / 32; w++) r += s_red[w];
+            total += r;
+        }
+    }
+    if (tid == 0) { a.partials[2 * (size_t)blockIdx.x] = total; a.partials[2 * (size_t)blockIdx.x + 1] = 0.0; }
+}
+
+// Log-likelihood through the cached structure when it exists for this handle, covers every column and the horizon, and the
+// network is sparse enough that streaming its active buckets beats the window sweep.  Returns 1 when it does not apply.
+int nhp_cont_try_adj_loglik(nhp_ctx *ctx, nhp_events *ev, SweepArgs &sa, int *grid_out) {
+    { const char *e = getenv("NHP_ADJ_LOGLIK"); if (e && atoi(e) == 0) return 1; }
+    if (!ctx->has_A || !ev->d_adj_i || ev->adj_cb != 0 || ev->adj_cs != 1 || ev->n_halo != 0 || ev->adj_cluster < 0) return 1;
+    if (!(ctx->density <= 0.25) || !(ev->adj_horizon >= sa.horizon) || sa.jmin > 0) return 1;
+    if (ctx->kind == NHP_EXPONENTIAL && ev->adj_horizon != sa.horizon && !(sa.horizon < ctx->dtmax)) return 1;  // only a cut-off horizon may be exceeded
+    const int64_t K = ctx->K;
+    AdjLoglikArgs a;
+    a.node_ptr = ev->d_node_ptr; a.K = (int)K; a.table = sa.table; a.lambda0 = sa.lambda0; a.abits = ctx->d_abits; a.words = (int)ctx->abits_words; a.D = ctx->dtmax;
+    a.vstart = ev->d_adj_vstart; a.vnode = ev->d_adj_vnode; a.vbase = ev->d_adj_vbase; a.boff = ev->d_adj_boff; a.ent_i = ev->d_adj_i; a.ent_x = ev->d_adj_dt;
+    a.nv = (int)ev->adj_nv; a.chunk_max = (ev->adj_chunk_max + 1) & ~1; a.partials = sa.partials; a.flag = sa.flag;
+    const size_t smem = (size_t)a.chunk_max * sizeof(double) + (size_t)K * sizeof(int) + 16;
+    if (smem > (size_t)ctx->smem_optin - 4096) return 1;
+    NHP_CUDA(ctx, fast_tables_upload(ctx->stream));
+    const int grid = (int)std::min<int64_t>(ev->adj_nv, ctx->sm_count);
+    if (ctx->kind == NHP_EXPONENTIAL) {
+        NHP_CUDA(ctx, cudaFuncSetAttribute(k_adj_loglik<NHP_EXPONENTIAL, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        k_adj_loglik<NHP_EXPONENTIAL, 0><<<grid, ADJ_THREADS, smem, ctx->stream>>>(a);
+    } else if (ev->adj_kind == 1) {
+        NHP_CUDA(ctx, cudaFuncSetAttribute(k_adj_loglik<NHP_LOGITNORMAL, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        k_adj_loglik<NHP_LOGITNORMAL, 1><<<grid, ADJ_THREADS, smem, ctx->stream>>>(a);
+    } else {
+        NHP_CUDA(ctx, cudaFuncSetAttribute(k_adj_loglik<NHP_LOGITNORMAL, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        k_adj_loglik<NHP_LOGITNORMAL, 0><<<grid, ADJ_THREADS, smem, ctx->stream>>>(a);
+    }
+    NHP_LAUNCHED(ctx);
+    NHP_CUDA(ctx, cudaGetLastError());
+    *grid_out = grid;
+    return NHP_OK;
 }
 
 __global__ void k_iota(int *v, int64_t n) {

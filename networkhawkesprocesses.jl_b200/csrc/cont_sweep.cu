@@ -468,6 +468,7 @@ int nhp_cont_run_loglik(nhp_ctx *ctx, nhp_events *ev, int recursive) {
     int sgrid = 0;
     // recursive Exponential on unsharded data: the chunked scan when it beats the cut-off window (cont_exp_scan.cu)
     int sp = (recursive && ctx->kind == NHP_EXPONENTIAL) ? nhp_cont_try_exp_scan(ctx, ev, a, &sgrid) : 1;
+    if (sp == 1 && !recursive) sp = nhp_cont_try_adj_loglik(ctx, ev, a, &sgrid);  // sparse network with a cached pair structure: active buckets only
     if (sp == 1) sp = try_special(ctx, ev, a, 0, &sgrid);
     if (sp < 0) return sp;
     if (sp == NHP_OK) p.grid = sgrid;

@@ -189,3 +189,42 @@ def test_device_chain_network_process_runs_and_stays_finite():
     assert len(res.samples) == 6 and all(np.all(np.isfinite(s)) for s in res.samples)
     assert set(np.unique(proc.adjacency_matrix)) <= {0.0, 1.0}
     assert 0.0 < proc.network.rho < 1.0
+
+
+@pytest.mark.parametrize("kind,pre,chunk", [("ln", "1", None), ("ln", "0", 64), ("exp", "1", 7), ("ln", "1", 64)])
+def test_loglikelihood_through_the_cached_structure_matches_oracle(monkeypatch, kind, pre, chunk):
+    """Once a handle carries the pair structure, the log-likelihood of a sparse network streams the buckets of the active links only
+    (k_adj_loglik): same value as the oracle and as the window sweep, with all payload / chunking variants."""
+    import ctypes
+    monkeypatch.setenv("NHP_ADJ_PRE", pre)
+    if chunk is not None:
+        monkeypatch.setenv("NHP_ADJ_CHUNK", str(chunk))
+    K, n, rho = 23, 5000, 0.15
+    t, nodes, T = synth.poisson_stream(n, K, 70.0, 21)
+    proc, om = make_ln(K, 5, density=rho, wmax=2.0 / (K * rho)) if kind == "ln" else make_exp(K, 5, density=rho, wmax=2.0 / (K * rho), dtmax=1.0)
+    proc.network = nhp.BernoulliNetworkModel(rho, K)
+    ctx = proc._ctx()
+    d = proc.upload((t, nodes, T))
+    proc._push(ctx)
+    ll = ctypes.c_double()
+    ctx.check(ctx.lib.nhp_cont_loglik(ctx.h, d.h, 0, ctypes.byref(ll)))          # window sweep: no structure yet
+    ll_window = ll.value
+    ctx.check(ctx.lib.nhp_cont_resample_adjacency_dev(ctx.h, d.h, rho, 5, 1, 0, 1, 1))  # builds the structure, changes A
+    nhp.pull_params_(proc, ctx)
+    A1 = proc.adjacency_matrix.copy()
+    assert 0 < np.count_nonzero(A1 * proc.weights.W) <= 0.25 * K * K
+    launches = ctx.launches
+    ctx.check(ctx.lib.nhp_cont_loglik(ctx.h, d.h, 0, ctypes.byref(ll)))          # structure path
+    ll_struct = ll.value
+    monkeypatch.setenv("NHP_ADJ_LOGLIK", "0")
+    ctx.check(ctx.lib.nhp_cont_loglik(ctx.h, d.h, 0, ctypes.byref(ll)))          # window sweep, new A
+    ll_window1 = ll.value
+    if kind == "ln":
+        om1 = orc.Cont(1, proc.baseline.lam, proc.weights.W, proc.impulses.mu, proc.impulses.tau, A=A1, dtmax=1.0)
+    else:
+        om1 = orc.Cont(0, proc.baseline.lam, proc.weights.W, proc.impulses.theta, A=A1, dtmax=1.0)
+    ref = om1.loglik(t, nodes, T, recursive=False)
+    assert ll_struct == pytest.approx(ref, rel=1e-10)
+    assert ll_struct == pytest.approx(ll_window1, rel=1e-12)
+    assert ll_window != ll_window1 or np.array_equal(A1, proc.adjacency_matrix)
+    d.free()
