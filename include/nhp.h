@@ -179,6 +179,17 @@ int nhp_cont_resample_network(nhp_ctx *ctx, uint64_t seed, uint64_t counter, dou
 int nhp_cont_resample_params(nhp_ctx *ctx, nhp_events *ev, uint64_t seed, uint64_t counter, double duration, const double *hyper, int n_hyper, int flags);
 /* Current parameters in the layouts of nhp_cont_params_set; any pointer may be NULL. */
 int nhp_cont_params_get(nhp_ctx *ctx, double *lambda0, double *W, double *A, double *p1, double *p2);
+/* Device-side sample trace of `mcmc!` (inference.jl:49-70; the reference pushes params(process) = [rho; lambda0; W; theta | mu, tau;
+ * vec(A)] per sweep, continuous.jl:325-333).  _begin reserves `capacity` slots for the context's current model (real-valued
+ * parameters as they are, the adjacency matrix bit-packed: K^2 / 8 bytes); _push appends the context's current parameters
+ * (device-to-device on the context's stream, no host synchronisation) -- nhp_cont_gibbs_sweep does it by itself while a trace is
+ * open; _read copies samples [first, first + count) to the host, one sample after the other in the layouts of
+ * nhp_cont_params_get (rho[count], lambda0[count*K], W | A | p1 | p2 [count*K*K]; any pointer may be NULL). */
+int nhp_cont_trace_begin(nhp_ctx *ctx, int64_t capacity);
+int nhp_cont_trace_push(nhp_ctx *ctx);
+int nhp_cont_trace_count(const nhp_ctx *ctx, int64_t *count, int64_t *capacity);
+int nhp_cont_trace_read(nhp_ctx *ctx, int64_t first, int64_t count, double *rho, double *lambda0, double *W, double *A, double *p1, double *p2);
+int nhp_cont_trace_free(nhp_ctx *ctx);
 
 /* ---- multi-GPU (one process and one context per GPU; NCCL over NVLink, loaded with dlopen) ---------------------
  * SURVEY.md section 8e.  Time shards (nhp_events_upload with n_halo / index_base) carry the log-likelihood, the parent

@@ -247,6 +247,7 @@ extern "C" int nhp_cont_gibbs_sweep(nhp_ctx *ctx, nhp_events *ev_shard, nhp_even
         NHP_TRY(nhp_comm_allgather_adjacency(ctx));
         if (net_alpha > 0.0) NHP_TRY(nhp_cont_resample_network(ctx, seed, counter, net_alpha, net_beta, nullptr));
     }
+    if (ctx->trace_cap > 0 && ctx->trace_len < ctx->trace_cap) NHP_TRY(nhp_cont_trace_push(ctx));  // the sample of this sweep stays on the device
     return NHP_OK;
 }
 

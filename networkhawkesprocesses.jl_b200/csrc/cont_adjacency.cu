@@ -482,7 +482,7 @@ struct AdjSweepArgs {
     int chunk_max;         // doubles of shared memory in front of the adjacency bit row
     int *flag, *next; unsigned long long *stat;
     int col_begin, col_stride, ncols;
-    int s0;
+    int s0, lmax;   // first batch size; log2 of the largest
 };
 
 // thread-block cluster primitives (distributed shared memory of the CTAs that share a column)
@@ -715,10 +715,10 @@ template <int KIND, int PRE, bool CL> __global__ void __launch_bounds__(ADJ_THRE
     typedef typename EntryOf<KIND>::type E;
     extern __shared__ __align__(16) double lam_s[];  // [chunk_max] intensities of the resident chunk | adjacency bits of the column
     __shared__ FastTables s_ft;
-    __shared__ double s_part[32], s_pmax[32];
-    __shared__ double s_cl[2][ADJ_CLUSTER_MAX][32], s_cm[2][ADJ_CLUSTER_MAX][32];  // [batch parity][source CTA][bucket of the batch]: sums, largest contributions
-    __shared__ int s_col, s_first;
-    __shared__ unsigned s_mask, s_onmask;
+    __shared__ double s_part[2][32], s_pmax[2][32];                                // [batch parity][warp]: this CTA's partial sums, largest contributions
+    __shared__ double s_cl[2][ADJ_CLUSTER_MAX][32], s_cm[2][ADJ_CLUSTER_MAX][32];  // [batch parity][source CTA][bucket of the batch]: the same, cluster-wide
+    __shared__ double s_dec[2][4][32];                                             // [batch parity][W Mn, logit rho, u, logit u][bucket of the batch]
+    __shared__ int s_col;
     fast_tables_load(&s_ft);
     const FastTables *ft = &s_ft;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -813,14 +813,18 @@ template <int KIND, int PRE, bool CL> __global__ void __launch_bounds__(ADJ_THRE
             const int q = p + qi;
             const bool act = qi < Sc;
             // the deciding lanes fetch their inputs before the batch so that the latency hides behind it
-            double d_wmn = 0.0, d_lrho = 0.0, d_u = 2.0, d_lu = 0.0;  // logit(u): delta - logit(u) is the margin by which the decision u <= sigmoid(delta) holds
+            // (into shared memory: every warp takes the decisions for itself behind the batch's one barrier)
             if (warp == 0 && lane < Sc) {
+                double d0, d1, d2, d3;
                 const double *dp = reinterpret_cast<const double *>(a.dec + ((p + lane) + (int64_t)K * c));
-                asm("ld.global.nc.v4.f64 {%0,%1,%2,%3}, [%4];" : "=d"(d_wmn), "=d"(d_lrho), "=d"(d_u), "=d"(d_lu) : "l"(dp));
+                asm("ld.global.nc.v4.f64 {%0,%1,%2,%3}, [%4];" : "=d"(d0), "=d"(d1), "=d"(d2), "=d"(d3) : "l"(dp));
+                s_dec[parity][0][lane] = d0; s_dec[parity][1][lane] = d1; s_dec[parity][2][lane] = d2; s_dec[parity][3][lane] = d3;
             }
             E en = E();
             bool on = false;
             if (act) { en = load_entry(col + q); on = (s_ab[q >> 5] >> (q & 31)) & 1u; }
+            // lane = bucket: the state of its link now (warp 0 changes the bits while slower warps still take their decisions)
+            const bool old_on = lane < Sc && ((s_ab[(p + lane) >> 5] >> ((p + lane) & 31)) & 1u);
             const double onf = on ? 1.0 : 0.0, floor_ = on ? lam0 : -__longlong_as_double(0x7ff0000000000000LL);
             if (S <= 4 && resident) {
                 // short batches are latency bound: pull the entries of the buckets that can come next (they follow in memory) into L2 now
@@ -869,25 +873,36 @@ template <int KIND, int PRE, bool CL> __global__ void __launch_bounds__(ADJ_THRE
             acc = warp_sum(acc);
 #pragma unroll
             for (int d = 16; d >= 1; d >>= 1) gmx = fmax(gmx, __shfl_xor_sync(0xffffffffu, gmx, d));
-            if (lane == 0) { s_part[warp] = acc; s_pmax[warp] = gmx; }
-            __syncthreads();
-            if (CL) {  // this CTA's share of every bucket of the batch goes to all CTAs of the cluster
-                if (warp == 0 && lane < Sc) {
-                    double mine = 0.0, mmax = 0.0;
-                    for (int s = 0; s < nsub; s++) { mine += s_part[lane + (s << lg)]; mmax = fmax(mmax, s_pmax[lane + (s << lg)]); }
-                    for (unsigned r = 0; r < csize; r++) { st_cluster_f64(&s_cl[parity][crank][lane], r, mine); st_cluster_f64(&s_cm[parity][crank][lane], r, mmax); }
-                }
+            // One barrier per batch.  With one warp per bucket (S = 32) the warp sends its sum straight to every CTA of the cluster; the
+            // buffers alternate with the batch parity (a CTA or warp that runs ahead writes the other half).
+            if (CL && nsub == 1) {
+                if (act && lane == 0)
+                    for (unsigned r = 0; r < csize; r++) { st_cluster_f64(&s_cl[parity][crank][qi], r, acc); st_cluster_f64(&s_cm[parity][crank][qi], r, gmx); }
                 cluster_sync_all();
+            } else {
+                if (lane == 0) { s_part[parity][warp] = acc; s_pmax[parity][warp] = gmx; }
+                __syncthreads();
+                if (CL) {  // this CTA's share of every bucket of the batch goes to all CTAs of the cluster
+                    if (warp == 0 && lane < Sc) {
+                        double mine = 0.0, mmax = 0.0;
+                        for (int s = 0; s < nsub; s++) { mine += s_part[parity][lane + (s << lg)]; mmax = fmax(mmax, s_pmax[parity][lane + (s << lg)]); }
+                        for (unsigned r = 0; r < csize; r++) { st_cluster_f64(&s_cl[parity][crank][lane], r, mine); st_cluster_f64(&s_cm[parity][crank][lane], r, mmax); }
+                    }
+                    cluster_sync_all();
+                }
             }
-            if (warp == 0) {
+            int stop;
+            unsigned fm, onm;
+            {   // the decisions of the batch, taken by every warp alike (lane = bucket)
                 const bool have = lane < Sc;
                 double sum = 0.0, gmax = 0.0;  // log-intensity difference of the bucket; largest change a flip of its link makes to any intensity
                 if (have) {
                     if (CL) for (unsigned r = 0; r < csize; r++) { sum += s_cl[parity][r][lane]; gmax = fmax(gmax, s_cm[parity][r][lane]); }  // fixed order: every CTA decides alike
-                    else for (int s = 0; s < nsub; s++) { sum += s_part[lane + (s << lg)]; gmax = fmax(gmax, s_pmax[lane + (s << lg)]); }
+                    else for (int s = 0; s < nsub; s++) { sum += s_part[parity][lane + (s << lg)]; gmax = fmax(gmax, s_pmax[parity][lane + (s << lg)]); }
                 }
+                const double d_wmn = s_dec[parity][0][lane], d_lrho = s_dec[parity][1][lane], d_u = s_dec[parity][2][lane];
+                const double d_lu = s_dec[parity][3][lane];  // logit(u): delta - logit(u) is the margin by which the decision u <= sigmoid(delta) holds
                 const int qq = p + lane;
-                const bool old_on = have && ((s_ab[qq >> 5] >> (qq & 31)) & 1u);
                 // ll1 - ll0 (continuous.jl:477-483): integrated-intensity difference, log-intensity difference, prior
                 const double delta = -d_wmn + sum + d_lrho;
                 // rand(Bernoulli(p1)) = rand() <= p1 with p1 = sigmoid(delta).  u <= sigmoid(delta) <=> logit(u) <= delta, and the two sides
@@ -922,23 +937,18 @@ template <int KIND, int PRE, bool CL> __global__ void __launch_bounds__(ADJ_THRE
                 const bool uncertified = have && cum > 0.0 && !(margin > fabs(sum) * cum * (4.0 / lam0) + slack);
                 const bool toobig = flip && !(gmax <= 0.5 * lam0);
                 const unsigned um = __ballot_sync(0xffffffffu, uncertified), bm = __ballot_sync(0xffffffffu, toobig);
-                int stop = Sc;
+                stop = Sc;
                 if (um) stop = min(stop, __ffs(um) - 1);
                 if (bm) stop = min(stop, __ffs(bm));
-                const unsigned acc_mask = stop >= 32 ? flipmask : (flipmask & ((1u << stop) - 1u));
-                if (lane == 0) { s_first = stop; s_mask = acc_mask; }
-                const unsigned onmask = __ballot_sync(0xffffffffu, new_on);
-                if (lane == 0) s_onmask = onmask;
-                if (have && ((acc_mask >> lane) & 1u)) {
+                fm = stop >= 32 ? flipmask : (flipmask & ((1u << stop) - 1u));
+                onm = __ballot_sync(0xffffffffu, new_on);
+                // warp 0 records the accepted flips; the others see the new bits behind the barrier of the first flip's application
+                if (warp == 0 && have && ((fm >> lane) & 1u)) {
                     if (crank == 0) Acol[qq] = new_on ? 1.0 : 0.0;
                     atomicXor(&s_ab[qq >> 5], 1u << (qq & 31));
                 }
             }
-            __syncthreads();
             parity ^= 1u;
-            const int stop = s_first;
-            unsigned fm = s_mask;
-            const unsigned onm = s_onmask;
             n_batches++;
             n_steps += stop; n_flips += __popc(fm); n_redo += Sc - stop;
             if (resident && (fm & (fm - 1))) {  // several flips: all their buckets start towards L2 now, the first one's latency covers the others
@@ -971,7 +981,7 @@ template <int KIND, int PRE, bool CL> __global__ void __launch_bounds__(ADJ_THRE
             fw_steps = 0.9f * fw_steps + (float)stop; fw_flips = 0.9f * fw_flips + (stop < Sc ? 1.f : 0.f);  // "flip" = a batch cut short
             {
                 const float target = 2.f * rsqrtf(fw_flips / fw_steps + 1e-3f);
-                const int l2 = min(5, max(0, __float2int_rn(__log2f(target))));
+                const int l2 = min(a.lmax, max(0, __float2int_rn(__log2f(target))));
                 S = 1 << l2;
             }
         }
@@ -1456,6 +1466,9 @@ static int adj_run(nhp_ctx *ctx, nhp_events *ev, const double *d_rho, double rho
         w.ncols = (int)((K - col_begin + col_stride - 1) / col_stride);
         w.s0 = ADJ_SMAX;
         { const char *e = getenv("NHP_ADJ_S0"); if (e && atoi(e) >= 1 && atoi(e) <= 32 && (atoi(e) & (atoi(e) - 1)) == 0) w.s0 = atoi(e); }
+        w.lmax = 5;
+        { const char *e = getenv("NHP_ADJ_LMAX"); if (e && atoi(e) >= 0 && atoi(e) <= 5) w.lmax = atoi(e); }
+        if (w.s0 > (1 << w.lmax)) w.s0 = 1 << w.lmax;
         const size_t smem = (size_t)w.chunk_max * sizeof(double) + (size_t)((K + 31) / 32) * sizeof(unsigned) + 16;
         NHP_CHECK(ctx, smem <= (size_t)ctx->smem_optin - 4096, NHP_ERR_UNSUPPORTED, "adjacency sampler: K=%lld needs more shared memory than the device has", (long long)K);
         NHP_CUDA(ctx, cudaMemsetAsync(ctx->d_adj_ctl, 0, 8 * sizeof(int), s));

@@ -78,6 +78,7 @@ extern "C" int nhp_destroy(nhp_ctx *ctx) {
     cudaSetDevice(ctx->device);
     cudaStreamSynchronize(ctx->stream);
     nhp_comm_destroy(ctx);
+    nhp_cont_trace_free(ctx);
     nhp_big_flush(ctx);
     free_cont(ctx);
     cudaFree(ctx->d_partials); cudaFree(ctx->d_scratch); cudaFree(ctx->d_flag); cudaFree(ctx->d_winstat);

@@ -159,6 +159,9 @@ struct nhp_ctx {
     unsigned long long *d_adj_stat = nullptr;  // [8] sweep diagnostics (steps, batches, flips, recomputed steps)
     double *d_save = nullptr;     // nhp_cont_params_save: [K + 4 K^2] copy of lambda0, W, A, p1, p2
     double rho = -1.0;            // link probability of the Bernoulli network kept with the context (nhp_cont_resample_network)
+    // device-side sample trace (cont_trace.cu): [trace_cap] slots of (rho, lambda0, W, p1 [, p2]) + bit-packed adjacency matrices
+    double *d_trace = nullptr; uint32_t *d_trace_bits = nullptr;
+    int64_t trace_cap = 0, trace_len = 0, trace_K = 0; int trace_kind = 0; bool trace_has_A = false;
     double sweep_info[8] = {0};   // last nhp_cont_gibbs_sweep: ms of the parent sweep, of (second pass + draws + tables), of the adjacency kernel
     double adj_info[8] = {0};     // last adjacency sweep: steps, batches, flips, recomputed steps, entries, chunks, kernel ms, build ms
 

@@ -320,6 +320,45 @@ function resample_on_device!(process::ContinuousHawkesProcess, data)
     return NetworkHawkesProcesses.params(process)
 end
 
+# `mcmc!` (inference.jl:49-70) with the chain and its sample trace on the device: the parameters go up once, every sweep is one
+# nhp_cont_gibbs_sweep (which appends its sample to the device-side trace, adjacency bit-packed), one read at the end.
+function mcmc_on_device!(process::ContinuousHawkesProcess, data; nsteps=1000)
+    ev = device_events(process, data)
+    push_params!(process)
+    b, w, imp = process.baseline, process.weights, process.impulses
+    hyper = imp isa ExponentialImpulseResponse ? Float64[b.α0, b.β0, w.κ, w.ν, imp.α, imp.β] :
+                                                  Float64[b.α0, b.β0, w.κ, w.ν, imp.μμ, imp.κμ, imp.α0, imp.β0]
+    net = process isa ContinuousNetworkHawkesProcess
+    bern = net && process.network isa BernoulliNetworkModel
+    bern && check(ccall((:nhp_cont_network_set, LIB[]), Cint, (Ptr{Cvoid}, Float64), CTX[], Float64(process.network.ρ)))
+    check(ccall((:nhp_cont_trace_begin, LIB[]), Cint, (Ptr{Cvoid}, Int64), CTX[], nsteps))
+    seed = Base.rand(UInt64)
+    start = time()
+    for step in 1:nsteps
+        check(ccall((:nhp_cont_gibbs_sweep, LIB[]), Cint,
+            (Ptr{Cvoid}, Ptr{Cvoid}, Ptr{Cvoid}, UInt64, UInt64, Float64, Ptr{Float64}, Cint, Float64, Float64),
+            CTX[], ev.h, ev.full, seed, UInt64(step), Float64(data[3]), hyper, length(hyper),
+            bern ? Float64(process.network.α) : 0.0, bern ? Float64(process.network.β) : 0.0))
+    end
+    K = ndims(process); ln = !(imp isa ExponentialImpulseResponse)
+    ρ = Vector{Float64}(undef, nsteps); λ = Matrix{Float64}(undef, K, nsteps); W = Array{Float64}(undef, K, K, nsteps)
+    q1 = Array{Float64}(undef, K, K, nsteps); q2 = Array{Float64}(undef, K, K, nsteps); A = Array{Float64}(undef, K, K, nsteps)
+    check(ccall((:nhp_cont_trace_read, LIB[]), Cint,
+        (Ptr{Cvoid}, Int64, Int64, Ptr{Float64}, Ptr{Float64}, Ptr{Float64}, Ptr{Float64}, Ptr{Float64}, Ptr{Float64}),
+        CTX[], 0, nsteps, ρ, λ, W, net ? A : C_NULL, q1, ln ? q2 : C_NULL))
+    check(ccall((:nhp_cont_trace_free, LIB[]), Cint, (Ptr{Cvoid},), CTX[]))
+    samples = Vector{Vector{Float64}}(undef, nsteps)
+    for k in 1:nsteps   # the order of params(process): continuous.jl:116-119 / 325-333
+        impv = ln ? [vec(q1[:, :, k]); vec(q2[:, :, k])] : vec(q1[:, :, k])
+        samples[k] = net ? [bern ? [ρ[k]] : Float64[]; λ[:, k]; vec(W[:, :, k]); impv; vec(A[:, :, k])] : [λ[:, k]; impv; vec(W[:, :, k])]
+    end
+    b.λ = λ[:, end]; w.W = W[:, :, end]
+    if ln; imp.μ = q1[:, :, end]; imp.τ = q2[:, :, end] else imp.θ = q1[:, :, end] end
+    net && (process.adjacency_matrix .= A[:, :, end])
+    bern && (process.network.ρ = ρ[end])
+    return NetworkHawkesProcesses.MarkovChainMonteCarlo(samples, time() - start)
+end
+
 # ================================================== discrete path ===============================================================
 function device_counts(data::AbstractMatrix)
     cached(COUNT_CACHE, data) do

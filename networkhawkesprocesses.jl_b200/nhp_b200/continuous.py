@@ -542,6 +542,49 @@ def resample_on_device_(process, data, rng=None, seed=0, counter=0, push=True, p
             d.free()
 
 
+def mcmc_device_(process, data, nsteps=1000, seed=0):
+    """`mcmc!` (inference.jl:49-70) with the chain AND its sample trace on the device: parameters go up once, every sweep is one
+    nhp_cont_gibbs_sweep (which appends its sample to the trace: device-to-device, adjacency bit-packed), and the trace comes back
+    in one read at the end.  Returns MarkovChainMonteCarlo with the samples in the order of `params(process)`
+    ([rho;] lambda0; theta | mu, tau; W [; vec(A)], continuous.jl:116-119, 325-333); the process holds the last sample."""
+    ctx = process._ctx()
+    d, tmp = process._data(data)
+    t0 = time.time()
+    try:
+        K = process.ndims()
+        net = process.adjacency_matrix is not None
+        bern = net and isinstance(process.network, BernoulliNetworkModel)
+        process._push(ctx)
+        if bern:
+            ctx.check(ctx.lib.nhp_cont_network_set(ctx.h, float(process.network.rho)))
+        ctx.check(ctx.lib.nhp_cont_trace_begin(ctx.h, int(nsteps)))
+        hy = _hyper(process)
+        for step in range(nsteps):
+            ctx.check(ctx.lib.nhp_cont_gibbs_sweep(ctx.h, d.h, d.h, int(seed), int(step), float(d.duration), _ptr(hy), hy.size,
+                                                   float(process.network.alpha) if bern else 0.0, float(process.network.beta) if bern else 0.0))
+        ln = process.impulses.p2() is not None
+        rho, l0, W, p1 = np.empty(nsteps), np.empty((nsteps, K)), np.empty((nsteps, K * K)), np.empty((nsteps, K * K))
+        p2 = np.empty((nsteps, K * K)) if ln else None
+        A = np.empty((nsteps, K * K)) if net else None
+        ctx.check(ctx.lib.nhp_cont_trace_read(ctx.h, 0, int(nsteps), _ptr(rho), _ptr(l0), _ptr(W), _ptr(A), _ptr(p1), _ptr(p2)))
+        ctx.check(ctx.lib.nhp_cont_trace_free(ctx.h))
+        pull_params_(process, ctx)
+        if bern:
+            process.network.rho = float(rho[-1])
+        samples = []
+        for k in range(nsteps):
+            imp = [p1[k]] + ([p2[k]] if ln else [])
+            if net:  # continuous.jl:325-333: [network; baseline; weights; impulses; vec(A)]
+                parts = ([np.array([rho[k]])] if bern else [process.network.params()]) + [l0[k], W[k]] + imp + [A[k]]
+            else:    # continuous.jl:116-119: [baseline; impulses; weights]
+                parts = [l0[k]] + imp + [W[k]]
+            samples.append(np.concatenate(parts))
+        return MarkovChainMonteCarlo(samples, time.time() - t0)
+    finally:
+        if tmp:
+            d.free()
+
+
 def adjacency_info(ctx=None):
     """Diagnostics of the context's last adjacency sweep (nhp_cont_adjacency_info)."""
     ctx = ctx or default_context()

@@ -7,6 +7,7 @@ import pytest
 
 import nhp_b200 as nhp
 import oracle_ffi as orc
+import synth
 
 pytestmark = pytest.mark.gpu
 
@@ -73,3 +74,39 @@ def test_mle_readme_example_runs():
     res = nhp.mle_(fit, (t, nodes, T), max_iter=60, seed=1)
     assert res.maximum >= ll_true - 1e-6          # the optimiser ends at least as high as the generating parameters
     assert np.all(np.abs(fit.baseline.lam - 1.0) < 0.3)
+
+
+@pytest.mark.parametrize("network", [False, True])
+def test_device_trace_holds_the_chain_samples(network):
+    """mcmc_device_: the whole chain on the device with the device-side sample trace (nhp_cont_trace_*) gives the same samples as
+    the device chain that pulls every sweep's parameters to the host (same Philox keys), in the order of params(process)."""
+    import ctypes
+    K, nsteps = 5, 7
+    lam0, W, mu, tau, A = synth.ln_params(K, 3, wmax=0.4, density=0.6 if network else None)
+
+    def make():
+        base, imp, wts = nhp.HomogeneousProcess(lam0.copy()), nhp.LogitNormalImpulseResponse(mu.copy(), tau.copy(), 1.0), nhp.DenseWeightModel(W.copy())
+        if network:
+            return nhp.ContinuousNetworkHawkesProcess(base, imp, wts, A.copy(), nhp.BernoulliNetworkModel(0.5, K))
+        return nhp.ContinuousStandardHawkesProcess(base, imp, wts)
+
+    p0 = make()
+    t, nodes, T = nhp.rand(p0, 300.0, np.random.default_rng(4))
+    a, b = make(), make()
+    ref = nhp.mcmc_(a, (t, nodes, T), nsteps=nsteps, seed=9, device_draws=True)
+    got = nhp.mcmc_device_(b, (t, nodes, T), nsteps=nsteps, seed=9)
+    assert len(got.samples) == nsteps
+    for x, y in zip(ref.samples, got.samples):  # the float statistics are accumulated with atomics: equal up to the summation order
+        np.testing.assert_allclose(x, y, rtol=1e-9, atol=1e-12)
+    np.testing.assert_allclose(a.params(), b.params(), rtol=1e-9, atol=1e-12)
+    # capacity and state errors
+    ctx = b._ctx()
+    assert ctx.lib.nhp_cont_trace_push(ctx.h) < 0  # no open trace
+    b._push(ctx)
+    ctx.check(ctx.lib.nhp_cont_trace_begin(ctx.h, 1))
+    ctx.check(ctx.lib.nhp_cont_trace_push(ctx.h))
+    assert ctx.lib.nhp_cont_trace_push(ctx.h) < 0  # full
+    n, cap = ctypes.c_int64(), ctypes.c_int64()
+    ctx.check(ctx.lib.nhp_cont_trace_count(ctx.h, ctypes.byref(n), ctypes.byref(cap)))
+    assert (n.value, cap.value) == (1, 1)
+    ctx.check(ctx.lib.nhp_cont_trace_free(ctx.h))

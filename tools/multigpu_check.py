@@ -121,6 +121,20 @@ def main():
     res["composite_links"] = int(Ad.sum())
     ok &= res["composite_param_spread"] < 1e-12 and np.all(np.isfinite(chk))
 
+    # ---------------- intensity(process, data, times): the query times are sharded, the stream is replicated, no exchange but the gather
+    proc._push(ctx)
+    nq = 2001
+    tq = np.linspace(0.0, T, nq)
+    lam_full = nhp.intensity(proc, full, tq)                      # [nq, K]
+    q0, q1 = rank * nq // world, (rank + 1) * nq // world
+    lam_mine = nhp.intensity(proc, full, tq[q0:q1])
+    gathered_q = np.zeros((nq, K))
+    gathered_q[q0:q1] = lam_mine
+    flat = np.ascontiguousarray(gathered_q.ravel())
+    ctx.check(lib.nhp_comm_allreduce_host(ctx.h, _ptr(flat), flat.size))  # disjoint slices: the sum is the gather
+    res["query_shard_max_abs_err"] = float(np.max(np.abs(flat.reshape(nq, K) - lam_full)))
+    ok &= res["query_shard_max_abs_err"] == 0.0
+
     # ---------------- discrete process: time shards with an L-bin halo
     N, Tb, B, L = 12, 6000, 4, 8
     rng = np.random.default_rng(4)
