@@ -184,7 +184,8 @@ template <int KIND> __global__ void __launch_bounds__(256) k_adjacency(const Adj
 // cached structure: build once, sweep many times
 // ---------------------------------------------------------------------------------------
 constexpr int ADJ_CHUNK_MAX = 26624;   // child events per chunk: 208 KB of shared-memory intensities
-constexpr int ADJ_THREADS = 1024;      // sweep CTA: one per SM
+constexpr int ADJ_THREADS = 1024;      // sweep CTA: one per SM (512 threads with 128 registers each measured 8 % slower: 45.3 vs 41.9 ms)
+constexpr int ADJ_VW = 32;             // bucket slots of a batch: one per warp (a CTA with fewer warps takes several slots per warp, one after the other)
 constexpr int ADJ_SMAX = 32;           // largest speculative batch (buckets per batch); the size follows the observed flip rate, down to 1
 constexpr int ADJ_CLUSTER_MAX = 8;     // portable cluster size limit
 
@@ -375,9 +376,9 @@ __global__ void __launch_bounds__(1024) k_adj_build(const AdjBuildArgs a) {
             }
         }
         __syncthreads();
-        // ---- section sizes (padded to whole groups of 32 entries)
+        // ---- section sizes (singles padded to whole blocks of 64 entries, runs to whole groups of 32)
         for (int p = tid; p < K; p += blockDim.x) {
-            s_off[2 * p + 1] = (int)((s_curS[p] + 31u) & ~31u);
+            s_off[2 * p + 1] = (int)((s_curS[p] + 63u) & ~63u);   // singles: whole blocks of 64 entries (the sweep reads them unconditionally)
             s_off[2 * p + 2] = (int)((s_curM[p] + 31u) & ~31u);
         }
         if (tid == 0) s_off[0] = 0;
@@ -595,9 +596,6 @@ __device__ __forceinline__ void acc_factor2(AdjAcc &A, double v0, double l0, dou
     A.gm = max(A.gm, max(__double2hiint(v0), __double2hiint(v1)));
 }
 
-// singles of one bucket: this warp takes the blocks of 64 entries that start at gb, gb + stride, ... below s1 (sections are whole groups
-// of 32 entries, 32-entry aligned: a lane reads entries 2 lane, 2 lane + 1 of its block with one 32-bit and two 128-bit loads; the last
-// block may be half a block); one block ahead in flight.  Padding entries evaluate to zero and contribute the factor 1.
 // L2 prefetch of the 64-entry block that starts at entry kb: lanes 0-1 take the two 64-byte halves of the indices, lanes 2-9 (2-17 with
 // the 16-byte payload) the 64-byte pieces of the payload (one instruction per block; the arrays carry slack behind their last entry)
 struct AdjPf { const char *base; int scale; };
@@ -612,6 +610,11 @@ __device__ __forceinline__ void adj_pf(const AdjPf &f, int kb) {
     if (f.base) asm volatile("prefetch.global.L2 [%0];" ::"l"(f.base + (int64_t)kb * f.scale));
 }
 
+// singles of one bucket: this warp takes the blocks of 64 entries that start at gb, gb + stride, ... below s1 (the section is padded to
+// whole blocks and starts on a 32-entry boundary: a lane reads entries 2 lane, 2 lane + 1 of its block with one 32-bit and one 256-bit
+// load); one block ahead in registers, the block three ahead on its way to L2.  Padding entries evaluate to zero: factor 1.
+// (Measured alternatives: two blocks ahead in registers spills at 64 registers per thread, 66 vs 42 ms; 512-thread CTAs with 128
+// registers and that loop, 45 ms; loads made unconditional on the warp-uniform block test, 43.6 ms.)
 template <int KIND, int PRE>
 __device__ __forceinline__ void adj_singles(const typename EntryOf<KIND>::type &en, const unsigned short *__restrict__ ei, const double *__restrict__ ex,
                                             int gb, const int s1, const int stride, const int lane, const double onf,
@@ -715,7 +718,7 @@ template <int KIND, int PRE, bool CL> __global__ void __launch_bounds__(ADJ_THRE
     typedef typename EntryOf<KIND>::type E;
     extern __shared__ __align__(16) double lam_s[];  // [chunk_max] intensities of the resident chunk | adjacency bits of the column
     __shared__ FastTables s_ft;
-    __shared__ double s_part[2][32], s_pmax[2][32];                                // [batch parity][warp]: this CTA's partial sums, largest contributions
+    __shared__ double s_part[2][ADJ_VW], s_pmax[2][ADJ_VW];                                // [batch parity][warp]: this CTA's partial sums, largest contributions
     __shared__ double s_cl[2][ADJ_CLUSTER_MAX][32], s_cm[2][ADJ_CLUSTER_MAX][32];  // [batch parity][source CTA][bucket of the batch]: the same, cluster-wide
     __shared__ double s_dec[2][4][32];                                             // [batch parity][W Mn, logit rho, u, logit u][bucket of the batch]
     __shared__ int s_col;
@@ -809,9 +812,7 @@ template <int KIND, int PRE, bool CL> __global__ void __launch_bounds__(ADJ_THRE
         while (p < K) {
             const int Sc = min(S, K - p);
             const int lg = 31 - __clz(S);
-            const int qi = warp & (S - 1), sub = warp >> lg, nsub = 32 >> lg;
-            const int q = p + qi;
-            const bool act = qi < Sc;
+            const int nsub = ADJ_VW >> lg;  // slots per bucket: slot vw works on bucket vw & (S - 1), share vw >> lg
             // the deciding lanes fetch their inputs before the batch so that the latency hides behind it
             // (into shared memory: every warp takes the decisions for itself behind the batch's one barrier)
             if (warp == 0 && lane < Sc) {
@@ -820,12 +821,8 @@ template <int KIND, int PRE, bool CL> __global__ void __launch_bounds__(ADJ_THRE
                 asm("ld.global.nc.v4.f64 {%0,%1,%2,%3}, [%4];" : "=d"(d0), "=d"(d1), "=d"(d2), "=d"(d3) : "l"(dp));
                 s_dec[parity][0][lane] = d0; s_dec[parity][1][lane] = d1; s_dec[parity][2][lane] = d2; s_dec[parity][3][lane] = d3;
             }
-            E en = E();
-            bool on = false;
-            if (act) { en = load_entry(col + q); on = (s_ab[q >> 5] >> (q & 31)) & 1u; }
             // lane = bucket: the state of its link now (warp 0 changes the bits while slower warps still take their decisions)
             const bool old_on = lane < Sc && ((s_ab[(p + lane) >> 5] >> ((p + lane) & 31)) & 1u);
-            const double onf = on ? 1.0 : 0.0, floor_ = on ? lam0 : -__longlong_as_double(0x7ff0000000000000LL);
             if (S <= 4 && resident) {
                 // short batches are latency bound: pull the entries of the buckets that can come next (they follow in memory) into L2 now
                 const int g = g_lo;
@@ -835,7 +832,10 @@ template <int KIND, int PRE, bool CL> __global__ void __launch_bounds__(ADJ_THRE
                 const int f0 = bo[2 * q0], f1 = bo[2 * q1];
                 adj_pf_range<PRE>(a.ent_i + vb, a.ent_x + (PRE ? 2 : 1) * vb, f0, f1, tid);
             }
-            double acc = 0.0, gmx = 0.0;
+            constexpr int NR = ADJ_VW / (ADJ_THREADS / 32);  // slots per warp, taken one after the other
+            double acc[NR], gmx[NR];
+#pragma unroll
+            for (int r = 0; r < NR; r++) { acc[r] = 0.0; gmx[r] = 0.0; }
             for (int g = g_lo; g < g_hi; g++) {
                 if (!resident) {
                     const int len = max(0, min(csz, ne - g * csz));
@@ -843,44 +843,64 @@ template <int KIND, int PRE, bool CL> __global__ void __launch_bounds__(ADJ_THRE
                     for (int e = tid; e < len; e += ADJ_THREADS) lam_s[e] = __ldcg(lamg + (size_t)g * csz + e);  // written by this CTA: read through L2
                     __syncthreads();
                 }
-                if (act) {
-                    const int *bo = a.boff + (int64_t)(v0 + g) * brow;
-                    const int b0 = bo[2 * q], bm = bo[2 * q + 1], b1 = bo[2 * q + 2];
-                    const int64_t vb = a.vbase[v0 + g];
-                    const unsigned short *ei = a.ent_i + vb;
-                    const double *ex = a.ent_x + (PRE ? 2 : 1) * vb;
-                    const AdjPf pf = adj_pf_setup<PRE>(ei, ex, lane);
-                    if (q + Sc < K) {  // the bucket this warp takes if the whole batch is accepted: its first blocks go to L2 now
-                        const int nb = bo[2 * (q + Sc)] + sub * 64;
-                        adj_pf(pf, nb); adj_pf(pf, nb + nsub * 64);
-                    }
-                    AdjAcc A;
-                    acc_init(A);
-                    adj_singles<KIND, PRE>(en, ei, ex, b0 + sub * 64, bm, nsub * 64, lane, onf, floor_, a.D, lam_s, ft, pf, A);
-                    adj_runs<KIND, PRE>(en, ei, ex, bm + sub * 32, b1, nsub * 32, lane, onf, floor_, a.D, lam_s, ft, A);
-                    if (__all_sync(0xffffffffu, acc_in_range(A))) {
-                        acc += (fast_log_n(A.num, ft) - fast_log_n(A.den, ft)) + (double)A.bal * 0.6931471805599453;
-                        if (A.gm > 0) gmx = fmax(gmx, __hiloint2double(A.gm + 1, 0));  // upper bound of the largest contribution
-                    } else {  // warp-uniform, rare
-                        const double2 d0 = adj_direct<KIND, PRE>(en, ei, ex, b0 + sub * 64, bm, nsub * 64, lane, onf, floor_, a.D, lam_s, ft);  // the same blocks, half by half
-                        const double2 d1 = adj_direct<KIND, PRE>(en, ei, ex, b0 + sub * 64 + 32, bm, nsub * 64, lane, onf, floor_, a.D, lam_s, ft);
-                        const double2 d2 = adj_direct<KIND, PRE>(en, ei, ex, bm + sub * 32, b1, nsub * 32, lane, onf, floor_, a.D, lam_s, ft);
-                        acc += d0.x + d1.x + d2.x;
-                        gmx = fmax(gmx, fmax(d0.y, fmax(d1.y, d2.y)));
+                const int *bo = a.boff + (int64_t)(v0 + g) * brow;
+                const int64_t vb = a.vbase[v0 + g];
+                const unsigned short *ei = a.ent_i + vb;
+                const double *ex = a.ent_x + (PRE ? 2 : 1) * vb;
+                const AdjPf pf = adj_pf_setup<PRE>(ei, ex, lane);
+#pragma unroll
+                for (int r = 0; r < NR; r++) {
+                    const int vw = warp + r * (ADJ_THREADS / 32);
+                    const int qi = vw & (S - 1), sub = vw >> lg, q = p + qi;
+                    if (qi < Sc) {
+                        const E en = load_entry(col + q);
+                        const bool on = (s_ab[q >> 5] >> (q & 31)) & 1u;
+                        const double onf = on ? 1.0 : 0.0, floor_ = on ? lam0 : -__longlong_as_double(0x7ff0000000000000LL);
+                        const int b0 = bo[2 * q], bm = bo[2 * q + 1], b1 = bo[2 * q + 2];
+                        if (q + Sc < K) {  // the bucket this slot takes if the whole batch is accepted: its first blocks go to L2 now
+                            const int nb = bo[2 * (q + Sc)] + sub * 64;
+                            adj_pf(pf, nb); adj_pf(pf, nb + nsub * 64);
+                        }
+                        AdjAcc A;
+                        acc_init(A);
+                        adj_singles<KIND, PRE>(en, ei, ex, b0 + sub * 64, bm, nsub * 64, lane, onf, floor_, a.D, lam_s, ft, pf, A);
+                        adj_runs<KIND, PRE>(en, ei, ex, bm + sub * 32, b1, nsub * 32, lane, onf, floor_, a.D, lam_s, ft, A);
+                        if (__all_sync(0xffffffffu, acc_in_range(A))) {
+                            acc[r] += (fast_log_n(A.num, ft) - fast_log_n(A.den, ft)) + (double)A.bal * 0.6931471805599453;
+                            if (A.gm > 0) gmx[r] = fmax(gmx[r], __hiloint2double(A.gm + 1, 0));  // upper bound of the largest contribution
+                        } else {  // warp-uniform, rare
+                            const double2 d0 = adj_direct<KIND, PRE>(en, ei, ex, b0 + sub * 64, bm, nsub * 64, lane, onf, floor_, a.D, lam_s, ft);  // the same blocks, half by half
+                            const double2 d1 = adj_direct<KIND, PRE>(en, ei, ex, b0 + sub * 64 + 32, bm, nsub * 64, lane, onf, floor_, a.D, lam_s, ft);
+                            const double2 d2 = adj_direct<KIND, PRE>(en, ei, ex, bm + sub * 32, b1, nsub * 32, lane, onf, floor_, a.D, lam_s, ft);
+                            acc[r] += d0.x + d1.x + d2.x;
+                            gmx[r] = fmax(gmx[r], fmax(d0.y, fmax(d1.y, d2.y)));
+                        }
                     }
                 }
             }
-            acc = warp_sum(acc);
 #pragma unroll
-            for (int d = 16; d >= 1; d >>= 1) gmx = fmax(gmx, __shfl_xor_sync(0xffffffffu, gmx, d));
-            // One barrier per batch.  With one warp per bucket (S = 32) the warp sends its sum straight to every CTA of the cluster; the
+            for (int r = 0; r < NR; r++) {
+                acc[r] = warp_sum(acc[r]);
+#pragma unroll
+                for (int d = 16; d >= 1; d >>= 1) gmx[r] = fmax(gmx[r], __shfl_xor_sync(0xffffffffu, gmx[r], d));
+            }
+            // One barrier per batch.  With one slot per bucket (S = 32) the warp sends its sums straight to every CTA of the cluster; the
             // buffers alternate with the batch parity (a CTA or warp that runs ahead writes the other half).
             if (CL && nsub == 1) {
-                if (act && lane == 0)
-                    for (unsigned r = 0; r < csize; r++) { st_cluster_f64(&s_cl[parity][crank][qi], r, acc); st_cluster_f64(&s_cm[parity][crank][qi], r, gmx); }
+                if (lane == 0) {
+#pragma unroll
+                    for (int r = 0; r < NR; r++) {
+                        const int qi = warp + r * (ADJ_THREADS / 32);
+                        if (qi < Sc)
+                            for (unsigned rk = 0; rk < csize; rk++) { st_cluster_f64(&s_cl[parity][crank][qi], rk, acc[r]); st_cluster_f64(&s_cm[parity][crank][qi], rk, gmx[r]); }
+                    }
+                }
                 cluster_sync_all();
             } else {
-                if (lane == 0) { s_part[parity][warp] = acc; s_pmax[parity][warp] = gmx; }
+                if (lane == 0) {
+#pragma unroll
+                    for (int r = 0; r < NR; r++) { s_part[parity][warp + r * (ADJ_THREADS / 32)] = acc[r]; s_pmax[parity][warp + r * (ADJ_THREADS / 32)] = gmx[r]; }
+                }
                 __syncthreads();
                 if (CL) {  // this CTA's share of every bucket of the batch goes to all CTAs of the cluster
                     if (warp == 0 && lane < Sc) {
@@ -1229,13 +1249,13 @@ static int adj_build_structure(nhp_ctx *ctx, nhp_events *ev, double horizon, int
     ADJ_B(cudaMemcpyAsync(&max_win, ctx->d_adj_ctl + 4, sizeof(int), cudaMemcpyDeviceToHost, s));
     ADJ_B(cudaMemcpyAsync(vc.data(), d_vcount, (size_t)nv * sizeof(unsigned long long), cudaMemcpyDeviceToHost, s));
     ADJ_B(cudaStreamSynchronize(s));
-    // room per virtual column: its pairs plus the padding of its 2 K sections to whole groups of 32 entries (an upper bound; the regions
+    // room per virtual column: its pairs plus the padding of its 2 K sections to whole blocks (64 entries: singles) / groups (32: runs) (an upper bound; the regions
     // start on group boundaries so that the sweeps' paired loads are aligned)
     std::vector<int64_t> vbase(nv + 1);
     int64_t tot = 0, pairs = 0;
     for (int64_t v = 0; v < nv; v++) {
         vbase[v] = tot;
-        const unsigned long long room = vc[v] + std::min<unsigned long long>(62ull * (unsigned long long)K, 31ull * vc[v]);
+        const unsigned long long room = vc[v] + std::min<unsigned long long>(94ull * (unsigned long long)K, 63ull * vc[v]);
         if (room >= 0x7fffffffull) return drop(nhp_fail(ctx, NHP_ERR_UNSUPPORTED, "adjacency sampler: a column chunk has %llu window entries (limit 2^31)", vc[v]));
         pairs += (int64_t)vc[v];
         tot += (int64_t)((room + 31ull) & ~31ull);
