@@ -1162,10 +1162,13 @@ __global__ void __launch_bounds__(256) k_disc_adj_gather(const double *__restric
                                                          const int *__restrict__ nz_t, const int *__restrict__ child_ptr, double *__restrict__ lam_scratch,
                                                          double *__restrict__ g_scratch) {
     extern __shared__ double s_dynd[];  // [N*B] coefficients | [N][ADJ_TE + 1] tile
-    const int c = blockIdx.y;
+    // children vary fastest over the grid: the CTAs that are resident together work on the same stretch of time for different
+    // children, so a conv row comes from HBM once and from L2 for the other children with a count in that bin (with the children on
+    // the slow axis every non-zero (bin, child) re-read its 8 N B-byte row from DRAM: 75 GB for 9.6 GB of rows at config 3)
+    const int c = blockIdx.x;
     const int NB = N * B;
     const int e0 = child_ptr[c], ne = child_ptr[c + 1] - e0;
-    const int t0 = blockIdx.x * ADJ_TE;
+    const int t0 = blockIdx.y * ADJ_TE;
     if (t0 >= ne) return;
     double *s_coef = s_dynd, *tile = s_dynd + NB;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -1276,7 +1279,7 @@ extern "C" int nhp_disc_resample_adjacency(nhp_ctx *ctx, nhp_disc *dd, const dou
         for (int64_t c = 0; c < N; c++) max_ne = std::max(max_ne, cp[c + 1] - cp[c]);
         if (max_ne > 0) {
             DCUDA(ctx, cudaFuncSetAttribute(k_disc_adj_gather, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)coef_smem));
-            dim3 gg((unsigned)((max_ne + ADJ_TE - 1) / ADJ_TE), (unsigned)N);
+            dim3 gg((unsigned)N, (unsigned)((max_ne + ADJ_TE - 1) / ADJ_TE));
             k_disc_adj_gather<<<gg, 256, coef_smem, s>>>(dd->d_conv, ctx->dd_lambda0, ctx->dd_W, ctx->dd_theta, ctx->ddt, d_A, (int)N, (int)B, ex->nz_t, ex->child_ptr, d_lam, d_G);
             NHP_LAUNCHED(ctx);
         }
