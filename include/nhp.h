@@ -252,6 +252,14 @@ int nhp_disc_loglik(nhp_ctx *ctx, nhp_disc *dd, double *ll);
  * counts[c + N*k], k = 0 baseline, k = 1 + p*B + b.  u (one uniform per event, consumed in
  * (t outer, c inner, draw) order) or NULL for Philox. */
 int nhp_disc_gibbs_counts(nhp_ctx *ctx, nhp_disc *dd, uint64_t seed, uint64_t counter, const double *u, int64_t nu, double *counts);
+/* The conjugate draws of the discrete `resample!` (discrete.jl:361-367 / 416-424) on the device, from the counts the last
+ * nhp_disc_gibbs_counts left there (its `counts` argument may be NULL):  lambda0[c] ~ Gamma(alpha0 + counts[c,0], 1/(beta0 + T dt))
+ * (baselines.jl:413-419, intended form), W[p,c] ~ Gamma(kappa + sum_b counts[c,p,b], 1/(nu + Mn[p])) (weights.jl:59-64),
+ * theta[p,c,:] ~ Dirichlet(gamma + counts[c,p,:]) (impulses.jl:337-353).  Mn[N] = events per node; hyper = [alpha0, beta0, kappa, nu,
+ * gamma]; Philox keyed (seed, element, counter).  The new parameters replace the context's (every derived table is rebuilt) and are
+ * returned in the layouts of nhp_disc_params_set.  Parity with the reference is distributional. */
+int nhp_disc_resample_params(nhp_ctx *ctx, nhp_disc *dd, uint64_t seed, uint64_t counter, const double *Mn, const double *hyper, int n_hyper,
+                             double *lambda0, double *W, double *theta);
 /* update_parents + the three VB reductions  parents.jl:136-177, baselines.jl:444-452,
  * weights.jl:70-91, impulses.jl:355-371.  e0[N], E[N*N*B] are the exp-expectations. */
 int nhp_disc_vb_stats(nhp_ctx *ctx, nhp_disc *dd, const double *e0, const double *E, double *alpha_sum, double *kappa_sum,

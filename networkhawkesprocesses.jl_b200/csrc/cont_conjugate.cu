@@ -292,3 +292,81 @@ extern "C" int nhp_cont_params_restore(nhp_ctx *ctx) {
     ctx->cont_set = true;
     return NHP_OK;
 }
+
+
+// ---------------------------------------------------------------------------------------
+// discrete Gibbs sweep (discrete.jl:361-367 / 416-424): conjugate draws from the counts of the last parent sweep
+//   baseline  lambda0[c] ~ Gamma(alpha0 + counts[c, 0], 1 / (beta0 + T dt))          intended form of baselines.jl:413-419 (quirk Q2)
+//   weights   W[p,c]     ~ Gamma(kappa + sum_b counts[c, p, b], 1 / (nu + Mn[p]))     weights.jl:59-64
+//   impulses  theta[p,c,:] ~ Dirichlet(gamma + counts[c, p, :])                        impulses.jl:337-353 (normalised Gammas)
+// ---------------------------------------------------------------------------------------
+struct DiscConjArgs {
+    int N, B;
+    uint64_t seed, counter;
+    double Tdt, alpha0, beta0, kappa, nu, gamma;
+    const double *counts, *Mn;
+    double *lambda0, *W, *theta;
+};
+__global__ void k_disc_conjugate(const DiscConjArgs a) {
+    const int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const int64_t NN = (int64_t)a.N * a.N;
+    if (e < a.N) {
+        PhiloxStream r(a.seed, (uint32_t)e, 8u, a.counter);
+        a.lambda0[e] = r.gamma(a.alpha0 + a.counts[e], 1.0 / (a.beta0 + a.Tdt));
+    }
+    if (e >= NN) return;
+    const int p = (int)(e % a.N), c = (int)(e / a.N);  // e = p + N c as in W
+    double m = 0.0;
+    for (int b = 0; b < a.B; b++) m += a.counts[c + (int64_t)a.N * (1 + p * a.B + b)];
+    {
+        PhiloxStream r(a.seed, (uint32_t)e, 9u, a.counter);
+        a.W[e] = r.gamma(a.kappa + m, 1.0 / (a.nu + a.Mn[p]));
+    }
+    PhiloxStream r(a.seed, (uint32_t)e, 10u, a.counter);
+    double tot = 0.0;
+    for (int b = 0; b < a.B; b++) {
+        const double g = r.gamma(a.gamma + a.counts[c + (int64_t)a.N * (1 + p * a.B + b)], 1.0);
+        a.theta[e + NN * b] = g;  // theta[p + N (c + N b)]
+        tot += g;
+    }
+    for (int b = 0; b < a.B; b++) a.theta[e + NN * b] /= tot;
+}
+
+extern "C" int nhp_disc_resample_params(nhp_ctx *ctx, nhp_disc *dd, uint64_t seed, uint64_t counter, const double *Mn, const double *hyper, int n_hyper,
+                                        double *lambda0, double *W, double *theta) {
+    NHP_CHECK(ctx, ctx != nullptr, NHP_ERR_INVALID, "ctx is NULL");
+    NHP_CHECK(ctx, dd != nullptr && ctx->disc_set, NHP_ERR_STATE, "nhp_disc_resample_params: discrete parameters not set");
+    const int64_t N = ctx->dN, B = ctx->dB, NN = N * N;
+    NHP_CHECK(ctx, dd->N == N, NHP_ERR_INVALID, "nhp_disc_resample_params: the data has %lld nodes, the parameters %lld", (long long)dd->N, (long long)N);
+    NHP_CHECK(ctx, ctx->dd_counts && ctx->dd_counts_N == N && ctx->dd_counts_B == B, NHP_ERR_STATE,
+              "nhp_disc_resample_params: no counts of a parent sweep with these parameters on the device (call nhp_disc_gibbs_counts first)");
+    NHP_CHECK(ctx, Mn && hyper && n_hyper == 5 && lambda0 && W && theta, NHP_ERR_INVALID, "nhp_disc_resample_params: need Mn[N], 5 hyper-parameters and the three outputs");
+    NHP_CUDA(ctx, cudaSetDevice(ctx->device));
+    cudaStream_t s = ctx->stream;
+    void *scratch = nullptr;
+    NHP_TRY(nhp_scratch(ctx, (size_t)N * sizeof(double), &scratch));
+    NHP_CUDA(ctx, cudaMemcpyAsync(scratch, Mn, (size_t)N * sizeof(double), cudaMemcpyHostToDevice, s));
+    DiscConjArgs a;
+    a.N = (int)N; a.B = (int)B; a.seed = seed; a.counter = counter; a.Tdt = (double)(dd->T - dd->t_halo) * ctx->ddt;
+    a.alpha0 = hyper[0]; a.beta0 = hyper[1]; a.kappa = hyper[2]; a.nu = hyper[3]; a.gamma = hyper[4];
+    a.counts = ctx->dd_counts; a.Mn = (const double *)scratch; a.lambda0 = ctx->dd_lambda0; a.W = ctx->dd_W; a.theta = ctx->dd_theta;
+    NHP_TRY(nhp_timer_begin(ctx));
+    k_disc_conjugate<<<(unsigned)((NN + 127) / 128), 128, 0, s>>>(a);
+    NHP_LAUNCHED(ctx);
+    NHP_CUDA(ctx, cudaGetLastError());
+    NHP_TRY(nhp_timer_end(ctx));
+    // the new parameters go to the host (they are the sample), and the derived tables (bump, sparse parent lists) follow them
+    NHP_CUDA(ctx, cudaMemcpyAsync(lambda0, ctx->dd_lambda0, (size_t)N * sizeof(double), cudaMemcpyDeviceToHost, s));
+    NHP_CUDA(ctx, cudaMemcpyAsync(W, ctx->dd_W, (size_t)NN * sizeof(double), cudaMemcpyDeviceToHost, s));
+    NHP_CUDA(ctx, cudaMemcpyAsync(theta, ctx->dd_theta, (size_t)(NN * B) * sizeof(double), cudaMemcpyDeviceToHost, s));
+    std::vector<double> A;
+    if (ctx->d_has_A) {
+        A.resize((size_t)NN);
+        NHP_CUDA(ctx, cudaMemcpyAsync(A.data(), ctx->dd_A, (size_t)NN * sizeof(double), cudaMemcpyDeviceToHost, s));
+    }
+    NHP_CUDA(ctx, cudaStreamSynchronize(s));
+    const double ms = ctx->last_ms;
+    const int rc = nhp_disc_params_set(ctx, N, B, lambda0, W, ctx->d_has_A ? A.data() : nullptr, theta, ctx->ddt);
+    ctx->last_ms = ms;
+    return rc;
+}

@@ -961,7 +961,6 @@ static int pick_slabs(nhp_ctx *ctx, int64_t N, int64_t nnz) {
 
 extern "C" int nhp_disc_gibbs_counts(nhp_ctx *ctx, nhp_disc *dd, uint64_t seed, uint64_t counter, const double *u, int64_t nu, double *counts) {
     NHP_TRY(disc_ready(ctx, dd, "nhp_disc_gibbs_counts"));
-    NHP_CHECK(ctx, counts != nullptr, NHP_ERR_INVALID, "nhp_disc_gibbs_counts: counts is NULL");
     NHP_CHECK(ctx, !u || nu >= dd->total_events, NHP_ERR_INVALID, "nhp_disc_gibbs_counts: need %lld uniforms, got %lld", (long long)dd->total_events, (long long)nu);
     DiscExtra *ex = extra_of(dd);
     const int64_t N = dd->N, NB = N * dd->B, NK = 1 + NB;
@@ -1001,7 +1000,16 @@ extern "C" int nhp_disc_gibbs_counts(nhp_ctx *ctx, nhp_disc *dd, uint64_t seed, 
     DCUDA(ctx, cudaMemcpyAsync(&flag, ctx->d_flag, sizeof(int), cudaMemcpyDeviceToHost, s));
     NHP_TRY(nhp_timer_end(ctx));
     NHP_CHECK(ctx, !(flag & 8), NHP_ERR_NUMERIC, "resample_parents (discrete): invalid Multinomial probability vector (parents.jl:116)");
-    DCUDA(ctx, cudaMemcpyAsync(counts, d_counts, bytes_c, cudaMemcpyDeviceToHost, s));
+    // the counts stay on the device for nhp_disc_resample_params (device-side conjugate draws); the host copy is optional
+    if (ctx->dd_counts_cap < (size_t)(N * NK)) {
+        DCUDA(ctx, cudaStreamSynchronize(s));
+        cudaFree(ctx->dd_counts); ctx->dd_counts = nullptr; ctx->dd_counts_cap = 0;
+        DCUDA(ctx, cudaMalloc(&ctx->dd_counts, bytes_c));
+        ctx->dd_counts_cap = (size_t)(N * NK);
+    }
+    DCUDA(ctx, cudaMemcpyAsync(ctx->dd_counts, d_counts, bytes_c, cudaMemcpyDeviceToDevice, s));
+    ctx->dd_counts_N = N; ctx->dd_counts_B = dd->B;
+    if (counts) DCUDA(ctx, cudaMemcpyAsync(counts, d_counts, bytes_c, cudaMemcpyDeviceToHost, s));
     DCUDA(ctx, cudaStreamSynchronize(s));
     return NHP_OK;
 }

@@ -197,6 +197,8 @@ struct nhp_ctx {
     int *dd_klist = nullptr, *dd_kptr = nullptr;  // per child: ascending k = p*B+b of the structurally non-zero entries
     double *dd_btc = nullptr;     // bumpT values at dd_klist
     double dd_density = 1.0;
+    double *dd_counts = nullptr;  // [N * (1 + N B)] counts of the last discrete Gibbs parent sweep (counts[c + N k]), kept for the device-side draws
+    size_t dd_counts_cap = 0; int64_t dd_counts_N = 0, dd_counts_B = 0;
     int64_t dd_maxNA = 0;
 };
 

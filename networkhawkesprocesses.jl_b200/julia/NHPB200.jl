@@ -516,6 +516,22 @@ function update!(impulse::DiscreteGaussianImpulseResponse, data, parents::FusedV
 end
 
 # (E) discrete.jl:426
+# optional: the conjugate draws of the discrete `resample!` (discrete.jl:361-367 / 416-424) on the device, from the counts the last
+# resample_parents left there (baseline Gamma, weight Gamma, Dirichlet theta; Philox keyed by the sweep counter)
+function resample_params_on_device!(process::DiscreteHawkesProcess, data::Matrix{Int64}, convolved::DeviceConvolved)
+    N = ndims(process); B = size(process.impulses.θ, 3)
+    b, w, imp = process.baseline, process.weights, process.impulses
+    Mn = Float64.(vec(sum(data, dims=2)))
+    hyper = Float64[b.α0, b.β0, w.κ, w.ν, imp.γ]
+    λ = Vector{Float64}(undef, N); W = Matrix{Float64}(undef, N, N); θ = Array{Float64}(undef, N, N, B)
+    SWEEP[] += 1
+    check(ccall((:nhp_disc_resample_params, LIB[]), Cint,
+        (Ptr{Cvoid}, Ptr{Cvoid}, UInt64, UInt64, Ptr{Float64}, Ptr{Float64}, Cint, Ptr{Float64}, Ptr{Float64}, Ptr{Float64}),
+        CTX[], convolved.counts.h, Base.rand(UInt64), SWEEP[], Mn, hyper, 5, λ, W, θ))
+    b.λ = λ; w.W = W; imp.θ = θ
+    return nothing
+end
+
 function resample_adjacency_matrix!(process::DiscreteNetworkHawkesProcess, data, convolved::DeviceConvolved)
     push_params!(process)
     A = Matrix{Float64}(process.adjacency_matrix)

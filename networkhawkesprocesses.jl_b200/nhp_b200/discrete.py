@@ -256,6 +256,30 @@ def resample_(process, data, rng, seed=0, counter=0):
     return process.params()
 
 
+def resample_on_device_(process, data, rng=None, seed=0, counter=0):
+    """One Gibbs sweep, `resample!` (discrete.jl:361-367 / 416-424), with the conjugate draws on the device: the counts of the parent
+    sweep stay there (nhp_disc_gibbs_counts with no host copy) and nhp_disc_resample_params draws lambda0, W and the Dirichlet theta
+    from them (Philox: seed, counter); the adjacency sweep and the network draw follow as in `resample_`.  `rng` only feeds the
+    host-side network draw."""
+    d = process._ready(data)
+    ctx = process._ctx()
+    N, B = d.N, process.impulses.nbasis()
+    b, w, imp = process.baseline, process.weights, process.impulses
+    Mn = _f64(vb_row_sums(process, d))  # events per node (cached with the data)
+    process._push(ctx)
+    ctx.check(ctx.lib.nhp_disc_gibbs_counts(ctx.h, d.h, int(seed), int(counter), None, 0, None))
+    hy = np.array([b.alpha0, b.beta0, w.kappa, w.nu, imp.gamma], dtype=np.float64)
+    lam, W, th = np.empty(N), np.empty(N * N), np.empty(N * N * B)
+    ctx.check(ctx.lib.nhp_disc_resample_params(ctx.h, d.h, int(seed), int(counter), _ptr(Mn), _ptr(hy), hy.size, _ptr(lam), _ptr(W), _ptr(th)))
+    b.lam = lam
+    w.W = W.reshape(N, N).T.copy()                             # W[p + N c] -> [p, c]
+    imp.theta = th.reshape(B, N, N).transpose(2, 1, 0).copy()  # theta[p + N (c + N b)] -> [p, c, b]
+    if process.adjacency_matrix is not None:
+        resample_adjacency_matrix_(process, d, seed=seed, counter=counter + (1 << 40))
+        process.network.resample_(process.adjacency_matrix, rng if rng is not None else np.random.default_rng(seed + counter))
+    return process.params()
+
+
 def vb_row_sums(process, d):
     if not hasattr(d, "_rowsum"):
         N, B = d.N, process.impulses.nbasis()

@@ -211,3 +211,42 @@ def test_gibbs_counts_after_adjacency_resample_use_the_new_adjacency():
     ctx.check(ctx.lib.nhp_disc_gibbs_counts(ctx.h, d.h, 0, 0, _ptr(u), u.size, _ptr(counts)))  # no params_set in between
     ref = orc.Disc(lam0, W, theta, dt=1.0, A=A_new).gibbs_counts(data, oconv, u)
     assert np.array_equal(counts.reshape(1 + N * B, N).T, ref)
+
+
+def test_device_conjugate_draws_have_the_posterior_moments():
+    """nhp_disc_resample_params: lambda0 / W Gamma draws and the Dirichlet theta from the device-resident counts of one parent sweep
+    (discrete.jl:361-367): moments over repeated draws with different Philox counters against the closed forms."""
+    rng = np.random.default_rng(11)
+    N, T, B, L = 5, 4000, 3, 6
+    l0, W, th = rng.uniform(0.05, 0.15, N), rng.uniform(0.0, 0.5 / N, (N, N)), rng.dirichlet(np.ones(B), (N, N))
+    data = rng.poisson(0.15, (N, T)).astype(np.int64)
+    proc = D.DiscreteStandardHawkesProcess(D.DiscreteHomogeneousProcess(l0), D.DiscreteGaussianImpulseResponse(th, L), nhp.DenseWeightModel(W))
+    d = proc.upload(data)
+    ctx = proc._ctx()
+    u = rng.random(int(data.sum()))
+    C = D.resample_parents(proc, d, u=u)                     # [c, k]; the same counts stay on the device
+    Mn = data.sum(axis=1).astype(np.float64)
+    b, w, imp = proc.baseline, proc.weights, proc.impulses
+    hy = np.array([b.alpha0, b.beta0, w.kappa, w.nu, imp.gamma])
+    from nhp_b200.core import _ptr
+    R = 400
+    L0, WW, TH = np.empty((R, N)), np.empty((R, N, N)), np.empty((R, N, N, B))
+    for r in range(R):
+        lam, Wf, thf = np.empty(N), np.empty(N * N), np.empty(N * N * B)
+        # the draws replace the context's parameters, the counts on the device stay those of the sweep above
+        ctx.check(ctx.lib.nhp_disc_resample_params(ctx.h, d.h, 5, r, _ptr(Mn), _ptr(hy), 5, _ptr(lam), _ptr(Wf), _ptr(thf)))
+        L0[r], WW[r], TH[r] = lam, Wf.reshape(N, N).T, thf.reshape(B, N, N).transpose(2, 1, 0)
+    np.testing.assert_allclose(TH.sum(axis=3), 1.0, rtol=1e-12)
+    a_l, r_l = b.alpha0 + C[:, 0], b.beta0 + T * proc.dt
+    assert np.all(np.abs(L0.mean(0) - a_l / r_l) < 5 * np.sqrt(a_l) / r_l / np.sqrt(R) + 1e-12)
+    Cpb = C[:, 1:].reshape(N, N, B)                          # [c, p, b]
+    a_w, r_w = w.kappa + Cpb.sum(axis=2).T, (w.nu + Mn)[:, None]
+    assert np.all(np.abs(WW.mean(0) - a_w / r_w) < 5 * np.sqrt(a_w) / r_w / np.sqrt(R) + 1e-12)
+    g = imp.gamma + Cpb.transpose(1, 0, 2)                   # [p, c, b]
+    g0 = g.sum(axis=2, keepdims=True)
+    mean, var = g / g0, g * (g0 - g) / (g0 ** 2 * (g0 + 1.0))
+    assert np.all(np.abs(TH.mean(0) - mean) < 5 * np.sqrt(var / R) + 1e-12)
+    # and the whole device sweep runs as a chain
+    for s_ in range(3):
+        x = D.resample_on_device_(proc, d, seed=3, counter=s_)
+        assert np.all(np.isfinite(x))
