@@ -527,7 +527,7 @@ function resample_params_on_device!(process::DiscreteHawkesProcess, data::Matrix
     SWEEP[] += 1
     check(ccall((:nhp_disc_resample_params, LIB[]), Cint,
         (Ptr{Cvoid}, Ptr{Cvoid}, UInt64, UInt64, Ptr{Float64}, Ptr{Float64}, Cint, Ptr{Float64}, Ptr{Float64}, Ptr{Float64}),
-        CTX[], convolved.counts.h, Base.rand(UInt64), SWEEP[], Mn, hyper, 5, λ, W, θ))
+        CTX[], convolved.d.h, Base.rand(UInt64), SWEEP[], Mn, hyper, 5, λ, W, θ))
     b.λ = λ; w.W = W; imp.θ = θ
     return nothing
 end
