@@ -464,6 +464,38 @@ def run_ours(args, rank, world, local_rank):
     total_ms = float(tmax.item())
     value = n_total * args.steps / (total_ms * 1e-3)
 
+    # ---- full-size checks (size-independent properties on the whole timed stream; outside the timed region):
+    #      the two independent log-likelihood algorithms agree (window sweep over the time-sorted stream vs the active buckets of the
+    #      parent-bucketed pair structure), every event got exactly one parent (sum M0 + sum Mnm = sum Mn = events), A stays 0/1
+    full = None
+    if world == 1:
+        set_params()
+        lls = {}
+        for name, env in (("structure", None), ("window", "0")):
+            if env is None:
+                os.environ.pop("NHP_ADJ_LOGLIK", None)
+            else:
+                os.environ["NHP_ADJ_LOGLIK"] = env
+            llv = ctypes.c_double()
+            ctx.check(lib.nhp_cont_loglik(ctx.h, ev_full, 0, ctypes.byref(llv)))
+            lls[name] = llv.value
+            lls[name + "_ms"] = float(lib.nhp_last_kernel_ms(ctx.h))
+        os.environ.pop("NHP_ADJ_LOGLIK", None)
+        ctx.check(lib.nhp_cont_resample_parents(ctx.h, ev_full, SEED, 777, None, None, None))
+        M0, Mn, Mnm = np.empty(K), np.empty(K), np.empty(K2)
+        ctx.check(lib.nhp_cont_suffstats_read(ctx.h, _ptr(M0), _ptr(Mn), _ptr(Mnm), None, None))
+        Acur = np.empty(K2)
+        ctx.check(lib.nhp_cont_params_get(ctx.h, None, None, _ptr(Acur), None, None))
+        full = {"events": n_total, "loglik_structure": lls["structure"], "loglik_window": lls["window"],
+                "loglik_structure_ms": lls["structure_ms"], "loglik_window_ms": lls["window_ms"],
+                "loglik_rel_diff": abs(lls["structure"] - lls["window"]) / abs(lls["window"]),
+                "parents_assigned": float(M0.sum() + Mnm.sum()), "events_per_node_sum": float(Mn.sum()),
+                "parents_on_inactive_links": float(Mnm[Acur == 0.0].sum()), "adjacency_is_binary": bool(np.all((Acur == 0.0) | (Acur == 1.0)))}
+        full["ok"] = bool(full["loglik_rel_diff"] <= 1e-10 and full["parents_assigned"] == n_total and full["events_per_node_sum"] == n_total
+                          and full["parents_on_inactive_links"] == 0.0 and full["adjacency_is_binary"])
+        if not full["ok"]:
+            raise SystemExit("bench.py: full-size property check failed: %r" % full)
+
     # ---- e2e with the data resident (what `mcmc!` does: upload once, then per sweep only parameters go up and the sample comes back)
     o_l0, o_W, o_A, o_p1, o_p2 = np.empty(K), np.empty(K2), np.empty(K2), np.empty(K2), np.empty(K2)
     sync_all()
@@ -605,7 +637,7 @@ def run_ours(args, rank, world, local_rank):
                        "full_gibbs_sweep_ms": ms_step - med["loglik"],
                        "full_gibbs_sweep_events_per_s": n_total / ((ms_step - med["loglik"]) * 1e-3),
                        "phase_ms_rank0": med, "log_likelihood_last_step": ll_last,
-                       "data_generation_s": gen_s, "events_total": n_total, "parity_checked": bool(parity and parity.get("ok")), "parity": parity}}
+                       "data_generation_s": gen_s, "events_total": n_total, "parity_checked": bool(parity and parity.get("ok")), "parity": parity, "full_size_checks": full}}
 
     if world == 1 and not args.no_cpu_baseline:
         rows, cores, desc, _ = cpu_step_time(args, 1, cpu_sample)
