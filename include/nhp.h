@@ -85,6 +85,21 @@ int nhp_events_download(nhp_ctx *ctx, nhp_events *ev, double *times, int64_t *no
 int nhp_cont_params_set(nhp_ctx *ctx, int kind, int64_t K, const double *lambda0, const double *W, const double *A,
                         const double *p1, const double *p2, double dtmax);
 
+/* Inhomogeneous baseline inside the sweeps: LogGaussianCoxProcess (baselines.jl:187-336), lambda0_k(t) = LinearInterpolator(x,
+ * lambda[k])(t) (utils/interpolation.jl:27-36).  x[n_grid] strictly increasing, values[g + n_grid*k] >= 0.  After this call the
+ * log-likelihood, intensity and parent sweeps of the context use lambda0_k(t_i) as the baseline rate of event i (parent weights:
+ * "baseline last", parents.jl:25-46) and sum_k integrate(lambda0_k) (trapezoid, baselines.jl:336) as the baseline compensator; an
+ * event or query time outside [x[0], x[n_grid-1]] is an error (the reference throws a DomainError).  n_grid = 0 returns to the
+ * homogeneous lambda0; nhp_cont_params_set also does (re-apply the curves after it).  The adjacency sampler and the analytic
+ * gradient take a homogeneous baseline (NHP_ERR_UNSUPPORTED otherwise). */
+int nhp_cont_baseline_grid(nhp_ctx *ctx, int64_t n_grid, const double *x, const double *values);
+/* The likelihood of the elliptical-slice update of the curves (baselines.jl:214-254: resample!(::LogGaussianCoxProcess) =
+ * split_extract + loglikelihood per node), for all K nodes at once and for CANDIDATE curves `values` on grid `x`:
+ *   ll[k] = -integrate(f_k) + sum over the events of node k that the last parent sweep attributed to the baseline of log f_k(t_i).
+ * The parent assignment is the device-resident one of the last nhp_cont_resample_parents on `ev` (split_extract never
+ * materialises).  Time shards return additive shares. */
+int nhp_cont_baseline_loglik(nhp_ctx *ctx, nhp_events *ev, int64_t n_grid, const double *x, const double *values, double *ll);
+
 /* Look-back horizon the sweeps use for the current parameters: dtmax for LogitNormal; for
  * Exponential min(dtmax, H) where H is the cut-off beyond which the omitted tail of any event's
  * history is < 1e-14 of the smallest baseline rate (every omitted term <= max(W theta)

@@ -1099,7 +1099,7 @@ template <int KIND, int PRE> __global__ void __launch_bounds__(ADJ_THREADS, 1) k
 // network is sparse enough that streaming its active buckets beats the window sweep.  Returns 1 when it does not apply.
 int nhp_cont_try_adj_loglik(nhp_ctx *ctx, nhp_events *ev, SweepArgs &sa, int *grid_out) {
     { const char *e = getenv("NHP_ADJ_LOGLIK"); if (e && atoi(e) == 0) return 1; }
-    if (!ctx->has_A || !ev->d_adj_i || ev->adj_cb != 0 || ev->adj_cs != 1 || ev->n_halo != 0 || ev->adj_cluster < 0) return 1;
+    if (!ctx->has_A || !ev->d_adj_i || ev->adj_cb != 0 || ev->adj_cs != 1 || ev->n_halo != 0 || ev->adj_cluster < 0 || sa.lam0ev) return 1;
     if (!(ctx->density <= 0.25) || !(ev->adj_horizon >= sa.horizon) || sa.jmin > 0) return 1;
     if (ctx->kind == NHP_EXPONENTIAL && ev->adj_horizon != sa.horizon && !(sa.horizon < ctx->dtmax)) return 1;  // only a cut-off horizon may be exceeded
     const int64_t K = ctx->K;
@@ -1440,6 +1440,7 @@ static int adj_run(nhp_ctx *ctx, nhp_events *ev, const double *d_rho, double rho
     NHP_CHECK(ctx, ev != nullptr && ev->K == ctx->K, NHP_ERR_INVALID, "adjacency sampler: bad events handle");
     NHP_CHECK(ctx, ev->n_halo == 0 && ev->index_base == 0, NHP_ERR_UNSUPPORTED,
               "the adjacency sampler works on unsharded data (multi-GPU partitions the columns, not the time axis)");
+    NHP_CHECK(ctx, ctx->bgrid_n == 0, NHP_ERR_UNSUPPORTED, "the adjacency sampler takes a homogeneous baseline (grid baselines serve the log-likelihood, intensity and parent sweeps)");
     NHP_CUDA(ctx, cudaSetDevice(ctx->device));
     NHP_CUDA(ctx, fast_tables_upload(ctx->stream));
     NHP_TRY(adj_ensure_ctx(ctx));

@@ -57,10 +57,11 @@ template <int KIND> __global__ void __launch_bounds__(1024) k_child_sweep(const 
             __syncthreads();
         }
         const int e0 = ca.item_e0[item], e1 = min(e0 + CH_EVENTS, ca.node_ptr[c + 1]);
-        const double lam0 = __ldg(a.lambda0 + c);
+        const double lam0_node = __ldg(a.lambda0 + c);
         int m0 = 0;
         for (int e = e0 + warp; e < e1; e += BS / 32) {
             const int i = ca.order[e];
+            const double lam0 = a.lam0ev ? __ldg(a.lam0ev + i) : lam0_node;
             const double ti = __ldg(a.t + i);
             const double thr = ti - a.horizon;
             const int jlo = (int)a.jmin;

@@ -108,6 +108,7 @@ int nhp_cont_try_exp_scan(nhp_ctx *ctx, nhp_events *ev, SweepArgs &a, int *grid_
     if (env && atoi(env) == 0) return 1;
     const bool force = env && atoi(env) == 1;
     if (ctx->kind != NHP_EXPONENTIAL || ev->n_halo != 0 || ev->index_base != 0) return 1;  // shards keep the horizon halo
+    if (a.lam0ev) return 1;  // grid baseline: the window sweeps carry the per-event rate
     const int64_t K = ctx->K, n = ev->n;
     if (n < 2) return 1;
     const size_t smem_agg = (size_t)K * K * sizeof(double);

@@ -178,6 +178,7 @@ extern "C" int nhp_cont_loglik_grad_dev(nhp_ctx *ctx, nhp_events *ev, int recurs
     NHP_CUDA(ctx, cudaSetDevice(ctx->device));
     SweepArgs a;
     NHP_TRY(nhp_cont_fill_args(ctx, ev, recursive, a));
+    NHP_CHECK(ctx, a.lam0ev == nullptr, NHP_ERR_UNSUPPORTED, "the analytic gradient takes a homogeneous baseline");
     const int64_t K = ctx->K, own = ev->n - ev->n_halo;
     const StatsLayout sl{K};
     cudaStream_t s = ctx->stream;
@@ -254,7 +255,7 @@ extern "C" int nhp_cont_loglik_grad_read(nhp_ctx *ctx, nhp_events *ev, double *l
     if (dp1) NHP_CUDA(ctx, cudaMemcpyAsync(dp1, ctx->d_stats0 + sl.off_S1(), (size_t)(K * K) * sizeof(double), cudaMemcpyDeviceToHost, s));
     if (dp2) NHP_CUDA(ctx, cudaMemcpyAsync(dp2, ctx->d_stats1, (size_t)(K * K) * sizeof(double), cudaMemcpyDeviceToHost, s));
     NHP_CUDA(ctx, cudaStreamSynchronize(s));
-    const double base = (ev->flags & 1) ? ctx->lambda0_sum * ev->duration : 0.0;
+    const double base = nhp_cont_baseline_term(ctx, ev);
     if (ll) *ll = h[0] - h[1] - base;
     return NHP_OK;
 }

@@ -12,6 +12,7 @@ struct QueryArgs {
     const double *t; const int *c; int64_t n;
     const double *tq; int64_t nq;
     int K; const void *table; const double *lambda0;
+    const double *gx, *gv; int G;  // grid baseline (G == 0: homogeneous lambda0)
     double D, horizon;
     double *out;  // [nq*K], out[q + nq*k]
 };
@@ -85,7 +86,16 @@ template <int KIND> __global__ void __launch_bounds__(256) k_intensity_query(con
 #pragma unroll
         for (int m = 0; m < MAXC; m++) {
             int ch = cbase + m * 256 + threadIdx.x;
-            if (ch < a.K) a.out[q + a.nq * (int64_t)ch] = a.lambda0[ch] + acc[m];
+            if (ch < a.K) {
+                double b0 = a.lambda0[ch];
+                if (a.G > 0) {  // lambda0_ch(t0) on the grid (interpolation.jl:27-36; the host has checked the support)
+                    const double *y = a.gv + (int64_t)ch * a.G;
+                    int lo = 0, hi = a.G - 1;
+                    while (hi - lo > 1) { const int mid = (lo + hi) >> 1; if (a.gx[mid] <= t0) lo = mid; else hi = mid; }
+                    b0 = t0 >= a.gx[a.G - 1] ? y[a.G - 1] : (y[lo + 1] * (t0 - a.gx[lo]) + y[lo] * (a.gx[lo + 1] - t0)) / (a.gx[lo + 1] - a.gx[lo]);
+                }
+                a.out[q + a.nq * (int64_t)ch] = b0 + acc[m];
+            }
         }
     }
 }
@@ -108,6 +118,13 @@ extern "C" int nhp_cont_intensity(nhp_ctx *ctx, nhp_events *ev, const double *ti
     QueryArgs a;
     a.t = ev->d_t; a.c = ev->d_c; a.n = ev->n; a.tq = dq; a.nq = nq; a.K = (int)ctx->K; a.table = ctx->d_table; a.lambda0 = ctx->d_lambda0;
     a.D = ctx->dtmax; a.horizon = nhp_cont_horizon_value(ctx, ev->index_base + ev->n, 0); a.out = dout;
+    a.gx = ctx->d_bgrid_x; a.gv = ctx->d_bgrid_v; a.G = (int)ctx->bgrid_n;
+    if (ctx->bgrid_n > 0) {
+        std::vector<double> gx((size_t)ctx->bgrid_n);
+        NHP_CUDA(ctx, cudaMemcpy(gx.data(), ctx->d_bgrid_x, gx.size() * sizeof(double), cudaMemcpyDeviceToHost));
+        for (int64_t q = 0; q < nq; q++)
+            NHP_CHECK(ctx, times[q] >= gx.front() && times[q] <= gx.back(), NHP_ERR_INVALID, "intensity: time outside the interpolation support of the baseline grid (interpolation.jl:29)");
+    }
     NHP_TRY(nhp_timer_begin(ctx));
     if (ctx->kind == NHP_LOGITNORMAL) k_intensity_query<NHP_LOGITNORMAL><<<(unsigned)nq, 256, 0, ctx->stream>>>(a);
     else k_intensity_query<NHP_EXPONENTIAL><<<(unsigned)nq, 256, 0, ctx->stream>>>(a);

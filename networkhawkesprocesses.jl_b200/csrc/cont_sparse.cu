@@ -148,7 +148,7 @@ __global__ void __launch_bounds__(NHP_BLOCK, 5) k_sweep_sparse(const SparseArgs 
         if (!tl.staged) {  // window larger than the staging buffer: direct path from global memory
             if (live && g == 0) {
                 const double ti = __ldg(a.t + i);
-                const double S = direct_sum<KIND, false>(a, tl, ft, i, ti, ci, jlo) + __ldg(a.lambda0 + ci);
+                const double S = direct_sum<KIND, false>(a, tl, ft, i, ti, ci, jlo) + base_rate(a, i, ci);
                 if (MODE == SP_LOGLIK) sum_log += log(S);
                 else if (MODE == SP_INTENSITY) a.lam_out[i - a.first] = S;
                 else {
@@ -260,7 +260,7 @@ __global__ void __launch_bounds__(NHP_BLOCK, 5) k_sweep_sparse(const SparseArgs 
                     for (int k = 0; k < c; k++) S += val[o + k];
                 }
             }
-            S += __ldg(a.lambda0 + ci);
+            S += base_rate(a, i, ci);
             if (MODE == SP_LOGLIK) sum_log += log(S);
             else if (MODE == SP_INTENSITY) a.lam_out[i - a.first] = S;
             else {

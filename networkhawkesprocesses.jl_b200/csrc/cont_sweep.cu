@@ -113,7 +113,7 @@ __device__ __forceinline__ void sweep_body(const SweepArgs &a, const Tile &tl, c
         }
         acc = group_sum<G>(acc, gmask);
         if (gl == 0) {
-            const double lam = __ldg(a.lambda0 + ci) + acc;
+            const double lam = base_rate(a, tl.i0 + ev, ci) + acc;
             if (MODE == MODE_INTENSITY) a.lam_out[tl.i0 + ev - a.first] = lam;
             else { sum_log += log(lam); sum_row += __ldg(a.rowsum + ci); }
         }
@@ -195,7 +195,7 @@ __device__ __forceinline__ void parents_body(const SweepArgs &a, const Tile &tl,
             acc += v;
             if (nr < R) my_v[nr * NHP_BLOCK] = v;
         }
-        const double lam0 = __ldg(a.lambda0 + ci);
+        const double lam0 = base_rate(a, i, ci);
         const double S = group_sum<G>(acc, gmask) + lam0;  // sum([weights...; baseline])
         const int64_t gi = a.index_base + i;
         const double u = a.u ? __ldg(a.u + (i - a.first)) : philox_uniform(a.seed, (uint64_t)gi, a.counter);
@@ -441,6 +441,7 @@ static int fill_args(nhp_ctx *ctx, nhp_events *ev, int recursive, SweepArgs &a, 
     a.jmin = rec ? ev->n_t0 : 0;
     a.tile_lo = ev->d_tile_lo; a.te = p.te; a.cap = p.cap; a.K = (int)ctx->K;
     a.table = ctx->d_table; a.lambda0 = ctx->d_lambda0;
+    NHP_TRY(nhp_cont_event_baseline(ctx, ev, &a.lam0ev));
     a.rowsum = (rec && ctx->has_A) ? ctx->d_rowsum_w : ctx->d_rowsum;  // quirk Q3
     a.D = ctx->dtmax; a.horizon = horizon;
     a.partials = nullptr; a.lam_out = nullptr; a.poff = ev->d_poff; a.u = nullptr; a.seed = 0; a.counter = 0;
@@ -495,7 +496,7 @@ extern "C" int nhp_cont_loglik(nhp_ctx *ctx, nhp_events *ev, int recursive, doub
     double h[2];
     NHP_CUDA(ctx, cudaMemcpyAsync(h, ctx->d_stats0, sizeof(h), cudaMemcpyDeviceToHost, ctx->stream));
     NHP_TRY(nhp_timer_end(ctx));
-    double base = (ev->flags & 1) ? ctx->lambda0_sum * ev->duration : 0.0;  // sum(integrated_intensity(baseline, duration))
+    double base = nhp_cont_baseline_term(ctx, ev);  // sum(integrated_intensity(baseline, duration))
     // ll = -sum_k lambda0_k T - sum_i rowsum(c_i) + sum_i log lambda_i   (continuous.jl:217-238)
     *ll = (0.0 - base) - h[1] + h[0];
     return NHP_OK;
@@ -631,7 +632,7 @@ extern "C" int nhp_cont_sweep_loglik(nhp_ctx *ctx, nhp_events *ev, double *ll) {
     double h[2];
     NHP_CUDA(ctx, cudaMemcpyAsync(h, ctx->d_stats0, sizeof(h), cudaMemcpyDeviceToHost, ctx->stream));
     NHP_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
-    double base = (ev->flags & 1) ? ctx->lambda0_sum * ev->duration : 0.0;
+    double base = nhp_cont_baseline_term(ctx, ev);
     *ll = (0.0 - base) - h[1] + h[0];
     return NHP_OK;
 }

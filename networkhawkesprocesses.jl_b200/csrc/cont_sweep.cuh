@@ -20,6 +20,7 @@ struct SweepArgs {
     int K;
     const void *table;      // EntryLN / EntryEX [K*K] child-major
     const double *lambda0;  // [K]
+    const double *lam0ev;   // [n] baseline rate at every event (grid baseline), or NULL: lambda0[node]
     const double *rowsum;   // [K]
     double D;               // dtmax of the LogitNormal support
     double horizon;         // look-back horizon of the window (dtmax, or the Exponential cut-off; may be +Inf)
@@ -32,6 +33,9 @@ struct SweepArgs {
     int *flag;              // device error flag
     int want_ll;            // parent sweep also accumulates the log-likelihood terms (NHP_OPT_SWEEP_LOGLIK)
 };
+
+// baseline rate of event i on node ci: lambda0_ci(t_i) (baselines.jl:328-336) precomputed per event, or the homogeneous lambda0_ci
+__device__ __forceinline__ double base_rate(const SweepArgs &a, int64_t i, int ci) { return a.lam0ev ? __ldg(a.lam0ev + i) : __ldg(a.lambda0 + ci); }
 
 // ---------------------------------------------------------------------------------------
 // mbarrier + 1-D bulk async copy (TMA engine; SASS UBLKCP)

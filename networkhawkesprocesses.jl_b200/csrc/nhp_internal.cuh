@@ -82,6 +82,8 @@ struct nhp_events {
     unsigned short *d_wlen = nullptr;  // [n - n_halo] window length of every own event (saturated at 65535), same cache
     // by-node order of the own events + work items of the child-major sweep (cont_child.cu), built on first use
     int *d_order = nullptr, *d_node_ptr = nullptr, *d_item_node = nullptr, *d_item_e0 = nullptr;
+    double *d_lam0ev = nullptr;     // [n] baseline rate at every event for the context's grid baseline (version below), built on first use
+    uint64_t lam0ev_version = 0;
     int64_t n_items = 0;
     // cached structure of the adjacency sampler (cont_adjacency.cu): every (child event, window predecessor) pair, grouped by
     // virtual column = (child column, time chunk of at most adj_chunk_cap of the column's events) and bucketed by parent node,
@@ -144,6 +146,10 @@ struct nhp_ctx {
     double lambda0_sum = 0.0;
     double a_sum = 0.0;           // sum of the adjacency matrix (number of links), refreshed with the tables
     double *d_lambda0 = nullptr;  // [K]
+    // inhomogeneous baseline (LogGaussianCoxProcess, baselines.jl:187-336): lambda0_k(t) piecewise linear on a grid (cont_baseline.cu)
+    double *d_bgrid_x = nullptr, *d_bgrid_v = nullptr;  // [bgrid_n] grid, [K][bgrid_n] values
+    int64_t bgrid_n = 0; uint64_t bgrid_version = 0;     // 0 points: homogeneous lambda0
+    double baseline_integral = 0.0;                      // sum_k integrate(lambda0_k) over the grid (trapezoid)
     double *d_W = nullptr, *d_A = nullptr, *d_p1 = nullptr, *d_p2 = nullptr; // raw [K*K] parent-major as passed
     void *d_table = nullptr;      // EntryLN/EntryEX [K*K] child-major
     double *d_rowsum = nullptr;   // [K] sum_c [A]W[p,c]
@@ -285,6 +291,8 @@ int nhp_cont_prepare_windows(nhp_ctx *ctx, nhp_events *ev, double horizon);
 int nhp_cont_run_loglik(nhp_ctx *ctx, nhp_events *ev, int recursive);
 double nhp_cont_horizon_value(const nhp_ctx *ctx, int64_t n_total, int recursive);
 int nhp_events_build_node_index(nhp_ctx *ctx, nhp_events *ev);  // d_order / d_node_ptr (cont_child.cu)
+int nhp_cont_event_baseline(nhp_ctx *ctx, nhp_events *ev, const double **lam0ev);  // cont_baseline.cu: NULL for a homogeneous baseline
+double nhp_cont_baseline_term(const nhp_ctx *ctx, const nhp_events *ev);             // sum(integrated_intensity(baseline, duration)) of the log-likelihood
 struct SweepArgs;
 int nhp_cont_try_adj_loglik(nhp_ctx *ctx, nhp_events *ev, SweepArgs &sa, int *grid_out);  // cont_adjacency.cu: 1 = does not apply
 void nhp_events_free_adjacency(nhp_ctx *ctx, nhp_events *ev, cudaStream_t s);

@@ -149,9 +149,12 @@ function push_params!(process::ContinuousHawkesProcess)
     K = ndims(process)
     check(ccall((:nhp_cont_params_set, LIB[]), Cint,
         (Ptr{Cvoid}, Cint, Int64, Ptr{Float64}, Ptr{Float64}, Ptr{Float64}, Ptr{Float64}, Ptr{Float64}, Float64),
-        CTX[], kind(process.impulses), K, convert(Vector{Float64}, process.baseline.λ), convert(Matrix{Float64}, process.weights.W),
+        CTX[], kind(process.impulses), K, baseline_rates(process.baseline), convert(Matrix{Float64}, process.weights.W),
         adjacency(process), p1(process.impulses), p2(process.impulses), Float64(process.impulses.Δtmax)))
+    push_baseline!(process)   # LogGaussianCoxProcess: the curves replace the homogeneous rates inside the sweeps
 end
+baseline_rates(b::HomogeneousProcess) = convert(Vector{Float64}, b.λ)
+baseline_rates(b::LogGaussianCoxProcess) = Float64[sum(l) / length(l) for l in b.λ]   # placeholder rates; the grid takes over
 
 # ================================================== continuous path =============================================================
 # (R) continuous.jl:210 / :360.  On several GPUs every rank computes its shard's share and the shares are summed (NCCL).
@@ -287,6 +290,23 @@ function resample_adjacency_matrix!(process::ContinuousNetworkHawkesProcess, dat
     end
     process.adjacency_matrix .= A
     return nothing
+end
+
+# LogGaussianCoxProcess baselines (baselines.jl:187-336) inside the sweeps: push_params! sends the curves after the parameters, and the
+# elliptical-slice likelihood of resample!(::LogGaussianCoxProcess, data, parents) (baselines.jl:247-254) is evaluated for all nodes at
+# once from the device-resident parent assignment -- split_extract never materialises.
+function push_baseline!(process::ContinuousHawkesProcess)
+    b = process.baseline
+    b isa LogGaussianCoxProcess || return nothing
+    vals = reduce(hcat, b.λ)                                   # [grid, node]: values[g + n_grid*k]
+    check(ccall((:nhp_cont_baseline_grid, LIB[]), Cint, (Ptr{Cvoid}, Int64, Ptr{Float64}, Ptr{Float64}), CTX[], length(b.x), b.x, vals))
+end
+function loglikelihood(process::LogGaussianCoxProcess, data::FusedParents, y::Matrix{Float64})  # y[grid, node]: all nodes at once
+    vals = exp.(process.m .+ y)
+    ll = Vector{Float64}(undef, size(y, 2))
+    check(ccall((:nhp_cont_baseline_loglik, LIB[]), Cint, (Ptr{Cvoid}, Ptr{Cvoid}, Int64, Ptr{Float64}, Ptr{Float64}, Ptr{Float64}),
+        CTX[], data.ev.h, length(process.x), process.x, vals, ll))
+    return ll
 end
 
 # optional: the whole `resample!(process, data)` (continuous.jl:202-208 / 350-358) in one call that never leaves the device

@@ -3,7 +3,7 @@
 from ._lib import NHPError, LIB_PATH, load  # noqa: F401
 from .core import Context, ContinuousData, default_context  # noqa: F401
 from .continuous import (  # noqa: F401
-    HomogeneousProcess, ExponentialImpulseResponse, LogitNormalImpulseResponse, DenseWeightModel, SparseWeightModel,
+    HomogeneousProcess, LogGaussianCoxProcess, ExponentialImpulseResponse, LogitNormalImpulseResponse, DenseWeightModel, SparseWeightModel,
     DenseNetworkModel, BernoulliNetworkModel, ContinuousStandardHawkesProcess, ContinuousNetworkHawkesProcess,
     loglikelihood, loglikelihood_gradient, gradient_vector, event_intensity, intensity, resample_parents, sweep_loglikelihood, sufficient_statistics, resample_adjacency_matrix_,
     resample_, resample_on_device_, pull_params_, adjacency_info, mcmc_, mcmc_device_, mle_, rand, rand_device, MarkovChainMonteCarlo, MaximumLikelihood)

@@ -65,6 +65,8 @@ PROTOTYPES = {
     "nhp_comm_allreduce_stats": (c_int, [c_void_p, c_int]),
     "nhp_comm_allreduce_host": (c_int, [c_void_p, c_void_p, c_int64]),
     "nhp_disc_resample_params": (c_int, [c_void_p, c_void_p, c_uint64, c_uint64, c_void_p, c_void_p, c_int, c_void_p, c_void_p, c_void_p]),
+    "nhp_cont_baseline_grid": (c_int, [c_void_p, c_int64, c_void_p, c_void_p]),
+    "nhp_cont_baseline_loglik": (c_int, [c_void_p, c_void_p, c_int64, c_void_p, c_void_p, c_void_p]),
     "nhp_cont_trace_begin": (c_int, [c_void_p, c_int64]),
     "nhp_cont_trace_push": (c_int, [c_void_p]),
     "nhp_cont_trace_count": (c_int, [c_void_p, POINTER(c_int64), POINTER(c_int64)]),

@@ -59,6 +59,84 @@ class HomogeneousProcess:
         return float(np.sum(gamma(self.alpha0, scale=1.0 / self.beta0).logpdf(self.lam)))
 
 
+class LogGaussianCoxProcess:
+    """baselines.jl:187-336: lambda_k(t) = exp(m + y_k(t)), y_k ~ GP(0, SquaredExponentialKernel(sigma, eta)) on the grid `x`, linearly
+    interpolated in between (utils/interpolation.jl).  `lam[k, g]` are the curve values at the grid points.  On the device the curves
+    live inside the sweeps (nhp_cont_baseline_grid); the elliptical-slice update evaluates its likelihood for all nodes at once from the
+    device-resident parent assignment (nhp_cont_baseline_loglik)."""
+
+    def __init__(self, x, lam, m=0.0, sigma=1.0, eta=1.0):
+        self.x = np.array(x, dtype=np.float64).reshape(-1)
+        self.lam_grid = np.array(lam, dtype=np.float64)
+        if self.lam_grid.ndim != 2 or self.lam_grid.shape[1] != self.x.size:
+            raise ValueError("LogGaussianCoxProcess: lam must be [nodes, len(x)]")
+        if np.any(self.lam_grid < 0):
+            raise ValueError("LogGaussianCoxProcess: intensities must be non-negative")
+        self.m, self.sigma, self.eta = float(m), float(sigma), float(eta)
+        d = self.x[:, None] - self.x[None, :]
+        self.Sigma = self.sigma ** 2 * np.exp(-0.5 * (d / self.eta) ** 2) + 1e-8 * np.eye(self.x.size)
+        self._chol = np.linalg.cholesky(self.Sigma)
+
+    @property
+    def lam(self):
+        """What nhp_cont_params_set takes as lambda0 (the curves replace it on the device): the time averages."""
+        return self.integrated_intensity() / (self.x[-1] - self.x[0])
+
+    def ndims(self):
+        return self.lam_grid.shape[0]
+
+    def params(self):
+        return self.lam_grid.ravel().copy()
+
+    def intensity(self, node, time):
+        if time < self.x[0] or time > self.x[-1]:
+            raise ValueError("Value is outside interpolation support")  # DomainError interpolation.jl:29
+        return float(np.interp(time, self.x, self.lam_grid[node]))
+
+    def integrated_intensity(self):
+        return np.trapezoid(self.lam_grid, self.x, axis=1) if hasattr(np, "trapezoid") else np.trapz(self.lam_grid, self.x, axis=1)
+
+    def logprior(self):
+        y = np.log(self.lam_grid) - self.m
+        z = np.linalg.solve(self._chol, y.T)
+        return float(-0.5 * np.sum(z * z) - self.ndims() * (np.sum(np.log(np.diag(self._chol))) + 0.5 * self.x.size * np.log(2 * np.pi)))
+
+    def resample_(self, ctx, d, rng, max_attempts=100):
+        """resample!(process::LogGaussianCoxProcess, data, parents) (baselines.jl:214-254): one elliptical-slice update per node
+        [Murray, Adams & MacKay 2010]; all nodes advance together, every attempt is one device evaluation of the K likelihoods."""
+        K, G = self.lam_grid.shape
+        xs = _f64(self.x)
+
+        def loglik(vals):
+            ll = np.empty(K)
+            ctx.check(ctx.lib.nhp_cont_baseline_loglik(ctx.h, d.h, G, _ptr(xs), _ptr(_f64(vals.ravel())), _ptr(ll)))
+            return ll
+
+        y = np.log(self.lam_grid) - self.m
+        nu = (self._chol @ rng.standard_normal((G, K))).T
+        lly = loglik(self.lam_grid) + np.log(rng.random(K))
+        theta = rng.uniform(0.0, 2.0 * np.pi, K)
+        lo, hi = theta - 2.0 * np.pi, theta.copy()
+        done = np.zeros(K, dtype=bool)
+        ynew = y.copy()
+        for _ in range(max_attempts):
+            cand = y * np.cos(theta)[:, None] + nu * np.sin(theta)[:, None]
+            vals = np.where(done[:, None], np.exp(self.m + ynew), np.exp(self.m + cand))
+            ok = (loglik(vals) >= lly) & ~done
+            ynew[ok] = cand[ok]
+            done |= ok
+            if done.all():
+                break
+            neg = theta < 0.0
+            lo = np.where(~done & neg, theta, lo)
+            hi = np.where(~done & ~neg, theta, hi)
+            theta = np.where(done, theta, rng.uniform(lo, hi))
+        else:
+            raise RuntimeError("Elliptical slice sampling reached maximum attempts.")  # baselines.jl:316
+        self.lam_grid = np.exp(self.m + ynew)
+        return self.lam_grid.copy()
+
+
 class ExponentialImpulseResponse:
     """impulses.jl:30-37: theta[parent, child]; dtmax defaults to Inf."""
     kind = NHP_EXPONENTIAL
@@ -247,6 +325,9 @@ class ContinuousHawkesProcess:
         p1 = _fmat(imp.p1())
         p2 = None if imp.p2() is None else _fmat(imp.p2())
         ctx.check(ctx.lib.nhp_cont_params_set(ctx.h, imp.kind, K, _ptr(lam), _ptr(W), _ptr(A), _ptr(p1), _ptr(p2), float(imp.dtmax)))
+        if isinstance(self.baseline, LogGaussianCoxProcess):  # the curves replace the homogeneous lambda0 inside the sweeps
+            b = self.baseline
+            ctx.check(ctx.lib.nhp_cont_baseline_grid(ctx.h, b.x.size, _ptr(_f64(b.x)), _ptr(_f64(b.lam_grid.ravel()))))
 
     def upload(self, data, ctx=None):
         """Make `data = (events, nodes, duration)` device resident; pass the result wherever `data` is accepted."""
@@ -467,7 +548,10 @@ def resample_(process, data, rng, seed=0, counter=0):
         process._push(ctx)
         _resample_parents(ctx, d, seed, counter, None, False)
         st = _read_stats(ctx, d, process.ndims())
-        process.baseline.resample_(st["M0"], d.duration, rng)
+        if isinstance(process.baseline, LogGaussianCoxProcess):
+            process.baseline.resample_(ctx, d, rng)
+        else:
+            process.baseline.resample_(st["M0"], d.duration, rng)
         process.weights.resample_(st["Mn"], st["Mnm"], rng)
         process.impulses.resample_(st["Mnm"], st["S1"], st["S2"], rng)
         if process.adjacency_matrix is not None:
