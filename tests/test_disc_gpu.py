@@ -34,7 +34,8 @@ def test_kat_e(kat):
     assert D.loglikelihood(proc, d) == pytest.approx(k["ll"], rel=1e-12)
 
 
-@pytest.mark.parametrize("N,T,B,L,network", [(3, 500, 3, 4, False), (20, 3000, 4, 8, True), (70, 1500, 6, 12, False), (5, 200, 1 + 1, 2, True)])
+@pytest.mark.parametrize("N,T,B,L,network", [(3, 500, 3, 4, False), (20, 3000, 4, 8, True), (70, 1500, 6, 12, False), (5, 200, 1 + 1, 2, True),
+                                             (200, 3000, 6, 12, True)])  # last: BASELINE config 3's shape (N = 200, B = 6, L = 12: the NT = 5 DMMA tile)
 def test_convolve_intensity_loglik(N, T, B, L, network):
     proc, om, data = make(N, T, B, L, 3 + N, network)
     d = proc.upload(data)
@@ -46,7 +47,7 @@ def test_convolve_intensity_loglik(N, T, B, L, network):
 
 
 @pytest.mark.parametrize("warp", ["1", "0"])
-@pytest.mark.parametrize("N,T,B,L,network", [(3, 400, 3, 4, False), (12, 1500, 4, 6, True), (70, 800, 6, 12, False)])
+@pytest.mark.parametrize("N,T,B,L,network", [(3, 400, 3, 4, False), (12, 1500, 4, 6, True), (70, 800, 6, 12, False), (200, 1500, 6, 12, True)])
 def test_gibbs_counts_match_given_uniforms(N, T, B, L, network, warp, monkeypatch):
     monkeypatch.setenv("NHP_DISC_WARP", warp)
     proc, om, data = make(N, T, B, L, 11 + N, network, rate=0.2)
@@ -114,7 +115,7 @@ def test_gibbs_counts_distribution():
 
 
 @pytest.mark.parametrize("warp", ["1", "0"])
-@pytest.mark.parametrize("N,T,B,L", [(3, 400, 3, 4), (15, 2000, 5, 10), (70, 800, 6, 12)])
+@pytest.mark.parametrize("N,T,B,L", [(3, 400, 3, 4), (15, 2000, 5, 10), (70, 800, 6, 12), (200, 1200, 6, 12)])
 def test_vb_statistics(N, T, B, L, warp, monkeypatch):
     monkeypatch.setenv("NHP_DISC_WARP", warp)
     proc, om, data = make(N, T, B, L, 31 + N, False, rate=0.1)
@@ -140,7 +141,7 @@ def test_vb_and_gibbs_steps_run():
     np.testing.assert_allclose(proc.impulses.theta.sum(axis=2), 1.0, rtol=1e-12)
 
 
-@pytest.mark.parametrize("N,T,B,L", [(4, 300, 3, 4), (8, 600, 2, 5)])
+@pytest.mark.parametrize("N,T,B,L", [(4, 300, 3, 4), (8, 600, 2, 5), (48, 300, 6, 12)])
 def test_discrete_adjacency_matches_oracle(N, T, B, L):
     proc, om, data = make(N, T, B, L, 51 + N, True, rate=0.2)
     d = proc.upload(data)

@@ -13,6 +13,7 @@ pytestmark = pytest.mark.gpu
 
 @pytest.mark.parametrize("kind,K,n,rate,density,dtmax", [
     ("ln", 60, 40000, 64.0, 0.05, 1.0),      # typical: ~3 hits per window
+    ("ln", 1000, 30000, 64.0, 0.05, 1.0),    # BASELINE config 4's exact shape (K = 1000, rho = 0.05, mean window 64: SG = 2) at an oracle-sized N
     ("ln", 1200, 30000, 64.0, 0.05, 1.0),    # K > 1024: bit rows longer than one warp load
     ("ln", 30, 20000, 200.0, 0.6, 1.0),      # dense-ish: slot overflow -> direct path for most events
     ("ln", 12, 20000, 300.0, None, 1.0),     # Standard process forced through the sparse kernel (every pair active)
