@@ -263,6 +263,11 @@ int nhp_disc_params_set(nhp_ctx *ctx, int64_t N, int64_t B, const double *lambda
 int nhp_disc_intensity(nhp_ctx *ctx, nhp_disc *dd, double *lam);
 /* loglikelihood(process, data, convolved)  discrete.jl:91-102 */
 int nhp_disc_loglik(nhp_ctx *ctx, nhp_disc *dd, double *ll);
+/* Extension for the discrete `mle!` (discrete.jl:211-296; the reference differentiates numerically): the log-likelihood of
+ * nhp_disc_loglik (ll may be NULL) and its analytic gradient in the layouts of nhp_disc_params_set -- dlambda0[N], dW[N*N]
+ * (dW[p + N*c]), dtheta[N*N*B] (dtheta[p + N*(c + N*b)]); entries with A[p,c] = 0 get 0.  The T x N x (N B) contraction collapses to the
+ * non-zero bins plus the conv column sums.  Time shards return additive shares. */
+int nhp_disc_loglik_grad(nhp_ctx *ctx, nhp_disc *dd, double *ll, double *dlambda0, double *dW, double *dtheta);
 /* resample_parents(process, data, convolved) reduced over t  parents.jl:82-134:
  * counts[c + N*k], k = 0 baseline, k = 1 + p*B + b.  u (one uniform per event, consumed in
  * (t outer, c inner, draw) order) or NULL for Philox. */

@@ -1086,6 +1086,101 @@ extern "C" int nhp_disc_vb_stats(nhp_ctx *ctx, nhp_disc *dd, const double *e0, c
 }
 
 // ---------------------------------------------------------------------------------------
+// Analytic gradient of the discrete log-likelihood for `mle!` (discrete.jl:211-296; the reference hands Optim a gradient-free
+// objective, its comments at :220-231 sketch the gradient form).  With r[t,c] = s[t,c] / lambda[t,c] - 1:
+//   d ll / d lambda0[c]   = dt sum_t r[t,c]
+//   d ll / d bump[k,c]    = sum_t conv[t,k] r[t,c] = Gs[k,c] - csum[k],   Gs[k,c] = sum over the NON-ZERO bins of conv[t,k] s / lambda
+//   d ll / d W[p,c]       = [A] dt sum_b theta[p,c,b] (Gs - csum)[(p,b),c];    d ll / d theta[p,c,b] = [A] W[p,c] dt (Gs - csum)[(p,b),c]
+// so the T x N x (N B) contraction collapses to the non-zero bins (4 % of the cells at config 3) plus the conv column sums that the
+// convolution already left behind: the same (time block, child) warp-per-bin pass as the VB statistics.
+// ---------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) k_disc_grad_warp(const double *__restrict__ convT, const double *__restrict__ bumpT, const double *__restrict__ lambda0, double dt,
+                                                        int N, int NB, const int *__restrict__ nz_t, const int *__restrict__ nz_s, const int *__restrict__ child_ptr, int tb,
+                                                        double *__restrict__ rsum, double *__restrict__ GsT) {
+    extern __shared__ double s_buf[];  // [NB] bump column of the child | [8][NB] per-warp accumulators
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    double *bt = s_buf, *acc = s_buf + NB + (size_t)warp * NB;
+    const int c = blockIdx.x % N, blk = blockIdx.x / N;
+    const int ei0 = child_ptr[c], e1 = child_ptr[c + 1];
+    const int b0 = nz_lower_bound(nz_t, ei0, e1, blk * tb), b1 = nz_lower_bound(nz_t, b0, e1, (blk + 1) * tb);
+    if (b0 == b1) return;  // block-uniform
+    for (int k = threadIdx.x; k < NB; k += 256) bt[k] = bumpT[(int64_t)c * NB + k];
+    for (int k = lane; k < NB; k += 32) acc[k] = 0.0;
+    __syncthreads();
+    const double base = lambda0[c] * dt;
+    double asum = 0.0;
+    for (int e = b0 + warp; e < b1; e += 8) {
+        const double *row = convT + (int64_t)nz_t[e] * NB;
+        double part = 0.0;
+        for (int k = lane; k < NB; k += 32) part += __ldg(row + k) * bt[k];
+        const double r = (double)nz_s[e] / (base + warp_sum_d(part));  // s / lambda[t,c]
+        asum += r;
+        for (int k = lane; k < NB; k += 32) acc[k] += r * __ldg(row + k);
+    }
+    __syncthreads();
+    for (int k = threadIdx.x; k < NB; k += 256) {
+        double g = 0.0;
+#pragma unroll
+        for (int wv = 0; wv < 8; wv++) g += s_buf[NB + (size_t)wv * NB + k];
+        if (g != 0.0) atomicAdd(&GsT[(int64_t)c * NB + k], g);
+    }
+    if (lane == 0 && asum != 0.0) atomicAdd(&rsum[c], asum);
+}
+// one thread per (p, c): chain rule from the bump gradient to W and theta; thread c < N also finishes d/d lambda0
+__global__ void k_disc_grad_finish(const double *__restrict__ GsT, const double *__restrict__ csum, const double *__restrict__ rsum, const double *__restrict__ W,
+                                   const double *__restrict__ A, const double *__restrict__ theta, double dt, double own_bins, int N, int B,
+                                   double *__restrict__ dl0, double *__restrict__ dW, double *__restrict__ dth) {
+    const int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x, NN = (int64_t)N * N;
+    if (e < N) dl0[e] = dt * (rsum[e] - own_bins);
+    if (e >= NN) return;
+    const int p = (int)(e % N), c = (int)(e / N);  // e = p + N c
+    const double a = A ? A[e] : 1.0, w = W[e];
+    double s = 0.0;
+    for (int b = 0; b < B; b++) {
+        const double g = GsT[(int64_t)c * N * B + p * B + b] - csum[p * B + b];
+        s += theta[e + NN * b] * g;
+        dth[e + NN * b] = a * w * dt * g;
+    }
+    dW[e] = a * dt * s;
+}
+
+extern "C" int nhp_disc_loglik_grad(nhp_ctx *ctx, nhp_disc *dd, double *ll, double *dlambda0, double *dW, double *dtheta) {
+    NHP_TRY(disc_ready(ctx, dd, "nhp_disc_loglik_grad"));
+    NHP_CHECK(ctx, dlambda0 && dW && dtheta, NHP_ERR_INVALID, "nhp_disc_loglik_grad: NULL output");
+    if (ll) NHP_TRY(nhp_disc_loglik(ctx, dd, ll));
+    const double ms_ll = ll ? ctx->last_ms : 0.0;
+    DiscExtra *ex = extra_of(dd);
+    const int64_t N = dd->N, B = dd->B, NB = N * B, NN = N * N;
+    cudaStream_t s = ctx->stream;
+    void *scratch;
+    NHP_TRY(nhp_scratch(ctx, (size_t)(NB * N + N + N + NN + NN * B) * sizeof(double), &scratch));
+    double *d_Gs = (double *)scratch, *d_rs = d_Gs + NB * N, *d_l0 = d_rs + N, *d_dW = d_l0 + N, *d_dth = d_dW + NN;
+    DCUDA(ctx, cudaMemsetAsync(d_Gs, 0, (size_t)(NB * N + N) * sizeof(double), s));
+    NHP_TRY(nhp_timer_begin(ctx));
+    if (ex->nnz > 0) {
+        const size_t wsmem = (size_t)9 * NB * sizeof(double);
+        NHP_CHECK(ctx, wsmem <= (size_t)ctx->smem_optin - 4096, NHP_ERR_UNSUPPORTED, "nhp_disc_loglik_grad: N B = %lld exceeds the shared-memory accumulators", (long long)NB);
+        DCUDA(ctx, cudaFuncSetAttribute(k_disc_grad_warp, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)wsmem));
+        const int tb = pick_time_block(ctx, dd, ex->nnz);
+        const int64_t nblk = (dd->T + tb - 1) / tb;
+        k_disc_grad_warp<<<(unsigned)(N * nblk), 256, wsmem, s>>>(dd->d_conv, ctx->dd_bump + NB * N, ctx->dd_lambda0, ctx->ddt, (int)N, (int)NB, ex->nz_t, ex->nz_s, ex->child_ptr,
+                                                                  tb, d_rs, d_Gs);
+        NHP_LAUNCHED(ctx);
+    }
+    k_disc_grad_finish<<<(unsigned)((NN + 255) / 256), 256, 0, s>>>(d_Gs, ex->csum, d_rs, ctx->dd_W, ctx->d_has_A ? ctx->dd_A : nullptr, ctx->dd_theta, ctx->ddt,
+                                                                    (double)(dd->T - dd->t_halo), (int)N, (int)B, d_l0, d_dW, d_dth);
+    NHP_LAUNCHED(ctx);
+    DCUDA(ctx, cudaGetLastError());
+    NHP_TRY(nhp_timer_end(ctx));
+    ctx->last_ms += ms_ll;
+    DCUDA(ctx, cudaMemcpyAsync(dlambda0, d_l0, (size_t)N * sizeof(double), cudaMemcpyDeviceToHost, s));
+    DCUDA(ctx, cudaMemcpyAsync(dW, d_dW, (size_t)NN * sizeof(double), cudaMemcpyDeviceToHost, s));
+    DCUDA(ctx, cudaMemcpyAsync(dtheta, d_dth, (size_t)(NN * B) * sizeof(double), cudaMemcpyDeviceToHost, s));
+    DCUDA(ctx, cudaStreamSynchronize(s));
+    return NHP_OK;
+}
+
+// ---------------------------------------------------------------------------------------
 // discrete adjacency Gibbs (discrete.jl:426-480): per column c, p sequential.
 //   ll1 - ll0 = sum_{t: s>0} s [log(lam^{-p} + G_p) - log(lam^{-p})] - sum_t G_p[t] + log rho - log(1-rho),
 //   G_p[t] = sum_b convT[t,(p,b)] W[p,c] theta[p,c,b] dt.   One CTA per column; the rank-1 update of the

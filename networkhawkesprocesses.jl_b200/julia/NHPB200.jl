@@ -536,6 +536,17 @@ function update!(impulse::DiscreteGaussianImpulseResponse, data, parents::FusedV
 end
 
 # (E) discrete.jl:426
+# optional extension for the discrete `mle!` (discrete.jl:211-296 differentiates numerically): log-likelihood + analytic gradient
+function loglikelihood_gradient(process::DiscreteHawkesProcess, data, convolved::DeviceConvolved)
+    push_params!(process)
+    N = ndims(process); B = size(process.impulses.θ, 3)
+    ll = Ref{Float64}(0.0)
+    dλ = Vector{Float64}(undef, N); dW = Matrix{Float64}(undef, N, N); dθ = Array{Float64}(undef, N, N, B)
+    check(ccall((:nhp_disc_loglik_grad, LIB[]), Cint, (Ptr{Cvoid}, Ptr{Cvoid}, Ref{Float64}, Ptr{Float64}, Ptr{Float64}, Ptr{Float64}),
+        CTX[], convolved.d.h, ll, dλ, dW, dθ))
+    return ll[], (λ=dλ, W=dW, θ=dθ)
+end
+
 # optional: the conjugate draws of the discrete `resample!` (discrete.jl:361-367 / 416-424) on the device, from the counts the last
 # resample_parents left there (baseline Gamma, weight Gamma, Dirichlet theta; Philox keyed by the sweep counter)
 function resample_params_on_device!(process::DiscreteHawkesProcess, data::Matrix{Int64}, convolved::DeviceConvolved)

@@ -64,6 +64,7 @@ PROTOTYPES = {
     "nhp_comm_rank": (c_int, [c_void_p, POINTER(c_int), POINTER(c_int)]),
     "nhp_comm_allreduce_stats": (c_int, [c_void_p, c_int]),
     "nhp_comm_allreduce_host": (c_int, [c_void_p, c_void_p, c_int64]),
+    "nhp_disc_loglik_grad": (c_int, [c_void_p, c_void_p, POINTER(c_double), c_void_p, c_void_p, c_void_p]),
     "nhp_disc_resample_params": (c_int, [c_void_p, c_void_p, c_uint64, c_uint64, c_void_p, c_void_p, c_int, c_void_p, c_void_p, c_void_p]),
     "nhp_cont_baseline_grid": (c_int, [c_void_p, c_int64, c_void_p, c_void_p]),
     "nhp_cont_baseline_loglik": (c_int, [c_void_p, c_void_p, c_int64, c_void_p, c_void_p, c_void_p]),

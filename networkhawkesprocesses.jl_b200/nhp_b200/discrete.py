@@ -179,6 +179,19 @@ def loglikelihood(process, data):
     return ll.value
 
 
+def loglikelihood_gradient(process, data):
+    """Extension for `mle!` (discrete.jl:211-296; the reference differentiates numerically): the log-likelihood and its analytic
+    gradient (nhp_disc_loglik_grad).  Returns `(ll, grads)` with `lambda0 [N]`, `W [p, c]`, `theta [p, c, b]`."""
+    ctx = process._ctx()
+    d = process._ready(data)
+    process._push(ctx)
+    N, B = d.N, process.impulses.nbasis()
+    ll = ctypes.c_double()
+    g0, gW, gT = np.empty(N), np.empty(N * N), np.empty(N * N * B)
+    ctx.check(ctx.lib.nhp_disc_loglik_grad(ctx.h, d.h, ctypes.byref(ll), _ptr(g0), _ptr(gW), _ptr(gT)))
+    return ll.value, dict(lambda0=g0, W=gW.reshape(N, N).T.copy(), theta=gT.reshape(B, N, N).transpose(2, 1, 0).copy())
+
+
 def resample_parents(process, data, seed=0, counter=0, u=None):
     """parents.jl:82-117 reduced over t: counts[c, k], k = 0 baseline, k = 1 + p*B + b."""
     ctx = process._ctx()

@@ -251,3 +251,37 @@ def test_device_conjugate_draws_have_the_posterior_moments():
     for s_ in range(3):
         x = D.resample_on_device_(proc, d, seed=3, counter=s_)
         assert np.all(np.isfinite(x))
+
+
+@pytest.mark.parametrize("N,T,B,L,network", [(4, 600, 3, 5, False), (30, 2500, 4, 8, True), (200, 1500, 6, 12, True)])
+def test_analytic_gradient_of_the_discrete_loglikelihood(N, T, B, L, network):
+    """nhp_disc_loglik_grad against a NumPy statement of the gradient (dense contraction over all bins) built on the oracle's convolution,
+    and against central differences of the oracle's log-likelihood."""
+    proc, om, data = make(N, T, B, L, 90 + N, network, rate=0.08)
+    d = proc.upload(data)
+    ll, g = D.loglikelihood_gradient(proc, d)
+    conv = orc.disc_convolve(data, orc.disc_basis(L, B))          # [t, p, b]
+    assert ll == pytest.approx(om.loglik(data, conv), rel=1e-10)
+    lam0, W, th = proc.baseline.lam, proc.weights.W, proc.impulses.theta
+    A = np.ones((N, N)) if proc.adjacency_matrix is None else proc.adjacency_matrix
+    dt = proc.dt
+    bump = (A * W)[:, :, None] * th * dt                            # [p, c, b]
+    lam = lam0[None, :] * dt + np.einsum("tpb,pcb->tc", conv, bump)
+    r = data.T / lam - 1.0                                          # [t, c]
+    Gb = np.einsum("tpb,tc->pcb", conv, r)
+    np.testing.assert_allclose(g["lambda0"], dt * r.sum(axis=0), rtol=1e-9, atol=1e-9 * T)
+    scale_W, scale_T = np.max(np.abs(dt * (th * Gb).sum(axis=2))), np.max(np.abs(W[:, :, None] * dt * Gb))
+    np.testing.assert_allclose(g["W"], A * dt * (th * Gb).sum(axis=2), rtol=1e-9, atol=1e-10 * scale_W)
+    np.testing.assert_allclose(g["theta"], (A * W)[:, :, None] * dt * Gb, rtol=1e-9, atol=1e-10 * scale_T)
+    if N <= 30:  # central differences of the oracle on a few entries
+        rng = np.random.default_rng(1)
+        for _ in range(4):
+            p, c = rng.integers(0, N, 2)
+            if A[p, c] == 0.0:
+                continue
+            h = 1e-3 * max(W[p, c], 1e-3)  # the oracle's ll ~ 1e4 carries ~1e-12 of rounding: a smaller step drowns in it
+            Wp, Wm = W.copy(), W.copy()
+            Wp[p, c] += h
+            Wm[p, c] -= h
+            fd = (orc.Disc(lam0, Wp, th, dt=dt, A=proc.adjacency_matrix).loglik(data, conv) - orc.Disc(lam0, Wm, th, dt=dt, A=proc.adjacency_matrix).loglik(data, conv)) / (2 * h)
+            assert g["W"][p, c] == pytest.approx(fd, rel=1e-4, abs=1e-3)

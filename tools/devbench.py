@@ -127,6 +127,8 @@ if __name__ == "__main__":
             st = D.vb_statistics(proc, d, e0, E); print(f"vb stats {ctx.last_kernel_ms:.2f} ms", flush=True)
         for rep in range(2):
             D.resample_adjacency_matrix_(proc, d, seed=2, counter=rep); print(f"disc adjacency {ctx.last_kernel_ms:.2f} ms links {int(proc.adjacency_matrix.sum())}", flush=True)
+        for rep in range(2):
+            llg, _ = D.loglikelihood_gradient(proc, d); print(f"loglik + analytic gradient {ctx.last_kernel_ms:.2f} ms  ll={llg:.6e}", flush=True)
         sys.exit(0)
     if which == "cfg5":  # cfg5 n
         n, K = int(float(sys.argv[2])), 5000
