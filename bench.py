@@ -210,7 +210,7 @@ def workload_config(args, world, n_total, n_shard):
             "data_mode": args.data, "chain": args.chain,
             "sharding": ("contiguous time shards + dtmax halo (log-likelihood, parent sweep, statistics); child columns c % N == rank on the replicated stream "
                          "(adjacency sweep)") if world > 1 else "single GPU",
-            "l2_policy": "inputs (1.2 GB of events, 64 GB of cached adjacency pairs) are larger than the 126 MB L2; no explicit flush"}
+            "l2_policy": "inputs (1.2 GB of events, 116 GB of cached adjacency pairs) are larger than the 126 MB L2; no explicit flush"}
 
 
 # ------------------------------------------------------------------------------------------

@@ -123,3 +123,21 @@ def test_gradient_vector_follows_params_order(kind):
         np.testing.assert_array_equal(q.impulses.p2(), g["p2"])
     h = _hyper(p)  # [alpha0, beta0, kappa, nu, impulse hyper-parameters] as nhp_cont_resample_params expects
     assert h.size == (8 if kind == "ln" else 6) and np.all(h[:4] == [p.baseline.alpha0, p.baseline.beta0, p.weights.kappa, p.weights.nu])
+
+
+def test_log_gaussian_cox_process_host_methods():
+    """Host side of the LogGaussianCoxProcess baseline (baselines.jl:187-336): interpolation support, trapezoid integral, parameter
+    vector; the placeholder rates handed to nhp_cont_params_set are the time averages of the curves."""
+    x = np.linspace(0.0, 10.0, 6)
+    lam = np.array([[1.0, 2.0, 3.0, 2.0, 1.0, 1.0], [0.5] * 6])
+    b = nhp.LogGaussianCoxProcess(x, lam, m=0.0, sigma=1.0, eta=2.0)
+    assert b.ndims() == 2 and b.params().size == 12
+    assert b.intensity(0, 1.0) == pytest.approx(1.5)                       # interpolation.jl:31
+    assert b.intensity(0, 10.0) == pytest.approx(1.0)                      # the last grid point belongs to the support
+    with pytest.raises(ValueError):
+        b.intensity(0, 10.5)                                               # DomainError interpolation.jl:29
+    np.testing.assert_allclose(b.integrated_intensity(), [2.0 * (0.5 * 1 + 2 + 3 + 2 + 1 + 0.5 * 1), 5.0])
+    np.testing.assert_allclose(b.lam, b.integrated_intensity() / 10.0)
+    assert np.isfinite(b.logprior())
+    with pytest.raises(ValueError):
+        nhp.LogGaussianCoxProcess(x, lam[:, :-1])
