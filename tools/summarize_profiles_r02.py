@@ -57,15 +57,15 @@ def table(title, cmd, rows, note):
 def regions(rep, kernel_index=None, min_share=0.01):
     """Per-region accounting from the SASS page: consecutive instructions with a similar execution count form a region (a loop body,
     a phase); reports each region's share of the stall samples and of the executed warp instructions."""
-    args = ['ncu', '-i', rep, '--page', 'source', '--csv', '--print-source', 'sass']
-    if kernel_index is not None:
-        args += ['--launch-skip', str(kernel_index), '--launch-count', '1']
-    out = subprocess.run(args, capture_output=True, text=True).stdout
+    out = subprocess.run(['ncu', '-i', rep, '--page', 'source', '--csv', '--print-source', 'sass'], capture_output=True, text=True).stdout
     rows = list(csv.reader(io.StringIO(out)))
-    hi = [i for i, r in enumerate(rows) if r and r[0] == "Address"][0]
+    # one table per kernel of the report: "Kernel Name" line, header line ("Address", ...), instruction rows
+    heads = [i for i, r in enumerate(rows) if r and r[0] == "Address"]
+    hi = heads[kernel_index if kernel_index is not None and kernel_index < len(heads) else 0]
+    end = min([h for h in heads if h > hi] + [len(rows)])
     hdr = rows[hi]
     iS, iI, iP = hdr.index("Source"), hdr.index("Instructions Executed"), hdr.index("# Samples")
-    body = [r for r in rows[hi + 1:] if len(r) > iP and r[0].startswith("0x")]
+    body = [r for r in rows[hi + 1:end] if len(r) > iP and r[0].startswith("0x")]
     tot_s = sum(int(r[iP]) for r in body) or 1
     tot_i = sum(int(r[iI]) for r in body) or 1
     segs, k0, cur, acc = [], 0, None, []
@@ -91,10 +91,10 @@ def f(d, k):
 
 
 def main():
-    step_rep = sys.argv[1] if len(sys.argv) > 1 else os.path.join(G, 'r4a_prof_step.ncu-rep')
+    step_rep = sys.argv[1] if len(sys.argv) > 1 else os.path.join(G, 'r6a_prof_step.ncu-rep')
     build_rep = sys.argv[2] if len(sys.argv) > 2 else os.path.join(G, 'r3p_prof_build.ncu-rep')
-    launch_csv = sys.argv[3] if len(sys.argv) > 3 else os.path.join(G, 'r4a_launches.csv')
-    bench_json = sys.argv[4] if len(sys.argv) > 4 else os.path.join(G, 'r4a_bench.json')
+    launch_csv = sys.argv[3] if len(sys.argv) > 3 else os.path.join(G, 'r6a_launches.csv')
+    bench_json = sys.argv[4] if len(sys.argv) > 4 else os.path.join(G, 'r6a_bench.json')
     os.makedirs(P, exist_ok=True)
 
     # ---- launch list
@@ -114,7 +114,7 @@ def main():
     md = ["# r02 ncu launch list -- `python bench.py --steps 2 --warmup 1 --no-cpu-baseline` (N=1, cfg4: 1e8 events, K=1000, rho=0.05, hawkes data)", "",
           "`ncu --metrics gpu__time_duration.sum --clock-control none -c 600` after the same command exited 0 without ncu.  Per-launch times are cold-cache and",
           "serialised: compare SHARES.  One step = `k_sweep_sparse<1,0>` (log-likelihood) + `k_sweep_sparse<1,2>` (parent sweep + statistics) + `k_xbar`, `k_second_pass`,",
-          "`k_conjugate`, the table rebuild, `k_adj_prep` + `k_adj_sweep` (adjacency sweep) + `k_beta_draw`; `k_adj_build` / `k_adj_count` / `k_adj_links` and the CUB sort run once",
+          "`k_conjugate`, the table rebuild, `k_adj_prep` + `k_adj_sweep` (adjacency sweep) + `k_beta_draw`; from the second step on the log-likelihood is `k_adj_loglik` (active buckets of the cached structure); `k_adj_build` / `k_adj_count` / `k_adj_links` and the CUB sort run once",
           "per events handle (structure build); `k_rand_*` is the device simulator that generates the stream; the rest is set-up and the roofline micro-benchmarks.", "",
           "| kernel | launches | total ms | share | mean ms |", "|---|---:|---:|---:|---:|"]
     for k, v in sorted(agg.items(), key=lambda kv: -sum(kv[1])):
@@ -133,15 +133,15 @@ def main():
             "3 %% section padding, the re-read of the buckets whose link flipped and of the links that are on at the start of a column); %.1f warp instructions per 32 pairs" %
             (f(adj, 'smsp__inst_executed.sum') / (pairs / 32.0)),
             "(round 1: 211).  The kernel is bound by instruction issue inside the streaming phase and by the barriers between the phases of a batch",
-            "(stream 32 buckets -> cluster exchange -> decisions by warp 0 -> flips).  Regions of the SASS page (consecutive instructions with similar execution counts):", "",
+            "(stream 32 buckets -> exchange of the sums through distributed shared memory + one cluster barrier -> decisions, taken by every warp alike -> flips).  Regions of the SASS page (consecutive instructions with similar execution counts):", "",
             "| SASS instructions | executions | stall samples | warp instructions | hottest instruction (share of samples) |", "|---|---:|---:|---:|---|"]
     for a, b, c, s, i, t, src in reg:
         note.append("| %d-%d | %d | %.1f %% | %.1f %% | `%s` (%.1f %%) |" % (a, b, c, s, i, src, t))
     note += ["", "The region that executes once per 64-entry block of singles is the streaming loop (130 instructions per 64 pairs: one 32-bit + one 256-bit load, two table-driven",
              "exps, two shared-memory intensity look-ups, product accumulation, three min/max trackers, an L2 prefetch); the regions with ~7e6 executions are the",
-             "per-batch phases (32 warps x 130 CTAs x batches); `LDS.128` behind `BAR.SYNC` is the wait for warp 0's decisions, `UCGABAR_WAIT` the cluster barrier."]
-    txt = table("r02 ncu full capture -- the three kernels of the bench step (N=1, cfg4, hawkes data)",
-                "`ncu --set full --clock-control none --import-source on --kernel-name regex:\"k_adj_sweep|k_sweep_sparse\" --launch-skip 6 --launch-count 3` under "
+             "per-batch phases (32 warps x 130 CTAs x batches); `UCGABAR_WAIT` is the cluster barrier that ends a batch (waiting for the slowest warp of the slowest CTA), the `BRA` behind `BAR.SYNC` the barrier of a flip's application."]
+    txt = table("r02 ncu full capture -- the three kernels of the bench step (N=1, cfg4, hawkes data): log-likelihood through the cached structure (`k_adj_loglik`), parent sweep (`k_sweep_sparse<1,2>`), adjacency sweep (`k_adj_sweep`)",
+                "`ncu --set full --clock-control none --import-source on --kernel-name regex:\"k_adj_sweep|k_sweep_sparse|k_adj_loglik\" --launch-skip 5 --launch-count 3` under "
                 "`python bench.py --steps 2 --warmup 1 --no-cpu-baseline`.", rows, "\n".join(note))
     open(os.path.join(P, 'r02_ncu_step_kernels.md'), 'w').write(txt)
     dom = {"kernel": adj['Kernel Name'][0], "pairs": pairs,
