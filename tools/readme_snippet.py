@@ -9,5 +9,5 @@ data = proc.upload(nhp.rand(proc, 200.0, np.random.default_rng(0)))
 ll = nhp.loglikelihood(proc, data)
 ll2, grads = nhp.loglikelihood_gradient(proc, data)
 parents, parentnodes = nhp.resample_parents(proc, data, seed=1)
-chain = nhp.mcmc_(proc, data, nsteps=200, device_draws=True, store_every=10)
+chain = nhp.mcmc_device_(proc, data, nsteps=200)
 print("readme snippet ok", ll, ll2, len(parents), len(chain.samples))
