@@ -407,7 +407,7 @@ def run_ours(args, rank, world, local_rank):
         e0 = torch.cuda.Event(enable_timing=True); e1 = torch.cuda.Event(enable_timing=True)
         e0.record(stream)
         ll = ctypes.c_double()
-        ctx.check(lib.nhp_cont_loglik(ctx.h, ev_shard, 0, ctypes.byref(ll)))
+        ctx.check(lib.nhp_cont_loglik_dist(ctx.h, ev_shard, ev_full, 0, ctypes.byref(ll)))  # N > 1: the rank's share (its columns of the structure once it exists, else its time shard)
         llk = ctx.last_kernel_ms
         llv = np.array([ll.value])
         ctx.check(lib.nhp_comm_allreduce_host(ctx.h, _ptr(llv), 1))
@@ -505,7 +505,7 @@ def run_ours(args, rank, world, local_rank):
     for k in range(once_steps):
         set_params()
         ll = ctypes.c_double()
-        ctx.check(lib.nhp_cont_loglik(ctx.h, ev_shard, 0, ctypes.byref(ll)))
+        ctx.check(lib.nhp_cont_loglik_dist(ctx.h, ev_shard, ev_full, 0, ctypes.byref(ll)))  # N > 1: the rank's share (its columns of the structure once it exists, else its time shard)
         llv = np.array([ll.value])
         ctx.check(lib.nhp_comm_allreduce_host(ctx.h, _ptr(llv), 1))
         ctx.check(lib.nhp_cont_gibbs_sweep(ctx.h, ev_shard, ev_full, SEED, 2000 + k, float(duration), _ptr(hyper), hyper.size, 1.0, 1.0))

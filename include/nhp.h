@@ -111,6 +111,10 @@ int nhp_cont_horizon(nhp_ctx *ctx, int64_t n_total, int recursive, double *horiz
  * (continuous.jl:241-276 / 407-442, incl. quirks Q3/Q6/Q7 of SURVEY.md section 9).  For a shard
  * the result is the shard's additive share (sum over ranks = ll). */
 int nhp_cont_loglik(nhp_ctx *ctx, nhp_events *ev, int recursive, double *ll);
+/* Multi-GPU form: this rank's additive share (sum over ranks = ll).  ev_shard is the rank's time shard; when the replicated stream
+ * ev_full (may be NULL) already carries the rank's columns of the adjacency structure, the share is taken from it instead (active
+ * buckets of the columns c = rank mod nranks; rank 0 adds the baseline and compensator terms).  Single GPU: nhp_cont_loglik(ev_shard). */
+int nhp_cont_loglik_dist(nhp_ctx *ctx, nhp_events *ev_shard, nhp_events *ev_full, int recursive, double *share);
 /* Extension for mle! (continuous.jl:144-198; the reference gives Optim a gradient-free objective, i.e.
  * ~2P log-likelihood evaluations per finite-difference gradient): the log-likelihood of nhp_cont_loglik
  * together with its analytic gradient, from two sweeps over the events.  Layouts as the parameters:

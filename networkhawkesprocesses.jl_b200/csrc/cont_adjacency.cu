@@ -1104,9 +1104,9 @@ template <int KIND, int PRE> __global__ void __launch_bounds__(ADJ_THREADS, 1) k
 
 // Log-likelihood through the cached structure when it exists for this handle, covers every column and the horizon, and the
 // network is sparse enough that streaming its active buckets beats the window sweep.  Returns 1 when it does not apply.
-int nhp_cont_try_adj_loglik(nhp_ctx *ctx, nhp_events *ev, SweepArgs &sa, int *grid_out) {
+int nhp_cont_try_adj_loglik(nhp_ctx *ctx, nhp_events *ev, SweepArgs &sa, int *grid_out, int cb, int cs) {  // structure of the columns c % cs == cb: their share
     { const char *e = getenv("NHP_ADJ_LOGLIK"); if (e && atoi(e) == 0) return 1; }
-    if (!ctx->has_A || !ev->d_adj_i || ev->adj_cb != 0 || ev->adj_cs != 1 || ev->n_halo != 0 || ev->adj_cluster < 0 || sa.lam0ev) return 1;
+    if (!ctx->has_A || !ev->d_adj_i || ev->adj_cb != cb || ev->adj_cs != cs || ev->n_halo != 0 || ev->adj_cluster < 0 || sa.lam0ev) return 1;
     if (!(ctx->density <= 0.25) || !(ev->adj_horizon >= sa.horizon) || sa.jmin > 0) return 1;
     if (ctx->kind == NHP_EXPONENTIAL && ev->adj_horizon != sa.horizon && !(sa.horizon < ctx->dtmax)) return 1;  // only a cut-off horizon may be exceeded
     const int64_t K = ctx->K;

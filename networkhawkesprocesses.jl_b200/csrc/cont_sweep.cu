@@ -481,6 +481,38 @@ int nhp_cont_run_loglik(nhp_ctx *ctx, nhp_events *ev, int recursive) {
     return NHP_OK;
 }
 
+// Log-likelihood share of this rank in a multi-GPU job (sum over ranks = ll).  When the replicated stream `ev_full` carries this
+// rank's part of the adjacency structure (the columns c = rank mod nranks, built by the first adjacency sweep) the share is taken from
+// it -- sum log lambda over the events on the rank's columns, active buckets only; rank 0 adds the baseline and compensator terms.
+// Otherwise (no structure yet, dense network, recursive semantics) it is the time shard's share as in nhp_cont_loglik(ev_shard).
+extern "C" int nhp_cont_loglik_dist(nhp_ctx *ctx, nhp_events *ev_shard, nhp_events *ev_full, int recursive, double *share) {
+    NHP_CHECK(ctx, ctx != nullptr, NHP_ERR_INVALID, "ctx is NULL");
+    NHP_CHECK(ctx, ev_shard != nullptr && share != nullptr, NHP_ERR_INVALID, "nhp_cont_loglik_dist: NULL argument");
+    NHP_CUDA(ctx, cudaSetDevice(ctx->device));
+    if (ev_full && !recursive && ctx->nranks > 1 && ev_full->d_adj_i && ev_full->adj_cb == ctx->rank && ev_full->adj_cs == ctx->nranks) {
+        SweepArgs a; LaunchPlan p;
+        NHP_TRY(fill_args(ctx, ev_full, 0, a, p));
+        if (p.tiles > 0) {
+            NHP_TRY(nhp_partials(ctx, 2 * (int64_t)ctx->sm_count * 32, &a.partials));
+            NHP_TRY(nhp_timer_begin(ctx));
+            int sgrid = 0;
+            const int sp = nhp_cont_try_adj_loglik(ctx, ev_full, a, &sgrid, ctx->rank, ctx->nranks);
+            if (sp < 0) return sp;
+            if (sp == NHP_OK) {
+                k_reduce_partials<<<1, 1024, 0, ctx->stream>>>(a.partials, sgrid, ctx->d_stats0, ev_full->d_Mn, a.rowsum, (int)ctx->K);
+                NHP_LAUNCHED(ctx);
+                double h[2];
+                NHP_CUDA(ctx, cudaMemcpyAsync(h, ctx->d_stats0, sizeof(h), cudaMemcpyDeviceToHost, ctx->stream));
+                NHP_TRY(nhp_timer_end(ctx));
+                *share = h[0] - (ctx->rank == 0 ? nhp_cont_baseline_term(ctx, ev_full) + h[1] : 0.0);
+                return NHP_OK;
+            }
+            NHP_TRY(nhp_timer_end(ctx));
+        }
+    }
+    return nhp_cont_loglik(ctx, ev_shard, recursive, share);
+}
+
 extern "C" int nhp_cont_loglik_dev(nhp_ctx *ctx, nhp_events *ev, int recursive) {
     NHP_CHECK(ctx, ctx != nullptr, NHP_ERR_INVALID, "ctx is NULL");
     NHP_CUDA(ctx, cudaSetDevice(ctx->device));

@@ -294,7 +294,7 @@ int nhp_events_build_node_index(nhp_ctx *ctx, nhp_events *ev);  // d_order / d_n
 int nhp_cont_event_baseline(nhp_ctx *ctx, nhp_events *ev, const double **lam0ev);  // cont_baseline.cu: NULL for a homogeneous baseline
 double nhp_cont_baseline_term(const nhp_ctx *ctx, const nhp_events *ev);             // sum(integrated_intensity(baseline, duration)) of the log-likelihood
 struct SweepArgs;
-int nhp_cont_try_adj_loglik(nhp_ctx *ctx, nhp_events *ev, SweepArgs &sa, int *grid_out);  // cont_adjacency.cu: 1 = does not apply
+int nhp_cont_try_adj_loglik(nhp_ctx *ctx, nhp_events *ev, SweepArgs &sa, int *grid_out, int cb = 0, int cs = 1);  // cont_adjacency.cu: 1 = does not apply
 void nhp_events_free_adjacency(nhp_ctx *ctx, nhp_events *ev, cudaStream_t s);
 void *nhp_big_alloc(nhp_ctx *ctx, size_t bytes);              // nullptr when the device cannot provide it
 void nhp_big_free(nhp_ctx *ctx, void *p, size_t bytes);       // ctx == nullptr: cudaFree

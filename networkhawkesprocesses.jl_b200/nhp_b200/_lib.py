@@ -66,6 +66,7 @@ PROTOTYPES = {
     "nhp_comm_allreduce_host": (c_int, [c_void_p, c_void_p, c_int64]),
     "nhp_disc_loglik_grad": (c_int, [c_void_p, c_void_p, POINTER(c_double), c_void_p, c_void_p, c_void_p]),
     "nhp_disc_resample_params": (c_int, [c_void_p, c_void_p, c_uint64, c_uint64, c_void_p, c_void_p, c_int, c_void_p, c_void_p, c_void_p]),
+    "nhp_cont_loglik_dist": (c_int, [c_void_p, c_void_p, c_void_p, c_int, POINTER(c_double)]),
     "nhp_cont_baseline_grid": (c_int, [c_void_p, c_int64, c_void_p, c_void_p]),
     "nhp_cont_baseline_loglik": (c_int, [c_void_p, c_void_p, c_int64, c_void_p, c_void_p, c_void_p]),
     "nhp_cont_trace_begin": (c_int, [c_void_p, c_int64]),

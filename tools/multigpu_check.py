@@ -106,6 +106,16 @@ def main():
     res["adjacency_links"] = int(A_full.sum())
     ok &= res["adjacency_mismatches"] == 0
 
+    # distributed log-likelihood: the share through this rank's columns of the structure (built by the partitioned sweep above)
+    proc._push(ctx)
+    ctx.check(lib.nhp_cont_loglik(ctx.h, full.h, 0, ctypes.byref(ll_full)))
+    share = ctypes.c_double()
+    ctx.check(lib.nhp_cont_loglik_dist(ctx.h, shard.h, full.h, 0, ctypes.byref(share)))
+    v = np.array([share.value])
+    ctx.check(lib.nhp_comm_allreduce_host(ctx.h, _ptr(v), 1))
+    res["loglik_dist_rel_err"] = abs(v[0] - ll_full.value) / abs(ll_full.value)
+    ok &= res["loglik_dist_rel_err"] < 1e-12
+
     # composite sweep: identical parameters on every rank
     proc._push(ctx)
     ctx.check(lib.nhp_cont_network_set(ctx.h, rho))
