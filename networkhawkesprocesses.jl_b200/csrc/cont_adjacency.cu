@@ -490,6 +490,7 @@ struct AdjSweepArgs {
     int chunk_max;         // doubles of shared memory in front of the adjacency bit row
     int *flag, *next; unsigned long long *stat;
     int col_begin, col_stride, ncols;
+    const int *corder;     // [ncols] owned columns, most child events first (NULL: col_begin + i col_stride)
     int s0, lmax;   // first batch size; log2 of the largest
 };
 
@@ -498,6 +499,11 @@ __device__ __forceinline__ unsigned cluster_ctarank() { unsigned r; asm volatile
 __device__ __forceinline__ unsigned cluster_nctarank() { unsigned r; asm volatile("mov.u32 %0, %%cluster_nctarank;" : "=r"(r)); return r; }
 __device__ __forceinline__ void cluster_sync_all() {
     asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void st_cluster_u32(int *local_smem, unsigned rank, int v) {
+    unsigned ra;
+    asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(ra) : "r"(smem_u32(local_smem)), "r"(rank));
+    asm volatile("st.shared::cluster.u32 [%0], %1;" ::"r"(ra), "r"(v) : "memory");
 }
 __device__ __forceinline__ void st_cluster_f64(double *local_smem, unsigned rank, double v) {
     unsigned ra;
@@ -743,15 +749,24 @@ template <int KIND, int PRE, bool CL> __global__ void __launch_bounds__(ADJ_THRE
     // (the same arithmetic in every CTA of a cluster, so they agree on S).
     float fw_steps = 64.f, fw_flips = 64.f * fmaxf(4.f / (float)(a.s0 * a.s0) - 1e-3f, 0.f);
     int S = a.s0;
-    for (int ci = cid;; ci += ncl) {
-        if (!CL) {  // a single CTA per column: dynamic scheduling
-            __syncthreads();
+    (void)ncl; (void)cid;
+    for (;;) {
+        // dynamic scheduling, longest columns first (a.corder): a CTA, or the first CTA of a cluster for all of its cluster, takes the
+        // next column
+        __syncthreads();
+        if (CL) {
+            if (crank == 0 && tid == 0) {
+                const int nx = atomicAdd(a.next, 1);
+                for (unsigned r = 0; r < csize; r++) st_cluster_u32(&s_col, r, nx);
+            }
+            cluster_sync_all();
+        } else {
             if (tid == 0) s_col = atomicAdd(a.next, 1);
             __syncthreads();
-            ci = s_col;
         }
+        const int ci = s_col;
         if (ci >= a.ncols) break;
-        const int c = a.col_begin + ci * a.col_stride;
+        const int c = a.corder ? a.corder[ci] : a.col_begin + ci * a.col_stride;
         const int e0 = a.node_ptr[c], ne = a.node_ptr[c + 1] - e0;
         const int v0 = a.vstart[c], G = a.vstart[c + 1] - v0;  // CL: G == cluster size
         const int csz = adj_chunk_size(ne, G);
@@ -1324,6 +1339,14 @@ static int adj_build_structure(nhp_ctx *ctx, nhp_events *ev, double horizon, int
         std::stable_sort(key.begin(), key.end(), [](const std::pair<double, int> &a, const std::pair<double, int> &b) { return a.first < b.first; });
         for (int64_t v = 0; v < nv; v++) vorder[(size_t)v] = key[(size_t)v].second;
     }
+    {   // sweep order of the owned columns: most child events first (longest-processing-time scheduling of the clusters)
+        std::vector<int> co;
+        for (int64_t c = cb; c < K; c += cs) co.push_back((int)c);
+        std::stable_sort(co.begin(), co.end(), [&](int x, int y) { return mn[x] > mn[y]; });
+        ADJ_S(cudaMallocAsync(&ev->d_adj_corder, std::max<size_t>(co.size(), 1) * sizeof(int), s));
+        ADJ_S(cudaMemcpyAsync(ev->d_adj_corder, co.data(), co.size() * sizeof(int), cudaMemcpyHostToDevice, s));
+        ADJ_S(cudaStreamSynchronize(s));
+    }
     int *d_vorder = nullptr;
     ADJ_S(cudaMallocAsync(&d_vorder, (size_t)nv * sizeof(int), s));
     ADJ_S(cudaMemcpyAsync(d_vorder, vorder.data(), (size_t)nv * sizeof(int), cudaMemcpyHostToDevice, s));
@@ -1506,7 +1529,7 @@ static int adj_run(nhp_ctx *ctx, nhp_events *ev, const double *d_rho, double rho
         w.lam = ev->d_adj_lam;
         w.chunk_max = (ev->adj_chunk_max + 1) & ~1;
         w.flag = ctx->d_flag; w.next = ctx->d_adj_ctl; w.stat = ctx->d_adj_stat;
-        w.col_begin = (int)col_begin; w.col_stride = (int)col_stride;
+        w.col_begin = (int)col_begin; w.col_stride = (int)col_stride; w.corder = ev->d_adj_corder;
         w.ncols = (int)((K - col_begin + col_stride - 1) / col_stride);
         w.s0 = ADJ_SMAX;
         { const char *e = getenv("NHP_ADJ_S0"); if (e && atoi(e) >= 1 && atoi(e) <= 32 && (atoi(e) & (atoi(e) - 1)) == 0) w.s0 = atoi(e); }

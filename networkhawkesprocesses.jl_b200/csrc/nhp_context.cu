@@ -331,7 +331,8 @@ void nhp_events_free_adjacency(nhp_ctx *ctx, nhp_events *ev, cudaStream_t s) {
     // synchronisation, and the next structure of a similar size starts from warm memory
     nhp_big_free(ctx, ev->d_adj_i, ev->adj_bytes_i); nhp_big_free(ctx, ev->d_adj_dt, ev->adj_bytes_dt);
     ev->adj_bytes_i = ev->adj_bytes_dt = 0;
-    void *blocks[] = {ev->d_adj_vstart, ev->d_adj_vnode, ev->d_adj_vbase, ev->d_adj_boff, ev->d_adj_lam};
+    void *blocks[] = {ev->d_adj_vstart, ev->d_adj_vnode, ev->d_adj_vbase, ev->d_adj_boff, ev->d_adj_lam, ev->d_adj_corder};
+    ev->d_adj_corder = nullptr;
     for (void *b : blocks) if (b) cudaFreeAsync(b, s);
     ev->d_adj_vstart = ev->d_adj_vnode = ev->d_adj_boff = nullptr; ev->d_adj_vbase = nullptr; ev->d_adj_i = nullptr;
     ev->d_adj_dt = ev->d_adj_q = ev->d_adj_lam = nullptr;

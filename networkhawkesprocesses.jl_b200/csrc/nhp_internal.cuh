@@ -95,6 +95,7 @@ struct nhp_events {
     int64_t adj_nv = 0;              // number of virtual columns
     int *d_adj_vstart = nullptr;     // [K+1] first virtual column of every column
     int *d_adj_vnode = nullptr;      // [nv] child column of every virtual column
+    int *d_adj_corder = nullptr;     // [owned columns] sweep order: most child events first
     int64_t *d_adj_vbase = nullptr;  // [nv+1] first entry of every virtual column
     int *d_adj_boff = nullptr;       // [nv][2K+1] section offsets inside a virtual column: singles of parent p at [2p], its runs at [2p+1]
     unsigned short *d_adj_i = nullptr;  // [adj_total] child event index inside its chunk | bit 15: same (event, parent) as the previous entry
