@@ -54,14 +54,18 @@ def table(title, cmd, rows, note):
     return "\n".join(md)
 
 
-def regions(rep, kernel_index=None, min_share=0.01):
+def regions(rep, kernel_index=None, min_share=0.01):  # kernel_index: substring of the kernel name
     """Per-region accounting from the SASS page: consecutive instructions with a similar execution count form a region (a loop body,
     a phase); reports each region's share of the stall samples and of the executed warp instructions."""
     out = subprocess.run(['ncu', '-i', rep, '--page', 'source', '--csv', '--print-source', 'sass'], capture_output=True, text=True).stdout
     rows = list(csv.reader(io.StringIO(out)))
-    # one table per kernel of the report: "Kernel Name" line, header line ("Address", ...), instruction rows
+    # one table (sometimes repeated) per kernel of the report: "Kernel Name" line, header line ("Address", ...), instruction rows
     heads = [i for i, r in enumerate(rows) if r and r[0] == "Address"]
-    hi = heads[kernel_index if kernel_index is not None and kernel_index < len(heads) else 0]
+    pick = heads[0]
+    if kernel_index is not None:
+        named = [h for h in heads if h > 0 and rows[h - 1] and rows[h - 1][0] == "Kernel Name" and str(kernel_index) in rows[h - 1][1]]
+        pick = named[0] if named else heads[0]
+    hi = pick
     end = min([h for h in heads if h > hi] + [len(rows)])
     hdr = rows[hi]
     iS, iI, iP = hdr.index("Source"), hdr.index("Instructions Executed"), hdr.index("# Samples")
@@ -126,8 +130,7 @@ def main():
     rows = raw(step_rep)
     adj = [d for d in rows if 'k_adj_sweep' in d['Kernel Name'][0]][0]
     pairs = json.load(open(bench_json))["roofline"]["adjacency_sweep"]["pairs"]
-    ai = [k for k, d in enumerate(rows) if d is adj][0]
-    reg, tot_i = regions(step_rep, ai)
+    reg, tot_i = regions(step_rep, 'k_adj_sweep')
     note = ["Reading (adjacency sweep, `k_adj_sweep<LOGITNORMAL, payload, cluster>`): %.1f GB read for %.1f GB of cached pairs (18 B x %.3g pairs; the rest is the" %
             (f(adj, 'dram__bytes_read.sum') * SCALE[adj['dram__bytes_read.sum'][1]] / 1e9, 18 * pairs / 1e9, pairs),
             "3 %% section padding, the re-read of the buckets whose link flipped and of the links that are on at the start of a column); %.1f warp instructions per 32 pairs" %
