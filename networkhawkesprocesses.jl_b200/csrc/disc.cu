@@ -260,6 +260,105 @@ __global__ void __launch_bounds__(256) k_convolve_tp(const int *__restrict__ dat
     }
 }
 
+// HBM-bound form (B <= 8, L <= 64, N <= 256): a thread owns one node p and walks SEGMENTS of consecutive time rows, so
+//  (i)   the non-zero lags of its window live in a bit mask that slides with t and the last RS >= L counts in a per-thread ring in
+//        shared memory (one global count load per (t, p) instead of L; the counts are sparse, 4 % non-zero bins at config 3); only
+//        the non-zero lags take the B multiply-adds, lags ascending as before (same rounding),
+//  (ii)  the column sums sum_t convT[t][p*B + b] over the own bins accumulate in registers and the separate pass that re-read all of
+//        convT (9.6 GB at config 3) is gone,
+//  (iii) a warp's 32 (t, p..p+31) results -- one contiguous span of 32*B doubles of convT -- go through a per-warp staging buffer
+//        (pitch B + 1 for even B: conflict-free) and leave as fully coalesced stores (the thread-per-(t,p) stores were 8 bytes at a
+//        8*B-byte stride).
+// PW = N rounded up to whole warps, R = row groups per CTA (blockDim = PW * R); CONV_TT = rows per segment; RS = ring slots (power of 2).
+constexpr int CONV_TT = 128;
+template <int B>
+__global__ void __launch_bounds__(256, 4) k_convolve_rows(const int *__restrict__ data, int N, int64_t T, int64_t t_own, const double *__restrict__ phi, int L,
+                                                          int PW, int R, int RS, double *__restrict__ convT, double *__restrict__ csum) {
+    constexpr int PITCH = (B & 1) ? B : B + 1;
+    extern __shared__ double s_cv[];  // [L * B] phi | per warp: [32 * PITCH] staging | [RS][blockDim] ring of counts
+    double *s_phi = s_cv;
+    for (int i = threadIdx.x; i < L * B; i += blockDim.x) s_phi[i] = phi[i];
+    __syncthreads();
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarp = blockDim.x >> 5;
+    double *stg = s_cv + L * B + warp * 32 * PITCH;
+    int *ring = reinterpret_cast<int *>(s_cv + L * B + nwarp * 32 * PITCH) + threadIdx.x;  // slot k of this thread: ring[k * blockDim.x]
+    const int bd = blockDim.x, rmask = RS - 1;
+    const int r = threadIdx.x / PW, p = threadIdx.x - r * PW;  // warps never straddle row groups: PW is a multiple of 32
+    const int p0 = p - lane;                                  // first node of this warp
+    const int nq = max(0, min(32, N - p0)) * B;               // doubles this warp writes per row
+    const int NB = N * B;
+    const bool live = p < N;
+    const unsigned long long lmask = L >= 64 ? ~0ull : ((1ull << L) - 1ull);
+    int rd[B];  // staged position of the m-th double this lane stores: element q = lane + 32 m sits at (q / B) * PITCH + q % B
+#pragma unroll
+    for (int m = 0; m < B; m++) { const int q = lane + 32 * m; rd[m] = (q / B) * PITCH + q % B; }
+    double cs[B];
+#pragma unroll
+    for (int b = 0; b < B; b++) cs[b] = 0.0;
+    const int64_t nseg = (T + CONV_TT - 1) / CONV_TT;
+    for (int64_t seg = (int64_t)blockIdx.x * R + r; seg < nseg; seg += (int64_t)gridDim.x * R) {
+        const int64_t tb = seg * CONV_TT;
+        const int nt = (int)min((int64_t)CONV_TT, T - tb);
+        unsigned long long nz = 0ull;  // bit l - 1: data[t - l][p] != 0
+        const int *col = data + tb * N + (live ? p : 0);
+        if (live) {
+            const int lmax = (int)min((int64_t)L, tb);
+            for (int l = 1; l <= lmax; l++) {
+                const int v = __ldg(col - l * N);
+                ring[((int)(tb & rmask) - l & rmask) * bd] = v;
+                nz |= (unsigned long long)(v != 0) << (l - 1);
+            }
+        }
+        int slot = (int)(tb & rmask);  // ring slot of row t
+        double *dst = convT + tb * NB + (int64_t)p0 * B;
+        for (int it = 0; it < nt; it++, col += N, dst += NB, slot = (slot + 1) & rmask) {
+            double acc[B];
+#pragma unroll
+            for (int b = 0; b < B; b++) acc[b] = 0.0;
+            const int cur = live ? __ldg(col) : 0;  // enters the window of row t + 1
+            for (unsigned long long m = nz; m;) {
+                const int l1 = __ffsll((long long)m) - 1;  // lag - 1
+                m &= m - 1;
+                const double dv = (double)ring[((slot - 1 - l1) & rmask) * bd];
+                const double *ph = s_phi + l1;
+#pragma unroll
+                for (int b = 0; b < B; b++) acc[b] += ph[L * b] * dv;
+            }
+            ring[slot * bd] = cur;
+            nz = ((nz << 1) | (unsigned long long)(cur != 0)) & lmask;
+            const double ownf = tb + it >= t_own ? 1.0 : 0.0;
+#pragma unroll
+            for (int b = 0; b < B; b++) {
+                const double v = fmax(acc[b], 0.0);
+                stg[lane * PITCH + b] = v;
+                cs[b] = fma(ownf, v, cs[b]);
+            }
+            __syncwarp();
+            if (nq == 32 * B) {
+#pragma unroll
+                for (int m = 0; m < B; m++) dst[lane + 32 * m] = stg[rd[m]];
+            } else {
+#pragma unroll
+                for (int m = 0; m < B; m++)
+                    if (lane + 32 * m < nq) dst[lane + 32 * m] = stg[rd[m]];
+            }
+            __syncwarp();
+        }
+    }
+    if (live) {
+#pragma unroll
+        for (int b = 0; b < B; b++)
+            if (cs[b] != 0.0) atomicAdd(&csum[p * B + b], cs[b]);
+    }
+}
+typedef void (*conv_rows_fn)(const int *, int, int64_t, int64_t, const double *, int, int, int, int, double *, double *);
+static conv_rows_fn conv_rows_kernel(int B) {
+    switch (B) {
+        case 1: return k_convolve_rows<1>; case 2: return k_convolve_rows<2>; case 3: return k_convolve_rows<3>; case 4: return k_convolve_rows<4>;
+        case 5: return k_convolve_rows<5>; case 6: return k_convolve_rows<6>; case 7: return k_convolve_rows<7>; default: return k_convolve_rows<8>;
+    }
+}
+
 // Julia layout export: out[t + T*(n + N*b)] = convT[t][n*B + b]   (tiled transpose)
 __global__ void k_conv_export(const double *__restrict__ convT, int N, int B, int64_t T, double *__restrict__ out) {
     __shared__ double tile[32][33];
@@ -305,6 +404,28 @@ extern "C" int nhp_disc_convolve(nhp_ctx *ctx, nhp_disc *dd, const double *phi, 
     dd->L = L; dd->B = B;
     NHP_TRY(nhp_timer_begin(ctx));
     int grid = (int)std::min<int64_t>(dd->T, (int64_t)ctx->sm_count * 16);
+    const char *envr = getenv("NHP_DISC_CONV_ROWS");
+    if (B <= 8 && L <= 64 && dd->N <= 256 && !(envr && atoi(envr) == 0)) {
+        // rows kernel: stores through a staging buffer, column sums fused (no second pass over convT)
+        const int PW = (int)((dd->N + 31) / 32) * 32, R = std::max(1, 256 / PW), threads = PW * R;
+        int RS = 1;
+        while (RS < L) RS <<= 1;
+        const int pitch = (B & 1) ? (int)B : (int)B + 1;
+        const size_t smem = ((size_t)(L * B) + (size_t)(threads / 32) * 32 * pitch) * sizeof(double) + (size_t)RS * threads * sizeof(int);
+        conv_rows_fn kern = conv_rows_kernel((int)B);
+        DCUDA(ctx, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)std::max<size_t>(smem, 1024)));
+        int per_sm = 1;
+        DCUDA(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, threads, smem));
+        per_sm = std::max(per_sm, 1);
+        const int64_t nseg = (dd->T + CONV_TT - 1) / CONV_TT;
+        const int g3 = (int)std::min<int64_t>((nseg + R - 1) / R, (int64_t)ctx->sm_count * per_sm);
+        DCUDA(ctx, cudaMemsetAsync(ex->csum, 0, (size_t)NB * sizeof(double), s));
+        kern<<<g3, threads, smem, s>>>(dd->d_data, (int)dd->N, dd->T, dd->t_halo, ex->phi, (int)L, PW, R, RS, dd->d_conv, ex->csum);
+        NHP_LAUNCHED(ctx);
+        DCUDA(ctx, cudaGetLastError());
+        NHP_TRY(nhp_timer_end(ctx));
+        goto exported;
+    }
     if (B <= 8) {
         int g2 = (int)std::min<int64_t>((dd->T * dd->N + 255) / 256, (int64_t)ctx->sm_count * 32);
         k_convolve_tp<8><<<g2, 256, (size_t)(L * B) * sizeof(double), s>>>(dd->d_data, (int)dd->N, dd->T, ex->phi, (int)L, (int)B, dd->d_conv);
@@ -316,6 +437,7 @@ extern "C" int nhp_disc_convolve(nhp_ctx *ctx, nhp_disc *dd, const double *phi, 
     NHP_LAUNCHED(ctx);
     DCUDA(ctx, cudaGetLastError());
     NHP_TRY(nhp_timer_end(ctx));
+exported:
     if (conv_out) {
         void *scratch;
         NHP_TRY(nhp_scratch(ctx, (size_t)dd->T * NB * sizeof(double), &scratch));

@@ -115,7 +115,7 @@ if __name__ == "__main__":
                                               nhp.BernoulliNetworkModel(0.1, N))
         ctx = proc._ctx()
         t0 = time.perf_counter(); d = proc.upload(data); print(f"upload {1e3*(time.perf_counter()-t0):.0f} ms, events {int(data.sum())}, nonzero bins {int((data>0).sum())}", flush=True)
-        for rep in range(2):
+        for rep in range(4):
             D.convolve(proc, d, export=False); print(f"convolve kernel {ctx.last_kernel_ms:.2f} ms ({(4*N*T + 8*T*N*B)/ctx.last_kernel_ms/1e6:.0f} GB/s)", flush=True)
         for rep in range(3):
             ll = D.loglikelihood(proc, d); ms = ctx.last_kernel_ms
