@@ -271,7 +271,10 @@ __global__ void __launch_bounds__(256) k_convolve_tp(const int *__restrict__ dat
 //        8*B-byte stride).
 // PW = N rounded up to whole warps, R = row groups per CTA (blockDim = PW * R); CONV_TT = rows per segment; RS = ring slots (power of 2).
 constexpr int CONV_TT = 128;
-template <int B>
+template <typename M> __device__ __forceinline__ int conv_ffs(M m);
+template <> __device__ __forceinline__ int conv_ffs<unsigned>(unsigned m) { return __ffs((int)m); }
+template <> __device__ __forceinline__ int conv_ffs<unsigned long long>(unsigned long long m) { return __ffsll((long long)m); }
+template <int B, typename M>  // M: the lag mask, 32 bits when L <= 32
 __global__ void __launch_bounds__(256, 4) k_convolve_rows(const int *__restrict__ data, int N, int64_t T, int64_t t_own, const double *__restrict__ phi, int L,
                                                           int PW, int R, int RS, double *__restrict__ convT, double *__restrict__ csum) {
     constexpr int PITCH = (B & 1) ? B : B + 1;
@@ -288,7 +291,7 @@ __global__ void __launch_bounds__(256, 4) k_convolve_rows(const int *__restrict_
     const int nq = max(0, min(32, N - p0)) * B;               // doubles this warp writes per row
     const int NB = N * B;
     const bool live = p < N;
-    const unsigned long long lmask = L >= 64 ? ~0ull : ((1ull << L) - 1ull);
+    const M lmask = L >= (int)(8 * sizeof(M)) ? ~(M)0 : (M)(((M)1 << L) - (M)1);
     int rd[B];  // staged position of the m-th double this lane stores: element q = lane + 32 m sits at (q / B) * PITCH + q % B
 #pragma unroll
     for (int m = 0; m < B; m++) { const int q = lane + 32 * m; rd[m] = (q / B) * PITCH + q % B; }
@@ -299,14 +302,14 @@ __global__ void __launch_bounds__(256, 4) k_convolve_rows(const int *__restrict_
     for (int64_t seg = (int64_t)blockIdx.x * R + r; seg < nseg; seg += (int64_t)gridDim.x * R) {
         const int64_t tb = seg * CONV_TT;
         const int nt = (int)min((int64_t)CONV_TT, T - tb);
-        unsigned long long nz = 0ull;  // bit l - 1: data[t - l][p] != 0
+        M nz = 0;  // bit l - 1: data[t - l][p] != 0
         const int *col = data + tb * N + (live ? p : 0);
         if (live) {
             const int lmax = (int)min((int64_t)L, tb);
             for (int l = 1; l <= lmax; l++) {
                 const int v = __ldg(col - l * N);
                 ring[((int)(tb & rmask) - l & rmask) * bd] = v;
-                nz |= (unsigned long long)(v != 0) << (l - 1);
+                nz |= (M)(v != 0) << (l - 1);
             }
         }
         int slot = (int)(tb & rmask);  // ring slot of row t
@@ -316,8 +319,8 @@ __global__ void __launch_bounds__(256, 4) k_convolve_rows(const int *__restrict_
 #pragma unroll
             for (int b = 0; b < B; b++) acc[b] = 0.0;
             const int cur = live ? __ldg(col) : 0;  // enters the window of row t + 1
-            for (unsigned long long m = nz; m;) {
-                const int l1 = __ffsll((long long)m) - 1;  // lag - 1
+            for (M m = nz; m;) {
+                const int l1 = conv_ffs<M>(m) - 1;  // lag - 1
                 m &= m - 1;
                 const double dv = (double)ring[((slot - 1 - l1) & rmask) * bd];
                 const double *ph = s_phi + l1;
@@ -325,11 +328,11 @@ __global__ void __launch_bounds__(256, 4) k_convolve_rows(const int *__restrict_
                 for (int b = 0; b < B; b++) acc[b] += ph[L * b] * dv;
             }
             ring[slot * bd] = cur;
-            nz = ((nz << 1) | (unsigned long long)(cur != 0)) & lmask;
+            nz = ((nz << 1) | (M)(cur != 0)) & lmask;
             const double ownf = tb + it >= t_own ? 1.0 : 0.0;
 #pragma unroll
             for (int b = 0; b < B; b++) {
-                const double v = fmax(acc[b], 0.0);
+                const double v = __double2hiint(acc[b]) < 0 ? 0.0 : acc[b];  // max(0, .): negative sums (a basis with negative lobes) clamp to zero
                 stg[lane * PITCH + b] = v;
                 cs[b] = fma(ownf, v, cs[b]);
             }
@@ -352,12 +355,13 @@ __global__ void __launch_bounds__(256, 4) k_convolve_rows(const int *__restrict_
     }
 }
 typedef void (*conv_rows_fn)(const int *, int, int64_t, int64_t, const double *, int, int, int, int, double *, double *);
-static conv_rows_fn conv_rows_kernel(int B) {
+template <typename M> static conv_rows_fn conv_rows_kernel_m(int B) {
     switch (B) {
-        case 1: return k_convolve_rows<1>; case 2: return k_convolve_rows<2>; case 3: return k_convolve_rows<3>; case 4: return k_convolve_rows<4>;
-        case 5: return k_convolve_rows<5>; case 6: return k_convolve_rows<6>; case 7: return k_convolve_rows<7>; default: return k_convolve_rows<8>;
+        case 1: return k_convolve_rows<1, M>; case 2: return k_convolve_rows<2, M>; case 3: return k_convolve_rows<3, M>; case 4: return k_convolve_rows<4, M>;
+        case 5: return k_convolve_rows<5, M>; case 6: return k_convolve_rows<6, M>; case 7: return k_convolve_rows<7, M>; default: return k_convolve_rows<8, M>;
     }
 }
+static conv_rows_fn conv_rows_kernel(int B, int L) { return L <= 32 ? conv_rows_kernel_m<unsigned>(B) : conv_rows_kernel_m<unsigned long long>(B); }
 
 // Julia layout export: out[t + T*(n + N*b)] = convT[t][n*B + b]   (tiled transpose)
 __global__ void k_conv_export(const double *__restrict__ convT, int N, int B, int64_t T, double *__restrict__ out) {
@@ -412,7 +416,7 @@ extern "C" int nhp_disc_convolve(nhp_ctx *ctx, nhp_disc *dd, const double *phi, 
         while (RS < L) RS <<= 1;
         const int pitch = (B & 1) ? (int)B : (int)B + 1;
         const size_t smem = ((size_t)(L * B) + (size_t)(threads / 32) * 32 * pitch) * sizeof(double) + (size_t)RS * threads * sizeof(int);
-        conv_rows_fn kern = conv_rows_kernel((int)B);
+        conv_rows_fn kern = conv_rows_kernel((int)B, (int)L);
         DCUDA(ctx, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)std::max<size_t>(smem, 1024)));
         int per_sm = 1;
         DCUDA(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, threads, smem));

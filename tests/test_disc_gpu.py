@@ -46,6 +46,20 @@ def test_convolve_intensity_loglik(N, T, B, L, network):
     assert D.loglikelihood(proc, d) == pytest.approx(om.loglik(data, oconv), rel=1e-10)
 
 
+@pytest.mark.parametrize("N,T,B,L", [(33, 700, 5, 40), (64, 300, 7, 32), (9, 1000, 8, 33), (1, 130, 1, 1), (300, 260, 3, 5), (200, 129, 6, 64)])
+def test_convolve_row_kernel_shapes(N, T, B, L):
+    """Shapes around the limits of the row-segment convolve kernel (k_convolve_rows): 64-bit lag masks (L > 32), partial warps, several
+    row groups per CTA (small N), segment boundaries (T just above a multiple of 128), N > 256 (thread-per-(t, p) kernel); the basis is
+    the reference's (discrete.jl:171-180 through the oracle); max(0, .) and the lags-ascending sum give the oracle's digits."""
+    proc, om, data = make(N, T, B, L, 40 + N, False, rate=0.3)
+    d = proc.upload(data)
+    conv = D.convolve(proc, d)
+    oconv = orc.disc_convolve(data, orc.disc_basis(L, B))
+    np.testing.assert_allclose(conv, oconv, rtol=1e-13, atol=1e-300)
+    # the fused column sums feed the compensator of the log-likelihood
+    assert D.loglikelihood(proc, d) == pytest.approx(om.loglik(data, oconv), rel=1e-10)
+
+
 @pytest.mark.parametrize("warp", ["1", "0"])
 @pytest.mark.parametrize("N,T,B,L,network", [(3, 400, 3, 4, False), (12, 1500, 4, 6, True), (70, 800, 6, 12, False), (200, 1500, 6, 12, True)])
 def test_gibbs_counts_match_given_uniforms(N, T, B, L, network, warp, monkeypatch):
