@@ -667,8 +667,8 @@ __global__ void __launch_bounds__(256) k_disc_dmma(const double *__restrict__ co
                                                    double dt, int N, int NB, int64_t T, int64_t t_first, const int *__restrict__ data,
                                                    double *__restrict__ lam_out, double *__restrict__ partials) {
     constexpr int BN = 8 * NT, LDB = BN + 4;
-    __shared__ double As[DBM * DLDA];
-    __shared__ double Bs[DBK * LDB];
+    extern __shared__ double s_dm[];  // two stages: A tiles [2][DBM * DLDA] | B tiles [2][DBK * LDB]
+    double *const As0 = s_dm, *const Bs0 = s_dm + 2 * DBM * DLDA;
     __shared__ double red[8];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int g = lane >> 2, q = lane & 3;
@@ -702,7 +702,8 @@ __global__ void __launch_bounds__(256) k_disc_dmma(const double *__restrict__ co
             vb[u] = (e < DBK * BN && k0 + kk < NB && c0 + cc < N) ? __ldg(bumpM + (int64_t)(k0 + kk) * N + c0 + cc) : 0.0;
         }
     };
-    auto stash = [&]() {
+    auto stash = [&](int stage) {
+        double *As = As0 + stage * (DBM * DLDA), *Bs = Bs0 + stage * (DBK * LDB);
 #pragma unroll
         for (int j = 0; j < 8; j++) As[ar * DLDA + ah * 8 + j] = va[j];
 #pragma unroll
@@ -711,11 +712,16 @@ __global__ void __launch_bounds__(256) k_disc_dmma(const double *__restrict__ co
             if (e < DBK * BN) { const int kk = e / BN, cc = e - kk * BN; Bs[kk * LDB + cc] = vb[u]; }
         }
     };
+    // two shared-memory stages, ONE barrier per k-slab: while the tensor cores work on stage s the next slab (already in registers)
+    // goes to stage s ^ 1, which every warp finished reading before the previous barrier
     fetch(0);
-    for (int k0 = 0; k0 < NB; k0 += DBK) {
-        stash();
-        __syncthreads();
-        if (k0 + DBK < NB) fetch(k0 + DBK);
+    stash(0);
+    __syncthreads();
+    int stage = 0;
+    for (int k0 = 0; k0 < NB; k0 += DBK, stage ^= 1) {
+        const bool more = k0 + DBK < NB;
+        if (more) fetch(k0 + DBK);
+        const double *As = As0 + stage * (DBM * DLDA), *Bs = Bs0 + stage * (DBK * LDB);
 #pragma unroll
         for (int ks = 0; ks < DBK / 4; ks++) {
             double a[2], b[NT];
@@ -728,6 +734,7 @@ __global__ void __launch_bounds__(256) k_disc_dmma(const double *__restrict__ co
 #pragma unroll
                 for (int n = 0; n < NT; n++) dmma_8x8x4(acc[m][n][0], acc[m][n][1], a[m], b[n]);
         }
+        if (more) stash(stage ^ 1);
         __syncthreads();
     }
     double part = 0.0;
@@ -742,8 +749,15 @@ __global__ void __launch_bounds__(256) k_disc_dmma(const double *__restrict__ co
                 if (t < T && c < N) {
                     const double lam = lambda0[c] * dt + acc[m][n][j];
                     if (LOGLIK) {
+                        // log pdf(Poisson(lam), s) = xlogy(s, lam) - lam - loggamma(s + 1)   (discrete.jl:98); most bins are empty: the
+                        // logarithm is taken for s > 0 only and loggamma (0 for s = 0, 1) for s > 1 only
                         const int sct = data[t * N + c];
-                        part += (sct ? (double)sct * log(lam) : 0.0) - lam - lgamma((double)sct + 1.0);
+                        double term = -lam;
+                        if (sct > 0) {
+                            term += (double)sct * log(lam);
+                            if (sct > 1) term -= lgamma((double)sct + 1.0);
+                        }
+                        part += term;
                     } else lam_out[t + T * (int64_t)c] = lam;
                 }
             }
@@ -777,8 +791,10 @@ static void launch_dmma(nhp_ctx *ctx, nhp_disc *dd, int64_t t_first, int64_t row
     const int nt = pick_nt(N);
     dim3 grid((unsigned)((N + 8 * nt - 1) / (8 * nt)), (unsigned)((rows + DBM - 1) / DBM));
     *grid_out = grid;
-#define NHP_DMMA_CASE(NTV) case NTV: k_disc_dmma<NTV, LOGLIK><<<grid, 256, 0, ctx->stream>>>(dd->d_conv, ctx->dd_bump, ctx->dd_lambda0, ctx->ddt, (int)N, (int)NB, dd->T, t_first, dd->d_data, lam_out, partials); break;
-    switch (nt) { NHP_DMMA_CASE(4) NHP_DMMA_CASE(5) default: k_disc_dmma<6, LOGLIK><<<grid, 256, 0, ctx->stream>>>(dd->d_conv, ctx->dd_bump, ctx->dd_lambda0, ctx->ddt, (int)N, (int)NB, dd->T, t_first, dd->d_data, lam_out, partials); break; }
+#define NHP_DMMA_CASE(NTV) { constexpr size_t smem = (size_t)(2 * DBM * DLDA + 2 * DBK * (8 * NTV + 4)) * sizeof(double); \
+        cudaFuncSetAttribute(k_disc_dmma<NTV, LOGLIK>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); \
+        k_disc_dmma<NTV, LOGLIK><<<grid, 256, smem, ctx->stream>>>(dd->d_conv, ctx->dd_bump, ctx->dd_lambda0, ctx->ddt, (int)N, (int)NB, dd->T, t_first, dd->d_data, lam_out, partials); }
+    switch (nt) { case 4: NHP_DMMA_CASE(4) break; case 5: NHP_DMMA_CASE(5) break; default: NHP_DMMA_CASE(6) break; }
 #undef NHP_DMMA_CASE
     NHP_LAUNCHED(ctx);
 }
