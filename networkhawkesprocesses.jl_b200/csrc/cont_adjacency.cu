@@ -492,6 +492,8 @@ struct AdjSweepArgs {
     int col_begin, col_stride, ncols;
     const int *corder;     // [ncols] owned columns, most child events first (NULL: col_begin + i col_stride)
     int s0, lmax;   // first batch size; log2 of the largest
+    int bo_smem;    // 1: the bucket offsets of the resident chunk are kept in shared memory behind the adjacency bits ((2 K + 1) ints)
+    int cert;       // 1: one-sided certification bounds (default); 0: the symmetric bound with the lambda0 / 2 cut (NHP_ADJ_CERT=0)
 };
 
 // thread-block cluster primitives (distributed shared memory of the CTAs that share a column)
@@ -783,12 +785,20 @@ template <int KIND, int PRE, bool CL> __global__ void __launch_bounds__(ADJ_THRE
             const unsigned m = __ballot_sync(0xffffffffu, p < K && Acol[p] != 0.0);
             if (lane == 0) s_ab[w] = m;
         }
+        // bucket offsets of the resident chunk: every phase starts from them (a slot's section bounds, a flip's bucket, the prefetch
+        // targets), and the stream of pair records leaves nothing of this array in L2 -- from shared memory when there is room
+        const int *bo_res = a.boff + (int64_t)(v0 + g_lo) * brow;
+        if (a.bo_smem && resident) {
+            int *s_bo = reinterpret_cast<int *>(s_ab + ((abw + 3) & ~3));
+            for (int e = tid; e < brow; e += ADJ_THREADS) s_bo[e] = __ldg(bo_res + e);
+            bo_res = s_bo;  // visible behind the barrier that follows the intensities' initialisation
+        }
         // ---- current intensities: lambda0 + the links that are on
         for (int g = g_lo; g < g_hi; g++) {
             const int len = max(0, min(csz, ne - g * csz));
             for (int e = tid; e < len; e += ADJ_THREADS) lam_s[e] = lam0;
             __syncthreads();
-            const int *bo = a.boff + (int64_t)(v0 + g) * brow;
+            const int *bo = resident ? bo_res : a.boff + (int64_t)(v0 + g) * brow;
             const int64_t vb = a.vbase[v0 + g];
             const unsigned short *ei = a.ent_i + vb;
             const double *ex = a.ent_x + (PRE ? 2 : 1) * vb;
@@ -812,6 +822,7 @@ template <int KIND, int PRE, bool CL> __global__ void __launch_bounds__(ADJ_THRE
                             const int pp = r == 0 ? pn : pa;
                             const int f0 = bo[2 * pp], f1 = bo[2 * pp + 2];
                             adj_pf_range<PRE>(ei, ex, f0, f1, tid);
+                            if (tid == ADJ_THREADS - 1) asm volatile("prefetch.global.L2 [%0];" ::"l"(col + pp));  // and its table entry
                         }
                     }
                     const int p = s_on[j];
@@ -848,7 +859,7 @@ template <int KIND, int PRE, bool CL> __global__ void __launch_bounds__(ADJ_THRE
             if (S <= 4 && resident) {
                 // short batches are latency bound: pull the entries of the buckets that can come next (they follow in memory) into L2 now
                 const int g = g_lo;
-                const int *bo = a.boff + (int64_t)(v0 + g) * brow;
+                const int *bo = bo_res;
                 const int q0 = min(p + Sc, K), q1 = min(p + Sc + 2 * S + 2, K);
                 const int64_t vb = a.vbase[v0 + g];
                 const int f0 = bo[2 * q0], f1 = bo[2 * q1];
@@ -865,7 +876,7 @@ template <int KIND, int PRE, bool CL> __global__ void __launch_bounds__(ADJ_THRE
                     for (int e = tid; e < len; e += ADJ_THREADS) lam_s[e] = __ldcg(lamg + (size_t)g * csz + e);  // written by this CTA: read through L2
                     __syncthreads();
                 }
-                const int *bo = a.boff + (int64_t)(v0 + g) * brow;
+                const int *bo = resident ? bo_res : a.boff + (int64_t)(v0 + g) * brow;
                 const int64_t vb = a.vbase[v0 + g];
                 const unsigned short *ei = a.ent_i + vb;
                 const double *ex = a.ent_x + (PRE ? 2 : 1) * vb;
@@ -882,6 +893,7 @@ template <int KIND, int PRE, bool CL> __global__ void __launch_bounds__(ADJ_THRE
                         if (q + Sc < K) {  // the bucket this slot takes if the whole batch is accepted: its first blocks go to L2 now
                             const int nb = bo[2 * (q + Sc)] + sub * 64;
                             adj_pf(pf, nb); adj_pf(pf, nb + nsub * 64);
+                            if (lane == 31) asm volatile("prefetch.global.L2 [%0];" ::"l"(col + q + Sc));  // and its table entry
                         }
                         AdjAcc A;
                         acc_init(A);
@@ -903,8 +915,11 @@ template <int KIND, int PRE, bool CL> __global__ void __launch_bounds__(ADJ_THRE
 #pragma unroll
             for (int r = 0; r < NR; r++) {
                 acc[r] = warp_sum(acc[r]);
-#pragma unroll
-                for (int d = 16; d >= 1; d >>= 1) gmx[r] = fmax(gmx[r], __shfl_xor_sync(0xffffffffu, gmx[r], d));
+                {   // largest contribution of the warp: the values are >= 0 and only serve as upper bounds, so the maximum is taken over the
+                    // high words (rounded up): one integer warp reduction instead of a butterfly of FP64 maxima
+                    const int hw = __double2hiint(gmx[r]) + (__double2loint(gmx[r]) != 0 ? 1 : 0);
+                    gmx[r] = __hiloint2double(__reduce_max_sync(0xffffffffu, hw), 0);
+                }
             }
             // One barrier per batch.  With one slot per bucket (S = 32) the warp sends its sums straight to every CTA of the cluster; the
             // buffers alternate with the batch parity (a CTA or warp that runs ahead writes the other half).
@@ -959,29 +974,55 @@ template <int KIND, int PRE, bool CL> __global__ void __launch_bounds__(ADJ_THRE
                 if (have && delta != delta) atomicOr(a.flag, 64);
                 const unsigned flipmask = __ballot_sync(0xffffffffu, have && new_on != old_on);
                 // Certified speculation.  The sums of this batch were taken with the intensities as they stood at its start.  A flip of
-                // bucket j moves every intensity by at most gmax_j, and a term log((b + g) / b) of a later bucket moves by at most
-                // 4 term dlam / lambda0 while dlam <= lambda0 / 2 (d term / d b = -(g / (b + g)) / b, g / (b + g) <= term, b >= lambda0; the
-                // factor 4 covers a decreasing b), so a later sum S moves by at most 4 S cum / lambda0, cum = the gmax of the flips so far.
-                // A decision whose margin |delta - logit(u)| exceeds that bound (plus rounding slack) is the decision the sequential sweep
-                // takes; the batch is accepted up to the first bucket that cannot be certified, and restarts there.
-                // cum = exclusive prefix sum over the flips (warp scan: the same values in every CTA of the cluster); a flip whose change is
-                // too large to bound (> lambda0 / 2) ends the batch behind itself.
+                // bucket j moves the intensity of every event by at most gmax_j: up when the link goes on, down when it goes off.  A term
+                // of a later bucket is f(b) = log(1 + g / b) with b >= lambda0 its intensity without that bucket's parent, and for r >= 1
+                // log(1 + r x) <= r log(1 + x) (Bernoulli), so with b' the intensity after the flips
+                //   b' <  b:  f(b') <= (b / b') f(b) <= (1 + off / lambda0) f(b),      off = sum of gmax over the accepted flips that went off
+                //   b' >= b:  f(b') >= (b / b') f(b) >= f(b) / (1 + on / lambda0),     on  = ... that went on
+                // for ANY size of the change.  The later sum S (>= 0) therefore ends up in [S / (1 + on / lambda0), S (1 + off / lambda0)]:
+                // a decision "off" (delta < logit u) can only be overturned by the upper end, a decision "on" only by the lower end.
+                // A decision whose margin |delta - logit(u)| exceeds its side's bound (plus rounding slack) is the decision the sequential
+                // sweep takes; the batch is accepted up to the first bucket that cannot be certified, and restarts there.
+                // on / off = exclusive prefix sums over the flips (warp scan: the same values in every CTA of the cluster).
                 const bool flip = (flipmask >> lane) & 1u;
-                double inc = flip ? gmax : 0.0;
+                int stop_;
+                if (a.cert) {
+                    double inc_on = (flip && new_on) ? gmax : 0.0, inc_off = (flip && !new_on) ? gmax : 0.0;
 #pragma unroll
-                for (int d = 1; d < 32; d <<= 1) {
-                    const double t = __shfl_up_sync(0xffffffffu, inc, d);
-                    if (lane >= d) inc += t;
+                    for (int d = 1; d < 32; d <<= 1) {
+                        const double t1 = __shfl_up_sync(0xffffffffu, inc_on, d), t0 = __shfl_up_sync(0xffffffffu, inc_off, d);
+                        if (lane >= d) { inc_on += t1; inc_off += t0; }
+                    }
+                    double cum_on = __shfl_up_sync(0xffffffffu, inc_on, 1), cum_off = __shfl_up_sync(0xffffffffu, inc_off, 1);
+                    if (lane == 0) { cum_on = 0.0; cum_off = 0.0; }
+                    const double slack = 1e-7 + 1e-10 * fabs(delta);
+                    const double S_ = fabs(sum);
+                    // (1.0000001: the scan's own rounding, so that the bound stays an upper bound)
+                    const double shift = new_on ? S_ * (cum_on / (lam0 + cum_on)) : S_ * (cum_off / lam0);
+                    const bool uncertified = have && (cum_on > 0.0 || cum_off > 0.0) && !(margin > 1.0000001 * shift + slack);
+                    const unsigned um = __ballot_sync(0xffffffffu, uncertified);
+                    stop_ = Sc;
+                    if (um) stop_ = min(stop_, __ffs(um) - 1);
+                } else {
+                    // (the first version: symmetric bound 4 S cum / lambda0 from the derivative, valid while cum <= lambda0 / 2; a flip whose
+                    // change is larger ends the batch behind itself)
+                    double inc = flip ? gmax : 0.0;
+#pragma unroll
+                    for (int d = 1; d < 32; d <<= 1) {
+                        const double t = __shfl_up_sync(0xffffffffu, inc, d);
+                        if (lane >= d) inc += t;
+                    }
+                    double cum = __shfl_up_sync(0xffffffffu, inc, 1);
+                    if (lane == 0) cum = 0.0;
+                    const double slack = 1e-7 + 1e-10 * fabs(delta);
+                    const bool uncertified = have && cum > 0.0 && !(margin > fabs(sum) * cum * (4.0 / lam0) + slack);
+                    const bool toobig = flip && !(gmax <= 0.5 * lam0);
+                    const unsigned um = __ballot_sync(0xffffffffu, uncertified), bm = __ballot_sync(0xffffffffu, toobig);
+                    stop_ = Sc;
+                    if (um) stop_ = min(stop_, __ffs(um) - 1);
+                    if (bm) stop_ = min(stop_, __ffs(bm));
                 }
-                double cum = __shfl_up_sync(0xffffffffu, inc, 1);
-                if (lane == 0) cum = 0.0;
-                const double slack = 1e-7 + 1e-10 * fabs(delta);
-                const bool uncertified = have && cum > 0.0 && !(margin > fabs(sum) * cum * (4.0 / lam0) + slack);
-                const bool toobig = flip && !(gmax <= 0.5 * lam0);
-                const unsigned um = __ballot_sync(0xffffffffu, uncertified), bm = __ballot_sync(0xffffffffu, toobig);
-                stop = Sc;
-                if (um) stop = min(stop, __ffs(um) - 1);
-                if (bm) stop = min(stop, __ffs(bm));
+                stop = stop_;
                 fm = stop >= 32 ? flipmask : (flipmask & ((1u << stop) - 1u));
                 onm = __ballot_sync(0xffffffffu, new_on);
                 // warp 0 records the accepted flips; the others see the new bits behind the barrier of the first flip's application
@@ -994,7 +1035,7 @@ template <int KIND, int PRE, bool CL> __global__ void __launch_bounds__(ADJ_THRE
             n_batches++;
             n_steps += stop; n_flips += __popc(fm); n_redo += Sc - stop;
             if (resident && (fm & (fm - 1))) {  // several flips: all their buckets start towards L2 now, the first one's latency covers the others
-                const int *bo = a.boff + (int64_t)(v0 + g_lo) * brow;
+                const int *bo = bo_res;
                 const int64_t vb = a.vbase[v0 + g_lo];
                 for (unsigned f2 = fm & (fm - 1); f2; f2 &= f2 - 1) {
                     const int qf = p + __ffs(f2) - 1;
@@ -1010,7 +1051,7 @@ template <int KIND, int PRE, bool CL> __global__ void __launch_bounds__(ADJ_THRE
                 const double sgn = ((onm >> j) & 1u) ? 1.0 : -1.0;
                 const E enf = load_entry(col + qf);
                 for (int g = g_lo; g < g_hi; g++) {
-                    const int *bo = a.boff + (int64_t)(v0 + g) * brow;
+                    const int *bo = resident ? bo_res : a.boff + (int64_t)(v0 + g) * brow;
                     const int b0 = bo[2 * qf], bm = bo[2 * qf + 1], b1 = bo[2 * qf + 2];
                     const int64_t vb = a.vbase[v0 + g];
                     const unsigned short *ei = a.ent_i + vb;
@@ -1534,9 +1575,17 @@ static int adj_run(nhp_ctx *ctx, nhp_events *ev, const double *d_rho, double rho
         w.s0 = ADJ_SMAX;
         { const char *e = getenv("NHP_ADJ_S0"); if (e && atoi(e) >= 1 && atoi(e) <= 32 && (atoi(e) & (atoi(e) - 1)) == 0) w.s0 = atoi(e); }
         w.lmax = 5;
+        w.cert = 1;
+        { const char *e = getenv("NHP_ADJ_CERT"); if (e) w.cert = atoi(e) != 0; }
         { const char *e = getenv("NHP_ADJ_LMAX"); if (e && atoi(e) >= 0 && atoi(e) <= 5) w.lmax = atoi(e); }
         if (w.s0 > (1 << w.lmax)) w.s0 = 1 << w.lmax;
-        const size_t smem = (size_t)w.chunk_max * sizeof(double) + (size_t)((K + 31) / 32) * sizeof(unsigned) + 16;
+        size_t smem = (size_t)w.chunk_max * sizeof(double) + (size_t)((K + 31) / 32) * sizeof(unsigned) + 16;
+        {   // room for the resident chunk's bucket offsets?  (the kernel's static shared memory: 12.1 KB, see -Xptxas -v)
+            const size_t bo_bytes = (size_t)(((K + 31) / 32 + 3) & ~3) * sizeof(unsigned) - (size_t)((K + 31) / 32) * sizeof(unsigned) + (size_t)(2 * K + 1) * sizeof(int);
+            const char *e = getenv("NHP_ADJ_BO_SMEM");
+            w.bo_smem = !(e && atoi(e) == 0) && smem + bo_bytes + 12800 <= (size_t)ctx->smem_optin;
+            if (w.bo_smem) smem += bo_bytes;
+        }
         NHP_CHECK(ctx, smem <= (size_t)ctx->smem_optin - 4096, NHP_ERR_UNSUPPORTED, "adjacency sampler: K=%lld needs more shared memory than the device has", (long long)K);
         NHP_CUDA(ctx, cudaMemsetAsync(ctx->d_adj_ctl, 0, 8 * sizeof(int), s));
         NHP_CUDA(ctx, cudaMemsetAsync(ctx->d_adj_stat, 0, 8 * sizeof(unsigned long long), s));
