@@ -189,6 +189,7 @@ constexpr int ADJ_CHUNK_MAX = 26624;   // child events per chunk: 208 KB of shar
 constexpr int ADJ_THREADS = 1024;      // sweep CTA: one per SM (512 threads with 128 registers each measured 8 % slower: 45.3 vs 41.9 ms)
 constexpr int ADJ_VW = 32;             // bucket slots of a batch: one per warp (a CTA with fewer warps takes several slots per warp, one after the other)
 constexpr int ADJ_SMAX = 32;           // largest speculative batch (buckets per batch); the size follows the observed flip rate, down to 1
+constexpr int ADJ_INIT_PF = 8;       // links ahead whose buckets are prefetched to L2 while a column's intensities are built up
 constexpr int ADJ_CLUSTER_MAX = 8;     // portable cluster size limit
 
 // a column's ne child events are split into G chunks of this many events (the last one may be shorter)
@@ -704,25 +705,50 @@ __device__ __noinline__ double2 adj_direct(const typename EntryOf<KIND>::type en
     return make_double2(acc, gmx);
 }
 
-// add sgn * (this parent's contribution) to the intensities of a bucket's events: all warps of the CTA, groups warp, warp + 32, ...
+// add sgn * (this parent's contribution) to the intensities of a bucket's events: all warps of the CTA.  A bucket holds about one entry
+// per thread, so the call is a chain of latencies rather than a stream: the loads of the thread's first single and of the warp's first
+// run group (and the look-ahead word of that group) are all issued before the first of them is used, and the run groups go to the warps
+// from the last one down (the first warps are the ones that get a second single).
 template <int KIND, int PRE>
 __device__ __forceinline__ void adj_apply(const typename EntryOf<KIND>::type &en, const unsigned short *__restrict__ ei, const double *__restrict__ ex,
                                           const int s0, const int sm, const int rs, const int s1, const int warp, const int lane,
                                           const double sgn, double *lam, const double D, const FastTables *ft) {  // singles [s0, sm), run groups from rs (a group boundary) to s1
-    for (int k = s0 + warp * 32 + lane; k < sm; k += ADJ_THREADS) {  // singles: distinct events, no bookkeeping
+    const double xdef = PRE ? 0.0 : -1.0;
+    int k = s0 + warp * 32 + lane;
+    const bool hs = k < sm;
+    unsigned iis = 0u;
+    double xs = xdef, ys = 0.0;
+    if (hs) { iis = __ldg(ei + k); adj_ld<PRE>(ex, k, xs, ys); }
+    int eb = rs + (ADJ_THREADS / 32 - 1 - warp) * 32;
+    const bool hr = eb < s1;  // warp-uniform
+    unsigned iir = 0u;
+    double xr = xdef, yr = 0.0;
+    int nf = -1;
+    if (hr) {
+        if (eb + lane < s1) { iir = __ldg(ei + eb + lane); adj_ld<PRE>(ex, eb + lane, xr, yr); }
+        if (eb + 32 < s1) nf = (int)__ldg(ei + eb + 32);
+    }
+    if (hs) {  // singles: distinct events, no bookkeeping
+        const double v = adj_value<KIND, PRE>(en, xs, ys, D, ft);
+        if (v > 0.0) lam[iis] += sgn * v;
+    }
+    for (k += ADJ_THREADS; k < sm; k += ADJ_THREADS) {
         const unsigned ii = __ldg(ei + k);
         double x, y;
         adj_ld<PRE>(ex, k, x, y);
         const double v = adj_value<KIND, PRE>(en, x, y, D, ft);
         if (v > 0.0) lam[ii] += sgn * v;
     }
-    for (int eb = rs + warp * 32; eb < s1; eb += ADJ_THREADS) {      // runs: the head carries the run's total
-        const bool valid = eb + lane < s1;
-        const unsigned ii = valid ? (unsigned)__ldg(ei + eb + lane) : 0u;
-        double x = PRE ? 0.0 : -1.0, y = 0.0;
-        if (valid) adj_ld<PRE>(ex, eb + lane, x, y);
+    if (hr) {  // runs: the head carries the run's total
         double gs;
-        if (adj_group<KIND, PRE>(en, ei, ex, eb, s1, lane, ii, x, y, D, ft, gs) && gs > 0.0) lam[ii & 0x7fffu] += sgn * gs;
+        if (adj_group<KIND, PRE>(en, ei, ex, eb, s1, lane, iir, xr, yr, D, ft, gs, nf) && gs > 0.0) lam[iir & 0x7fffu] += sgn * gs;
+        for (eb += ADJ_THREADS; eb < s1; eb += ADJ_THREADS) {
+            const bool valid = eb + lane < s1;
+            const unsigned ii = valid ? (unsigned)__ldg(ei + eb + lane) : 0u;
+            double x = xdef, y = 0.0;
+            if (valid) adj_ld<PRE>(ex, eb + lane, x, y);
+            if (adj_group<KIND, PRE>(en, ei, ex, eb, s1, lane, ii, x, y, D, ft, gs) && gs > 0.0) lam[ii & 0x7fffu] += sgn * gs;
+        }
     }
 }
 
@@ -802,7 +828,7 @@ template <int KIND, int PRE, bool CL> __global__ void __launch_bounds__(ADJ_THRE
             const int64_t vb = a.vbase[v0 + g];
             const unsigned short *ei = a.ent_i + vb;
             const double *ex = a.ent_x + (PRE ? 2 : 1) * vb;
-            // the links that are on, listed (the exchange buffers are idle here) so that the bucket two links ahead can be pulled into L2
+            // the links that are on, listed (the exchange buffers are idle here) so that the buckets of the links ahead can be pulled into L2
             // (the half the peers do not write before the next cluster barrier: they fill [parity] at the end of their first batch)
             int *s_on = reinterpret_cast<int *>(&s_cl[parity ^ 1u][0][0]);
             constexpr int ON_CAP = (int)(sizeof(s_cl) / 2 / sizeof(int));
@@ -815,16 +841,12 @@ template <int KIND, int PRE, bool CL> __global__ void __launch_bounds__(ADJ_THRE
                     for (unsigned bits = s_ab[w0 + tid]; bits; bits &= bits - 1) s_on[o++] = (w0 + tid) * 32 + __ffs(bits) - 1;
                 }
                 __syncthreads();
+                // A link's step is short (a bucket holds about one entry per thread), so the buckets ADJ_INIT_PF links ahead are on their way
+                // to L2 -- two ahead would arrive behind their turn -- and the table entries of all listed links start at once
+                for (int j = tid; j < non; j += ADJ_THREADS) asm volatile("prefetch.global.L2 [%0];" ::"l"(col + s_on[j]));
+                for (int r = 1; r < min(ADJ_INIT_PF, non); r++) adj_pf_range<PRE>(ei, ex, bo[2 * s_on[r]], bo[2 * s_on[r] + 2], tid);
                 for (int j = 0; j < non; j++) {
-                    if (j + 2 < non || j == 0) {
-                        const int pn = s_on[min(j + 2, non - 1)], pa = j == 0 ? s_on[min(1, non - 1)] : pn;
-                        for (int r = 0; r < (j == 0 ? 2 : 1); r++) {
-                            const int pp = r == 0 ? pn : pa;
-                            const int f0 = bo[2 * pp], f1 = bo[2 * pp + 2];
-                            adj_pf_range<PRE>(ei, ex, f0, f1, tid);
-                            if (tid == ADJ_THREADS - 1) asm volatile("prefetch.global.L2 [%0];" ::"l"(col + pp));  // and its table entry
-                        }
-                    }
+                    if (j + ADJ_INIT_PF < non) { const int pp = s_on[j + ADJ_INIT_PF]; adj_pf_range<PRE>(ei, ex, bo[2 * pp], bo[2 * pp + 2], tid); }
                     const int p = s_on[j];
                     const int b0 = bo[2 * p], bm = bo[2 * p + 1], b1 = bo[2 * p + 2];
                     if (b1 != b0) {
@@ -1087,6 +1109,7 @@ struct AdjLoglikArgs {
     const int *node_ptr; int K; const void *table; const double *lambda0; const uint32_t *abits; int words; double D;
     const int *vstart, *vnode; const int64_t *vbase; const int *boff; const unsigned short *ent_i; const double *ent_x;
     int nv, chunk_max; double *partials; int *flag;
+    int cap;   // links whose section bounds are staged in shared memory per round (0: read from global memory)
 };
 template <int KIND, int PRE> __global__ void __launch_bounds__(ADJ_THREADS, 1) k_adj_loglik(const AdjLoglikArgs a) {
     typedef typename EntryOf<KIND>::type E;
@@ -1128,17 +1151,37 @@ template <int KIND, int PRE> __global__ void __launch_bounds__(ADJ_THREADS, 1) k
         const unsigned short *ei = a.ent_i + vb;
         const double *ex = a.ent_x + (PRE ? 2 : 1) * vb;
         const E *col = reinterpret_cast<const E *>(a.table) + (size_t)c * K;
-        // the active buckets one after the other, the two behind the current one on their way to L2
-        for (int j = 0; j < min(2, non); j++) adj_pf_range<PRE>(ei, ex, bo[2 * s_on[j]], bo[2 * s_on[j] + 2], tid);
-        for (int j = 0; j < non; j++) {
-            if (j + 2 < non) adj_pf_range<PRE>(ei, ex, bo[2 * s_on[j + 2]], bo[2 * s_on[j + 2] + 2], tid);
-            const int p = s_on[j];
-            const int b0 = bo[2 * p], bm = bo[2 * p + 1], b1 = bo[2 * p + 2];
-            if (b1 != b0) {
-                const E en = load_entry(col + p);
-                adj_apply<KIND, PRE>(en, ei, ex, b0, bm, bm, b1, warp, lane, 1.0, lam_s, a.D, ft);  // one head per event and bucket
+        // The active buckets one after the other.  A bucket holds about one entry per thread, so a link's step is a chain of dependent
+        // latencies: the section bounds of up to `cap` links are gathered into shared memory at once (the stream of pair records leaves
+        // nothing of the offsets array in L2), their table entries start towards L2 together, and the buckets ADJ_INIT_PF links ahead are
+        // prefetched (two ahead arrive behind their turn).
+        const int cap = a.cap > 0 ? a.cap : non;
+        int *s_b3 = s_on + K;  // [3 cap] when a.cap > 0
+        for (int j0 = 0; j0 < non; j0 += max(cap, 1)) {
+            const int nj = min(cap, non - j0);
+            for (int j = tid; j < nj; j += ADJ_THREADS) {
+                const int p = s_on[j0 + j];
+                if (a.cap > 0) { s_b3[3 * j] = __ldg(bo + 2 * p); s_b3[3 * j + 1] = __ldg(bo + 2 * p + 1); s_b3[3 * j + 2] = __ldg(bo + 2 * p + 2); }
+                asm volatile("prefetch.global.L2 [%0];" ::"l"(col + p));
             }
-            __syncthreads();  // the next parent may touch the same events
+            if (a.cap > 0) __syncthreads();
+            for (int r = 0; r < min(ADJ_INIT_PF, nj); r++) {
+                const int p = s_on[j0 + r];
+                adj_pf_range<PRE>(ei, ex, a.cap > 0 ? s_b3[3 * r] : bo[2 * p], a.cap > 0 ? s_b3[3 * r + 2] : bo[2 * p + 2], tid);
+            }
+            for (int j = 0; j < nj; j++) {
+                if (j + ADJ_INIT_PF < nj) {
+                    const int r = j + ADJ_INIT_PF, p = s_on[j0 + r];
+                    adj_pf_range<PRE>(ei, ex, a.cap > 0 ? s_b3[3 * r] : bo[2 * p], a.cap > 0 ? s_b3[3 * r + 2] : bo[2 * p + 2], tid);
+                }
+                const int p = s_on[j0 + j];
+                const int b0 = a.cap > 0 ? s_b3[3 * j] : bo[2 * p], bm = a.cap > 0 ? s_b3[3 * j + 1] : bo[2 * p + 1], b1 = a.cap > 0 ? s_b3[3 * j + 2] : bo[2 * p + 2];
+                if (b1 != b0) {
+                    const E en = load_entry(col + p);
+                    adj_apply<KIND, PRE>(en, ei, ex, b0, bm, bm, b1, warp, lane, 1.0, lam_s, a.D, ft);  // one head per event and bucket
+                }
+                __syncthreads();  // the next parent may touch the same events (and the next round rewrites the staged bounds)
+            }
         }
         double acc = 0.0;
         for (int e = tid; e < len; e += ADJ_THREADS) {
@@ -1170,8 +1213,12 @@ int nhp_cont_try_adj_loglik(nhp_ctx *ctx, nhp_events *ev, SweepArgs &sa, int *gr
     a.node_ptr = ev->d_node_ptr; a.K = (int)K; a.table = sa.table; a.lambda0 = sa.lambda0; a.abits = ctx->d_abits; a.words = (int)ctx->abits_words; a.D = ctx->dtmax;
     a.vstart = ev->d_adj_vstart; a.vnode = ev->d_adj_vnode; a.vbase = ev->d_adj_vbase; a.boff = ev->d_adj_boff; a.ent_i = ev->d_adj_i; a.ent_x = ev->d_adj_dt;
     a.nv = (int)ev->adj_nv; a.chunk_max = (ev->adj_chunk_max + 1) & ~1; a.partials = sa.partials; a.flag = sa.flag;
-    const size_t smem = (size_t)a.chunk_max * sizeof(double) + (size_t)K * sizeof(int) + 16;
+    size_t smem = (size_t)a.chunk_max * sizeof(double) + (size_t)K * sizeof(int) + 16;
     if (smem > (size_t)ctx->smem_optin - 4096) return 1;
+    a.cap = 256;  // 3 KB of staged section bounds when they fit next to the intensities
+    { const char *e = getenv("NHP_ADJ_LL_STAGE"); if (e && atoi(e) == 0) a.cap = 0; }
+    if (smem + 3 * (size_t)a.cap * sizeof(int) > (size_t)ctx->smem_optin - 4096) a.cap = 0;
+    smem += 3 * (size_t)a.cap * sizeof(int);
     NHP_CUDA(ctx, fast_tables_upload(ctx->stream));
     const int grid = (int)std::min<int64_t>(ev->adj_nv, ctx->sm_count);
     if (ctx->kind == NHP_EXPONENTIAL) {
