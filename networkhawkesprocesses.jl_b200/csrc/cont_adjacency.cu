@@ -664,18 +664,31 @@ template <int KIND, int PRE>
 __device__ __forceinline__ void adj_runs(const typename EntryOf<KIND>::type &en, const unsigned short *__restrict__ ei, const double *__restrict__ ex,
                                          int eb, const int b1, const int stride, const int lane, const double onf,
                                          const double floor_, const double D, const double *lam_s, const FastTables *ft, AdjAcc &A) {
+    // one group ahead in registers: the lane's entry of the next group and the index word behind it (the look-ahead of adj_group)
     const double xdef = PRE ? 0.0 : -1.0;
+    unsigned iw = 0u;
+    double xw = xdef, yw = 0.0;
+    int nfw = -1;
+    if (eb < b1) {
+        if (eb + lane < b1) { iw = (unsigned)__ldg(ei + eb + lane); adj_ld<PRE>(ex, eb + lane, xw, yw); }
+        if (eb + 32 < b1) nfw = (int)__ldg(ei + eb + 32);
+    }
     while (eb < b1) {
 #pragma unroll 1
         for (int u = 0; u < ADJ_RENORM; u++) {
-            const bool valid = eb + lane < b1;
-            const unsigned ii = valid ? (unsigned)__ldg(ei + eb + lane) : 0u;
-            double x = xdef, y = 0.0;
-            if (valid) adj_ld<PRE>(ex, eb + lane, x, y);
+            const unsigned ii = iw;
+            const double x = xw, y = yw;
+            const int nf = nfw;
+            const int en_ = eb + stride;
+            iw = 0u; xw = xdef; yw = 0.0; nfw = -1;
+            if (en_ < b1) {  // warp-uniform
+                if (en_ + lane < b1) { iw = (unsigned)__ldg(ei + en_ + lane); adj_ld<PRE>(ex, en_ + lane, xw, yw); }
+                if (en_ + 32 < b1) nfw = (int)__ldg(ei + en_ + 32);
+            }
             double gs;
-            const bool head = adj_group<KIND, PRE>(en, ei, ex, eb, b1, lane, ii, x, y, D, ft, gs);
+            const bool head = adj_group<KIND, PRE>(en, ei, ex, eb, b1, lane, ii, x, y, D, ft, gs, nf);
             acc_factor(A, head ? gs : 0.0, lam_s[ii & 0x7fffu], onf, floor_);
-            eb += stride;
+            eb = en_;
             if (eb >= b1) break;
         }
         acc_renorm(A);
