@@ -604,7 +604,7 @@ def run_ours(args, rank, world, local_rank):
                     "algorithmic_unit": "%.0f B per cached (child event, window predecessor) pair (u16 event index + %s) x %.4g pairs, streamed once per sweep"
                                         % (bpp, "f64 logit + f64 Jacobian of the lag" if bpp == 18.0 else "f64 lag", pairs),
                     "binding_resource": "HBM stream of the cached pairs plus instruction issue: one table-driven exp, one shared-memory intensity look-up and two "
-                                        "running products per pair (profiles/r02_ncu_adj_sweep.md); fp64_view compares with full LogitNormal pair evaluations",
+                                        "running products per pair (profiles/r02_ncu_step_kernels.md); fp64_view compares with full LogitNormal pair evaluations",
                     "fp64_view": {"bound": "fp64 impulse evaluations", "achieved": pairs / adj_s, "peak": peaks["ln_pairs_per_s"], "unit": "pairs/s",
                                   "frac": pairs / adj_s / peaks["ln_pairs_per_s"],
                                   "peak_source": "register-resident LogitNormal pair evaluations measured in this run (nhp_bench_fp64 which=1); FP64 FMA peak %.1f TFLOP/s" % peaks["fp64_fma_tflops"]},

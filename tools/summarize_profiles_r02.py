@@ -140,9 +140,18 @@ def main():
             "| SASS instructions | executions | stall samples | warp instructions | hottest instruction (share of samples) |", "|---|---:|---:|---:|---|"]
     for a, b, c, s, i, t, src in reg:
         note.append("| %d-%d | %d | %.1f %% | %.1f %% | `%s` (%.1f %%) |" % (a, b, c, s, i, src, t))
-    note += ["", "The region that executes once per 64-entry block of singles is the streaming loop (130 instructions per 64 pairs: one 32-bit + one 256-bit load, two table-driven",
-             "exps, two shared-memory intensity look-ups, product accumulation, three min/max trackers, an L2 prefetch); the regions with ~7e6 executions are the",
-             "per-batch phases (32 warps x 130 CTAs x batches); `UCGABAR_WAIT` is the cluster barrier that ends a batch (waiting for the slowest warp of the slowest CTA), the `BRA` behind `BAR.SYNC` the barrier of a flip's application."]
+    note += ["", "The region that executes once per 64-entry block of singles (~1e8 executions) is the streaming loop (140 instructions per 64 pairs: one 32-bit + one 256-bit load, two table-driven",
+             "exps, two shared-memory intensity look-ups, product accumulation, three min/max trackers, an L2 prefetch); the regions with ~5e6 executions are the",
+             "per-batch phases (32 warps x 130 CTAs x batches), those with ~8e6 the application of a link (a column's initial intensities, flips); `UCGABAR_WAIT` is the cluster barrier",
+             "that ends a batch (waiting for the slowest warp of the slowest CTA), the `BRA` behind `BAR.SYNC` the barrier of a link's application."]
+    obj = os.path.join(ROOT, "networkhawkesprocesses.jl_b200", "csrc", "build", "cont_adjacency.o")
+    if os.path.exists(obj):  # the same samples by line of the kernel body (valid when the object is the build the report was captured from)
+        r = subprocess.run([sys.executable, os.path.join(ROOT, "tools", "ncu_source_lines.py"), step_rep, obj, "_Z11k_adj_sweepILi1ELi1ELb1EEv12AdjSweepArgs", "0"],
+                           capture_output=True, text=True)
+        if r.returncode == 0:
+            note += ["", "The same samples by line of the kernel body (`python tools/ncu_source_lines.py`; `cont_adjacency.cu` as of the commit of this file: `adj_singles` /",
+                     "`adj_runs` calls = the streaming phase, `cluster_sync_all` = the batch's barrier, the `adj_apply` call in the column prologue = the links that are on,",
+                     "the `adj_apply` call behind the decisions = flips):", ""] + r.stdout.strip().split("\n")
     txt = table("r02 ncu full capture -- the three kernels of the bench step (N=1, cfg4, hawkes data): log-likelihood through the cached structure (`k_adj_loglik`), parent sweep (`k_sweep_sparse<1,2>`), adjacency sweep (`k_adj_sweep`)",
                 "`ncu --set full --clock-control none --import-source on --kernel-name regex:\"k_adj_sweep|k_sweep_sparse|k_adj_loglik\" --launch-skip 5 --launch-count 3` under "
                 "`python bench.py --steps 2 --warmup 1 --no-cpu-baseline`.", rows, "\n".join(note))
