@@ -21,9 +21,12 @@
 // and a flip never leaves the chip.  The K sequential Bernoulli steps run speculatively in batches of S <= 32 buckets: a
 // step only changes lambda when its link flips, so the S sums are evaluated in parallel (32/S warps per bucket) from the
 // current lambda, every CTA's partial sums travel through distributed shared memory to all CTAs of the cluster (one cluster
-// barrier per batch), each CTA then takes the same decisions in order, and the first flip (if any) is applied and the batch
-// restarts behind it (S halves after a flip -- down to 1, the plain sequential sweep, when a chain flips a third of its
-// links per sweep -- and doubles after a clean batch).  The result is exactly that of the sequential sweep.  The log terms are
+// barrier per batch), each CTA then takes the same decisions in order and accepts them as far as they can be CERTIFIED: a
+// flip moves every intensity by at most its bucket's largest contribution, which bounds a later sum S from both sides,
+// S / (1 + on / lambda0) <= S' <= S (1 + off / lambda0); a decision whose margin exceeds its side's bound is the decision of
+// the sequential sweep (see the decision block of k_adj_sweep).  The batch is cut at the first bucket that cannot be
+// certified and restarts there; the accepted flips are applied (S follows the observed restart rate, down to 1, the plain
+// sequential sweep).  The result is exactly that of the sequential sweep.  The log terms are
 // accumulated as a quotient of running products (one log per lane and batch instead of one per entry).
 // Columns too large for a cluster's shared memory keep lambda in global memory between batches and stream their chunks
 // per batch through one CTA.  Everything is order-deterministic: no atomics, fixed reduction trees.

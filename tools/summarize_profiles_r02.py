@@ -149,7 +149,7 @@ def main():
         r = subprocess.run([sys.executable, os.path.join(ROOT, "tools", "ncu_source_lines.py"), step_rep, obj, "_Z11k_adj_sweepILi1ELi1ELb1EEv12AdjSweepArgs", "0"],
                            capture_output=True, text=True)
         if r.returncode == 0:
-            note += ["", "The same samples by line of the kernel body (`python tools/ncu_source_lines.py`; `cont_adjacency.cu` as of the commit of this file: `adj_singles` /",
+            note += ["", "The same samples by line of the kernel body (`python tools/ncu_source_lines.py`; `cont_adjacency.cu` as of the captured build (name its commit here): `adj_singles` /",
                      "`adj_runs` calls = the streaming phase, `cluster_sync_all` = the batch's barrier, the `adj_apply` call in the column prologue = the links that are on,",
                      "the `adj_apply` call behind the decisions = flips):", ""] + r.stdout.strip().split("\n")
     txt = table("r02 ncu full capture -- the three kernels of the bench step (N=1, cfg4, hawkes data): log-likelihood through the cached structure (`k_adj_loglik`), parent sweep (`k_sweep_sparse<1,2>`), adjacency sweep (`k_adj_sweep`)",
